@@ -1,0 +1,292 @@
+/*
+ * spark_b200.h -- the C ABI of libsparkb200.so: a B200-native (sm_100a) implementation of
+ * Spark SQL's shuffle / sort / hash-aggregate / hash-join physical-execution hot path.
+ *
+ * The reference (apache/spark) has no FFI on this path: the operators are JVM
+ * classes.  Each entry point below therefore replaces the *body* of one reference operator's
+ * doExecute()/doExecuteColumnar() and is what a Scala `Gpu*Exec extends SparkPlan` calls through
+ * the JNI shim (scala/ + INTEGRATION.md); tests and bench.py bind the same symbols with ctypes.
+ * Citations are relative to the reference tree:
+ *   SQLX = sql/core/src/main/scala/org/apache/spark/sql/execution
+ *   CATJ = sql/catalyst/src/main/java/org/apache/spark/sql
+ *
+ * Conventions
+ *  - plain C types only; every call returns 0 (SB_OK) or an SB_ERR_* code, and
+ *    sb_last_error() returns the thread-local message (reference behaviour: operators throw,
+ *    the task fails, the scheduler retries -- the JNI shim turns non-zero into an exception).
+ *  - column buffers use the Arrow layout the reference exposes through ArrowColumnVector
+ *    (CATJ/vectorized/ArrowColumnVector.java:42-47): values buffer, validity BITMAP (LSB first,
+ *    NULL pointer = no nulls), int32 offsets for strings.  BOOL is one byte per value like
+ *    OffHeapColumnVector (sql/core/src/main/java/.../vectorized/OffHeapColumnVector.java:67-76).
+ *  - sb_table handles are device-resident (HBM), immutable and reference counted: the creator
+ *    owns one reference ("the executor that creates a ColumnarBatch is responsible for closing
+ *    it", SQLX/SparkPlan.scala:355-358 -> sb_table_release == ColumnarBatch.close()).
+ *  - no CPU fallback and no spill anywhere: an operator either runs on the GPU or fails.
+ */
+#ifndef SPARK_B200_H
+#define SPARK_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SB_ABI_VERSION 1
+
+/* ---- error codes ---------------------------------------------------------------------- */
+#define SB_OK 0
+#define SB_ERR_CUDA 1        /* CUDA runtime/driver error (message carries cudaGetErrorString) */
+#define SB_ERR_INVALID 2     /* bad argument / malformed plan */
+#define SB_ERR_OOM 3         /* HBM exhausted: hard error (reference analogue: aggregateOutOfMemoryError,
+                                SQLX/aggregate/HashAggregateExec.scala:998-1001) */
+#define SB_ERR_NCCL 4
+#define SB_ERR_UNSUPPORTED 5 /* type/operator combination not implemented on the GPU path */
+#define SB_ERR_NOT_INITIALIZED 6
+
+/* ---- physical column types (widths follow the reference's row->column converters,
+ *      SQLX/Columnar.scala:290-326, 444-457) --------------------------------------------- */
+#define SB_BOOL 1        /* 1 byte / value */
+#define SB_INT8 2
+#define SB_INT16 3
+#define SB_INT32 4
+#define SB_INT64 5
+#define SB_FLOAT32 6
+#define SB_FLOAT64 7
+#define SB_DATE32 8      /* days since epoch, int32 */
+#define SB_TIMESTAMP 9   /* microseconds, int64 */
+#define SB_DECIMAL64 10  /* precision <= 18: unscaled int64 + scale */
+#define SB_STRING 11     /* int32 offsets + byte arena */
+
+/* One column of a batch: the C image of a ColumnVector (CATJ/vectorized/ColumnVector.java:63-366). */
+typedef struct sb_column {
+  int32_t type;             /* SB_* */
+  int32_t scale;            /* decimal scale, else 0 */
+  int64_t length;           /* rows */
+  int64_t null_count;       /* -1 = unknown */
+  const void *data;         /* values; SB_STRING: byte arena */
+  const uint8_t *validity;  /* Arrow bitmap or NULL */
+  const int32_t *offsets;   /* SB_STRING only: length+1 entries */
+} sb_column;
+
+typedef struct sb_table sb_table;             /* ColumnarBatch resident in HBM */
+typedef struct sb_stream sb_stream;           /* one per Spark task thread (CUDA stream + scratch) */
+typedef struct sb_hash_table sb_hash_table;   /* HashedRelation resident in HBM */
+
+/* ---- lifecycle: ExecutorPlugin.init / shutdown (core/src/main/java/org/apache/spark/api/plugin/
+ *      ExecutorPlugin.java); the GPU ordinal comes from TaskContext.resources()("gpu") ------- */
+int sb_init(int32_t device_ordinal);
+int sb_shutdown(void);
+const char *sb_last_error(void);
+int32_t sb_abi_version(void);
+/* out[0]=SM count, out[1]=HBM bytes total, out[2]=HBM bytes free, out[3]=compute capability*10 */
+int sb_device_info(int64_t out[4]);
+/* number of kernels this library has launched since sb_init (for bench.py's gpu_launches) */
+int64_t sb_kernel_launch_count(void);
+
+/* per-kernel device timing: when enabled, the hot kernels are bracketed by CUDA events on the stream they
+ * are launched on; sb_profile_get returns the summed duration and launch count of one kernel by name
+ * (e.g. "agg_update", "partition_scatter", "join_probe") -- bench.py's roofline numbers come from here. */
+int sb_profile_enable(int32_t on);
+int sb_profile_reset(void);
+int sb_profile_get(const char *kernel_name, double *out_total_ms, int64_t *out_launches);
+
+/* pinned host buffers for columns that cross PCIe (the JVM side allocates its off-heap column
+ * buffers here so H2D/D2H copies are true DMA) */
+int sb_host_alloc(int64_t bytes, void **out);
+int sb_host_free(void *p);
+
+int sb_stream_create(sb_stream **out);
+int sb_stream_destroy(sb_stream *s);
+int sb_stream_synchronize(sb_stream *s);
+/* device-side timing on the stream the kernels are launched on (bench.py's roofline numbers) */
+int sb_stream_record_start(sb_stream *s);
+int sb_stream_record_stop(sb_stream *s);
+int sb_stream_elapsed_ms(sb_stream *s, float *out_ms);   /* synchronizes on the stop event */
+
+/* ---- tables: RowToColumnarExec / ColumnarToRowExec replacements (SQLX/Columnar.scala:503-546,
+ *      67-214) are host<->HBM copies of Arrow buffers ------------------------------------- */
+int sb_table_import_host(const sb_column *cols, int32_t ncols, sb_stream *s, sb_table **out);   /* H2D copy */
+int sb_table_import_device(const sb_column *cols, int32_t ncols, sb_table **out);              /* borrow device buffers */
+int sb_table_num_rows(const sb_table *t, int64_t *out);
+int sb_table_num_columns(const sb_table *t, int32_t *out);
+int sb_table_column(const sb_table *t, int32_t i, sb_column *out);   /* device pointers; string: data bytes = offsets[length] */
+int sb_table_string_bytes(const sb_table *t, int32_t i, int64_t *out);
+/* D2H copy of column i into caller buffers (validity/offsets may be NULL when not needed);
+ * out_null_count may be NULL */
+int sb_table_export_host(const sb_table *t, int32_t i, void *data, uint8_t *validity, int32_t *offsets,
+                         int64_t *out_null_count, sb_stream *s);
+int sb_table_retain(sb_table *t);
+int sb_table_release(sb_table *t);
+/* new table made of a subset / reordering of columns (shares buffers; ProjectExec of plain
+ * attribute references) */
+int sb_table_select(const sb_table *t, const int32_t *cols, int32_t ncols, sb_table **out);
+/* concatenates columns of two tables with equal row counts (shares buffers) */
+int sb_table_zip(const sb_table *a, const sb_table *b, sb_table **out);
+/* rows [begin, end) as a new table (copies) */
+int sb_table_slice(const sb_table *t, int64_t begin, int64_t end, sb_stream *s, sb_table **out);
+/* concatenation of tables with identical schemas (copies) */
+int sb_table_concat(const sb_table *const *tables, int32_t ntables, sb_stream *s, sb_table **out);
+
+/* ---- expressions: FilterExec / ProjectExec payload (SQLX/basicPhysicalOperators.scala:47, 245),
+ *      postfix programs over the input table's columns.  Null-propagating arithmetic and
+ *      comparisons, Kleene AND/OR, non-ANSI wrap-around integers, Divide -> NULL on zero,
+ *      double comparison with NaN == NaN and NaN largest (SQLOrderingUtil.compareDoubles). ---- */
+#define SB_OP_COL 1        /* push column `arg` */
+#define SB_OP_LIT_I64 2    /* push literal lit.i */
+#define SB_OP_LIT_F64 3    /* push literal lit.d */
+#define SB_OP_LIT_NULL 4
+#define SB_OP_ADD 10
+#define SB_OP_SUB 11
+#define SB_OP_MUL 12
+#define SB_OP_DIV 13       /* double division */
+#define SB_OP_NEG 14
+#define SB_OP_EQ 20
+#define SB_OP_NE 21
+#define SB_OP_LT 22
+#define SB_OP_LE 23
+#define SB_OP_GT 24
+#define SB_OP_GE 25
+#define SB_OP_AND 30
+#define SB_OP_OR 31
+#define SB_OP_NOT 32
+#define SB_OP_ISNULL 33
+#define SB_OP_ISNOTNULL 34
+#define SB_OP_CAST_F64 40
+#define SB_OP_CAST_I64 41
+#define SB_OP_CAST_I32 42
+
+/* value class of a node's result */
+#define SB_VT_BOOL 1
+#define SB_VT_I32 2   /* int8/int16/int32/date32 arithmetic wraps at 32 bits */
+#define SB_VT_I64 3
+#define SB_VT_F64 4
+
+typedef struct sb_expr_node {
+  int32_t op;       /* SB_OP_* */
+  int32_t vtype;    /* SB_VT_* of the result */
+  int32_t arg;      /* SB_OP_COL: column index */
+  int32_t pad;
+  union { int64_t i; double d; } lit;
+} sb_expr_node;
+
+typedef struct sb_expr {
+  const sb_expr_node *nodes;   /* postfix order */
+  int32_t n;
+  int32_t out_type;            /* SB_* type of the materialised result column */
+} sb_expr;
+
+/* FilterExec + ProjectExec in one pass: rows where `predicate` is TRUE survive (NULL drops the row);
+ * predicate may be NULL (no filter); each projection becomes one output column. */
+int sb_filter_project(const sb_table *in, const sb_expr *predicate, const sb_expr *projections, int32_t nproj,
+                      sb_stream *s, sb_table **out);
+
+/* ---- ShuffleExchangeExec, map side (SQLX/exchange/ShuffleExchangeExec.scala:359-619) ---------
+ * partition id = pmod(Murmur3Hash(keys, 42), n): bit-exact with HashPartitioning.partitionIdExpression
+ * (sql/catalyst/.../plans/physical/partitioning.scala:339-341; Murmur3_x86_32.java:47-150). */
+int sb_partition_ids(const sb_table *in, const int32_t *key_cols, int32_t nkeys, int32_t num_partitions,
+                     sb_stream *s, int32_t *out_ids_device);
+/* rows regrouped partition-contiguously, arrival order kept inside a partition (what the shuffle writers
+ * guarantee per map task); out_offsets_host[num_partitions+1] = partition boundaries. */
+int sb_hash_partition(const sb_table *in, const int32_t *key_cols, int32_t nkeys, int32_t num_partitions,
+                      sb_stream *s, sb_table **out, int64_t *out_offsets_host);
+/* RoundRobinPartitioning (ShuffleExchangeExec.scala:428-442): row i -> (start + 1 + i) mod n */
+int sb_round_robin_partition(const sb_table *in, int32_t start, int32_t num_partitions, sb_stream *s,
+                             sb_table **out, int64_t *out_offsets_host);
+
+/* ---- HashAggregateExec (SQLX/aggregate/HashAggregateExec.scala:50) with the child FilterExec /
+ *      ProjectExec fused in.  Buffer algebra: Sum.scala:113-178, Average.scala:80-135,
+ *      Count.scala:94-105, Min/Max. ---------------------------------------------------------- */
+#define SB_AGG_SUM 1
+#define SB_AGG_AVG 2
+#define SB_AGG_COUNT 3        /* count(expr): non-null rows */
+#define SB_AGG_COUNT_STAR 4
+#define SB_AGG_MIN 5
+#define SB_AGG_MAX 6
+
+#define SB_AGG_MODE_PARTIAL 1   /* input rows -> keys ++ buffers  (AggUtils.scala:131-208) */
+#define SB_AGG_MODE_FINAL 2     /* keys ++ buffers -> keys ++ results */
+#define SB_AGG_MODE_COMPLETE 3  /* input rows -> keys ++ results */
+
+typedef struct sb_agg_spec {
+  int32_t func;        /* SB_AGG_* */
+  int32_t pad;
+  sb_expr input;       /* Partial/Complete: value expression (ignored for COUNT_STAR).
+                          Final: ignored -- buffers are read positionally after the keys. */
+} sb_agg_spec;
+
+typedef struct sb_agg_plan {
+  int32_t mode;                /* SB_AGG_MODE_* */
+  int32_t nkeys;
+  const int32_t *key_cols;     /* grouping columns of the input table (fixed-width types) */
+  int32_t naggs;
+  int32_t pad;
+  const sb_agg_spec *aggs;
+  const sb_expr *filter;       /* fused FilterExec predicate or NULL */
+  int64_t expected_groups;     /* sizing hint (0 = unknown) */
+} sb_agg_plan;
+
+/* Output: key columns, then per aggregate either its buffer columns (Partial: sum -> [sum];
+ * avg -> [sum f64, count i64]; count -> [count]; min/max -> [value]) or its result column. */
+int sb_hash_aggregate(const sb_table *in, const sb_agg_plan *plan, sb_stream *s, sb_table **out);
+
+/* ---- SortExec (SQLX/SortExec.scala:39): stable sort of one partition.  Ordering and NULL
+ *      placement follow SortPrefix / PrefixComparators / UnsafeInMemorySorter
+ *      (SortOrder.scala:128-242, PrefixComparators.java:28-182, UnsafeInMemorySorter.java:241-262,
+ *      348-390) and RadixSort.java:178-259 for the single-column radix path. -------------------- */
+typedef struct sb_sort_order {
+  int32_t col;
+  int32_t ascending;     /* 1 = ASC */
+  int32_t nulls_first;   /* 1 = NULLS FIRST */
+  int32_t pad;
+} sb_sort_order;
+
+int sb_sort(const sb_table *in, const sb_sort_order *orders, int32_t norders, sb_stream *s, sb_table **out);
+/* the permutation only (int64 row indices, device buffer of in.num_rows entries) */
+int sb_sort_permutation(const sb_table *in, const sb_sort_order *orders, int32_t norders, sb_stream *s,
+                        int64_t *out_perm_device);
+/* TakeOrderedAndProjectExec (SQLX/limit.scala:310-411): first k rows of the sorted input */
+int sb_top_n(const sb_table *in, const sb_sort_order *orders, int32_t norders, int64_t k, sb_stream *s,
+             sb_table **out);
+
+/* ---- joins: BroadcastHashJoinExec / ShuffledHashJoinExec / SortMergeJoinExec replacement
+ *      (SQLX/joins/HashJoin.scala:184-400, HashedRelation.scala:136-168).  A row with any NULL key
+ *      never matches.  Output = probe(streamed) columns ++ build columns; semi/anti = probe only. ---- */
+#define SB_JOIN_INNER 0
+#define SB_JOIN_LEFT_OUTER 1   /* streamed side preserved */
+#define SB_JOIN_LEFT_SEMI 2
+#define SB_JOIN_LEFT_ANTI 3
+
+int sb_join_build(const sb_table *build, const int32_t *key_cols, int32_t nkeys, sb_stream *s, sb_hash_table **out);
+int sb_join_probe(const sb_hash_table *ht, const sb_table *probe, const int32_t *key_cols, int32_t nkeys,
+                  int32_t join_type, sb_stream *s, sb_table **out);
+int sb_hash_table_release(sb_hash_table *ht);
+
+/* ---- multi-GPU: one executor process per GPU; the exchange is an NCCL all-to-all over NVLink
+ *      instead of shuffle files + Netty fetch (core/.../shuffle/sort/SortShuffleManager.scala:70,
+ *      core/.../storage/ShuffleBlockFetcherIterator.scala). ------------------------------------ */
+#define SB_UNIQUE_ID_BYTES 128
+int sb_comm_get_unique_id(uint8_t out_id[SB_UNIQUE_ID_BYTES]);                 /* rank 0 (driver plugin) */
+int sb_comm_init(int32_t rank, int32_t nranks, const uint8_t id[SB_UNIQUE_ID_BYTES]);
+int sb_comm_destroy(void);
+int sb_comm_rank(int32_t *rank, int32_t *nranks);
+/* Ownership of reducer partitions: rank r owns the contiguous range [ceil(r*n/R), ceil((r+1)*n/R))
+ * (ShuffledRowRDD maps reducer partitions to tasks; which executor runs which task is the scheduler's choice).
+ * Host-only planner used by sb_all_to_all: fills the rows this rank sends to every destination.  No GPU needed. */
+int sb_exchange_plan(const int64_t *part_offsets, int32_t num_partitions, int32_t nranks,
+                     int64_t *out_send_rows /* nranks */);
+/* ShuffleExchangeExec, both sides: `in` is partition-contiguous (from sb_hash_partition) with
+ * part_offsets_host; every rank receives the partitions it owns from all ranks.  The received rows are
+ * grouped by SOURCE rank (fetch order is unspecified in the reference too), each source block being
+ * partition-contiguous; out_part_offsets_host[num_partitions+1] accumulates the received rows per
+ * partition id (only owned partitions are non-empty).  Collective: all ranks call it in the same order. */
+int sb_all_to_all(const sb_table *in, const int64_t *part_offsets_host, int32_t num_partitions, sb_stream *s,
+                  sb_table **out, int64_t *out_part_offsets_host);
+/* BroadcastExchangeExec (SQLX/exchange/BroadcastExchangeExec.scala:45-279): every rank gets the
+ * concatenation of all ranks' tables, in rank order. */
+int sb_all_gather(const sb_table *in, sb_stream *s, sb_table **out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPARK_B200_H */

@@ -1,0 +1,387 @@
+// primitives.cu -- exclusive scan, gather, compaction.
+#include "primitives.cuh"
+
+namespace sb {
+
+// ------------------------------------------------------------------------------------ scan
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+template <typename T>
+__device__ __forceinline__ T block_exclusive_scan(T v, T *smem_warp /* 32 */, T &block_total) {
+  // inclusive warp scan
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  T x = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    T y = __shfl_up_sync(0xffffffffu, x, d);
+    if (lane >= d) x += y;
+  }
+  if (lane == 31) smem_warp[warp] = x;
+  __syncthreads();
+  if (warp == 0) {
+    T w = lane < (blockDim.x >> 5) ? smem_warp[lane] : (T)0;
+    T s = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      T y = __shfl_up_sync(0xffffffffu, s, d);
+      if (lane >= d) s += y;
+    }
+    smem_warp[lane] = s - w;  // exclusive warp offsets; total = last inclusive
+    if (lane == 31) smem_warp[32] = s;
+  }
+  __syncthreads();
+  T res = smem_warp[warp] + x - v;
+  block_total = smem_warp[32];
+  return res;
+}
+
+template <typename Tin, typename Tout>
+__global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(const Tin *__restrict__ in, Tout *__restrict__ partials, int64_t n) {
+  __shared__ Tout sm[33];
+  int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+  Tout s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++)
+    if (base + k < n) s += (Tout)in[base + k];
+  Tout tot;
+  block_exclusive_scan<Tout>(s, sm, tot);
+  if (threadIdx.x == 0) partials[blockIdx.x] = tot;
+}
+
+template <typename Tin, typename Tout>
+__global__ void __launch_bounds__(SCAN_THREADS) scan_down_kernel(const Tin *in, Tout *out, const Tout *__restrict__ partials_excl,
+                                                                 int64_t n, Tout *total) {
+  __shared__ Tout sm[33];
+  int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+  Tout v[SCAN_ITEMS];
+  Tout s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) {
+    v[k] = base + k < n ? (Tout)in[base + k] : (Tout)0;
+    s += v[k];
+  }
+  Tout tot;
+  Tout ex = block_exclusive_scan<Tout>(s, sm, tot);
+  Tout off = (partials_excl ? partials_excl[blockIdx.x] : (Tout)0) + ex;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) {
+    if (base + k < n) out[base + k] = off;
+    off += v[k];
+  }
+  if (total && blockIdx.x == gridDim.x - 1 && threadIdx.x == SCAN_THREADS - 1) *total = off;
+}
+
+template <typename Tin, typename Tout>
+static void exclusive_scan_impl(const Tin *in, Tout *out, int64_t n, Tout *total_dev, cudaStream_t st) {
+  if (n <= 0) {
+    if (total_dev) SB_CUDA(cudaMemsetAsync(total_dev, 0, sizeof(Tout), st));
+    return;
+  }
+  int64_t nb = (n + SCAN_TILE - 1) / SCAN_TILE;
+  if (nb == 1) {
+    scan_down_kernel<Tin, Tout><<<1, SCAN_THREADS, 0, st>>>(in, out, nullptr, n, total_dev);
+    SB_LAUNCH_CHECK();
+    return;
+  }
+  Scratch partials(sizeof(Tout) * nb, st);
+  scan_reduce_kernel<Tin, Tout><<<(unsigned)nb, SCAN_THREADS, 0, st>>>(in, partials.as<Tout>(), n);
+  SB_LAUNCH_CHECK();
+  exclusive_scan_impl<Tout, Tout>(partials.as<Tout>(), partials.as<Tout>(), nb, nullptr, st);
+  scan_down_kernel<Tin, Tout><<<(unsigned)nb, SCAN_THREADS, 0, st>>>(in, out, partials.as<Tout>(), n, total_dev);
+  SB_LAUNCH_CHECK();
+}
+
+void exclusive_scan_i64(const int64_t *in, int64_t *out, int64_t n, int64_t *total_dev, cudaStream_t st) {
+  exclusive_scan_impl<int64_t, int64_t>(in, out, n, total_dev, st);
+}
+void exclusive_scan_i32(const int32_t *in, int32_t *out, int64_t n, int32_t *total_dev, cudaStream_t st) {
+  exclusive_scan_impl<int32_t, int32_t>(in, out, n, total_dev, st);
+}
+void exclusive_scan_i32_to_i64(const int32_t *in, int64_t *out, int64_t n, int64_t *total_dev, cudaStream_t st) {
+  exclusive_scan_impl<int32_t, int64_t>(in, out, n, total_dev, st);
+}
+
+// ------------------------------------------------------------------------------------ gather
+constexpr int GATHER_MAX_COLS = 12;
+struct GatherArgs {
+  int ncols;
+  int width[GATHER_MAX_COLS];
+  const void *src[GATHER_MAX_COLS];
+  void *dst[GATHER_MAX_COLS];
+  const uint8_t *src_valid[GATHER_MAX_COLS];
+  uint32_t *dst_valid[GATHER_MAX_COLS];   // null -> no validity output
+};
+
+__global__ void __launch_bounds__(256) gather_fixed_kernel(GatherArgs a, const int64_t *__restrict__ idx, int64_t nout) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool in_range = i < nout;
+  int64_t j = in_range ? idx[i] : -1;
+  bool has = j >= 0;
+#pragma unroll 1
+  for (int c = 0; c < a.ncols; c++) {
+    if (has) {
+      switch (a.width[c]) {
+        case 1: ((uint8_t *)a.dst[c])[i] = ((const uint8_t *)a.src[c])[j]; break;
+        case 2: ((uint16_t *)a.dst[c])[i] = ((const uint16_t *)a.src[c])[j]; break;
+        case 4: ((uint32_t *)a.dst[c])[i] = ((const uint32_t *)a.src[c])[j]; break;
+        default: ((uint64_t *)a.dst[c])[i] = ((const uint64_t *)a.src[c])[j]; break;
+      }
+    } else if (in_range) {
+      switch (a.width[c]) {
+        case 1: ((uint8_t *)a.dst[c])[i] = 0; break;
+        case 2: ((uint16_t *)a.dst[c])[i] = 0; break;
+        case 4: ((uint32_t *)a.dst[c])[i] = 0; break;
+        default: ((uint64_t *)a.dst[c])[i] = 0; break;
+      }
+    }
+    if (a.dst_valid[c]) {
+      bool v = has && bit_valid(a.src_valid[c], j);
+      uint32_t word = __ballot_sync(0xffffffffu, v);
+      if ((threadIdx.x & 31) == 0 && (i - (i & 31)) < nout) a.dst_valid[c][i >> 5] = word;
+    }
+  }
+}
+
+// strings: lengths -> scan -> byte copy (one warp per row)
+__global__ void gather_str_len_kernel(const int32_t *__restrict__ src_off, const int64_t *__restrict__ idx, int64_t nout,
+                                      int32_t *__restrict__ out_len) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nout) return;
+  int64_t j = idx[i];
+  out_len[i] = j >= 0 ? src_off[j + 1] - src_off[j] : 0;
+}
+__global__ void gather_str_copy_kernel(const uint8_t *__restrict__ src, const int32_t *__restrict__ src_off,
+                                       const int64_t *__restrict__ idx, int64_t nout, const int32_t *__restrict__ dst_off,
+                                       uint8_t *__restrict__ dst) {
+  int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (w >= nout) return;
+  int64_t j = idx[w];
+  if (j < 0) return;
+  int32_t so = src_off[j], len = src_off[j + 1] - so, d = dst_off[w];
+  for (int k = lane; k < len; k += 32) dst[d + k] = src[so + k];
+}
+
+static Column gather_string(const Column &c, const int64_t *idx, int64_t nout, bool neg, cudaStream_t st) {
+  Column r;
+  r.type = c.type;
+  r.length = nout;
+  r.offsets = buffer_alloc((nout + 1) * 4 + 16, st);
+  int32_t *off = (int32_t *)r.offsets->ptr;
+  Scratch total(8, st);
+  if (nout > 0) {
+    gather_str_len_kernel<<<(unsigned)((nout + 255) / 256), 256, 0, st>>>(c.o(), idx, nout, off);
+    SB_LAUNCH_CHECK();
+  }
+  // scan over nout lengths, writing nout+1 offsets: scan in place then append the total
+  exclusive_scan_i32(off, off, nout, total.as<int32_t>(), st);
+  SB_CUDA(cudaMemcpyAsync(off + nout, total.ptr, 4, cudaMemcpyDeviceToDevice, st));
+  int32_t bytes = 0;
+  SB_CUDA(cudaMemcpyAsync(&bytes, total.ptr, 4, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaStreamSynchronize(st));
+  r.string_bytes = bytes;
+  r.data = buffer_alloc(bytes + 16, st);
+  if (nout > 0 && bytes > 0) {
+    gather_str_copy_kernel<<<(unsigned)((nout * 32 + 255) / 256), 256, 0, st>>>((const uint8_t *)c.d(), c.o(), idx, nout, off,
+                                                                               (uint8_t *)r.data->ptr);
+    SB_LAUNCH_CHECK();
+  }
+  if (c.validity || neg) {
+    r.validity = buffer_alloc(bitmap_alloc_bytes(nout), st);
+    r.null_count = -1;
+    GatherArgs a;
+    a.ncols = 1;
+    a.width[0] = 0;   // validity only: width 0 hits the default store... avoid: handled below
+    a.src[0] = nullptr;
+    a.dst[0] = nullptr;
+    a.src_valid[0] = c.v();
+    a.dst_valid[0] = (uint32_t *)r.validity->ptr;
+    // reuse the fixed kernel with a dummy 1-byte column
+    Scratch dummy_src(16, st), dummy_dst(nout + 16, st);
+    (void)dummy_src;
+    a.width[0] = 1;
+    a.dst[0] = dummy_dst.ptr;
+    a.src[0] = c.d();
+    if (nout > 0) {
+      // src[j] read of 1 byte must be in-bounds: use the offsets buffer (>= 4*(n+1) bytes) instead
+      a.src[0] = c.o();
+      gather_fixed_kernel<<<(unsigned)((nout + 255) / 256), 256, 0, st>>>(a, idx, nout);
+      SB_LAUNCH_CHECK();
+    }
+  }
+  return r;
+}
+
+Column gather_column(const Column &c, const int64_t *idx, int64_t nout, bool neg, cudaStream_t st) {
+  if (c.type == SB_STRING) return gather_string(c, idx, nout, neg, st);
+  Column r = column_alloc(c.type, c.scale, nout, c.validity != nullptr || neg, st);
+  if (nout == 0) return r;
+  GatherArgs a;
+  a.ncols = 1;
+  a.width[0] = type_width(c.type);
+  a.src[0] = c.d();
+  a.dst[0] = r.data->ptr;
+  a.src_valid[0] = c.v();
+  a.dst_valid[0] = r.validity ? (uint32_t *)r.validity->ptr : nullptr;
+  gather_fixed_kernel<<<(unsigned)((nout + 255) / 256), 256, 0, st>>>(a, idx, nout);
+  SB_LAUNCH_CHECK();
+  return r;
+}
+
+sb_table *gather_table(const sb_table *in, const int64_t *idx, int64_t nout, bool neg, cudaStream_t st) {
+  sb_table *t = table_new(nout);
+  try {
+    t->cols.resize(in->cols.size());
+    GatherArgs a;
+    a.ncols = 0;
+    auto flush = [&]() {
+      if (a.ncols && nout > 0) {
+        gather_fixed_kernel<<<(unsigned)((nout + 255) / 256), 256, 0, st>>>(a, idx, nout);
+        SB_LAUNCH_CHECK();
+      }
+      a.ncols = 0;
+    };
+    for (size_t i = 0; i < in->cols.size(); i++) {
+      const Column &c = in->cols[i];
+      if (c.type == SB_STRING) {
+        t->cols[i] = gather_string(c, idx, nout, neg, st);
+        continue;
+      }
+      Column r = column_alloc(c.type, c.scale, nout, c.validity != nullptr || neg, st);
+      t->cols[i] = r;
+      int k = a.ncols++;
+      a.width[k] = type_width(c.type);
+      a.src[k] = c.d();
+      a.dst[k] = r.data->ptr;
+      a.src_valid[k] = c.v();
+      a.dst_valid[k] = r.validity ? (uint32_t *)r.validity->ptr : nullptr;
+      if (a.ncols == GATHER_MAX_COLS) flush();
+    }
+    flush();
+  } catch (...) {
+    table_free(t);
+    throw;
+  }
+  return t;
+}
+
+// ------------------------------------------------------------------------------------ compaction
+__global__ void mask_to_i32_kernel(const uint8_t *__restrict__ mask, int64_t n, int32_t *__restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = mask[i] ? 1 : 0;
+}
+__global__ void compact_write_kernel(const uint8_t *__restrict__ mask, const int64_t *__restrict__ pos, int64_t n,
+                                     int64_t *__restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && mask[i]) out[pos[i]] = i;
+}
+
+int64_t compact_mask(const uint8_t *mask, int64_t n, int64_t *out_idx, cudaStream_t st) {
+  if (n == 0) return 0;
+  Scratch flags(n * 4, st), pos(n * 8, st), total(8, st);
+  unsigned nb = (unsigned)((n + 255) / 256);
+  mask_to_i32_kernel<<<nb, 256, 0, st>>>(mask, n, flags.as<int32_t>());
+  SB_LAUNCH_CHECK();
+  exclusive_scan_i32_to_i64(flags.as<int32_t>(), pos.as<int64_t>(), n, total.as<int64_t>(), st);
+  compact_write_kernel<<<nb, 256, 0, st>>>(mask, pos.as<int64_t>(), n, out_idx);
+  SB_LAUNCH_CHECK();
+  int64_t cnt = 0;
+  SB_CUDA(cudaMemcpyAsync(&cnt, total.ptr, 8, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaStreamSynchronize(st));
+  return cnt;
+}
+
+__global__ void iota_kernel(int64_t *out, int64_t n, int64_t begin) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = begin + i;
+}
+void iota_i64(int64_t *out, int64_t n, int64_t begin, cudaStream_t st) {
+  if (n <= 0) return;
+  iota_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(out, n, begin);
+  SB_LAUNCH_CHECK();
+}
+
+}  // namespace sb
+
+using namespace sb;
+
+extern "C" {
+
+int sb_table_slice(const sb_table *t, int64_t begin, int64_t end, sb_stream *s, sb_table **out) {
+  SB_API_BEGIN
+  require_init();
+  SB_REQUIRE(t && out && begin >= 0 && end >= begin && end <= t->nrows, "slice [%lld,%lld) out of range", (long long)begin,
+             (long long)end);
+  cudaStream_t st = stream_of(s);
+  int64_t n = end - begin;
+  Scratch idx(n * 8 + 8, st);
+  iota_i64(idx.as<int64_t>(), n, begin, st);
+  *out = gather_table(t, idx.as<int64_t>(), n, false, st);
+  SB_API_END
+}
+
+int sb_table_concat(const sb_table *const *tables, int32_t ntables, sb_stream *s, sb_table **out) {
+  SB_API_BEGIN
+  require_init();
+  SB_REQUIRE(tables && ntables >= 1 && out, "concat needs at least one table");
+  cudaStream_t st = stream_of(s);
+  const sb_table *first = tables[0];
+  int64_t total = 0;
+  for (int i = 0; i < ntables; i++) {
+    SB_REQUIRE(tables[i]->cols.size() == first->cols.size(), "concat: schema mismatch");
+    total += tables[i]->nrows;
+  }
+  sb_table *r = table_new(total);
+  try {
+    for (size_t c = 0; c < first->cols.size(); c++) {
+      int32_t type = first->cols[c].type;
+      if (type == SB_STRING) fail(SB_ERR_UNSUPPORTED, "concat of string columns is not implemented");
+      bool any_valid = false;
+      for (int i = 0; i < ntables; i++) {
+        SB_REQUIRE(tables[i]->cols[c].type == type, "concat: column %zu type mismatch", c);
+        any_valid |= tables[i]->cols[c].validity != nullptr;
+      }
+      int w = type_width(type);
+      Column col = column_alloc(type, first->cols[c].scale, total, false, st);
+      int64_t off = 0;
+      for (int i = 0; i < ntables; i++) {
+        int64_t n = tables[i]->nrows;
+        if (n) SB_CUDA(cudaMemcpyAsync((char *)col.data->ptr + off * w, tables[i]->cols[c].d(), (size_t)(n * w),
+                                       cudaMemcpyDeviceToDevice, st));
+        off += n;
+      }
+      r->cols.push_back(col);
+      if (any_valid) {
+        // validity: rebuild through a gather of each piece's bits (pieces start at arbitrary bit offsets)
+        Column &rc = r->cols.back();
+        rc.validity = buffer_alloc(bitmap_alloc_bytes(total), st);
+        rc.null_count = -1;
+        SB_CUDA(cudaMemsetAsync(rc.validity->ptr, 0xff, (size_t)bitmap_alloc_bytes(total), st));
+        std::vector<uint8_t> host((size_t)bitmap_bytes(total) + 8, 0xff);
+        int64_t o = 0;
+        for (int i = 0; i < ntables; i++) {
+          int64_t n = tables[i]->nrows;
+          if (tables[i]->cols[c].validity && n) {
+            std::vector<uint8_t> piece((size_t)bitmap_bytes(n));
+            SB_CUDA(cudaMemcpyAsync(piece.data(), tables[i]->cols[c].v(), piece.size(), cudaMemcpyDeviceToHost, st));
+            SB_CUDA(cudaStreamSynchronize(st));
+            for (int64_t k = 0; k < n; k++)
+              if (!((piece[k >> 3] >> (k & 7)) & 1)) host[(o + k) >> 3] &= ~(1u << ((o + k) & 7));
+          }
+          o += n;
+        }
+        SB_CUDA(cudaMemcpyAsync(rc.validity->ptr, host.data(), (size_t)bitmap_bytes(total), cudaMemcpyHostToDevice, st));
+        SB_CUDA(cudaStreamSynchronize(st));
+      }
+    }
+  } catch (...) {
+    table_free(r);
+    throw;
+  }
+  *out = r;
+  SB_API_END
+}
+
+}  // extern "C"

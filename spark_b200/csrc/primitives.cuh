@@ -1,0 +1,26 @@
+// primitives.cuh -- device-wide building blocks shared by the operators: exclusive scan,
+// row gather (take) with validity, mask compaction.
+#pragma once
+#include "common.cuh"
+
+namespace sb {
+
+// out[i] = sum_{j<i} in[j]; total (if non-null, device pointer) = sum of all.  in may alias out.
+void exclusive_scan_i64(const int64_t *in, int64_t *out, int64_t n, int64_t *total_dev, cudaStream_t st);
+void exclusive_scan_i32(const int32_t *in, int32_t *out, int64_t n, int32_t *total_dev, cudaStream_t st);
+// widening scan: int32 counts -> int64 offsets
+void exclusive_scan_i32_to_i64(const int32_t *in, int64_t *out, int64_t n, int64_t *total_dev, cudaStream_t st);
+
+// Gather rows of every column of `in` at positions idx[0..nout) (idx < 0 -> NULL row, used for
+// outer-join padding).  Result columns carry validity when the source has it or idx may be negative.
+sb_table *gather_table(const sb_table *in, const int64_t *idx_dev, int64_t nout, bool idx_may_be_negative,
+                       cudaStream_t st);
+Column gather_column(const Column &c, const int64_t *idx_dev, int64_t nout, bool idx_may_be_negative, cudaStream_t st);
+
+// indices of rows whose mask byte is non-zero, in row order; returns count (synchronizes the stream)
+int64_t compact_mask(const uint8_t *mask_dev, int64_t n, int64_t *out_idx_dev, cudaStream_t st);
+
+// fills idx[i] = begin + i
+void iota_i64(int64_t *out, int64_t n, int64_t begin, cudaStream_t st);
+
+}  // namespace sb

@@ -1,0 +1,370 @@
+// sort.cu -- SortExec / TakeOrderedAndProjectExec on the GPU: stable LSD radix sort, no spill.
+//
+// Reference path replaced (citations relative to the reference tree):
+//   SQLX/SortExec.scala:39 (createSorter :75-107: radix only for ONE sort column of a prefix-sortable type),
+//   SortPrefix (sql/catalyst/.../expressions/SortOrder.scala:128-242), PrefixComparators.java:28-182
+//   (double prefix: sign-flip, -0.0 -> 0.0, NaN canonical and largest), UnsafeInMemorySorter.java:241-262
+//   (NULL-prefix records are parked at the front by swapping the first non-null record to the end) and
+//   :348-390 (NULL block emitted first/last per nullsFirst, independent of ASC/DESC),
+//   RadixSort.sortKeyPrefixArray (RadixSort.java:178-259: LSD, 8-bit digits, bytes equal in all records are
+//   skipped, signed top byte, DESC = reversed bucket walk keeping in-bucket insertion order),
+//   TimSort + RowOrdering for everything else (stable), TakeOrderedAndProjectExec SQLX/limit.scala:347-386.
+//
+// GPU design: every sort column is turned into an order-preserving unsigned 64-bit key (signed -> flip the sign
+// bit, double -> PrefixComparators transform, DESC -> bitwise complement), so one ascending stable LSD pass
+// implementation covers all four (ASC|DESC) x (NULLS FIRST|LAST) orders with the reference's tie order.
+// Each 8-bit pass = digit histogram kernel + the stable multisplit of partition.cu over (key, row id) pairs;
+// constant bytes are skipped like the reference does.  Multi-column orders run column by column from the
+// last to the first (stable passes compose into the lexicographic order TimSort + RowOrdering produces).
+// Payload columns are gathered once at the end.
+#include "common.cuh"
+#include "multisplit.cuh"
+#include "primitives.cuh"
+
+namespace sb {
+
+constexpr int SORT_THREADS = 256;
+
+// order-preserving key of row `row` of a column for an ascending unsigned sort
+__device__ __forceinline__ uint64_t sort_key(const void *data, int32_t type, int64_t row, bool desc) {
+  uint64_t k;
+  switch (type) {
+    case SB_FLOAT32: case SB_FLOAT64: {   // DoublePrefixComparator.computePrefix
+      double v = type == SB_FLOAT32 ? (double)((const float *)data)[row] : ((const double *)data)[row];
+      if (v == 0.0) v = 0.0;
+      int64_t b = double_bits_canonical(v);
+      k = (uint64_t)b ^ ((uint64_t)(b >> 63) | 0x8000000000000000ull);
+      break;
+    }
+    case SB_BOOL: k = ((const uint8_t *)data)[row] ? 1 : 0; k ^= 0x8000000000000000ull; break;
+    default: k = (uint64_t)load_i64(data, type, row) ^ 0x8000000000000000ull; break;   // signed -> unsigned order
+  }
+  return desc ? ~k : k;
+}
+
+// keys[i] = key of row rows[i] (rows == nullptr -> identity); isnull[i] optional
+__global__ void __launch_bounds__(SORT_THREADS) make_keys_kernel(const void *data, const uint8_t *valid, int32_t type, int desc,
+                                                                 const uint32_t *__restrict__ rows, int64_t n,
+                                                                 uint64_t *__restrict__ keys, uint8_t *__restrict__ isnull) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int64_t r = rows ? rows[i] : i;
+  bool v = bit_valid(valid, r);
+  keys[i] = v ? sort_key(data, type, r, desc != 0) : 0;
+  if (isnull) isnull[i] = !v;
+}
+
+// one read pass: the eight 256-bin digit histograms (to know which bytes vary, RadixSort.java:213-236)
+__global__ void __launch_bounds__(SORT_THREADS) digit_counts_kernel(const uint64_t *__restrict__ keys, int64_t n,
+                                                                    unsigned long long *__restrict__ counts /* [8][256] */) {
+  __shared__ uint32_t sh[8 * 256];
+  for (int i = threadIdx.x; i < 8 * 256; i += SORT_THREADS) sh[i] = 0;
+  __syncthreads();
+  for (int64_t i = (int64_t)blockIdx.x * SORT_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * SORT_THREADS) {
+    uint64_t k = keys[i];
+#pragma unroll
+    for (int b = 0; b < 8; b++) atomicAdd(&sh[b * 256 + ((k >> (8 * b)) & 0xff)], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 8 * 256; i += SORT_THREADS)
+    if (sh[i]) atomicAdd(&counts[i], (unsigned long long)sh[i]);
+}
+
+// bucket id = digit `byte` of the key, plus the per-block histogram in the layout multisplit_scatter expects
+__global__ void __launch_bounds__(SORT_THREADS) digit_hist_kernel(const uint64_t *__restrict__ keys, int64_t n, int byte,
+                                                                  int64_t chunk, int32_t *__restrict__ bucket,
+                                                                  uint32_t *__restrict__ hist) {
+  __shared__ uint32_t sh[256];
+  sh[threadIdx.x] = 0;
+  __syncthreads();
+  int64_t begin = (int64_t)blockIdx.x * chunk;
+  int64_t end = begin + chunk < n ? begin + chunk : n;
+  for (int64_t i = begin + threadIdx.x; i < end; i += SORT_THREADS) {
+    int d = (int)((keys[i] >> (8 * byte)) & 0xff);
+    bucket[i] = d;
+    atomicAdd(&sh[d], 1u);
+  }
+  __syncthreads();
+  hist[(int64_t)threadIdx.x * gridDim.x + blockIdx.x] = sh[threadIdx.x];
+}
+
+// 1-bit stable split used for NULL placement in multi-column orders
+__global__ void __launch_bounds__(SORT_THREADS) flag_hist_kernel(const uint8_t *__restrict__ flag, int invert, int64_t n,
+                                                                 int64_t chunk, int32_t *__restrict__ bucket,
+                                                                 uint32_t *__restrict__ hist) {
+  __shared__ uint32_t sh[2];
+  if (threadIdx.x < 2) sh[threadIdx.x] = 0;
+  __syncthreads();
+  int64_t begin = (int64_t)blockIdx.x * chunk;
+  int64_t end = begin + chunk < n ? begin + chunk : n;
+  for (int64_t i = begin + threadIdx.x; i < end; i += SORT_THREADS) {
+    int d = (flag[i] != 0) ^ invert;
+    bucket[i] = d;
+    atomicAdd(&sh[d], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < 2) hist[(int64_t)threadIdx.x * gridDim.x + blockIdx.x] = sh[threadIdx.x];
+}
+
+// Stable ascending LSD radix sort of (keys, vals) in place (ping-pong buffers inside).  Returns passes run.
+static int radix_sort_pairs(uint64_t *keys, uint32_t *vals, int64_t n, cudaStream_t st) {
+  if (n <= 1) return 0;
+  Scratch counts(8 * 256 * 8, st);
+  SB_CUDA(cudaMemsetAsync(counts.ptr, 0, 8 * 256 * 8, st));
+  int grid = grid_for(n, SORT_THREADS * 8, rt().num_sms * 8);
+  digit_counts_kernel<<<grid, SORT_THREADS, 0, st>>>(keys, n, counts.as<unsigned long long>());
+  SB_LAUNCH_CHECK();
+  std::vector<unsigned long long> h(8 * 256);
+  SB_CUDA(cudaMemcpyAsync(h.data(), counts.ptr, 8 * 256 * 8, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaStreamSynchronize(st));
+  bool varies[8];
+  for (int b = 0; b < 8; b++) {
+    varies[b] = true;
+    for (int d = 0; d < 256; d++)
+      if (h[b * 256 + d] == (unsigned long long)n) varies[b] = false;   // every record shares this byte: skip the pass
+  }
+  PartGeometry g = part_geometry(n);
+  Scratch keys2(n * 8 + 16, st), vals2(n * 4 + 16, st), bucket(n * 4 + 16, st), hist((int64_t)256 * g.nblocks * 4 + 16, st);
+  uint64_t *ik = keys, *ok = keys2.as<uint64_t>();
+  uint32_t *iv = vals, *ov = vals2.as<uint32_t>();
+  int passes = 0;
+  for (int b = 0; b < 8; b++) {
+    if (!varies[b]) continue;
+    digit_hist_kernel<<<g.nblocks, SORT_THREADS, 0, st>>>(ik, n, b, g.chunk, bucket.as<int32_t>(), hist.as<uint32_t>());
+    SB_LAUNCH_CHECK();
+    SplitCol cols[2] = {{8, ik, ok, nullptr, nullptr}, {4, iv, ov, nullptr, nullptr}};
+    multisplit_scatter(bucket.as<int32_t>(), hist.as<uint32_t>(), 256, g, cols, 2, n, nullptr, nullptr, st);
+    std::swap(ik, ok);
+    std::swap(iv, ov);
+    passes++;
+  }
+  if (ik != keys) {
+    SB_CUDA(cudaMemcpyAsync(keys, ik, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
+    SB_CUDA(cudaMemcpyAsync(vals, iv, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  SB_CUDA(cudaStreamSynchronize(st));   // scratch buffers die here
+  return passes;
+}
+
+// stable split of vals by a 0/1 flag (flag[i] belongs to vals[i]): zeros first unless invert
+static void stable_split_by_flag(const uint8_t *flag, int invert, uint32_t *vals, int64_t n, cudaStream_t st) {
+  if (n <= 1) return;
+  PartGeometry g = part_geometry(n);
+  Scratch vals2(n * 4 + 16, st), bucket(n * 4 + 16, st), hist((int64_t)2 * g.nblocks * 4 + 16, st);
+  flag_hist_kernel<<<g.nblocks, SORT_THREADS, 0, st>>>(flag, invert, n, g.chunk, bucket.as<int32_t>(), hist.as<uint32_t>());
+  SB_LAUNCH_CHECK();
+  SplitCol col = {4, vals, vals2.ptr, nullptr, nullptr};
+  multisplit_scatter(bucket.as<int32_t>(), hist.as<uint32_t>(), 2, g, &col, 1, n, nullptr, nullptr, st);
+  SB_CUDA(cudaMemcpyAsync(vals, vals2.ptr, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+  SB_CUDA(cudaStreamSynchronize(st));
+}
+
+// ---- UnsafeInMemorySorter.insertRecord replay (radix path with NULLs) ----------------------------------
+// Rows from the first non-null row f on form a "tape": a non-null row appends itself, a NULL row re-appends
+// the record at the head of the queue (tape[k] for the k-th such NULL).  After all inserts the non-null
+// records sit in tape[r .. r+m) (r = NULLs after f, m = non-null count).  ptr[j] starts as j (push) or k
+// (copy of tape[k]) and is resolved by pointer jumping.
+__global__ void tape_init_kernel(const uint8_t *__restrict__ isnull, const int64_t *__restrict__ nulls_before, int64_t f,
+                                 int64_t len, uint32_t *__restrict__ ptr) {
+  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= len) return;
+  int64_t row = f + j;
+  ptr[j] = isnull[row] ? (uint32_t)(nulls_before[row] - f) : (uint32_t)j;
+}
+__global__ void tape_jump_kernel(uint32_t *ptr, int64_t len, int *changed) {
+  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= len) return;
+  uint32_t p = ptr[j];
+  uint32_t q = ptr[p];
+  if (q != p) {
+    ptr[j] = q;
+    *changed = 1;
+  }
+}
+__global__ void tape_finish_kernel(const uint32_t *__restrict__ ptr, int64_t f, int64_t r, int64_t m, uint32_t *__restrict__ order) {
+  int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < m) order[q] = (uint32_t)(f + ptr[r + q]);
+}
+__global__ void u8_to_i32_kernel(const uint8_t *__restrict__ in, int64_t n, int32_t *__restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i] ? 1 : 0;
+}
+__global__ void iota_u32_kernel(uint32_t *out, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (uint32_t)i;
+}
+__global__ void null_rows_kernel(const uint8_t *__restrict__ isnull, const int64_t *__restrict__ nulls_before, int64_t n,
+                                 uint32_t *__restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && isnull[i]) out[nulls_before[i]] = (uint32_t)i;
+}
+__global__ void u32_to_i64_kernel(const uint32_t *__restrict__ in, int64_t n, int64_t *__restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i];
+}
+
+static inline unsigned nblk(int64_t n) { return (unsigned)((n + 255) / 256); }
+
+static bool radix_eligible(int32_t type) { return type != SB_STRING; }
+
+// writes the sorted permutation (uint32 row ids) into perm (n entries)
+static void sort_permutation_impl(const sb_table *in, const sb_sort_order *orders, int32_t norders, uint32_t *perm, cudaStream_t st) {
+  const int64_t n = in->nrows;
+  SB_REQUIRE(n < (1ll << 32), "tables of 2^32 rows or more must be sorted in chunks");
+  SB_REQUIRE(norders >= 1 && orders, "sort needs at least one order");
+  for (int k = 0; k < norders; k++) {
+    SB_REQUIRE(orders[k].col >= 0 && orders[k].col < (int)in->cols.size(), "sort column %d out of range", orders[k].col);
+    if (!radix_eligible(in->cols[orders[k].col].type))
+      fail(SB_ERR_UNSUPPORTED, "sorting on string columns is not implemented (dictionary-encode them)");
+  }
+  if (n == 0) return;
+  if (norders == 1) {
+    // ---- the reference's radix path --------------------------------------------------------------
+    const Column &c = in->cols[orders[0].col];
+    const bool desc = !orders[0].ascending, nulls_first = orders[0].nulls_first != 0;
+    Scratch keys(n * 8 + 16, st);
+    if (!c.validity) {
+      iota_u32_kernel<<<nblk(n), 256, 0, st>>>(perm, n);
+      SB_LAUNCH_CHECK();
+      make_keys_kernel<<<nblk(n), SORT_THREADS, 0, st>>>(c.d(), nullptr, c.type, desc, nullptr, n, keys.as<uint64_t>(), nullptr);
+      SB_LAUNCH_CHECK();
+      radix_sort_pairs(keys.as<uint64_t>(), perm, n, st);
+      return;
+    }
+    Scratch isnull(n + 16, st), flags(n * 4 + 16, st), nulls_before(n * 8 + 16, st), total(8, st);
+    make_keys_kernel<<<nblk(n), SORT_THREADS, 0, st>>>(c.d(), c.v(), c.type, desc, nullptr, n, keys.as<uint64_t>(), isnull.as<uint8_t>());
+    SB_LAUNCH_CHECK();
+    u8_to_i32_kernel<<<nblk(n), 256, 0, st>>>(isnull.as<uint8_t>(), n, flags.as<int32_t>());
+    SB_LAUNCH_CHECK();
+    exclusive_scan_i32_to_i64(flags.as<int32_t>(), nulls_before.as<int64_t>(), n, total.as<int64_t>(), st);
+    int64_t nnull = 0;
+    SB_CUDA(cudaMemcpyAsync(&nnull, total.ptr, 8, cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaStreamSynchronize(st));
+    const int64_t m = n - nnull;
+    uint32_t *null_part = nulls_first ? perm : perm + m;
+    uint32_t *sorted_part = nulls_first ? perm + nnull : perm;
+    if (nnull > 0) {   // NULL block keeps arrival order
+      null_rows_kernel<<<nblk(n), 256, 0, st>>>(isnull.as<uint8_t>(), nulls_before.as<int64_t>(), n, null_part);
+      SB_LAUNCH_CHECK();
+    }
+    if (m == 0) return;
+    if (nnull == 0) {
+      iota_u32_kernel<<<nblk(n), 256, 0, st>>>(sorted_part, n);
+      SB_LAUNCH_CHECK();
+      radix_sort_pairs(keys.as<uint64_t>(), sorted_part, n, st);
+      return;
+    }
+    // first non-null row f: found on the host from the null prefix counts (nulls_before[i] == i up to f)
+    // -> f = number of leading NULL rows; binary search over the monotone predicate nulls_before[i] == i
+    int64_t f;
+    {
+      int64_t lo = 0, hi = n;   // invariant: rows < lo are leading NULLs
+      while (lo < hi) {
+        int64_t mid = (lo + hi) / 2, nb = 0;
+        uint8_t isn = 0;
+        SB_CUDA(cudaMemcpyAsync(&nb, nulls_before.as<int64_t>() + mid, 8, cudaMemcpyDeviceToHost, st));
+        SB_CUDA(cudaMemcpyAsync(&isn, isnull.as<uint8_t>() + mid, 1, cudaMemcpyDeviceToHost, st));
+        SB_CUDA(cudaStreamSynchronize(st));
+        if (nb == mid && isn) lo = mid + 1; else hi = mid;
+      }
+      f = lo;
+    }
+    const int64_t len = n - f, r = nnull - f;
+    Scratch ptr(len * 4 + 16, st), changed(4, st);
+    tape_init_kernel<<<nblk(len), 256, 0, st>>>(isnull.as<uint8_t>(), nulls_before.as<int64_t>(), f, len, ptr.as<uint32_t>());
+    SB_LAUNCH_CHECK();
+    for (;;) {
+      SB_CUDA(cudaMemsetAsync(changed.ptr, 0, 4, st));
+      tape_jump_kernel<<<nblk(len), 256, 0, st>>>(ptr.as<uint32_t>(), len, changed.as<int>());
+      SB_LAUNCH_CHECK();
+      int ch = 0;
+      SB_CUDA(cudaMemcpyAsync(&ch, changed.ptr, 4, cudaMemcpyDeviceToHost, st));
+      SB_CUDA(cudaStreamSynchronize(st));
+      if (!ch) break;
+    }
+    tape_finish_kernel<<<nblk(m), 256, 0, st>>>(ptr.as<uint32_t>(), f, r, m, sorted_part);
+    SB_LAUNCH_CHECK();
+    Scratch keys_nn(m * 8 + 16, st);
+    make_keys_kernel<<<nblk(m), SORT_THREADS, 0, st>>>(c.d(), nullptr, c.type, desc, sorted_part, m, keys_nn.as<uint64_t>(), nullptr);
+    SB_LAUNCH_CHECK();
+    radix_sort_pairs(keys_nn.as<uint64_t>(), sorted_part, m, st);
+    return;
+  }
+  // ---- multi-column: stable passes from the last sort column to the first ---------------------------------
+  iota_u32_kernel<<<nblk(n), 256, 0, st>>>(perm, n);
+  SB_LAUNCH_CHECK();
+  Scratch keys(n * 8 + 16, st), isnull(n + 16, st);
+  for (int k = norders - 1; k >= 0; k--) {
+    const Column &c = in->cols[orders[k].col];
+    make_keys_kernel<<<nblk(n), SORT_THREADS, 0, st>>>(c.d(), c.v(), c.type, !orders[k].ascending, perm, n, keys.as<uint64_t>(),
+                                                       c.validity ? isnull.as<uint8_t>() : nullptr);
+    SB_LAUNCH_CHECK();
+    radix_sort_pairs(keys.as<uint64_t>(), perm, n, st);
+    if (c.validity) {   // NULLs of this column first or last, keeping the order established so far
+      make_keys_kernel<<<nblk(n), SORT_THREADS, 0, st>>>(c.d(), c.v(), c.type, 0, perm, n, keys.as<uint64_t>(), isnull.as<uint8_t>());
+      SB_LAUNCH_CHECK();
+      stable_split_by_flag(isnull.as<uint8_t>(), orders[k].nulls_first ? 1 : 0, perm, n, st);
+    }
+  }
+}
+
+}  // namespace sb
+
+using namespace sb;
+
+extern "C" {
+
+int sb_sort_permutation(const sb_table *in, const sb_sort_order *orders, int32_t norders, sb_stream *s, int64_t *out_perm_device) {
+  SB_API_BEGIN
+  require_init();
+  SB_REQUIRE(in && out_perm_device, "null argument");
+  cudaStream_t st = stream_of(s);
+  int64_t n = in->nrows;
+  Scratch perm(n * 4 + 16, st);
+  sort_permutation_impl(in, orders, norders, perm.as<uint32_t>(), st);
+  if (n > 0) {
+    u32_to_i64_kernel<<<nblk(n), 256, 0, st>>>(perm.as<uint32_t>(), n, out_perm_device);
+    SB_LAUNCH_CHECK();
+  }
+  SB_CUDA(cudaStreamSynchronize(st));
+  SB_API_END
+}
+
+int sb_sort(const sb_table *in, const sb_sort_order *orders, int32_t norders, sb_stream *s, sb_table **out) {
+  SB_API_BEGIN
+  require_init();
+  SB_REQUIRE(in && out, "null argument");
+  cudaStream_t st = stream_of(s);
+  int64_t n = in->nrows;
+  Scratch perm(n * 4 + 16, st), perm64(n * 8 + 16, st);
+  sort_permutation_impl(in, orders, norders, perm.as<uint32_t>(), st);
+  if (n > 0) {
+    u32_to_i64_kernel<<<nblk(n), 256, 0, st>>>(perm.as<uint32_t>(), n, perm64.as<int64_t>());
+    SB_LAUNCH_CHECK();
+  }
+  *out = gather_table(in, perm64.as<int64_t>(), n, false, st);
+  SB_CUDA(cudaStreamSynchronize(st));
+  SB_API_END
+}
+
+// TakeOrderedAndProjectExec: the reference keeps a bounded priority queue per partition and merges
+// (limit.scala:347-386); the result is the first k rows of the total order, which is what this returns.
+int sb_top_n(const sb_table *in, const sb_sort_order *orders, int32_t norders, int64_t k, sb_stream *s, sb_table **out) {
+  SB_API_BEGIN
+  require_init();
+  SB_REQUIRE(in && out && k >= 0, "bad argument");
+  cudaStream_t st = stream_of(s);
+  int64_t n = in->nrows;
+  int64_t take = k < n ? k : n;
+  Scratch perm(n * 4 + 16, st), perm64(take * 8 + 16, st);
+  sort_permutation_impl(in, orders, norders, perm.as<uint32_t>(), st);
+  if (take > 0) {
+    u32_to_i64_kernel<<<nblk(take), 256, 0, st>>>(perm.as<uint32_t>(), take, perm64.as<int64_t>());
+    SB_LAUNCH_CHECK();
+  }
+  *out = gather_table(in, perm64.as<int64_t>(), take, false, st);
+  SB_CUDA(cudaStreamSynchronize(st));
+  SB_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,428 @@
+"""SparkPlan operator mirrors that run on the GPU through the C ABI.
+
+Each class has the name, constructor shape and `executeColumnar()` contract of the reference operator it
+replaces (SQLX = sql/core/src/main/scala/org/apache/spark/sql/execution):
+
+  FilterExec / ProjectExec           SQLX/basicPhysicalOperators.scala:245 / :47
+  HashAggregateExec                  SQLX/aggregate/HashAggregateExec.scala:50
+  ShuffleExchangeExec                SQLX/exchange/ShuffleExchangeExec.scala:190
+  SortExec                           SQLX/SortExec.scala:39
+  TakeOrderedAndProjectExec          SQLX/limit.scala:310
+  BroadcastHashJoinExec              SQLX/joins/BroadcastHashJoinExec.scala:40
+  SortMergeJoinExec                  SQLX/joins/SortMergeJoinExec.scala:39   (same multiset, hash build/probe)
+  B200ColumnarRule                   a ColumnarRule (SQLX/Columnar.scala:47-50): preColumnarTransitions collapses
+                                     Filter/Project into the consuming HashAggregateExec, like WholeStageCodegen
+
+In a Spark deployment these bodies live in the Scala plugin (scala/) and call the same sb_*
+functions through JNI; this module is the binding used by the tests and bench.py.  One "partition" here is
+one ColumnarBatch on one GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _capi as capi
+from .columnar import ColumnarBatch, Stream, _h
+from .expressions import (AggregateFunction, AttributeReference, CompiledExpr, Expression, Schema, SortOrder)
+
+
+def _schema_of(batch: ColumnarBatch) -> Schema:
+    return Schema(batch.names, [batch.column_desc(i).type for i in range(len(batch.names))])
+
+
+class SparkPlan:
+    children = ()
+
+    def executeColumnar(self, stream: Stream = None) -> ColumnarBatch:
+        raise NotImplementedError
+
+    # the reference's public entry point is execute*/collect; to_arrow is ColumnarToRowExec + collect
+    def collect(self, stream=None):
+        b = self.executeColumnar(stream)
+        try:
+            return b.to_arrow(stream)
+        finally:
+            b.close()
+
+
+class LocalTableScanExec(SparkPlan):
+    """Leaf that hands out an existing HBM batch (the scan/RowToColumnar boundary)."""
+
+    def __init__(self, batch: ColumnarBatch):
+        self.batch = batch
+
+    def executeColumnar(self, stream=None):
+        return self.batch.rename(self.batch.names)
+
+
+class FilterExec(SparkPlan):
+    def __init__(self, condition: Expression, child: SparkPlan):
+        self.condition = condition
+        self.child = child
+        self.children = (child,)
+
+    def executeColumnar(self, stream=None):
+        inp = self.child.executeColumnar(stream)
+        try:
+            return _filter_project(inp, self.condition, [(n, AttributeReference(n)) for n in inp.names], stream)
+        finally:
+            inp.close()
+
+
+class ProjectExec(SparkPlan):
+    def __init__(self, projectList, child: SparkPlan):
+        """projectList: [(name, Expression)] (Alias(expr, name)) or bare attribute names."""
+        self.projectList = [(p, AttributeReference(p)) if isinstance(p, str) else p for p in projectList]
+        self.child = child
+        self.children = (child,)
+
+    def executeColumnar(self, stream=None):
+        inp = self.child.executeColumnar(stream)
+        try:
+            return _filter_project(inp, None, self.projectList, stream)
+        finally:
+            inp.close()
+
+
+def _filter_project(inp: ColumnarBatch, condition, project_list, stream) -> ColumnarBatch:
+    lib = capi.load()
+    schema = _schema_of(inp)
+    pred = CompiledExpr(condition, schema) if condition is not None else None
+    projs = [CompiledExpr(e, schema) for _, e in project_list]
+    arr = (capi.sb_expr * max(1, len(projs)))()
+    for i, p in enumerate(projs):
+        arr[i] = p.c
+    h = C.c_void_p()
+    capi.check(lib.sb_filter_project(inp.handle, C.byref(pred.c) if pred else None, arr, len(projs), _h(stream), C.byref(h)))
+    ats = []
+    for _, e in project_list:
+        ats.append(inp.arrow_types[schema.index(e.name)] if isinstance(e, AttributeReference) else None)
+    return ColumnarBatch(h, [n for n, _ in project_list], ats)
+
+
+class HashAggregateExec(SparkPlan):
+    """groupingExpressions: attribute names; aggregateExpressions: [(AggregateFunction, result_name)];
+    mode: 'partial' | 'final' | 'complete'.  `condition` / expression inputs are the fused child
+    FilterExec / ProjectExec (set by B200ColumnarRule or directly)."""
+
+    def __init__(self, groupingExpressions, aggregateExpressions, child: SparkPlan, mode="complete", condition=None,
+                 expected_groups=0):
+        self.groupingExpressions = list(groupingExpressions)
+        self.aggregateExpressions = list(aggregateExpressions)
+        self.child = child
+        self.children = (child,)
+        self.mode = mode
+        self.condition = condition
+        self.expected_groups = expected_groups
+
+    def output_names(self):
+        names = list(self.groupingExpressions)
+        for fn, name in self.aggregateExpressions:
+            if self.mode == "partial":
+                names += {"sum": [name + "#sum"], "avg": [name + "#sum", name + "#count"], "count": [name + "#count"],
+                          "count_star": [name + "#count"], "min": [name + "#val"], "max": [name + "#val"]}[fn.func]
+            else:
+                names.append(name)
+        return names
+
+    def executeColumnar(self, stream=None):
+        inp = self.child.executeColumnar(stream)
+        try:
+            return self.run(inp, stream)
+        finally:
+            inp.close()
+
+    def run(self, inp: ColumnarBatch, stream=None) -> ColumnarBatch:
+        lib = capi.load()
+        schema = _schema_of(inp)
+        keep = []
+        key_idx = [schema.index(k) for k in self.groupingExpressions]
+        key_arr = (C.c_int32 * max(1, len(key_idx)))(*key_idx)
+        specs = (capi.sb_agg_spec * max(1, len(self.aggregateExpressions)))()
+        for i, (fn, _name) in enumerate(self.aggregateExpressions):
+            specs[i].func = capi.SB_AGG[fn.func]
+            if self.mode != "final" and fn.child is not None:
+                ce = CompiledExpr(fn.child, schema)
+                keep.append(ce)
+                specs[i].input = ce.c
+        plan = capi.sb_agg_plan()
+        plan.mode = capi.SB_AGG_MODE[self.mode]
+        plan.nkeys = len(key_idx)
+        plan.key_cols = C.cast(key_arr, C.POINTER(C.c_int32))
+        plan.naggs = len(self.aggregateExpressions)
+        plan.aggs = C.cast(specs, C.POINTER(capi.sb_agg_spec))
+        if self.condition is not None:
+            fc = CompiledExpr(self.condition, schema)
+            keep.append(fc)
+            plan.filter = C.pointer(fc.c)
+        plan.expected_groups = self.expected_groups
+        h = C.c_void_p()
+        capi.check(lib.sb_hash_aggregate(inp.handle, C.byref(plan), _h(stream), C.byref(h)))
+        names = self.output_names()
+        ats = [inp.arrow_types[i] for i in key_idx] + [None] * (len(names) - len(key_idx))
+        return ColumnarBatch(h, names, ats)
+
+
+class HashPartitioning:
+    def __init__(self, expressions, numPartitions):
+        self.expressions = list(expressions)
+        self.numPartitions = numPartitions
+
+
+class RoundRobinPartitioning:
+    def __init__(self, numPartitions, start=0):
+        self.numPartitions = numPartitions
+        self.start = start   # XORShiftRandom(mapPartitionId).nextInt(n) in the reference: parity unpinned
+
+
+class SinglePartition:
+    numPartitions = 1
+
+
+class ShuffleExchangeExec(SparkPlan):
+    """Map side always runs on the local GPU (partition ids + regrouping).  With a communicator
+    (sb_comm_init done, world size > 1) the buckets are exchanged with the NCCL all-to-all and the
+    result holds the partitions this rank owns (partition p -> rank p % world)."""
+
+    def __init__(self, outputPartitioning, child: SparkPlan):
+        self.outputPartitioning = outputPartitioning
+        self.child = child
+        self.children = (child,)
+        self.partition_offsets = None
+
+    def executeColumnar(self, stream=None):
+        inp = self.child.executeColumnar(stream)
+        try:
+            return self.run(inp, stream)
+        finally:
+            inp.close()
+
+    def map_side(self, inp: ColumnarBatch, stream=None):
+        lib = capi.load()
+        p = self.outputPartitioning
+        n = p.numPartitions
+        offs = (C.c_int64 * (n + 1))()
+        h = C.c_void_p()
+        if isinstance(p, HashPartitioning):
+            idx = [inp.column_index(k) for k in p.expressions]
+            arr = (C.c_int32 * max(1, len(idx)))(*idx)
+            capi.check(lib.sb_hash_partition(inp.handle, arr, len(idx), n, _h(stream), C.byref(h), offs))
+        elif isinstance(p, RoundRobinPartitioning):
+            capi.check(lib.sb_round_robin_partition(inp.handle, p.start, n, _h(stream), C.byref(h), offs))
+        else:
+            capi.check(lib.sb_round_robin_partition(inp.handle, 0, 1, _h(stream), C.byref(h), offs))
+        return ColumnarBatch(h, inp.names, inp.arrow_types), np.array(list(offs), dtype=np.int64)
+
+    def run(self, inp: ColumnarBatch, stream=None) -> ColumnarBatch:
+        lib = capi.load()
+        part, offs = self.map_side(inp, stream)
+        rank, world = C.c_int32(), C.c_int32()
+        capi.check(lib.sb_comm_rank(C.byref(rank), C.byref(world)))
+        if world.value <= 1:
+            self.partition_offsets = offs
+            return part
+        try:
+            n = self.outputPartitioning.numPartitions
+            in_offs = (C.c_int64 * (n + 1))(*offs.tolist())
+            out_offs = (C.c_int64 * (n + 1))()
+            h = C.c_void_p()
+            capi.check(lib.sb_all_to_all(part.handle, in_offs, n, _h(stream), C.byref(h), out_offs))
+            self.partition_offsets = np.array(list(out_offs), dtype=np.int64)
+            return ColumnarBatch(h, part.names, part.arrow_types)
+        finally:
+            part.close()
+
+    def partition_ids(self, inp: ColumnarBatch, stream=None) -> np.ndarray:
+        """Partition id of every input row (for parity checks against Pmod(Murmur3Hash(keys), n))."""
+        import torch
+        lib = capi.load()
+        p = self.outputPartitioning
+        idx = [inp.column_index(k) for k in p.expressions]
+        arr = (C.c_int32 * max(1, len(idx)))(*idx)
+        out = torch.empty(max(inp.num_rows, 1), dtype=torch.int32, device="cuda")
+        capi.check(lib.sb_partition_ids(inp.handle, arr, len(idx), p.numPartitions, _h(stream), C.c_void_p(out.data_ptr())))
+        capi.check(lib.sb_stream_synchronize(_h(stream)))
+        return out[: inp.num_rows].cpu().numpy()
+
+
+def _orders_c(batch: ColumnarBatch, sortOrder):
+    arr = (capi.sb_sort_order * max(1, len(sortOrder)))()
+    for i, o in enumerate(sortOrder):
+        arr[i].col = batch.column_index(o.child)
+        arr[i].ascending = int(o.ascending)
+        arr[i].nulls_first = int(o.nulls_first)
+    return arr
+
+
+class SortExec(SparkPlan):
+    def __init__(self, sortOrder, child: SparkPlan, global_=False):
+        self.sortOrder = [o if isinstance(o, SortOrder) else SortOrder(*o) for o in sortOrder]
+        self.child = child
+        self.children = (child,)
+        self.global_ = global_
+
+    def executeColumnar(self, stream=None):
+        inp = self.child.executeColumnar(stream)
+        try:
+            h = C.c_void_p()
+            capi.check(capi.load().sb_sort(inp.handle, _orders_c(inp, self.sortOrder), len(self.sortOrder), _h(stream), C.byref(h)))
+            return ColumnarBatch(h, inp.names, inp.arrow_types)
+        finally:
+            inp.close()
+
+
+class TakeOrderedAndProjectExec(SparkPlan):
+    def __init__(self, limit, sortOrder, projectList, child: SparkPlan):
+        self.limit = limit
+        self.sortOrder = [o if isinstance(o, SortOrder) else SortOrder(*o) for o in sortOrder]
+        self.projectList = projectList
+        self.child = child
+        self.children = (child,)
+
+    def executeColumnar(self, stream=None):
+        inp = self.child.executeColumnar(stream)
+        try:
+            h = C.c_void_p()
+            capi.check(capi.load().sb_top_n(inp.handle, _orders_c(inp, self.sortOrder), len(self.sortOrder), self.limit,
+                                            _h(stream), C.byref(h)))
+            top = ColumnarBatch(h, inp.names, inp.arrow_types)
+            if self.projectList is None:
+                return top
+            try:
+                return top.select(self.projectList)
+            finally:
+                top.close()
+        finally:
+            inp.close()
+
+
+class HashedRelation:
+    """Build side resident in HBM (HashedRelation.scala:136-168): sb_hash_table handle."""
+
+    def __init__(self, batch: ColumnarBatch, keys, stream=None):
+        lib = capi.load()
+        idx = [batch.column_index(k) for k in keys]
+        arr = (C.c_int32 * max(1, len(idx)))(*idx)
+        h = C.c_void_p()
+        capi.check(lib.sb_join_build(batch.handle, arr, len(idx), _h(stream), C.byref(h)))
+        self.handle = h
+        self.names = batch.names
+        self.arrow_types = batch.arrow_types
+
+    def close(self):
+        if self.handle:
+            capi.load().sb_hash_table_release(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class BroadcastHashJoinExec(SparkPlan):
+    """leftKeys/rightKeys: attribute names; joinType: inner | left_outer | left_semi | left_anti;
+    buildSide: 'right' (the left side is streamed).  Output: left ++ right columns (HashJoin.scala:55-70)."""
+
+    def __init__(self, leftKeys, rightKeys, joinType, buildSide, left: SparkPlan, right: SparkPlan):
+        if buildSide != "right":
+            raise capi.SparkB200Error(5, "only buildSide='right' is implemented (swap the children)")
+        self.leftKeys, self.rightKeys = list(leftKeys), list(rightKeys)
+        self.joinType = joinType
+        self.left, self.right = left, right
+        self.children = (left, right)
+
+    def executeColumnar(self, stream=None):
+        build = self.right.executeColumnar(stream)
+        try:
+            rel = HashedRelation(build, self.rightKeys, stream)
+        finally:
+            build.close()
+        try:
+            probe = self.left.executeColumnar(stream)
+            try:
+                return probe_join(rel, probe, self.leftKeys, self.joinType, stream)
+            finally:
+                probe.close()
+        finally:
+            rel.close()
+
+
+def probe_join(rel: HashedRelation, probe: ColumnarBatch, keys, joinType, stream=None) -> ColumnarBatch:
+    lib = capi.load()
+    idx = [probe.column_index(k) for k in keys]
+    arr = (C.c_int32 * max(1, len(idx)))(*idx)
+    h = C.c_void_p()
+    capi.check(lib.sb_join_probe(rel.handle, probe.handle, arr, len(idx), capi.SB_JOIN[joinType], _h(stream), C.byref(h)))
+    if joinType in ("left_semi", "left_anti"):
+        return ColumnarBatch(h, probe.names, probe.arrow_types)
+    return ColumnarBatch(h, probe.names + rel.names, probe.arrow_types + rel.arrow_types)
+
+
+class SortMergeJoinExec(BroadcastHashJoinExec):
+    """The reference sorts both sides and merges (SortMergeJoinExec.scala:1213-1360); the GPU engine produces
+    the same multiset with a hash build/probe and therefore does not report an outputOrdering."""
+
+    def __init__(self, leftKeys, rightKeys, joinType, left, right):
+        super().__init__(leftKeys, rightKeys, joinType, "right", left, right)
+
+
+class B200ColumnarRule:
+    """preColumnarTransitions: collapse Project/Filter chains under a HashAggregateExec into it (what
+    CollapseCodegenStages + WholeStageCodegenExec do for the CPU path)."""
+
+    def preColumnarTransitions(self, plan: SparkPlan) -> SparkPlan:
+        for attr in ("child", "left", "right"):
+            if hasattr(plan, attr):
+                setattr(plan, attr, self.preColumnarTransitions(getattr(plan, attr)))
+        if hasattr(plan, "child"):
+            plan.children = (plan.child,)
+        if isinstance(plan, HashAggregateExec) and plan.mode != "final":
+            child = plan.child
+            subst = {}
+            cond = plan.condition
+            changed = False
+            while True:
+                if isinstance(child, ProjectExec):
+                    m = {n: _substitute(e, subst) for n, e in child.projectList}
+                    subst = m
+                    child = child.child
+                    changed = True
+                elif isinstance(child, FilterExec) and cond is None:
+                    cond = child.condition   # filter sits below the projections: it sees source attributes
+                    child = child.child
+                    changed = True
+                else:
+                    break
+            if changed:
+                group_ok = all(isinstance(subst.get(g, AttributeReference(g)), AttributeReference) and
+                               subst.get(g, AttributeReference(g)).name == g for g in plan.groupingExpressions) if subst else True
+                if group_ok:
+                    aggs = []
+                    for fn, name in plan.aggregateExpressions:
+                        if fn.child is not None and subst:
+                            fn = type(fn)(_substitute(fn.child, subst))
+                        aggs.append((fn, name))
+                    return HashAggregateExec(plan.groupingExpressions, aggs, child, plan.mode, cond, plan.expected_groups)
+        return plan
+
+    def postColumnarTransitions(self, plan: SparkPlan) -> SparkPlan:
+        return plan
+
+
+def _substitute(e: Expression, mapping):
+    import copy
+    if isinstance(e, AttributeReference):
+        return mapping.get(e.name, e)
+    e2 = copy.copy(e)
+    for attr in ("left", "right", "child"):
+        if hasattr(e2, attr):
+            setattr(e2, attr, _substitute(getattr(e2, attr), mapping))
+    if hasattr(e2, "left"):
+        e2.children = (e2.left, e2.right)
+    elif hasattr(e2, "child"):
+        e2.children = (e2.child,)
+    return e2

@@ -1,0 +1,73 @@
+"""CPU-side checks of the drop-in boundary: the shared library loads, exports every symbol
+include/spark_b200.h declares, and refuses to run without a GPU (no CPU fallback)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+
+def test_library_exports_every_declared_symbol():
+    from spark_b200 import _capi as capi
+    lib = capi.load()
+    syms = capi.declared_symbols()
+    assert len(syms) >= 40
+    missing = [s for s in syms if not hasattr(lib, s)]
+    assert not missing, missing
+    assert set(capi._SIGNATURES) == set(syms), set(capi._SIGNATURES) ^ set(syms)
+    assert lib.sb_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible")
+    from spark_b200 import _capi as capi
+    lib = capi.load()
+    assert lib.sb_init(0) != 0
+    assert b"no CPU fallback" in lib.sb_last_error()
+    h = C.c_void_p()
+    assert lib.sb_stream_create(C.byref(h)) == 6          # SB_ERR_NOT_INITIALIZED
+    cols = (capi.sb_column * 1)()
+    assert lib.sb_table_import_host(cols, 0, None, C.byref(h)) == 6
+
+
+def test_exchange_plan_contiguous_ownership():
+    """Host-only planner of the all-to-all: rank r owns partitions [ceil(r*n/R), ceil((r+1)*n/R))."""
+    from spark_b200 import _capi as capi
+    lib = capi.load()
+    rng = np.random.default_rng(0)
+    for nparts, nranks in [(200, 8), (2048, 8), (5, 2), (3, 4), (1, 2)]:
+        counts = rng.integers(0, 100, nparts)
+        offs = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+        send = np.zeros(nranks, np.int64)
+        rc = lib.sb_exchange_plan(offs.ctypes.data_as(C.POINTER(C.c_int64)), nparts, nranks,
+                                  send.ctypes.data_as(C.POINTER(C.c_int64)))
+        assert rc == 0
+        assert send.sum() == counts.sum()
+        lo = [-(-r * nparts // nranks) for r in range(nranks + 1)]
+        for r in range(nranks):
+            assert send[r] == counts[lo[r]:lo[r + 1]].sum()
+
+
+def test_expression_lowering_and_fusion_rule():
+    from spark_b200 import _capi as capi
+    from spark_b200.expressions import CompiledExpr, Literal, Schema, Sum, col
+    from spark_b200.execution import B200ColumnarRule, FilterExec, HashAggregateExec, ProjectExec, SparkPlan
+    schema = Schema(["p", "d", "s"], [capi.SB_FLOAT64, capi.SB_FLOAT64, capi.SB_DATE32])
+    e = col("p") * (Literal(1) - col("d"))
+    ce = CompiledExpr(e, schema)
+    ops = [ce.arr[i].op for i in range(ce.c.n)]
+    assert ops == [capi.SB_OP["COL"], capi.SB_OP["LIT_F64"], capi.SB_OP["COL"], capi.SB_OP["SUB"], capi.SB_OP["MUL"]]
+    assert ce.arr[1].lit.d == 1.0 and ce.c.out_type == capi.SB_FLOAT64
+    assert e.sexpr() == ("mul", ("col", "p"), ("sub", ("lit", 1, np.int32), ("col", "d")))
+
+    class Leaf(SparkPlan):
+        pass
+    leaf = Leaf()
+    plan = HashAggregateExec(["k"], [(Sum(col("x")), "sx")],
+                             ProjectExec([("k", col("k")), ("x", col("p") * col("d"))], FilterExec(col("s") <= Literal(10), leaf)),
+                             mode="partial")
+    fused = B200ColumnarRule().preColumnarTransitions(plan)
+    assert isinstance(fused, HashAggregateExec) and fused.child is leaf
+    assert fused.condition.sexpr()[0] == "le"
+    assert fused.aggregateExpressions[0][0].child.sexpr() == ("mul", ("col", "p"), ("col", "d"))

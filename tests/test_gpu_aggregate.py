@@ -1,0 +1,192 @@
+"""GPU parity: HashAggregateExec (+ fused FilterExec/ProjectExec) vs the oracle."""
+import numpy as np
+import pyarrow as pa
+import pytest
+
+from oracle import oracle as O
+from util import assert_tables_equal
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(plan_fn, t, stream):
+    from spark_b200.columnar import ColumnarBatch
+    from spark_b200.execution import LocalTableScanExec
+    batch = ColumnarBatch.from_arrow(t, stream)
+    return plan_fn(LocalTableScanExec(batch)).collect(stream)
+
+
+# configs[0] of BASELINE.json: SELECT k, SUM(v) GROUP BY k on a 1M-row two-column DataFrame
+@pytest.mark.parametrize("groups", [4, 1024, 65536, 1 << 20])
+@pytest.mark.parametrize("vtype", ["int64", "float64"])
+def test_c1_group_by_sum(gpu, stream, groups, vtype):
+    from spark_b200.execution import HashAggregateExec
+    from spark_b200.expressions import Sum, col
+    n = 1 << 20
+    rng = np.random.default_rng(42)
+    k = rng.integers(0, groups, n)
+    v = rng.integers(-2 ** 31, 2 ** 31, n) if vtype == "int64" else rng.random(n) * 1e4
+    t = pa.table({"k": k, "v": v})
+    got = _run(lambda scan: HashAggregateExec(["k"], [(Sum(col("v")), "sum_v")], scan), t, stream)
+    want = O.hash_aggregate(t, ["k"], [("sum", "v", "sum_v")])
+    assert_tables_equal(got, want, key_cols=["k"])
+
+
+def test_all_functions_nulls_and_null_keys(gpu, stream):
+    from spark_b200.execution import HashAggregateExec
+    from spark_b200.expressions import Average, Count, Max, Min, Sum, col
+    n = 50000
+    rng = np.random.default_rng(7)
+    d = rng.standard_normal(n)
+    d[rng.random(n) < 0.01] = np.nan
+    t = pa.table({"k1": pa.array(rng.integers(0, 50, n).astype(np.int32), mask=rng.random(n) < 0.05),
+                  "k2": pa.array(rng.integers(0, 3, n).astype(np.int8), mask=rng.random(n) < 0.05),
+                  "v": pa.array(rng.integers(-10 ** 12, 10 ** 12, n), mask=rng.random(n) < 0.3),
+                  "d": pa.array(d, mask=rng.random(n) < 0.3),
+                  "i": pa.array(rng.integers(-1000, 1000, n).astype(np.int32), mask=rng.random(n) < 0.3)})
+    aggs = [(Sum(col("v")), "sv"), (Sum(col("d")), "sd"), (Average(col("d")), "ad"), (Average(col("i")), "ai"),
+            (Count(col("v")), "cv"), (Count(), "n"), (Min(col("v")), "mnv"), (Max(col("v")), "mxv"),
+            (Min(col("d")), "mnd"), (Max(col("d")), "mxd"), (Min(col("i")), "mni")]
+    oaggs = [("sum", "v", "sv"), ("sum", "d", "sd"), ("avg", "d", "ad"), ("avg", "i", "ai"), ("count", "v", "cv"),
+             ("count_star", None, "n"), ("min", "v", "mnv"), ("max", "v", "mxv"), ("min", "d", "mnd"), ("max", "d", "mxd"),
+             ("min", "i", "mni")]
+    got = _run(lambda scan: HashAggregateExec(["k1", "k2"], aggs, scan), t, stream)
+    want = O.hash_aggregate(t, ["k1", "k2"], oaggs)
+    assert_tables_equal(got, want, key_cols=["k1", "k2"])
+
+
+@pytest.mark.parametrize("ktype", ["int64", "float64", "date32", "bool"])
+def test_single_key_types_including_sentinel_and_null(gpu, stream, ktype):
+    from spark_b200.execution import HashAggregateExec
+    from spark_b200.expressions import Count, Sum, col
+    n = 20000
+    rng = np.random.default_rng(11)
+    if ktype == "int64":
+        k = rng.integers(-5, 5, n)
+        k[:10] = -1                      # 0xFFFF... is the table's EMPTY sentinel
+        k[10:20] = 2 ** 63 - 1
+        karr = pa.array(k, mask=rng.random(n) < 0.1)
+    elif ktype == "float64":
+        k = rng.integers(-3, 3, n).astype(np.float64)
+        k[rng.random(n) < 0.1] = -0.0    # must group with 0.0 (NormalizeFloatingNumbers)
+        k[rng.random(n) < 0.1] = np.nan
+        karr = pa.array(k, mask=rng.random(n) < 0.1)
+    elif ktype == "date32":
+        karr = pa.array(rng.integers(0, 40, n).astype(np.int32), mask=rng.random(n) < 0.1).cast(pa.date32())
+    else:
+        karr = pa.array(rng.integers(0, 2, n).astype(bool), mask=rng.random(n) < 0.1)
+    t = pa.table({"k": karr, "v": rng.integers(0, 100, n)})
+    got = _run(lambda scan: HashAggregateExec(["k"], [(Sum(col("v")), "s"), (Count(), "c")], scan), t, stream)
+    want = O.hash_aggregate(t, ["k"], [("sum", "v", "s"), ("count_star", None, "c")])
+    if ktype == "float64":
+        # compare NaN/-0.0 keys by bit-normalised value
+        norm = lambda tb: tb.set_column(0, "k", pa.array([None if x is None else (float("nan") if x != x else x + 0.0)
+                                                          for x in tb.column("k").to_pylist()]))
+        got, want = norm(got), norm(want)
+    assert_tables_equal(got, want, key_cols=["k"])
+
+
+def test_partial_exchange_final_equals_complete(gpu, stream):
+    """AggUtils.scala:131-208 mode algebra: Partial on two 'map tasks' -> concat -> Final == Complete."""
+    from spark_b200.columnar import ColumnarBatch
+    from spark_b200.execution import HashAggregateExec, LocalTableScanExec
+    from spark_b200.expressions import Average, Count, Max, Sum, col
+    n = 40000
+    rng = np.random.default_rng(3)
+    t = pa.table({"k": rng.integers(0, 300, n).astype(np.int32),
+                  "v": pa.array(rng.integers(-1000, 1000, n), mask=rng.random(n) < 0.2), "d": rng.random(n)})
+    aggs = [(Sum(col("v")), "s"), (Average(col("d")), "a"), (Count(col("v")), "c"), (Count(), "n"), (Max(col("d")), "mx")]
+    oaggs = [("sum", "v", "s"), ("avg", "d", "a"), ("count", "v", "c"), ("count_star", None, "n"), ("max", "d", "mx")]
+    parts = []
+    for half in (t.slice(0, n // 2), t.slice(n // 2)):
+        b = ColumnarBatch.from_arrow(half, stream)
+        parts.append(HashAggregateExec(["k"], aggs, LocalTableScanExec(b), mode="partial").collect(stream))
+        want_partial = O.hash_aggregate(half, ["k"], oaggs, "partial")
+        assert_tables_equal(parts[-1], want_partial, key_cols=["k"])
+    merged = pa.concat_tables(parts)
+    b = ColumnarBatch.from_arrow(merged, stream)
+    got = HashAggregateExec(["k"], aggs, LocalTableScanExec(b), mode="final").collect(stream)
+    want = O.hash_aggregate(t, ["k"], oaggs, "complete")
+    assert_tables_equal(got, want, key_cols=["k"])
+
+
+def test_global_aggregate_without_keys_and_empty_input(gpu, stream):
+    from spark_b200.execution import HashAggregateExec
+    from spark_b200.expressions import Average, Count, Sum, col
+    t = pa.table({"v": pa.array([1, 2, None, 4], type=pa.int64()), "d": [0.5, 1.5, 2.5, 3.5]})
+    aggs = [(Sum(col("v")), "s"), (Average(col("d")), "a"), (Count(), "n")]
+    got = _run(lambda scan: HashAggregateExec([], aggs, scan), t, stream)
+    assert got.to_pydict() == {"s": [7], "a": [2.0], "n": [4]}
+    empty = t.slice(0, 0)
+    got = _run(lambda scan: HashAggregateExec([], aggs, scan), empty, stream)
+    assert got.to_pydict() == {"s": [None], "a": [None], "n": [0]}     # one row even for empty input
+    got = _run(lambda scan: HashAggregateExec(["v"], aggs[1:], scan), empty, stream)
+    assert got.num_rows == 0
+
+
+def _q1_oracle(t):
+    from spark_b200 import tpch
+    f = O.filter_table(t, ("le", ("col", "l_shipdate"), ("lit", tpch.Q1_CUTOFF, np.int32)))
+    dp = ("mul", ("col", "l_extendedprice"), ("sub", ("lit", 1.0), ("col", "l_discount")))
+    p = O.project(f, [(c, ("col", c)) for c in ["l_returnflag", "l_linestatus", "l_quantity", "l_extendedprice", "l_discount"]] +
+                  [("disc_price", dp), ("charge", ("mul", dp, ("add", ("lit", 1.0), ("col", "l_tax"))))])
+    return O.hash_aggregate(p, ["l_returnflag", "l_linestatus"], tpch.q1_oracle_aggs())
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_tpch_q1_fused_and_unfused(gpu, stream, fused):
+    """configs[1] shape at a size the oracle finishes in seconds; the fused plan (FilterExec/ProjectExec inside the
+    aggregate kernel) and the operator-by-operator plan must both equal the oracle."""
+    from spark_b200 import tpch
+    from spark_b200.columnar import ColumnarBatch
+    from spark_b200.execution import LocalTableScanExec
+    t = tpch.lineitem_q1_table(600_000, seed=5)
+    batch = ColumnarBatch.from_arrow(t, stream)
+    partial = tpch.q1_partial_plan(LocalTableScanExec(batch), fused=fused)
+    got = tpch.q1_final_plan(partial, sort=False).collect(stream)
+    assert_tables_equal(got, _q1_oracle(t), key_cols=["l_returnflag", "l_linestatus"])
+
+
+def test_fusion_rule_produces_same_result(gpu, stream):
+    from spark_b200 import tpch
+    from spark_b200.columnar import ColumnarBatch
+    from spark_b200.execution import B200ColumnarRule, HashAggregateExec, LocalTableScanExec
+    t = tpch.lineitem_q1_table(100_000, seed=6)
+    batch = ColumnarBatch.from_arrow(t, stream)
+    plan = tpch.q1_partial_plan(LocalTableScanExec(batch), fused=False)
+    fused = B200ColumnarRule().preColumnarTransitions(plan)
+    assert isinstance(fused, HashAggregateExec) and isinstance(fused.child, LocalTableScanExec) and fused.condition is not None
+    got = tpch.q1_final_plan(fused, sort=False).collect(stream)
+    assert_tables_equal(got, _q1_oracle(t), key_cols=["l_returnflag", "l_linestatus"])
+
+
+def test_general_expressions_take_the_materialising_path(gpu, stream):
+    """Predicate with OR / arithmetic and an aggregate input that is not a product form."""
+    from spark_b200.execution import HashAggregateExec
+    from spark_b200.expressions import Literal, Sum, col
+    n = 30000
+    rng = np.random.default_rng(8)
+    t = pa.table({"k": rng.integers(0, 20, n).astype(np.int32), "a": pa.array(rng.integers(-50, 50, n), mask=rng.random(n) < 0.1),
+                  "b": rng.integers(-50, 50, n), "x": rng.random(n), "y": pa.array(rng.random(n), mask=rng.random(n) < 0.1)})
+    cond = ((col("a") + col("b")) > Literal(0)) | (col("x") < col("y"))
+    aggs = [(Sum(col("a") * col("b") - Literal(3)), "s1"), (Sum((col("x") + col("y")) / (col("b"))), "s2")]
+    got = _run(lambda scan: HashAggregateExec(["k"], aggs, scan, condition=cond), t, stream)
+    f = O.filter_table(t, cond.sexpr())
+    p = O.project(f, [("k", ("col", "k")), ("e1", aggs[0][0].child.sexpr()), ("e2", aggs[1][0].child.sexpr())])
+    want = O.hash_aggregate(p, ["k"], [("sum", "e1", "s1"), ("sum", "e2", "s2")])
+    assert_tables_equal(got, want, key_cols=["k"])
+
+
+def test_filter_project_operator(gpu, stream):
+    from spark_b200.execution import FilterExec, ProjectExec
+    from spark_b200.expressions import Literal, col
+    n = 10000
+    rng = np.random.default_rng(2)
+    t = pa.table({"a": pa.array(rng.integers(-100, 100, n).astype(np.int32), mask=rng.random(n) < 0.1),
+                  "x": pa.array(rng.standard_normal(n), mask=rng.random(n) < 0.1),
+                  "s": pa.array(["v%d" % i if i % 7 else None for i in range(n)])})
+    cond = (col("a") >= Literal(-10)) & col("x").is_not_null()
+    proj = [("a", col("a")), ("s", col("s")), ("e", col("x") * Literal(2.0) + col("a")), ("q", col("x") / col("a"))]
+    got = _run(lambda scan: ProjectExec(proj, FilterExec(cond, scan)), t, stream)
+    want = O.project(O.filter_table(t, cond.sexpr()), [(n_, e.sexpr()) for n_, e in proj])
+    assert_tables_equal(got, want, ordered=True)
