@@ -35,7 +35,8 @@ constexpr int AGG_THREADS = 128;
 constexpr int AGG_ITEMS = 8;
 constexpr int AGG_DICT = 8;          // tier-1 dictionary entries per block
 constexpr int AGG_MAX_SLOTS = 16;
-constexpr int AGG_MAX_KEYS = 4;
+constexpr int AGG_MAX_KEYS = 6;
+constexpr int AGG_MAX_WORDS = 4;
 constexpr int AGG_MAX_TERMS = 4;
 constexpr int AGG_MAX_FACT = 3;
 constexpr int AGG_PROBE_LIMIT = 64;
@@ -44,6 +45,7 @@ constexpr uint64_t EMPTY_KEY = 0xFFFFFFFFFFFFFFFFull;
 enum SlotKind { K_ADD_I64 = 0, K_ADD_F64 = 1, K_MIN_U64 = 2, K_MAX_U64 = 3 };
 enum ValXform { X_NONE = 0, X_SIGNED = 1, X_DOUBLE = 2 };   // value -> order-preserving u64 for min/max
 enum FactorMode { F_COL = 0, F_LIT_MINUS_COL = 1, F_LIT_PLUS_COL = 2, F_COL_MINUS_LIT = 3 };
+enum SlotClass { CLS_GENERIC = 0, CLS_ONE = 1, CLS_F64_PRODUCT = 2 };   // ONE: count(*) ; F64_PRODUCT: non-null double factors
 enum TermOp { T_EQ = 0, T_NE, T_LT, T_LE, T_GT, T_GE, T_NOTNULL };
 
 struct Factor {
@@ -58,6 +60,8 @@ struct SlotSrc {
   int32_t nf;        // number of factors (0 = constant one)
   int32_t is_one;    // value is 1 when every factor column is non-null (COUNT)
   int32_t xform;     // ValXform for min/max
+  int32_t cls;       // SlotClass, precomputed on the host so the kernel takes ONE uniform branch per slot
+  int32_t pad;
   Factor f[AGG_MAX_FACT];
 };
 struct KeySrc {
@@ -67,6 +71,8 @@ struct KeySrc {
   int32_t bits;      // value bits
   int32_t shift;     // position in the packed word
   int32_t null_shift;  // bit position of the null flag or -1
+  int32_t word;      // which 64-bit key word holds the value (wide keys)
+  int32_t null_word; // which word holds the null flag
 };
 struct FilterTerm {
   const void *data;
@@ -84,7 +90,9 @@ struct AggArgs {
   FilterTerm term[AGG_MAX_TERMS];
   const uint8_t *mask;   // optional materialised predicate (1 byte / row)
   SlotSrc slot[AGG_MAX_SLOTS];
-  uint64_t *tkeys;       // [cap + 2]   slot cap = NULL key, slot cap+1 = key equal to the EMPTY sentinel
+  int32_t nwords, pad0;  // 1 = packed single word; 2..AGG_MAX_WORDS = wide keys (lock-protocol table)
+  uint32_t *tstate;      // wide keys only: [cap] 0 empty, 1 being written, 2 ready
+  uint64_t *tkeys;       // [nwords][cap + 2]   slot cap = NULL key, slot cap+1 = key equal to the EMPTY sentinel
   uint64_t *tacc;        // [nslots][cap + 2]
   int32_t *flags;        // [0] abort (table too small), [1] NULL-key slot used, [2] sentinel-key slot used
   int64_t cap;
@@ -239,7 +247,430 @@ __device__ __forceinline__ int64_t table_slot(const AggArgs &a, uint64_t key, in
   return -1;
 }
 
-// Shared memory layout: uint64 dict_keys[AGG_DICT]; uint64 acc[AGG_DICT * nslots][AGG_THREADS]
+constexpr int64_t DST_SKIP = INT64_MIN;
+
+// ---------------------------------------------------------------------------------------------------------
+// Tile processing.  A thread owns AGG_ITEMS rows of a tile (row = row0 + k*AGG_THREADS, coalesced per k).
+// Rules that keep the instruction count per row low (first profile: 524 thread-instructions per row, 12% BRA,
+// 12% BSSY/BSYNC -- see profiles/r01_agg_update.md):
+//   * every descriptor (filter term, key column, accumulator slot) is read from the parameter bank once per
+//     tile, and every warp-uniform decision (column type, factor mode, accumulator kind) is taken OUTSIDE the
+//     unrolled row loop;
+//   * FULL tiles use unclamped loads, so the AGG_ITEMS loads of a column are LDG [base + k*stride] with
+//     immediate offsets and are all in flight together; only the last partial tile clamps the row index.
+// ---------------------------------------------------------------------------------------------------------
+template <bool FULL, typename T>
+__device__ __forceinline__ void load_batch_as_i64(const void *__restrict__ data, int64_t row0, int64_t last, int64_t (&out)[AGG_ITEMS]) {
+  const T *p = (const T *)data + row0;
+#pragma unroll
+  for (int k = 0; k < AGG_ITEMS; k++) {
+    if (FULL) out[k] = (int64_t)p[k * AGG_THREADS];
+    else {
+      int64_t r = row0 + (int64_t)k * AGG_THREADS;
+      out[k] = (int64_t)((const T *)data)[r < last ? r : last];
+    }
+  }
+}
+template <bool FULL>
+__device__ __forceinline__ void load_i64_batch(const void *__restrict__ data, int32_t type, int64_t row0, int64_t last,
+                                               int64_t (&out)[AGG_ITEMS]) {
+  switch (type) {
+    case SB_BOOL: load_batch_as_i64<FULL, uint8_t>(data, row0, last, out); break;
+    case SB_INT8: load_batch_as_i64<FULL, int8_t>(data, row0, last, out); break;
+    case SB_INT16: load_batch_as_i64<FULL, int16_t>(data, row0, last, out); break;
+    case SB_INT32: case SB_DATE32: case SB_FLOAT32: load_batch_as_i64<FULL, int32_t>(data, row0, last, out); break;
+    default: load_batch_as_i64<FULL, int64_t>(data, row0, last, out); break;
+  }
+}
+template <bool FULL>
+__device__ __forceinline__ void load_f64_batch(const void *__restrict__ data, int32_t type, int64_t row0, int64_t last,
+                                               double (&out)[AGG_ITEMS]) {
+  if (type == SB_FLOAT64) {
+    const double *p = (const double *)data + row0;
+#pragma unroll
+    for (int k = 0; k < AGG_ITEMS; k++) {
+      if (FULL) out[k] = p[k * AGG_THREADS];
+      else {
+        int64_t r = row0 + (int64_t)k * AGG_THREADS;
+        out[k] = ((const double *)data)[r < last ? r : last];
+      }
+    }
+  } else {
+    int64_t t[AGG_ITEMS];
+    load_i64_batch<FULL>(data, type, row0, last, t);
+    if (type == SB_FLOAT32) {
+#pragma unroll
+      for (int k = 0; k < AGG_ITEMS; k++) out[k] = (double)__int_as_float((int32_t)t[k]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < AGG_ITEMS; k++) out[k] = (double)t[k];
+    }
+  }
+}
+// validity bits of the AGG_ITEMS rows; the caller skips this entirely when the column has no bitmap
+template <bool FULL>
+__device__ __forceinline__ void load_valid_batch(const uint8_t *__restrict__ valid, int64_t row0, int64_t last, bool (&out)[AGG_ITEMS]) {
+  uint8_t b[AGG_ITEMS];
+#pragma unroll
+  for (int k = 0; k < AGG_ITEMS; k++) {
+    int64_t r = row0 + (int64_t)k * AGG_THREADS;
+    if (!FULL) r = r < last ? r : last;
+    b[k] = valid[r >> 3];
+  }
+#pragma unroll
+  for (int k = 0; k < AGG_ITEMS; k++) {
+    int64_t r = row0 + (int64_t)k * AGG_THREADS;
+    if (!FULL) r = r < last ? r : last;
+    out[k] = (b[k] >> (r & 7)) & 1;
+  }
+}
+
+
+
+// fused FilterExec: conjunction of column-vs-literal terms, applied to the thread's AGG_ITEMS rows
+template <bool FULL>
+__device__ __forceinline__ void apply_filter_terms(const AggArgs &a, int64_t row0, bool (&keep)[AGG_ITEMS]) {
+  const int64_t last = a.n - 1;
+  for (int t = 0; t < a.nterms; t++) {
+    const void *data = a.term[t].data;
+    const uint8_t *vptr = a.term[t].valid;
+    const int32_t type = a.term[t].type, op = a.term[t].op, is_f64 = a.term[t].is_f64;
+    const int64_t lit = a.term[t].lit;
+    if (vptr) {   // a NULL comparison drops the row
+      bool valid[AGG_ITEMS];
+      load_valid_batch<FULL>(vptr, row0, last, valid);
+#pragma unroll
+      for (int k = 0; k < AGG_ITEMS; k++) keep[k] = keep[k] && valid[k];
+    }
+    if (op == T_NOTNULL) continue;
+    int c[AGG_ITEMS];
+    if (is_f64) {
+      double x[AGG_ITEMS];
+      load_f64_batch<FULL>(data, type, row0, last, x);
+      const double y = __longlong_as_double(lit);
+#pragma unroll
+      for (int k = 0; k < AGG_ITEMS; k++) {   // SQLOrderingUtil.compareDoubles
+        bool xn = x[k] != x[k], yn = y != y;
+        c[k] = x[k] == y ? 0 : (xn || yn) ? (int)xn - (int)yn : (x[k] < y ? -1 : 1);
+      }
+    } else {
+      int64_t x[AGG_ITEMS];
+      load_i64_batch<FULL>(data, type, row0, last, x);
+#pragma unroll
+      for (int k = 0; k < AGG_ITEMS; k++) c[k] = x[k] == lit ? 0 : (x[k] < lit ? -1 : 1);
+    }
+    switch (op) {   // uniform: one specialised row loop per operator
+#define SB_CMP(COND) _Pragma("unroll") for (int k = 0; k < AGG_ITEMS; k++) keep[k] = keep[k] && (COND);
+      case T_EQ: SB_CMP(c[k] == 0) break;
+      case T_NE: SB_CMP(c[k] != 0) break;
+      case T_LT: SB_CMP(c[k] < 0) break;
+      case T_LE: SB_CMP(c[k] <= 0) break;
+      case T_GT: SB_CMP(c[k] > 0) break;
+      default: SB_CMP(c[k] >= 0) break;
+#undef SB_CMP
+    }
+  }
+}
+
+// value of one factor for the thread's rows: col | lit-col | lit+col | col-lit (mode switch outside the row loop)
+template <bool FULL>
+__device__ __forceinline__ void factor_batch(const Factor &f, int64_t row0, int64_t last, double (&y)[AGG_ITEMS]) {
+  const int32_t mode = f.mode;
+  const double lit = f.lit;
+  load_f64_batch<FULL>(f.data, f.type, row0, last, y);
+  switch (mode) {
+    case F_LIT_MINUS_COL:
+#pragma unroll
+      for (int k = 0; k < AGG_ITEMS; k++) y[k] = __dsub_rn(lit, y[k]);
+      break;
+    case F_LIT_PLUS_COL:
+#pragma unroll
+      for (int k = 0; k < AGG_ITEMS; k++) y[k] = __dadd_rn(lit, y[k]);
+      break;
+    case F_COL_MINUS_LIT:
+#pragma unroll
+      for (int k = 0; k < AGG_ITEMS; k++) y[k] = __dsub_rn(y[k], lit);
+      break;
+    default: break;
+  }
+}
+
+// slot descriptor outer, rows inner.  dst[k] >= 0: HBM table slot; doff[k] >= 0: offset of the row's group in
+// the lane-private shared-memory accumulators (dictionary hit); both negative: row filtered out.
+template <bool FULL>
+__device__ __forceinline__ void accumulate_slots(const AggArgs &a, int64_t row0, const int64_t (&dst)[AGG_ITEMS],
+                                                 const int (&doff)[AGG_ITEMS], uint64_t *acc, int ns, int64_t stride) {
+  const int64_t last = a.n - 1;
+  for (int s = 0; s < ns; s++) {
+    const int kind = a.slot[s].kind, nf = a.slot[s].nf, is_one = a.slot[s].is_one, xform = a.slot[s].xform;
+    uint64_t v[AGG_ITEMS];
+    bool ok[AGG_ITEMS];
+#pragma unroll
+    for (int k = 0; k < AGG_ITEMS; k++) ok[k] = dst[k] >= 0 || doff[k] >= 0;
+    // NULL inputs do not contribute (Sum.scala:113, Count.scala:94)
+    for (int f = 0; f < nf; f++) {
+      const uint8_t *vptr = a.slot[s].f[f].valid;
+      if (vptr) {
+        bool valid[AGG_ITEMS];
+        load_valid_batch<FULL>(vptr, row0, last, valid);
+#pragma unroll
+        for (int k = 0; k < AGG_ITEMS; k++) ok[k] = ok[k] && valid[k];
+      }
+    }
+    if (is_one) {
+#pragma unroll
+      for (int k = 0; k < AGG_ITEMS; k++) v[k] = 1;
+    } else if (kind == K_ADD_F64 || xform == X_DOUBLE) {
+      double y[AGG_ITEMS];
+      factor_batch<FULL>(a.slot[s].f[0], row0, last, y);
+      for (int f = 1; f < nf; f++) {   // left-deep product, evaluated in the reference's order
+        double z[AGG_ITEMS];
+        factor_batch<FULL>(a.slot[s].f[f], row0, last, z);
+#pragma unroll
+        for (int k = 0; k < AGG_ITEMS; k++) y[k] = __dmul_rn(y[k], z[k]);
+      }
+      if (xform == X_DOUBLE) {   // order-preserving bits for min/max, NaN canonical (largest)
+#pragma unroll
+        for (int k = 0; k < AGG_ITEMS; k++) {
+          int64_t b = double_bits_canonical(y[k]);
+          v[k] = (uint64_t)b ^ ((uint64_t)(b >> 63) | 0x8000000000000000ull);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < AGG_ITEMS; k++) v[k] = (uint64_t)__double_as_longlong(y[k]);
+      }
+    } else {
+      int64_t x[AGG_ITEMS];
+      load_i64_batch<FULL>(a.slot[s].f[0].data, a.slot[s].f[0].type, row0, last, x);
+      const uint64_t flip = xform == X_SIGNED ? 0x8000000000000000ull : 0ull;
+#pragma unroll
+      for (int k = 0; k < AGG_ITEMS; k++) v[k] = (uint64_t)x[k] ^ flip;
+    }
+    uint64_t *sacc = acc + (size_t)s * AGG_THREADS;
+    uint64_t *gacc = a.tacc + (int64_t)s * stride;
+    switch (kind) {   // uniform: one specialised row loop per accumulator kind
+#define SB_ACC(LOCAL, GLOBAL)                                          \
+  _Pragma("unroll") for (int k = 0; k < AGG_ITEMS; k++) {              \
+    if (!ok[k]) continue;                                              \
+    if (doff[k] >= 0) { uint64_t *p = sacc + doff[k]; LOCAL; }         \
+    else { uint64_t *p = gacc + dst[k]; GLOBAL; }                      \
+  }
+      case K_ADD_F64:
+        SB_ACC(*(double *)p = __dadd_rn(*(double *)p, __longlong_as_double((int64_t)v[k])),
+               atomicAdd((double *)p, __longlong_as_double((int64_t)v[k])))
+        break;
+      case K_ADD_I64:
+        SB_ACC(*p += v[k], atomicAdd((unsigned long long *)p, (unsigned long long)v[k]))
+        break;
+      case K_MIN_U64:
+        SB_ACC(*p = v[k] < *p ? v[k] : *p, atomicMin((unsigned long long *)p, (unsigned long long)v[k]))
+        break;
+      default:
+        SB_ACC(*p = v[k] > *p ? v[k] : *p, atomicMax((unsigned long long *)p, (unsigned long long)v[k]))
+        break;
+#undef SB_ACC
+    }
+  }
+}
+
+// Branch-free variant used when every kept row of the warp resolved to a dictionary entry: filtered rows and
+// NULL inputs are steered to a "trash" accumulator group (index AGG_DICT), so the row loop is LDS + op + STS.
+template <bool FULL>
+__device__ __forceinline__ void accumulate_slots_dict(const AggArgs &a, int64_t row0, const int (&doff)[AGG_ITEMS], uint64_t *acc,
+                                                      int ns, int trash) {
+  const int64_t last = a.n - 1;
+  for (int s = 0; s < ns; s++) {
+    const int cls = a.slot[s].cls;
+    uint64_t *sacc = acc + (size_t)s * AGG_THREADS;
+    if (cls == CLS_F64_PRODUCT) {
+      const int nf = a.slot[s].nf;
+      double y[AGG_ITEMS];
+      factor_batch<FULL>(a.slot[s].f[0], row0, last, y);
+      for (int f = 1; f < nf; f++) {
+        double z[AGG_ITEMS];
+        factor_batch<FULL>(a.slot[s].f[f], row0, last, z);
+#pragma unroll
+        for (int k = 0; k < AGG_ITEMS; k++) y[k] = __dmul_rn(y[k], z[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < AGG_ITEMS; k++) {
+        double *p = (double *)(sacc + doff[k]);
+        *p = __dadd_rn(*p, y[k]);
+      }
+    } else if (cls == CLS_ONE) {
+#pragma unroll
+      for (int k = 0; k < AGG_ITEMS; k++) sacc[doff[k]] += 1;
+    } else {
+      const int kind = a.slot[s].kind, nf = a.slot[s].nf, is_one = a.slot[s].is_one, xform = a.slot[s].xform;
+      uint64_t v[AGG_ITEMS];
+      int tgt[AGG_ITEMS];
+#pragma unroll
+      for (int k = 0; k < AGG_ITEMS; k++) tgt[k] = doff[k];
+      for (int f = 0; f < nf; f++) {
+        const uint8_t *vptr = a.slot[s].f[f].valid;
+        if (vptr) {
+          bool valid[AGG_ITEMS];
+          load_valid_batch<FULL>(vptr, row0, last, valid);
+#pragma unroll
+          for (int k = 0; k < AGG_ITEMS; k++) tgt[k] = valid[k] ? tgt[k] : trash;
+        }
+      }
+      if (is_one) {
+#pragma unroll
+        for (int k = 0; k < AGG_ITEMS; k++) v[k] = 1;
+      } else if (kind == K_ADD_F64 || xform == X_DOUBLE) {
+        double y[AGG_ITEMS];
+        factor_batch<FULL>(a.slot[s].f[0], row0, last, y);
+        for (int f = 1; f < nf; f++) {
+          double z[AGG_ITEMS];
+          factor_batch<FULL>(a.slot[s].f[f], row0, last, z);
+#pragma unroll
+          for (int k = 0; k < AGG_ITEMS; k++) y[k] = __dmul_rn(y[k], z[k]);
+        }
+        if (xform == X_DOUBLE) {
+#pragma unroll
+          for (int k = 0; k < AGG_ITEMS; k++) {
+            int64_t b = double_bits_canonical(y[k]);
+            v[k] = (uint64_t)b ^ ((uint64_t)(b >> 63) | 0x8000000000000000ull);
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < AGG_ITEMS; k++) v[k] = (uint64_t)__double_as_longlong(y[k]);
+        }
+      } else {
+        int64_t x[AGG_ITEMS];
+        load_i64_batch<FULL>(a.slot[s].f[0].data, a.slot[s].f[0].type, row0, last, x);
+        const uint64_t flip = xform == X_SIGNED ? 0x8000000000000000ull : 0ull;
+#pragma unroll
+        for (int k = 0; k < AGG_ITEMS; k++) v[k] = (uint64_t)x[k] ^ flip;
+      }
+      switch (kind) {
+#define SB_ACCD(EXPR) _Pragma("unroll") for (int k = 0; k < AGG_ITEMS; k++) { uint64_t *p = sacc + tgt[k]; EXPR; }
+        case K_ADD_F64: SB_ACCD(*(double *)p = __dadd_rn(*(double *)p, __longlong_as_double((int64_t)v[k]))) break;
+        case K_ADD_I64: SB_ACCD(*p += v[k]) break;
+        case K_MIN_U64: SB_ACCD(*p = v[k] < *p ? v[k] : *p) break;
+        default: SB_ACCD(*p = v[k] > *p ? v[k] : *p) break;
+#undef SB_ACCD
+      }
+    }
+  }
+}
+
+// Shared memory layout: uint64 dict_keys[AGG_DICT]; uint64 acc[(AGG_DICT + 1) * nslots][AGG_THREADS] (last group = trash)
+template <bool FULL>
+__device__ __forceinline__ void process_tile(const AggArgs &a, int64_t base, int use_dict, uint64_t *dict_keys, uint64_t *acc, int tid,
+                                             int ns, int64_t stride) {
+  const int64_t row0 = base + tid;
+  const int64_t last = a.n - 1;
+  bool keep[AGG_ITEMS];
+  uint64_t key[AGG_ITEMS];
+#pragma unroll
+  for (int k = 0; k < AGG_ITEMS; k++) {
+    keep[k] = FULL || row0 + (int64_t)k * AGG_THREADS < a.n;
+    key[k] = 0;
+  }
+  if (a.mask) {
+    int64_t m[AGG_ITEMS];
+    load_batch_as_i64<FULL, uint8_t>(a.mask, row0, last, m);
+#pragma unroll
+    for (int k = 0; k < AGG_ITEMS; k++) keep[k] = keep[k] && m[k] != 0;
+  }
+  apply_filter_terms<FULL>(a, row0, keep);
+  // ---- group key packing --------------------------------------------------------------------------------
+  int special[AGG_ITEMS];
+#pragma unroll
+  for (int k = 0; k < AGG_ITEMS; k++) special[k] = 0;
+  if (a.single64) {
+    const void *kd = a.key[0].data;
+    const uint8_t *kv = a.key[0].valid;
+    const int32_t kt = a.key[0].type;
+    int64_t x[AGG_ITEMS];
+    load_batch_as_i64<FULL, int64_t>(kd, row0, last, x);      // raw 64-bit words (int64 or double bits)
+    if (kt == SB_FLOAT64) {   // NormalizeFloatingNumbers: -0.0 -> 0.0, NaN canonical
+#pragma unroll
+      for (int k = 0; k < AGG_ITEMS; k++) {
+        double d = __longlong_as_double(x[k]);
+        x[k] = d == 0.0 ? 0ll : double_bits_canonical(d);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < AGG_ITEMS; k++) {
+      key[k] = (uint64_t)x[k];
+      special[k] = key[k] == EMPTY_KEY ? 2 : 0;
+    }
+    if (kv) {
+      bool valid[AGG_ITEMS];
+      load_valid_batch<FULL>(kv, row0, last, valid);
+#pragma unroll
+      for (int k = 0; k < AGG_ITEMS; k++) special[k] = valid[k] ? special[k] : 1;
+    }
+  } else {
+    for (int i = 0; i < a.nkeys; i++) {
+      const void *kd = a.key[i].data;
+      const uint8_t *kv = a.key[i].valid;
+      const int32_t kt = a.key[i].type, bits = a.key[i].bits, shift = a.key[i].shift, nshift = a.key[i].null_shift;
+      int64_t x[AGG_ITEMS];
+      load_i64_batch<FULL>(kd, kt, row0, last, x);
+      if (kt == SB_FLOAT32) {
+#pragma unroll
+        for (int k = 0; k < AGG_ITEMS; k++) {
+          float f = __int_as_float((int32_t)x[k]);
+          x[k] = f == 0.0f ? 0 : (int64_t)(uint32_t)float_bits_canonical(f);
+        }
+      }
+      const uint64_t vmask = bits < 64 ? (1ull << bits) - 1 : ~0ull;
+      if (kv) {
+        bool valid[AGG_ITEMS];
+        load_valid_batch<FULL>(kv, row0, last, valid);
+#pragma unroll
+        for (int k = 0; k < AGG_ITEMS; k++) key[k] |= valid[k] ? ((uint64_t)x[k] & vmask) << shift : 1ull << nshift;
+      } else {
+#pragma unroll
+        for (int k = 0; k < AGG_ITEMS; k++) key[k] |= ((uint64_t)x[k] & vmask) << shift;
+      }
+    }
+  }
+  // ---- where does each row accumulate? ---------------------------------------------------------------------
+  int64_t dst[AGG_ITEMS];
+  int doff[AGG_ITEMS];
+  const int trash = AGG_DICT * ns * AGG_THREADS + tid;
+  bool all_dict = true;
+#pragma unroll
+  for (int k = 0; k < AGG_ITEMS; k++) {
+    dst[k] = -1;
+    doff[k] = -1;
+    if (!keep[k]) continue;
+    int gid = -1;
+    if (use_dict && special[k] == 0) {
+      // linear probing over the AGG_DICT entries starting at a key-dependent entry: a resident key is
+      // normally found by the first probe
+      const uint32_t h0 = (uint32_t)(key[k] ^ (key[k] >> 7) ^ (key[k] >> 17) ^ (key[k] >> 32));
+#pragma unroll 1
+      for (int i = 0; i < AGG_DICT; i++) {
+        const int g = (h0 + i) & (AGG_DICT - 1);
+        uint64_t dk = dict_keys[g];
+        if (dk == EMPTY_KEY) {
+          uint64_t old = atomicCAS((unsigned long long *)&dict_keys[g], (unsigned long long)EMPTY_KEY, (unsigned long long)key[k]);
+          dk = old == EMPTY_KEY ? key[k] : old;
+        }
+        if (dk == key[k]) { gid = g; break; }
+      }
+    }
+    if (gid >= 0) doff[k] = gid * ns * AGG_THREADS + tid;
+    else {
+      dst[k] = table_slot(a, key[k], special[k]);
+      all_dict = false;
+    }
+  }
+  if (use_dict && __all_sync(0xffffffffu, all_dict)) {
+#pragma unroll
+    for (int k = 0; k < AGG_ITEMS; k++) doff[k] = doff[k] >= 0 ? doff[k] : trash;
+    accumulate_slots_dict<FULL>(a, row0, doff, acc, ns, trash);
+  } else {
+    accumulate_slots<FULL>(a, row0, dst, doff, acc, ns, stride);
+  }
+}
+
 __global__ void __launch_bounds__(AGG_THREADS) agg_update_kernel(const __grid_constant__ AggArgs a, int use_dict) {
   extern __shared__ uint64_t sm[];
   uint64_t *dict_keys = sm;
@@ -250,49 +681,16 @@ __global__ void __launch_bounds__(AGG_THREADS) agg_update_kernel(const __grid_co
     if (tid < AGG_DICT) dict_keys[tid] = EMPTY_KEY;
     for (int s = 0; s < ns; s++) {
       uint64_t id = slot_identity(a.slot[s].kind);
-      for (int g = 0; g < AGG_DICT; g++) acc[(g * ns + s) * AGG_THREADS + tid] = id;
+      for (int g = 0; g <= AGG_DICT; g++) acc[(g * ns + s) * AGG_THREADS + tid] = id;
     }
     __syncthreads();
   }
   const int64_t tile = (int64_t)AGG_THREADS * AGG_ITEMS;
+  const int64_t stride = a.cap + 2;
   for (int64_t base = (int64_t)blockIdx.x * tile; base < a.n; base += (int64_t)gridDim.x * tile) {
-    if (a.flags[0]) break;   // another block found the table too small: give up early
-#pragma unroll 2
-    for (int k = 0; k < AGG_ITEMS; k++) {
-      int64_t row = base + (int64_t)k * AGG_THREADS + tid;
-      if (row >= a.n) break;
-      if (!filter_row(a, row)) continue;
-      int special;
-      uint64_t key = pack_key(a, row, special);
-      int gid = -1;
-      if (use_dict && special == 0) {
-#pragma unroll
-        for (int g = 0; g < AGG_DICT; g++) {
-          uint64_t dk = dict_keys[g];
-          if (dk == key) { gid = g; break; }
-          if (dk == EMPTY_KEY) {
-            uint64_t old = atomicCAS((unsigned long long *)&dict_keys[g], (unsigned long long)EMPTY_KEY, (unsigned long long)key);
-            if (old == EMPTY_KEY || old == key) { gid = g; break; }
-          }
-        }
-      }
-      if (gid >= 0) {
-        for (int s = 0; s < ns; s++) {
-          uint64_t v;
-          if (!slot_value(a.slot[s], row, v)) continue;
-          uint64_t *p = &acc[(gid * ns + s) * AGG_THREADS + tid];
-          *p = apply_op(a.slot[s].kind, *p, v);
-        }
-      } else {
-        int64_t slot = table_slot(a, key, special);
-        if (slot < 0) continue;
-        for (int s = 0; s < ns; s++) {
-          uint64_t v;
-          if (!slot_value(a.slot[s], row, v)) continue;
-          global_op(a.slot[s].kind, &a.tacc[(int64_t)s * (a.cap + 2) + slot], v);
-        }
-      }
-    }
+    if (*(volatile int32_t *)a.flags) break;   // another block found the table too small: give up early
+    if (base + tile <= a.n) process_tile<true>(a, base, use_dict, dict_keys, acc, tid, ns, stride);
+    else process_tile<false>(a, base, use_dict, dict_keys, acc, tid, ns, stride);
   }
   if (!use_dict) return;
   __syncthreads();
@@ -309,9 +707,111 @@ __global__ void __launch_bounds__(AGG_THREADS) agg_update_kernel(const __grid_co
     for (int d = 16; d >= 1; d >>= 1) v = apply_op(kind, v, __shfl_xor_sync(0xffffffffu, v, d));
     if (lane == 0) {
       int64_t slot = table_slot(a, key, 0);
-      if (slot >= 0) global_op(kind, &a.tacc[(int64_t)s * (a.cap + 2) + slot], v);
+      if (slot >= 0) global_op(kind, &a.tacc[(int64_t)s * stride + slot], v);
     }
   }
+}
+
+// ---- wide grouping keys (> 63 bits, e.g. Q3's (l_orderkey, o_orderdate, o_shippriority)) -----------------
+// Same row loop, but the key is up to AGG_MAX_WORDS 64-bit words and the HBM table entry is published with a
+// small state machine: 0 empty -> 1 (claimed by atomicCAS, key words being written) -> 2 ready.
+template <int NW>
+__device__ __forceinline__ int64_t table_slot_wide(const AggArgs &a, const uint64_t (&w)[NW]) {
+  const int64_t stride = a.cap + 2;
+  uint64_t mask = (uint64_t)a.cap - 1;
+  uint64_t hh = 0;
+#pragma unroll
+  for (int i = 0; i < NW; i++) hh = mix64(hh ^ w[i]);
+  uint64_t h = hh & mask;
+  volatile uint32_t *state = a.tstate;
+  for (int step = 0; step < AGG_PROBE_LIMIT;) {
+    uint32_t s = state[h];
+    if (s == 0) {
+      if (atomicCAS(&a.tstate[h], 0u, 1u) == 0u) {
+#pragma unroll
+        for (int i = 0; i < NW; i++) a.tkeys[(int64_t)i * stride + h] = w[i];
+        __threadfence();
+        state[h] = 2u;
+        return (int64_t)h;
+      }
+      continue;   // somebody else claimed it: look again
+    }
+    if (s == 1) continue;   // being written
+    __threadfence();
+    bool eq = true;
+#pragma unroll
+    for (int i = 0; i < NW; i++) eq &= ((volatile uint64_t *)a.tkeys)[(int64_t)i * stride + h] == w[i];
+    if (eq) return (int64_t)h;
+    h = (h + 1) & mask;
+    step++;
+  }
+  a.flags[0] = 1;
+  return -1;
+}
+
+template <int NW>
+__global__ void __launch_bounds__(AGG_THREADS) agg_update_wide_kernel(const __grid_constant__ AggArgs a) {
+  const int tid = threadIdx.x;
+  const int ns = a.nslots;
+  const int64_t tile = (int64_t)AGG_THREADS * AGG_ITEMS;
+  const int64_t stride = a.cap + 2;
+  for (int64_t base = (int64_t)blockIdx.x * tile; base < a.n; base += (int64_t)gridDim.x * tile) {
+    if (a.flags[0]) break;
+    const int64_t row0 = base + tid;
+    bool keep[AGG_ITEMS];
+    uint64_t key[AGG_ITEMS][NW];
+    int64_t dst[AGG_ITEMS];
+    int doff[AGG_ITEMS];
+#pragma unroll
+    for (int k = 0; k < AGG_ITEMS; k++) {
+      int64_t row = row0 + (int64_t)k * AGG_THREADS;
+      keep[k] = row < a.n && (a.mask == nullptr || a.mask[row]);
+#pragma unroll
+      for (int i = 0; i < NW; i++) key[k][i] = 0;
+    }
+    apply_filter_terms<false>(a, row0, keep);
+    for (int i = 0; i < a.nkeys; i++) {
+      const KeySrc ks = a.key[i];
+#pragma unroll
+      for (int k = 0; k < AGG_ITEMS; k++) {
+        if (!keep[k]) continue;
+        int64_t row = row0 + (int64_t)k * AGG_THREADS;
+        uint64_t v;
+        int target = ks.word;
+        if (!bit_valid(ks.valid, row)) { v = 1ull << ks.null_shift; target = ks.null_word; }
+        else {
+          if (ks.type == SB_FLOAT32) {
+            float f = ((const float *)ks.data)[row];
+            v = f == 0.0f ? 0u : (uint32_t)float_bits_canonical(f);
+          } else if (ks.type == SB_FLOAT64) {
+            double d = ((const double *)ks.data)[row];
+            v = d == 0.0 ? 0ull : (uint64_t)double_bits_canonical(d);
+          } else {
+            v = (uint64_t)load_i64(ks.data, ks.type, row);
+            if (ks.bits < 64) v &= (1ull << ks.bits) - 1;
+          }
+          v <<= ks.shift;
+        }
+#pragma unroll
+        for (int wi = 0; wi < NW; wi++)
+          if (wi == target) key[k][wi] |= v;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < AGG_ITEMS; k++) {
+      dst[k] = -1;
+      doff[k] = -1;
+      if (!keep[k]) continue;
+      dst[k] = table_slot_wide<NW>(a, key[k]);
+    }
+    accumulate_slots<false>(a, row0, dst, doff, nullptr, ns, stride);
+  }
+}
+
+__global__ void occupied_wide_kernel(const uint32_t *__restrict__ tstate, int64_t cap, uint8_t *__restrict__ occ) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < cap) occ[i] = tstate[i] == 2u;
+  else if (i < cap + 2) occ[i] = 0;
 }
 
 __global__ void fill_u64_kernel(uint64_t *p, int64_t n, uint64_t v) {
@@ -331,7 +831,7 @@ __global__ void occupied_kernel(const uint64_t *__restrict__ tkeys, int64_t cap,
 struct EmitKey {
   void *out;
   uint32_t *out_valid;
-  int32_t type, bits, shift, null_shift;
+  int32_t type, bits, shift, null_shift, word, null_word;
 };
 enum EmitOp { E_RAW = 0, E_SUM_NULLABLE, E_AVG, E_MINMAX };
 struct EmitCol {
@@ -367,7 +867,6 @@ __global__ void __launch_bounds__(256) agg_emit_kernel(const __grid_constant__ E
   int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   bool in_range = r < e.ngroups;
   int64_t slot = in_range ? e.slot_ids[r] : 0;
-  uint64_t key = in_range ? e.tkeys[slot] : 0;
   const int64_t stride = e.cap + 2;
 #pragma unroll 1
   for (int k = 0; k < e.nkeys; k++) {
@@ -375,12 +874,13 @@ __global__ void __launch_bounds__(256) agg_emit_kernel(const __grid_constant__ E
     bool valid = in_range;
     int64_t v = 0;
     if (in_range) {
+      uint64_t key = e.tkeys[(int64_t)ek.word * stride + slot];
       if (e.single64) {
         if (slot == e.cap) valid = false;                       // NULL group key
         else if (slot == e.cap + 1) v = (int64_t)EMPTY_KEY;
         else v = (int64_t)key;
       } else {
-        if (ek.null_shift >= 0 && ((key >> ek.null_shift) & 1)) valid = false;
+        if (ek.null_shift >= 0 && ((e.tkeys[(int64_t)ek.null_word * stride + slot] >> ek.null_shift) & 1)) valid = false;
         else {
           uint64_t u = key >> ek.shift;
           if (ek.bits < 64) {
@@ -671,13 +1171,12 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
     ks.bits = type_width(c.type) * 8;
     total_bits += ks.bits + (c.validity ? 1 : 0);
   }
+  a.nwords = 1;
   if (plan->nkeys == 1 && a.key[0].bits == 64) {
     a.single64 = 1;
     a.key[0].shift = 0;
     a.key[0].null_shift = -1;
-  } else {
-    if (total_bits > 63)
-      fail(SB_ERR_UNSUPPORTED, "grouping keys need %d bits; this build packs at most 63 bits of fixed-width keys", total_bits);
+  } else if (total_bits <= 63) {
     int pos = 0;
     for (int k = 0; k < plan->nkeys; k++) {
       a.key[k].shift = pos;
@@ -685,6 +1184,30 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
       if (a.key[k].valid) a.key[k].null_shift = pos++;
       else a.key[k].null_shift = -1;
     }
+  } else {
+    // wide key: value fields first (a field never straddles words), then the null flags in the free bits
+    int used[AGG_MAX_WORDS + 1] = {0};
+    int nw = 0;
+    for (int k = 0; k < plan->nkeys; k++) {
+      int w = 0;
+      while (w < AGG_MAX_WORDS && used[w] + a.key[k].bits > 64) w++;
+      if (w >= AGG_MAX_WORDS) fail(SB_ERR_UNSUPPORTED, "grouping keys do not fit in %d 64-bit words", AGG_MAX_WORDS);
+      a.key[k].word = w;
+      a.key[k].shift = used[w];
+      used[w] += a.key[k].bits;
+      if (w + 1 > nw) nw = w + 1;
+    }
+    for (int k = 0; k < plan->nkeys; k++) {
+      a.key[k].null_shift = -1;
+      if (!a.key[k].valid) continue;
+      int w = 0;
+      while (w < AGG_MAX_WORDS && used[w] + 1 > 64) w++;
+      if (w >= AGG_MAX_WORDS) fail(SB_ERR_UNSUPPORTED, "grouping keys do not fit in %d 64-bit words", AGG_MAX_WORDS);
+      a.key[k].null_word = w;
+      a.key[k].null_shift = used[w]++;
+      if (w + 1 > nw) nw = w + 1;
+    }
+    a.nwords = nw < 2 ? 2 : nw;
   }
 
   // ---- fused filter ---------------------------------------------------------------------------
@@ -799,6 +1322,16 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
     }
   }
   a.nslots = b.args.nslots;
+  for (int i = 0; i < a.nslots; i++) {
+    SlotSrc &sl = a.slot[i];
+    sl.cls = CLS_GENERIC;
+    if (sl.is_one && sl.nf == 0 && sl.kind == K_ADD_I64) sl.cls = CLS_ONE;
+    if (!sl.is_one && sl.kind == K_ADD_F64 && sl.xform == X_NONE && sl.nf >= 1) {
+      bool plain = true;
+      for (int k = 0; k < sl.nf; k++) plain &= sl.f[k].type == SB_FLOAT64 && sl.f[k].valid == nullptr;
+      if (plain) sl.cls = CLS_F64_PRODUCT;
+    }
+  }
 
   // ---- table sizing + update, retrying with a larger table when probing gives up ---------------
   int64_t cap_max = next_pow2(n > 512 ? 2 * n : 1024);
@@ -806,45 +1339,55 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
   if (cap < 1024) cap = 1024;
   if (cap > cap_max) cap = cap_max;
   const bool use_dict = plan->nkeys > 0 || true;
-  size_t smem = use_dict ? (size_t)(AGG_DICT + (size_t)AGG_DICT * a.nslots * AGG_THREADS) * 8 : 0;
+  size_t smem = use_dict ? (size_t)(AGG_DICT + (size_t)(AGG_DICT + 1) * a.nslots * AGG_THREADS) * 8 : 0;
   static bool attr_set = false;
   if (!attr_set) {
     SB_CUDA(cudaFuncSetAttribute(agg_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
   SB_REQUIRE(smem <= 200 * 1024, "aggregate needs %zu bytes of shared memory", smem);
-  int blocks_per_sm = smem ? (int)((220 * 1024) / (smem + 1024)) : 8;
+  int blocks_per_sm = smem ? (int)((227 * 1024) / (smem + 1024)) : 8;
   if (blocks_per_sm < 1) blocks_per_sm = 1;
   if (blocks_per_sm > 8) blocks_per_sm = 8;
   int grid = grid_for(n, AGG_THREADS * AGG_ITEMS, rt().num_sms * blocks_per_sm);
 
   Scratch flags(16, st);
-  void *tkeys = nullptr, *tacc = nullptr;
+  void *tkeys = nullptr, *tacc = nullptr, *tstate = nullptr;
   struct TableFree {
-    void *&k, *&v;
+    void *&k, *&v, *&s;
     cudaStream_t st;
     ~TableFree() {
       if (k) cudaFreeAsync(k, st);
       if (v) cudaFreeAsync(v, st);
+      if (s) cudaFreeAsync(s, st);
     }
-  } table_free_guard{tkeys, tacc, st};
+  } table_free_guard{tkeys, tacc, tstate, st};
 
   for (;;) {
     int64_t slots = cap + 2;
-    SB_CUDA(cudaMallocAsync(&tkeys, (size_t)slots * 8, st));
+    SB_CUDA(cudaMallocAsync(&tkeys, (size_t)slots * 8 * a.nwords, st));
     SB_CUDA(cudaMallocAsync(&tacc, (size_t)slots * 8 * (a.nslots ? a.nslots : 1), st));
-    SB_CUDA(cudaMemsetAsync(tkeys, 0xff, (size_t)slots * 8, st));
+    if (a.nwords > 1) {
+      SB_CUDA(cudaMallocAsync(&tstate, (size_t)slots * 4, st));
+      SB_CUDA(cudaMemsetAsync(tstate, 0, (size_t)slots * 4, st));
+    } else {
+      SB_CUDA(cudaMemsetAsync(tkeys, 0xff, (size_t)slots * 8, st));
+    }
     SB_CUDA(cudaMemsetAsync(tacc, 0, (size_t)slots * 8 * (a.nslots ? a.nslots : 1), st));
     for (int s = 0; s < a.nslots; s++)
       if (a.slot[s].kind == K_MIN_U64) SB_CUDA(cudaMemsetAsync((uint64_t *)tacc + (int64_t)s * slots, 0xff, (size_t)slots * 8, st));
     SB_CUDA(cudaMemsetAsync(flags.ptr, 0, 16, st));
     a.tkeys = (uint64_t *)tkeys;
+    a.tstate = (uint32_t *)tstate;
     a.tacc = (uint64_t *)tacc;
     a.flags = flags.as<int32_t>();
     a.cap = cap;
     if (n > 0) {
       KernelTimer kt(final_mode ? "agg_update_final" : "agg_update", st);
-      agg_update_kernel<<<grid, AGG_THREADS, smem, st>>>(a, use_dict ? 1 : 0);
+      if (a.nwords == 1) agg_update_kernel<<<grid, AGG_THREADS, smem, st>>>(a, use_dict ? 1 : 0);
+      else if (a.nwords == 2) agg_update_wide_kernel<2><<<grid, AGG_THREADS, 0, st>>>(a);
+      else if (a.nwords == 3) agg_update_wide_kernel<3><<<grid, AGG_THREADS, 0, st>>>(a);
+      else agg_update_wide_kernel<4><<<grid, AGG_THREADS, 0, st>>>(a);
       SB_LAUNCH_CHECK();
     }
     int32_t hflags[4];
@@ -854,6 +1397,7 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
     if (cap >= cap_max) fail(SB_ERR_CUDA, "hash aggregate table overflow at maximum capacity %lld", (long long)cap);
     cudaFreeAsync(tkeys, st); tkeys = nullptr;
     cudaFreeAsync(tacc, st); tacc = nullptr;
+    if (tstate) { cudaFreeAsync(tstate, st); tstate = nullptr; }
     cap = cap * 16 > cap_max ? cap_max : cap * 16;
   }
 
@@ -874,7 +1418,8 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
     }
   } else {
     Scratch occ(slots + 16, st);
-    occupied_kernel<<<(unsigned)((slots + 255) / 256), 256, 0, st>>>((uint64_t *)tkeys, cap, flags.as<int32_t>(), occ.as<uint8_t>());
+    if (a.nwords > 1) occupied_wide_kernel<<<(unsigned)((slots + 255) / 256), 256, 0, st>>>((uint32_t *)tstate, cap, occ.as<uint8_t>());
+    else occupied_kernel<<<(unsigned)((slots + 255) / 256), 256, 0, st>>>((uint64_t *)tkeys, cap, flags.as<int32_t>(), occ.as<uint8_t>());
     SB_LAUNCH_CHECK();
     ngroups = compact_mask(occ.as<uint8_t>(), slots, slot_ids.as<int64_t>(), st);
   }
@@ -901,6 +1446,8 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
       e.key[k].bits = a.key[k].bits;
       e.key[k].shift = a.key[k].shift;
       e.key[k].null_shift = a.key[k].null_shift;
+      e.key[k].word = a.key[k].word;
+      e.key[k].null_word = a.key[k].null_word;
     }
     SB_REQUIRE(outs.size() <= 2 * AGG_MAX_SLOTS, "too many aggregate output columns");
     e.ncols = (int)outs.size();

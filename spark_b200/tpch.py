@@ -189,3 +189,47 @@ def nation_table() -> pa.Table:
 
 def region_table() -> pa.Table:
     return pa.table({"r_regionkey": np.arange(5, dtype=np.int64), "r_name": np.arange(5, dtype=np.int32)})
+
+
+# ------------------------------------------------------------------------------------------ Q3 / Q5 plans
+def q3_plan(customer: SparkPlan, orders: SparkPlan, lineitem: SparkPlan, partial_final: bool = True) -> SparkPlan:
+    """q3.sql as a physical plan.  Shape follows tpch-plan-stability/q3/simplified.txt (two hash joins feeding a
+    Partial/Final aggregate and TakeOrderedAndProject); the build sides are the filtered customer and the
+    customer-filtered orders (the golden plan's no-statistics choice of lineitem as a broadcast side is a
+    planner decision, not a semantic one: inner joins commute)."""
+    from .execution import BroadcastHashJoinExec, TakeOrderedAndProjectExec
+    from .expressions import SortOrder
+    cust = ProjectExec(["c_custkey"], FilterExec(col("c_mktsegment").eq(Literal(Q3_SEGMENT)), customer))
+    ord_f = FilterExec(col("o_orderdate") < Literal(Q3_DATE), orders)
+    j1 = BroadcastHashJoinExec(["o_custkey"], ["c_custkey"], "inner", "right", ord_f, cust)
+    j1p = ProjectExec(["o_orderkey", "o_orderdate", "o_shippriority"], j1)
+    li = ProjectExec(["l_orderkey", "l_extendedprice", "l_discount"], FilterExec(col("l_shipdate") > Literal(Q3_DATE), lineitem))
+    j2 = BroadcastHashJoinExec(["l_orderkey"], ["o_orderkey"], "inner", "right", li, j1p)
+    keys = ["l_orderkey", "o_orderdate", "o_shippriority"]
+    aggs = [(Sum(col("l_extendedprice") * (Literal(1) - col("l_discount"))), "revenue")]
+    if partial_final:
+        agg = HashAggregateExec(keys, aggs, HashAggregateExec(keys, aggs, j2, mode="partial"), mode="final")
+    else:
+        agg = HashAggregateExec(keys, aggs, j2, mode="complete")
+    return TakeOrderedAndProjectExec(10, [SortOrder("revenue", False), SortOrder("o_orderdate", True)],
+                                     ["l_orderkey", "revenue", "o_orderdate", "o_shippriority"], agg)
+
+
+def q5_plan(customer, orders, lineitem, supplier, nation, region) -> SparkPlan:
+    """q5.sql: six-way join, filter on region and order date, group by nation name, order by revenue desc."""
+    from .execution import BroadcastHashJoinExec
+    reg = ProjectExec(["r_regionkey"], FilterExec(col("r_name").eq(Literal(Q5_REGION)), region))
+    nat = ProjectExec(["n_nationkey", "n_name"], BroadcastHashJoinExec(["n_regionkey"], ["r_regionkey"], "inner", "right", nation, reg))
+    sup = ProjectExec(["s_suppkey", "s_nationkey", "n_name"],
+                      BroadcastHashJoinExec(["s_nationkey"], ["n_nationkey"], "inner", "right", supplier, nat))
+    ord_f = FilterExec((col("o_orderdate") >= Literal(Q5_DATE_LO)) & (col("o_orderdate") < Literal(Q5_DATE_HI)), orders)
+    oc = ProjectExec(["o_orderkey", "c_nationkey"],
+                     BroadcastHashJoinExec(["o_custkey"], ["c_custkey"], "inner", "right", ord_f, ProjectExec(["c_custkey", "c_nationkey"], customer)))
+    lo = ProjectExec(["l_suppkey", "c_nationkey", "l_extendedprice", "l_discount"],
+                     BroadcastHashJoinExec(["l_orderkey"], ["o_orderkey"], "inner", "right",
+                                           ProjectExec(["l_orderkey", "l_suppkey", "l_extendedprice", "l_discount"], lineitem), oc))
+    los = BroadcastHashJoinExec(["l_suppkey"], ["s_suppkey"], "inner", "right", lo, sup)
+    same_nation = FilterExec(col("c_nationkey").eq(col("s_nationkey")), los)     # c_nationkey = s_nationkey (second join key)
+    aggs = [(Sum(col("l_extendedprice") * (Literal(1) - col("l_discount"))), "revenue")]
+    agg = HashAggregateExec(["n_name"], aggs, HashAggregateExec(["n_name"], aggs, same_nation, mode="partial"), mode="final")
+    return SortExec([("revenue", False, False)], agg)

@@ -27,7 +27,7 @@ def _mixed_table(n, seed=42, nulls=True):
         "f64": maybe(f),
         "b": maybe(rng.integers(0, 2, n).astype(bool)),
         "d": maybe(rng.integers(0, 20000, n).astype(np.int32)).cast(pa.date32()),
-        "s": pa.array([None if (nulls and rng.random() < 0.1) else strs[i] for i in rng.integers(0, len(strs), n)]),
+        "s": pa.array([None if (nulls and rng.random() < 0.1) else strs[i] for i in rng.integers(0, len(strs), n)], type=pa.string()),
         "row": np.arange(n, dtype=np.int64),
     })
 
