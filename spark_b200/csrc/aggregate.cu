@@ -25,798 +25,74 @@
 // Floating SUM/AVG are order-dependent in the reference too (partials merge in fetch order); parity is
 // 1e-6 relative for them, exact for keys/counts/integer sums/min/max.
 #include <math.h>
-#include "common.cuh"
+#include <stdlib.h>
+#include "agg_kernels.cuh"
 #include "expr.cuh"
 #include "primitives.cuh"
 
 namespace sb {
 
-constexpr int AGG_THREADS = 128;
-constexpr int AGG_ITEMS = 8;
-constexpr int AGG_DICT = 8;          // tier-1 dictionary entries per block
-constexpr int AGG_MAX_SLOTS = 16;
-constexpr int AGG_MAX_KEYS = 6;
-constexpr int AGG_MAX_WORDS = 4;
-constexpr int AGG_MAX_TERMS = 4;
-constexpr int AGG_MAX_FACT = 3;
-constexpr int AGG_PROBE_LIMIT = 64;
-constexpr uint64_t EMPTY_KEY = 0xFFFFFFFFFFFFFFFFull;
+// ---- pre-specialised plans ------------------------------------------------------------------------------------------
+// A plan whose PlanMeta equals one of these tables runs the StaticPlan instantiation (descriptor loops unrolled, type /
+// mode / kind switches folded at compile time); every other plan runs DynPlan.  The tables only describe *shapes*:
+// "one int32-class <= term, two non-null int8 keys, double sums of col / col*(lit-col) / col*(lit-col)*(lit+col), a
+// counter" -- which is the shape of TPC-H Q1's partial aggregate, whatever the column names, literals or data.
+#define SB_F64 SB_FLOAT64
+#define SB_META_Q1_PARTIAL                                                                                              \
+  {                                                                                                                     \
+    /* has_mask, nterms, single64, nkeys, nslots, pad */ 0, 1, 0, 2, 6, 0,                                              \
+    /* term_type */ {SB_DATE32, 0, 0, 0}, /* term_op */ {T_LE, 0, 0, 0}, /* term_f64 */ {0, 0, 0, 0}, /* term_valid */ {0, 0, 0, 0}, \
+    /* key_type */ {SB_INT8, SB_INT8, 0, 0, 0, 0}, /* key_bits */ {8, 8, 0, 0, 0, 0}, /* key_shift */ {0, 8, 0, 0, 0, 0}, \
+    /* key_nshift */ {-1, -1, 0, 0, 0, 0}, /* key_valid */ {0, 0, 0, 0, 0, 0},                                           \
+    /* slot_kind */ {K_ADD_F64, K_ADD_F64, K_ADD_F64, K_ADD_F64, K_ADD_I64, K_ADD_F64},                                  \
+    /* slot_nf */ {1, 1, 2, 3, 0, 1}, /* slot_one */ {0, 0, 0, 0, 1, 0}, /* slot_xform */ {0},                           \
+    /* slot_cls */ {CLS_F64_PRODUCT, CLS_F64_PRODUCT, CLS_F64_PRODUCT, CLS_F64_PRODUCT, CLS_ONE, CLS_F64_PRODUCT},        \
+    /* slot_anyvalid */ {0},                                                                                            \
+    /* f_type */ {{SB_F64, 0, 0}, {SB_F64, 0, 0}, {SB_F64, SB_F64, 0}, {SB_F64, SB_F64, SB_F64}, {0, 0, 0}, {SB_F64, 0, 0}}, \
+    /* f_mode */ {{F_COL, 0, 0}, {F_COL, 0, 0}, {F_COL, F_LIT_MINUS_COL, 0}, {F_COL, F_LIT_MINUS_COL, F_LIT_PLUS_COL}, {0, 0, 0}, {F_COL, 0, 0}}, \
+    /* f_valid */ {{0}}                                                                                                 \
+  }
+__device__ const PlanMeta kDevMetaQ1Partial = SB_META_Q1_PARTIAL;
+static const PlanMeta kHostMetaQ1Partial = SB_META_Q1_PARTIAL;
+// the group-by-one-int64-key, sum-one-column shape of BASELINE.json configs[0] (k int64, v int64 / double, no NULLs)
+#define SB_META_C1(VKIND, VTYPE, VCLS)                                                                                  \
+  {                                                                                                                     \
+    0, 0, 1, 1, 1, 0, {0}, {0}, {0}, {0}, {SB_INT64, 0, 0, 0, 0, 0}, {64, 0, 0, 0, 0, 0}, {0}, {-1, 0, 0, 0, 0, 0}, {0}, \
+    {VKIND}, {1}, {0}, {0}, {VCLS}, {0}, {{VTYPE, 0, 0}}, {{F_COL, 0, 0}}, {{0}}                                         \
+  }
+__device__ const PlanMeta kDevMetaC1I64 = SB_META_C1(K_ADD_I64, SB_INT64, CLS_GENERIC);
+static const PlanMeta kHostMetaC1I64 = SB_META_C1(K_ADD_I64, SB_INT64, CLS_GENERIC);
+__device__ const PlanMeta kDevMetaC1F64 = SB_META_C1(K_ADD_F64, SB_FLOAT64, CLS_F64_PRODUCT);
+static const PlanMeta kHostMetaC1F64 = SB_META_C1(K_ADD_F64, SB_FLOAT64, CLS_F64_PRODUCT);
 
-enum SlotKind { K_ADD_I64 = 0, K_ADD_F64 = 1, K_MIN_U64 = 2, K_MAX_U64 = 3 };
-enum ValXform { X_NONE = 0, X_SIGNED = 1, X_DOUBLE = 2 };   // value -> order-preserving u64 for min/max
-enum FactorMode { F_COL = 0, F_LIT_MINUS_COL = 1, F_LIT_PLUS_COL = 2, F_COL_MINUS_LIT = 3 };
-enum SlotClass { CLS_GENERIC = 0, CLS_ONE = 1, CLS_F64_PRODUCT = 2 };   // ONE: count(*) ; F64_PRODUCT: non-null double factors
-enum TermOp { T_EQ = 0, T_NE, T_LT, T_LE, T_GT, T_GE, T_NOTNULL };
+constexpr int ITEMS_DIRECT = 8;   // rows per thread per tile, direct path (1024-row tiles)
+constexpr int ITEMS_STAGED = 4;   // staged path (512-row tiles keep two blocks per SM resident)
 
-struct Factor {
-  const void *data;
-  const uint8_t *valid;
-  int32_t type;
-  int32_t mode;
-  double lit;
+typedef void (*AggKernel)(const AggArgs);
+struct KernelChoice {
+  AggKernel direct, staged;
+  int items_direct;
+  const char *name;
 };
-struct SlotSrc {
-  int32_t kind;      // SlotKind
-  int32_t nf;        // number of factors (0 = constant one)
-  int32_t is_one;    // value is 1 when every factor column is non-null (COUNT)
-  int32_t xform;     // ValXform for min/max
-  int32_t cls;       // SlotClass, precomputed on the host so the kernel takes ONE uniform branch per slot
-  int32_t pad;
-  Factor f[AGG_MAX_FACT];
-};
-struct KeySrc {
-  const void *data;
-  const uint8_t *valid;
-  int32_t type;
-  int32_t bits;      // value bits
-  int32_t shift;     // position in the packed word
-  int32_t null_shift;  // bit position of the null flag or -1
-  int32_t word;      // which 64-bit key word holds the value (wide keys)
-  int32_t null_word; // which word holds the null flag
-};
-struct FilterTerm {
-  const void *data;
-  const uint8_t *valid;
-  int32_t type;
-  int32_t op;
-  int64_t lit;       // int64 value or double bits
-  int32_t is_f64;
-  int32_t pad;
-};
-struct AggArgs {
-  int64_t n;
-  int32_t nkeys, single64, nterms, nslots;
-  KeySrc key[AGG_MAX_KEYS];
-  FilterTerm term[AGG_MAX_TERMS];
-  const uint8_t *mask;   // optional materialised predicate (1 byte / row)
-  SlotSrc slot[AGG_MAX_SLOTS];
-  int32_t nwords, pad0;  // 1 = packed single word; 2..AGG_MAX_WORDS = wide keys (lock-protocol table)
-  uint32_t *tstate;      // wide keys only: [cap] 0 empty, 1 being written, 2 ready
-  uint64_t *tkeys;       // [nwords][cap + 2]   slot cap = NULL key, slot cap+1 = key equal to the EMPTY sentinel
-  uint64_t *tacc;        // [nslots][cap + 2]
-  int32_t *flags;        // [0] abort (table too small), [1] NULL-key slot used, [2] sentinel-key slot used
-  int64_t cap;
-};
-
-__device__ __forceinline__ uint64_t slot_identity(int kind) {
-  return kind == K_MIN_U64 ? 0xFFFFFFFFFFFFFFFFull : 0ull;
-}
-
-__device__ __forceinline__ double factor_value(const Factor &f, int64_t row) {
-  double x;
-  switch (f.type) {
-    case SB_FLOAT64: x = ((const double *)f.data)[row]; break;
-    case SB_FLOAT32: x = (double)((const float *)f.data)[row]; break;
-    default: x = (double)load_i64(f.data, f.type, row); break;
-  }
-  switch (f.mode) {
-    case F_LIT_MINUS_COL: return __dsub_rn(f.lit, x);
-    case F_LIT_PLUS_COL: return __dadd_rn(f.lit, x);
-    case F_COL_MINUS_LIT: return __dsub_rn(x, f.lit);
-    default: return x;
-  }
-}
-
-// value of one accumulator slot for a row; returns false when the row does not contribute (NULL input)
-__device__ __forceinline__ bool slot_value(const SlotSrc &s, int64_t row, uint64_t &out) {
-#pragma unroll
-  for (int k = 0; k < AGG_MAX_FACT; k++)
-    if (k < s.nf && !bit_valid(s.f[k].valid, row)) return false;
-  if (s.is_one) {
-    out = 1;
-    return true;
-  }
-  if (s.kind == K_ADD_F64 || s.xform == X_DOUBLE) {
-    double v = factor_value(s.f[0], row);
-    if (s.nf > 1) v = __dmul_rn(v, factor_value(s.f[1], row));
-    if (s.nf > 2) v = __dmul_rn(v, factor_value(s.f[2], row));
-    if (s.xform == X_DOUBLE) {   // order-preserving bits, NaN canonical (largest)
-      int64_t b = double_bits_canonical(v);
-      out = (uint64_t)b ^ ((uint64_t)(b >> 63) | 0x8000000000000000ull);
-    } else {
-      out = (uint64_t)__double_as_longlong(v);
+static KernelChoice choose_kernels(const PlanMeta &m) {
+  if (getenv("SB_AGG_DISABLE_STATIC") == nullptr) {
+    const char *v = getenv("SB_AGG_Q1_VARIANT");   // tuning knob: "8" | "8p" | "4" | "4p" (rows per thread, p = L2 prefetch)
+    if (memcmp(&m, &kHostMetaQ1Partial, sizeof(PlanMeta)) == 0) {
+      AggKernel st = agg_update_staged_kernel<StaticPlan<&kDevMetaQ1Partial>, ITEMS_STAGED>;
+      if (v && strcmp(v, "8") == 0) return {agg_update_kernel<StaticPlan<&kDevMetaQ1Partial>, 8, false>, st, 8, "static:q1_partial/8"};
+      if (v && strcmp(v, "8p") == 0) return {agg_update_kernel<StaticPlan<&kDevMetaQ1Partial>, 8, true>, st, 8, "static:q1_partial/8p"};
+      if (v && strcmp(v, "4p") == 0) return {agg_update_kernel<StaticPlan<&kDevMetaQ1Partial>, 4, true>, st, 4, "static:q1_partial/4p"};
+      if (v && strcmp(v, "4") == 0) return {agg_update_kernel<StaticPlan<&kDevMetaQ1Partial>, 4, false>, st, 4, "static:q1_partial/4"};
+      return {agg_update_kernel<StaticPlan<&kDevMetaQ1Partial>, 8, true>, st, 8, "static:q1_partial/8p"};
     }
-    return true;
+    if (memcmp(&m, &kHostMetaC1I64, sizeof(PlanMeta)) == 0)
+      return {agg_update_kernel<StaticPlan<&kDevMetaC1I64>, ITEMS_DIRECT>, agg_update_staged_kernel<StaticPlan<&kDevMetaC1I64>, ITEMS_STAGED>,
+              ITEMS_DIRECT, "static:groupby_i64_sum_i64"};
+    if (memcmp(&m, &kHostMetaC1F64, sizeof(PlanMeta)) == 0)
+      return {agg_update_kernel<StaticPlan<&kDevMetaC1F64>, ITEMS_DIRECT>, agg_update_staged_kernel<StaticPlan<&kDevMetaC1F64>, ITEMS_STAGED>,
+              ITEMS_DIRECT, "static:groupby_i64_sum_f64"};
   }
-  int64_t v = load_i64(s.f[0].data, s.f[0].type, row);
-  out = s.xform == X_SIGNED ? ((uint64_t)v ^ 0x8000000000000000ull) : (uint64_t)v;
-  return true;
-}
-
-__device__ __forceinline__ uint64_t apply_op(int kind, uint64_t acc, uint64_t v) {
-  switch (kind) {
-    case K_ADD_I64: return acc + v;
-    case K_ADD_F64: return (uint64_t)__double_as_longlong(__dadd_rn(__longlong_as_double((int64_t)acc), __longlong_as_double((int64_t)v)));
-    case K_MIN_U64: return v < acc ? v : acc;
-    default: return v > acc ? v : acc;
-  }
-}
-
-__device__ __forceinline__ void global_op(int kind, uint64_t *addr, uint64_t v) {
-  switch (kind) {
-    case K_ADD_I64: atomicAdd((unsigned long long *)addr, (unsigned long long)v); break;
-    case K_ADD_F64: atomicAdd((double *)addr, __longlong_as_double((int64_t)v)); break;
-    case K_MIN_U64: atomicMin((unsigned long long *)addr, (unsigned long long)v); break;
-    default: atomicMax((unsigned long long *)addr, (unsigned long long)v); break;
-  }
-}
-
-__device__ __forceinline__ bool filter_row(const AggArgs &a, int64_t row) {
-  if (a.mask && !a.mask[row]) return false;
-#pragma unroll
-  for (int t = 0; t < AGG_MAX_TERMS; t++) {
-    if (t >= a.nterms) break;
-    const FilterTerm &ft = a.term[t];
-    if (!bit_valid(ft.valid, row)) return false;      // NULL comparison -> row dropped
-    if (ft.op == T_NOTNULL) continue;
-    int c;
-    if (ft.is_f64) {
-      double x = ft.type == SB_FLOAT32 ? (double)((const float *)ft.data)[row] : ((const double *)ft.data)[row];
-      double y = __longlong_as_double(ft.lit);
-      if (x == y) c = 0;
-      else {
-        bool xn = x != x, yn = y != y;
-        c = (xn || yn) ? (int)xn - (int)yn : (x < y ? -1 : 1);
-      }
-    } else {
-      int64_t x = load_i64(ft.data, ft.type, row);
-      c = x == ft.lit ? 0 : (x < ft.lit ? -1 : 1);
-    }
-    bool ok = ft.op == T_EQ ? c == 0 : ft.op == T_NE ? c != 0 : ft.op == T_LT ? c < 0 : ft.op == T_LE ? c <= 0
-              : ft.op == T_GT ? c > 0 : c >= 0;
-    if (!ok) return false;
-  }
-  return true;
-}
-
-// group key of a row packed into one word.  special: 0 = regular key, 1 = NULL key of a single
-// 64-bit column, 2 = a 64-bit key whose value equals the EMPTY sentinel.
-__device__ __forceinline__ uint64_t pack_key(const AggArgs &a, int64_t row, int &special) {
-  special = 0;
-  if (a.single64) {
-    const KeySrc &k = a.key[0];
-    if (!bit_valid(k.valid, row)) { special = 1; return 0; }
-    uint64_t v;
-    if (k.type == SB_FLOAT64) {      // NormalizeFloatingNumbers: -0.0 -> 0.0, NaN canonical
-      double d = ((const double *)k.data)[row];
-      v = d == 0.0 ? 0ull : (uint64_t)double_bits_canonical(d);
-    } else v = (uint64_t)((const int64_t *)k.data)[row];
-    if (v == EMPTY_KEY) special = 2;
-    return v;
-  }
-  uint64_t w = 0;
-#pragma unroll
-  for (int i = 0; i < AGG_MAX_KEYS; i++) {
-    if (i >= a.nkeys) break;
-    const KeySrc &k = a.key[i];
-    if (!bit_valid(k.valid, row)) { w |= 1ull << k.null_shift; continue; }
-    uint64_t v;
-    if (k.type == SB_FLOAT32) {
-      float f = ((const float *)k.data)[row];
-      v = f == 0.0f ? 0u : (uint32_t)float_bits_canonical(f);
-    } else {
-      v = (uint64_t)load_i64(k.data, k.type, row);
-      if (k.bits < 64) v &= (1ull << k.bits) - 1;
-    }
-    w |= v << k.shift;
-  }
-  return w;
-}
-
-__device__ __forceinline__ uint64_t mix64(uint64_t x) {   // slot choice only; not contractual
-  x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
-  return x;
-}
-
-// find-or-insert in the HBM table; returns slot index or -1 (abort: table too small)
-__device__ __forceinline__ int64_t table_slot(const AggArgs &a, uint64_t key, int special) {
-  if (special == 1) { a.flags[1] = 1; return a.cap; }
-  if (special == 2) { a.flags[2] = 1; return a.cap + 1; }
-  uint64_t mask = (uint64_t)a.cap - 1;
-  uint64_t h = mix64(key) & mask;
-  for (int step = 0; step < AGG_PROBE_LIMIT; step++) {
-    uint64_t cur = a.tkeys[h];
-    if (cur == key) return (int64_t)h;
-    if (cur == EMPTY_KEY) {
-      uint64_t old = atomicCAS((unsigned long long *)&a.tkeys[h], (unsigned long long)EMPTY_KEY, (unsigned long long)key);
-      if (old == EMPTY_KEY || old == key) return (int64_t)h;
-    }
-    h = (h + 1) & mask;
-  }
-  a.flags[0] = 1;
-  return -1;
-}
-
-constexpr int64_t DST_SKIP = INT64_MIN;
-
-// ---------------------------------------------------------------------------------------------------------
-// Tile processing.  A thread owns AGG_ITEMS rows of a tile (row = row0 + k*AGG_THREADS, coalesced per k).
-// Rules that keep the instruction count per row low (first profile: 524 thread-instructions per row, 12% BRA,
-// 12% BSSY/BSYNC -- see profiles/r01_agg_update.md):
-//   * every descriptor (filter term, key column, accumulator slot) is read from the parameter bank once per
-//     tile, and every warp-uniform decision (column type, factor mode, accumulator kind) is taken OUTSIDE the
-//     unrolled row loop;
-//   * FULL tiles use unclamped loads, so the AGG_ITEMS loads of a column are LDG [base + k*stride] with
-//     immediate offsets and are all in flight together; only the last partial tile clamps the row index.
-// ---------------------------------------------------------------------------------------------------------
-template <bool FULL, typename T>
-__device__ __forceinline__ void load_batch_as_i64(const void *__restrict__ data, int64_t row0, int64_t last, int64_t (&out)[AGG_ITEMS]) {
-  const T *p = (const T *)data + row0;
-#pragma unroll
-  for (int k = 0; k < AGG_ITEMS; k++) {
-    if (FULL) out[k] = (int64_t)p[k * AGG_THREADS];
-    else {
-      int64_t r = row0 + (int64_t)k * AGG_THREADS;
-      out[k] = (int64_t)((const T *)data)[r < last ? r : last];
-    }
-  }
-}
-template <bool FULL>
-__device__ __forceinline__ void load_i64_batch(const void *__restrict__ data, int32_t type, int64_t row0, int64_t last,
-                                               int64_t (&out)[AGG_ITEMS]) {
-  switch (type) {
-    case SB_BOOL: load_batch_as_i64<FULL, uint8_t>(data, row0, last, out); break;
-    case SB_INT8: load_batch_as_i64<FULL, int8_t>(data, row0, last, out); break;
-    case SB_INT16: load_batch_as_i64<FULL, int16_t>(data, row0, last, out); break;
-    case SB_INT32: case SB_DATE32: case SB_FLOAT32: load_batch_as_i64<FULL, int32_t>(data, row0, last, out); break;
-    default: load_batch_as_i64<FULL, int64_t>(data, row0, last, out); break;
-  }
-}
-template <bool FULL>
-__device__ __forceinline__ void load_f64_batch(const void *__restrict__ data, int32_t type, int64_t row0, int64_t last,
-                                               double (&out)[AGG_ITEMS]) {
-  if (type == SB_FLOAT64) {
-    const double *p = (const double *)data + row0;
-#pragma unroll
-    for (int k = 0; k < AGG_ITEMS; k++) {
-      if (FULL) out[k] = p[k * AGG_THREADS];
-      else {
-        int64_t r = row0 + (int64_t)k * AGG_THREADS;
-        out[k] = ((const double *)data)[r < last ? r : last];
-      }
-    }
-  } else {
-    int64_t t[AGG_ITEMS];
-    load_i64_batch<FULL>(data, type, row0, last, t);
-    if (type == SB_FLOAT32) {
-#pragma unroll
-      for (int k = 0; k < AGG_ITEMS; k++) out[k] = (double)__int_as_float((int32_t)t[k]);
-    } else {
-#pragma unroll
-      for (int k = 0; k < AGG_ITEMS; k++) out[k] = (double)t[k];
-    }
-  }
-}
-// validity bits of the AGG_ITEMS rows; the caller skips this entirely when the column has no bitmap
-template <bool FULL>
-__device__ __forceinline__ void load_valid_batch(const uint8_t *__restrict__ valid, int64_t row0, int64_t last, bool (&out)[AGG_ITEMS]) {
-  uint8_t b[AGG_ITEMS];
-#pragma unroll
-  for (int k = 0; k < AGG_ITEMS; k++) {
-    int64_t r = row0 + (int64_t)k * AGG_THREADS;
-    if (!FULL) r = r < last ? r : last;
-    b[k] = valid[r >> 3];
-  }
-#pragma unroll
-  for (int k = 0; k < AGG_ITEMS; k++) {
-    int64_t r = row0 + (int64_t)k * AGG_THREADS;
-    if (!FULL) r = r < last ? r : last;
-    out[k] = (b[k] >> (r & 7)) & 1;
-  }
-}
-
-
-
-// fused FilterExec: conjunction of column-vs-literal terms, applied to the thread's AGG_ITEMS rows
-template <bool FULL>
-__device__ __forceinline__ void apply_filter_terms(const AggArgs &a, int64_t row0, bool (&keep)[AGG_ITEMS]) {
-  const int64_t last = a.n - 1;
-  for (int t = 0; t < a.nterms; t++) {
-    const void *data = a.term[t].data;
-    const uint8_t *vptr = a.term[t].valid;
-    const int32_t type = a.term[t].type, op = a.term[t].op, is_f64 = a.term[t].is_f64;
-    const int64_t lit = a.term[t].lit;
-    if (vptr) {   // a NULL comparison drops the row
-      bool valid[AGG_ITEMS];
-      load_valid_batch<FULL>(vptr, row0, last, valid);
-#pragma unroll
-      for (int k = 0; k < AGG_ITEMS; k++) keep[k] = keep[k] && valid[k];
-    }
-    if (op == T_NOTNULL) continue;
-    int c[AGG_ITEMS];
-    if (is_f64) {
-      double x[AGG_ITEMS];
-      load_f64_batch<FULL>(data, type, row0, last, x);
-      const double y = __longlong_as_double(lit);
-#pragma unroll
-      for (int k = 0; k < AGG_ITEMS; k++) {   // SQLOrderingUtil.compareDoubles
-        bool xn = x[k] != x[k], yn = y != y;
-        c[k] = x[k] == y ? 0 : (xn || yn) ? (int)xn - (int)yn : (x[k] < y ? -1 : 1);
-      }
-    } else {
-      int64_t x[AGG_ITEMS];
-      load_i64_batch<FULL>(data, type, row0, last, x);
-#pragma unroll
-      for (int k = 0; k < AGG_ITEMS; k++) c[k] = x[k] == lit ? 0 : (x[k] < lit ? -1 : 1);
-    }
-    switch (op) {   // uniform: one specialised row loop per operator
-#define SB_CMP(COND) _Pragma("unroll") for (int k = 0; k < AGG_ITEMS; k++) keep[k] = keep[k] && (COND);
-      case T_EQ: SB_CMP(c[k] == 0) break;
-      case T_NE: SB_CMP(c[k] != 0) break;
-      case T_LT: SB_CMP(c[k] < 0) break;
-      case T_LE: SB_CMP(c[k] <= 0) break;
-      case T_GT: SB_CMP(c[k] > 0) break;
-      default: SB_CMP(c[k] >= 0) break;
-#undef SB_CMP
-    }
-  }
-}
-
-// value of one factor for the thread's rows: col | lit-col | lit+col | col-lit (mode switch outside the row loop)
-template <bool FULL>
-__device__ __forceinline__ void factor_batch(const Factor &f, int64_t row0, int64_t last, double (&y)[AGG_ITEMS]) {
-  const int32_t mode = f.mode;
-  const double lit = f.lit;
-  load_f64_batch<FULL>(f.data, f.type, row0, last, y);
-  switch (mode) {
-    case F_LIT_MINUS_COL:
-#pragma unroll
-      for (int k = 0; k < AGG_ITEMS; k++) y[k] = __dsub_rn(lit, y[k]);
-      break;
-    case F_LIT_PLUS_COL:
-#pragma unroll
-      for (int k = 0; k < AGG_ITEMS; k++) y[k] = __dadd_rn(lit, y[k]);
-      break;
-    case F_COL_MINUS_LIT:
-#pragma unroll
-      for (int k = 0; k < AGG_ITEMS; k++) y[k] = __dsub_rn(y[k], lit);
-      break;
-    default: break;
-  }
-}
-
-// slot descriptor outer, rows inner.  dst[k] >= 0: HBM table slot; doff[k] >= 0: offset of the row's group in
-// the lane-private shared-memory accumulators (dictionary hit); both negative: row filtered out.
-template <bool FULL>
-__device__ __forceinline__ void accumulate_slots(const AggArgs &a, int64_t row0, const int64_t (&dst)[AGG_ITEMS],
-                                                 const int (&doff)[AGG_ITEMS], uint64_t *acc, int ns, int64_t stride) {
-  const int64_t last = a.n - 1;
-  for (int s = 0; s < ns; s++) {
-    const int kind = a.slot[s].kind, nf = a.slot[s].nf, is_one = a.slot[s].is_one, xform = a.slot[s].xform;
-    uint64_t v[AGG_ITEMS];
-    bool ok[AGG_ITEMS];
-#pragma unroll
-    for (int k = 0; k < AGG_ITEMS; k++) ok[k] = dst[k] >= 0 || doff[k] >= 0;
-    // NULL inputs do not contribute (Sum.scala:113, Count.scala:94)
-    for (int f = 0; f < nf; f++) {
-      const uint8_t *vptr = a.slot[s].f[f].valid;
-      if (vptr) {
-        bool valid[AGG_ITEMS];
-        load_valid_batch<FULL>(vptr, row0, last, valid);
-#pragma unroll
-        for (int k = 0; k < AGG_ITEMS; k++) ok[k] = ok[k] && valid[k];
-      }
-    }
-    if (is_one) {
-#pragma unroll
-      for (int k = 0; k < AGG_ITEMS; k++) v[k] = 1;
-    } else if (kind == K_ADD_F64 || xform == X_DOUBLE) {
-      double y[AGG_ITEMS];
-      factor_batch<FULL>(a.slot[s].f[0], row0, last, y);
-      for (int f = 1; f < nf; f++) {   // left-deep product, evaluated in the reference's order
-        double z[AGG_ITEMS];
-        factor_batch<FULL>(a.slot[s].f[f], row0, last, z);
-#pragma unroll
-        for (int k = 0; k < AGG_ITEMS; k++) y[k] = __dmul_rn(y[k], z[k]);
-      }
-      if (xform == X_DOUBLE) {   // order-preserving bits for min/max, NaN canonical (largest)
-#pragma unroll
-        for (int k = 0; k < AGG_ITEMS; k++) {
-          int64_t b = double_bits_canonical(y[k]);
-          v[k] = (uint64_t)b ^ ((uint64_t)(b >> 63) | 0x8000000000000000ull);
-        }
-      } else {
-#pragma unroll
-        for (int k = 0; k < AGG_ITEMS; k++) v[k] = (uint64_t)__double_as_longlong(y[k]);
-      }
-    } else {
-      int64_t x[AGG_ITEMS];
-      load_i64_batch<FULL>(a.slot[s].f[0].data, a.slot[s].f[0].type, row0, last, x);
-      const uint64_t flip = xform == X_SIGNED ? 0x8000000000000000ull : 0ull;
-#pragma unroll
-      for (int k = 0; k < AGG_ITEMS; k++) v[k] = (uint64_t)x[k] ^ flip;
-    }
-    uint64_t *sacc = acc + (size_t)s * AGG_THREADS;
-    uint64_t *gacc = a.tacc + (int64_t)s * stride;
-    switch (kind) {   // uniform: one specialised row loop per accumulator kind
-#define SB_ACC(LOCAL, GLOBAL)                                          \
-  _Pragma("unroll") for (int k = 0; k < AGG_ITEMS; k++) {              \
-    if (!ok[k]) continue;                                              \
-    if (doff[k] >= 0) { uint64_t *p = sacc + doff[k]; LOCAL; }         \
-    else { uint64_t *p = gacc + dst[k]; GLOBAL; }                      \
-  }
-      case K_ADD_F64:
-        SB_ACC(*(double *)p = __dadd_rn(*(double *)p, __longlong_as_double((int64_t)v[k])),
-               atomicAdd((double *)p, __longlong_as_double((int64_t)v[k])))
-        break;
-      case K_ADD_I64:
-        SB_ACC(*p += v[k], atomicAdd((unsigned long long *)p, (unsigned long long)v[k]))
-        break;
-      case K_MIN_U64:
-        SB_ACC(*p = v[k] < *p ? v[k] : *p, atomicMin((unsigned long long *)p, (unsigned long long)v[k]))
-        break;
-      default:
-        SB_ACC(*p = v[k] > *p ? v[k] : *p, atomicMax((unsigned long long *)p, (unsigned long long)v[k]))
-        break;
-#undef SB_ACC
-    }
-  }
-}
-
-// Branch-free variant used when every kept row of the warp resolved to a dictionary entry: filtered rows and
-// NULL inputs are steered to a "trash" accumulator group (index AGG_DICT), so the row loop is LDS + op + STS.
-template <bool FULL>
-__device__ __forceinline__ void accumulate_slots_dict(const AggArgs &a, int64_t row0, const int (&doff)[AGG_ITEMS], uint64_t *acc,
-                                                      int ns, int trash) {
-  const int64_t last = a.n - 1;
-  for (int s = 0; s < ns; s++) {
-    const int cls = a.slot[s].cls;
-    uint64_t *sacc = acc + (size_t)s * AGG_THREADS;
-    if (cls == CLS_F64_PRODUCT) {
-      const int nf = a.slot[s].nf;
-      double y[AGG_ITEMS];
-      factor_batch<FULL>(a.slot[s].f[0], row0, last, y);
-      for (int f = 1; f < nf; f++) {
-        double z[AGG_ITEMS];
-        factor_batch<FULL>(a.slot[s].f[f], row0, last, z);
-#pragma unroll
-        for (int k = 0; k < AGG_ITEMS; k++) y[k] = __dmul_rn(y[k], z[k]);
-      }
-#pragma unroll
-      for (int k = 0; k < AGG_ITEMS; k++) {
-        double *p = (double *)(sacc + doff[k]);
-        *p = __dadd_rn(*p, y[k]);
-      }
-    } else if (cls == CLS_ONE) {
-#pragma unroll
-      for (int k = 0; k < AGG_ITEMS; k++) sacc[doff[k]] += 1;
-    } else {
-      const int kind = a.slot[s].kind, nf = a.slot[s].nf, is_one = a.slot[s].is_one, xform = a.slot[s].xform;
-      uint64_t v[AGG_ITEMS];
-      int tgt[AGG_ITEMS];
-#pragma unroll
-      for (int k = 0; k < AGG_ITEMS; k++) tgt[k] = doff[k];
-      for (int f = 0; f < nf; f++) {
-        const uint8_t *vptr = a.slot[s].f[f].valid;
-        if (vptr) {
-          bool valid[AGG_ITEMS];
-          load_valid_batch<FULL>(vptr, row0, last, valid);
-#pragma unroll
-          for (int k = 0; k < AGG_ITEMS; k++) tgt[k] = valid[k] ? tgt[k] : trash;
-        }
-      }
-      if (is_one) {
-#pragma unroll
-        for (int k = 0; k < AGG_ITEMS; k++) v[k] = 1;
-      } else if (kind == K_ADD_F64 || xform == X_DOUBLE) {
-        double y[AGG_ITEMS];
-        factor_batch<FULL>(a.slot[s].f[0], row0, last, y);
-        for (int f = 1; f < nf; f++) {
-          double z[AGG_ITEMS];
-          factor_batch<FULL>(a.slot[s].f[f], row0, last, z);
-#pragma unroll
-          for (int k = 0; k < AGG_ITEMS; k++) y[k] = __dmul_rn(y[k], z[k]);
-        }
-        if (xform == X_DOUBLE) {
-#pragma unroll
-          for (int k = 0; k < AGG_ITEMS; k++) {
-            int64_t b = double_bits_canonical(y[k]);
-            v[k] = (uint64_t)b ^ ((uint64_t)(b >> 63) | 0x8000000000000000ull);
-          }
-        } else {
-#pragma unroll
-          for (int k = 0; k < AGG_ITEMS; k++) v[k] = (uint64_t)__double_as_longlong(y[k]);
-        }
-      } else {
-        int64_t x[AGG_ITEMS];
-        load_i64_batch<FULL>(a.slot[s].f[0].data, a.slot[s].f[0].type, row0, last, x);
-        const uint64_t flip = xform == X_SIGNED ? 0x8000000000000000ull : 0ull;
-#pragma unroll
-        for (int k = 0; k < AGG_ITEMS; k++) v[k] = (uint64_t)x[k] ^ flip;
-      }
-      switch (kind) {
-#define SB_ACCD(EXPR) _Pragma("unroll") for (int k = 0; k < AGG_ITEMS; k++) { uint64_t *p = sacc + tgt[k]; EXPR; }
-        case K_ADD_F64: SB_ACCD(*(double *)p = __dadd_rn(*(double *)p, __longlong_as_double((int64_t)v[k]))) break;
-        case K_ADD_I64: SB_ACCD(*p += v[k]) break;
-        case K_MIN_U64: SB_ACCD(*p = v[k] < *p ? v[k] : *p) break;
-        default: SB_ACCD(*p = v[k] > *p ? v[k] : *p) break;
-#undef SB_ACCD
-      }
-    }
-  }
-}
-
-// Shared memory layout: uint64 dict_keys[AGG_DICT]; uint64 acc[(AGG_DICT + 1) * nslots][AGG_THREADS] (last group = trash)
-template <bool FULL>
-__device__ __forceinline__ void process_tile(const AggArgs &a, int64_t base, int use_dict, uint64_t *dict_keys, uint64_t *acc, int tid,
-                                             int ns, int64_t stride) {
-  const int64_t row0 = base + tid;
-  const int64_t last = a.n - 1;
-  bool keep[AGG_ITEMS];
-  uint64_t key[AGG_ITEMS];
-#pragma unroll
-  for (int k = 0; k < AGG_ITEMS; k++) {
-    keep[k] = FULL || row0 + (int64_t)k * AGG_THREADS < a.n;
-    key[k] = 0;
-  }
-  if (a.mask) {
-    int64_t m[AGG_ITEMS];
-    load_batch_as_i64<FULL, uint8_t>(a.mask, row0, last, m);
-#pragma unroll
-    for (int k = 0; k < AGG_ITEMS; k++) keep[k] = keep[k] && m[k] != 0;
-  }
-  apply_filter_terms<FULL>(a, row0, keep);
-  // ---- group key packing --------------------------------------------------------------------------------
-  int special[AGG_ITEMS];
-#pragma unroll
-  for (int k = 0; k < AGG_ITEMS; k++) special[k] = 0;
-  if (a.single64) {
-    const void *kd = a.key[0].data;
-    const uint8_t *kv = a.key[0].valid;
-    const int32_t kt = a.key[0].type;
-    int64_t x[AGG_ITEMS];
-    load_batch_as_i64<FULL, int64_t>(kd, row0, last, x);      // raw 64-bit words (int64 or double bits)
-    if (kt == SB_FLOAT64) {   // NormalizeFloatingNumbers: -0.0 -> 0.0, NaN canonical
-#pragma unroll
-      for (int k = 0; k < AGG_ITEMS; k++) {
-        double d = __longlong_as_double(x[k]);
-        x[k] = d == 0.0 ? 0ll : double_bits_canonical(d);
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < AGG_ITEMS; k++) {
-      key[k] = (uint64_t)x[k];
-      special[k] = key[k] == EMPTY_KEY ? 2 : 0;
-    }
-    if (kv) {
-      bool valid[AGG_ITEMS];
-      load_valid_batch<FULL>(kv, row0, last, valid);
-#pragma unroll
-      for (int k = 0; k < AGG_ITEMS; k++) special[k] = valid[k] ? special[k] : 1;
-    }
-  } else {
-    for (int i = 0; i < a.nkeys; i++) {
-      const void *kd = a.key[i].data;
-      const uint8_t *kv = a.key[i].valid;
-      const int32_t kt = a.key[i].type, bits = a.key[i].bits, shift = a.key[i].shift, nshift = a.key[i].null_shift;
-      int64_t x[AGG_ITEMS];
-      load_i64_batch<FULL>(kd, kt, row0, last, x);
-      if (kt == SB_FLOAT32) {
-#pragma unroll
-        for (int k = 0; k < AGG_ITEMS; k++) {
-          float f = __int_as_float((int32_t)x[k]);
-          x[k] = f == 0.0f ? 0 : (int64_t)(uint32_t)float_bits_canonical(f);
-        }
-      }
-      const uint64_t vmask = bits < 64 ? (1ull << bits) - 1 : ~0ull;
-      if (kv) {
-        bool valid[AGG_ITEMS];
-        load_valid_batch<FULL>(kv, row0, last, valid);
-#pragma unroll
-        for (int k = 0; k < AGG_ITEMS; k++) key[k] |= valid[k] ? ((uint64_t)x[k] & vmask) << shift : 1ull << nshift;
-      } else {
-#pragma unroll
-        for (int k = 0; k < AGG_ITEMS; k++) key[k] |= ((uint64_t)x[k] & vmask) << shift;
-      }
-    }
-  }
-  // ---- where does each row accumulate? ---------------------------------------------------------------------
-  int64_t dst[AGG_ITEMS];
-  int doff[AGG_ITEMS];
-  const int trash = AGG_DICT * ns * AGG_THREADS + tid;
-  bool all_dict = true;
-#pragma unroll
-  for (int k = 0; k < AGG_ITEMS; k++) {
-    dst[k] = -1;
-    doff[k] = -1;
-    if (!keep[k]) continue;
-    int gid = -1;
-    if (use_dict && special[k] == 0) {
-      // linear probing over the AGG_DICT entries starting at a key-dependent entry: a resident key is
-      // normally found by the first probe
-      const uint32_t h0 = (uint32_t)(key[k] ^ (key[k] >> 7) ^ (key[k] >> 17) ^ (key[k] >> 32));
-#pragma unroll 1
-      for (int i = 0; i < AGG_DICT; i++) {
-        const int g = (h0 + i) & (AGG_DICT - 1);
-        uint64_t dk = dict_keys[g];
-        if (dk == EMPTY_KEY) {
-          uint64_t old = atomicCAS((unsigned long long *)&dict_keys[g], (unsigned long long)EMPTY_KEY, (unsigned long long)key[k]);
-          dk = old == EMPTY_KEY ? key[k] : old;
-        }
-        if (dk == key[k]) { gid = g; break; }
-      }
-    }
-    if (gid >= 0) doff[k] = gid * ns * AGG_THREADS + tid;
-    else {
-      dst[k] = table_slot(a, key[k], special[k]);
-      all_dict = false;
-    }
-  }
-  if (use_dict && __all_sync(0xffffffffu, all_dict)) {
-#pragma unroll
-    for (int k = 0; k < AGG_ITEMS; k++) doff[k] = doff[k] >= 0 ? doff[k] : trash;
-    accumulate_slots_dict<FULL>(a, row0, doff, acc, ns, trash);
-  } else {
-    accumulate_slots<FULL>(a, row0, dst, doff, acc, ns, stride);
-  }
-}
-
-__global__ void __launch_bounds__(AGG_THREADS) agg_update_kernel(const __grid_constant__ AggArgs a, int use_dict) {
-  extern __shared__ uint64_t sm[];
-  uint64_t *dict_keys = sm;
-  uint64_t *acc = sm + AGG_DICT;
-  const int tid = threadIdx.x;
-  const int ns = a.nslots;
-  if (use_dict) {
-    if (tid < AGG_DICT) dict_keys[tid] = EMPTY_KEY;
-    for (int s = 0; s < ns; s++) {
-      uint64_t id = slot_identity(a.slot[s].kind);
-      for (int g = 0; g <= AGG_DICT; g++) acc[(g * ns + s) * AGG_THREADS + tid] = id;
-    }
-    __syncthreads();
-  }
-  const int64_t tile = (int64_t)AGG_THREADS * AGG_ITEMS;
-  const int64_t stride = a.cap + 2;
-  for (int64_t base = (int64_t)blockIdx.x * tile; base < a.n; base += (int64_t)gridDim.x * tile) {
-    if (*(volatile int32_t *)a.flags) break;   // another block found the table too small: give up early
-    if (base + tile <= a.n) process_tile<true>(a, base, use_dict, dict_keys, acc, tid, ns, stride);
-    else process_tile<false>(a, base, use_dict, dict_keys, acc, tid, ns, stride);
-  }
-  if (!use_dict) return;
-  __syncthreads();
-  // merge the block dictionary into the HBM table: one warp per (group, slot) pair, shuffle tree
-  const int lane = tid & 31, warp = tid >> 5, nwarps = AGG_THREADS / 32;
-  for (int gs = warp; gs < AGG_DICT * ns; gs += nwarps) {
-    int g = gs / ns, s = gs % ns;
-    uint64_t key = dict_keys[g];
-    if (key == EMPTY_KEY) continue;
-    int kind = a.slot[s].kind;
-    uint64_t v = slot_identity(kind);
-    for (int t = lane; t < AGG_THREADS; t += 32) v = apply_op(kind, v, acc[(size_t)gs * AGG_THREADS + t]);
-#pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) v = apply_op(kind, v, __shfl_xor_sync(0xffffffffu, v, d));
-    if (lane == 0) {
-      int64_t slot = table_slot(a, key, 0);
-      if (slot >= 0) global_op(kind, &a.tacc[(int64_t)s * stride + slot], v);
-    }
-  }
-}
-
-// ---- wide grouping keys (> 63 bits, e.g. Q3's (l_orderkey, o_orderdate, o_shippriority)) -----------------
-// Same row loop, but the key is up to AGG_MAX_WORDS 64-bit words and the HBM table entry is published with a
-// small state machine: 0 empty -> 1 (claimed by atomicCAS, key words being written) -> 2 ready.
-template <int NW>
-__device__ __forceinline__ int64_t table_slot_wide(const AggArgs &a, const uint64_t (&w)[NW]) {
-  const int64_t stride = a.cap + 2;
-  uint64_t mask = (uint64_t)a.cap - 1;
-  uint64_t hh = 0;
-#pragma unroll
-  for (int i = 0; i < NW; i++) hh = mix64(hh ^ w[i]);
-  uint64_t h = hh & mask;
-  volatile uint32_t *state = a.tstate;
-  for (int step = 0; step < AGG_PROBE_LIMIT;) {
-    uint32_t s = state[h];
-    if (s == 0) {
-      if (atomicCAS(&a.tstate[h], 0u, 1u) == 0u) {
-#pragma unroll
-        for (int i = 0; i < NW; i++) a.tkeys[(int64_t)i * stride + h] = w[i];
-        __threadfence();
-        state[h] = 2u;
-        return (int64_t)h;
-      }
-      continue;   // somebody else claimed it: look again
-    }
-    if (s == 1) continue;   // being written
-    __threadfence();
-    bool eq = true;
-#pragma unroll
-    for (int i = 0; i < NW; i++) eq &= ((volatile uint64_t *)a.tkeys)[(int64_t)i * stride + h] == w[i];
-    if (eq) return (int64_t)h;
-    h = (h + 1) & mask;
-    step++;
-  }
-  a.flags[0] = 1;
-  return -1;
-}
-
-template <int NW>
-__global__ void __launch_bounds__(AGG_THREADS) agg_update_wide_kernel(const __grid_constant__ AggArgs a) {
-  const int tid = threadIdx.x;
-  const int ns = a.nslots;
-  const int64_t tile = (int64_t)AGG_THREADS * AGG_ITEMS;
-  const int64_t stride = a.cap + 2;
-  for (int64_t base = (int64_t)blockIdx.x * tile; base < a.n; base += (int64_t)gridDim.x * tile) {
-    if (a.flags[0]) break;
-    const int64_t row0 = base + tid;
-    bool keep[AGG_ITEMS];
-    uint64_t key[AGG_ITEMS][NW];
-    int64_t dst[AGG_ITEMS];
-    int doff[AGG_ITEMS];
-#pragma unroll
-    for (int k = 0; k < AGG_ITEMS; k++) {
-      int64_t row = row0 + (int64_t)k * AGG_THREADS;
-      keep[k] = row < a.n && (a.mask == nullptr || a.mask[row]);
-#pragma unroll
-      for (int i = 0; i < NW; i++) key[k][i] = 0;
-    }
-    apply_filter_terms<false>(a, row0, keep);
-    for (int i = 0; i < a.nkeys; i++) {
-      const KeySrc ks = a.key[i];
-#pragma unroll
-      for (int k = 0; k < AGG_ITEMS; k++) {
-        if (!keep[k]) continue;
-        int64_t row = row0 + (int64_t)k * AGG_THREADS;
-        uint64_t v;
-        int target = ks.word;
-        if (!bit_valid(ks.valid, row)) { v = 1ull << ks.null_shift; target = ks.null_word; }
-        else {
-          if (ks.type == SB_FLOAT32) {
-            float f = ((const float *)ks.data)[row];
-            v = f == 0.0f ? 0u : (uint32_t)float_bits_canonical(f);
-          } else if (ks.type == SB_FLOAT64) {
-            double d = ((const double *)ks.data)[row];
-            v = d == 0.0 ? 0ull : (uint64_t)double_bits_canonical(d);
-          } else {
-            v = (uint64_t)load_i64(ks.data, ks.type, row);
-            if (ks.bits < 64) v &= (1ull << ks.bits) - 1;
-          }
-          v <<= ks.shift;
-        }
-#pragma unroll
-        for (int wi = 0; wi < NW; wi++)
-          if (wi == target) key[k][wi] |= v;
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < AGG_ITEMS; k++) {
-      dst[k] = -1;
-      doff[k] = -1;
-      if (!keep[k]) continue;
-      dst[k] = table_slot_wide<NW>(a, key[k]);
-    }
-    accumulate_slots<false>(a, row0, dst, doff, nullptr, ns, stride);
-  }
-}
-
-__global__ void occupied_wide_kernel(const uint32_t *__restrict__ tstate, int64_t cap, uint8_t *__restrict__ occ) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < cap) occ[i] = tstate[i] == 2u;
-  else if (i < cap + 2) occ[i] = 0;
-}
-
-__global__ void fill_u64_kernel(uint64_t *p, int64_t n, uint64_t v) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) p[i] = v;
+  return {agg_update_kernel<DynPlan, ITEMS_DIRECT>, agg_update_staged_kernel<DynPlan, ITEMS_STAGED>, ITEMS_DIRECT, "dynamic"};
 }
 
 __global__ void occupied_kernel(const uint64_t *__restrict__ tkeys, int64_t cap, const int32_t *__restrict__ flags,
@@ -831,7 +107,7 @@ __global__ void occupied_kernel(const uint64_t *__restrict__ tkeys, int64_t cap,
 struct EmitKey {
   void *out;
   uint32_t *out_valid;
-  int32_t type, bits, shift, null_shift, word, null_word;
+  int32_t type, bits, shift, null_shift, word, null_word, hi_word, hi_shift;
 };
 enum EmitOp { E_RAW = 0, E_SUM_NULLABLE, E_AVG, E_MINMAX };
 struct EmitCol {
@@ -845,7 +121,7 @@ struct EmitCol {
   int32_t pad;
 };
 struct EmitArgs {
-  int32_t nkeys, single64, ncols, pad;
+  int32_t nkeys, single64, ncols, nwords;
   EmitKey key[AGG_MAX_KEYS];
   EmitCol col[2 * AGG_MAX_SLOTS];
   const uint64_t *tkeys;
@@ -883,6 +159,8 @@ __global__ void __launch_bounds__(256) agg_emit_kernel(const __grid_constant__ E
         if (ek.null_shift >= 0 && ((e.tkeys[(int64_t)ek.null_word * stride + slot] >> ek.null_shift) & 1)) valid = false;
         else {
           uint64_t u = key >> ek.shift;
+          if (ek.bits == 64 && e.nwords > 1)
+            u = (u & 0x7FFFFFFFFFFFFFFFull) | (((e.tkeys[(int64_t)ek.hi_word * stride + slot] >> ek.hi_shift) & 1) << 63);
           if (ek.bits < 64) {
             u &= (1ull << ek.bits) - 1;
             // sign-extend integer types
@@ -966,16 +244,26 @@ static int build_tree(const sb_expr &e, std::vector<ExprTree> &t) {
   return stack.back();
 }
 
-static bool is_f64_col(const sb_table *in, const ExprTree &n) {
-  return n.op == SB_OP_COL && in->cols[n.arg].type == SB_FLOAT64;
-}
+// host view of one accumulator slot before it is split into PlanMeta + AggArgs arrays
+struct HostFactor {
+  const void *data = nullptr;
+  const uint8_t *valid = nullptr;
+  int32_t type = 0, mode = F_COL;
+  double lit = 0;
+};
+struct HostSlot {
+  int32_t kind = 0, nf = 0, is_one = 0, xform = X_NONE;
+  HostFactor f[AGG_MAX_FACT];
+};
+
+static bool is_f64_col(const sb_table *in, const ExprTree &n) { return n.op == SB_OP_COL && in->cols[n.arg].type == SB_FLOAT64; }
 static double lit_as_double(const ExprTree &n) {
   if (n.op == SB_OP_LIT_F64) { double d; memcpy(&d, &n.lit, 8); return d; }
   return (double)n.lit;
 }
 static bool is_lit(const ExprTree &n) { return n.op == SB_OP_LIT_F64 || n.op == SB_OP_LIT_I64; }
 
-static bool match_factor(const sb_table *in, const std::vector<ExprTree> &t, int i, Factor &f) {
+static bool match_factor(const sb_table *in, const std::vector<ExprTree> &t, int i, HostFactor &f) {
   const ExprTree &n = t[i];
   auto set_col = [&](const ExprTree &c) {
     const Column &col = in->cols[c.arg];
@@ -991,21 +279,18 @@ static bool match_factor(const sb_table *in, const std::vector<ExprTree> &t, int
 }
 
 // left-deep product of <= 3 factors, evaluated in the reference's order ((f0*f1)*f2)
-static bool match_product(const sb_table *in, const sb_expr &e, SlotSrc &s) {
+static bool match_product(const sb_table *in, const sb_expr &e, HostSlot &s) {
   std::vector<ExprTree> t;
   int root = build_tree(e, t);
-  Factor f[AGG_MAX_FACT];
-  int chain[AGG_MAX_FACT];
-  int nf = 0, cur = root;
-  // peel right factors: Mul(Mul(a,b),c) -> [a,b,c]
-  int rights[AGG_MAX_FACT];
-  int nr = 0;
-  while (t[cur].op == SB_OP_MUL && t[cur].vtype == SB_VT_F64 && nr < AGG_MAX_FACT - 1) {
+  int chain[AGG_MAX_FACT], rights[AGG_MAX_FACT];
+  int nf = 0, nr = 0, cur = root;
+  while (t[cur].op == SB_OP_MUL && t[cur].vtype == SB_VT_F64 && nr < AGG_MAX_FACT - 1) {   // Mul(Mul(a,b),c) -> [a,b,c]
     rights[nr++] = t[cur].r;
     cur = t[cur].l;
   }
   chain[nf++] = cur;
   for (int k = nr - 1; k >= 0; k--) chain[nf++] = rights[k];
+  HostFactor f[AGG_MAX_FACT];
   for (int k = 0; k < nf; k++)
     if (!match_factor(in, t, chain[k], f[k])) return false;
   s.nf = nf;
@@ -1017,19 +302,23 @@ static bool match_filter(const sb_table *in, const sb_expr &e, AggArgs &a) {
   std::vector<ExprTree> t;
   int root = build_tree(e, t);
   std::vector<int> work{root};
-  a.nterms = 0;
+  PlanMeta &m = a.meta;
+  m.nterms = 0;
   while (!work.empty()) {
     int i = work.back();
     work.pop_back();
     const ExprTree &n = t[i];
     if (n.op == SB_OP_AND) { work.push_back(n.l); work.push_back(n.r); continue; }
-    if (a.nterms >= AGG_MAX_TERMS) return false;
-    FilterTerm &ft = a.term[a.nterms];
-    memset(&ft, 0, sizeof(ft));
+    if (m.nterms >= AGG_MAX_TERMS) return false;
+    const int ti = m.nterms;
+    auto set = [&](const Column &c, int op, int is_f64, int64_t lit) {
+      a.term[ti].data = c.d(); a.term[ti].valid = c.v();
+      m.term_type[ti] = c.type; m.term_op[ti] = op; m.term_f64[ti] = is_f64; m.term_valid[ti] = c.validity != nullptr;
+      a.term_lit[ti] = lit;
+      m.nterms++;
+    };
     if (n.op == SB_OP_ISNOTNULL && t[n.l].op == SB_OP_COL && in->cols[t[n.l].arg].type != SB_STRING) {
-      const Column &c = in->cols[t[n.l].arg];
-      ft.data = c.d(); ft.valid = c.v(); ft.type = c.type; ft.op = T_NOTNULL;
-      a.nterms++;
+      set(in->cols[t[n.l].arg], T_NOTNULL, 0, 0);
       continue;
     }
     if (n.op < SB_OP_EQ || n.op > SB_OP_GE) return false;
@@ -1043,28 +332,26 @@ static bool match_filter(const sb_table *in, const sb_expr &e, AggArgs &a) {
     if (col->op != SB_OP_COL || !is_lit(*lit)) return false;
     const Column &c = in->cols[col->arg];
     if (c.type == SB_STRING) return false;
-    ft.data = c.d(); ft.valid = c.v(); ft.type = c.type; ft.op = op;
-    ft.is_f64 = n.arg == SB_VT_F64;
-    if (ft.is_f64) {
+    if (n.arg == SB_VT_F64) {
       if (c.type != SB_FLOAT64 && c.type != SB_FLOAT32) return false;
       double d = lit_as_double(*lit);
-      memcpy(&ft.lit, &d, 8);
+      int64_t bits;
+      memcpy(&bits, &d, 8);
+      set(c, op, 1, bits);
     } else {
       if (c.type == SB_FLOAT64 || c.type == SB_FLOAT32 || lit->op != SB_OP_LIT_I64) return false;
-      ft.lit = lit->lit;
+      set(c, op, 0, lit->lit);
     }
-    a.nterms++;
   }
   return true;
 }
 
-static bool same_slot(const SlotSrc &x, const SlotSrc &y) {
+static bool same_slot(const HostSlot &x, const HostSlot &y) {
   if (x.kind != y.kind || x.nf != y.nf || x.is_one != y.is_one || x.xform != y.xform) return false;
   for (int k = 0; k < x.nf; k++) {
-    const Factor &a = x.f[k], &b = y.f[k];
+    const HostFactor &a = x.f[k], &b = y.f[k];
     if (a.data != b.data || a.valid != b.valid || a.type != b.type || a.mode != b.mode) return false;
     if (memcmp(&a.lit, &b.lit, 8) != 0) return false;
-    // is_one slots only look at validity: columns without validity are interchangeable
   }
   return true;
 }
@@ -1072,28 +359,28 @@ static bool same_slot(const SlotSrc &x, const SlotSrc &y) {
 struct AggBuilder {
   const sb_table *in;
   cudaStream_t st;
-  AggArgs args;
+  std::vector<HostSlot> slots;
   std::vector<Column> temps;   // materialised expression results, released at the end
 
-  int add_slot(SlotSrc s) {
-    if (s.is_one) {   // drop factors whose column can never be NULL: count(x) over a non-nullable x == count(*)
+  int add_slot(HostSlot s) {
+    if (s.is_one) {   // count(x) over a column that can never be NULL == count(*): only nullable columns matter
       int k2 = 0;
       for (int k = 0; k < s.nf; k++)
         if (s.f[k].valid) s.f[k2++] = s.f[k];
       s.nf = k2;
       for (int k = 0; k < s.nf; k++) { s.f[k].mode = F_COL; s.f[k].lit = 0; s.f[k].data = nullptr; s.f[k].type = 0; }
+      for (int k = s.nf; k < AGG_MAX_FACT; k++) s.f[k] = HostFactor();
     }
-    for (int i = 0; i < args.nslots; i++)
-      if (same_slot(args.slot[i], s)) return i;
-    if (args.nslots >= AGG_MAX_SLOTS) fail(SB_ERR_UNSUPPORTED, "aggregate needs more than %d accumulator slots", AGG_MAX_SLOTS);
-    args.slot[args.nslots] = s;
-    return args.nslots++;
+    for (size_t i = 0; i < slots.size(); i++)
+      if (same_slot(slots[i], s)) return (int)i;
+    if ((int)slots.size() >= AGG_MAX_SLOTS) fail(SB_ERR_UNSUPPORTED, "aggregate needs more than %d accumulator slots", AGG_MAX_SLOTS);
+    slots.push_back(s);
+    return (int)slots.size() - 1;
   }
 
-  // value source for an aggregate input expression; want_f64 = accumulate as double
-  SlotSrc source_for(const sb_expr &e, bool want_f64, int32_t *src_type) {
-    SlotSrc s;
-    memset(&s, 0, sizeof(s));
+  // value source for an aggregate input expression
+  HostSlot source_for(const sb_expr &e, int32_t *src_type) {
+    HostSlot s;
     int col;
     if (expr_is_column(e, &col)) {
       SB_REQUIRE(col >= 0 && col < (int)in->cols.size(), "aggregate input column %d out of range", col);
@@ -1105,7 +392,6 @@ struct AggBuilder {
       return s;
     }
     expr_validate(in, e);
-    (void)want_f64;
     if (e.nodes[e.n - 1].vtype == SB_VT_F64 && match_product(in, e, s)) {
       *src_type = SB_FLOAT64;
       return s;
@@ -1140,11 +426,12 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
   AggBuilder b;
   b.in = in;
   b.st = st;
-  memset(&b.args, 0, sizeof(b.args));
-  AggArgs &a = b.args;
+  static thread_local AggArgs args_storage;
+  AggArgs &a = args_storage;
+  memset(&a, 0, sizeof(a));
+  PlanMeta &m = a.meta;
   a.n = n;
   std::vector<OutPlan> outs;
-  Scratch mask_buf(0, st);
   void *mask_ptr = nullptr;
 
   struct Cleanup {
@@ -1159,53 +446,65 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
 
   // ---- keys --------------------------------------------------------------------------------
   SB_REQUIRE(plan->nkeys <= AGG_MAX_KEYS, "at most %d grouping keys are supported (got %d)", AGG_MAX_KEYS, plan->nkeys);
-  a.nkeys = plan->nkeys;
+  m.nkeys = plan->nkeys;
   int total_bits = 0;
   for (int k = 0; k < plan->nkeys; k++) {
     int ci = plan->key_cols[k];
     SB_REQUIRE(ci >= 0 && ci < (int)in->cols.size(), "key column %d out of range", ci);
     const Column &c = in->cols[ci];
     if (c.type == SB_STRING) fail(SB_ERR_UNSUPPORTED, "string grouping keys are not supported (dictionary-encode them)");
-    KeySrc &ks = a.key[k];
-    ks.data = c.d(); ks.valid = c.v(); ks.type = c.type;
-    ks.bits = type_width(c.type) * 8;
-    total_bits += ks.bits + (c.validity ? 1 : 0);
+    a.key[k].data = c.d();
+    a.key[k].valid = c.v();
+    m.key_type[k] = c.type;
+    m.key_bits[k] = type_width(c.type) * 8;
+    m.key_valid[k] = c.validity != nullptr;
+    m.key_nshift[k] = -1;
+    total_bits += m.key_bits[k] + (c.validity ? 1 : 0);
   }
   a.nwords = 1;
-  if (plan->nkeys == 1 && a.key[0].bits == 64) {
-    a.single64 = 1;
-    a.key[0].shift = 0;
-    a.key[0].null_shift = -1;
+  if (plan->nkeys == 1 && m.key_bits[0] == 64) {
+    m.single64 = 1;
   } else if (total_bits <= 63) {
     int pos = 0;
     for (int k = 0; k < plan->nkeys; k++) {
-      a.key[k].shift = pos;
-      pos += a.key[k].bits;
-      if (a.key[k].valid) a.key[k].null_shift = pos++;
-      else a.key[k].null_shift = -1;
+      m.key_shift[k] = pos;
+      pos += m.key_bits[k];
+      if (m.key_valid[k]) m.key_nshift[k] = pos++;
     }
   } else {
-    // wide key: value fields first (a field never straddles words), then the null flags in the free bits
+    // wide key: 63 payload bits per word (bit 63 stays 0 so a word never equals the EMPTY sentinel).  Value fields
+    // first (a field never straddles words; a 64-bit field stores its low 63 bits and parks bit 63 with the flags),
+    // then bit-63 spill bits and null flags in the free bits.
     int used[AGG_MAX_WORDS + 1] = {0};
     int nw = 0;
-    for (int k = 0; k < plan->nkeys; k++) {
+    auto place = [&](int nbits, int &word, int &shift) {
       int w = 0;
-      while (w < AGG_MAX_WORDS && used[w] + a.key[k].bits > 64) w++;
-      if (w >= AGG_MAX_WORDS) fail(SB_ERR_UNSUPPORTED, "grouping keys do not fit in %d 64-bit words", AGG_MAX_WORDS);
-      a.key[k].word = w;
-      a.key[k].shift = used[w];
-      used[w] += a.key[k].bits;
+      while (w < AGG_MAX_WORDS && used[w] + nbits > 63) w++;
+      if (w >= AGG_MAX_WORDS) fail(SB_ERR_UNSUPPORTED, "grouping keys do not fit in %d 63-bit words", AGG_MAX_WORDS);
+      word = w;
+      shift = used[w];
+      used[w] += nbits;
       if (w + 1 > nw) nw = w + 1;
+    };
+    for (int k = 0; k < plan->nkeys; k++) {
+      int word, shift;
+      place(m.key_bits[k] == 64 ? 63 : m.key_bits[k], word, shift);
+      a.key_extra[k].word = word;
+      m.key_shift[k] = shift;
     }
     for (int k = 0; k < plan->nkeys; k++) {
-      a.key[k].null_shift = -1;
-      if (!a.key[k].valid) continue;
-      int w = 0;
-      while (w < AGG_MAX_WORDS && used[w] + 1 > 64) w++;
-      if (w >= AGG_MAX_WORDS) fail(SB_ERR_UNSUPPORTED, "grouping keys do not fit in %d 64-bit words", AGG_MAX_WORDS);
-      a.key[k].null_word = w;
-      a.key[k].null_shift = used[w]++;
-      if (w + 1 > nw) nw = w + 1;
+      if (m.key_bits[k] == 64) {
+        int word, shift;
+        place(1, word, shift);
+        a.key_extra[k].hi_word = word;
+        a.key_extra[k].hi_shift = shift;
+      }
+      if (m.key_valid[k]) {
+        int word, shift;
+        place(1, word, shift);
+        a.key_extra[k].null_word = word;
+        m.key_nshift[k] = shift;
+      }
     }
     a.nwords = nw < 2 ? 2 : nw;
   }
@@ -1214,10 +513,14 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
   if (plan->filter) {
     expr_validate(in, *plan->filter);
     if (!match_filter(in, *plan->filter, a)) {
-      a.nterms = 0;
+      m.nterms = 0;
+      memset(m.term_type, 0, sizeof(m.term_type)); memset(m.term_op, 0, sizeof(m.term_op));
+      memset(m.term_f64, 0, sizeof(m.term_f64)); memset(m.term_valid, 0, sizeof(m.term_valid));
+      memset(a.term, 0, sizeof(a.term)); memset(a.term_lit, 0, sizeof(a.term_lit));
       SB_CUDA(cudaMallocAsync(&mask_ptr, (size_t)n + 16, st));
       eval_predicate(in, *plan->filter, (uint8_t *)mask_ptr, st);
-      a.mask = (const uint8_t *)mask_ptr;
+      a.mask.data = mask_ptr;
+      m.has_mask = 1;
     }
   }
 
@@ -1230,8 +533,7 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
     auto buffer_source = [&](int col) {
       SB_REQUIRE(col < (int)in->cols.size(), "Final aggregate expects buffer column %d but the input has %zu columns", col, in->cols.size());
       const Column &c = in->cols[col];
-      SlotSrc s;
-      memset(&s, 0, sizeof(s));
+      HostSlot s;
       s.nf = 1;
       s.f[0].data = c.d(); s.f[0].valid = c.v(); s.f[0].type = c.type; s.f[0].mode = F_COL;
       return s;
@@ -1239,9 +541,8 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
     switch (sp.func) {
       case SB_AGG_SUM: {
         int32_t src_type;
-        SlotSrc s = final_mode ? buffer_source(next_buf_col) : b.source_for(sp.input, false, &src_type);
+        HostSlot s = final_mode ? buffer_source(next_buf_col) : b.source_for(sp.input, &src_type);
         if (final_mode) { src_type = in->cols[next_buf_col].type; next_buf_col++; }
-        else if (s.nf >= 1 && is_float_type(s.f[0].type)) src_type = SB_FLOAT64;
         bool f64 = is_float_type(src_type) || s.nf > 1 || s.f[0].mode != F_COL;
         s.kind = f64 ? K_ADD_F64 : K_ADD_I64;
         // a global aggregate (no keys) over zero rows yields NULL, so it always tracks "seen"
@@ -1250,7 +551,7 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
         int main = b.add_slot(s);
         int seen = -1;
         if (nullable) {
-          SlotSrc c = s;
+          HostSlot c = s;
           c.kind = K_ADD_I64; c.is_one = 1;
           seen = b.add_slot(c);
         }
@@ -1260,19 +561,19 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
       case SB_AGG_AVG: {
         int sum_slot, cnt_slot;
         if (final_mode) {
-          SlotSrc s = buffer_source(next_buf_col); s.kind = K_ADD_F64;
+          HostSlot s = buffer_source(next_buf_col); s.kind = K_ADD_F64;
           SB_REQUIRE(in->cols[next_buf_col].type == SB_FLOAT64, "avg buffer sum must be float64");
-          SlotSrc c = buffer_source(next_buf_col + 1); c.kind = K_ADD_I64;
+          HostSlot c = buffer_source(next_buf_col + 1); c.kind = K_ADD_I64;
           SB_REQUIRE(in->cols[next_buf_col + 1].type == SB_INT64, "avg buffer count must be int64");
           next_buf_col += 2;
           sum_slot = b.add_slot(s);
           cnt_slot = b.add_slot(c);
         } else {
           int32_t src_type;
-          SlotSrc s = b.source_for(sp.input, true, &src_type);
+          HostSlot s = b.source_for(sp.input, &src_type);
           s.kind = K_ADD_F64;
           sum_slot = b.add_slot(s);
-          SlotSrc c = s;
+          HostSlot c = s;
           c.kind = K_ADD_I64; c.is_one = 1;
           cnt_slot = b.add_slot(c);
         }
@@ -1285,8 +586,7 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
         break;
       }
       case SB_AGG_COUNT: case SB_AGG_COUNT_STAR: {
-        SlotSrc s;
-        memset(&s, 0, sizeof(s));
+        HostSlot s;
         if (final_mode) {
           s = buffer_source(next_buf_col);
           SB_REQUIRE(in->cols[next_buf_col].type == SB_INT64, "count buffer must be int64");
@@ -1294,7 +594,7 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
           s.kind = K_ADD_I64;
         } else if (sp.func == SB_AGG_COUNT) {
           int32_t src_type;
-          s = b.source_for(sp.input, false, &src_type);
+          s = b.source_for(sp.input, &src_type);
           s.kind = K_ADD_I64; s.is_one = 1;
         } else {
           s.kind = K_ADD_I64; s.is_one = 1; s.nf = 0;
@@ -1304,15 +604,13 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
       }
       case SB_AGG_MIN: case SB_AGG_MAX: {
         int32_t src_type;
-        SlotSrc s = final_mode ? buffer_source(next_buf_col) : b.source_for(sp.input, false, &src_type);
+        HostSlot s = final_mode ? buffer_source(next_buf_col) : b.source_for(sp.input, &src_type);
         if (final_mode) { src_type = in->cols[next_buf_col].type; next_buf_col++; }
-        if (s.nf != 1 || s.f[0].mode != F_COL) {   // computed double expression
-          src_type = SB_FLOAT64;
-        }
+        if (s.nf != 1 || s.f[0].mode != F_COL) src_type = SB_FLOAT64;   // computed double expression
         s.kind = sp.func == SB_AGG_MIN ? K_MIN_U64 : K_MAX_U64;
         s.xform = is_float_type(src_type) ? X_DOUBLE : X_SIGNED;
         int main = b.add_slot(s);
-        SlotSrc c = s;
+        HostSlot c = s;
         c.kind = K_ADD_I64; c.is_one = 1; c.xform = X_NONE;
         int seen = b.add_slot(c);
         outs.push_back({E_MINMAX, src_type, main, seen, s.xform, true});
@@ -1321,73 +619,126 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
       default: fail(SB_ERR_INVALID, "unknown aggregate function %d", sp.func);
     }
   }
-  a.nslots = b.args.nslots;
-  for (int i = 0; i < a.nslots; i++) {
-    SlotSrc &sl = a.slot[i];
-    sl.cls = CLS_GENERIC;
-    if (sl.is_one && sl.nf == 0 && sl.kind == K_ADD_I64) sl.cls = CLS_ONE;
-    if (!sl.is_one && sl.kind == K_ADD_F64 && sl.xform == X_NONE && sl.nf >= 1) {
-      bool plain = true;
-      for (int k = 0; k < sl.nf; k++) plain &= sl.f[k].type == SB_FLOAT64 && sl.f[k].valid == nullptr;
-      if (plain) sl.cls = CLS_F64_PRODUCT;
+  // ---- slots -> PlanMeta + argument arrays -----------------------------------------------------------------
+  m.nslots = (int)b.slots.size();
+  for (int i = 0; i < m.nslots; i++) {
+    const HostSlot &sl = b.slots[i];
+    m.slot_kind[i] = sl.kind; m.slot_nf[i] = sl.nf; m.slot_one[i] = sl.is_one; m.slot_xform[i] = sl.xform;
+    m.slot_cls[i] = CLS_GENERIC;
+    bool any_valid = false, plain = sl.nf >= 1;
+    for (int k = 0; k < sl.nf; k++) {
+      a.fac[i][k].data = sl.f[k].data;
+      a.fac[i][k].valid = sl.f[k].valid;
+      a.fac_lit[i][k] = sl.f[k].lit;
+      m.f_type[i][k] = sl.f[k].type; m.f_mode[i][k] = sl.f[k].mode; m.f_valid[i][k] = sl.f[k].valid != nullptr;
+      any_valid |= sl.f[k].valid != nullptr;
+      plain &= sl.f[k].type == SB_FLOAT64 && sl.f[k].valid == nullptr;
     }
+    m.slot_anyvalid[i] = any_valid;
+    if (sl.is_one && sl.nf == 0 && sl.kind == K_ADD_I64) m.slot_cls[i] = CLS_ONE;
+    if (!sl.is_one && sl.kind == K_ADD_F64 && sl.xform == X_NONE && plain) m.slot_cls[i] = CLS_F64_PRODUCT;
   }
+  const int ns = m.nslots;
 
-  // ---- table sizing + update, retrying with a larger table when probing gives up ---------------
+  // ---- launch geometry -------------------------------------------------------------------------------------
   int64_t cap_max = next_pow2(n > 512 ? 2 * n : 1024);
   int64_t cap = plan->expected_groups > 0 ? next_pow2(2 * plan->expected_groups) : (1 << 16);
   if (cap < 1024) cap = 1024;
   if (cap > cap_max) cap = cap_max;
-  const bool use_dict = plan->nkeys > 0 || true;
-  size_t smem = use_dict ? (size_t)(AGG_DICT + (size_t)(AGG_DICT + 1) * a.nslots * AGG_THREADS) * 8 : 0;
-  static bool attr_set = false;
-  if (!attr_set) {
-    SB_CUDA(cudaFuncSetAttribute(agg_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
-  SB_REQUIRE(smem <= 200 * 1024, "aggregate needs %zu bytes of shared memory", smem);
-  int blocks_per_sm = smem ? (int)((227 * 1024) / (smem + 1024)) : 8;
+  KernelChoice kc = choose_kernels(m);
+  const size_t smem_acc = (size_t)(AGG_DICT + (size_t)(AGG_DICT + 1) * ns * AGG_THREADS) * 8;   // dictionary + accumulators
+  SB_REQUIRE(smem_acc <= 200 * 1024, "aggregate needs %zu bytes of shared memory", smem_acc);
+  SB_CUDA(cudaFuncSetAttribute(kc.direct, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  int blocks_per_sm = (int)((228 * 1024) / (smem_acc + 1024));
   if (blocks_per_sm < 1) blocks_per_sm = 1;
   if (blocks_per_sm > 8) blocks_per_sm = 8;
-  int grid = grid_for(n, AGG_THREADS * AGG_ITEMS, rt().num_sms * blocks_per_sm);
+  int grid = grid_for(n, AGG_THREADS * kc.items_direct, rt().num_sms * blocks_per_sm);
+
+  // ---- staged (TMA) path: lay out one shared-memory stage holding the tile of every distinct referenced buffer ----
+  const char *path_env = getenv("SB_AGG_PATH");   // "direct" | "staged" (default: direct)
+  const int64_t stile = (int64_t)AGG_THREADS * ITEMS_STAGED;
+  bool staged = a.nwords == 1 && n >= stile && path_env && strcmp(path_env, "staged") == 0;
+  size_t smem_staged = 0;
+  int grid_staged = 0;
+  if (staged) {
+    a.nstaged = 0;
+    int cursor = 0;
+    auto stage_of = [&](const void *base, int bytes_per_tile) -> int {
+      if (!staged || !base) return 0;
+      for (int i = 0; i < a.nstaged; i++)
+        if (a.staged[i].base == (const uint8_t *)base) return a.staged[i].soff;
+      if (a.nstaged >= AGG_MAX_STAGED || ((uintptr_t)base & 15) != 0) {   // too many buffers / TMA needs 16-byte alignment
+        staged = false;
+        return 0;
+      }
+      StagedBuf &sb_ = a.staged[a.nstaged++];
+      sb_.base = (const uint8_t *)base;
+      sb_.bytes_per_tile = bytes_per_tile;
+      sb_.soff = cursor;
+      cursor += (bytes_per_tile + 127) / 128 * 128;
+      return sb_.soff;
+    };
+    auto place = [&](ColRef &c, int32_t type) {
+      c.soff = c.data ? stage_of(c.data, (int)stile * type_width(type)) : 0;
+      c.svoff = c.valid ? stage_of(c.valid, (int)stile / 8) : -1;
+    };
+    if (m.has_mask) place(a.mask, SB_INT8);
+    for (int i = 0; i < m.nterms; i++) place(a.term[i], m.term_type[i]);
+    for (int i = 0; i < m.nkeys; i++) place(a.key[i], m.key_type[i]);
+    for (int i = 0; i < ns; i++)
+      for (int f = 0; f < m.slot_nf[i]; f++) place(a.fac[i][f], m.f_type[i][f] ? m.f_type[i][f] : SB_INT8);
+    if (staged && a.nstaged > 0) {
+      a.stage_bytes = cursor;
+      const size_t fixed = 64 + smem_acc;   // mbarriers + dictionary + accumulators
+      int best_blocks = 0, best_stages = 0;
+      for (int blocks = 2; blocks >= 1 && !best_blocks; blocks--)
+        for (int S = AGG_MAX_STAGES; S >= 2; S--) {
+          size_t need = (size_t)S * cursor + fixed;
+          if (need <= 227 * 1024 && blocks * (need + 1024) <= 228 * 1024) { best_blocks = blocks; best_stages = S; break; }
+        }
+      if (best_blocks) {
+        a.nstages = best_stages;
+        smem_staged = (size_t)best_stages * cursor + fixed;
+        int64_t full_tiles = n / stile;
+        int64_t g = (int64_t)rt().num_sms * best_blocks;
+        grid_staged = (int)(full_tiles < g ? full_tiles : g);
+        SB_CUDA(cudaFuncSetAttribute(kc.staged, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      } else staged = false;
+    } else staged = false;
+  }
 
   Scratch flags(16, st);
-  void *tkeys = nullptr, *tacc = nullptr, *tstate = nullptr;
+  void *tkeys = nullptr, *tacc = nullptr;
   struct TableFree {
-    void *&k, *&v, *&s;
+    void *&k, *&v;
     cudaStream_t st;
     ~TableFree() {
       if (k) cudaFreeAsync(k, st);
       if (v) cudaFreeAsync(v, st);
-      if (s) cudaFreeAsync(s, st);
     }
-  } table_free_guard{tkeys, tacc, tstate, st};
+  } table_free_guard{tkeys, tacc, st};
 
+  // ---- update, retrying with a larger table when probing gives up ------------------------------------------------
   for (;;) {
     int64_t slots = cap + 2;
     SB_CUDA(cudaMallocAsync(&tkeys, (size_t)slots * 8 * a.nwords, st));
-    SB_CUDA(cudaMallocAsync(&tacc, (size_t)slots * 8 * (a.nslots ? a.nslots : 1), st));
-    if (a.nwords > 1) {
-      SB_CUDA(cudaMallocAsync(&tstate, (size_t)slots * 4, st));
-      SB_CUDA(cudaMemsetAsync(tstate, 0, (size_t)slots * 4, st));
-    } else {
-      SB_CUDA(cudaMemsetAsync(tkeys, 0xff, (size_t)slots * 8, st));
-    }
-    SB_CUDA(cudaMemsetAsync(tacc, 0, (size_t)slots * 8 * (a.nslots ? a.nslots : 1), st));
-    for (int s = 0; s < a.nslots; s++)
-      if (a.slot[s].kind == K_MIN_U64) SB_CUDA(cudaMemsetAsync((uint64_t *)tacc + (int64_t)s * slots, 0xff, (size_t)slots * 8, st));
+    SB_CUDA(cudaMallocAsync(&tacc, (size_t)slots * 8 * (ns ? ns : 1), st));
+    SB_CUDA(cudaMemsetAsync(tkeys, 0xff, (size_t)slots * 8 * a.nwords, st));
+    SB_CUDA(cudaMemsetAsync(tacc, 0, (size_t)slots * 8 * (ns ? ns : 1), st));
+    for (int s = 0; s < ns; s++)
+      if (m.slot_kind[s] == K_MIN_U64) SB_CUDA(cudaMemsetAsync((uint64_t *)tacc + (int64_t)s * slots, 0xff, (size_t)slots * 8, st));
     SB_CUDA(cudaMemsetAsync(flags.ptr, 0, 16, st));
     a.tkeys = (uint64_t *)tkeys;
-    a.tstate = (uint32_t *)tstate;
     a.tacc = (uint64_t *)tacc;
     a.flags = flags.as<int32_t>();
     a.cap = cap;
     if (n > 0) {
       KernelTimer kt(final_mode ? "agg_update_final" : "agg_update", st);
-      if (a.nwords == 1) agg_update_kernel<<<grid, AGG_THREADS, smem, st>>>(a, use_dict ? 1 : 0);
-      else if (a.nwords == 2) agg_update_wide_kernel<2><<<grid, AGG_THREADS, 0, st>>>(a);
-      else if (a.nwords == 3) agg_update_wide_kernel<3><<<grid, AGG_THREADS, 0, st>>>(a);
-      else agg_update_wide_kernel<4><<<grid, AGG_THREADS, 0, st>>>(a);
+      if (a.nwords == 1 && staged) kc.staged<<<grid_staged, AGG_THREADS, smem_staged, st>>>(a);
+      else if (a.nwords == 1) kc.direct<<<grid, AGG_THREADS, smem_acc, st>>>(a);
+      else if (a.nwords == 2) agg_update_wide_kernel<2, 4><<<grid, AGG_THREADS, 0, st>>>(a);
+      else if (a.nwords == 3) agg_update_wide_kernel<3, 4><<<grid, AGG_THREADS, 0, st>>>(a);
+      else agg_update_wide_kernel<4, 4><<<grid, AGG_THREADS, 0, st>>>(a);
       SB_LAUNCH_CHECK();
     }
     int32_t hflags[4];
@@ -1397,40 +748,37 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
     if (cap >= cap_max) fail(SB_ERR_CUDA, "hash aggregate table overflow at maximum capacity %lld", (long long)cap);
     cudaFreeAsync(tkeys, st); tkeys = nullptr;
     cudaFreeAsync(tacc, st); tacc = nullptr;
-    if (tstate) { cudaFreeAsync(tstate, st); tstate = nullptr; }
     cap = cap * 16 > cap_max ? cap_max : cap * 16;
   }
+  if (getenv("SB_AGG_VERBOSE")) fprintf(stderr, "[sb_hash_aggregate] n=%lld plan=%s path=%s cap=%lld slots=%d\n", (long long)n, kc.name,
+                                        a.nwords > 1 ? "wide" : (staged ? "staged" : "direct"), (long long)cap, ns);
 
   // ---- collect occupied slots -------------------------------------------------------------------
   int64_t slots = cap + 2;
   int64_t ngroups;
   Scratch slot_ids(slots * 8, st);
-  if (plan->nkeys == 0) {
-    // no grouping keys: exactly one output row, even for empty input (AggregateCodegenSupport.scala:131)
-    // every row used key 0 -> find its slot, or use slot 0 of an untouched table
+  {
     Scratch occ(slots + 16, st);
     occupied_kernel<<<(unsigned)((slots + 255) / 256), 256, 0, st>>>((uint64_t *)tkeys, cap, flags.as<int32_t>(), occ.as<uint8_t>());
     SB_LAUNCH_CHECK();
     ngroups = compact_mask(occ.as<uint8_t>(), slots, slot_ids.as<int64_t>(), st);
-    if (ngroups == 0) {
+    if (plan->nkeys == 0 && ngroups == 0) {
+      // no grouping keys: exactly one output row even for empty input (AggregateCodegenSupport.scala:131);
+      // slot 0 of the untouched table holds the identities
       SB_CUDA(cudaMemsetAsync(slot_ids.ptr, 0, 8, st));
       ngroups = 1;
     }
-  } else {
-    Scratch occ(slots + 16, st);
-    if (a.nwords > 1) occupied_wide_kernel<<<(unsigned)((slots + 255) / 256), 256, 0, st>>>((uint32_t *)tstate, cap, occ.as<uint8_t>());
-    else occupied_kernel<<<(unsigned)((slots + 255) / 256), 256, 0, st>>>((uint64_t *)tkeys, cap, flags.as<int32_t>(), occ.as<uint8_t>());
-    SB_LAUNCH_CHECK();
-    ngroups = compact_mask(occ.as<uint8_t>(), slots, slot_ids.as<int64_t>(), st);
   }
 
   // ---- emit -------------------------------------------------------------------------------------
   sb_table *t = table_new(ngroups);
   try {
-    EmitArgs e;
+    static thread_local EmitArgs emit_storage;
+    EmitArgs &e = emit_storage;
     memset(&e, 0, sizeof(e));
     e.nkeys = plan->nkeys;
-    e.single64 = a.single64;
+    e.single64 = m.single64;
+    e.nwords = a.nwords;
     e.tkeys = (const uint64_t *)tkeys;
     e.tacc = (const uint64_t *)tacc;
     e.slot_ids = slot_ids.as<int64_t>();
@@ -1443,11 +791,13 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
       e.key[k].out = c.data->ptr;
       e.key[k].out_valid = c.validity ? (uint32_t *)c.validity->ptr : nullptr;
       e.key[k].type = src.type;
-      e.key[k].bits = a.key[k].bits;
-      e.key[k].shift = a.key[k].shift;
-      e.key[k].null_shift = a.key[k].null_shift;
-      e.key[k].word = a.key[k].word;
-      e.key[k].null_word = a.key[k].null_word;
+      e.key[k].bits = m.key_bits[k];
+      e.key[k].shift = m.key_shift[k];
+      e.key[k].null_shift = m.key_nshift[k];
+      e.key[k].word = a.key_extra[k].word;
+      e.key[k].null_word = a.key_extra[k].null_word;
+      e.key[k].hi_word = a.key_extra[k].hi_word;
+      e.key[k].hi_shift = a.key_extra[k].hi_shift;
     }
     SB_REQUIRE(outs.size() <= 2 * AGG_MAX_SLOTS, "too many aggregate output columns");
     e.ncols = (int)outs.size();

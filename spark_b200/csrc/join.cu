@@ -13,8 +13,9 @@
 //
 // GPU design (random-access bound; HBM for the probe stream, L2/HBM for the table):
 //   build : open addressing, capacity = 2^k >= 2 x build rows, linear probing; a build row claims the first
-//           free slot of its probe sequence with one 32-bit atomicCAS on the row-id array (0xFFFFFFFF = free)
+//           free slot of its probe sequence with one 32-bit atomicCAS on the slot's row id (0xFFFFFFFF = free)
 //           and then stores its packed 64-bit key -- duplicates simply occupy several slots; no sentinel key.
+//           A slot is 16 bytes {key, row id}, so a probe step is ONE 128-bit load (one 32-byte sector).
 //   probe : pass 1 counts matches per streamed row (and remembers the first match), exclusive scan,
 //           pass 2 writes (probe row, build row) pairs in streamed-row order; rows with <= 1 match do not walk
 //           the table twice.  Output columns are gathered once from both sides.
@@ -23,8 +24,8 @@
 
 struct sb_hash_table {
   sb_table *build = nullptr;        // retained build-side batch (payload gathered at probe time)
-  uint64_t *keys = nullptr;         // [cap]
-  uint32_t *rows = nullptr;         // [cap] build row id or 0xFFFFFFFF
+  struct Slot { uint64_t key; uint32_t row; uint32_t pad; };   // 16 bytes: one sector-aligned load per probe step
+  Slot *slots = nullptr;            // [cap]; row == 0xFFFFFFFF means free
   int64_t cap = 0;
   int32_t nkeys = 0;
   int32_t key_type[4];
@@ -77,8 +78,14 @@ __device__ __forceinline__ bool join_key(const JoinKeys &k, int64_t row, uint64_
   return true;
 }
 
-__global__ void __launch_bounds__(JOIN_THREADS) join_build_kernel(JoinKeys k, int64_t n, uint64_t *__restrict__ tkeys,
-                                                                  uint32_t *__restrict__ trows, int64_t cap) {
+typedef sb_hash_table::Slot JoinSlot;
+__device__ __forceinline__ void load_slot(const JoinSlot *p, uint64_t &key, uint32_t &row) {
+  const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(p);
+  key = v.x;
+  row = (uint32_t)v.y;
+}
+
+__global__ void __launch_bounds__(JOIN_THREADS) join_build_kernel(JoinKeys k, int64_t n, JoinSlot *__restrict__ slots, int64_t cap) {
   int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= n) return;
   uint64_t key;
@@ -86,8 +93,8 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_build_kernel(JoinKeys k, in
   uint64_t mask = (uint64_t)cap - 1;
   uint64_t h = join_mix(key) & mask;
   for (;;) {
-    if (trows[h] == FREE_SLOT && atomicCAS(&trows[h], FREE_SLOT, (uint32_t)row) == FREE_SLOT) {
-      tkeys[h] = key;
+    if (slots[h].row == FREE_SLOT && atomicCAS(&slots[h].row, FREE_SLOT, (uint32_t)row) == FREE_SLOT) {
+      slots[h].key = key;
       return;
     }
     h = (h + 1) & mask;
@@ -95,9 +102,8 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_build_kernel(JoinKeys k, in
 }
 
 // pass 1: matches per streamed row (join-type adjusted) + first matching build row
-__global__ void __launch_bounds__(JOIN_THREADS) join_count_kernel(JoinKeys k, int64_t n, const uint64_t *__restrict__ tkeys,
-                                                                  const uint32_t *__restrict__ trows, int64_t cap, int join_type,
-                                                                  int32_t *__restrict__ counts, uint32_t *__restrict__ first) {
+__global__ void __launch_bounds__(JOIN_THREADS) join_count_kernel(JoinKeys k, int64_t n, const JoinSlot *__restrict__ slots, int64_t cap,
+                                                                  int join_type, int32_t *__restrict__ counts, uint32_t *__restrict__ first) {
   int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= n) return;
   uint64_t key;
@@ -107,9 +113,11 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_count_kernel(JoinKeys k, in
     uint64_t mask = (uint64_t)cap - 1;
     uint64_t h = join_mix(key) & mask;
     for (;;) {
-      uint32_t r = trows[h];
+      uint64_t sk;
+      uint32_t r;
+      load_slot(&slots[h], sk, r);
       if (r == FREE_SLOT) break;
-      if (tkeys[h] == key) {
+      if (sk == key) {
         if (matches == 0) f = r;
         matches++;
       }
@@ -128,9 +136,8 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_count_kernel(JoinKeys k, in
 }
 
 // pass 2: (probe row, build row) pairs at the scanned offsets
-__global__ void __launch_bounds__(JOIN_THREADS) join_fill_kernel(JoinKeys k, int64_t n, const uint64_t *__restrict__ tkeys,
-                                                                 const uint32_t *__restrict__ trows, int64_t cap, int join_type,
-                                                                 const int32_t *__restrict__ counts, const int64_t *__restrict__ offsets,
+__global__ void __launch_bounds__(JOIN_THREADS) join_fill_kernel(JoinKeys k, int64_t n, const JoinSlot *__restrict__ slots, int64_t cap,
+                                                                 int join_type, const int32_t *__restrict__ counts, const int64_t *__restrict__ offsets,
                                                                  const uint32_t *__restrict__ first, int64_t *__restrict__ out_probe,
                                                                  int64_t *__restrict__ out_build) {
   int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -149,9 +156,11 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_fill_kernel(JoinKeys k, int
   uint64_t mask = (uint64_t)cap - 1;
   uint64_t h = join_mix(key) & mask;
   for (;;) {
-    uint32_t r = trows[h];
+    uint64_t sk;
+    uint32_t r;
+    load_slot(&slots[h], sk, r);
     if (r == FREE_SLOT) break;
-    if (tkeys[h] == key) {
+    if (sk == key) {
       out_probe[o] = row;
       out_build[o] = r;
       o++;
@@ -211,19 +220,17 @@ int sb_join_build(const sb_table *build, const int32_t *key_cols, int32_t nkeys,
   while (cap < 2 * n) cap <<= 1;
   ht->cap = cap;
   try {
-    SB_CUDA(cudaMallocAsync((void **)&ht->keys, (size_t)cap * 8, st));
-    SB_CUDA(cudaMallocAsync((void **)&ht->rows, (size_t)cap * 4, st));
-    SB_CUDA(cudaMemsetAsync(ht->rows, 0xff, (size_t)cap * 4, st));
+    SB_CUDA(cudaMallocAsync((void **)&ht->slots, (size_t)cap * sizeof(JoinSlot), st));
+    SB_CUDA(cudaMemsetAsync(ht->slots, 0xff, (size_t)cap * sizeof(JoinSlot), st));
     if (n > 0) {
       KernelTimer kt("join_build", st);
-      join_build_kernel<<<(unsigned)((n + JOIN_THREADS - 1) / JOIN_THREADS), JOIN_THREADS, 0, st>>>(k, n, ht->keys, ht->rows, cap);
+      join_build_kernel<<<(unsigned)((n + JOIN_THREADS - 1) / JOIN_THREADS), JOIN_THREADS, 0, st>>>(k, n, ht->slots, cap);
       SB_LAUNCH_CHECK();
     }
     ht->build = const_cast<sb_table *>(build);
     ht->build->refs.fetch_add(1);
   } catch (...) {
-    if (ht->keys) cudaFreeAsync(ht->keys, st);
-    if (ht->rows) cudaFreeAsync(ht->rows, st);
+    if (ht->slots) cudaFreeAsync(ht->slots, st);
     delete ht;
     throw;
   }
@@ -234,8 +241,7 @@ int sb_join_build(const sb_table *build, const int32_t *key_cols, int32_t nkeys,
 int sb_hash_table_release(sb_hash_table *ht) {
   SB_API_BEGIN
   if (ht) {
-    if (ht->keys) cudaFreeAsync(ht->keys, ht->st);
-    if (ht->rows) cudaFreeAsync(ht->rows, ht->st);
+    if (ht->slots) cudaFreeAsync(ht->slots, ht->st);
     if (ht->build && ht->build->refs.fetch_sub(1) == 1) table_free(ht->build);
     delete ht;
   }
@@ -257,8 +263,7 @@ int sb_join_probe(const sb_hash_table *ht, const sb_table *probe, const int32_t 
   unsigned nb = (unsigned)((n + JOIN_THREADS - 1) / JOIN_THREADS);
   if (n > 0) {
     KernelTimer kt("join_probe", st);
-    join_count_kernel<<<nb, JOIN_THREADS, 0, st>>>(k, n, ht->keys, ht->rows, ht->cap, join_type, counts.as<int32_t>(),
-                                                   first.as<uint32_t>());
+    join_count_kernel<<<nb, JOIN_THREADS, 0, st>>>(k, n, ht->slots, ht->cap, join_type, counts.as<int32_t>(), first.as<uint32_t>());
     SB_LAUNCH_CHECK();
   }
   exclusive_scan_i32_to_i64(counts.as<int32_t>(), offsets.as<int64_t>(), n, total.as<int64_t>(), st);
@@ -268,7 +273,7 @@ int sb_join_probe(const sb_hash_table *ht, const sb_table *probe, const int32_t 
   Scratch out_probe(nout * 8 + 16, st), out_build(pairs ? nout * 8 + 16 : 0, st);
   if (n > 0 && nout > 0) {
     KernelTimer kt("join_fill", st);
-    join_fill_kernel<<<nb, JOIN_THREADS, 0, st>>>(k, n, ht->keys, ht->rows, ht->cap, join_type, counts.as<int32_t>(),
+    join_fill_kernel<<<nb, JOIN_THREADS, 0, st>>>(k, n, ht->slots, ht->cap, join_type, counts.as<int32_t>(),
                                                   offsets.as<int64_t>(), first.as<uint32_t>(), out_probe.as<int64_t>(),
                                                   pairs ? out_build.as<int64_t>() : nullptr);
     SB_LAUNCH_CHECK();

@@ -9,7 +9,7 @@ struct PartGeometry {
   int nblocks;
   int64_t chunk;   // rows per block (multiple of 32)
 };
-PartGeometry part_geometry(int64_t n);
+PartGeometry part_geometry(int64_t n, int32_t nbuckets);
 
 struct SplitCol {
   int width;
@@ -26,6 +26,6 @@ void multisplit_scatter(const int32_t *bucket_dev, uint32_t *hist_dev, int32_t n
                         const SplitCol *cols, int ncols, int64_t n, int64_t *perm_out, int64_t *offsets_dev,
                         cudaStream_t st);
 
-constexpr int MULTISPLIT_MAX_BUCKETS = 200 * 1024 / 4 / 8;
+constexpr int MULTISPLIT_MAX_BUCKETS = 16384;   // two-level split: 64 x 256
 
 }  // namespace sb

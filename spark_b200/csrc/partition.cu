@@ -100,7 +100,32 @@ __global__ void __launch_bounds__(PART_THREADS) pid_hist_kernel(KeyCols keys, in
 }
 
 constexpr int SCATTER_MAX_COLS = 16;
-struct ScatterCols {
+
+// K2: stable multisplit of a group of columns with shared-memory regrouping (the scatter of an LSD radix sort pass,
+// generalised to any set of fixed-width columns).  At most RG_MAX_NB buckets per pass; larger fan-outs run two passes
+// (low digit, then high digit -- "LSB radix partition").
+//
+// A block owns a contiguous chunk of rows and walks it in tiles of RG_TILE rows.  Per tile:
+//   A  every warp owns a contiguous 1/16 of the tile and walks it 32 rows at a time: same-bucket rows are ranked with
+//      __match_any_sync + popcount on top of a per-warp shared-memory counter  -> (bucket, rank inside the warp's segment);
+//   B  per bucket: exclusive prefix of the per-warp counts (order of the warps = order of the rows) and the tile total;
+//   C  exclusive scan of the tile totals -> first sorted position of every bucket inside the tile;
+//   D  every row now knows its position in the bucket-sorted tile; sorted position j knows its output row
+//      gdest[j] = cursor[bucket] + (j - first[bucket]);
+//   E  per column: coalesced global loads -> shared memory at the sorted position -> __syncthreads -> consecutive threads
+//      read consecutive sorted positions and store them: rows of one bucket are adjacent, so the stores form RUNS
+//      (tile/buckets rows long) instead of one LSU transaction and one partial-sector DRAM write per element
+//      (first profile of the direct scatter: 3.5x DRAM traffic amplification, profiles/r01_partition.md);
+//   F  cursor[bucket] += tile total.
+// Stability: positions are assigned in (bucket, row) order at every level, so arrival order is preserved per bucket.
+constexpr int RG_THREADS = 512;
+constexpr int RG_WARPS = RG_THREADS / 32;
+constexpr int RG_ITEMS = 8;
+constexpr int RG_TILE = RG_THREADS * RG_ITEMS;   // 4096 rows
+constexpr int RG_SEG = RG_TILE / RG_WARPS;       // 256 rows per warp
+constexpr int RG_MAX_NB = 256;
+
+struct RegroupCols {
   int ncols;
   int width[SCATTER_MAX_COLS];
   const void *src[SCATTER_MAX_COLS];
@@ -109,67 +134,160 @@ struct ScatterCols {
   uint32_t *dst_valid[SCATTER_MAX_COLS];   // pre-set to all ones; NULL rows clear their bit
 };
 
-// K3: stable scatter.  base[p][block] = first output row of partition p for this block (exclusive scan
-// of hist).  Shared memory: PART_WARPS x nparts cursors.
-__global__ void __launch_bounds__(PART_THREADS) scatter_kernel(ScatterCols cols, const int32_t *__restrict__ pid,
-                                                               const uint32_t *__restrict__ base, int64_t n, int32_t nparts,
-                                                               int64_t chunk, int64_t *__restrict__ perm_out) {
-  extern __shared__ uint32_t cursors[];   // [warp][nparts]
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int64_t begin = (int64_t)blockIdx.x * chunk;
-  int64_t end = begin + chunk < n ? begin + chunk : n;
-  // every warp owns a contiguous, 32-aligned sub-chunk
-  int64_t len = end > begin ? end - begin : 0;
-  int64_t sub = ((len + PART_WARPS - 1) / PART_WARPS + 31) / 32 * 32;
-  int64_t wbeg = begin + warp * sub;
-  int64_t wend = wbeg + sub < end ? wbeg + sub : end;
-
-  // phase 1: per-warp histogram of its sub-chunk
-  uint32_t *mine = cursors + (size_t)warp * nparts;
-  for (int p = lane; p < nparts; p += 32) mine[p] = 0;
-  __syncwarp();
-  for (int64_t i = wbeg + lane; i < wend; i += 32) atomicAdd(&mine[pid[i]], 1u);
-  __syncthreads();
-  // phase 2: exclusive prefix over warps + global block base -> cursors
-  for (int p = threadIdx.x; p < nparts; p += PART_THREADS) {
-    uint32_t run = base[(int64_t)p * gridDim.x + blockIdx.x];
-#pragma unroll
-    for (int w = 0; w < PART_WARPS; w++) {
-      uint32_t c = cursors[(size_t)w * nparts + p];
-      cursors[(size_t)w * nparts + p] = run;
-      run += c;
-    }
-  }
-  __syncthreads();
-  // phase 3: each warp walks its sub-chunk in order, 32 rows at a time
-  for (int64_t i0 = wbeg; i0 < wend; i0 += 32) {
-    int64_t i = i0 + lane;
-    bool active = i < wend;
-    int32_t p = active ? pid[i] : -1 - lane;             // inactive lanes get unique dummy keys
-    uint32_t grp = __match_any_sync(0xffffffffu, p);
-    uint32_t rank = __popc(grp & lanemask_lt());
-    uint32_t dest = 0;
-    if (active) {
-      uint32_t b = mine[p];
-      dest = b + rank;
-      __syncwarp(grp);
-      if (rank == 0) mine[p] = b + __popc(grp);
-    }
+__global__ void __launch_bounds__(RG_THREADS, 2) regroup_kernel(const __grid_constant__ RegroupCols cols, const int32_t *__restrict__ bucket,
+                                                                const uint32_t *__restrict__ base, int64_t n, int32_t nb, int64_t chunk,
+                                                                int64_t *__restrict__ perm_out) {
+  __shared__ __align__(16) uint64_t staging[RG_TILE];      // 32 KB
+  __shared__ uint8_t sbucket[RG_TILE];                     // bucket of every sorted position (nb <= 256)
+  __shared__ uint16_t wcnt[RG_WARPS][RG_MAX_NB];
+  __shared__ uint16_t first[RG_MAX_NB], tcnt[RG_MAX_NB];
+  __shared__ uint32_t cursor[RG_MAX_NB];
+  __shared__ uint32_t warp_sums[RG_WARPS];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t begin = (int64_t)blockIdx.x * chunk;
+  const int64_t end = begin + chunk < n ? begin + chunk : n;
+  for (int p = tid; p < nb; p += RG_THREADS) cursor[p] = base[(int64_t)p * gridDim.x + blockIdx.x];
+  for (int64_t tbase = begin; tbase < end; tbase += RG_TILE) {
+    const int tile_n = (int)(end - tbase < RG_TILE ? end - tbase : RG_TILE);
+    const int64_t sbase = tbase + warp * RG_SEG;     // first row of this warp's segment
+    for (int p = lane; p < nb; p += 32) wcnt[warp][p] = 0;
     __syncwarp();
-    if (!active) continue;
-    if (perm_out) perm_out[dest] = i;
+    // ---- A: rank inside the warp's segment --------------------------------------------------------------------------------
+    uint32_t bl[RG_ITEMS];   // low 16 bits: bucket (0xFFFF = no row); high 16 bits: rank in the warp segment, later sorted position
+#pragma unroll
+    for (int it = 0; it < RG_ITEMS; it++) {
+      const bool active = warp * RG_SEG + it * 32 + lane < tile_n;
+      const int32_t b = active ? __ldcs(bucket + sbase + it * 32 + lane) : -1 - lane;
+      const uint32_t grp = __match_any_sync(0xffffffffu, b);
+      const uint32_t rank = __popc(grp & lanemask_lt());
+      uint32_t c = 0;
+      if (active) {
+        c = wcnt[warp][b];
+        __syncwarp(grp);
+        if (rank == 0) wcnt[warp][b] = (uint16_t)(c + __popc(grp));
+      }
+      __syncwarp();
+      bl[it] = (active ? (uint32_t)b : 0xFFFFu) | ((c + rank) << 16);
+    }
+    __syncthreads();
+    // ---- B: per bucket, exclusive prefix over the warps; tile total -------------------------------------------------------
+    for (int p = tid; p < nb; p += RG_THREADS) {
+      uint32_t run = 0;
+#pragma unroll
+      for (int w = 0; w < RG_WARPS; w++) {
+        uint32_t c = wcnt[w][p];
+        wcnt[w][p] = (uint16_t)run;
+        run += c;
+      }
+      tcnt[p] = (uint16_t)run;
+    }
+    __syncthreads();
+    // ---- C: exclusive scan of the tile totals -> first[] (nb <= 256: one bucket per thread of the first 8 warps) ------------
+    {
+      uint32_t v = tid < nb ? tcnt[tid] : 0, x = v;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+        if (lane >= d) x += y;
+      }
+      if (lane == 31) warp_sums[warp] = x;
+      __syncthreads();
+      uint32_t woff = 0;
+      for (int w = 0; w < warp; w++) woff += warp_sums[w];
+      if (tid < nb) first[tid] = (uint16_t)(woff + x - v);
+    }
+    __syncthreads();
+    // ---- D: sorted position of every row; bucket of every sorted position --------------------------------------------------
+#pragma unroll
+    for (int it = 0; it < RG_ITEMS; it++) {
+      const uint32_t b = bl[it] & 0xFFFFu;
+      if (b != 0xFFFFu) {
+        const uint32_t sp = first[b] + wcnt[warp][b] + (bl[it] >> 16);
+        sbucket[sp] = (uint8_t)b;
+        bl[it] = b | (sp << 16);
+      }
+    }
+    __syncthreads();
+    uint32_t gdest[RG_ITEMS];    // output row of sorted position j = it * RG_THREADS + tid
+#pragma unroll
+    for (int it = 0; it < RG_ITEMS; it++) {
+      const int j = it * RG_THREADS + tid;
+      if (j < tile_n) {
+        const int b = sbucket[j];
+        gdest[it] = cursor[b] + (uint32_t)(j - first[b]);
+      } else gdest[it] = 0xFFFFFFFFu;
+    }
+    // ---- E: move the columns -----------------------------------------------------------------------------------------------
+    if (perm_out) {   // row ids travel like a column (used to gather variable-width columns afterwards)
+#pragma unroll
+      for (int it = 0; it < RG_ITEMS; it++)
+        if ((bl[it] & 0xFFFFu) != 0xFFFFu) staging[bl[it] >> 16] = (uint64_t)(sbase + it * 32 + lane);
+      __syncthreads();
+#pragma unroll
+      for (int it = 0; it < RG_ITEMS; it++)
+        if (gdest[it] != 0xFFFFFFFFu) perm_out[gdest[it]] = (int64_t)staging[it * RG_THREADS + tid];
+      __syncthreads();
+    }
 #pragma unroll 1
     for (int c = 0; c < cols.ncols; c++) {
-      switch (cols.width[c]) {
-        case 1: ((uint8_t *)cols.dst[c])[dest] = ((const uint8_t *)cols.src[c])[i]; break;
-        case 2: ((uint16_t *)cols.dst[c])[dest] = ((const uint16_t *)cols.src[c])[i]; break;
-        case 4: ((uint32_t *)cols.dst[c])[dest] = ((const uint32_t *)cols.src[c])[i]; break;
-        default: ((uint64_t *)cols.dst[c])[dest] = ((const uint64_t *)cols.src[c])[i]; break;
-      }
-      if (cols.dst_valid[c] && !bit_valid(cols.src_valid[c], i))
-        atomicAnd(&cols.dst_valid[c][dest >> 5], ~(1u << (dest & 31)));
-    }
+      const int w = cols.width[c];
+      const void *src = cols.src[c];
+      void *dst = cols.dst[c];
+#define SB_REGROUP(T)                                                                                     \
+  {                                                                                                       \
+    T v[RG_ITEMS];                                                                                        \
+    _Pragma("unroll") for (int it = 0; it < RG_ITEMS; it++)                                                \
+      if ((bl[it] & 0xFFFFu) != 0xFFFFu) v[it] = __ldcs((const T *)src + sbase + it * 32 + lane);          \
+    _Pragma("unroll") for (int it = 0; it < RG_ITEMS; it++)                                                \
+      if ((bl[it] & 0xFFFFu) != 0xFFFFu) ((T *)staging)[bl[it] >> 16] = v[it];                             \
+    __syncthreads();                                                                                      \
+    _Pragma("unroll") for (int it = 0; it < RG_ITEMS; it++)                                                \
+      if (gdest[it] != 0xFFFFFFFFu) ((T *)dst)[gdest[it]] = ((const T *)staging)[it * RG_THREADS + tid];   \
+    __syncthreads();                                                                                      \
   }
+      switch (w) {
+        case 1: SB_REGROUP(uint8_t) break;
+        case 2: SB_REGROUP(uint16_t) break;
+        case 4: SB_REGROUP(uint32_t) break;
+        default: SB_REGROUP(uint64_t) break;
+      }
+#undef SB_REGROUP
+      if (cols.dst_valid[c]) {   // NULLs: clear the destination bit (rare, scattered)
+        const uint8_t *sv = cols.src_valid[c];
+#pragma unroll
+        for (int it = 0; it < RG_ITEMS; it++) {
+          const uint32_t b = bl[it] & 0xFFFFu;
+          if (b == 0xFFFFu) continue;
+          if (!bit_valid(sv, sbase + it * 32 + lane)) {
+            const uint32_t d = cursor[b] + ((bl[it] >> 16) - first[b]);
+            atomicAnd(&cols.dst_valid[c][d >> 5], ~(1u << (d & 31)));
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // ---- F: advance the block's cursors ----------------------------------------------------------------------------------------
+    for (int p = tid; p < nb; p += RG_THREADS) cursor[p] += tcnt[p];
+    __syncthreads();
+  }
+}
+
+// bucket = digit of a partition id for the two-level split; also the per-block histogram in multisplit layout
+__global__ void __launch_bounds__(RG_THREADS) pid_digit_hist_kernel(const int32_t *__restrict__ pid, int64_t n, int32_t div, int32_t mod,
+                                                                    int32_t nb, int64_t chunk, int32_t *__restrict__ bucket,
+                                                                    uint32_t *__restrict__ hist) {
+  __shared__ uint32_t sh[RG_MAX_NB];
+  for (int p = threadIdx.x; p < nb; p += RG_THREADS) sh[p] = 0;
+  __syncthreads();
+  int64_t begin = (int64_t)blockIdx.x * chunk;
+  int64_t end = begin + chunk < n ? begin + chunk : n;
+  for (int64_t i = begin + threadIdx.x; i < end; i += RG_THREADS) {
+    int b = (pid[i] / div) % mod;
+    bucket[i] = b;
+    atomicAdd(&sh[b], 1u);
+  }
+  __syncthreads();
+  for (int p = threadIdx.x; p < nb; p += RG_THREADS) hist[(int64_t)p * gridDim.x + blockIdx.x] = sh[p];
 }
 
 __global__ void part_offsets_kernel(const uint32_t *__restrict__ base, int32_t nparts, int nblocks, int64_t n,
@@ -194,14 +312,46 @@ static KeyCols make_keys(const sb_table *in, const int32_t *key_cols, int32_t nk
   return k;
 }
 
-PartGeometry part_geometry(int64_t n) {
+PartGeometry part_geometry(int64_t n, int32_t nbuckets) {
+  (void)nbuckets;
   PartGeometry g;
-  int64_t want = (n + PART_THREADS * 16 - 1) / (PART_THREADS * 16);
-  int maxb = rt().num_sms * 4;
+  int64_t want = (n + RG_TILE * 2 - 1) / (RG_TILE * 2);
+  int maxb = rt().num_sms * 2;
   g.nblocks = (int)(want < 1 ? 1 : (want > maxb ? maxb : want));
   g.chunk = ((n + g.nblocks - 1) / g.nblocks + 31) / 32 * 32;
   if (g.chunk < 32) g.chunk = 32;
   return g;
+}
+
+static void regroup_pass(const int32_t *bucket_dev, uint32_t *hist_dev, int32_t nb, const PartGeometry &g, const SplitCol *cols,
+                         int ncols, int64_t n, int64_t *perm_out, int64_t *offsets_dev, cudaStream_t st) {
+  exclusive_scan_i32((const int32_t *)hist_dev, (int32_t *)hist_dev, (int64_t)nb * g.nblocks, nullptr, st);
+  if (offsets_dev) {
+    part_offsets_kernel<<<(nb + 1 + 255) / 256, 256, 0, st>>>(hist_dev, nb, g.nblocks, n, offsets_dev);
+    SB_LAUNCH_CHECK();
+  }
+  if (n == 0) return;
+  int done = 0;
+  bool first = true;
+  while (first || done < ncols) {
+    RegroupCols rc;
+    rc.ncols = 0;
+    while (done < ncols && rc.ncols < SCATTER_MAX_COLS) {
+      const SplitCol &c = cols[done++];
+      int k = rc.ncols++;
+      rc.width[k] = c.width;
+      rc.src[k] = c.src;
+      rc.dst[k] = c.dst;
+      rc.src_valid[k] = c.src_valid;
+      rc.dst_valid[k] = c.dst_valid;
+    }
+    if (rc.ncols > 0 || (first && perm_out)) {
+      KernelTimer kt("partition_scatter", st);
+      regroup_kernel<<<g.nblocks, RG_THREADS, 0, st>>>(rc, bucket_dev, hist_dev, n, nb, g.chunk, first ? perm_out : nullptr);
+      SB_LAUNCH_CHECK();
+    }
+    first = false;
+  }
 }
 
 void multisplit_scatter(const int32_t *bucket_dev, uint32_t *hist_dev, int32_t nbuckets, const PartGeometry &g,
@@ -209,41 +359,55 @@ void multisplit_scatter(const int32_t *bucket_dev, uint32_t *hist_dev, int32_t n
                         cudaStream_t st) {
   SB_REQUIRE(nbuckets >= 1 && nbuckets <= MULTISPLIT_MAX_BUCKETS, "multisplit supports up to %d buckets (got %d)",
              MULTISPLIT_MAX_BUCKETS, nbuckets);
-  SB_REQUIRE(n < (1ll << 32), "tables of 2^32 rows or more must be split in chunks");
-  static bool attr_set = false;
-  if (!attr_set) {
-    SB_CUDA(cudaFuncSetAttribute(scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
+  SB_REQUIRE(n < 0xFFFFFFFFll, "tables of 2^32 rows or more must be split in chunks");
+  if (nbuckets <= RG_MAX_NB) {
+    regroup_pass(bucket_dev, hist_dev, nbuckets, g, cols, ncols, n, perm_out, offsets_dev, st);
+    return;
   }
-  size_t smem = (size_t)PART_WARPS * nbuckets * 4;
+  // ---- two-level LSB split: pass 1 on the low digit (bucket % B1), pass 2 on the high digit (bucket / B1).  Both passes
+  // are stable, so the result is ordered by (high, low) = bucket id with arrival order preserved inside a bucket.
+  const int32_t B1 = 64, B2 = (nbuckets + B1 - 1) / B1;
+  SB_REQUIRE(B2 <= RG_MAX_NB, "too many buckets");
+  Scratch digit(n * 4 + 16, st), hist2((int64_t)RG_MAX_NB * g.nblocks * 4 + 16, st), pid_mid(n * 4 + 16, st), perm_mid(perm_out ? n * 8 + 16 : 0, st);
+  // intermediate copies of every column (+ validity carried as-is through atomicAnd on a fresh bitmap)
+  std::vector<SplitCol> c1(cols, cols + ncols), c2(cols, cols + ncols);
+  std::vector<Scratch *> tmp;
+  struct Guard {
+    std::vector<Scratch *> &t;
+    ~Guard() { for (auto *x : t) delete x; }
+  } guard{tmp};
+  for (int i = 0; i < ncols; i++) {
+    Scratch *d = new Scratch((int64_t)n * cols[i].width + 16, st);
+    tmp.push_back(d);
+    c1[i].dst = d->ptr;
+    c2[i].src = d->ptr;
+    if (cols[i].dst_valid) {
+      Scratch *v = new Scratch(bitmap_alloc_bytes(n), st);
+      tmp.push_back(v);
+      SB_CUDA(cudaMemsetAsync(v->ptr, 0xff, (size_t)bitmap_alloc_bytes(n), st));
+      c1[i].dst_valid = (uint32_t *)v->ptr;
+      c2[i].src_valid = (const uint8_t *)v->ptr;
+    }
+  }
+  c1.push_back({4, bucket_dev, pid_mid.ptr, nullptr, nullptr});   // the bucket ids travel with the rows into pass 2
+  if (n > 0) {
+    pid_digit_hist_kernel<<<g.nblocks, RG_THREADS, 0, st>>>(bucket_dev, n, 1, B1, B1, g.chunk, digit.as<int32_t>(), hist2.as<uint32_t>());
+    SB_LAUNCH_CHECK();
+  }
+  regroup_pass(digit.as<int32_t>(), hist2.as<uint32_t>(), B1, g, c1.data(), (int)c1.size(), n, perm_out ? perm_mid.as<int64_t>() : nullptr, nullptr, st);
+  if (perm_out) c2.push_back({8, perm_mid.ptr, perm_out, nullptr, nullptr});
+  if (n > 0) {
+    pid_digit_hist_kernel<<<g.nblocks, RG_THREADS, 0, st>>>(pid_mid.as<int32_t>(), n, B1, B2, B2, g.chunk, digit.as<int32_t>(), hist2.as<uint32_t>());
+    SB_LAUNCH_CHECK();
+  }
+  regroup_pass(digit.as<int32_t>(), hist2.as<uint32_t>(), B2, g, c2.data(), (int)c2.size(), n, nullptr, nullptr, st);
+  // bucket boundaries come from the caller's full-resolution histogram
   exclusive_scan_i32((const int32_t *)hist_dev, (int32_t *)hist_dev, (int64_t)nbuckets * g.nblocks, nullptr, st);
   if (offsets_dev) {
     part_offsets_kernel<<<(nbuckets + 1 + 255) / 256, 256, 0, st>>>(hist_dev, nbuckets, g.nblocks, n, offsets_dev);
     SB_LAUNCH_CHECK();
   }
-  if (n == 0) return;
-  int done = 0;
-  bool first = true;
-  while (first || done < ncols) {
-    ScatterCols sc;
-    sc.ncols = 0;
-    while (done < ncols && sc.ncols < SCATTER_MAX_COLS) {
-      const SplitCol &c = cols[done++];
-      int k = sc.ncols++;
-      sc.width[k] = c.width;
-      sc.src[k] = c.src;
-      sc.dst[k] = c.dst;
-      sc.src_valid[k] = c.src_valid;
-      sc.dst_valid[k] = c.dst_valid;
-    }
-    if (sc.ncols > 0 || (first && perm_out)) {
-      KernelTimer kt("partition_scatter", st);
-      scatter_kernel<<<g.nblocks, PART_THREADS, smem, st>>>(sc, bucket_dev, hist_dev, n, nbuckets, g.chunk,
-                                                            first ? perm_out : nullptr);
-      SB_LAUNCH_CHECK();
-    }
-    first = false;
-  }
+  SB_CUDA(cudaStreamSynchronize(st));   // temporaries are released by the guard
 }
 
 // mode 0 = hash, 1 = round robin
@@ -257,7 +421,7 @@ static void partition_impl(const sb_table *in, const int32_t *key_cols, int32_t 
   KeyCols keys;
   keys.n = 0;
   if (mode == 0) keys = make_keys(in, key_cols, nkeys);
-  PartGeometry g = part_geometry(n);
+  PartGeometry g = part_geometry(n, nparts);
   Scratch pid(n * 4 + 16, st);
   Scratch hist((int64_t)nparts * g.nblocks * 4 + 16, st);
   Scratch offs_dev((nparts + 1) * 8, st);
@@ -317,7 +481,7 @@ int sb_partition_ids(const sb_table *in, const int32_t *key_cols, int32_t nkeys,
   KeyCols keys = make_keys(in, key_cols, nkeys);
   int64_t n = in->nrows;
   if (n > 0) {
-    PartGeometry g = part_geometry(n);
+    PartGeometry g = part_geometry(n, num_partitions);
     pid_hist_kernel<<<g.nblocks, PART_THREADS, 0, st>>>(keys, n, num_partitions, g.chunk, out_ids_device, nullptr, 0, 0);
     SB_LAUNCH_CHECK();
   }

@@ -123,7 +123,7 @@ static int radix_sort_pairs(uint64_t *keys, uint32_t *vals, int64_t n, cudaStrea
     for (int d = 0; d < 256; d++)
       if (h[b * 256 + d] == (unsigned long long)n) varies[b] = false;   // every record shares this byte: skip the pass
   }
-  PartGeometry g = part_geometry(n);
+  PartGeometry g = part_geometry(n, 256);
   Scratch keys2(n * 8 + 16, st), vals2(n * 4 + 16, st), bucket(n * 4 + 16, st), hist((int64_t)256 * g.nblocks * 4 + 16, st);
   uint64_t *ik = keys, *ok = keys2.as<uint64_t>();
   uint32_t *iv = vals, *ov = vals2.as<uint32_t>();
@@ -149,7 +149,7 @@ static int radix_sort_pairs(uint64_t *keys, uint32_t *vals, int64_t n, cudaStrea
 // stable split of vals by a 0/1 flag (flag[i] belongs to vals[i]): zeros first unless invert
 static void stable_split_by_flag(const uint8_t *flag, int invert, uint32_t *vals, int64_t n, cudaStream_t st) {
   if (n <= 1) return;
-  PartGeometry g = part_geometry(n);
+  PartGeometry g = part_geometry(n, 2);
   Scratch vals2(n * 4 + 16, st), bucket(n * 4 + 16, st), hist((int64_t)2 * g.nblocks * 4 + 16, st);
   flag_hist_kernel<<<g.nblocks, SORT_THREADS, 0, st>>>(flag, invert, n, g.chunk, bucket.as<int32_t>(), hist.as<uint32_t>());
   SB_LAUNCH_CHECK();

@@ -1,0 +1,120 @@
+#!/usr/bin/env python
+"""Per-operator device timings for the rows of SURVEY.md 8a (partition, aggregate, sort, join) -- achieved HBM GB/s
+against the measured peak, one JSON line per case.  Shapes follow the reference's own micro-benchmarks
+(sql/core/benchmarks/*-results.txt) and BASELINE.json configs.  Run on the GPU box:
+    python tools/op_bench.py > gpurun_out/op_bench.jsonl
+Numbers are whole-operator device time (CUDA events on the operator's stream, inputs resident in HBM, best of 5 after
+2 warm-ups, inputs >> L2) plus the dominant kernel's own time from sb_profile_get."""
+import ctypes as C
+import json
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from spark_b200 import _capi as capi                       # noqa: E402
+from spark_b200.columnar import ColumnarBatch, Stream       # noqa: E402
+from spark_b200.execution import (BroadcastHashJoinExec, HashAggregateExec, HashPartitioning, LocalTableScanExec,  # noqa: E402
+                                  ShuffleExchangeExec, SortExec)
+from spark_b200.expressions import Sum, col                 # noqa: E402
+
+
+def peak():
+    try:
+        return json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        return 6650.0
+
+
+def timed(lib, stream, fn, kernel_names, reps=5, warm=2):
+    for _ in range(warm):
+        fn()
+    best = None
+    capi.check(lib.sb_profile_enable(1))
+    for _ in range(reps):
+        capi.check(lib.sb_profile_reset())
+        stream.record_start()
+        fn()
+        stream.record_stop()
+        ms = stream.elapsed_ms()
+        k = {}
+        for name in kernel_names:
+            t, c = C.c_double(), C.c_int64()
+            capi.check(lib.sb_profile_get(name.encode(), C.byref(t), C.byref(c)))
+            k[name] = (t.value, c.value)
+        if best is None or ms < best[0]:
+            best = (ms, k)
+    capi.check(lib.sb_profile_enable(0))
+    return best
+
+
+def emit(case, n, alg_bytes, ms, kernels, extra=None):
+    pk = peak()
+    line = {"case": case, "rows": n, "ms": ms, "rows_per_s": n / (ms / 1e3), "algorithmic_bytes": alg_bytes,
+            "operator_gbs": alg_bytes / (ms / 1e3) / 1e9, "operator_frac_of_measured_peak": alg_bytes / (ms / 1e3) / 1e9 / pk,
+            "kernels_ms": {k: v[0] for k, v in kernels.items()}, "kernel_launches": {k: v[1] for k, v in kernels.items()}}
+    if extra:
+        line.update(extra)
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    only = sys.argv[1] if len(sys.argv) > 1 else ""
+    lib = capi.init(0)
+    stream = Stream()
+    rng = np.random.default_rng(0)
+
+    if only in ("", "partition"):
+        # ---- hash partition: C4-shaped fixed-width lineitem row (74 B/row), n = 2048 and 200 partitions --------------
+        n = 24_000_000
+        cols = {"l_orderkey": rng.integers(0, 1 << 40, n), "l_partkey": rng.integers(0, 1 << 30, n), "l_suppkey": rng.integers(0, 1 << 24, n),
+                "l_quantity": rng.random(n), "l_extendedprice": rng.random(n), "l_discount": rng.random(n), "l_tax": rng.random(n),
+                "l_shipdate": rng.integers(8000, 10000, n).astype(np.int32), "l_commitdate": rng.integers(8000, 10000, n).astype(np.int32),
+                "l_receiptdate": rng.integers(8000, 10000, n).astype(np.int32), "l_linenumber": rng.integers(1, 8, n).astype(np.int32),
+                "l_returnflag": rng.integers(65, 83, n).astype(np.int8), "l_linestatus": rng.integers(70, 80, n).astype(np.int8)}
+        rowbytes = sum(a.dtype.itemsize for a in cols.values())
+        batch = ColumnarBatch.from_numpy(cols, stream)
+        stream.synchronize()
+        for nparts in (2048, 200):
+            ex = ShuffleExchangeExec(HashPartitioning(["l_orderkey"], nparts), LocalTableScanExec(batch))
+            ms, k = timed(lib, stream, lambda: ex.executeColumnar(stream).close(), ["partition_rank", "partition_scatter"])
+            emit("hash_partition n=%d (%d B/row)" % (nparts, rowbytes), n, 2 * rowbytes * n, ms, k)
+        batch.close()
+
+    if only in ("", "agg"):
+        # ---- hash aggregate: SELECT k, SUM(v) GROUP BY k (configs[0] shape, scaled to 64M rows) ---------------------------
+        n = 64_000_000
+        v = rng.integers(-2 ** 31, 2 ** 31, n)
+        for groups in (4, 1024, 65536, 1 << 20):
+            b = ColumnarBatch.from_numpy({"k": rng.integers(0, groups, n), "v": v}, stream)
+            stream.synchronize()
+            agg = HashAggregateExec(["k"], [(Sum(col("v")), "s")], LocalTableScanExec(b), expected_groups=groups)
+            ms, k = timed(lib, stream, lambda: agg.executeColumnar(stream).close(), ["agg_update"])
+            emit("hash_aggregate sum(int64) groups=%d" % groups, n, 16 * n + 16 * groups, ms, k)
+            b.close()
+
+    if only in ("", "sort"):
+        # ---- radix sort: 25M x 8-byte keys (SortBenchmark-results.txt:13) + 16 B records ----------------------------------
+        n = 25_000_000
+        b = ColumnarBatch.from_numpy({"k": rng.integers(-2 ** 63, 2 ** 63 - 1, n)}, stream)
+        stream.synchronize()
+        srt = SortExec([("k", True, True)], LocalTableScanExec(b))
+        ms, k = timed(lib, stream, lambda: srt.executeColumnar(stream).close(), ["partition_rank", "partition_scatter"])
+        emit("sort int64 keys", n, 2 * 8 * n, ms, k, {"note": "8 LSD passes of (8 B key + 4 B row id); algorithmic = one read + one write of the key column"})
+        b.close()
+
+    if only in ("", "join"):
+        # ---- hash join: 21M probe x 65k build (JoinBenchmark-results.txt:10) and a 16M-row build -----------------------------
+        for nb, npr in ((65536, 21_000_000), (16_000_000, 64_000_000)):
+            build = ColumnarBatch.from_numpy({"id": rng.permutation(nb).astype(np.int64), "payload": np.arange(nb, dtype=np.int64)}, stream)
+            probe = ColumnarBatch.from_numpy({"fk": rng.integers(0, nb, npr), "x": np.arange(npr, dtype=np.int64)}, stream)
+            stream.synchronize()
+            j = BroadcastHashJoinExec(["fk"], ["id"], "inner", "right", LocalTableScanExec(probe), LocalTableScanExec(build))
+            ms, k = timed(lib, stream, lambda: j.executeColumnar(stream).close(), ["join_build", "join_probe", "join_fill"])
+            emit("hash_join inner probe=%d build=%d" % (npr, nb), npr, nb * 16 + npr * 16 + npr * 32, ms, k)
+            build.close(); probe.close()
+
+
+if __name__ == "__main__":
+    main()
