@@ -95,8 +95,18 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def _use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host thread it can."""
+    try:
+        ncpu = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncpu = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(ncpu)
+
+
 def cpu_q1(cols, n, reps):
     """Times the oracle's whole-stage restatement of Q1 (Partial per thread + Final merge)."""
+    _use_all_host_threads()
     from oracle import oracle as O
     from spark_b200 import tpch
     L = O.lib()

@@ -134,6 +134,29 @@ struct RegroupCols {
   uint32_t *dst_valid[SCATTER_MAX_COLS];   // pre-set to all ones; NULL rows clear their bit
 };
 
+// one column of one tile: coalesced loads -> staging at the sorted position -> barrier -> run-forming stores.
+// FULLT (tile completely populated) drops every predicate; addresses are base pointers + compile-time offsets.
+template <typename T, bool FULLT>
+__device__ __forceinline__ void regroup_move_column(const void *__restrict__ src, void *__restrict__ dst, int64_t first_row, int tid,
+                                                    const uint32_t (&sp)[RG_ITEMS], const uint32_t (&gdest)[RG_ITEMS], uint32_t amask,
+                                                    uint32_t gmask, uint64_t *staging) {
+  const T *srcp = (const T *)src + first_row;       // row of item 0 for this lane; item `it` is 32 rows further
+  T *stg = (T *)staging;
+  const T *stg_read = (const T *)staging + tid;
+  T v[RG_ITEMS];
+#pragma unroll
+  for (int it = 0; it < RG_ITEMS; it++)
+    if (FULLT || ((amask >> it) & 1)) v[it] = __ldcs(srcp + it * 32);
+#pragma unroll
+  for (int it = 0; it < RG_ITEMS; it++)
+    if (FULLT || ((amask >> it) & 1)) stg[sp[it]] = v[it];
+  __syncthreads();
+#pragma unroll
+  for (int it = 0; it < RG_ITEMS; it++)
+    if (FULLT || ((gmask >> it) & 1)) ((T *)dst)[gdest[it]] = stg_read[it * RG_THREADS];
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(RG_THREADS, 2) regroup_kernel(const __grid_constant__ RegroupCols cols, const int32_t *__restrict__ bucket,
                                                                 const uint32_t *__restrict__ base, int64_t n, int32_t nb, int64_t chunk,
                                                                 int64_t *__restrict__ perm_out) {
@@ -209,23 +232,30 @@ __global__ void __launch_bounds__(RG_THREADS, 2) regroup_kernel(const __grid_con
     }
     __syncthreads();
     uint32_t gdest[RG_ITEMS];    // output row of sorted position j = it * RG_THREADS + tid
+    uint32_t sp[RG_ITEMS];       // sorted position of this thread's rows
+    uint32_t amask = 0, gmask = 0;
 #pragma unroll
     for (int it = 0; it < RG_ITEMS; it++) {
       const int j = it * RG_THREADS + tid;
       if (j < tile_n) {
         const int b = sbucket[j];
         gdest[it] = cursor[b] + (uint32_t)(j - first[b]);
-      } else gdest[it] = 0xFFFFFFFFu;
+        gmask |= 1u << it;
+      } else gdest[it] = 0;
+      sp[it] = bl[it] >> 16;
+      if ((bl[it] & 0xFFFFu) != 0xFFFFu) amask |= 1u << it;
     }
+    const bool fullt = tile_n == RG_TILE;
+    const int64_t first_row = sbase + lane;
     // ---- E: move the columns -----------------------------------------------------------------------------------------------
     if (perm_out) {   // row ids travel like a column (used to gather variable-width columns afterwards)
 #pragma unroll
       for (int it = 0; it < RG_ITEMS; it++)
-        if ((bl[it] & 0xFFFFu) != 0xFFFFu) staging[bl[it] >> 16] = (uint64_t)(sbase + it * 32 + lane);
+        if ((amask >> it) & 1) staging[sp[it]] = (uint64_t)(first_row + it * 32);
       __syncthreads();
 #pragma unroll
       for (int it = 0; it < RG_ITEMS; it++)
-        if (gdest[it] != 0xFFFFFFFFu) perm_out[gdest[it]] = (int64_t)staging[it * RG_THREADS + tid];
+        if ((gmask >> it) & 1) perm_out[gdest[it]] = (int64_t)staging[it * RG_THREADS + tid];
       __syncthreads();
     }
 #pragma unroll 1
@@ -233,18 +263,19 @@ __global__ void __launch_bounds__(RG_THREADS, 2) regroup_kernel(const __grid_con
       const int w = cols.width[c];
       const void *src = cols.src[c];
       void *dst = cols.dst[c];
-#define SB_REGROUP(T)                                                                                     \
-  {                                                                                                       \
-    T v[RG_ITEMS];                                                                                        \
-    _Pragma("unroll") for (int it = 0; it < RG_ITEMS; it++)                                                \
-      if ((bl[it] & 0xFFFFu) != 0xFFFFu) v[it] = __ldcs((const T *)src + sbase + it * 32 + lane);          \
-    _Pragma("unroll") for (int it = 0; it < RG_ITEMS; it++)                                                \
-      if ((bl[it] & 0xFFFFu) != 0xFFFFu) ((T *)staging)[bl[it] >> 16] = v[it];                             \
-    __syncthreads();                                                                                      \
-    _Pragma("unroll") for (int it = 0; it < RG_ITEMS; it++)                                                \
-      if (gdest[it] != 0xFFFFFFFFu) ((T *)dst)[gdest[it]] = ((const T *)staging)[it * RG_THREADS + tid];   \
-    __syncthreads();                                                                                      \
-  }
+      {   // pull the NEXT column's rows of this tile (or the next tile's bucket ids) towards L2 while this column moves
+        const bool last = c + 1 == cols.ncols;
+        const char *nsrc = last ? (const char *)(bucket + RG_TILE) : (const char *)cols.src[c + 1];
+        const int nw = last ? 4 : cols.width[c + 1];
+        if (!last || tbase + RG_TILE + RG_TILE <= end) {
+#pragma unroll
+          for (int it = 0; it < RG_ITEMS; it++)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nsrc + (first_row + it * 32) * nw));
+        }
+      }
+#define SB_REGROUP(T)                                                                                              \
+  if (fullt) regroup_move_column<T, true>(src, dst, first_row, tid, sp, gdest, amask, gmask, staging);              \
+  else regroup_move_column<T, false>(src, dst, first_row, tid, sp, gdest, amask, gmask, staging);
       switch (w) {
         case 1: SB_REGROUP(uint8_t) break;
         case 2: SB_REGROUP(uint16_t) break;
@@ -256,10 +287,10 @@ __global__ void __launch_bounds__(RG_THREADS, 2) regroup_kernel(const __grid_con
         const uint8_t *sv = cols.src_valid[c];
 #pragma unroll
         for (int it = 0; it < RG_ITEMS; it++) {
-          const uint32_t b = bl[it] & 0xFFFFu;
-          if (b == 0xFFFFu) continue;
-          if (!bit_valid(sv, sbase + it * 32 + lane)) {
-            const uint32_t d = cursor[b] + ((bl[it] >> 16) - first[b]);
+          if (!((amask >> it) & 1)) continue;
+          if (!bit_valid(sv, first_row + it * 32)) {
+            const uint32_t b = sbucket[sp[it]];
+            const uint32_t d = cursor[b] + (sp[it] - first[b]);
             atomicAnd(&cols.dst_valid[c][d >> 5], ~(1u << (d & 31)));
           }
         }
