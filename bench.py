@@ -214,11 +214,24 @@ def main():
             finally:
                 inp.close()
 
+    class BatchSource(SparkPlan):
+        """Leaf whose batch is swapped per step, so the operator tree (and its compiled plans) is built once."""
+
+        def __init__(self):
+            self.batch = None
+
+        def executeColumnar(self, stream=None):
+            return self.batch.rename(self.batch.names)
+
+    source = BatchSource()
+    partial_plan = tpch.q1_partial_plan(source, fused=True)
+    if world > 1:
+        partial_plan = AllGatherExec(partial_plan)
+    q1_plan = tpch.q1_final_plan(partial_plan, sort=True)
+
     def q1(batch):
-        partial = tpch.q1_partial_plan(LocalTableScanExec(batch), fused=True)
-        if world > 1:
-            partial = AllGatherExec(partial)
-        return tpch.q1_final_plan(partial, sort=True)
+        source.batch = batch
+        return q1_plan
 
     resident = import_batch()
     stream.synchronize()

@@ -249,6 +249,14 @@ int sb_sort_permutation(const sb_table *in, const sb_sort_order *orders, int32_t
 int sb_top_n(const sb_table *in, const sb_sort_order *orders, int32_t norders, int64_t k, sb_stream *s,
              sb_table **out);
 
+/* RangePartitioning for a global sort (core/src/main/scala/org/apache/spark/Partitioner.scala:175-320, used by
+ * ShuffleExchangeExec.scala:381-401): partition id = number of range bounds the row's key is strictly greater than under
+ * the sort order (getPartition :241-260).  `bounds` is a one-column table holding the numPartitions-1 sorted bounds (the
+ * sampling that picks them stays on the JVM side: RangePartitioner.sketch/determineBounds); rows are regrouped
+ * partition-contiguously with arrival order kept, like sb_hash_partition.  One sort column, fixed-width type. */
+int sb_range_partition(const sb_table *in, const sb_sort_order *order, const sb_table *bounds, sb_stream *s,
+                       sb_table **out, int64_t *out_offsets_host);
+
 /* ---- joins: BroadcastHashJoinExec / ShuffledHashJoinExec / SortMergeJoinExec replacement
  *      (SQLX/joins/HashJoin.scala:184-400, HashedRelation.scala:136-168).  A row with any NULL key
  *      never matches.  Output = probe(streamed) columns ++ build columns; semi/anti = probe only. ---- */

@@ -258,6 +258,37 @@ def round_robin_partition(table, num_partitions, start):
     return take_table(table, perm), offs
 
 
+def range_partition_ids(table, order, bounds):
+    """RangePartitioner.getPartition (core/src/main/scala/org/apache/spark/Partitioner.scala:241-260): the partition of a row
+    is the number of range bounds its key is strictly greater than under the sort ordering (NULL placement and double
+    ordering as in the sort).  order = (col, ascending, nulls_first); bounds = pyarrow array of the sorted bounds."""
+    name, asc, nf = order
+    nb = len(bounds)
+    both = pa.table({"k": pa.concat_arrays([table.column(name).combine_chunks() if isinstance(table.column(name), pa.ChunkedArray) else table.column(name),
+                                            bounds.cast(table.column(name).type)]), "i": np.arange(table.num_rows + nb)})
+    n = table.num_rows
+    pid = np.zeros(n, np.int32)
+    cols = _cols(both, ["k", "i"])
+    ords = (so_sort_order * 1)()
+    ords[0].col = 0; ords[0].ascending = int(asc); ords[0].nulls_first = int(nf)
+    # stable sort of keys ++ bounds: a bound counts for a key iff it sorts strictly before it, i.e. ties must put keys first
+    perm = np.empty(n + nb, np.int64)
+    # order rows so that for equal values keys (index < n) precede bounds (index >= n): arrival order already does that
+    lib().so_sort_rows(_carray(cols), ords, 1, n + nb, perm.ctypes.data)
+    is_bound = perm >= n
+    bounds_before = np.cumsum(is_bound) - is_bound
+    pid_sorted = bounds_before
+    out = np.empty(n + nb, np.int64)
+    out[perm] = pid_sorted
+    return out[:n].astype(np.int32)
+
+
+def range_partition(table, order, bounds):
+    pid = range_partition_ids(table, order, bounds)
+    perm, offs = scatter_by_pid(pid, len(bounds) + 1)
+    return take_table(table, perm), offs
+
+
 # --------------------------------------------------------------------------- sort
 _RADIX_TYPES = {SO_BOOL, SO_INT8, SO_INT16, SO_INT32, SO_INT64, SO_FLOAT32, SO_FLOAT64, SO_DATE32,
                 SO_TIMESTAMP, SO_DECIMAL64}

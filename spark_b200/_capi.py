@@ -93,6 +93,7 @@ _SIGNATURES = {
     "sb_partition_ids": [_p, C.POINTER(_i32), _i32, _i32, _p, _p],
     "sb_hash_partition": [_p, C.POINTER(_i32), _i32, _i32, _p, _pp, C.POINTER(_i64)],
     "sb_round_robin_partition": [_p, _i32, _i32, _p, _pp, C.POINTER(_i64)],
+    "sb_range_partition": [_p, C.POINTER(sb_sort_order), _p, _p, _pp, C.POINTER(_i64)],
     "sb_hash_aggregate": [_p, C.POINTER(sb_agg_plan), _p, _pp],
     "sb_sort": [_p, C.POINTER(sb_sort_order), _i32, _p, _pp],
     "sb_sort_permutation": [_p, C.POINTER(sb_sort_order), _i32, _p, _p],

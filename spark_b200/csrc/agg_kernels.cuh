@@ -20,7 +20,8 @@ constexpr int AGG_MAX_KEYS = 6;
 constexpr int AGG_MAX_WORDS = 4;
 constexpr int AGG_MAX_TERMS = 4;
 constexpr int AGG_MAX_FACT = 3;
-constexpr int AGG_MAX_STAGED = 16;    // distinct buffers (values + validity bitmaps) a staged tile may hold
+constexpr int AGG_MAX_COLS = 20;      // distinct input columns of one plan
+constexpr int AGG_MAX_STAGED = 32;    // distinct buffers (values + validity bitmaps) a staged tile may hold
 constexpr int AGG_MAX_STAGES = 4;
 constexpr int AGG_PROBE_LIMIT = 64;
 constexpr uint64_t EMPTY_KEY = 0xFFFFFFFFFFFFFFFFull;
@@ -39,6 +40,12 @@ struct PlanMeta {
   int32_t slot_kind[AGG_MAX_SLOTS], slot_nf[AGG_MAX_SLOTS], slot_one[AGG_MAX_SLOTS], slot_xform[AGG_MAX_SLOTS],
       slot_cls[AGG_MAX_SLOTS], slot_anyvalid[AGG_MAX_SLOTS];
   int32_t f_type[AGG_MAX_SLOTS][AGG_MAX_FACT], f_mode[AGG_MAX_SLOTS][AGG_MAX_FACT], f_valid[AGG_MAX_SLOTS][AGG_MAX_FACT];
+  // every descriptor names its input by an index into AggArgs::col (distinct columns, numbered in order of first use:
+  // mask, filter terms, keys, slot factors).  With a static plan two descriptors over the same column use the same
+  // pointer expression, so the compiler merges their loads (Q1: 11 loads per row -> 7).
+  int32_t ncols, mask_col;
+  int32_t col_type[AGG_MAX_COLS];
+  int32_t term_col[AGG_MAX_TERMS], key_col[AGG_MAX_KEYS], f_col[AGG_MAX_SLOTS][AGG_MAX_FACT];
 };
 
 struct ColRef {              // where one input buffer lives
@@ -58,12 +65,9 @@ struct KeyExtra {            // wide-key placement (multi-word keys only)
 struct AggArgs {
   PlanMeta meta;
   int64_t n;
-  ColRef mask;                                   // materialised predicate (1 byte / row) when meta.has_mask
-  ColRef term[AGG_MAX_TERMS];
+  ColRef col[AGG_MAX_COLS];                      // distinct input columns (meta.*_col index into this)
   int64_t term_lit[AGG_MAX_TERMS];               // int64 value or double bits
-  ColRef key[AGG_MAX_KEYS];
   KeyExtra key_extra[AGG_MAX_KEYS];
-  ColRef fac[AGG_MAX_SLOTS][AGG_MAX_FACT];
   double fac_lit[AGG_MAX_SLOTS][AGG_MAX_FACT];
   int32_t nwords, nstaged, stage_bytes, nstages;
   StagedBuf staged[AGG_MAX_STAGED];
@@ -238,7 +242,7 @@ __device__ __forceinline__ void apply_filter_terms(const AggArgs &a, const TileC
   plan_for<P>(m.nterms, [&](int i) {
     if (m.term_valid[i]) {
       bool valid[ITEMS];
-      load_valid_batch<ITEMS, FULL, !STAGED>(tile_valid<STAGED>(t, a.term[i]), t, valid);
+      load_valid_batch<ITEMS, FULL, !STAGED>(tile_valid<STAGED>(t, a.col[m.term_col[i]]), t, valid);
 #pragma unroll
       for (int k = 0; k < ITEMS; k++) keep[k] = keep[k] && valid[k];
     }
@@ -247,7 +251,7 @@ __device__ __forceinline__ void apply_filter_terms(const AggArgs &a, const TileC
     int c[ITEMS];
     if (m.term_f64[i]) {
       double x[ITEMS];
-      load_f64_batch<ITEMS, FULL, !STAGED>(tile_ptr<STAGED>(t, a.term[i]), m.term_type[i], t, x);
+      load_f64_batch<ITEMS, FULL, !STAGED>(tile_ptr<STAGED>(t, a.col[m.term_col[i]]), m.term_type[i], t, x);
       const double y = __longlong_as_double(a.term_lit[i]);
 #pragma unroll
       for (int k = 0; k < ITEMS; k++) {   // SQLOrderingUtil.compareDoubles
@@ -256,7 +260,7 @@ __device__ __forceinline__ void apply_filter_terms(const AggArgs &a, const TileC
       }
     } else {
       int64_t x[ITEMS];
-      load_i64_batch<ITEMS, FULL, !STAGED>(tile_ptr<STAGED>(t, a.term[i]), m.term_type[i], t, x);
+      load_i64_batch<ITEMS, FULL, !STAGED>(tile_ptr<STAGED>(t, a.col[m.term_col[i]]), m.term_type[i], t, x);
       const int64_t lit = a.term_lit[i];
 #pragma unroll
       for (int k = 0; k < ITEMS; k++) c[k] = x[k] == lit ? 0 : (x[k] < lit ? -1 : 1);
@@ -278,7 +282,7 @@ __device__ __forceinline__ void apply_filter_terms(const AggArgs &a, const TileC
 template <class P, int ITEMS, bool FULL, bool STAGED>
 __device__ __forceinline__ void factor_batch(const AggArgs &a, int s, int f, const TileCtx &t, double (&y)[ITEMS]) {
   const PlanMeta &m = P::meta(a);
-  load_f64_batch<ITEMS, FULL, !STAGED>(tile_ptr<STAGED>(t, a.fac[s][f]), m.f_type[s][f], t, y);
+  load_f64_batch<ITEMS, FULL, !STAGED>(tile_ptr<STAGED>(t, a.col[m.f_col[s][f]]), m.f_type[s][f], t, y);
   const int mode = m.f_mode[s][f];
   if (mode == F_COL) return;
   const double lit = a.fac_lit[s][f];
@@ -333,7 +337,7 @@ __device__ __forceinline__ void slot_values(const AggArgs &a, int s, const TileC
     }
   } else {
     int64_t x[ITEMS];
-    load_i64_batch<ITEMS, FULL, !STAGED>(tile_ptr<STAGED>(t, a.fac[s][0]), m.f_type[s][0], t, x);
+    load_i64_batch<ITEMS, FULL, !STAGED>(tile_ptr<STAGED>(t, a.col[m.f_col[s][0]]), m.f_type[s][0], t, x);
     const uint64_t flip = xform == X_SIGNED ? 0x8000000000000000ull : 0ull;
 #pragma unroll
     for (int k = 0; k < ITEMS; k++) v[k] = (uint64_t)x[k] ^ flip;
@@ -348,7 +352,7 @@ __device__ __forceinline__ void slot_input_valid(const AggArgs &a, int s, const 
   plan_for<P>(m.slot_nf[s], [&](int f) {
     if (m.f_valid[s][f]) {
       bool valid[ITEMS];
-      load_valid_batch<ITEMS, FULL, !STAGED>(tile_valid<STAGED>(t, a.fac[s][f]), t, valid);
+      load_valid_batch<ITEMS, FULL, !STAGED>(tile_valid<STAGED>(t, a.col[m.f_col[s][f]]), t, valid);
 #pragma unroll
       for (int k = 0; k < ITEMS; k++) ok[k] = ok[k] && valid[k];
     }
@@ -492,7 +496,7 @@ __device__ __forceinline__ void process_tile(const AggArgs &a, const TileCtx &t,
   }
   if (m.has_mask) {
     int64_t x[ITEMS];
-    load_batch_as_i64<ITEMS, FULL, !STAGED, uint8_t>(tile_ptr<STAGED>(t, a.mask), t, x);
+    load_batch_as_i64<ITEMS, FULL, !STAGED, uint8_t>(tile_ptr<STAGED>(t, a.col[m.mask_col]), t, x);
 #pragma unroll
     for (int k = 0; k < ITEMS; k++) keep[k] = keep[k] && x[k] != 0;
   }
@@ -503,7 +507,7 @@ __device__ __forceinline__ void process_tile(const AggArgs &a, const TileCtx &t,
   for (int k = 0; k < ITEMS; k++) special[k] = 0;
   if (m.single64) {
     int64_t x[ITEMS];
-    load_batch_as_i64<ITEMS, FULL, !STAGED, int64_t>(tile_ptr<STAGED>(t, a.key[0]), t, x);      // raw 64-bit words
+    load_batch_as_i64<ITEMS, FULL, !STAGED, int64_t>(tile_ptr<STAGED>(t, a.col[m.key_col[0]]), t, x);      // raw 64-bit words
     if (m.key_type[0] == SB_FLOAT64) {   // NormalizeFloatingNumbers: -0.0 -> 0.0, NaN canonical
 #pragma unroll
       for (int k = 0; k < ITEMS; k++) {
@@ -518,7 +522,7 @@ __device__ __forceinline__ void process_tile(const AggArgs &a, const TileCtx &t,
     }
     if (m.key_valid[0]) {
       bool valid[ITEMS];
-      load_valid_batch<ITEMS, FULL, !STAGED>(tile_valid<STAGED>(t, a.key[0]), t, valid);
+      load_valid_batch<ITEMS, FULL, !STAGED>(tile_valid<STAGED>(t, a.col[m.key_col[0]]), t, valid);
 #pragma unroll
       for (int k = 0; k < ITEMS; k++) special[k] = valid[k] ? special[k] : 1;
     }
@@ -526,7 +530,7 @@ __device__ __forceinline__ void process_tile(const AggArgs &a, const TileCtx &t,
     plan_for<P>(m.nkeys, [&](int i) {
       const int kt = m.key_type[i], bits = m.key_bits[i], shift = m.key_shift[i];
       int64_t x[ITEMS];
-      load_i64_batch<ITEMS, FULL, !STAGED>(tile_ptr<STAGED>(t, a.key[i]), kt, t, x);
+      load_i64_batch<ITEMS, FULL, !STAGED>(tile_ptr<STAGED>(t, a.col[m.key_col[i]]), kt, t, x);
       if (kt == SB_FLOAT32) {
 #pragma unroll
         for (int k = 0; k < ITEMS; k++) {
@@ -538,7 +542,7 @@ __device__ __forceinline__ void process_tile(const AggArgs &a, const TileCtx &t,
       if (m.key_valid[i]) {
         const int nshift = m.key_nshift[i];
         bool valid[ITEMS];
-        load_valid_batch<ITEMS, FULL, !STAGED>(tile_valid<STAGED>(t, a.key[i]), t, valid);
+        load_valid_batch<ITEMS, FULL, !STAGED>(tile_valid<STAGED>(t, a.col[m.key_col[i]]), t, valid);
 #pragma unroll
         for (int k = 0; k < ITEMS; k++) key[k] |= valid[k] ? ((uint64_t)x[k] & vmask) << shift : 1ull << nshift;
       } else {
@@ -635,11 +639,7 @@ __device__ __forceinline__ void prefetch_col(const void *data, int32_t type, int
 template <class P, int ITEMS>
 __device__ __forceinline__ void prefetch_tile(const AggArgs &a, int64_t row0) {
   const PlanMeta &m = P::meta(a);
-  plan_for<P>(m.nterms, [&](int i) { prefetch_col<ITEMS>(a.term[i].data, m.term_type[i], row0); });
-  plan_for<P>(m.nkeys, [&](int i) { prefetch_col<ITEMS>(a.key[i].data, m.key_type[i], row0); });
-  plan_for<P>(m.nslots, [&](int s) {
-    plan_for<P>(m.slot_nf[s], [&](int f) { prefetch_col<ITEMS>(a.fac[s][f].data, m.f_type[s][f], row0); });
-  });
+  plan_for<P>(m.ncols, [&](int c) { prefetch_col<ITEMS>(a.col[c].data, m.col_type[c], row0); });
 }
 
 // ---- direct kernel: columns are read straight from HBM --------------------------------------------------------------
@@ -810,7 +810,7 @@ __global__ void __launch_bounds__(AGG_THREADS) agg_update_wide_kernel(const __gr
     }
     if (m.has_mask) {
       int64_t x[ITEMS];
-      load_batch_as_i64<ITEMS, false, true, uint8_t>(a.mask.data, t, x);
+      load_batch_as_i64<ITEMS, false, true, uint8_t>(a.col[m.mask_col].data, t, x);
 #pragma unroll
       for (int k = 0; k < ITEMS; k++) keep[k] = keep[k] && x[k] != 0;
     }
@@ -820,9 +820,9 @@ __global__ void __launch_bounds__(AGG_THREADS) agg_update_wide_kernel(const __gr
       const KeyExtra ke = a.key_extra[i];
       int64_t x[ITEMS];
       bool valid[ITEMS];
-      if (kt == SB_FLOAT64) load_batch_as_i64<ITEMS, false, true, int64_t>(a.key[i].data, t, x);
-      else load_i64_batch<ITEMS, false, true>(a.key[i].data, kt, t, x);
-      if (m.key_valid[i]) load_valid_batch<ITEMS, false, true>(a.key[i].valid, t, valid);
+      if (kt == SB_FLOAT64) load_batch_as_i64<ITEMS, false, true, int64_t>(a.col[m.key_col[i]].data, t, x);
+      else load_i64_batch<ITEMS, false, true>(a.col[m.key_col[i]].data, kt, t, x);
+      if (m.key_valid[i]) load_valid_batch<ITEMS, false, true>(a.col[m.key_col[i]].valid, t, valid);
 #pragma unroll
       for (int k = 0; k < ITEMS; k++) {
         if (m.key_valid[i] && !valid[k]) {

@@ -26,6 +26,7 @@
 // 1e-6 relative for them, exact for keys/counts/integer sums/min/max.
 #include <math.h>
 #include <stdlib.h>
+#include <memory>
 #include "agg_kernels.cuh"
 #include "expr.cuh"
 #include "primitives.cuh"
@@ -50,7 +51,12 @@ namespace sb {
     /* slot_anyvalid */ {0},                                                                                            \
     /* f_type */ {{SB_F64, 0, 0}, {SB_F64, 0, 0}, {SB_F64, SB_F64, 0}, {SB_F64, SB_F64, SB_F64}, {0, 0, 0}, {SB_F64, 0, 0}}, \
     /* f_mode */ {{F_COL, 0, 0}, {F_COL, 0, 0}, {F_COL, F_LIT_MINUS_COL, 0}, {F_COL, F_LIT_MINUS_COL, F_LIT_PLUS_COL}, {0, 0, 0}, {F_COL, 0, 0}}, \
-    /* f_valid */ {{0}}                                                                                                 \
+    /* f_valid */ {{0}},                                                                                                \
+    /* ncols, mask_col */ 7, 0,                                                                                         \
+    /* col_type: shipdate, returnflag, linestatus, quantity, extendedprice, discount, tax */                            \
+    {SB_DATE32, SB_INT8, SB_INT8, SB_F64, SB_F64, SB_F64, SB_F64},                                                       \
+    /* term_col */ {0, 0, 0, 0}, /* key_col */ {1, 2, 0, 0, 0, 0},                                                      \
+    /* f_col */ {{3, 0, 0}, {4, 0, 0}, {4, 5, 0}, {4, 5, 6}, {0, 0, 0}, {5, 0, 0}}                                       \
   }
 __device__ const PlanMeta kDevMetaQ1Partial = SB_META_Q1_PARTIAL;
 static const PlanMeta kHostMetaQ1Partial = SB_META_Q1_PARTIAL;
@@ -58,7 +64,8 @@ static const PlanMeta kHostMetaQ1Partial = SB_META_Q1_PARTIAL;
 #define SB_META_C1(VKIND, VTYPE, VCLS)                                                                                  \
   {                                                                                                                     \
     0, 0, 1, 1, 1, 0, {0}, {0}, {0}, {0}, {SB_INT64, 0, 0, 0, 0, 0}, {64, 0, 0, 0, 0, 0}, {0}, {-1, 0, 0, 0, 0, 0}, {0}, \
-    {VKIND}, {1}, {0}, {0}, {VCLS}, {0}, {{VTYPE, 0, 0}}, {{F_COL, 0, 0}}, {{0}}                                         \
+    {VKIND}, {1}, {0}, {0}, {VCLS}, {0}, {{VTYPE, 0, 0}}, {{F_COL, 0, 0}}, {{0}},                                        \
+    2, 0, {SB_INT64, VTYPE}, {0}, {0}, {{1, 0, 0}}                                                                      \
   }
 __device__ const PlanMeta kDevMetaC1I64 = SB_META_C1(K_ADD_I64, SB_INT64, CLS_GENERIC);
 static const PlanMeta kHostMetaC1I64 = SB_META_C1(K_ADD_I64, SB_INT64, CLS_GENERIC);
@@ -251,6 +258,11 @@ struct HostFactor {
   int32_t type = 0, mode = F_COL;
   double lit = 0;
 };
+struct HostRef {
+  const void *data = nullptr;
+  const uint8_t *valid = nullptr;
+  int32_t type = 0;
+};
 struct HostSlot {
   int32_t kind = 0, nf = 0, is_one = 0, xform = X_NONE;
   HostFactor f[AGG_MAX_FACT];
@@ -298,7 +310,7 @@ static bool match_product(const sb_table *in, const sb_expr &e, HostSlot &s) {
   return true;
 }
 
-static bool match_filter(const sb_table *in, const sb_expr &e, AggArgs &a) {
+static bool match_filter(const sb_table *in, const sb_expr &e, AggArgs &a, HostRef *term_refs) {
   std::vector<ExprTree> t;
   int root = build_tree(e, t);
   std::vector<int> work{root};
@@ -312,7 +324,7 @@ static bool match_filter(const sb_table *in, const sb_expr &e, AggArgs &a) {
     if (m.nterms >= AGG_MAX_TERMS) return false;
     const int ti = m.nterms;
     auto set = [&](const Column &c, int op, int is_f64, int64_t lit) {
-      a.term[ti].data = c.d(); a.term[ti].valid = c.v();
+      term_refs[ti] = {c.d(), c.v(), c.type};
       m.term_type[ti] = c.type; m.term_op[ti] = op; m.term_f64[ti] = is_f64; m.term_valid[ti] = c.validity != nullptr;
       a.term_lit[ti] = lit;
       m.nterms++;
@@ -431,7 +443,18 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
   memset(&a, 0, sizeof(a));
   PlanMeta &m = a.meta;
   a.n = n;
+  // distinct input columns, numbered in order of first use (mask, filter terms, keys, slot factors)
+  auto col_index = [&](const void *data, const uint8_t *valid, int32_t type) -> int {
+    for (int i = 0; i < m.ncols; i++)
+      if (a.col[i].data == data && a.col[i].valid == valid && m.col_type[i] == type) return i;
+    if (m.ncols >= AGG_MAX_COLS) fail(SB_ERR_UNSUPPORTED, "aggregate references more than %d distinct columns", AGG_MAX_COLS);
+    a.col[m.ncols].data = data;
+    a.col[m.ncols].valid = valid;
+    m.col_type[m.ncols] = type;
+    return m.ncols++;
+  };
   std::vector<OutPlan> outs;
+  HostRef mask_ref, term_refs[AGG_MAX_TERMS], key_refs[AGG_MAX_KEYS];
   void *mask_ptr = nullptr;
 
   struct Cleanup {
@@ -453,8 +476,7 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
     SB_REQUIRE(ci >= 0 && ci < (int)in->cols.size(), "key column %d out of range", ci);
     const Column &c = in->cols[ci];
     if (c.type == SB_STRING) fail(SB_ERR_UNSUPPORTED, "string grouping keys are not supported (dictionary-encode them)");
-    a.key[k].data = c.d();
-    a.key[k].valid = c.v();
+    key_refs[k] = {c.d(), c.v(), c.type};
     m.key_type[k] = c.type;
     m.key_bits[k] = type_width(c.type) * 8;
     m.key_valid[k] = c.validity != nullptr;
@@ -512,14 +534,15 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
   // ---- fused filter ---------------------------------------------------------------------------
   if (plan->filter) {
     expr_validate(in, *plan->filter);
-    if (!match_filter(in, *plan->filter, a)) {
+    if (!match_filter(in, *plan->filter, a, term_refs)) {
       m.nterms = 0;
       memset(m.term_type, 0, sizeof(m.term_type)); memset(m.term_op, 0, sizeof(m.term_op));
       memset(m.term_f64, 0, sizeof(m.term_f64)); memset(m.term_valid, 0, sizeof(m.term_valid));
-      memset(a.term, 0, sizeof(a.term)); memset(a.term_lit, 0, sizeof(a.term_lit));
+      for (auto &r : term_refs) r = HostRef();
+      memset(a.term_lit, 0, sizeof(a.term_lit));
       SB_CUDA(cudaMallocAsync(&mask_ptr, (size_t)n + 16, st));
       eval_predicate(in, *plan->filter, (uint8_t *)mask_ptr, st);
-      a.mask.data = mask_ptr;
+      mask_ref = {mask_ptr, nullptr, SB_INT8};
       m.has_mask = 1;
     }
   }
@@ -619,6 +642,10 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
       default: fail(SB_ERR_INVALID, "unknown aggregate function %d", sp.func);
     }
   }
+  // ---- columns: canonical numbering (mask, filter terms, keys, slot factors) -------------------------------------
+  if (m.has_mask) m.mask_col = col_index(mask_ref.data, mask_ref.valid, mask_ref.type);
+  for (int i = 0; i < m.nterms; i++) m.term_col[i] = col_index(term_refs[i].data, term_refs[i].valid, term_refs[i].type);
+  for (int i = 0; i < m.nkeys; i++) m.key_col[i] = col_index(key_refs[i].data, key_refs[i].valid, key_refs[i].type);
   // ---- slots -> PlanMeta + argument arrays -----------------------------------------------------------------
   m.nslots = (int)b.slots.size();
   for (int i = 0; i < m.nslots; i++) {
@@ -627,8 +654,7 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
     m.slot_cls[i] = CLS_GENERIC;
     bool any_valid = false, plain = sl.nf >= 1;
     for (int k = 0; k < sl.nf; k++) {
-      a.fac[i][k].data = sl.f[k].data;
-      a.fac[i][k].valid = sl.f[k].valid;
+      m.f_col[i][k] = col_index(sl.f[k].data, sl.f[k].valid, sl.f[k].type);
       a.fac_lit[i][k] = sl.f[k].lit;
       m.f_type[i][k] = sl.f[k].type; m.f_mode[i][k] = sl.f[k].mode; m.f_valid[i][k] = sl.f[k].valid != nullptr;
       any_valid |= sl.f[k].valid != nullptr;
@@ -678,15 +704,11 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
       cursor += (bytes_per_tile + 127) / 128 * 128;
       return sb_.soff;
     };
-    auto place = [&](ColRef &c, int32_t type) {
-      c.soff = c.data ? stage_of(c.data, (int)stile * type_width(type)) : 0;
+    for (int i = 0; i < m.ncols; i++) {
+      ColRef &c = a.col[i];
+      c.soff = c.data ? stage_of(c.data, (int)stile * type_width(m.col_type[i] ? m.col_type[i] : SB_INT8)) : 0;
       c.svoff = c.valid ? stage_of(c.valid, (int)stile / 8) : -1;
-    };
-    if (m.has_mask) place(a.mask, SB_INT8);
-    for (int i = 0; i < m.nterms; i++) place(a.term[i], m.term_type[i]);
-    for (int i = 0; i < m.nkeys; i++) place(a.key[i], m.key_type[i]);
-    for (int i = 0; i < ns; i++)
-      for (int f = 0; f < m.slot_nf[i]; f++) place(a.fac[i][f], m.f_type[i][f] ? m.f_type[i][f] : SB_INT8);
+    }
     if (staged && a.nstaged > 0) {
       a.stage_bytes = cursor;
       const size_t fixed = 64 + smem_acc;   // mbarriers + dictionary + accumulators
@@ -707,7 +729,9 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
     } else staged = false;
   }
 
-  Scratch flags(16, st);
+  Scratch flags(32, st);
+  std::unique_ptr<Scratch> slot_ids_buf;
+  int64_t ngroups = 0;
   void *tkeys = nullptr, *tacc = nullptr;
   struct TableFree {
     void *&k, *&v;
@@ -727,7 +751,7 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
     SB_CUDA(cudaMemsetAsync(tacc, 0, (size_t)slots * 8 * (ns ? ns : 1), st));
     for (int s = 0; s < ns; s++)
       if (m.slot_kind[s] == K_MIN_U64) SB_CUDA(cudaMemsetAsync((uint64_t *)tacc + (int64_t)s * slots, 0xff, (size_t)slots * 8, st));
-    SB_CUDA(cudaMemsetAsync(flags.ptr, 0, 16, st));
+    SB_CUDA(cudaMemsetAsync(flags.ptr, 0, 32, st));
     a.tkeys = (uint64_t *)tkeys;
     a.tacc = (uint64_t *)tacc;
     a.flags = flags.as<int32_t>();
@@ -741,10 +765,23 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
       else agg_update_wide_kernel<4, 4><<<grid, AGG_THREADS, 0, st>>>(a);
       SB_LAUNCH_CHECK();
     }
-    int32_t hflags[4];
-    SB_CUDA(cudaMemcpyAsync(hflags, flags.ptr, 16, cudaMemcpyDeviceToHost, st));
-    SB_CUDA(cudaStreamSynchronize(st));
-    if (!hflags[0]) break;
+    // occupied slots -> dense list; the abort flag and the group count come back with ONE host round trip
+    {
+      const int64_t slots_now = cap + 2;
+      slot_ids_buf.reset(new Scratch(slots_now * 8, st));
+      Scratch occ(slots_now + 16, st), f32(slots_now * 4 + 16, st), pos(slots_now * 8 + 16, st);
+      occupied_kernel<<<(unsigned)((slots_now + 255) / 256), 256, 0, st>>>((uint64_t *)tkeys, cap, flags.as<int32_t>(), occ.as<uint8_t>());
+      SB_LAUNCH_CHECK();
+      compact_mask_async(occ.as<uint8_t>(), slots_now, slot_ids_buf->as<int64_t>(), f32.as<int32_t>(), pos.as<int64_t>(),
+                         (int64_t *)((char *)flags.ptr + 16), st);
+      int64_t host_buf[3];
+      SB_CUDA(cudaMemcpyAsync(host_buf, flags.ptr, 24, cudaMemcpyDeviceToHost, st));
+      SB_CUDA(cudaStreamSynchronize(st));
+      int32_t hflags[4];
+      memcpy(hflags, host_buf, 16);
+      ngroups = host_buf[2];
+      if (!hflags[0]) break;
+    }
     if (cap >= cap_max) fail(SB_ERR_CUDA, "hash aggregate table overflow at maximum capacity %lld", (long long)cap);
     cudaFreeAsync(tkeys, st); tkeys = nullptr;
     cudaFreeAsync(tacc, st); tacc = nullptr;
@@ -752,22 +789,12 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
   }
   if (getenv("SB_AGG_VERBOSE")) fprintf(stderr, "[sb_hash_aggregate] n=%lld plan=%s path=%s cap=%lld slots=%d\n", (long long)n, kc.name,
                                         a.nwords > 1 ? "wide" : (staged ? "staged" : "direct"), (long long)cap, ns);
-
-  // ---- collect occupied slots -------------------------------------------------------------------
-  int64_t slots = cap + 2;
-  int64_t ngroups;
-  Scratch slot_ids(slots * 8, st);
-  {
-    Scratch occ(slots + 16, st);
-    occupied_kernel<<<(unsigned)((slots + 255) / 256), 256, 0, st>>>((uint64_t *)tkeys, cap, flags.as<int32_t>(), occ.as<uint8_t>());
-    SB_LAUNCH_CHECK();
-    ngroups = compact_mask(occ.as<uint8_t>(), slots, slot_ids.as<int64_t>(), st);
-    if (plan->nkeys == 0 && ngroups == 0) {
-      // no grouping keys: exactly one output row even for empty input (AggregateCodegenSupport.scala:131);
-      // slot 0 of the untouched table holds the identities
-      SB_CUDA(cudaMemsetAsync(slot_ids.ptr, 0, 8, st));
-      ngroups = 1;
-    }
+  Scratch &slot_ids = *slot_ids_buf;
+  if (plan->nkeys == 0 && ngroups == 0) {
+    // no grouping keys: exactly one output row even for empty input (AggregateCodegenSupport.scala:131);
+    // slot 0 of the untouched table holds the identities
+    SB_CUDA(cudaMemsetAsync(slot_ids.ptr, 0, 8, st));
+    ngroups = 1;
   }
 
   // ---- emit -------------------------------------------------------------------------------------
@@ -816,7 +843,7 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
       agg_emit_kernel<<<(unsigned)((ngroups + 255) / 256), 256, 0, st>>>(e);
       SB_LAUNCH_CHECK();
     }
-    SB_CUDA(cudaStreamSynchronize(st));
+    // no host synchronisation: the table buffers stay valid until after the emit kernel in stream order
   } catch (...) {
     table_free(t);
     throw;

@@ -94,6 +94,7 @@ struct Buffer {  // a device allocation shared between tables (select/zip share 
   void *ptr = nullptr;
   int64_t bytes = 0;
   bool owned = true;
+  cudaStream_t st = nullptr;   // allocation stream: the buffer is freed in this stream's order (or stream 0 once it is gone)
   std::atomic<int> refs{1};
 };
 Buffer *buffer_alloc(int64_t bytes, cudaStream_t st);   // stream-ordered pool allocation

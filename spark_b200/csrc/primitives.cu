@@ -278,6 +278,19 @@ __global__ void compact_write_kernel(const uint8_t *__restrict__ mask, const int
   if (i < n && mask[i]) out[pos[i]] = i;
 }
 
+void compact_mask_async(const uint8_t *mask, int64_t n, int64_t *out_idx, int32_t *flags, int64_t *pos, int64_t *total_dev, cudaStream_t st) {
+  if (n == 0) {
+    SB_CUDA(cudaMemsetAsync(total_dev, 0, 8, st));
+    return;
+  }
+  unsigned nb = (unsigned)((n + 255) / 256);
+  mask_to_i32_kernel<<<nb, 256, 0, st>>>(mask, n, flags);
+  SB_LAUNCH_CHECK();
+  exclusive_scan_i32_to_i64(flags, pos, n, total_dev, st);
+  compact_write_kernel<<<nb, 256, 0, st>>>(mask, pos, n, out_idx);
+  SB_LAUNCH_CHECK();
+}
+
 int64_t compact_mask(const uint8_t *mask, int64_t n, int64_t *out_idx, cudaStream_t st) {
   if (n == 0) return 0;
   Scratch flags(n * 4, st), pos(n * 8, st), total(8, st);

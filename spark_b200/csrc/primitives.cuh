@@ -20,6 +20,10 @@ Column gather_column(const Column &c, const int64_t *idx_dev, int64_t nout, bool
 // indices of rows whose mask byte is non-zero, in row order; returns count (synchronizes the stream)
 int64_t compact_mask(const uint8_t *mask_dev, int64_t n, int64_t *out_idx_dev, cudaStream_t st);
 
+// same without the host round trip: the count lands in *total_dev (device); scratch buffers come from the caller
+void compact_mask_async(const uint8_t *mask_dev, int64_t n, int64_t *out_idx_dev, int32_t *flags_scratch, int64_t *pos_scratch,
+                        int64_t *total_dev, cudaStream_t st);
+
 // fills idx[i] = begin + i
 void iota_i64(int64_t *out, int64_t n, int64_t begin, cudaStream_t st);
 

@@ -31,9 +31,21 @@ void require_init() {
   if (!rt().initialized) fail(SB_ERR_NOT_INITIALIZED, "sb_init has not been called (no CUDA device bound)");
 }
 
+// streams created through sb_stream_create that are still alive (buffers free themselves in their stream's order)
+static std::mutex g_streams_mu;
+static std::vector<cudaStream_t> g_live_streams;
+static bool stream_alive(cudaStream_t st) {
+  if (st == nullptr) return true;
+  std::lock_guard<std::mutex> lk(g_streams_mu);
+  for (auto s : g_live_streams)
+    if (s == st) return true;
+  return false;
+}
+
 Buffer *buffer_alloc(int64_t bytes, cudaStream_t st) {
   Buffer *b = new Buffer();
   b->bytes = bytes;
+  b->st = st;
   if (bytes > 0) {
     cudaError_t e = cudaMallocAsync(&b->ptr, (size_t)bytes, st);
     if (e != cudaSuccess) {
@@ -57,7 +69,7 @@ void buffer_retain(Buffer *b) {
 void buffer_release(Buffer *b) {
   if (!b) return;
   if (b->refs.fetch_sub(1) == 1) {
-    if (b->owned && b->ptr) cudaFreeAsync(b->ptr, 0);
+    if (b->owned && b->ptr) cudaFreeAsync(b->ptr, stream_alive(b->st) ? b->st : (cudaStream_t)0);
     delete b;
   }
 }
@@ -251,6 +263,10 @@ int sb_stream_create(sb_stream **out) {
   SB_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
   SB_CUDA(cudaEventCreate(&s->ev_start));
   SB_CUDA(cudaEventCreate(&s->ev_stop));
+  {
+    std::lock_guard<std::mutex> lk(g_streams_mu);
+    g_live_streams.push_back(s->stream);
+  }
   *out = s;
   SB_API_END
 }
@@ -258,6 +274,11 @@ int sb_stream_destroy(sb_stream *s) {
   SB_API_BEGIN
   if (s) {
     cudaStreamSynchronize(s->stream);
+    {
+      std::lock_guard<std::mutex> lk(g_streams_mu);
+      for (size_t i = 0; i < g_live_streams.size(); i++)
+        if (g_live_streams[i] == s->stream) { g_live_streams.erase(g_live_streams.begin() + i); break; }
+    }
     cudaEventDestroy(s->ev_start);
     cudaEventDestroy(s->ev_stop);
     cudaStreamDestroy(s->stream);

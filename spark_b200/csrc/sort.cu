@@ -106,9 +106,31 @@ __global__ void __launch_bounds__(SORT_THREADS) flag_hist_kernel(const uint8_t *
   if (threadIdx.x < 2) hist[(int64_t)threadIdx.x * gridDim.x + blockIdx.x] = sh[threadIdx.x];
 }
 
+// Tiny inputs (the 4-row result of Q1, top-N candidates): one block ranks every element by counting -- rank = #keys smaller +
+// #equal keys with a smaller position -- which is a stable sort in one launch with no host round trip.
+constexpr int SMALL_SORT_MAX = 2048;
+__global__ void __launch_bounds__(256) small_sort_kernel(uint64_t *keys, uint32_t *vals, int n) {
+  __shared__ uint64_t sk[SMALL_SORT_MAX];
+  __shared__ uint32_t sv[SMALL_SORT_MAX];
+  for (int i = threadIdx.x; i < n; i += 256) { sk[i] = keys[i]; sv[i] = vals[i]; }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const uint64_t k = sk[i];
+    int rank = 0;
+    for (int j = 0; j < n; j++) rank += (sk[j] < k) || (sk[j] == k && j < i);
+    keys[rank] = k;
+    vals[rank] = sv[i];
+  }
+}
+
 // Stable ascending LSD radix sort of (keys, vals) in place (ping-pong buffers inside).  Returns passes run.
 static int radix_sort_pairs(uint64_t *keys, uint32_t *vals, int64_t n, cudaStream_t st) {
   if (n <= 1) return 0;
+  if (n <= SMALL_SORT_MAX) {
+    small_sort_kernel<<<1, 256, 0, st>>>(keys, vals, (int)n);
+    SB_LAUNCH_CHECK();
+    return 1;
+  }
   Scratch counts(8 * 256 * 8, st);
   SB_CUDA(cudaMemsetAsync(counts.ptr, 0, 8 * 256 * 8, st));
   int grid = grid_for(n, SORT_THREADS * 8, rt().num_sms * 8);
@@ -142,8 +164,7 @@ static int radix_sort_pairs(uint64_t *keys, uint32_t *vals, int64_t n, cudaStrea
     SB_CUDA(cudaMemcpyAsync(keys, ik, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
     SB_CUDA(cudaMemcpyAsync(vals, iv, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
   }
-  SB_CUDA(cudaStreamSynchronize(st));   // scratch buffers die here
-  return passes;
+  return passes;   // scratch buffers are freed in stream order
 }
 
 // stable split of vals by a 0/1 flag (flag[i] belongs to vals[i]): zeros first unless invert
@@ -156,7 +177,6 @@ static void stable_split_by_flag(const uint8_t *flag, int invert, uint32_t *vals
   SplitCol col = {4, vals, vals2.ptr, nullptr, nullptr};
   multisplit_scatter(bucket.as<int32_t>(), hist.as<uint32_t>(), 2, g, &col, 1, n, nullptr, nullptr, st);
   SB_CUDA(cudaMemcpyAsync(vals, vals2.ptr, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
-  SB_CUDA(cudaStreamSynchronize(st));
 }
 
 // ---- UnsafeInMemorySorter.insertRecord replay (radix path with NULLs) ----------------------------------
@@ -204,6 +224,45 @@ __global__ void u32_to_i64_kernel(const uint32_t *__restrict__ in, int64_t n, in
 }
 
 static inline unsigned nblk(int64_t n) { return (unsigned)((n + 255) / 256); }
+
+// RangePartitioner.getPartition (core/.../Partitioner.scala:241-260): partition = #bounds the key is strictly greater than.
+// Keys and bounds are compared as (null rank, order-preserving key): NULLs sort before everything when nulls_first, after
+// everything otherwise, exactly as the sort itself orders them.  Bounds are few (numPartitions - 1): binary search in shared memory.
+__global__ void __launch_bounds__(SORT_THREADS) range_pid_hist_kernel(const void *data, const uint8_t *valid, int32_t type, int desc,
+                                                                      int nulls_first, const void *bdata, const uint8_t *bvalid, int32_t nbounds,
+                                                                      int64_t n, int64_t chunk, int32_t *__restrict__ bucket,
+                                                                      uint32_t *__restrict__ hist) {
+  extern __shared__ uint64_t rp_smem[];
+  uint64_t *bkey = rp_smem;                               // [nbounds]
+  uint8_t *bnull = (uint8_t *)(bkey + nbounds);           // [nbounds]
+  uint32_t *sh = (uint32_t *)(((uintptr_t)(bnull + nbounds) + 3) & ~(uintptr_t)3);   // [nbounds + 1]
+  for (int i = threadIdx.x; i < nbounds; i += SORT_THREADS) {
+    bool v = bit_valid(bvalid, i);
+    bkey[i] = v ? sort_key(bdata, type, i, desc != 0) : 0;
+    bnull[i] = !v;
+  }
+  for (int i = threadIdx.x; i <= nbounds; i += SORT_THREADS) sh[i] = 0;
+  __syncthreads();
+  int64_t begin = (int64_t)blockIdx.x * chunk;
+  int64_t end = begin + chunk < n ? begin + chunk : n;
+  for (int64_t i = begin + threadIdx.x; i < end; i += SORT_THREADS) {
+    const bool v = bit_valid(valid, i);
+    const uint64_t k = v ? sort_key(data, type, i, desc != 0) : 0;
+    // rank of a value: NULL is 0 (first) or 2 (last), non-null is 1
+    const int kr = v ? 1 : (nulls_first ? 0 : 2);
+    int lo = 0, hi = nbounds;                            // count of bounds strictly less than the key
+    while (lo < hi) {
+      int mid = (lo + hi) >> 1;
+      const int br = bnull[mid] ? (nulls_first ? 0 : 2) : 1;
+      const bool less = br < kr || (br == kr && kr == 1 && bkey[mid] < k);
+      if (less) lo = mid + 1; else hi = mid;
+    }
+    bucket[i] = lo;
+    atomicAdd(&sh[lo], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i <= nbounds; i += SORT_THREADS) hist[(int64_t)i * gridDim.x + blockIdx.x] = sh[i];
+}
 
 static bool radix_eligible(int32_t type) { return type != SB_STRING; }
 
@@ -342,8 +401,51 @@ int sb_sort(const sb_table *in, const sb_sort_order *orders, int32_t norders, sb
     u32_to_i64_kernel<<<nblk(n), 256, 0, st>>>(perm.as<uint32_t>(), n, perm64.as<int64_t>());
     SB_LAUNCH_CHECK();
   }
-  *out = gather_table(in, perm64.as<int64_t>(), n, false, st);
-  SB_CUDA(cudaStreamSynchronize(st));
+  *out = gather_table(in, perm64.as<int64_t>(), n, false, st);   // stream-ordered: no host synchronisation needed
+  SB_API_END
+}
+
+int sb_range_partition(const sb_table *in, const sb_sort_order *order, const sb_table *bounds, sb_stream *s, sb_table **out,
+                       int64_t *out_offsets_host) {
+  SB_API_BEGIN
+  require_init();
+  SB_REQUIRE(in && order && bounds && out && out_offsets_host, "null argument");
+  SB_REQUIRE(order->col >= 0 && order->col < (int)in->cols.size(), "sort column %d out of range", order->col);
+  SB_REQUIRE(bounds->cols.size() == 1, "bounds must be a one-column table");
+  cudaStream_t st = stream_of(s);
+  const Column &c = in->cols[order->col];
+  const Column &b = bounds->cols[0];
+  SB_REQUIRE(c.type == b.type, "bounds column type %d differs from the sort column type %d", b.type, c.type);
+  if (!radix_eligible(c.type)) fail(SB_ERR_UNSUPPORTED, "range partitioning on string columns is not implemented");
+  for (auto &col : in->cols)
+    if (col.type == SB_STRING) fail(SB_ERR_UNSUPPORTED, "range partitioning of tables with string columns is not implemented");
+  const int64_t n = in->nrows;
+  const int32_t nbounds = (int32_t)bounds->nrows, nparts = nbounds + 1;
+  SB_REQUIRE(nparts <= MULTISPLIT_MAX_BUCKETS && nbounds <= 4096, "too many range bounds (%d)", nbounds);
+  PartGeometry g = part_geometry(n, nparts);
+  Scratch bucket(n * 4 + 16, st), hist((int64_t)nparts * g.nblocks * 4 + 16, st), offs_dev((int64_t)(nparts + 1) * 8, st);
+  size_t smem = (size_t)nbounds * 9 + 8 + (size_t)(nbounds + 1) * 4 + 16;
+  range_pid_hist_kernel<<<g.nblocks, SORT_THREADS, smem, st>>>(c.d(), c.v(), c.type, !order->ascending, order->nulls_first, b.d(), b.v(),
+                                                               nbounds, n, g.chunk, bucket.as<int32_t>(), hist.as<uint32_t>());
+  SB_LAUNCH_CHECK();
+  sb_table *t = table_new(n);
+  try {
+    std::vector<SplitCol> sc;
+    for (auto &col : in->cols) {
+      Column r = column_alloc(col.type, col.scale, n, col.validity != nullptr, st);
+      if (r.validity) SB_CUDA(cudaMemsetAsync(r.validity->ptr, 0xff, (size_t)bitmap_alloc_bytes(n), st));
+      r.null_count = col.null_count;
+      t->cols.push_back(r);
+      sc.push_back({type_width(col.type), col.d(), r.data->ptr, col.v(), r.validity ? (uint32_t *)r.validity->ptr : nullptr});
+    }
+    multisplit_scatter(bucket.as<int32_t>(), hist.as<uint32_t>(), nparts, g, sc.data(), (int)sc.size(), n, nullptr, offs_dev.as<int64_t>(), st);
+    SB_CUDA(cudaMemcpyAsync(out_offsets_host, offs_dev.ptr, (size_t)(nparts + 1) * 8, cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaStreamSynchronize(st));
+  } catch (...) {
+    table_free(t);
+    throw;
+  }
+  *out = t;
   SB_API_END
 }
 
@@ -363,7 +465,6 @@ int sb_top_n(const sb_table *in, const sb_sort_order *orders, int32_t norders, i
     SB_LAUNCH_CHECK();
   }
   *out = gather_table(in, perm64.as<int64_t>(), take, false, st);
-  SB_CUDA(cudaStreamSynchronize(st));
   SB_API_END
 }
 

@@ -134,9 +134,8 @@ class HashAggregateExec(SparkPlan):
         finally:
             inp.close()
 
-    def run(self, inp: ColumnarBatch, stream=None) -> ColumnarBatch:
-        lib = capi.load()
-        schema = _schema_of(inp)
+    def _compile(self, schema: Schema):
+        """Lower the plan to the C structs once per input schema (the Scala operator does this in doPrepare)."""
         keep = []
         key_idx = [schema.index(k) for k in self.groupingExpressions]
         key_arr = (C.c_int32 * max(1, len(key_idx)))(*key_idx)
@@ -158,6 +157,16 @@ class HashAggregateExec(SparkPlan):
             keep.append(fc)
             plan.filter = C.pointer(fc.c)
         plan.expected_groups = self.expected_groups
+        return plan, key_idx, (keep, key_arr, specs)
+
+    def run(self, inp: ColumnarBatch, stream=None) -> ColumnarBatch:
+        lib = capi.load()
+        schema = _schema_of(inp)
+        sig = (tuple(schema.names), tuple(schema.types))
+        cache = self.__dict__.setdefault("_compiled", {})
+        if sig not in cache:
+            cache[sig] = self._compile(schema)
+        plan, key_idx, _keepalive = cache[sig]
         h = C.c_void_p()
         capi.check(lib.sb_hash_aggregate(inp.handle, C.byref(plan), _h(stream), C.byref(h)))
         names = self.output_names()
@@ -179,6 +188,16 @@ class RoundRobinPartitioning:
 
 class SinglePartition:
     numPartitions = 1
+
+
+class RangePartitioning:
+    """RangePartitioning(ordering, numPartitions) with explicit range bounds (a one-column ColumnarBatch holding the
+    numPartitions - 1 sorted bounds; in Spark the RangePartitioner samples them on the JVM side)."""
+
+    def __init__(self, ordering, bounds: ColumnarBatch):
+        self.ordering = ordering if isinstance(ordering, SortOrder) else SortOrder(*ordering)
+        self.bounds = bounds
+        self.numPartitions = bounds.num_rows + 1
 
 
 class ShuffleExchangeExec(SparkPlan):
@@ -211,6 +230,8 @@ class ShuffleExchangeExec(SparkPlan):
             capi.check(lib.sb_hash_partition(inp.handle, arr, len(idx), n, _h(stream), C.byref(h), offs))
         elif isinstance(p, RoundRobinPartitioning):
             capi.check(lib.sb_round_robin_partition(inp.handle, p.start, n, _h(stream), C.byref(h), offs))
+        elif isinstance(p, RangePartitioning):
+            capi.check(lib.sb_range_partition(inp.handle, _orders_c(inp, [p.ordering]), p.bounds.handle, _h(stream), C.byref(h), offs))
         else:
             capi.check(lib.sb_round_robin_partition(inp.handle, 0, 1, _h(stream), C.byref(h), offs))
         return ColumnarBatch(h, inp.names, inp.arrow_types), np.array(list(offs), dtype=np.int64)

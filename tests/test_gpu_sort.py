@@ -132,3 +132,41 @@ def test_sort_full_size_properties(gpu, stream):
     ties = gk[1:] == gk[:-1]
     assert np.all(gr[1:][ties] > gr[:-1][ties])
     assert gr.sum() == n * (n - 1) // 2
+
+
+@pytest.mark.parametrize("asc", [True, False])
+@pytest.mark.parametrize("nulls_first", [True, False])
+@pytest.mark.parametrize("kind", ["int64_small", "float64", "date32"])
+def test_range_partition_and_global_sort(gpu, stream, kind, asc, nulls_first):
+    """Global sort = RangePartitioning exchange + per-partition SortExec (SortExec.scala:54-55 requires
+    OrderedDistribution; RangePartitioner.getPartition Partitioner.scala:241-260).  Partition ids and the stable regrouping
+    must equal the oracle's; sorting every range and concatenating them must give a totally ordered key column."""
+    from spark_b200.columnar import ColumnarBatch
+    from spark_b200.execution import LocalTableScanExec, RangePartitioning, ShuffleExchangeExec, SortExec
+    n = 60000
+    rng = np.random.default_rng(hash((kind, asc, nulls_first)) % 2 ** 32)
+    t = pa.table({"k": _col(kind, n, rng, 0.1), "row": np.arange(n, dtype=np.int64)})
+    # bounds: 15 sample values in sort order (duplicates, a NULL and a NaN bound are legal)
+    sample = t.slice(0, 15).select(["k"])
+    bounds_t = O.sort(sample, [("k", asc, nulls_first)])
+    bounds = bounds_t.column("k").combine_chunks()
+    batch = ColumnarBatch.from_arrow(t, stream)
+    bb = ColumnarBatch.from_arrow(bounds_t, stream)
+    ex = ShuffleExchangeExec(RangePartitioning(("k", asc, nulls_first), bb), LocalTableScanExec(batch))
+    part = ex.executeColumnar(stream)
+    got = part.to_arrow(stream)
+    want, offs = O.range_partition(t, ("k", asc, nulls_first), bounds)
+    assert np.array_equal(ex.partition_offsets, offs)
+    assert got.column("row").to_pylist() == want.column("row").to_pylist()        # stable regrouping, exact
+    # per-range sort + concatenation = global order
+    pieces = []
+    for p in range(len(offs) - 1):
+        if offs[p + 1] > offs[p]:
+            sl = part.slice(int(offs[p]), int(offs[p + 1]), stream)
+            pieces.append(SortExec([("k", asc, nulls_first)], LocalTableScanExec(sl)).collect(stream))
+    glob = pa.concat_tables(pieces)
+    ref = O.sort(t, [("k", asc, nulls_first)])
+    gk, rk = glob.column("k").to_pylist(), ref.column("k").to_pylist()
+    same = lambda a, b: (a is None and b is None) or (a is not None and b is not None and (a == b or (a != a and b != b)))
+    assert len(gk) == len(rk) and all(same(a, b) for a, b in zip(gk, rk))
+    assert sorted(glob.column("row").to_pylist()) == list(range(n))
