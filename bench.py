@@ -60,7 +60,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -113,11 +113,22 @@ def cpu_q1(cols, n, reps):
     k0 = np.zeros(16, np.int8); k1 = np.zeros(16, np.int8); sums = np.zeros(80); cnt = np.zeros(16, np.int64)
     args = [cols[c].ctypes.data for c in ("l_quantity", "l_extendedprice", "l_discount", "l_tax", "l_returnflag",
                                           "l_linestatus", "l_shipdate")]
-    times = []
-    for _ in range(reps):
+    def one_pass():
         t0 = time.perf_counter()
         L.so_q1_partial_final(*args, n, tpch.Q1_CUTOFF, 16, k0.ctypes.data, k1.ctypes.data, sums.ctypes.data, cnt.ctypes.data)
-        times.append(time.perf_counter() - t0)
+        return time.perf_counter() - t0
+    # untimed calibration: the scan is DRAM-bound on the host, and on SMT boxes one thread per core is
+    # sometimes faster than one per hardware thread -- keep whichever the CPU does better with
+    hw = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    best = None
+    for nt in sorted({hw, max(1, hw // 2)}, reverse=True):
+        L.so_set_threads(nt)
+        one_pass()
+        t = min(one_pass(), one_pass())
+        if best is None or t < best[0]:
+            best = (t, nt)
+    L.so_set_threads(best[1])
+    times = [one_pass() for _ in range(reps)]
     return times, L.so_threads()
 
 
@@ -147,7 +158,7 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--sf", type=float, default=10.0, help="TPC-H scale factor per GPU (default 10 = configs[1])")
@@ -241,14 +252,16 @@ def main():
         out.close()
 
     # ---- device-resident timing ----------------------------------------------------------------------------
+    # clocks / throttle reasons are sampled every 20 ms from before the warm-up until the end of the end-to-end loop,
+    # i.e. across both timed regions (the device-resident one alone lasts ~0.2 s)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         step_resident()
     capi.check(lib.sb_profile_enable(1))
     capi.check(lib.sb_profile_reset())
-    sampler = ClockSampler(local_rank)
     barrier()
-    if rank == 0:
-        sampler.start()
     launches0 = capi.kernel_launch_count()
     stream.record_start()
     for _ in range(args.steps):
@@ -256,7 +269,6 @@ def main():
     stream.record_stop()
     total_ms = stream.elapsed_ms()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
     launches = capi.kernel_launch_count() - launches0
     kms, kcount = C.c_double(), C.c_int64()
     capi.check(lib.sb_profile_get(b"agg_update", C.byref(kms), C.byref(kcount)))
@@ -293,14 +305,16 @@ def main():
         e2e_ms = float(t.item())
     e2e_value = world * n / (e2e_ms / 1000.0)
     d2h = int(sum(result.column(i).nbytes for i in range(result.num_columns)))
+    clocks = sampler.stop() if rank == 0 else None
 
     # ---- CPU baseline (rank 0, N=1 only): the oracle's whole-stage loop on this host's cores -------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        times, threads = cpu_q1(cols, n, 4)
-        best = min(times[1:])
-        cpu = {"value": n / best, "unit": "rows/s", "cores": threads, "kind": "port",
-               "sample": "full SF%g lineitem (%d rows), best of 3 after 1 warm-up, %.2f s of CPU time" % (args.sf, n, sum(times))}
+        times, threads = cpu_q1(cols, n, 13)
+        mean = sum(times[1:]) / len(times[1:])
+        cpu = {"value": n / mean, "unit": "rows/s", "cores": threads, "kind": "port",
+               "sample": "full SF%g lineitem (%d rows) x 12 passes after 1 warm-up, mean; %.1f core-seconds of CPU work"
+                         % (args.sf, n, sum(times[1:]) * threads)}
 
     if rank == 0:
         line = {"metric": "tpch_q1_rows_per_sec", "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps,
@@ -312,7 +326,10 @@ def main():
                            "l2_policy": "inputs (%.2f GB) larger than L2, no flush" % (alg_bytes / 1e9)},
                 "roofline": {"bound": "hbm", "kernel": "agg_update_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "frac_of_8tbs_nominal": achieved / 8000.0, "peak_source": peak_src,
-                             "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes, "traffic": None},
+                             "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                             # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel at SF10 (ncu --set full,
+                             # profiles/r01_agg_update.md): 2.4115 GB + 3.8 MB; reported only for the configuration it was captured on
+                             "traffic": 2415381704 if n == Q1_ROWS_SF10 else None},
                 "cpu_baseline": cpu,
                 "e2e": {"value": e2e_value, "unit": "rows/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": alg_bytes,
                         "d2h_bytes_per_step": d2h},

@@ -59,6 +59,7 @@ def lib():
         L = C.CDLL(build())
         i32, i64, p = C.c_int32, C.c_int64, C.c_void_p
         L.so_threads.restype = i32
+        L.so_set_threads.argtypes = [i32]; L.so_set_threads.restype = None
         L.so_murmur3_int.restype = i32; L.so_murmur3_int.argtypes = [i32, i32]
         L.so_murmur3_long.restype = i32; L.so_murmur3_long.argtypes = [i64, i32]
         L.so_murmur3_bytes.restype = i32; L.so_murmur3_bytes.argtypes = [C.c_char_p, i32, i32]

@@ -57,6 +57,14 @@ int so_threads(void) {
 #endif
 }
 
+void so_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 /* =====================================================================
  * Murmur3_x86_32  (common/unsafe/.../hash/Murmur3_x86_32.java:47-150)
  * ===================================================================== */

@@ -290,6 +290,17 @@ class ColumnarBatch:
         capi.check(capi.load().sb_table_slice(self.handle, begin, end, _h(stream), C.byref(h)))
         return ColumnarBatch(h, self.names, self.arrow_types)
 
+    @staticmethod
+    def concat(batches, stream=None) -> "ColumnarBatch":
+        """Row-wise concatenation on the device (the reduce side of an exchange stitches fetched blocks this way)."""
+        batches = list(batches)
+        if not batches:
+            raise ValueError("concat of zero batches")
+        arr = (C.c_void_p * len(batches))(*[b.handle for b in batches])
+        h = C.c_void_p()
+        capi.check(capi.load().sb_table_concat(arr, len(batches), _h(stream), C.byref(h)))
+        return ColumnarBatch(h, batches[0].names, batches[0].arrow_types)
+
     def close(self):
         if self.handle:
             capi.load().sb_table_release(self.handle)

@@ -78,18 +78,6 @@ static inline int32_t part_lo(int32_t r, int32_t nparts, int32_t nranks) {
   return (int32_t)(((int64_t)r * nparts + nranks - 1) / nranks);
 }
 
-// validity bitmap <-> one byte per row (bitmaps cannot be sliced at arbitrary row offsets)
-__global__ void bitmap_to_bytes_kernel(const uint8_t *__restrict__ bm, int64_t n, uint8_t *__restrict__ out) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = bit_valid(bm, i) ? 1 : 0;
-}
-__global__ void bytes_to_bitmap_kernel(const uint8_t *__restrict__ in, int64_t n, uint32_t *__restrict__ bm) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  bool v = i < n && in[i];
-  uint32_t w = __ballot_sync(0xffffffffu, v);
-  if ((threadIdx.x & 31) == 0 && (i - (i & 31)) < n) bm[i >> 5] = w;
-}
-
 }  // namespace sb
 
 using namespace sb;
@@ -221,10 +209,7 @@ int sb_all_to_all(const sb_table *in, const int64_t *part_offsets_host, int32_t 
         Scratch *sb = new Scratch(in->nrows + 16, st), *rb = new Scratch(nrecv + 16, st);
         temps.push_back(sb);
         temps.push_back(rb);
-        if (in->nrows > 0) {
-          bitmap_to_bytes_kernel<<<(unsigned)((in->nrows + 255) / 256), 256, 0, st>>>(src.v(), in->nrows, sb->as<uint8_t>());
-          SB_LAUNCH_CHECK();
-        }
+        bitmap_to_bytes(src.v(), in->nrows, sb->as<uint8_t>(), st);
         for (int peer = 0; peer < R; peer++) {
           if (send_rows[peer] > 0) SB_NCCL(nccl().Send(sb->as<uint8_t>() + send_off[peer], (size_t)send_rows[peer], ncclUint8, peer, c.comm, st));
           if (recv_rows[peer] > 0) SB_NCCL(nccl().Recv(rb->as<uint8_t>() + recv_off[peer], (size_t)recv_rows[peer], ncclUint8, peer, c.comm, st));
@@ -235,10 +220,7 @@ int sb_all_to_all(const sb_table *in, const int64_t *part_offsets_host, int32_t 
     SB_NCCL(nccl().GroupEnd());
     count_launch();   // the grouped NCCL kernel
     for (auto &p : pend) {
-      if (nrecv > 0) {
-        bytes_to_bitmap_kernel<<<(unsigned)((nrecv + 255) / 256), 256, 0, st>>>(p.recv_bytes, nrecv, (uint32_t *)p.col->validity->ptr);
-        SB_LAUNCH_CHECK();
-      }
+      bytes_to_bitmap(p.recv_bytes, nrecv, (uint32_t *)p.col->validity->ptr, st);
     }
     SB_CUDA(cudaStreamSynchronize(st));
     for (auto *x : temps) delete x;
@@ -295,10 +277,7 @@ int sb_all_gather(const sb_table *in, sb_stream *s, sb_table **out) {
         Scratch *sb = new Scratch(my + 16, st), *rb = new Scratch(total + 16, st);
         temps.push_back(sb);
         temps.push_back(rb);
-        if (my > 0) {
-          bitmap_to_bytes_kernel<<<(unsigned)((my + 255) / 256), 256, 0, st>>>(src.v(), my, sb->as<uint8_t>());
-          SB_LAUNCH_CHECK();
-        }
+        bitmap_to_bytes(src.v(), my, sb->as<uint8_t>(), st);
         for (int peer = 0; peer < R; peer++) {
           if (my > 0) SB_NCCL(nccl().Send(sb->as<uint8_t>(), (size_t)my, ncclUint8, peer, c.comm, st));
           if (rows[peer] > 0) SB_NCCL(nccl().Recv(rb->as<uint8_t>() + off[peer], (size_t)rows[peer], ncclUint8, peer, c.comm, st));
@@ -309,10 +288,7 @@ int sb_all_gather(const sb_table *in, sb_stream *s, sb_table **out) {
     SB_NCCL(nccl().GroupEnd());
     count_launch();
     for (auto &p : pend) {
-      if (total > 0) {
-        bytes_to_bitmap_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p.bytes, total, (uint32_t *)p.col->validity->ptr);
-        SB_LAUNCH_CHECK();
-      }
+      bytes_to_bitmap(p.bytes, total, (uint32_t *)p.col->validity->ptr, st);
     }
     SB_CUDA(cudaStreamSynchronize(st));
     for (auto *x : temps) delete x;

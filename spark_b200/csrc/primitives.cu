@@ -306,6 +306,27 @@ int64_t compact_mask(const uint8_t *mask, int64_t n, int64_t *out_idx, cudaStrea
   return cnt;
 }
 
+__global__ void bitmap_to_bytes_kernel(const uint8_t *__restrict__ bm, int64_t n, uint8_t *__restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = bit_valid(bm, i) ? 1 : 0;
+}
+__global__ void bytes_to_bitmap_kernel(const uint8_t *__restrict__ in, int64_t n, uint32_t *__restrict__ bm) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool v = i < n && in[i];
+  uint32_t w = __ballot_sync(0xffffffffu, v);
+  if ((threadIdx.x & 31) == 0 && (i - (i & 31)) < n) bm[i >> 5] = w;
+}
+void bitmap_to_bytes(const uint8_t *bm, int64_t n, uint8_t *out, cudaStream_t st) {
+  if (n <= 0) return;
+  bitmap_to_bytes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(bm, n, out);
+  SB_LAUNCH_CHECK();
+}
+void bytes_to_bitmap(const uint8_t *in, int64_t n, uint32_t *bm, cudaStream_t st) {
+  if (n <= 0) return;
+  bytes_to_bitmap_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, n, bm);
+  SB_LAUNCH_CHECK();
+}
+
 __global__ void iota_kernel(int64_t *out, int64_t n, int64_t begin) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = begin + i;
@@ -367,26 +388,18 @@ int sb_table_concat(const sb_table *const *tables, int32_t ntables, sb_stream *s
       }
       r->cols.push_back(col);
       if (any_valid) {
-        // validity: rebuild through a gather of each piece's bits (pieces start at arbitrary bit offsets)
+        // validity: pieces start at arbitrary bit offsets, so go through one byte per row on the device
         Column &rc = r->cols.back();
         rc.validity = buffer_alloc(bitmap_alloc_bytes(total), st);
         rc.null_count = -1;
-        SB_CUDA(cudaMemsetAsync(rc.validity->ptr, 0xff, (size_t)bitmap_alloc_bytes(total), st));
-        std::vector<uint8_t> host((size_t)bitmap_bytes(total) + 8, 0xff);
+        Scratch bytes(total + 16, st);
         int64_t o = 0;
         for (int i = 0; i < ntables; i++) {
           int64_t n = tables[i]->nrows;
-          if (tables[i]->cols[c].validity && n) {
-            std::vector<uint8_t> piece((size_t)bitmap_bytes(n));
-            SB_CUDA(cudaMemcpyAsync(piece.data(), tables[i]->cols[c].v(), piece.size(), cudaMemcpyDeviceToHost, st));
-            SB_CUDA(cudaStreamSynchronize(st));
-            for (int64_t k = 0; k < n; k++)
-              if (!((piece[k >> 3] >> (k & 7)) & 1)) host[(o + k) >> 3] &= ~(1u << ((o + k) & 7));
-          }
+          bitmap_to_bytes(tables[i]->cols[c].v(), n, bytes.as<uint8_t>() + o, st);
           o += n;
         }
-        SB_CUDA(cudaMemcpyAsync(rc.validity->ptr, host.data(), (size_t)bitmap_bytes(total), cudaMemcpyHostToDevice, st));
-        SB_CUDA(cudaStreamSynchronize(st));
+        bytes_to_bitmap(bytes.as<uint8_t>(), total, (uint32_t *)rc.validity->ptr, st);
       }
     }
   } catch (...) {

@@ -24,6 +24,10 @@ int64_t compact_mask(const uint8_t *mask_dev, int64_t n, int64_t *out_idx_dev, c
 void compact_mask_async(const uint8_t *mask_dev, int64_t n, int64_t *out_idx_dev, int32_t *flags_scratch, int64_t *pos_scratch,
                         int64_t *total_dev, cudaStream_t st);
 
+// validity bitmap <-> one byte per row (bitmaps cannot be sliced or concatenated at arbitrary row offsets)
+void bitmap_to_bytes(const uint8_t *bitmap_dev, int64_t n, uint8_t *out_dev, cudaStream_t st);   // bitmap == nullptr -> all ones
+void bytes_to_bitmap(const uint8_t *bytes_dev, int64_t n, uint32_t *bitmap_dev, cudaStream_t st);
+
 // fills idx[i] = begin + i
 void iota_i64(int64_t *out, int64_t n, int64_t begin, cudaStream_t st);
 
