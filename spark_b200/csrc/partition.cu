@@ -303,6 +303,246 @@ __global__ void __launch_bounds__(RG_THREADS, 2) regroup_kernel(const __grid_con
   }
 }
 
+// ---- K2, copy-engine version -------------------------------------------------------------------------------------------------
+// Same tile algebra as regroup_kernel (phases A-D, F), but phase E no longer loads anything itself: one elected thread keeps
+// RGT_STAGES bulk copies (cp.async.bulk -> mbarrier) in flight per block, walking the sequence
+//   tile 0: [bucket ids, column 0, column 1, ...], tile 1: [...], ...
+// so the next column tiles stream into shared memory in ROW order while the warps drain the current one.  Draining is
+// output-driven: the thread that owns sorted position j knows which row of the tile lands there (src = inverse of the
+// tile's bucket-sort permutation, kept in registers) and where it goes (gdest), so a column costs one shared-memory gather
+// and one global store per row and a single __syncthreads() (to hand the stage back), instead of
+// "global load -> shared scatter -> barrier -> shared load -> global store -> barrier" with the load latency exposed.
+constexpr int RGT_STAGES = 3;
+constexpr int RGT_STAGE_BYTES = RG_TILE * 8;   // one 8-byte column tile
+
+template <typename T, bool FULLT>
+__device__ __forceinline__ void regroup_drain_column(const uint8_t *__restrict__ stage, void *__restrict__ dst,
+                                                     const uint32_t (&src2)[RG_ITEMS / 2], const uint32_t (&gdest)[RG_ITEMS],
+                                                     uint32_t gmask) {
+  const T *s = (const T *)stage;
+  T v[RG_ITEMS];
+#pragma unroll
+  for (int it = 0; it < RG_ITEMS; it++) v[it] = s[(src2[it >> 1] >> ((it & 1) * 16)) & 0xFFFFu];
+#pragma unroll
+  for (int it = 0; it < RG_ITEMS; it++)
+    if (FULLT || ((gmask >> it) & 1)) ((T *)dst)[gdest[it]] = v[it];
+}
+
+__global__ void __launch_bounds__(RG_THREADS, 2) regroup_tma_kernel(const __grid_constant__ RegroupCols cols, const int32_t *__restrict__ bucket,
+                                                                    const uint32_t *__restrict__ base, int64_t n, int32_t nb, int64_t ntiles,
+                                                                    int64_t *__restrict__ perm_out, int l2_stream) {
+  extern __shared__ __align__(128) uint8_t ring[];          // RGT_STAGES x RGT_STAGE_BYTES
+  __shared__ __align__(8) uint64_t bars[RGT_STAGES];
+  __shared__ uint32_t readers_done[RGT_STAGES];
+  // wcnt (phases A-D) and ssrc (D-E) share storage; nothing but the copy engine ever writes a full stage, so handing a stage back
+  // needs no proxy fence (a fence.proxy.async is a MEMBAR.ALL.CTA: it would wait for the column's global stores to drain)
+  __shared__ __align__(16) uint16_t wcnt_ssrc[RG_TILE];
+  __shared__ uint8_t sbucket[RG_TILE];
+  __shared__ uint16_t first[RG_MAX_NB], tcnt[RG_MAX_NB];
+  uint16_t (*wcnt)[RG_MAX_NB] = reinterpret_cast<uint16_t (*)[RG_MAX_NB]>(wcnt_ssrc);
+  uint16_t *ssrc = wcnt_ssrc;
+  static_assert(RG_WARPS * RG_MAX_NB <= RG_TILE, "wcnt must fit in the ssrc storage");
+  __shared__ uint32_t cursor[RG_MAX_NB];
+  __shared__ uint32_t warp_sums[RG_WARPS];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // Tiles are dealt round-robin (block b: tiles b, b + grid, ...), so at any moment the grid works on ~grid CONSECUTIVE tiles:
+  // their runs are adjacent inside every bucket, which lets L2 complete the sectors two tiles share before eviction and keeps
+  // the DRAM write stream to (buckets x columns) compact regions instead of (blocks x buckets x columns) scattered ones.
+  if ((int64_t)blockIdx.x >= ntiles) return;
+  const int64_t tstride = (int64_t)gridDim.x * RG_TILE;
+  const int64_t begin = (int64_t)blockIdx.x * RG_TILE;
+  const int64_t end = n;
+  const int per_tile = cols.ncols + 1;
+  // Item i of the block's sequence (tile-major, [bucket ids, columns...] inside a tile) lives in stage i % RGT_STAGES.  A stage is
+  // refilled by whichever WARP finishes reading it last (shared counter), so the column loop has no block-wide barrier: warps
+  // drift up to RGT_STAGES - 1 items apart and a fast warp never waits for a slow one, only for data.
+  auto issue = [&](int64_t tb, int q, int stg_i) {
+    while (q >= per_tile) {
+      q -= per_tile;
+      tb += tstride;
+    }
+    if (tb >= end) return;
+    const int64_t rows = end - tb < RG_TILE ? end - tb : RG_TILE;
+    const char *src;
+    int w;
+    if (q == 0) {
+      src = (const char *)(bucket + tb);
+      w = 4;
+    } else {
+      w = cols.width[q - 1];
+      src = (const char *)cols.src[q - 1] + tb * w;
+    }
+    const uint32_t bytes = (uint32_t)(rows * w) & ~15u;     // a ragged tail (< 16 B) is fetched by the consumers
+    if (bytes) {
+      mbar_arrive_expect_tx(&bars[stg_i], bytes);
+      if (l2_stream) tma_load_1d_stream(ring + stg_i * RGT_STAGE_BYTES, src, bytes, &bars[stg_i]);
+      else tma_load_1d(ring + stg_i * RGT_STAGE_BYTES, src, bytes, &bars[stg_i]);
+    } else {
+      mbar_arrive(&bars[stg_i]);
+    }
+  };
+  if (tid == 0) {
+    for (int i = 0; i < RGT_STAGES; i++) {
+      mbar_init(&bars[i], 1);
+      readers_done[i] = 0;
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_proxy_async_smem();
+  }
+  __syncthreads();
+  if (tid == 0)
+    for (int i = 0; i < RGT_STAGES; i++) issue(begin, i, i);
+  int stage = 0;
+  uint32_t phase = 0;
+  // waits for the current stage; fetches the ragged tail of a partial tile; returns the stage's base
+  auto acquire = [&](const void *col_base, int w, int64_t tbase, int tile_n) -> uint8_t * {
+    mbar_wait(&bars[stage], phase);
+    uint8_t *stg = ring + stage * RGT_STAGE_BYTES;
+    if (tile_n < RG_TILE) {
+      const uint32_t total = (uint32_t)tile_n * w, done = total & ~15u;
+      if (tid < (int)(total - done)) stg[done + tid] = ((const uint8_t *)col_base + tbase * w)[done + tid];
+      fence_proxy_async_smem();   // generic-proxy bytes in a stage the copy engine will overwrite later
+      __syncthreads();
+    }
+    return stg;
+  };
+  // this warp is done with item (tbase, q) in the current stage; the last warp to say so refills the stage with item + RGT_STAGES
+  auto release = [&](int64_t tbase, int q) {
+    __syncwarp();
+    if (lane == 0 && (smem_add_acq_rel(&readers_done[stage], 1) + 1) % RG_WARPS == 0)   // never reset: RG_WARPS arrivals per use
+      issue(tbase, q + RGT_STAGES, stage);
+    if (++stage == RGT_STAGES) {
+      stage = 0;
+      phase ^= 1;
+    }
+  };
+  int64_t tile = blockIdx.x;
+  for (int64_t tbase = begin; tbase < end; tbase += tstride, tile += gridDim.x) {
+    const int tile_n = (int)(end - tbase < RG_TILE ? end - tbase : RG_TILE);
+    const bool fullt = tile_n == RG_TILE;
+    // first output row of every bucket for THIS tile (read by phase D, several barriers from here; the previous tile's readers
+    // are behind the barrier that ended its register load)
+    for (int p = tid; p < nb; p += RG_THREADS) cursor[p] = base[(int64_t)p * ntiles + tile];
+    for (int p = lane; p < nb; p += 32) wcnt[warp][p] = 0;
+    __syncwarp();
+    const uint8_t *stg = acquire(bucket, 4, tbase, tile_n);
+    // ---- A: rank inside the warp's segment (bucket ids come from the stage) ------------------------------------------------
+    uint32_t bl[RG_ITEMS];
+    {
+      const int32_t *sb = (const int32_t *)stg + warp * RG_SEG + lane;
+#pragma unroll
+      for (int it = 0; it < RG_ITEMS; it++) {
+        const bool active = warp * RG_SEG + it * 32 + lane < tile_n;
+        const int32_t b = active ? sb[it * 32] : -1 - lane;
+        const uint32_t grp = __match_any_sync(0xffffffffu, b);
+        const uint32_t rank = __popc(grp & lanemask_lt());
+        uint32_t c = 0;
+        if (active) {
+          c = wcnt[warp][b];
+          __syncwarp(grp);
+          if (rank == 0) wcnt[warp][b] = (uint16_t)(c + __popc(grp));
+        }
+        __syncwarp();
+        bl[it] = (active ? (uint32_t)b : 0xFFFFu) | ((c + rank) << 16);
+      }
+    }
+    release(tbase, 0);   // this warp has consumed its bucket ids
+    __syncthreads();
+    // ---- B: per bucket, exclusive prefix over the warps; tile total -------------------------------------------------------
+    for (int p = tid; p < nb; p += RG_THREADS) {
+      uint32_t run = 0;
+#pragma unroll
+      for (int w = 0; w < RG_WARPS; w++) {
+        uint32_t c = wcnt[w][p];
+        wcnt[w][p] = (uint16_t)run;
+        run += c;
+      }
+      tcnt[p] = (uint16_t)run;
+    }
+    __syncthreads();
+    // ---- C: exclusive scan of the tile totals -> first[] -------------------------------------------------------------------
+    {
+      uint32_t v = tid < nb ? tcnt[tid] : 0, x = v;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+        if (lane >= d) x += y;
+      }
+      if (lane == 31) warp_sums[warp] = x;
+      __syncthreads();
+      uint32_t woff = 0;
+      for (int w = 0; w < warp; w++) woff += warp_sums[w];
+      if (tid < nb) first[tid] = (uint16_t)(woff + x - v);
+    }
+    __syncthreads();
+    // ---- D: sorted position of every row -> (bucket, source row) of every sorted position ---------------------------------------
+#pragma unroll
+    for (int it = 0; it < RG_ITEMS; it++) {
+      const uint32_t b = bl[it] & 0xFFFFu;
+      if (b != 0xFFFFu) bl[it] = b | ((first[b] + wcnt[warp][b] + (bl[it] >> 16)) << 16);
+    }
+    __syncthreads();    // wcnt is dead: ssrc may overwrite it
+#pragma unroll
+    for (int it = 0; it < RG_ITEMS; it++) {
+      const uint32_t b = bl[it] & 0xFFFFu;
+      if (b != 0xFFFFu) {
+        sbucket[bl[it] >> 16] = (uint8_t)b;
+        ssrc[bl[it] >> 16] = (uint16_t)(warp * RG_SEG + it * 32 + lane);
+      }
+    }
+    __syncthreads();
+    uint32_t gdest[RG_ITEMS];        // output row of sorted position j = it * RG_THREADS + tid
+    uint32_t src2[RG_ITEMS / 2];     // tile row that lands at sorted position j, two per register
+    uint32_t gmask = 0;
+#pragma unroll
+    for (int it = 0; it < RG_ITEMS; it++) {
+      const int j = it * RG_THREADS + tid;
+      uint32_t srow = 0;
+      if (j < tile_n) {
+        const int b = sbucket[j];
+        gdest[it] = cursor[b] + (uint32_t)(j - first[b]);
+        srow = ssrc[j];
+        gmask |= 1u << it;
+      } else gdest[it] = 0;
+      if (it & 1) src2[it >> 1] |= srow << 16;
+      else src2[it >> 1] = srow;
+    }
+    __syncthreads();    // ssrc is in registers: the next tile may zero wcnt
+    // ---- E: drain the columns ------------------------------------------------------------------------------------------------
+    if (perm_out) {   // row ids of the rows in output order (used to gather variable-width columns afterwards)
+#pragma unroll
+      for (int it = 0; it < RG_ITEMS; it++)
+        if ((gmask >> it) & 1) perm_out[gdest[it]] = tbase + (int64_t)((src2[it >> 1] >> ((it & 1) * 16)) & 0xFFFFu);
+    }
+#pragma unroll 1
+    for (int c = 0; c < cols.ncols; c++) {
+      const int w = cols.width[c];
+      void *dst = cols.dst[c];
+      const uint8_t *cs = acquire(cols.src[c], w, tbase, tile_n);
+#define SB_DRAIN(T)                                                             \
+  if (fullt) regroup_drain_column<T, true>(cs, dst, src2, gdest, gmask);       \
+  else regroup_drain_column<T, false>(cs, dst, src2, gdest, gmask);
+      switch (w) {
+        case 1: SB_DRAIN(uint8_t) break;
+        case 2: SB_DRAIN(uint16_t) break;
+        case 4: SB_DRAIN(uint32_t) break;
+        default: SB_DRAIN(uint64_t) break;
+      }
+#undef SB_DRAIN
+      if (cols.dst_valid[c]) {   // NULLs: clear the destination bit (rare, scattered)
+        const uint8_t *sv = cols.src_valid[c];
+#pragma unroll
+        for (int it = 0; it < RG_ITEMS; it++) {
+          if (!((gmask >> it) & 1)) continue;
+          const int64_t row = tbase + (int64_t)((src2[it >> 1] >> ((it & 1) * 16)) & 0xFFFFu);
+          if (!bit_valid(sv, row)) atomicAnd(&cols.dst_valid[c][gdest[it] >> 5], ~(1u << (gdest[it] & 31)));
+        }
+      }
+      release(tbase, c + 1);
+    }
+  }
+}
+
 // bucket = digit of a partition id for the two-level split; also the per-block histogram in multisplit layout
 __global__ void __launch_bounds__(RG_THREADS) pid_digit_hist_kernel(const int32_t *__restrict__ pid, int64_t n, int32_t div, int32_t mod,
                                                                     int32_t nb, int64_t chunk, int32_t *__restrict__ bucket,
@@ -344,13 +584,22 @@ static KeyCols make_keys(const sb_table *in, const int32_t *key_cols, int32_t nk
 }
 
 PartGeometry part_geometry(int64_t n, int32_t nbuckets) {
-  (void)nbuckets;
   PartGeometry g;
+  if (nbuckets <= RG_MAX_NB) {
+    // one histogram column per TILE: the scatter deals tiles round-robin to a persistent grid (see regroup_tma_kernel)
+    g.chunk = RG_TILE;
+    int64_t nt = (n + RG_TILE - 1) / RG_TILE;
+    g.nblocks = (int)(nt < 1 ? 1 : nt);
+    return g;
+  }
+  // above the single-pass fan-out the caller's histogram only provides the bucket boundaries: keep it coarse
   int64_t want = (n + RG_TILE * 2 - 1) / (RG_TILE * 2);
   int maxb = rt().num_sms * 2;
   g.nblocks = (int)(want < 1 ? 1 : (want > maxb ? maxb : want));
-  g.chunk = ((n + g.nblocks - 1) / g.nblocks + 31) / 32 * 32;
-  if (g.chunk < 32) g.chunk = 32;
+  g.chunk = ((n + g.nblocks - 1) / g.nblocks + RG_TILE - 1) / RG_TILE * RG_TILE;
+  if (g.chunk < RG_TILE) g.chunk = RG_TILE;
+  g.nblocks = (int)((n + g.chunk - 1) / g.chunk);
+  if (g.nblocks < 1) g.nblocks = 1;
   return g;
 }
 
@@ -362,12 +611,15 @@ static void regroup_pass(const int32_t *bucket_dev, uint32_t *hist_dev, int32_t 
     SB_LAUNCH_CHECK();
   }
   if (n == 0) return;
+  SB_REQUIRE(g.chunk == RG_TILE, "internal: regroup needs a per-tile histogram");
   int done = 0;
   bool first = true;
   while (first || done < ncols) {
     RegroupCols rc;
     rc.ncols = 0;
-    while (done < ncols && rc.ncols < SCATTER_MAX_COLS) {
+    static const int max_cols = [] { const char *e = getenv("SB_RG_MAXCOLS"); int v = e ? atoi(e) : SCATTER_MAX_COLS; return v < 1 ? 1 : (v > SCATTER_MAX_COLS ? SCATTER_MAX_COLS : v); }();
+    static const int l2_stream = [] { const char *e = getenv("SB_RG_L2HINT"); return e ? atoi(e) : 0; }();
+    while (done < ncols && rc.ncols < max_cols) {
       const SplitCol &c = cols[done++];
       int k = rc.ncols++;
       rc.width[k] = c.width;
@@ -377,8 +629,26 @@ static void regroup_pass(const int32_t *bucket_dev, uint32_t *hist_dev, int32_t 
       rc.dst_valid[k] = c.dst_valid;
     }
     if (rc.ncols > 0 || (first && perm_out)) {
+      // the copy engine wants 16-byte aligned sources; anything else (a caller-provided, oddly offset device buffer) takes the
+      // load/store kernel.  SB_REGROUP_PATH=ldst forces it (A/B measurements).
+      static const bool force_ldst = [] { const char *e = getenv("SB_REGROUP_PATH"); return e && !strcmp(e, "ldst"); }();
+      bool aligned = ((uintptr_t)bucket_dev & 15) == 0;
+      for (int k = 0; k < rc.ncols; k++) aligned = aligned && ((uintptr_t)rc.src[k] & 15) == 0;
       KernelTimer kt("partition_scatter", st);
-      regroup_kernel<<<g.nblocks, RG_THREADS, 0, st>>>(rc, bucket_dev, hist_dev, n, nb, g.chunk, first ? perm_out : nullptr);
+      if (aligned && !force_ldst) {
+        static std::once_flag once;
+        std::call_once(once, [] {
+          SB_CUDA(cudaFuncSetAttribute(regroup_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RGT_STAGES * RGT_STAGE_BYTES));
+        });
+        static const int bps = [] { const char *e = getenv("SB_RG_BLOCKS_PER_SM"); return e ? atoi(e) : 2; }();
+        static const int grid_override = [] { const char *e = getenv("SB_RG_GRID"); return e ? atoi(e) : 0; }();
+        int grid = g.nblocks < rt().num_sms * bps ? g.nblocks : rt().num_sms * bps;
+        if (grid_override > 0 && grid_override < grid) grid = grid_override;
+        regroup_tma_kernel<<<grid, RG_THREADS, RGT_STAGES * RGT_STAGE_BYTES, st>>>(rc, bucket_dev, hist_dev, n, nb, (int64_t)g.nblocks,
+                                                                                   first ? perm_out : nullptr, l2_stream);
+      } else {
+        regroup_kernel<<<g.nblocks, RG_THREADS, 0, st>>>(rc, bucket_dev, hist_dev, n, nb, g.chunk, first ? perm_out : nullptr);
+      }
       SB_LAUNCH_CHECK();
     }
     first = false;
@@ -399,7 +669,8 @@ void multisplit_scatter(const int32_t *bucket_dev, uint32_t *hist_dev, int32_t n
   // are stable, so the result is ordered by (high, low) = bucket id with arrival order preserved inside a bucket.
   const int32_t B1 = 64, B2 = (nbuckets + B1 - 1) / B1;
   SB_REQUIRE(B2 <= RG_MAX_NB, "too many buckets");
-  Scratch digit(n * 4 + 16, st), hist2((int64_t)RG_MAX_NB * g.nblocks * 4 + 16, st), pid_mid(n * 4 + 16, st), perm_mid(perm_out ? n * 8 + 16 : 0, st);
+  const PartGeometry g2 = part_geometry(n, RG_MAX_NB);   // per-tile histograms for the two digit passes
+  Scratch digit(n * 4 + 16, st), hist2((int64_t)RG_MAX_NB * g2.nblocks * 4 + 16, st), pid_mid(n * 4 + 16, st), perm_mid(perm_out ? n * 8 + 16 : 0, st);
   // intermediate copies of every column (+ validity carried as-is through atomicAnd on a fresh bitmap)
   std::vector<SplitCol> c1(cols, cols + ncols), c2(cols, cols + ncols);
   std::vector<Scratch *> tmp;
@@ -422,16 +693,16 @@ void multisplit_scatter(const int32_t *bucket_dev, uint32_t *hist_dev, int32_t n
   }
   c1.push_back({4, bucket_dev, pid_mid.ptr, nullptr, nullptr});   // the bucket ids travel with the rows into pass 2
   if (n > 0) {
-    pid_digit_hist_kernel<<<g.nblocks, RG_THREADS, 0, st>>>(bucket_dev, n, 1, B1, B1, g.chunk, digit.as<int32_t>(), hist2.as<uint32_t>());
+    pid_digit_hist_kernel<<<g2.nblocks, RG_THREADS, 0, st>>>(bucket_dev, n, 1, B1, B1, g2.chunk, digit.as<int32_t>(), hist2.as<uint32_t>());
     SB_LAUNCH_CHECK();
   }
-  regroup_pass(digit.as<int32_t>(), hist2.as<uint32_t>(), B1, g, c1.data(), (int)c1.size(), n, perm_out ? perm_mid.as<int64_t>() : nullptr, nullptr, st);
+  regroup_pass(digit.as<int32_t>(), hist2.as<uint32_t>(), B1, g2, c1.data(), (int)c1.size(), n, perm_out ? perm_mid.as<int64_t>() : nullptr, nullptr, st);
   if (perm_out) c2.push_back({8, perm_mid.ptr, perm_out, nullptr, nullptr});
   if (n > 0) {
-    pid_digit_hist_kernel<<<g.nblocks, RG_THREADS, 0, st>>>(pid_mid.as<int32_t>(), n, B1, B2, B2, g.chunk, digit.as<int32_t>(), hist2.as<uint32_t>());
+    pid_digit_hist_kernel<<<g2.nblocks, RG_THREADS, 0, st>>>(pid_mid.as<int32_t>(), n, B1, B2, B2, g2.chunk, digit.as<int32_t>(), hist2.as<uint32_t>());
     SB_LAUNCH_CHECK();
   }
-  regroup_pass(digit.as<int32_t>(), hist2.as<uint32_t>(), B2, g, c2.data(), (int)c2.size(), n, nullptr, nullptr, st);
+  regroup_pass(digit.as<int32_t>(), hist2.as<uint32_t>(), B2, g2, c2.data(), (int)c2.size(), n, nullptr, nullptr, st);
   // bucket boundaries come from the caller's full-resolution histogram
   exclusive_scan_i32((const int32_t *)hist_dev, (int32_t *)hist_dev, (int64_t)nbuckets * g.nblocks, nullptr, st);
   if (offsets_dev) {

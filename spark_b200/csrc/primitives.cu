@@ -327,6 +327,12 @@ void bytes_to_bitmap(const uint8_t *in, int64_t n, uint32_t *bm, cudaStream_t st
   SB_LAUNCH_CHECK();
 }
 
+// string concat: offsets of one piece rebased onto the concatenated character buffer
+__global__ void rebase_offsets_kernel(const int32_t *__restrict__ in, int64_t n, int32_t char_base, int32_t *__restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i] - in[0] + char_base;
+}
+
 __global__ void iota_kernel(int64_t *out, int64_t n, int64_t begin) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = begin + i;
@@ -371,22 +377,50 @@ int sb_table_concat(const sb_table *const *tables, int32_t ntables, sb_stream *s
   try {
     for (size_t c = 0; c < first->cols.size(); c++) {
       int32_t type = first->cols[c].type;
-      if (type == SB_STRING) fail(SB_ERR_UNSUPPORTED, "concat of string columns is not implemented");
       bool any_valid = false;
+      int64_t chars = 0;
       for (int i = 0; i < ntables; i++) {
         SB_REQUIRE(tables[i]->cols[c].type == type, "concat: column %zu type mismatch", c);
         any_valid |= tables[i]->cols[c].validity != nullptr;
+        chars += tables[i]->cols[c].string_bytes;
       }
-      int w = type_width(type);
-      Column col = column_alloc(type, first->cols[c].scale, total, false, st);
-      int64_t off = 0;
-      for (int i = 0; i < ntables; i++) {
-        int64_t n = tables[i]->nrows;
-        if (n) SB_CUDA(cudaMemcpyAsync((char *)col.data->ptr + off * w, tables[i]->cols[c].d(), (size_t)(n * w),
-                                       cudaMemcpyDeviceToDevice, st));
-        off += n;
+      if (type == SB_STRING) {
+        SB_REQUIRE(chars <= INT32_MAX, "concat: string column %zu would exceed 2 GiB of characters", c);
+        Column col;
+        col.type = SB_STRING;
+        col.length = total;
+        col.string_bytes = chars;
+        col.offsets = buffer_alloc((total + 1) * 4 + 16, st);
+        col.data = buffer_alloc(chars + 16, st);
+        r->cols.push_back(col);
+        int64_t off = 0, cbase = 0;
+        for (int i = 0; i < ntables; i++) {
+          const Column &pc = tables[i]->cols[c];
+          int64_t n = tables[i]->nrows;
+          if (n) {
+            rebase_offsets_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pc.o(), n, (int32_t)cbase, (int32_t *)col.offsets->ptr + off);
+            SB_LAUNCH_CHECK();
+          }
+          if (pc.string_bytes)
+            SB_CUDA(cudaMemcpyAsync((char *)col.data->ptr + cbase, pc.d(), (size_t)pc.string_bytes, cudaMemcpyDeviceToDevice, st));
+          off += n;
+          cbase += pc.string_bytes;
+        }
+        int32_t last = (int32_t)chars;
+        SB_CUDA(cudaMemcpyAsync((int32_t *)col.offsets->ptr + total, &last, 4, cudaMemcpyHostToDevice, st));
+        SB_CUDA(cudaStreamSynchronize(st));   // `last` lives on this frame
+      } else {
+        int w = type_width(type);
+        Column col = column_alloc(type, first->cols[c].scale, total, false, st);
+        int64_t off = 0;
+        for (int i = 0; i < ntables; i++) {
+          int64_t n = tables[i]->nrows;
+          if (n) SB_CUDA(cudaMemcpyAsync((char *)col.data->ptr + off * w, tables[i]->cols[c].d(), (size_t)(n * w),
+                                         cudaMemcpyDeviceToDevice, st));
+          off += n;
+        }
+        r->cols.push_back(col);
       }
-      r->cols.push_back(col);
       if (any_valid) {
         // validity: pieces start at arbitrary bit offsets, so go through one byte per row on the device
         Column &rc = r->cols.back();
