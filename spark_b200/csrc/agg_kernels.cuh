@@ -73,8 +73,18 @@ struct AggArgs {
   StagedBuf staged[AGG_MAX_STAGED];
   uint64_t *tkeys;       // [nwords][cap + 2]   slot cap = NULL key, slot cap+1 = key equal to the EMPTY sentinel
   uint64_t *tacc;        // [nslots][cap + 2]
-  int32_t *flags;        // [0] abort (table too small), [1] NULL-key slot used, [2] sentinel-key slot used
+  int32_t *flags;        // [0] abort (table too small), [1] NULL-key slot used, [2] sentinel-key slot used,
+                         // [6] the dictionary tier met a shape it should not handle (see gate)
   int64_t cap;
+  // Automatic tier choice, no host round trip: the dictionary kernel runs with gate = 1; the first warp whose rows do not all
+  // resolve in its block's dictionary (more than AGG_DICT groups, or NULL / sentinel keys) raises flags[6], every block stops at
+  // its next tile boundary and leaves the number of tiles it finished in progress[block].  The shared-memory kernel is launched
+  // right behind it with gate = 2: it returns at once when flags[6] is clear, otherwise it picks up the unfinished tiles.
+  int32_t gate;          // 0: plain; 1: dictionary kernel, watch and yield; 2: shared-memory kernel, take over
+  int32_t scap;          // shared-memory tier: table capacity (power of two)
+  int32_t *progress;     // [dict_grid]
+  int32_t dict_grid, dict_items;
+  int32_t combine;       // shared-memory tier: combine same-entry rows of a warp before the atomics
 };
 
 struct DynPlan {
@@ -483,12 +493,10 @@ __device__ __forceinline__ void accumulate_slots_dict(const AggArgs &a, const Ti
 
 // Shared memory of the update kernels: uint64 dict_keys[AGG_DICT]; uint64 acc[(AGG_DICT + 1) * nslots][AGG_THREADS]
 // (last group = trash); the staged kernel puts the column stages and the mbarriers in front.
+// keep / packed group key / special-slot class of the thread's rows
 template <class P, int ITEMS, bool FULL, bool STAGED>
-__device__ __forceinline__ void process_tile(const AggArgs &a, const TileCtx &t, uint64_t *dict_keys, uint64_t *acc, int tid, int64_t stride) {
+__device__ __forceinline__ void tile_keys(const AggArgs &a, const TileCtx &t, bool (&keep)[ITEMS], uint64_t (&key)[ITEMS], int (&special)[ITEMS]) {
   const PlanMeta &m = P::meta(a);
-  const int ns = m.nslots;
-  bool keep[ITEMS];
-  uint64_t key[ITEMS];
 #pragma unroll
   for (int k = 0; k < ITEMS; k++) {
     keep[k] = FULL || t.row0 + (int64_t)k * AGG_THREADS <= t.last;
@@ -502,7 +510,6 @@ __device__ __forceinline__ void process_tile(const AggArgs &a, const TileCtx &t,
   }
   apply_filter_terms<P, ITEMS, FULL, STAGED>(a, t, keep);
   // ---- group key packing --------------------------------------------------------------------------------
-  int special[ITEMS];
 #pragma unroll
   for (int k = 0; k < ITEMS; k++) special[k] = 0;
   if (m.single64) {
@@ -551,6 +558,16 @@ __device__ __forceinline__ void process_tile(const AggArgs &a, const TileCtx &t,
       }
     });
   }
+}
+
+template <class P, int ITEMS, bool FULL, bool STAGED, bool YIELD = false>
+__device__ __forceinline__ bool process_tile(const AggArgs &a, const TileCtx &t, uint64_t *dict_keys, uint64_t *acc, int tid, int64_t stride) {
+  const PlanMeta &m = P::meta(a);
+  const int ns = m.nslots;
+  bool keep[ITEMS];
+  uint64_t key[ITEMS];
+  int special[ITEMS];
+  tile_keys<P, ITEMS, FULL, STAGED>(a, t, keep, key, special);
   // ---- where does each row accumulate? ---------------------------------------------------------------------
   int64_t dst[ITEMS];
   int doff[ITEMS];
@@ -578,9 +595,16 @@ __device__ __forceinline__ void process_tile(const AggArgs &a, const TileCtx &t,
     }
     if (gid >= 0) doff[k] = gid * ns * AGG_THREADS + tid;
     else {
-      dst[k] = table_slot(a, key[k], special[k]);
       all_dict = false;
+      if (!YIELD) dst[k] = table_slot(a, key[k], special[k]);
     }
+  }
+  if (YIELD) {   // watch-and-yield mode (AggArgs::gate == 1): a tile that does not resolve in the dictionary is left untouched
+    if (__syncthreads_or(!all_dict)) return false;
+#pragma unroll
+    for (int k = 0; k < ITEMS; k++) doff[k] = doff[k] >= 0 ? doff[k] : trash;
+    accumulate_slots_dict<P, ITEMS, FULL, STAGED>(a, t, doff, acc, trash);
+    return true;
   }
   if (__all_sync(0xffffffffu, all_dict)) {
 #pragma unroll
@@ -589,6 +613,7 @@ __device__ __forceinline__ void process_tile(const AggArgs &a, const TileCtx &t,
   } else {
     accumulate_slots<P, ITEMS, FULL, STAGED>(a, t, dst, doff, acc, stride);
   }
+  return true;
 }
 
 template <class P>
@@ -653,16 +678,225 @@ __global__ void __launch_bounds__(AGG_THREADS) agg_update_kernel(const __grid_co
   __syncthreads();
   constexpr int64_t TILE = (int64_t)AGG_THREADS * ITEMS;
   const int64_t stride = a.cap + 2;
-  for (int64_t base = (int64_t)blockIdx.x * TILE; base < a.n; base += (int64_t)gridDim.x * TILE) {
+  int32_t tiles_done = 0;
+  for (int64_t base = (int64_t)blockIdx.x * TILE; base < a.n; base += (int64_t)gridDim.x * TILE, tiles_done++) {
     if (*(volatile int32_t *)a.flags) break;   // another block found the table too small: give up early
     TileCtx t{nullptr, base + tid, a.n - 1};
     const int64_t next = base + (int64_t)gridDim.x * TILE;
     if (PREFETCH && next + TILE <= a.n) prefetch_tile<P, ITEMS>(a, next + tid);
-    if (base + TILE <= a.n) process_tile<P, ITEMS, true, false>(a, t, dict_keys, acc, tid, stride);
+    if (a.gate == 1) {   // watch and yield: stop at the first tile the dictionary cannot hold, or when another block did
+      if (*(volatile int32_t *)&a.flags[6]) break;
+      const bool done = base + TILE <= a.n ? process_tile<P, ITEMS, true, false, true>(a, t, dict_keys, acc, tid, stride)
+                                           : process_tile<P, ITEMS, false, false, true>(a, t, dict_keys, acc, tid, stride);
+      if (!done) {
+        *(volatile int32_t *)&a.flags[6] = 1;
+        break;
+      }
+    } else if (base + TILE <= a.n) process_tile<P, ITEMS, true, false>(a, t, dict_keys, acc, tid, stride);
     else process_tile<P, ITEMS, false, false>(a, t, dict_keys, acc, tid, stride);
   }
+  if (a.gate == 1 && tid == 0) a.progress[blockIdx.x] = tiles_done;
   __syncthreads();
   dict_merge<P>(a, dict_keys, acc, tid, stride);
+}
+
+// ---- shared-memory tier: medium cardinality ----------------------------------------------------------------------------------
+// Between "a handful of groups" (lane-private dictionary above) and "millions" (HBM table) sits the common GROUP BY over a
+// dimension attribute: hundreds to a few thousand groups.  Sending every row to the HBM table then means tens of millions of
+// atomics on a few thousand L2 lines (measured: 1024 groups run 15x slower than 4).  Here one 1024-thread block per SM keeps an
+// open-addressing table in shared memory (keys + one accumulator array per slot, shared-memory atomics), and flushes it into
+// the HBM table once at the end.  The table stops inserting at 75 % load; rows whose key is not resident take the HBM path,
+// and when that becomes the norm (high cardinality) the block stops probing altogether.
+// The block is eight 128-thread sub-blocks, each walking its own tiles with the tile geometry the loaders assume.
+constexpr int AGGS_SUB = 8;
+constexpr int AGGS_THREADS = AGG_THREADS * AGGS_SUB;
+constexpr int AGGS_PROBES = 8;
+enum { CTL_FILL = 0, CTL_BYPASS = 1, CTL_ROWS = 2, CTL_HITS = 3, CTL_SPECIAL = 4 /* and 5 */, CTL_WORDS = 8 };
+
+__device__ __forceinline__ void shared_op(int kind, uint64_t *p, uint64_t v) {
+  switch (kind) {
+    case K_ADD_I64: {   // a 64-bit shared-memory add is a compare-and-swap loop; two native 32-bit adds with a carry are not
+      uint32_t *w = (uint32_t *)p;
+      const uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+      const uint32_t old = atomicAdd(w, lo);
+      const uint32_t carry = old + lo < old ? 1u : 0u;
+      if (hi + carry) atomicAdd(w + 1, hi + carry);
+      break;
+    }
+    case K_ADD_F64: atomicAdd((double *)p, __longlong_as_double((int64_t)v)); break;
+    case K_MIN_U64: atomicMin((unsigned long long *)p, (unsigned long long)v); break;
+    default: atomicMax((unsigned long long *)p, (unsigned long long)v); break;
+  }
+}
+
+template <class P, int ITEMS, bool FULL>
+__device__ __forceinline__ void process_tile_smem(const AggArgs &a, const TileCtx &t, uint64_t *skeys, uint64_t *sacc, uint32_t *sctl,
+                                                  int64_t stride) {
+  const PlanMeta &m = P::meta(a);
+  bool keep[ITEMS];
+  uint64_t key[ITEMS];
+  int special[ITEMS];
+  tile_keys<P, ITEMS, FULL, false>(a, t, keep, key, special);
+  const uint32_t C = (uint32_t)a.scap, cmask = C - 1, fill_limit = C - (C >> 2);
+  volatile uint32_t *vctl = sctl;
+  // control words change under our feet: take one reading per warp so that warp-collective code below stays converged
+  const bool bypass = __shfl_sync(0xffffffffu, vctl[CTL_BYPASS], 0) != 0;
+  int64_t dst[ITEMS];
+  int soff[ITEMS];
+  uint32_t rows = 0, hits = 0;
+#pragma unroll
+  for (int k = 0; k < ITEMS; k++) {
+    dst[k] = -1;
+    soff[k] = -1;
+    if (!keep[k]) continue;
+    rows++;
+    if (special[k]) {   // NULL key / key equal to the EMPTY sentinel: two fixed entries behind the table
+      soff[k] = (int)C + special[k] - 1;
+      vctl[CTL_SPECIAL + special[k] - 1] = 1;
+      hits++;
+      continue;
+    }
+    if (!bypass) {
+      uint32_t x = ((uint32_t)key[k] ^ (uint32_t)(key[k] >> 32)) * 0x9E3779B1u;
+      uint32_t h = (x ^ (x >> 15)) & cmask;
+#pragma unroll 1
+      for (int p = 0; p < AGGS_PROBES; p++) {
+        uint64_t cur = *(volatile uint64_t *)&skeys[h];
+        if (cur == EMPTY_KEY && vctl[CTL_FILL] < fill_limit) {
+          cur = atomicCAS((unsigned long long *)&skeys[h], (unsigned long long)EMPTY_KEY, (unsigned long long)key[k]);
+          if (cur == EMPTY_KEY) {
+            atomicAdd(&sctl[CTL_FILL], 1u);
+            cur = key[k];
+          }
+        }
+        if (cur == key[k]) {
+          soff[k] = (int)h;
+          break;
+        }
+        if (cur == EMPTY_KEY) break;   // table closed for inserts and the key is not resident
+        h = (h + 1) & cmask;
+      }
+    }
+    if (soff[k] >= 0) hits++;
+    else dst[k] = table_slot(a, key[k], 0);
+  }
+  // once the table is full, watch the hit rate: a block that mostly misses stops probing (high cardinality)
+  if (!bypass && __shfl_sync(0xffffffffu, vctl[CTL_FILL], 0) >= fill_limit) {
+    rows = __reduce_add_sync(0xffffffffu, rows);
+    hits = __reduce_add_sync(0xffffffffu, hits);
+    if ((threadIdx.x & 31) == 0) {
+      uint32_t r = atomicAdd(&sctl[CTL_ROWS], rows) + rows, hh = atomicAdd(&sctl[CTL_HITS], hits) + hits;
+      if (r >= 16384 && hh * 2 < r) vctl[CTL_BYPASS] = 1;
+    }
+  }
+  // Rows of one warp that land on the same entry: with few distinct keys per warp every lane would fight for the same words
+  // (a 64-bit shared-memory atomic is a compare-and-swap loop), so when some entry has 3+ takers the lanes first combine their
+  // values through shuffles and only the lowest lane of every entry goes to memory.
+  // Only the compare-and-swap kinds need this (double sums, min, max; int64 sums use native 32-bit adds), a.combine says
+  // whether the plan has any.  MATCH is a slow instruction, so the check is rationed: every tile while the table holds few keys
+  // (where crowding is the norm), every 8th tile otherwise (hot keys among many still get relief there, and a crowded
+  // compare-and-swap is slow, not stuck).
+  uint32_t grp[ITEMS];
+  bool heavy = false;
+  const bool check = a.combine && (__shfl_sync(0xffffffffu, vctl[CTL_FILL] < 256u, 0) || ((t.row0 >> 9) & 7) == 0);
+  if (check) {
+#pragma unroll
+    for (int k = 0; k < ITEMS; k++) {
+      const uint32_t d = soff[k] >= 0 ? (uint32_t)soff[k] : 0x80000000u | (threadIdx.x & 31);   // HBM-bound rows are not combined
+      grp[k] = __match_any_sync(0xffffffffu, d);
+      heavy |= __popc(grp[k]) >= 3;
+    }
+    heavy = __any_sync(0xffffffffu, heavy);
+  }
+  const int lane = threadIdx.x & 31;
+  plan_for<P>(m.nslots, [&](int s) {
+    uint64_t v[ITEMS];
+    bool ok[ITEMS];
+#pragma unroll
+    for (int k = 0; k < ITEMS; k++) ok[k] = dst[k] >= 0 || soff[k] >= 0;
+    slot_input_valid<P, ITEMS, FULL, false>(a, s, t, ok);
+    slot_values<P, ITEMS, FULL, false>(a, s, t, v);
+    uint64_t *lacc = sacc + (size_t)s * (C + 2);
+    uint64_t *gacc = a.tacc + (int64_t)s * stride;
+    const int kind = m.slot_kind[s];
+    if (heavy && kind != K_ADD_I64) {
+      const uint64_t ident = slot_identity(kind);
+#pragma unroll
+      for (int k = 0; k < ITEMS; k++) {
+        const uint64_t x = ok[k] ? v[k] : ident;
+        const bool leader = (grp[k] & lanemask_lt()) == 0;
+        uint64_t acc = x;
+#pragma unroll 4
+        for (int i = 0; i < 32; i++) {
+          const uint64_t o = __shfl_sync(0xffffffffu, x, i);
+          if (leader && i != lane && ((grp[k] >> i) & 1)) acc = apply_op(kind, acc, o);
+        }
+        v[k] = acc;
+        ok[k] = leader && (dst[k] >= 0 || soff[k] >= 0);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < ITEMS; k++) {
+      if (!ok[k]) continue;
+      if (soff[k] >= 0) shared_op(kind, lacc + soff[k], v[k]);
+      else global_op(kind, gacc + dst[k], v[k]);
+    }
+  });
+}
+
+template <class P, int ITEMS>
+__global__ void __launch_bounds__(AGGS_THREADS) agg_update_smem_kernel(const __grid_constant__ AggArgs a) {
+  extern __shared__ __align__(128) uint64_t sm_tab[];
+  if (a.gate == 2 && *(volatile int32_t *)&a.flags[6] == 0) return;   // the dictionary tier finished the job
+  const PlanMeta &m = P::meta(a);
+  const int ns = m.nslots;
+  const uint32_t C = (uint32_t)a.scap;
+  uint64_t *skeys = sm_tab;                       // [C + 2]
+  uint64_t *sacc = sm_tab + (C + 2);              // [ns][C + 2]
+  uint32_t *sctl = (uint32_t *)(sacc + (size_t)ns * (C + 2));
+  for (uint32_t i = threadIdx.x; i < C + 2; i += AGGS_THREADS) {
+    skeys[i] = EMPTY_KEY;
+    for (int s = 0; s < ns; s++) sacc[(size_t)s * (C + 2) + i] = slot_identity(m.slot_kind[s]);
+  }
+  if (threadIdx.x < CTL_WORDS) sctl[threadIdx.x] = 0;
+  __syncthreads();
+  constexpr int64_t TILE = (int64_t)AGG_THREADS * ITEMS;
+  const int64_t stride = a.cap + 2;
+  const int tid = threadIdx.x & (AGG_THREADS - 1);
+  const int64_t vb = (int64_t)blockIdx.x * AGGS_SUB + (threadIdx.x / AGG_THREADS), nvb = (int64_t)gridDim.x * AGGS_SUB;
+  auto one_tile = [&](int64_t base) {
+    TileCtx t{nullptr, base + tid, a.n - 1};
+    if (base + TILE <= a.n) process_tile_smem<P, ITEMS, true>(a, t, skeys, sacc, sctl, stride);
+    else process_tile_smem<P, ITEMS, false>(a, t, skeys, sacc, sctl, stride);
+  };
+  if (a.gate == 2) {   // the tiles the dictionary kernel's blocks left behind (its tile = dict_items / ITEMS of ours)
+    const int64_t dtile = (int64_t)AGG_THREADS * a.dict_items;
+    for (int64_t b = vb; b < a.dict_grid; b += nvb)
+      for (int64_t j = a.progress[b];; j++) {
+        const int64_t base0 = (b + j * a.dict_grid) * dtile;
+        if (base0 >= a.n || *(volatile int32_t *)a.flags) break;
+        for (int64_t base = base0; base < base0 + dtile && base < a.n; base += TILE) one_tile(base);
+      }
+  } else {
+    for (int64_t base = vb * TILE; base < a.n; base += nvb * TILE) {
+      if (*(volatile int32_t *)a.flags) break;
+      one_tile(base);
+    }
+  }
+  __syncthreads();
+  for (uint32_t h = threadIdx.x; h < C + 2; h += AGGS_THREADS) {
+    int64_t slot;
+    if (h < C) {
+      const uint64_t key = skeys[h];
+      if (key == EMPTY_KEY) continue;
+      slot = table_slot(a, key, 0);
+    } else {
+      if (!sctl[CTL_SPECIAL + (h - C)]) continue;
+      slot = table_slot(a, 0, (int)(h - C) + 1);
+    }
+    if (slot < 0) continue;
+    for (int s = 0; s < ns; s++) global_op(m.slot_kind[s], &a.tacc[(int64_t)s * stride + slot], sacc[(size_t)s * (C + 2) + h]);
+  }
 }
 
 // ---- staged kernel: TMA bulk copies + mbarrier pipeline ----------------------------------------------------------------

@@ -76,10 +76,12 @@ constexpr int ITEMS_DIRECT = 8;   // rows per thread per tile, direct path (1024
 constexpr int ITEMS_STAGED = 4;   // staged path (512-row tiles keep two blocks per SM resident)
 
 typedef void (*AggKernel)(const AggArgs);
+constexpr int ITEMS_SMEM = 4;     // shared-memory tier: 512 threads x 4 rows
 struct KernelChoice {
   AggKernel direct, staged;
   int items_direct;
   const char *name;
+  AggKernel smem = agg_update_smem_kernel<DynPlan, ITEMS_SMEM>;
 };
 static KernelChoice choose_kernels(const PlanMeta &m) {
   if (getenv("SB_AGG_DISABLE_STATIC") == nullptr) {
@@ -94,10 +96,10 @@ static KernelChoice choose_kernels(const PlanMeta &m) {
     }
     if (memcmp(&m, &kHostMetaC1I64, sizeof(PlanMeta)) == 0)
       return {agg_update_kernel<StaticPlan<&kDevMetaC1I64>, ITEMS_DIRECT>, agg_update_staged_kernel<StaticPlan<&kDevMetaC1I64>, ITEMS_STAGED>,
-              ITEMS_DIRECT, "static:groupby_i64_sum_i64"};
+              ITEMS_DIRECT, "static:groupby_i64_sum_i64", agg_update_smem_kernel<StaticPlan<&kDevMetaC1I64>, ITEMS_SMEM>};
     if (memcmp(&m, &kHostMetaC1F64, sizeof(PlanMeta)) == 0)
       return {agg_update_kernel<StaticPlan<&kDevMetaC1F64>, ITEMS_DIRECT>, agg_update_staged_kernel<StaticPlan<&kDevMetaC1F64>, ITEMS_STAGED>,
-              ITEMS_DIRECT, "static:groupby_i64_sum_f64"};
+              ITEMS_DIRECT, "static:groupby_i64_sum_f64", agg_update_smem_kernel<StaticPlan<&kDevMetaC1F64>, ITEMS_SMEM>};
   }
   return {agg_update_kernel<DynPlan, ITEMS_DIRECT>, agg_update_staged_kernel<DynPlan, ITEMS_STAGED>, ITEMS_DIRECT, "dynamic"};
 }
@@ -679,6 +681,23 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
   if (blocks_per_sm < 1) blocks_per_sm = 1;
   if (blocks_per_sm > 8) blocks_per_sm = 8;
   int grid = grid_for(n, AGG_THREADS * kc.items_direct, rt().num_sms * blocks_per_sm);
+  // ---- tiers: "dict" (lane-private dictionary + HBM table), "smem" (shared-memory table + HBM table), or "auto": the
+  // dictionary kernel starts, yields as soon as the input turns out not to be a few-groups shape, and the shared-memory kernel
+  // launched behind it finishes the job (AggArgs::gate) -- no sample pass, no host round trip.
+  const char *tier_env = getenv("SB_AGG_TIER");
+  int tier = 0;   // 0 auto, 1 dict only, 2 smem only
+  if (tier_env && !strcmp(tier_env, "dict")) tier = 1;
+  else if (tier_env && !strcmp(tier_env, "smem")) tier = 2;
+  int32_t scap = 8192;
+  while (scap > 512 && (size_t)(scap + 2) * (1 + ns) * 8 + 64 > 200 * 1024) scap >>= 1;
+  if (tier == 0 && plan->expected_groups > 0)   // the caller knows: few -> dictionary, fits shared memory -> smem, else straight to HBM
+    tier = plan->expected_groups <= AGG_DICT || plan->expected_groups > scap ? 1 : 2;
+  const size_t smem_tab = (size_t)(scap + 2) * (1 + ns) * 8 + 64;
+  a.combine = 0;   // any compare-and-swap accumulator kind?
+  for (int i = 0; i < ns; i++) a.combine |= m.slot_kind[i] != K_ADD_I64;
+  const int grid_smem = grid_for(n, AGG_THREADS * ITEMS_SMEM * AGGS_SUB, rt().num_sms);
+  if (tier != 1) SB_CUDA(cudaFuncSetAttribute(kc.smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  a.scap = scap;
 
   // ---- staged (TMA) path: lay out one shared-memory stage holding the tile of every distinct referenced buffer ----
   const char *path_env = getenv("SB_AGG_PATH");   // "direct" | "staged" (default: direct)
@@ -729,7 +748,7 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
     } else staged = false;
   }
 
-  Scratch flags(32, st);
+  Scratch flags(32, st), progress((int64_t)grid * 4 + 16, st);
   std::unique_ptr<Scratch> slot_ids_buf;
   int64_t ngroups = 0;
   void *tkeys = nullptr, *tacc = nullptr;
@@ -758,8 +777,20 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
     a.cap = cap;
     if (n > 0) {
       KernelTimer kt(final_mode ? "agg_update_final" : "agg_update", st);
+      a.gate = 0;
       if (a.nwords == 1 && staged) kc.staged<<<grid_staged, AGG_THREADS, smem_staged, st>>>(a);
-      else if (a.nwords == 1) kc.direct<<<grid, AGG_THREADS, smem_acc, st>>>(a);
+      else if (a.nwords == 1 && tier == 1) kc.direct<<<grid, AGG_THREADS, smem_acc, st>>>(a);
+      else if (a.nwords == 1 && tier == 2) kc.smem<<<grid_smem, AGGS_THREADS, smem_tab, st>>>(a);
+      else if (a.nwords == 1) {
+        a.gate = 1;
+        a.progress = progress.as<int32_t>();
+        a.dict_grid = grid;
+        a.dict_items = kc.items_direct;
+        kc.direct<<<grid, AGG_THREADS, smem_acc, st>>>(a);
+        SB_LAUNCH_CHECK();
+        a.gate = 2;
+        kc.smem<<<grid_smem, AGGS_THREADS, smem_tab, st>>>(a);
+      }
       else if (a.nwords == 2) agg_update_wide_kernel<2, 4><<<grid, AGG_THREADS, 0, st>>>(a);
       else if (a.nwords == 3) agg_update_wide_kernel<3, 4><<<grid, AGG_THREADS, 0, st>>>(a);
       else agg_update_wide_kernel<4, 4><<<grid, AGG_THREADS, 0, st>>>(a);
@@ -787,8 +818,9 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
     cudaFreeAsync(tacc, st); tacc = nullptr;
     cap = cap * 16 > cap_max ? cap_max : cap * 16;
   }
-  if (getenv("SB_AGG_VERBOSE")) fprintf(stderr, "[sb_hash_aggregate] n=%lld plan=%s path=%s cap=%lld slots=%d\n", (long long)n, kc.name,
-                                        a.nwords > 1 ? "wide" : (staged ? "staged" : "direct"), (long long)cap, ns);
+  if (getenv("SB_AGG_VERBOSE")) fprintf(stderr, "[sb_hash_aggregate] n=%lld plan=%s path=%s tier=%s cap=%lld slots=%d scap=%d\n", (long long)n, kc.name,
+                                        a.nwords > 1 ? "wide" : (staged ? "staged" : "direct"), tier == 0 ? "auto" : (tier == 1 ? "dict" : "smem"),
+                                        (long long)cap, ns, scap);
   Scratch &slot_ids = *slot_ids_buf;
   if (plan->nkeys == 0 && ngroups == 0) {
     // no grouping keys: exactly one output row even for empty input (AggregateCodegenSupport.scala:131);

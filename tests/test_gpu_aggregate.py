@@ -193,8 +193,9 @@ def test_filter_project_operator(gpu, stream):
 
 
 @pytest.mark.parametrize("env", [{}, {"SB_AGG_DISABLE_STATIC": "1"}, {"SB_AGG_PATH": "staged"},
-                                 {"SB_AGG_PATH": "staged", "SB_AGG_DISABLE_STATIC": "1"}, {"SB_AGG_Q1_VARIANT": "4"}],
-                         ids=["static-direct", "dynamic-direct", "static-tma", "dynamic-tma", "static-direct-4rows"])
+                                 {"SB_AGG_PATH": "staged", "SB_AGG_DISABLE_STATIC": "1"}, {"SB_AGG_Q1_VARIANT": "4"},
+                                 {"SB_AGG_TIER": "smem"}, {"SB_AGG_TIER": "dict"}],
+                         ids=["static-direct", "dynamic-direct", "static-tma", "dynamic-tma", "static-direct-4rows", "smem-tier", "dict-tier"])
 def test_every_update_kernel_variant_matches_the_oracle(gpu, stream, env, monkeypatch):
     """The plan-specialised (StaticPlan), generic (DynPlan), direct-load and TMA-staged update kernels share one code base;
     each variant must produce the oracle's Q1 answer, including a ragged last tile and a NULL-able variant of the plan."""
@@ -225,3 +226,44 @@ def test_every_update_kernel_variant_matches_the_oracle(gpu, stream, env, monkey
     want2 = O.hash_aggregate(p, ["l_returnflag", "l_linestatus"], [("sum", "l_quantity", "sq"), ("avg", "l_quantity", "aq"),
                                                                     ("count", "l_quantity", "cq"), ("count_star", None, "n"), ("max", "dp", "mx")])
     assert_tables_equal(got2, want2, key_cols=["l_returnflag", "l_linestatus"])
+
+
+@pytest.mark.parametrize("groups", [5, 1000, 6000, 200_000])
+@pytest.mark.parametrize("tier", ["auto", "smem", "dict"])
+def test_cardinality_tiers_agree_with_the_oracle(gpu, stream, groups, tier, monkeypatch):
+    """Few groups (lane-private dictionary), a few thousand (shared-memory table), more than the shared-memory table holds
+    (spill to the HBM table, then bypass): every tier and the sampled automatic choice give the oracle's answer.  Keys include
+    NULL and -1 (the bit pattern of the table's EMPTY sentinel); inputs include NULLs; min/max/avg/count ride along."""
+    from spark_b200.columnar import ColumnarBatch
+    from spark_b200.execution import HashAggregateExec, LocalTableScanExec
+    from spark_b200.expressions import Average, Count, Max, Min, Sum, col
+    if tier != "auto":
+        monkeypatch.setenv("SB_AGG_TIER", tier)
+    n = 400_037
+    rng = np.random.default_rng(groups)
+    k = rng.integers(-1, groups - 1, n)
+    t = pa.table({"k": pa.array(k, mask=rng.random(n) < 0.03),
+                  "v": pa.array(rng.integers(-2 ** 40, 2 ** 40, n), mask=rng.random(n) < 0.1),
+                  "d": pa.array(rng.standard_normal(n) * 1e3)})
+    aggs = [(Sum(col("v")), "sv"), (Sum(col("d")), "sd"), (Average(col("d")), "ad"), (Count(col("v")), "cv"), (Count(), "n"),
+            (Min(col("v")), "mn"), (Max(col("d")), "mx")]
+    got = HashAggregateExec(["k"], aggs, LocalTableScanExec(ColumnarBatch.from_arrow(t, stream))).collect(stream)
+    want = O.hash_aggregate(t, ["k"], [("sum", "v", "sv"), ("sum", "d", "sd"), ("avg", "d", "ad"), ("count", "v", "cv"),
+                                       ("count_star", None, "n"), ("min", "v", "mn"), ("max", "d", "mx")])
+    assert_tables_equal(got, want, key_cols=["k"])
+
+
+@pytest.mark.parametrize("groups", [3, 1024])
+@pytest.mark.parametrize("vtype", ["i64", "f64"])
+def test_groupby_sum_static_shapes_through_both_tiers(gpu, stream, groups, vtype):
+    """BASELINE configs[0] shape (k int64, v int64/double, no NULLs): the plan-specialised kernels of both tiers."""
+    from spark_b200.columnar import ColumnarBatch
+    from spark_b200.execution import HashAggregateExec, LocalTableScanExec
+    from spark_b200.expressions import Sum, col
+    n = 600_011
+    rng = np.random.default_rng(groups + 7)
+    v = rng.integers(-2 ** 31, 2 ** 31, n) if vtype == "i64" else rng.random(n) * 1e4
+    t = pa.table({"k": rng.integers(0, groups, n), "v": v})
+    got = HashAggregateExec(["k"], [(Sum(col("v")), "s")], LocalTableScanExec(ColumnarBatch.from_arrow(t, stream))).collect(stream)
+    want = O.hash_aggregate(t, ["k"], [("sum", "v", "s")])
+    assert_tables_equal(got, want, key_cols=["k"])

@@ -86,12 +86,22 @@ def main():
         # ---- hash aggregate: SELECT k, SUM(v) GROUP BY k (configs[0] shape, scaled to 64M rows) ---------------------------
         n = 64_000_000
         v = rng.integers(-2 ** 31, 2 ** 31, n)
-        for groups in (4, 1024, 65536, 1 << 20):
+        group_list = [int(x) for x in os.environ["SB_OPBENCH_GROUPS"].split(",")] if os.environ.get("SB_OPBENCH_GROUPS") else [4, 1024, 65536, 1 << 20]
+        for groups in group_list:
             b = ColumnarBatch.from_numpy({"k": rng.integers(0, groups, n), "v": v}, stream)
             stream.synchronize()
-            agg = HashAggregateExec(["k"], [(Sum(col("v")), "s")], LocalTableScanExec(b), expected_groups=groups)
+            for hint, tag in ((groups, "hinted"), (0, "no hint")):   # Spark's planner has no cardinality to pass: "no hint" is the honest case
+                agg = HashAggregateExec(["k"], [(Sum(col("v")), "s")], LocalTableScanExec(b), expected_groups=hint)
+                ms, k = timed(lib, stream, lambda: agg.executeColumnar(stream).close(), ["agg_update"])
+                emit("hash_aggregate sum(int64) groups=%d (%s)" % (groups, tag), n, 16 * n + 16 * groups, ms, k)
+            b.close()
+        vd = rng.random(n) * 1e4
+        for groups in (16, 1024):   # double sums accumulate through compare-and-swap in shared memory: a different regime
+            b = ColumnarBatch.from_numpy({"k": rng.integers(0, groups, n), "v": vd}, stream)
+            stream.synchronize()
+            agg = HashAggregateExec(["k"], [(Sum(col("v")), "s")], LocalTableScanExec(b))
             ms, k = timed(lib, stream, lambda: agg.executeColumnar(stream).close(), ["agg_update"])
-            emit("hash_aggregate sum(int64) groups=%d" % groups, n, 16 * n + 16 * groups, ms, k)
+            emit("hash_aggregate sum(double) groups=%d (no hint)" % groups, n, 16 * n + 16 * groups, ms, k)
             b.close()
 
     if only in ("", "sort"):
