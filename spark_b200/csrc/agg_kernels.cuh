@@ -133,22 +133,28 @@ __device__ __forceinline__ uint64_t mix64(uint64_t x) {   // slot choice only; n
 
 // find-or-insert in the HBM table (single-word keys); returns slot index or -1 (abort: table too small).
 // special: 0 regular key, 1 NULL key of a single 64-bit column, 2 a 64-bit key equal to the EMPTY sentinel.
-__device__ __forceinline__ int64_t table_slot(const AggArgs &a, uint64_t key, int special) {
-  if (special == 1) { a.flags[1] = 1; return a.cap; }
-  if (special == 2) { a.flags[2] = 1; return a.cap + 1; }
-  uint64_t mask = (uint64_t)a.cap - 1;
-  uint64_t h = mix64(key) & mask;
+__device__ __forceinline__ uint64_t table_home(const AggArgs &a, uint64_t key) { return mix64(key) & ((uint64_t)a.cap - 1); }
+// continues a probe whose first word `cur` (the content of slot h) the caller has already fetched -- callers with several rows
+// per thread issue all first-probe loads together, so the L2 round trips overlap instead of queueing behind one another
+__device__ __forceinline__ int64_t table_slot_from(const AggArgs &a, uint64_t key, uint64_t h, uint64_t cur) {
+  const uint64_t mask = (uint64_t)a.cap - 1;
   for (int step = 0; step < AGG_PROBE_LIMIT; step++) {
-    uint64_t cur = a.tkeys[h];
     if (cur == key) return (int64_t)h;
     if (cur == EMPTY_KEY) {
       uint64_t old = atomicCAS((unsigned long long *)&a.tkeys[h], (unsigned long long)EMPTY_KEY, (unsigned long long)key);
       if (old == EMPTY_KEY || old == key) return (int64_t)h;
     }
     h = (h + 1) & mask;
+    cur = __ldcg(&a.tkeys[h]);
   }
   a.flags[0] = 1;
   return -1;
+}
+__device__ __forceinline__ int64_t table_slot(const AggArgs &a, uint64_t key, int special) {
+  if (special == 1) { a.flags[1] = 1; return a.cap; }
+  if (special == 2) { a.flags[2] = 1; return a.cap + 1; }
+  const uint64_t h = table_home(a, key);
+  return table_slot_from(a, key, h, __ldcg(&a.tkeys[h]));
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -599,8 +605,8 @@ __device__ __forceinline__ bool process_tile(const AggArgs &a, const TileCtx &t,
       if (!YIELD) dst[k] = table_slot(a, key[k], special[k]);
     }
   }
-  if (YIELD) {   // watch-and-yield mode (AggArgs::gate == 1): a tile that does not resolve in the dictionary is left untouched
-    if (__syncthreads_or(!all_dict)) return false;
+  if (YIELD) {   // watch-and-yield mode (AggArgs::gate == 1): a warp whose rows do not resolve in the dictionary leaves them untouched
+    if (!__all_sync(0xffffffffu, all_dict)) return false;
 #pragma unroll
     for (int k = 0; k < ITEMS; k++) doff[k] = doff[k] >= 0 ? doff[k] : trash;
     accumulate_slots_dict<P, ITEMS, FULL, STAGED>(a, t, doff, acc, trash);
@@ -668,7 +674,7 @@ __device__ __forceinline__ void prefetch_tile(const AggArgs &a, int64_t row0) {
 }
 
 // ---- direct kernel: columns are read straight from HBM --------------------------------------------------------------
-template <class P, int ITEMS, bool PREFETCH = false>
+template <class P, int ITEMS, bool PREFETCH = false, bool YIELD = false, bool FAT = false>
 __global__ void __launch_bounds__(AGG_THREADS) agg_update_kernel(const __grid_constant__ AggArgs a) {
   extern __shared__ __align__(128) uint64_t sm_direct[];
   uint64_t *dict_keys = sm_direct;
@@ -678,14 +684,19 @@ __global__ void __launch_bounds__(AGG_THREADS) agg_update_kernel(const __grid_co
   __syncthreads();
   constexpr int64_t TILE = (int64_t)AGG_THREADS * ITEMS;
   const int64_t stride = a.cap + 2;
-  int32_t tiles_done = 0;
-  for (int64_t base = (int64_t)blockIdx.x * TILE; base < a.n; base += (int64_t)gridDim.x * TILE, tiles_done++) {
-    if (*(volatile int32_t *)a.flags) break;   // another block found the table too small: give up early
+  // The abort / yield flags are sampled while a tile is being processed and acted on before the next one, so their L2 round trip
+  // hides behind the tile's own loads.  Yielding is per WARP (no block barrier in the hot loop): a warp records how many tiles
+  // it finished; the shared-memory kernel mirrors the tile geometry and picks up exactly the warp slices left behind.
+  int32_t tiles_done = 0, stop = 0;
+  for (int64_t base = (int64_t)blockIdx.x * TILE; base < a.n && !stop; base += (int64_t)gridDim.x * TILE) {
+    stop = *(volatile int32_t *)a.flags;                      // another block found the table too small: give up early
+    if (YIELD) stop |= *(volatile int32_t *)&a.flags[6];      // not a few-groups input: yield
     TileCtx t{nullptr, base + tid, a.n - 1};
     const int64_t next = base + (int64_t)gridDim.x * TILE;
     if (PREFETCH && next + TILE <= a.n) prefetch_tile<P, ITEMS>(a, next + tid);
-    if (a.gate == 1) {   // watch and yield: stop at the first tile the dictionary cannot hold, or when another block did
-      if (*(volatile int32_t *)&a.flags[6]) break;
+    if (FAT && a.gate == 3) {   // never taken; see SB_AGG_Q1_VARIANT=8pf in aggregate.cu
+      process_tile<P, ITEMS, true, false>(a, t, dict_keys, acc, tid, stride);
+    } else if constexpr (YIELD) {
       const bool done = base + TILE <= a.n ? process_tile<P, ITEMS, true, false, true>(a, t, dict_keys, acc, tid, stride)
                                            : process_tile<P, ITEMS, false, false, true>(a, t, dict_keys, acc, tid, stride);
       if (!done) {
@@ -694,8 +705,9 @@ __global__ void __launch_bounds__(AGG_THREADS) agg_update_kernel(const __grid_co
       }
     } else if (base + TILE <= a.n) process_tile<P, ITEMS, true, false>(a, t, dict_keys, acc, tid, stride);
     else process_tile<P, ITEMS, false, false>(a, t, dict_keys, acc, tid, stride);
+    tiles_done++;
   }
-  if (a.gate == 1 && tid == 0) a.progress[blockIdx.x] = tiles_done;
+  if (YIELD && (tid & 31) == 0) a.progress[blockIdx.x * (AGG_THREADS / 32) + (tid >> 5)] = tiles_done;
   __syncthreads();
   dict_merge<P>(a, dict_keys, acc, tid, stride);
 }
@@ -778,7 +790,21 @@ __device__ __forceinline__ void process_tile_smem(const AggArgs &a, const TileCt
       }
     }
     if (soff[k] >= 0) hits++;
-    else dst[k] = table_slot(a, key[k], 0);
+  }
+  {   // rows bound for the HBM table: every first probe in flight before the first one is looked at
+    uint64_t home[ITEMS], cur[ITEMS];
+#pragma unroll
+    for (int k = 0; k < ITEMS; k++) {
+      home[k] = 0;
+      cur[k] = 0;
+      if (keep[k] && soff[k] < 0) {
+        home[k] = table_home(a, key[k]);
+        cur[k] = __ldcg(&a.tkeys[home[k]]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < ITEMS; k++)
+      if (keep[k] && soff[k] < 0) dst[k] = table_slot_from(a, key[k], home[k], cur[k]);
   }
   // once the table is full, watch the hit rate: a block that mostly misses stops probing (high cardinality)
   if (!bypass && __shfl_sync(0xffffffffu, vctl[CTL_FILL], 0) >= fill_limit) {
@@ -871,8 +897,9 @@ __global__ void __launch_bounds__(AGGS_THREADS) agg_update_smem_kernel(const __g
   };
   if (a.gate == 2) {   // the tiles the dictionary kernel's blocks left behind (its tile = dict_items / ITEMS of ours)
     const int64_t dtile = (int64_t)AGG_THREADS * a.dict_items;
+    const int w = tid >> 5;
     for (int64_t b = vb; b < a.dict_grid; b += nvb)
-      for (int64_t j = a.progress[b];; j++) {
+      for (int64_t j = a.progress[b * (AGG_THREADS / 32) + w];; j++) {   // this warp's slice of dict block b's tiles j, j+1, ...
         const int64_t base0 = (b + j * a.dict_grid) * dtile;
         if (base0 >= a.n || *(volatile int32_t *)a.flags) break;
         for (int64_t base = base0; base < base0 + dtile && base < a.n; base += TILE) one_tile(base);

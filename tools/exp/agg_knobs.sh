@@ -1,4 +1,4 @@
-export SB_OPBENCH_GROUPS=4,16,1024,4096,65536
+export SB_OPBENCH_GROUPS=1024,65536,1048576,16777216
 for cfg in "A=0"; do
   echo "== $cfg"
   env $cfg timeout 150 python tools/op_bench.py agg 2>&1 | grep '^{' | python -c "
