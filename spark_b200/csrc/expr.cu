@@ -267,6 +267,7 @@ void eval_predicate(const sb_table *in, const sb_expr &pred, uint8_t *mask, cuda
   DevProg p = build_prog(in, pred);
   int64_t n = in->nrows;
   if (n == 0) return;
+  KernelTimer kt("filter_project", st);
   predicate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, n, mask);
   SB_LAUNCH_CHECK();
 }
@@ -282,6 +283,7 @@ Column eval_projection(const sb_table *in, const sb_expr &e, const int64_t *sel,
   SB_REQUIRE(e.out_type != SB_STRING && type_width(e.out_type) > 0, "bad projection result type %d", e.out_type);
   Column r = column_alloc(e.out_type, 0, nout, expr_nullable(in, e), st);
   if (nout == 0) return r;
+  KernelTimer kt("filter_project", st);
   projection_kernel<<<(unsigned)((nout + 255) / 256), 256, 0, st>>>(p, sel, nout, e.out_type, r.data->ptr,
                                                                     r.validity ? (uint32_t *)r.validity->ptr : nullptr);
   SB_LAUNCH_CHECK();

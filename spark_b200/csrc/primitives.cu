@@ -231,6 +231,7 @@ Column gather_column(const Column &c, const int64_t *idx, int64_t nout, bool neg
 }
 
 sb_table *gather_table(const sb_table *in, const int64_t *idx, int64_t nout, bool neg, cudaStream_t st) {
+  KernelTimer kt("gather", st);
   sb_table *t = table_new(nout);
   try {
     t->cols.resize(in->cols.size());
