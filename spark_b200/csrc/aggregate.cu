@@ -823,7 +823,7 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
     {
       const int64_t slots_now = cap + 2;
       slot_ids_buf.reset(new Scratch(slots_now * 8, st));
-      Scratch occ(slots_now + 16, st), f32(slots_now * 4 + 16, st), pos(slots_now * 8 + 16, st);
+      Scratch occ(slots_now + 16, st), f32(compact_tiles(slots_now) * 4 + 16, st), pos(compact_tiles(slots_now) * 8 + 16, st);
       occupied_kernel<<<(unsigned)((slots_now + 255) / 256), 256, 0, st>>>((uint64_t *)tkeys, cap, flags.as<int32_t>(), occ.as<uint8_t>());
       SB_LAUNCH_CHECK();
       compact_mask_async(occ.as<uint8_t>(), slots_now, slot_ids_buf->as<int64_t>(), f32.as<int32_t>(), pos.as<int64_t>(),

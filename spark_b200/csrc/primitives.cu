@@ -269,38 +269,91 @@ sb_table *gather_table(const sb_table *in, const int64_t *idx, int64_t nout, boo
 }
 
 // ------------------------------------------------------------------------------------ compaction
-__global__ void mask_to_i32_kernel(const uint8_t *__restrict__ mask, int64_t n, int32_t *__restrict__ out) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = mask[i] ? 1 : 0;
-}
-__global__ void compact_write_kernel(const uint8_t *__restrict__ mask, const int64_t *__restrict__ pos, int64_t n,
-                                     int64_t *__restrict__ out) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n && mask[i]) out[pos[i]] = i;
+// Two passes over the mask (1 B/row each) instead of mask -> int32 flags -> scan -> int64 positions -> write (25 B/row):
+// pass 1 counts the survivors of every 4096-row tile, a tiny scan turns the counts into tile offsets, pass 2 re-reads the
+// tile, ranks the survivors inside the block (thread-local count, warp shuffle scan, 8 warp totals) and writes their row ids.
+constexpr int CM_THREADS = 256;
+constexpr int CM_ITEMS = 16;                       // consecutive rows per thread: one 16-byte load
+constexpr int CM_TILE = CM_THREADS * CM_ITEMS;     // 4096 rows
+
+__device__ __forceinline__ uint32_t cm_load_bits(const uint8_t *__restrict__ mask, int64_t row0, int64_t n, bool aligned) {
+  uint32_t bits = 0;
+  if (aligned && row0 + CM_ITEMS <= n) {
+    const uint4 v = *reinterpret_cast<const uint4 *>(mask + row0);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+      for (int b = 0; b < 4; b++) bits |= ((w[j] >> (8 * b)) & 0xFFu) ? 1u << (4 * j + b) : 0u;
+  } else {
+#pragma unroll
+    for (int j = 0; j < CM_ITEMS; j++)
+      if (row0 + j < n && mask[row0 + j]) bits |= 1u << j;
+  }
+  return bits;
 }
 
-void compact_mask_async(const uint8_t *mask, int64_t n, int64_t *out_idx, int32_t *flags, int64_t *pos, int64_t *total_dev, cudaStream_t st) {
+__global__ void __launch_bounds__(CM_THREADS) compact_count_kernel(const uint8_t *__restrict__ mask, int64_t n, bool aligned,
+                                                                   int32_t *__restrict__ tile_counts) {
+  __shared__ int32_t wsum[CM_THREADS / 32];
+  const int64_t row0 = (int64_t)blockIdx.x * CM_TILE + (int64_t)threadIdx.x * CM_ITEMS;
+  int32_t c = __popc(cm_load_bits(mask, row0, n, aligned));
+  c = __reduce_add_sync(0xffffffffu, c);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int32_t t = 0;
+#pragma unroll
+    for (int w = 0; w < CM_THREADS / 32; w++) t += wsum[w];
+    tile_counts[blockIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(CM_THREADS) compact_write_kernel(const uint8_t *__restrict__ mask, int64_t n, bool aligned,
+                                                                   const int64_t *__restrict__ tile_offsets, int64_t *__restrict__ out) {
+  __shared__ int32_t wsum[CM_THREADS / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t row0 = (int64_t)blockIdx.x * CM_TILE + (int64_t)threadIdx.x * CM_ITEMS;
+  uint32_t bits = cm_load_bits(mask, row0, n, aligned);
+  const int32_t c = __popc(bits);
+  int32_t x = c;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int32_t y = __shfl_up_sync(0xffffffffu, x, d);
+    if (lane >= d) x += y;
+  }
+  if (lane == 31) wsum[warp] = x;
+  __syncthreads();
+  int32_t woff = 0;
+  for (int w = 0; w < warp; w++) woff += wsum[w];
+  int64_t *dst = out + tile_offsets[blockIdx.x] + woff + (x - c);
+  while (bits) {
+    const int j = __ffs(bits) - 1;
+    bits &= bits - 1;
+    *dst++ = row0 + j;
+  }
+}
+
+void compact_mask_async(const uint8_t *mask, int64_t n, int64_t *out_idx, int32_t *tile_counts, int64_t *tile_offsets, int64_t *total_dev,
+                        cudaStream_t st) {
   if (n == 0) {
     SB_CUDA(cudaMemsetAsync(total_dev, 0, 8, st));
     return;
   }
-  unsigned nb = (unsigned)((n + 255) / 256);
-  mask_to_i32_kernel<<<nb, 256, 0, st>>>(mask, n, flags);
+  const unsigned nb = (unsigned)compact_tiles(n);
+  const bool aligned = ((uintptr_t)mask & 15) == 0;
+  compact_count_kernel<<<nb, CM_THREADS, 0, st>>>(mask, n, aligned, tile_counts);
   SB_LAUNCH_CHECK();
-  exclusive_scan_i32_to_i64(flags, pos, n, total_dev, st);
-  compact_write_kernel<<<nb, 256, 0, st>>>(mask, pos, n, out_idx);
+  exclusive_scan_i32_to_i64(tile_counts, tile_offsets, nb, total_dev, st);
+  compact_write_kernel<<<nb, CM_THREADS, 0, st>>>(mask, n, aligned, tile_offsets, out_idx);
   SB_LAUNCH_CHECK();
 }
 
 int64_t compact_mask(const uint8_t *mask, int64_t n, int64_t *out_idx, cudaStream_t st) {
   if (n == 0) return 0;
-  Scratch flags(n * 4, st), pos(n * 8, st), total(8, st);
-  unsigned nb = (unsigned)((n + 255) / 256);
-  mask_to_i32_kernel<<<nb, 256, 0, st>>>(mask, n, flags.as<int32_t>());
-  SB_LAUNCH_CHECK();
-  exclusive_scan_i32_to_i64(flags.as<int32_t>(), pos.as<int64_t>(), n, total.as<int64_t>(), st);
-  compact_write_kernel<<<nb, 256, 0, st>>>(mask, pos.as<int64_t>(), n, out_idx);
-  SB_LAUNCH_CHECK();
+  const int64_t nb = compact_tiles(n);
+  Scratch counts(nb * 4 + 16, st), offsets(nb * 8 + 16, st), total(8, st);
+  compact_mask_async(mask, n, out_idx, counts.as<int32_t>(), offsets.as<int64_t>(), total.as<int64_t>(), st);
   int64_t cnt = 0;
   SB_CUDA(cudaMemcpyAsync(&cnt, total.ptr, 8, cudaMemcpyDeviceToHost, st));
   SB_CUDA(cudaStreamSynchronize(st));

@@ -20,9 +20,11 @@ Column gather_column(const Column &c, const int64_t *idx_dev, int64_t nout, bool
 // indices of rows whose mask byte is non-zero, in row order; returns count (synchronizes the stream)
 int64_t compact_mask(const uint8_t *mask_dev, int64_t n, int64_t *out_idx_dev, cudaStream_t st);
 
-// same without the host round trip: the count lands in *total_dev (device); scratch buffers come from the caller
-void compact_mask_async(const uint8_t *mask_dev, int64_t n, int64_t *out_idx_dev, int32_t *flags_scratch, int64_t *pos_scratch,
-                        int64_t *total_dev, cudaStream_t st);
+// same without the host round trip: the count lands in *total_dev (device); the caller provides the per-tile scratch
+// (compact_tiles(n) int32 counts and as many int64 offsets)
+inline int64_t compact_tiles(int64_t n) { return (n + 4095) / 4096; }
+void compact_mask_async(const uint8_t *mask_dev, int64_t n, int64_t *out_idx_dev, int32_t *tile_counts_scratch,
+                        int64_t *tile_offsets_scratch, int64_t *total_dev, cudaStream_t st);
 
 // validity bitmap <-> one byte per row (bitmaps cannot be sliced or concatenated at arbitrary row offsets)
 void bitmap_to_bytes(const uint8_t *bitmap_dev, int64_t n, uint8_t *out_dev, cudaStream_t st);   // bitmap == nullptr -> all ones

@@ -79,9 +79,15 @@ class ProjectExec(SparkPlan):
         self.children = (child,)
 
     def executeColumnar(self, stream=None):
-        inp = self.child.executeColumnar(stream)
+        # Project over Filter is one stage in the reference (whole-stage codegen fuses them, WholeStageCodegenExec.scala);
+        # here it is one native call: only the projected columns of the surviving rows are ever materialised
+        cond = None
+        child = self.child
+        if isinstance(child, FilterExec):
+            cond, child = child.condition, child.child
+        inp = child.executeColumnar(stream)
         try:
-            return _filter_project(inp, None, self.projectList, stream)
+            return _filter_project(inp, cond, self.projectList, stream)
         finally:
             inp.close()
 
