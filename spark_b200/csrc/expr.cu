@@ -8,6 +8,7 @@
 //
 // This is the general path: one pass per expression, results materialised as columns.  Hot fused
 // shapes (TPC-H stages) bypass it -- see aggregate.cu.
+#include <vector>
 #include "expr.cuh"
 #include "primitives.cuh"
 
@@ -263,11 +264,175 @@ __global__ void __launch_bounds__(256) projection_kernel(DevProg p, const int64_
   }
 }
 
+// ---- fast path: conjunctions of column-vs-literal comparisons (most pushed-down filters: Q1, Q3, Q5, Q6 ...) ----------------
+// Same semantics as the interpreter (a comparison with NULL is NULL, a row survives only if every term is TRUE; doubles compare
+// like SQLOrderingUtil.compareDoubles), but typed, vectorised and without the per-row program walk: a thread evaluates 16
+// consecutive rows from 16-byte loads and stores its 16 mask bytes with one 16-byte store.
+constexpr int SP_MAX_TERMS = 4;
+constexpr int SP_ROWS = 16;
+enum SpOp { SP_EQ = 0, SP_NE, SP_LT, SP_LE, SP_GT, SP_GE, SP_NOTNULL };
+struct SimplePred {
+  int32_t nterms;
+  int32_t type[SP_MAX_TERMS], op[SP_MAX_TERMS], f64[SP_MAX_TERMS];
+  const void *data[SP_MAX_TERMS];
+  const uint8_t *valid[SP_MAX_TERMS];
+  int64_t lit[SP_MAX_TERMS];   // int64 value or double bits
+};
+
+static bool match_simple_predicate(const sb_table *in, const sb_expr &e, SimplePred &sp) {
+  struct Item { int kind; int col; int64_t li; double ld; bool is_f; };   // kind: 0 column, 1 literal, 2 term set
+  std::vector<Item> stk;
+  sp.nterms = 0;
+  auto add_term = [&](const Column &c, int op, int f64, int64_t lit) {
+    if (sp.nterms >= SP_MAX_TERMS || c.type == SB_STRING) return false;
+    const int i = sp.nterms++;
+    sp.type[i] = c.type; sp.op[i] = op; sp.f64[i] = f64; sp.data[i] = c.d(); sp.valid[i] = c.v(); sp.lit[i] = lit;
+    return true;
+  };
+  for (int i = 0; i < e.n; i++) {
+    const sb_expr_node &nd = e.nodes[i];
+    if (nd.op == SB_OP_COL) { stk.push_back({0, nd.arg, 0, 0.0, false}); continue; }
+    if (nd.op == SB_OP_LIT_I64) { stk.push_back({1, 0, nd.lit.i, (double)nd.lit.i, false}); continue; }
+    if (nd.op == SB_OP_LIT_F64) { stk.push_back({1, 0, 0, nd.lit.d, true}); continue; }
+    if (nd.op == SB_OP_ISNOTNULL) {
+      if (stk.empty() || stk.back().kind != 0) return false;
+      const Column &c = in->cols[stk.back().col];
+      stk.pop_back();
+      if (!add_term(c, SP_NOTNULL, 0, 0)) return false;
+      stk.push_back({2, 0, 0, 0.0, false});
+      continue;
+    }
+    if (nd.op == SB_OP_AND) {
+      if (stk.size() < 2 || stk.back().kind != 2 || stk[stk.size() - 2].kind != 2) return false;
+      stk.pop_back();
+      continue;
+    }
+    if (nd.op >= SB_OP_EQ && nd.op <= SB_OP_GE) {
+      if (stk.size() < 2) return false;
+      Item r = stk.back(); stk.pop_back();
+      Item l = stk.back(); stk.pop_back();
+      int op = nd.op - SB_OP_EQ;
+      if (l.kind == 1 && r.kind == 0) {   // lit cmp col -> col cmp' lit
+        std::swap(l, r);
+        static const int flip[6] = {SP_EQ, SP_NE, SP_GT, SP_GE, SP_LT, SP_LE};
+        op = flip[op];
+      }
+      if (l.kind != 0 || r.kind != 1) return false;
+      const Column &c = in->cols[l.col];
+      if (nd.arg == SB_VT_F64) {
+        if (c.type != SB_FLOAT64 && c.type != SB_FLOAT32) return false;
+        int64_t bits;
+        memcpy(&bits, &r.ld, 8);
+        if (!add_term(c, op, 1, bits)) return false;
+      } else {
+        if (c.type == SB_FLOAT64 || c.type == SB_FLOAT32 || r.is_f) return false;
+        if (!add_term(c, op, 0, r.li)) return false;
+      }
+      stk.push_back({2, 0, 0, 0.0, false});
+      continue;
+    }
+    return false;
+  }
+  return stk.size() == 1 && stk.back().kind == 2 && sp.nterms >= 1;
+}
+
+template <typename T>
+__device__ __forceinline__ void sp_load16(const void *__restrict__ data, int64_t row0, int64_t n, int64_t (&x)[SP_ROWS]) {
+  const T *p = (const T *)data + row0;
+  if (row0 + SP_ROWS <= n && ((uintptr_t)p & 15) == 0) {
+    constexpr int PER = 16 / sizeof(T);
+#pragma unroll
+    for (int v = 0; v < SP_ROWS / PER; v++) {
+      const uint4 q = __ldg(reinterpret_cast<const uint4 *>(p) + v);
+      T tmp[PER];
+      memcpy(tmp, &q, 16);
+#pragma unroll
+      for (int j = 0; j < PER; j++) x[v * PER + j] = (int64_t)tmp[j];
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < SP_ROWS; j++) x[j] = row0 + j < n ? (int64_t)p[j] : 0;
+  }
+}
+
+__global__ void __launch_bounds__(256) simple_predicate_kernel(const __grid_constant__ SimplePred sp, int64_t n, uint8_t *__restrict__ mask) {
+  const int64_t row0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * SP_ROWS;
+  if (row0 >= n) return;
+  uint32_t keep = 0xFFFFu;
+#pragma unroll 1
+  for (int t = 0; t < sp.nterms; t++) {
+    if (sp.valid[t]) {
+      // rows row0..row0+15 start on a byte boundary of the bitmap (row0 is a multiple of 16)
+      const uint8_t *v = sp.valid[t] + (row0 >> 3);
+      uint32_t bits = v[0];
+      if (row0 + 8 < n) bits |= (uint32_t)v[1] << 8;
+      keep &= bits;
+    }
+    const int op = sp.op[t];
+    if (op == SP_NOTNULL) continue;
+    int64_t x[SP_ROWS];
+    switch (sp.type[t]) {
+      case SB_BOOL: sp_load16<uint8_t>(sp.data[t], row0, n, x); break;
+      case SB_INT8: sp_load16<int8_t>(sp.data[t], row0, n, x); break;
+      case SB_INT16: sp_load16<int16_t>(sp.data[t], row0, n, x); break;
+      case SB_INT32: case SB_DATE32: case SB_FLOAT32: sp_load16<int32_t>(sp.data[t], row0, n, x); break;
+      default: sp_load16<int64_t>(sp.data[t], row0, n, x); break;
+    }
+    uint32_t lt = 0, eq = 0;
+    if (sp.f64[t]) {
+      const double y = __longlong_as_double(sp.lit[t]);
+      const bool yn = y != y;
+#pragma unroll
+      for (int j = 0; j < SP_ROWS; j++) {   // SQLOrderingUtil.compareDoubles: NaN equals NaN and is larger than anything else
+        const double d = sp.type[t] == SB_FLOAT32 ? (double)__int_as_float((int32_t)x[j]) : __longlong_as_double(x[j]);
+        const bool dn = d != d;
+        const int c = d == y ? 0 : (dn || yn) ? (int)dn - (int)yn : (d < y ? -1 : 1);
+        lt |= (c < 0 ? 1u : 0u) << j;
+        eq |= (c == 0 ? 1u : 0u) << j;
+      }
+    } else {
+      const int64_t lit = sp.lit[t];
+#pragma unroll
+      for (int j = 0; j < SP_ROWS; j++) {
+        lt |= (x[j] < lit ? 1u : 0u) << j;
+        eq |= (x[j] == lit ? 1u : 0u) << j;
+      }
+    }
+    uint32_t ok;
+    switch (op) {
+      case SP_EQ: ok = eq; break;
+      case SP_NE: ok = ~eq; break;
+      case SP_LT: ok = lt; break;
+      case SP_LE: ok = lt | eq; break;
+      case SP_GT: ok = ~(lt | eq); break;
+      default: ok = ~lt; break;
+    }
+    keep &= ok;
+  }
+  if (row0 + SP_ROWS <= n) {   // mask + row0 is 16-byte aligned (scratch allocations are)
+    uint32_t w[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+      w[q] = ((keep >> (4 * q)) & 1u) | (((keep >> (4 * q + 1)) & 1u) << 8) | (((keep >> (4 * q + 2)) & 1u) << 16) | (((keep >> (4 * q + 3)) & 1u) << 24);
+    *reinterpret_cast<uint4 *>(mask + row0) = make_uint4(w[0], w[1], w[2], w[3]);
+  } else {
+    for (int j = 0; j < SP_ROWS && row0 + j < n; j++) mask[row0 + j] = (keep >> j) & 1u;
+  }
+}
+
 void eval_predicate(const sb_table *in, const sb_expr &pred, uint8_t *mask, cudaStream_t st) {
-  DevProg p = build_prog(in, pred);
   int64_t n = in->nrows;
   if (n == 0) return;
   KernelTimer kt("filter_project", st);
+  SimplePred sp;
+  const bool no_fast = getenv("SB_EXPR_INTERPRET_ONLY") != nullptr;   // parity tests run both paths
+  if (!no_fast && ((uintptr_t)mask & 15) == 0 && match_simple_predicate(in, pred, sp)) {
+    const int64_t threads = (n + SP_ROWS - 1) / SP_ROWS;
+    simple_predicate_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(sp, n, mask);
+    SB_LAUNCH_CHECK();
+    return;
+  }
+  DevProg p = build_prog(in, pred);
   predicate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, n, mask);
   SB_LAUNCH_CHECK();
 }

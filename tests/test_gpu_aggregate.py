@@ -267,3 +267,37 @@ def test_groupby_sum_static_shapes_through_both_tiers(gpu, stream, groups, vtype
     got = HashAggregateExec(["k"], [(Sum(col("v")), "s")], LocalTableScanExec(ColumnarBatch.from_arrow(t, stream))).collect(stream)
     want = O.hash_aggregate(t, ["k"], [("sum", "v", "s")])
     assert_tables_equal(got, want, key_cols=["k"])
+
+
+@pytest.mark.parametrize("interpret_only", [False, True], ids=["typed-fast-path", "interpreter"])
+@pytest.mark.parametrize("n", [1, 15, 16, 17, 4097, 100_003])
+def test_filter_predicates_of_every_type(gpu, stream, n, interpret_only, monkeypatch):
+    """FilterExec (basicPhysicalOperators.scala:245): conjunctions of column-vs-literal comparisons take the typed 16-rows-per-thread
+    kernel, everything else the interpreter; both must keep exactly the oracle's rows (NULL comparisons drop the row, NaN is the
+    largest double and equals itself, literal-on-the-left flips the operator), at sizes around the 16-row vector width."""
+    from spark_b200.execution import FilterExec
+    from spark_b200.expressions import Literal, col
+    if interpret_only:
+        monkeypatch.setenv("SB_EXPR_INTERPRET_ONLY", "1")
+    rng = np.random.default_rng(n)
+    d = rng.standard_normal(n)
+    d[rng.random(n) < 0.1] = np.nan
+    t = pa.table({"i8": pa.array(rng.integers(-5, 5, n).astype(np.int8), mask=rng.random(n) < 0.2),
+                  "i16": pa.array(rng.integers(-300, 300, n).astype(np.int16)),
+                  "i32": pa.array(rng.integers(-10, 10, n).astype(np.int32), mask=rng.random(n) < 0.1),
+                  "i64": pa.array(rng.integers(-2 ** 40, 2 ** 40, n), mask=rng.random(n) < 0.1),
+                  "dt": pa.array(rng.integers(9000, 9100, n).astype(np.int32)).cast(pa.date32()),
+                  "f32": pa.array(rng.standard_normal(n).astype(np.float32), mask=rng.random(n) < 0.1),
+                  "f64": pa.array(d, mask=rng.random(n) < 0.1),
+                  "row": np.arange(n, dtype=np.int64)})
+    conds = [col("i32") >= Literal(-3),
+             (col("i8") < Literal(2)) & (col("i16") != Literal(7)) & col("i64").is_not_null(),
+             (Literal(9050) > col("dt")) & (col("i64") <= Literal(2 ** 39)),
+             (col("f64") > Literal(0.25)) & (col("f32") <= Literal(0.5)),
+             col("f64").eq(Literal(float("nan"))),
+             (col("i32").eq(Literal(0))) & (col("f64") >= Literal(-1.0)) & (col("i8") > Literal(-4)) & (col("dt") >= Literal(9010)),
+             (col("i32") >= Literal(-3)) | (col("i8") < Literal(0))]        # OR: never the fast path
+    for cond in conds:
+        got = _run(lambda scan: FilterExec(cond, scan), t, stream)
+        want = O.filter_table(t, cond.sexpr())
+        assert got.column("row").to_pylist() == want.column("row").to_pylist(), cond.sexpr()
