@@ -10,6 +10,7 @@
 // a copy (e.g. the one bundled with PyTorch) shares it; the unique id travels host-side (driver plugin
 // in Spark, torch.distributed/gloo in the tests).
 #include <dlfcn.h>
+#include <algorithm>
 #include <nccl.h>
 #include "common.cuh"
 #include "primitives.cuh"
@@ -78,6 +79,111 @@ static inline int32_t part_lo(int32_t r, int32_t nparts, int32_t nranks) {
   return (int32_t)(((int64_t)r * nparts + nranks - 1) / nranks);
 }
 
+// ---- peer windows: the exchange's data path over NVLink / NVSwitch ---------------------------------------------------------------
+// NCCL send/recv moves unregistered buffers through its staging FIFOs (measured here: 124 GB/s per direction between two B200s
+// with 32 channels).  The buckets are large contiguous slices, so the copy engines can push them straight into the destination
+// GPU's memory: every rank owns one receive WINDOW (cudaMalloc + CUDA IPC, mapped once by every peer), a sender writes each
+// destination's slice of every column at the offset the receiver's layout dictates (all ranks know all counts, so all layouts
+// are computed locally), and NCCL is only the control plane: the counts all-gather that opens an exchange doubles as "every
+// rank is done with the previous window", a one-word all-gather after the pushes as "every push has landed".
+struct PeerWindow {
+  void *local = nullptr;
+  size_t bytes = 0;
+  std::vector<void *> remote;   // remote[r]: rank r's window mapped into this process (nullptr for self)
+  std::vector<cudaStream_t> push_streams;
+  cudaEvent_t ev_ready = nullptr;
+  std::vector<cudaEvent_t> ev_pushed;
+  bool disabled = false;        // IPC not available in this environment: the NCCL data path is used
+};
+static PeerWindow &window() {
+  static PeerWindow w;
+  return w;
+}
+
+// collective: an 8-byte all-gather every rank has to join
+static void nccl_barrier(cudaStream_t st) {
+  Comm &c = comm();
+  Scratch a(8, st), b(8 * c.nranks, st);
+  SB_CUDA(cudaMemsetAsync(a.ptr, 0, 8, st));
+  SB_NCCL(nccl().AllGather(a.ptr, b.ptr, 1, ncclInt64, c.comm, st));
+  SB_CUDA(cudaStreamSynchronize(st));
+}
+
+// collective: nobody frees a window a peer still has mapped
+static void window_release(cudaStream_t st) {
+  PeerWindow &w = window();
+  const bool had = w.local != nullptr;
+  for (void *p : w.remote)
+    if (p) cudaIpcCloseMemHandle(p);
+  w.remote.clear();
+  if (had && comm().comm) nccl_barrier(st);
+  if (w.local) cudaFree(w.local);
+  w.local = nullptr;
+  w.bytes = 0;
+}
+
+// Collective: every rank calls it with the same `need` (derived from the all-gathered counts).  Returns false when the peer
+// path is unavailable on ANY rank (decided collectively, so all ranks take the same branch).
+static bool window_ensure(size_t need, cudaStream_t st) {
+  PeerWindow &w = window();
+  Comm &c = comm();
+  if (w.disabled) return false;
+  if (w.bytes >= need && !w.remote.empty()) return true;
+  const int R = c.nranks;
+  SB_CUDA(cudaStreamSynchronize(st));
+  window_release(st);
+  size_t want = need + need / 2 + (64u << 20);
+  want = (want + (2u << 20) - 1) / (2u << 20) * (2u << 20);
+  struct Msg { cudaIpcMemHandle_t h; int64_t ok; };
+  Msg mine;
+  memset(&mine, 0, sizeof(mine));
+  mine.ok = cudaMalloc(&w.local, want) == cudaSuccess && cudaIpcGetMemHandle(&mine.h, w.local) == cudaSuccess;
+  if (!mine.ok) cudaGetLastError();
+  std::vector<Msg> all(R);
+  Scratch d_my(sizeof(Msg), st), d_all(sizeof(Msg) * R, st);
+  SB_CUDA(cudaMemcpyAsync(d_my.ptr, &mine, sizeof(Msg), cudaMemcpyHostToDevice, st));
+  SB_NCCL(nccl().AllGather(d_my.ptr, d_all.ptr, sizeof(Msg), ncclUint8, c.comm, st));
+  SB_CUDA(cudaMemcpyAsync(all.data(), d_all.ptr, sizeof(Msg) * R, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaStreamSynchronize(st));
+  int64_t ok = 1;
+  for (int r = 0; r < R; r++) ok &= all[r].ok;
+  w.remote.assign(R, nullptr);
+  if (ok)
+    for (int r = 0; r < R && ok; r++) {
+      if (r == c.rank) continue;
+      if (cudaIpcOpenMemHandle(&w.remote[r], all[r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        w.remote[r] = nullptr;
+        ok = 0;
+      }
+    }
+  // second round: did every rank manage to map every peer?
+  int64_t mapped = ok;
+  std::vector<int64_t> all_mapped(R);
+  Scratch d_m(8, st), d_ma(8 * R, st);
+  SB_CUDA(cudaMemcpyAsync(d_m.ptr, &mapped, 8, cudaMemcpyHostToDevice, st));
+  SB_NCCL(nccl().AllGather(d_m.ptr, d_ma.ptr, 1, ncclInt64, c.comm, st));
+  SB_CUDA(cudaMemcpyAsync(all_mapped.data(), d_ma.ptr, 8 * R, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaStreamSynchronize(st));
+  for (int r = 0; r < R; r++) ok &= all_mapped[r];
+  if (!ok) {
+    window_release(st);
+    w.disabled = true;
+    return false;
+  }
+  w.bytes = want;
+  if (w.push_streams.empty()) {
+    w.push_streams.resize(R, nullptr);
+    w.ev_pushed.resize(R, nullptr);
+    SB_CUDA(cudaEventCreateWithFlags(&w.ev_ready, cudaEventDisableTiming));
+    for (int r = 0; r < R; r++) {
+      SB_CUDA(cudaStreamCreateWithFlags(&w.push_streams[r], cudaStreamNonBlocking));
+      SB_CUDA(cudaEventCreateWithFlags(&w.ev_pushed[r], cudaEventDisableTiming));
+    }
+  }
+  return true;
+}
+
 }  // namespace sb
 
 using namespace sb;
@@ -114,6 +220,8 @@ int sb_comm_destroy(void) {
   Comm &c = comm();
   if (c.comm) {
     cudaDeviceSynchronize();
+    window_release(nullptr);
+    window().disabled = false;
     nccl().CommDestroy(c.comm);
     c.comm = nullptr;
   }
@@ -156,9 +264,12 @@ int sb_all_to_all(const sb_table *in, const int64_t *part_offsets_host, int32_t 
   std::vector<int64_t> my_counts(P), all_counts((size_t)R * P);
   for (int p = 0; p < P; p++) my_counts[p] = part_offsets_host[p + 1] - part_offsets_host[p];
   Scratch d_my(P * 8, st), d_all((int64_t)R * P * 8, st);
-  SB_CUDA(cudaMemcpyAsync(d_my.ptr, my_counts.data(), (size_t)P * 8, cudaMemcpyHostToDevice, st));
-  SB_NCCL(nccl().AllGather(d_my.ptr, d_all.ptr, (size_t)P, ncclInt64, c.comm, st));
-  SB_CUDA(cudaMemcpyAsync(all_counts.data(), d_all.ptr, (size_t)R * P * 8, cudaMemcpyDeviceToHost, st));
+  {
+    KernelTimer kt("a2a_counts", st);
+    SB_CUDA(cudaMemcpyAsync(d_my.ptr, my_counts.data(), (size_t)P * 8, cudaMemcpyHostToDevice, st));
+    SB_NCCL(nccl().AllGather(d_my.ptr, d_all.ptr, (size_t)P, ncclInt64, c.comm, st));
+    SB_CUDA(cudaMemcpyAsync(all_counts.data(), d_all.ptr, (size_t)R * P * 8, cudaMemcpyDeviceToHost, st));
+  }
   SB_CUDA(cudaStreamSynchronize(st));
   // 2. layout of what this rank receives: [source rank][owned partitions]
   const int lo = part_lo(c.rank, P, R), hi = part_lo(c.rank + 1, P, R);
@@ -183,23 +294,143 @@ int sb_all_to_all(const sb_table *in, const int64_t *part_offsets_host, int32_t 
       for (int src = 0; src < R; src++) rows += all_counts[(size_t)src * P + p];
     out_part_offsets_host[p + 1] = out_part_offsets_host[p] + rows;
   }
-  // 3. one grouped send/recv per (column buffer, peer)
+  // 3. data path.  Window layout of a receiver d: the columns one after the other (256-byte aligned), each laid out like the
+  //    output column ([source rank][owned partitions]); a nullable column is followed by its validity as one byte per row.
+  bool has_string = false;
+  for (auto &col : in->cols) has_string |= col.type == SB_STRING;
+  auto recv_total_of = [&](int d) {
+    int64_t rows = 0;
+    const int dl = part_lo(d, P, R), dh = part_lo(d + 1, P, R);
+    for (int src = 0; src < R; src++)
+      for (int p = dl; p < dh; p++) rows += all_counts[(size_t)src * P + p];
+    return rows;
+  };
+  auto recv_off_of = [&](int d, int src_rank) {   // first row of src_rank's segment in d's columns
+    int64_t rows = 0;
+    const int dl = part_lo(d, P, R), dh = part_lo(d + 1, P, R);
+    for (int sr = 0; sr < src_rank; sr++)
+      for (int p = dl; p < dh; p++) rows += all_counts[(size_t)sr * P + p];
+    return rows;
+  };
+  auto window_layout = [&](int64_t rows, std::vector<size_t> &col_off, std::vector<size_t> &val_off) {
+    size_t cur = 0;
+    col_off.assign(in->cols.size(), 0);
+    val_off.assign(in->cols.size(), 0);
+    for (size_t ci = 0; ci < in->cols.size(); ci++) {
+      col_off[ci] = cur;
+      cur += ((size_t)rows * type_width(in->cols[ci].type) + 255) / 256 * 256;
+      if (in->cols[ci].validity) {
+        val_off[ci] = cur;
+        cur += ((size_t)rows + 255) / 256 * 256;
+      }
+    }
+    return cur;
+  };
+  static const bool force_nccl = [] { const char *e = getenv("SB_EXCHANGE"); return e && !strcmp(e, "nccl"); }();
+  bool peer_path = !force_nccl && !has_string;
+  if (peer_path) {
+    size_t need = 0;
+    std::vector<size_t> co, vo;
+    for (int d = 0; d < R; d++) need = std::max(need, window_layout(recv_total_of(d), co, vo));
+    peer_path = window_ensure(need, st);
+  }
+  if (peer_path) {
+    PeerWindow &w = window();
+    sb_table *t = table_new(nrecv);
+    try {
+      KernelTimer kt_transfer("a2a_transfer", st);
+      const int me = c.rank;
+      std::vector<Scratch *> temps;
+      std::vector<uint8_t *> send_bytes(in->cols.size(), nullptr);
+      t->cols.reserve(in->cols.size());
+      for (size_t ci = 0; ci < in->cols.size(); ci++) {
+        const Column &col = in->cols[ci];
+        t->cols.push_back(column_alloc(col.type, col.scale, nrecv, col.validity != nullptr, st));
+        if (col.validity) {
+          Scratch *sb = new Scratch(in->nrows + 16, st);
+          temps.push_back(sb);
+          bitmap_to_bytes(col.v(), in->nrows, sb->as<uint8_t>(), st);
+          send_bytes[ci] = sb->as<uint8_t>();
+        }
+      }
+      SB_CUDA(cudaEventRecord(w.ev_ready, st));
+      // pushes: one stream per destination so every NVLink direction is busy at once
+      for (int d = 0; d < R; d++) {
+        if (send_rows[d] == 0) continue;
+        cudaStream_t ps = w.push_streams[d];
+        SB_CUDA(cudaStreamWaitEvent(ps, w.ev_ready, 0));
+        std::vector<size_t> co, vo;
+        window_layout(recv_total_of(d), co, vo);
+        const int64_t roff = recv_off_of(d, me);
+        for (size_t ci = 0; ci < in->cols.size(); ci++) {
+          const Column &col = in->cols[ci];
+          const int wd = type_width(col.type);
+          char *dst_base = d == me ? (char *)t->cols[ci].data->ptr : (char *)w.remote[d] + co[ci];
+          SB_CUDA(cudaMemcpyAsync(dst_base + roff * wd, (const char *)col.d() + send_off[d] * wd, (size_t)(send_rows[d] * wd),
+                                  cudaMemcpyDeviceToDevice, ps));
+          if (col.validity && d != me)
+            SB_CUDA(cudaMemcpyAsync((char *)w.remote[d] + vo[ci] + roff, send_bytes[ci] + send_off[d], (size_t)send_rows[d],
+                                    cudaMemcpyDeviceToDevice, ps));
+        }
+        SB_CUDA(cudaEventRecord(w.ev_pushed[d], ps));
+        SB_CUDA(cudaStreamWaitEvent(st, w.ev_pushed[d], 0));
+      }
+      // "every push has landed": a one-word all-gather ordered after this rank's pushes on st
+      {
+        Scratch d_one(8, st), d_allone(8 * R, st);
+        SB_CUDA(cudaMemsetAsync(d_one.ptr, 0, 8, st));
+        SB_NCCL(nccl().AllGather(d_one.ptr, d_allone.ptr, 1, ncclInt64, c.comm, st));
+        count_launch();
+        // copy out of the window (everything except this rank's own segment, which went straight to the columns)
+        std::vector<size_t> co, vo;
+        window_layout(nrecv, co, vo);
+        std::vector<Scratch *> vbytes;
+        for (size_t ci = 0; ci < in->cols.size(); ci++) {
+          const Column &col = in->cols[ci];
+          const int wd = type_width(col.type);
+          char *outp = (char *)t->cols[ci].data->ptr;
+          const char *win = (const char *)w.local + co[ci];
+          const int64_t a0 = recv_off[me], a1 = recv_off[me + 1];
+          if (a0 > 0) SB_CUDA(cudaMemcpyAsync(outp, win, (size_t)(a0 * wd), cudaMemcpyDeviceToDevice, st));
+          if (nrecv > a1) SB_CUDA(cudaMemcpyAsync(outp + a1 * wd, win + a1 * wd, (size_t)((nrecv - a1) * wd), cudaMemcpyDeviceToDevice, st));
+          if (col.validity) {
+            // own rows' validity bytes join the others in the window, then the whole column is re-packed into a bitmap
+            uint8_t *vwin = (uint8_t *)w.local + vo[ci];
+            if (a1 > a0) SB_CUDA(cudaMemcpyAsync(vwin + a0, send_bytes[ci] + send_off[me], (size_t)(a1 - a0), cudaMemcpyDeviceToDevice, st));
+            bytes_to_bitmap(vwin, nrecv, (uint32_t *)t->cols[ci].validity->ptr, st);
+          }
+        }
+        SB_CUDA(cudaStreamSynchronize(st));
+      }
+      for (auto *x : temps) delete x;
+    } catch (...) {
+      table_free(t);
+      throw;
+    }
+    *out = t;
+    return SB_OK;
+  }
+  // NCCL data path (string-free tables only as well; used when CUDA IPC is unavailable or SB_EXCHANGE=nccl):
+  // one grouped send/recv per (column buffer, peer)
   sb_table *t = table_new(nrecv);
   try {
     std::vector<Scratch *> temps;
     struct Pending { Column *col; uint8_t *recv_bytes; };
     std::vector<Pending> pend;
+    std::vector<std::pair<const uint8_t *, uint8_t *>> self_valid;   // (send bytes, recv bytes) of every nullable column
     t->cols.reserve(in->cols.size());
     for (auto &col : in->cols) {
       if (col.type == SB_STRING) fail(SB_ERR_UNSUPPORTED, "all-to-all of string columns is not implemented (dictionary-encode them)");
       t->cols.push_back(column_alloc(col.type, col.scale, nrecv, col.validity != nullptr, st));
     }
+    KernelTimer kt_transfer("a2a_transfer", st);
     SB_NCCL(nccl().GroupStart());
     for (size_t ci = 0; ci < in->cols.size(); ci++) {
       const Column &src = in->cols[ci];
       Column &dst = t->cols[ci];
       const int w = type_width(src.type);
       for (int peer = 0; peer < R; peer++) {
+        if (peer == c.rank) continue;   // the rank's own partitions never leave HBM (copied below, outside the NCCL group)
         if (send_rows[peer] > 0)
           SB_NCCL(nccl().Send((const char *)src.d() + send_off[peer] * w, (size_t)(send_rows[peer] * w), ncclUint8, peer, c.comm, st));
         if (recv_rows[peer] > 0)
@@ -211,14 +442,40 @@ int sb_all_to_all(const sb_table *in, const int64_t *part_offsets_host, int32_t 
         temps.push_back(rb);
         bitmap_to_bytes(src.v(), in->nrows, sb->as<uint8_t>(), st);
         for (int peer = 0; peer < R; peer++) {
+          if (peer == c.rank) continue;
           if (send_rows[peer] > 0) SB_NCCL(nccl().Send(sb->as<uint8_t>() + send_off[peer], (size_t)send_rows[peer], ncclUint8, peer, c.comm, st));
           if (recv_rows[peer] > 0) SB_NCCL(nccl().Recv(rb->as<uint8_t>() + recv_off[peer], (size_t)recv_rows[peer], ncclUint8, peer, c.comm, st));
         }
         pend.push_back({&dst, rb->as<uint8_t>()});
+        self_valid.push_back({sb->as<uint8_t>(), rb->as<uint8_t>()});
       }
     }
+    static cudaStream_t self_st = nullptr;
+    static cudaEvent_t ev_begin = nullptr, ev_done = nullptr;
+    if (!self_st) {
+      SB_CUDA(cudaStreamCreateWithFlags(&self_st, cudaStreamNonBlocking));
+      SB_CUDA(cudaEventCreateWithFlags(&ev_begin, cudaEventDisableTiming));
+      SB_CUDA(cudaEventCreateWithFlags(&ev_done, cudaEventDisableTiming));
+    }
+    SB_CUDA(cudaEventRecord(ev_begin, st));   // inputs and byte-expanded validity are ready here; the NCCL kernel is enqueued by GroupEnd
     SB_NCCL(nccl().GroupEnd());
     count_launch();   // the grouped NCCL kernel
+    // own partitions: plain device-to-device copies, on a second stream so they overlap the NVLink traffic
+    {
+      const int me = c.rank;
+      if (send_rows[me] > 0) {
+        SB_CUDA(cudaStreamWaitEvent(self_st, ev_begin, 0));
+        for (size_t ci = 0; ci < in->cols.size(); ci++) {
+          const int w = type_width(in->cols[ci].type);
+          SB_CUDA(cudaMemcpyAsync((char *)t->cols[ci].data->ptr + recv_off[me] * w, (const char *)in->cols[ci].d() + send_off[me] * w,
+                                  (size_t)(send_rows[me] * w), cudaMemcpyDeviceToDevice, self_st));
+        }
+        for (auto &sv : self_valid)
+          SB_CUDA(cudaMemcpyAsync(sv.second + recv_off[me], sv.first + send_off[me], (size_t)send_rows[me], cudaMemcpyDeviceToDevice, self_st));
+        SB_CUDA(cudaEventRecord(ev_done, self_st));
+        SB_CUDA(cudaStreamWaitEvent(st, ev_done, 0));
+      }
+    }
     for (auto &p : pend) {
       bytes_to_bitmap(p.recv_bytes, nrecv, (uint32_t *)p.col->validity->ptr, st);
     }
