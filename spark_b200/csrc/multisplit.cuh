@@ -7,9 +7,10 @@ namespace sb {
 
 struct PartGeometry {
   int nblocks;
-  int64_t chunk;   // rows per block (multiple of 32)
+  int64_t chunk;   // rows per histogram column (a multisplit tile for nbuckets <= 256)
 };
-PartGeometry part_geometry(int64_t n, int32_t nbuckets);
+// big_tiles: 8192-row tiles (wide rows into many buckets) instead of 4096-row tiles; only meaningful for nbuckets <= 256
+PartGeometry part_geometry(int64_t n, int32_t nbuckets, bool big_tiles = false);
 
 struct SplitCol {
   int width;

@@ -118,12 +118,20 @@ constexpr int SCATTER_MAX_COLS = 16;
 //      (first profile of the direct scatter: 3.5x DRAM traffic amplification, profiles/r01_partition.md);
 //   F  cursor[bucket] += tile total.
 // Stability: positions are assigned in (bucket, row) order at every level, so arrival order is preserved per bucket.
-constexpr int RG_THREADS = 512;
-constexpr int RG_WARPS = RG_THREADS / 32;
-constexpr int RG_ITEMS = 8;
-constexpr int RG_TILE = RG_THREADS * RG_ITEMS;   // 4096 rows
-constexpr int RG_SEG = RG_TILE / RG_WARPS;       // 256 rows per warp
+constexpr int RGL_THREADS = 512;
+constexpr int RGL_WARPS = RGL_THREADS / 32;
+constexpr int RGL_ITEMS = 8;
+constexpr int RGL_TILE = RGL_THREADS * RGL_ITEMS;   // 4096 rows
+constexpr int RGL_SEG = RGL_TILE / RGL_WARPS;       // 256 rows per warp
 constexpr int RG_MAX_NB = 256;
+// The copy-engine kernel below comes in two tile sizes (the tile is also the granularity of the histograms): 512 threads x 4096
+// rows, two blocks per SM -- best when the ranking phases dominate (sort passes, narrow rows, the 64 x 32 two-level split) -- and
+// 1024 threads x 8192 rows, one block per SM -- runs twice as long and half as many sectors shared between tiles, best for wide
+// rows into 100+ buckets (24 M x 74 B into 200: 1.24 -> 1.01 ms; the same tiles cost a sort pass 10 %).
+constexpr int RG_ITEMS = 8;
+constexpr int RG_TILE_SMALL = 512 * RG_ITEMS;
+constexpr int RG_TILE_BIG = 1024 * RG_ITEMS;
+constexpr int RG_SEG = 256;                      // rows per warp
 
 struct RegroupCols {
   int ncols;
@@ -138,48 +146,48 @@ struct RegroupCols {
 // FULLT (tile completely populated) drops every predicate; addresses are base pointers + compile-time offsets.
 template <typename T, bool FULLT>
 __device__ __forceinline__ void regroup_move_column(const void *__restrict__ src, void *__restrict__ dst, int64_t first_row, int tid,
-                                                    const uint32_t (&sp)[RG_ITEMS], const uint32_t (&gdest)[RG_ITEMS], uint32_t amask,
+                                                    const uint32_t (&sp)[RGL_ITEMS], const uint32_t (&gdest)[RGL_ITEMS], uint32_t amask,
                                                     uint32_t gmask, uint64_t *staging) {
   const T *srcp = (const T *)src + first_row;       // row of item 0 for this lane; item `it` is 32 rows further
   T *stg = (T *)staging;
   const T *stg_read = (const T *)staging + tid;
-  T v[RG_ITEMS];
+  T v[RGL_ITEMS];
 #pragma unroll
-  for (int it = 0; it < RG_ITEMS; it++)
+  for (int it = 0; it < RGL_ITEMS; it++)
     if (FULLT || ((amask >> it) & 1)) v[it] = __ldcs(srcp + it * 32);
 #pragma unroll
-  for (int it = 0; it < RG_ITEMS; it++)
+  for (int it = 0; it < RGL_ITEMS; it++)
     if (FULLT || ((amask >> it) & 1)) stg[sp[it]] = v[it];
   __syncthreads();
 #pragma unroll
-  for (int it = 0; it < RG_ITEMS; it++)
-    if (FULLT || ((gmask >> it) & 1)) ((T *)dst)[gdest[it]] = stg_read[it * RG_THREADS];
+  for (int it = 0; it < RGL_ITEMS; it++)
+    if (FULLT || ((gmask >> it) & 1)) ((T *)dst)[gdest[it]] = stg_read[it * RGL_THREADS];
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(RG_THREADS, 2) regroup_kernel(const __grid_constant__ RegroupCols cols, const int32_t *__restrict__ bucket,
+__global__ void __launch_bounds__(RGL_THREADS, 2) regroup_kernel(const __grid_constant__ RegroupCols cols, const int32_t *__restrict__ bucket,
                                                                 const uint32_t *__restrict__ base, int64_t n, int32_t nb, int64_t chunk,
                                                                 int64_t *__restrict__ perm_out) {
-  __shared__ __align__(16) uint64_t staging[RG_TILE];      // 32 KB
-  __shared__ uint8_t sbucket[RG_TILE];                     // bucket of every sorted position (nb <= 256)
-  __shared__ uint16_t wcnt[RG_WARPS][RG_MAX_NB];
+  __shared__ __align__(16) uint64_t staging[RGL_TILE];      // 32 KB
+  __shared__ uint8_t sbucket[RGL_TILE];                     // bucket of every sorted position (nb <= 256)
+  __shared__ uint16_t wcnt[RGL_WARPS][RG_MAX_NB];
   __shared__ uint16_t first[RG_MAX_NB], tcnt[RG_MAX_NB];
   __shared__ uint32_t cursor[RG_MAX_NB];
-  __shared__ uint32_t warp_sums[RG_WARPS];
+  __shared__ uint32_t warp_sums[RGL_WARPS];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t begin = (int64_t)blockIdx.x * chunk;
   const int64_t end = begin + chunk < n ? begin + chunk : n;
-  for (int p = tid; p < nb; p += RG_THREADS) cursor[p] = base[(int64_t)p * gridDim.x + blockIdx.x];
-  for (int64_t tbase = begin; tbase < end; tbase += RG_TILE) {
-    const int tile_n = (int)(end - tbase < RG_TILE ? end - tbase : RG_TILE);
-    const int64_t sbase = tbase + warp * RG_SEG;     // first row of this warp's segment
+  for (int p = tid; p < nb; p += RGL_THREADS) cursor[p] = base[(int64_t)p * gridDim.x + blockIdx.x];
+  for (int64_t tbase = begin; tbase < end; tbase += RGL_TILE) {
+    const int tile_n = (int)(end - tbase < RGL_TILE ? end - tbase : RGL_TILE);
+    const int64_t sbase = tbase + warp * RGL_SEG;     // first row of this warp's segment
     for (int p = lane; p < nb; p += 32) wcnt[warp][p] = 0;
     __syncwarp();
     // ---- A: rank inside the warp's segment --------------------------------------------------------------------------------
-    uint32_t bl[RG_ITEMS];   // low 16 bits: bucket (0xFFFF = no row); high 16 bits: rank in the warp segment, later sorted position
+    uint32_t bl[RGL_ITEMS];   // low 16 bits: bucket (0xFFFF = no row); high 16 bits: rank in the warp segment, later sorted position
 #pragma unroll
-    for (int it = 0; it < RG_ITEMS; it++) {
-      const bool active = warp * RG_SEG + it * 32 + lane < tile_n;
+    for (int it = 0; it < RGL_ITEMS; it++) {
+      const bool active = warp * RGL_SEG + it * 32 + lane < tile_n;
       const int32_t b = active ? __ldcs(bucket + sbase + it * 32 + lane) : -1 - lane;
       const uint32_t grp = __match_any_sync(0xffffffffu, b);
       const uint32_t rank = __popc(grp & lanemask_lt());
@@ -194,10 +202,10 @@ __global__ void __launch_bounds__(RG_THREADS, 2) regroup_kernel(const __grid_con
     }
     __syncthreads();
     // ---- B: per bucket, exclusive prefix over the warps; tile total -------------------------------------------------------
-    for (int p = tid; p < nb; p += RG_THREADS) {
+    for (int p = tid; p < nb; p += RGL_THREADS) {
       uint32_t run = 0;
 #pragma unroll
-      for (int w = 0; w < RG_WARPS; w++) {
+      for (int w = 0; w < RGL_WARPS; w++) {
         uint32_t c = wcnt[w][p];
         wcnt[w][p] = (uint16_t)run;
         run += c;
@@ -222,7 +230,7 @@ __global__ void __launch_bounds__(RG_THREADS, 2) regroup_kernel(const __grid_con
     __syncthreads();
     // ---- D: sorted position of every row; bucket of every sorted position --------------------------------------------------
 #pragma unroll
-    for (int it = 0; it < RG_ITEMS; it++) {
+    for (int it = 0; it < RGL_ITEMS; it++) {
       const uint32_t b = bl[it] & 0xFFFFu;
       if (b != 0xFFFFu) {
         const uint32_t sp = first[b] + wcnt[warp][b] + (bl[it] >> 16);
@@ -231,12 +239,12 @@ __global__ void __launch_bounds__(RG_THREADS, 2) regroup_kernel(const __grid_con
       }
     }
     __syncthreads();
-    uint32_t gdest[RG_ITEMS];    // output row of sorted position j = it * RG_THREADS + tid
-    uint32_t sp[RG_ITEMS];       // sorted position of this thread's rows
+    uint32_t gdest[RGL_ITEMS];    // output row of sorted position j = it * RGL_THREADS + tid
+    uint32_t sp[RGL_ITEMS];       // sorted position of this thread's rows
     uint32_t amask = 0, gmask = 0;
 #pragma unroll
-    for (int it = 0; it < RG_ITEMS; it++) {
-      const int j = it * RG_THREADS + tid;
+    for (int it = 0; it < RGL_ITEMS; it++) {
+      const int j = it * RGL_THREADS + tid;
       if (j < tile_n) {
         const int b = sbucket[j];
         gdest[it] = cursor[b] + (uint32_t)(j - first[b]);
@@ -245,17 +253,17 @@ __global__ void __launch_bounds__(RG_THREADS, 2) regroup_kernel(const __grid_con
       sp[it] = bl[it] >> 16;
       if ((bl[it] & 0xFFFFu) != 0xFFFFu) amask |= 1u << it;
     }
-    const bool fullt = tile_n == RG_TILE;
+    const bool fullt = tile_n == RGL_TILE;
     const int64_t first_row = sbase + lane;
     // ---- E: move the columns -----------------------------------------------------------------------------------------------
     if (perm_out) {   // row ids travel like a column (used to gather variable-width columns afterwards)
 #pragma unroll
-      for (int it = 0; it < RG_ITEMS; it++)
+      for (int it = 0; it < RGL_ITEMS; it++)
         if ((amask >> it) & 1) staging[sp[it]] = (uint64_t)(first_row + it * 32);
       __syncthreads();
 #pragma unroll
-      for (int it = 0; it < RG_ITEMS; it++)
-        if ((gmask >> it) & 1) perm_out[gdest[it]] = (int64_t)staging[it * RG_THREADS + tid];
+      for (int it = 0; it < RGL_ITEMS; it++)
+        if ((gmask >> it) & 1) perm_out[gdest[it]] = (int64_t)staging[it * RGL_THREADS + tid];
       __syncthreads();
     }
 #pragma unroll 1
@@ -265,11 +273,11 @@ __global__ void __launch_bounds__(RG_THREADS, 2) regroup_kernel(const __grid_con
       void *dst = cols.dst[c];
       {   // pull the NEXT column's rows of this tile (or the next tile's bucket ids) towards L2 while this column moves
         const bool last = c + 1 == cols.ncols;
-        const char *nsrc = last ? (const char *)(bucket + RG_TILE) : (const char *)cols.src[c + 1];
+        const char *nsrc = last ? (const char *)(bucket + RGL_TILE) : (const char *)cols.src[c + 1];
         const int nw = last ? 4 : cols.width[c + 1];
-        if (!last || tbase + RG_TILE + RG_TILE <= end) {
+        if (!last || tbase + RGL_TILE + RGL_TILE <= end) {
 #pragma unroll
-          for (int it = 0; it < RG_ITEMS; it++)
+          for (int it = 0; it < RGL_ITEMS; it++)
             asm volatile("prefetch.global.L2 [%0];" ::"l"(nsrc + (first_row + it * 32) * nw));
         }
       }
@@ -286,7 +294,7 @@ __global__ void __launch_bounds__(RG_THREADS, 2) regroup_kernel(const __grid_con
       if (cols.dst_valid[c]) {   // NULLs: clear the destination bit (rare, scattered)
         const uint8_t *sv = cols.src_valid[c];
 #pragma unroll
-        for (int it = 0; it < RG_ITEMS; it++) {
+        for (int it = 0; it < RGL_ITEMS; it++) {
           if (!((amask >> it) & 1)) continue;
           if (!bit_valid(sv, first_row + it * 32)) {
             const uint32_t b = sbucket[sp[it]];
@@ -298,7 +306,7 @@ __global__ void __launch_bounds__(RG_THREADS, 2) regroup_kernel(const __grid_con
     }
     __syncthreads();
     // ---- F: advance the block's cursors ----------------------------------------------------------------------------------------
-    for (int p = tid; p < nb; p += RG_THREADS) cursor[p] += tcnt[p];
+    for (int p = tid; p < nb; p += RGL_THREADS) cursor[p] += tcnt[p];
     __syncthreads();
   }
 }
@@ -313,7 +321,6 @@ __global__ void __launch_bounds__(RG_THREADS, 2) regroup_kernel(const __grid_con
 // and one global store per row and a single __syncthreads() (to hand the stage back), instead of
 // "global load -> shared scatter -> barrier -> shared load -> global store -> barrier" with the load latency exposed.
 constexpr int RGT_STAGES = 3;
-constexpr int RGT_STAGE_BYTES = RG_TILE * 8;   // one 8-byte column tile
 
 template <typename T, bool FULLT>
 __device__ __forceinline__ void regroup_drain_column(const uint8_t *__restrict__ stage, void *__restrict__ dst,
@@ -328,9 +335,13 @@ __device__ __forceinline__ void regroup_drain_column(const uint8_t *__restrict__
     if (FULLT || ((gmask >> it) & 1)) ((T *)dst)[gdest[it]] = v[it];
 }
 
-__global__ void __launch_bounds__(RG_THREADS, 2) regroup_tma_kernel(const __grid_constant__ RegroupCols cols, const int32_t *__restrict__ bucket,
-                                                                    const uint32_t *__restrict__ base, int64_t n, int32_t nb, int64_t ntiles,
-                                                                    int64_t *__restrict__ perm_out, int l2_stream) {
+template <int RG_THREADS>
+__global__ void __launch_bounds__(RG_THREADS, 1024 / RG_THREADS) regroup_tma_kernel(const __grid_constant__ RegroupCols cols, const int32_t *__restrict__ bucket,
+                                                                                 const uint32_t *__restrict__ base, int64_t n, int32_t nb, int64_t ntiles,
+                                                                                 int64_t *__restrict__ perm_out, int l2_stream) {
+  constexpr int RG_WARPS = RG_THREADS / 32, RG_TILE = RG_THREADS * RG_ITEMS;
+  constexpr int RGT_STAGE_BYTES = RG_TILE * 8;   // one 8-byte column tile
+  static_assert(RG_TILE / RG_WARPS == RG_SEG, "a warp ranks 256 rows");
   extern __shared__ __align__(128) uint8_t ring[];          // RGT_STAGES x RGT_STAGE_BYTES
   __shared__ __align__(8) uint64_t bars[RGT_STAGES];
   __shared__ uint32_t readers_done[RGT_STAGES];
@@ -544,21 +555,22 @@ __global__ void __launch_bounds__(RG_THREADS, 2) regroup_tma_kernel(const __grid
 }
 
 // bucket = digit of a partition id for the two-level split; also the per-block histogram in multisplit layout
-__global__ void __launch_bounds__(RG_THREADS) pid_digit_hist_kernel(const int32_t *__restrict__ pid, int64_t n, int32_t div, int32_t mod,
+constexpr int PDH_THREADS = 512;
+__global__ void __launch_bounds__(PDH_THREADS) pid_digit_hist_kernel(const int32_t *__restrict__ pid, int64_t n, int32_t div, int32_t mod,
                                                                     int32_t nb, int64_t chunk, int32_t *__restrict__ bucket,
                                                                     uint32_t *__restrict__ hist) {
   __shared__ uint32_t sh[RG_MAX_NB];
-  for (int p = threadIdx.x; p < nb; p += RG_THREADS) sh[p] = 0;
+  for (int p = threadIdx.x; p < nb; p += PDH_THREADS) sh[p] = 0;
   __syncthreads();
   int64_t begin = (int64_t)blockIdx.x * chunk;
   int64_t end = begin + chunk < n ? begin + chunk : n;
-  for (int64_t i = begin + threadIdx.x; i < end; i += RG_THREADS) {
+  for (int64_t i = begin + threadIdx.x; i < end; i += PDH_THREADS) {
     int b = (pid[i] / div) % mod;
     bucket[i] = b;
     atomicAdd(&sh[b], 1u);
   }
   __syncthreads();
-  for (int p = threadIdx.x; p < nb; p += RG_THREADS) hist[(int64_t)p * gridDim.x + blockIdx.x] = sh[p];
+  for (int p = threadIdx.x; p < nb; p += PDH_THREADS) hist[(int64_t)p * gridDim.x + blockIdx.x] = sh[p];
 }
 
 __global__ void part_offsets_kernel(const uint32_t *__restrict__ base, int32_t nparts, int nblocks, int64_t n,
@@ -583,21 +595,22 @@ static KeyCols make_keys(const sb_table *in, const int32_t *key_cols, int32_t nk
   return k;
 }
 
-PartGeometry part_geometry(int64_t n, int32_t nbuckets) {
+PartGeometry part_geometry(int64_t n, int32_t nbuckets, bool big_tiles) {
   PartGeometry g;
   if (nbuckets <= RG_MAX_NB) {
     // one histogram column per TILE: the scatter deals tiles round-robin to a persistent grid (see regroup_tma_kernel)
-    g.chunk = RG_TILE;
-    int64_t nt = (n + RG_TILE - 1) / RG_TILE;
+    g.chunk = big_tiles ? RG_TILE_BIG : RG_TILE_SMALL;
+    int64_t nt = (n + g.chunk - 1) / g.chunk;
     g.nblocks = (int)(nt < 1 ? 1 : nt);
     return g;
   }
   // above the single-pass fan-out the caller's histogram only provides the bucket boundaries: keep it coarse
-  int64_t want = (n + RG_TILE * 2 - 1) / (RG_TILE * 2);
+  const int64_t T = RG_TILE_SMALL;
+  int64_t want = (n + T * 2 - 1) / (T * 2);
   int maxb = rt().num_sms * 2;
   g.nblocks = (int)(want < 1 ? 1 : (want > maxb ? maxb : want));
-  g.chunk = ((n + g.nblocks - 1) / g.nblocks + RG_TILE - 1) / RG_TILE * RG_TILE;
-  if (g.chunk < RG_TILE) g.chunk = RG_TILE;
+  g.chunk = ((n + g.nblocks - 1) / g.nblocks + T - 1) / T * T;
+  if (g.chunk < T) g.chunk = T;
   g.nblocks = (int)((n + g.chunk - 1) / g.chunk);
   if (g.nblocks < 1) g.nblocks = 1;
   return g;
@@ -611,7 +624,8 @@ static void regroup_pass(const int32_t *bucket_dev, uint32_t *hist_dev, int32_t 
     SB_LAUNCH_CHECK();
   }
   if (n == 0) return;
-  SB_REQUIRE(g.chunk == RG_TILE, "internal: regroup needs a per-tile histogram");
+  SB_REQUIRE(g.chunk == RG_TILE_SMALL || g.chunk == RG_TILE_BIG, "internal: regroup needs a per-tile histogram");
+  const bool big = g.chunk == RG_TILE_BIG;
   int done = 0;
   bool first = true;
   while (first || done < ncols) {
@@ -638,16 +652,22 @@ static void regroup_pass(const int32_t *bucket_dev, uint32_t *hist_dev, int32_t 
       if (aligned && !force_ldst) {
         static std::once_flag once;
         std::call_once(once, [] {
-          SB_CUDA(cudaFuncSetAttribute(regroup_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RGT_STAGES * RGT_STAGE_BYTES));
+          SB_CUDA(cudaFuncSetAttribute(regroup_tma_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, RGT_STAGES * RG_TILE_SMALL * 8));
+          SB_CUDA(cudaFuncSetAttribute(regroup_tma_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, RGT_STAGES * RG_TILE_BIG * 8));
         });
-        static const int bps = [] { const char *e = getenv("SB_RG_BLOCKS_PER_SM"); return e ? atoi(e) : 2; }();
+        static const int bps_env = [] { const char *e = getenv("SB_RG_BLOCKS_PER_SM"); return e ? atoi(e) : 0; }();
         static const int grid_override = [] { const char *e = getenv("SB_RG_GRID"); return e ? atoi(e) : 0; }();
+        const int bps = bps_env > 0 ? bps_env : (big ? 1 : 2);
         int grid = g.nblocks < rt().num_sms * bps ? g.nblocks : rt().num_sms * bps;
         if (grid_override > 0 && grid_override < grid) grid = grid_override;
-        regroup_tma_kernel<<<grid, RG_THREADS, RGT_STAGES * RGT_STAGE_BYTES, st>>>(rc, bucket_dev, hist_dev, n, nb, (int64_t)g.nblocks,
-                                                                                   first ? perm_out : nullptr, l2_stream);
+        if (big)
+          regroup_tma_kernel<1024><<<grid, 1024, RGT_STAGES * RG_TILE_BIG * 8, st>>>(rc, bucket_dev, hist_dev, n, nb, (int64_t)g.nblocks,
+                                                                                  first ? perm_out : nullptr, l2_stream);
+        else
+          regroup_tma_kernel<512><<<grid, 512, RGT_STAGES * RG_TILE_SMALL * 8, st>>>(rc, bucket_dev, hist_dev, n, nb, (int64_t)g.nblocks,
+                                                                                  first ? perm_out : nullptr, l2_stream);
       } else {
-        regroup_kernel<<<g.nblocks, RG_THREADS, 0, st>>>(rc, bucket_dev, hist_dev, n, nb, g.chunk, first ? perm_out : nullptr);
+        regroup_kernel<<<g.nblocks, RGL_THREADS, 0, st>>>(rc, bucket_dev, hist_dev, n, nb, g.chunk, first ? perm_out : nullptr);
       }
       SB_LAUNCH_CHECK();
     }
@@ -669,7 +689,7 @@ void multisplit_scatter(const int32_t *bucket_dev, uint32_t *hist_dev, int32_t n
   // are stable, so the result is ordered by (high, low) = bucket id with arrival order preserved inside a bucket.
   const int32_t B1 = 64, B2 = (nbuckets + B1 - 1) / B1;
   SB_REQUIRE(B2 <= RG_MAX_NB, "too many buckets");
-  const PartGeometry g2 = part_geometry(n, RG_MAX_NB);   // per-tile histograms for the two digit passes
+  const PartGeometry g2 = part_geometry(n, RG_MAX_NB, false);   // per-tile histograms for the two digit passes
   Scratch digit(n * 4 + 16, st), hist2((int64_t)RG_MAX_NB * g2.nblocks * 4 + 16, st), pid_mid(n * 4 + 16, st), perm_mid(perm_out ? n * 8 + 16 : 0, st);
   // intermediate copies of every column (+ validity carried as-is through atomicAnd on a fresh bitmap)
   std::vector<SplitCol> c1(cols, cols + ncols), c2(cols, cols + ncols);
@@ -693,13 +713,13 @@ void multisplit_scatter(const int32_t *bucket_dev, uint32_t *hist_dev, int32_t n
   }
   c1.push_back({4, bucket_dev, pid_mid.ptr, nullptr, nullptr});   // the bucket ids travel with the rows into pass 2
   if (n > 0) {
-    pid_digit_hist_kernel<<<g2.nblocks, RG_THREADS, 0, st>>>(bucket_dev, n, 1, B1, B1, g2.chunk, digit.as<int32_t>(), hist2.as<uint32_t>());
+    pid_digit_hist_kernel<<<g2.nblocks, PDH_THREADS, 0, st>>>(bucket_dev, n, 1, B1, B1, g2.chunk, digit.as<int32_t>(), hist2.as<uint32_t>());
     SB_LAUNCH_CHECK();
   }
   regroup_pass(digit.as<int32_t>(), hist2.as<uint32_t>(), B1, g2, c1.data(), (int)c1.size(), n, perm_out ? perm_mid.as<int64_t>() : nullptr, nullptr, st);
   if (perm_out) c2.push_back({8, perm_mid.ptr, perm_out, nullptr, nullptr});
   if (n > 0) {
-    pid_digit_hist_kernel<<<g2.nblocks, RG_THREADS, 0, st>>>(pid_mid.as<int32_t>(), n, B1, B2, B2, g2.chunk, digit.as<int32_t>(), hist2.as<uint32_t>());
+    pid_digit_hist_kernel<<<g2.nblocks, PDH_THREADS, 0, st>>>(pid_mid.as<int32_t>(), n, B1, B2, B2, g2.chunk, digit.as<int32_t>(), hist2.as<uint32_t>());
     SB_LAUNCH_CHECK();
   }
   regroup_pass(digit.as<int32_t>(), hist2.as<uint32_t>(), B2, g2, c2.data(), (int)c2.size(), n, nullptr, nullptr, st);
@@ -723,7 +743,11 @@ static void partition_impl(const sb_table *in, const int32_t *key_cols, int32_t 
   KeyCols keys;
   keys.n = 0;
   if (mode == 0) keys = make_keys(in, key_cols, nkeys);
-  PartGeometry g = part_geometry(n, nparts);
+  int64_t rowbytes = 0;
+  for (auto &c : in->cols) rowbytes += c.type == SB_STRING ? 8 : type_width(c.type);   // strings travel as row ids
+  static const int tile_env = [] { const char *e = getenv("SB_RG_TILE"); return e ? atoi(e) : 0; }();   // 4096 | 8192 (A/B measurements)
+  const bool big_tiles = tile_env ? tile_env == 8192 : (nparts >= 64 && rowbytes >= 32);
+  PartGeometry g = part_geometry(n, nparts, big_tiles);
   Scratch pid(n * 4 + 16, st);
   Scratch hist((int64_t)nparts * g.nblocks * 4 + 16, st);
   Scratch offs_dev((nparts + 1) * 8, st);
