@@ -103,13 +103,15 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_build_kernel(JoinKeys k, in
 
 // pass 1: matches per streamed row (join-type adjusted) + first matching build row
 __global__ void __launch_bounds__(JOIN_THREADS) join_count_kernel(JoinKeys k, int64_t n, const JoinSlot *__restrict__ slots, int64_t cap,
-                                                                  int join_type, int32_t *__restrict__ counts, uint32_t *__restrict__ first) {
+                                                                  int join_type, int32_t *__restrict__ counts, uint32_t *__restrict__ first,
+                                                                  int32_t *__restrict__ block_counts) {
+  __shared__ int32_t wsum[JOIN_THREADS / 32];
   int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= n) return;
+  const bool in_range = row < n;
   uint64_t key;
   int32_t matches = 0;
   uint32_t f = FREE_SLOT;
-  if (join_key(k, row, key)) {
+  if (in_range && join_key(k, row, key)) {
     uint64_t mask = (uint64_t)cap - 1;
     uint64_t h = join_mix(key) & mask;
     for (;;) {
@@ -124,7 +126,6 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_count_kernel(JoinKeys k, in
       h = (h + 1) & mask;
     }
   }
-  first[row] = f;
   int32_t c;
   switch (join_type) {
     case SB_JOIN_INNER: c = matches; break;
@@ -132,19 +133,45 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_count_kernel(JoinKeys k, in
     case SB_JOIN_LEFT_SEMI: c = matches > 0 ? 1 : 0; break;
     default: c = matches > 0 ? 0 : 1; break;   // anti
   }
-  counts[row] = c;
+  if (!in_range) c = 0;
+  if (in_range) {
+    first[row] = f;
+    counts[row] = c;
+  }
+  // output rows of this block: the scan that turns counts into offsets runs over blocks, not rows (join_fill_kernel redoes
+  // the in-block prefix in shared memory), which saves an 8-byte offset per streamed row and two passes over them
+  int32_t t = __reduce_add_sync(0xffffffffu, c);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int32_t b = 0;
+#pragma unroll
+    for (int w = 0; w < JOIN_THREADS / 32; w++) b += wsum[w];
+    block_counts[blockIdx.x] = b;
+  }
 }
 
 // pass 2: (probe row, build row) pairs at the scanned offsets
 __global__ void __launch_bounds__(JOIN_THREADS) join_fill_kernel(JoinKeys k, int64_t n, const JoinSlot *__restrict__ slots, int64_t cap,
-                                                                 int join_type, const int32_t *__restrict__ counts, const int64_t *__restrict__ offsets,
-                                                                 const uint32_t *__restrict__ first, int64_t *__restrict__ out_probe,
-                                                                 int64_t *__restrict__ out_build) {
+                                                                 int join_type, const int32_t *__restrict__ counts,
+                                                                 const int64_t *__restrict__ block_offsets, const uint32_t *__restrict__ first,
+                                                                 int64_t *__restrict__ out_probe, int64_t *__restrict__ out_build) {
+  __shared__ int32_t wsum[JOIN_THREADS / 32];
   int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= n) return;
-  int32_t c = counts[row];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int32_t c = row < n ? counts[row] : 0;
+  int32_t x = c;   // inclusive prefix inside the warp
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int32_t y = __shfl_up_sync(0xffffffffu, x, d);
+    if (lane >= d) x += y;
+  }
+  if (lane == 31) wsum[warp] = x;
+  __syncthreads();
+  int32_t woff = 0;
+  for (int w = 0; w < warp; w++) woff += wsum[w];
   if (c == 0) return;
-  int64_t o = offsets[row];
+  int64_t o = block_offsets[blockIdx.x] + woff + (x - c);
   uint32_t f = first[row];
   if (c == 1 || join_type == SB_JOIN_LEFT_SEMI || join_type == SB_JOIN_LEFT_ANTI) {
     out_probe[o] = row;
@@ -259,14 +286,15 @@ int sb_join_probe(const sb_hash_table *ht, const sb_table *probe, const int32_t 
   const int64_t n = probe->nrows;
   JoinKeys k = make_join_keys(probe, key_cols, nkeys, ht);
   const bool pairs = join_type == SB_JOIN_INNER || join_type == SB_JOIN_LEFT_OUTER;
-  Scratch counts(n * 4 + 16, st), first(n * 4 + 16, st), offsets(n * 8 + 16, st), total(8, st);
   unsigned nb = (unsigned)((n + JOIN_THREADS - 1) / JOIN_THREADS);
+  Scratch counts(n * 4 + 16, st), first(n * 4 + 16, st), block_counts((int64_t)nb * 4 + 16, st), offsets((int64_t)nb * 8 + 16, st), total(8, st);
   if (n > 0) {
     KernelTimer kt("join_probe", st);
-    join_count_kernel<<<nb, JOIN_THREADS, 0, st>>>(k, n, ht->slots, ht->cap, join_type, counts.as<int32_t>(), first.as<uint32_t>());
+    join_count_kernel<<<nb, JOIN_THREADS, 0, st>>>(k, n, ht->slots, ht->cap, join_type, counts.as<int32_t>(), first.as<uint32_t>(),
+                                                   block_counts.as<int32_t>());
     SB_LAUNCH_CHECK();
   }
-  exclusive_scan_i32_to_i64(counts.as<int32_t>(), offsets.as<int64_t>(), n, total.as<int64_t>(), st);
+  exclusive_scan_i32_to_i64(block_counts.as<int32_t>(), offsets.as<int64_t>(), nb, total.as<int64_t>(), st);
   int64_t nout = 0;
   SB_CUDA(cudaMemcpyAsync(&nout, total.ptr, 8, cudaMemcpyDeviceToHost, st));
   SB_CUDA(cudaStreamSynchronize(st));
