@@ -632,25 +632,30 @@ __device__ __forceinline__ void dict_init(const AggArgs &a, uint64_t *dict_keys,
     for (int g = 0; g <= AGG_DICT; g++) acc[(g * ns + s) * AGG_THREADS + tid] = id;
   }
 }
-// merge the block dictionary into the HBM table: one warp per (group, slot) pair, shuffle tree
+// merge the block dictionary into the HBM table: one warp per GROUP -- one find-or-insert for the group, then a shuffle tree
+// and one fire-and-forget RED per slot (a probe per (group, slot) pair made the kernel's tail a chain of L2 round trips)
 template <class P>
 __device__ __forceinline__ void dict_merge(const AggArgs &a, const uint64_t *dict_keys, const uint64_t *acc, int tid, int64_t stride) {
   const PlanMeta &m = P::meta(a);
   const int ns = m.nslots;
   const int lane = tid & 31, warp = tid >> 5, nwarps = AGG_THREADS / 32;
-  for (int gs = warp; gs < AGG_DICT * ns; gs += nwarps) {
-    int g = gs / ns, s = gs % ns;
-    uint64_t key = dict_keys[g];
+  for (int g = warp; g < AGG_DICT; g += nwarps) {
+    const uint64_t key = dict_keys[g];
     if (key == EMPTY_KEY) continue;
-    int kind = m.slot_kind[s];
-    uint64_t v = slot_identity(kind);
-    for (int i = lane; i < AGG_THREADS; i += 32) v = apply_op(kind, v, acc[(size_t)gs * AGG_THREADS + i]);
+    int64_t slot = 0;
+    if (lane == 0) slot = table_slot(a, key, 0);
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    if (slot < 0) continue;
+    plan_for<P>(ns, [&](int s) {
+      const int kind = m.slot_kind[s];
+      const uint64_t *p = acc + (size_t)(g * ns + s) * AGG_THREADS;
+      uint64_t v = slot_identity(kind);
 #pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) v = apply_op(kind, v, __shfl_xor_sync(0xffffffffu, v, d));
-    if (lane == 0) {
-      int64_t slot = table_slot(a, key, 0);
-      if (slot >= 0) global_op(kind, &a.tacc[(int64_t)s * stride + slot], v);
-    }
+      for (int i = 0; i < AGG_THREADS / 32; i++) v = apply_op(kind, v, p[lane + 32 * i]);
+#pragma unroll
+      for (int d = 16; d >= 1; d >>= 1) v = apply_op(kind, v, __shfl_xor_sync(0xffffffffu, v, d));
+      if (lane == 0) global_op(kind, &a.tacc[(int64_t)s * stride + slot], v);
+    });
   }
 }
 

@@ -184,6 +184,46 @@ static bool window_ensure(size_t need, cudaStream_t st) {
   return true;
 }
 
+// ---- small-table all-gather: one fixed-size packed message per rank ------------------------------------------------------------
+// The broadcast of a small relation or of partial-aggregate rows (Q1: 4 rows x 12 columns per rank) is latency, not bandwidth:
+// count exchange + one send/recv per (column, peer) cost ~150 us.  Instead every rank packs [row count | every column padded to
+// AG_PACK_ROWS rows | one validity byte per row and column] into one buffer, ONE ncclAllGather moves it, and one kernel unpacks.
+// The protocol is optimistic and deterministic: all ranks read all headers; if any rank had more rows than fit, all of them take
+// the general path afterwards.
+constexpr int64_t AG_PACK_ROWS = 256;
+constexpr int AG_MAX_COLS = 64;
+struct AgPackArgs {
+  int32_t ncols, nranks;
+  int64_t my_rows, stride;                  // bytes per rank message
+  const void *src[AG_MAX_COLS];             // pack: this rank's columns
+  const uint8_t *src_valid[AG_MAX_COLS];
+  void *dst[AG_MAX_COLS];                   // unpack: output columns
+  uint8_t *dst_valid_bytes[AG_MAX_COLS];    // unpack: one byte per output row (nullable columns) or nullptr
+  int32_t width[AG_MAX_COLS];
+  int64_t data_off[AG_MAX_COLS], valid_off[AG_MAX_COLS];
+  int64_t rows[16], off[16];                // unpack: rows of every rank and their first output row (nranks <= 16)
+};
+__global__ void ag_pack_kernel(const __grid_constant__ AgPackArgs a, uint8_t *__restrict__ msg) {
+  const int c = blockIdx.x;
+  if (c == a.ncols) {
+    if (threadIdx.x == 0) *(int64_t *)msg = a.my_rows;
+    return;
+  }
+  const int64_t rows = a.my_rows < AG_PACK_ROWS ? a.my_rows : AG_PACK_ROWS;
+  const int64_t bytes = rows * a.width[c];
+  for (int64_t i = threadIdx.x; i < bytes; i += blockDim.x) msg[a.data_off[c] + i] = ((const uint8_t *)a.src[c])[i];
+  for (int64_t i = threadIdx.x; i < rows; i += blockDim.x) msg[a.valid_off[c] + i] = bit_valid(a.src_valid[c], i) ? 1 : 0;
+}
+__global__ void ag_unpack_kernel(const __grid_constant__ AgPackArgs a, const uint8_t *__restrict__ all) {
+  const int c = blockIdx.x, r = blockIdx.y;
+  const uint8_t *msg = all + (int64_t)r * a.stride;
+  const int64_t bytes = a.rows[r] * a.width[c];
+  uint8_t *out = (uint8_t *)a.dst[c] + a.off[r] * a.width[c];
+  for (int64_t i = threadIdx.x; i < bytes; i += blockDim.x) out[i] = msg[a.data_off[c] + i];
+  if (a.dst_valid_bytes[c])
+    for (int64_t i = threadIdx.x; i < a.rows[r]; i += blockDim.x) a.dst_valid_bytes[c][a.off[r] + i] = msg[a.valid_off[c] + i];
+}
+
 }  // namespace sb
 
 using namespace sb;
@@ -503,6 +543,74 @@ int sb_all_gather(const sb_table *in, sb_stream *s, sb_table **out) {
   }
   const int R = c.nranks;
   int64_t my = in->nrows;
+  // ---- optimistic packed path (see ag_pack_kernel) ----
+  bool packable = R <= 16 && (int)in->cols.size() <= AG_MAX_COLS;
+  for (auto &col : in->cols) packable = packable && col.type != SB_STRING;
+  if (packable) {
+    AgPackArgs a;
+    memset(&a, 0, sizeof(a));
+    a.ncols = (int)in->cols.size();
+    a.nranks = R;
+    a.my_rows = my;
+    int64_t cur = 16;
+    for (int ci = 0; ci < a.ncols; ci++) {
+      const Column &col = in->cols[ci];
+      a.width[ci] = type_width(col.type);
+      a.src[ci] = col.d();
+      a.src_valid[ci] = col.v();
+      a.data_off[ci] = cur;
+      cur += (AG_PACK_ROWS * a.width[ci] + 15) / 16 * 16;
+      a.valid_off[ci] = cur;
+      cur += AG_PACK_ROWS;
+    }
+    a.stride = (cur + 255) / 256 * 256;
+    Scratch msg(a.stride, st), all(a.stride * R, st);
+    ag_pack_kernel<<<a.ncols + 1, 128, 0, st>>>(a, msg.as<uint8_t>());
+    SB_LAUNCH_CHECK();
+    SB_NCCL(nccl().AllGather(msg.ptr, all.ptr, (size_t)a.stride, ncclUint8, c.comm, st));
+    count_launch();
+    std::vector<int64_t> hdr(R);
+    SB_CUDA(cudaMemcpy2DAsync(hdr.data(), 8, all.ptr, (size_t)a.stride, 8, (size_t)R, cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaStreamSynchronize(st));
+    bool fits = true;
+    int64_t total = 0;
+    for (int r = 0; r < R; r++) {
+      fits = fits && hdr[r] <= AG_PACK_ROWS;
+      a.rows[r] = hdr[r];
+      a.off[r] = total;
+      total += hdr[r];
+    }
+    if (fits) {
+      sb_table *t = table_new(total);
+      try {
+        std::vector<Scratch *> temps;
+        for (int ci = 0; ci < a.ncols; ci++) {
+          const Column &col = in->cols[ci];
+          t->cols.push_back(column_alloc(col.type, col.scale, total, col.validity != nullptr, st));
+          a.dst[ci] = t->cols[ci].data->ptr;
+          a.dst_valid_bytes[ci] = nullptr;
+          if (col.validity) {
+            Scratch *vb = new Scratch(total + 16, st);
+            temps.push_back(vb);
+            a.dst_valid_bytes[ci] = vb->as<uint8_t>();
+          }
+        }
+        if (total > 0) {
+          ag_unpack_kernel<<<dim3(a.ncols, R), 128, 0, st>>>(a, all.as<uint8_t>());
+          SB_LAUNCH_CHECK();
+          for (int ci = 0; ci < a.ncols; ci++)
+            if (a.dst_valid_bytes[ci]) bytes_to_bitmap(a.dst_valid_bytes[ci], total, (uint32_t *)t->cols[ci].validity->ptr, st);
+        }
+        for (auto *x : temps) delete x;   // stream-ordered frees
+      } catch (...) {
+        table_free(t);
+        throw;
+      }
+      *out = t;
+      return SB_OK;
+    }
+    // some rank's table did not fit: every rank saw that and continues with the general protocol
+  }
   std::vector<int64_t> rows(R), off(R + 1, 0);
   Scratch d_my(8, st), d_all(R * 8, st);
   SB_CUDA(cudaMemcpyAsync(d_my.ptr, &my, 8, cudaMemcpyHostToDevice, st));

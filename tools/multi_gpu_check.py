@@ -61,6 +61,14 @@ def main():
     allg = ColumnarBatch(h, small.names, small.arrow_types).to_arrow(stream)
     want_g = pa.concat_tables([shard(r).slice(0, 1000 + r) for r in range(world)])
     assert allg.to_pydict() == want_g.to_pydict(), "rank %d: all-gather differs" % rank
+    # small tables take the packed single-message path (<= 256 rows on every rank); an empty contribution is legal
+    for rows_of in (lambda r: 5 + 3 * r, lambda r: 0 if r == 0 else 256, lambda r: 256 + r):
+        tiny = ColumnarBatch.from_arrow(mine.slice(0, rows_of(rank)), stream)
+        h = C.c_void_p()
+        capi.check(lib.sb_all_gather(tiny.handle, stream.handle, C.byref(h)))
+        got_t = ColumnarBatch(h, tiny.names, tiny.arrow_types).to_arrow(stream)
+        want_t = pa.concat_tables([shard(r).slice(0, rows_of(r)) for r in range(world)])
+        assert got_t.to_pydict() == want_t.to_pydict(), "rank %d: small all-gather differs" % rank
     ok = torch.ones(1, device="cuda")
     dist.all_reduce(ok)
     if rank == 0:
