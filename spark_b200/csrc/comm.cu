@@ -195,6 +195,7 @@ constexpr int AG_MAX_COLS = 64;
 struct AgPackArgs {
   int32_t ncols, nranks;
   int64_t my_rows, stride;                  // bytes per rank message
+  uint64_t my_valid_mask;                   // bit c: this rank's column c carries a validity bitmap
   const void *src[AG_MAX_COLS];             // pack: this rank's columns
   const uint8_t *src_valid[AG_MAX_COLS];
   void *dst[AG_MAX_COLS];                   // unpack: output columns
@@ -206,7 +207,10 @@ struct AgPackArgs {
 __global__ void ag_pack_kernel(const __grid_constant__ AgPackArgs a, uint8_t *__restrict__ msg) {
   const int c = blockIdx.x;
   if (c == a.ncols) {
-    if (threadIdx.x == 0) *(int64_t *)msg = a.my_rows;
+    if (threadIdx.x == 0) {
+      ((int64_t *)msg)[0] = a.my_rows;
+      ((uint64_t *)msg)[1] = a.my_valid_mask;
+    }
     return;
   }
   const int64_t rows = a.my_rows < AG_PACK_ROWS ? a.my_rows : AG_PACK_ROWS;
@@ -301,22 +305,33 @@ int sb_all_to_all(const sb_table *in, const int64_t *part_offsets_host, int32_t 
   const int R = c.nranks;
   const int P = num_partitions;
   // 1. every rank learns every rank's per-partition row counts
-  std::vector<int64_t> my_counts(P), all_counts((size_t)R * P);
+  // (the last word of every rank's message says which of its columns carry a validity bitmap: a column is nullable in the
+  // exchange if it is on ANY rank -- a rank whose rows happen to hold no NULL may have dropped the bitmap)
+  SB_REQUIRE(in->cols.size() <= 64, "the exchange supports up to 64 columns");
+  const int PS = P + 1;
+  std::vector<int64_t> my_counts(PS), all_counts((size_t)R * PS);
   for (int p = 0; p < P; p++) my_counts[p] = part_offsets_host[p + 1] - part_offsets_host[p];
-  Scratch d_my(P * 8, st), d_all((int64_t)R * P * 8, st);
+  uint64_t my_mask = 0;
+  for (size_t ci = 0; ci < in->cols.size(); ci++)
+    if (in->cols[ci].validity) my_mask |= 1ull << ci;
+  my_counts[P] = (int64_t)my_mask;
+  Scratch d_my(PS * 8, st), d_all((int64_t)R * PS * 8, st);
   {
     KernelTimer kt("a2a_counts", st);
-    SB_CUDA(cudaMemcpyAsync(d_my.ptr, my_counts.data(), (size_t)P * 8, cudaMemcpyHostToDevice, st));
-    SB_NCCL(nccl().AllGather(d_my.ptr, d_all.ptr, (size_t)P, ncclInt64, c.comm, st));
-    SB_CUDA(cudaMemcpyAsync(all_counts.data(), d_all.ptr, (size_t)R * P * 8, cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaMemcpyAsync(d_my.ptr, my_counts.data(), (size_t)PS * 8, cudaMemcpyHostToDevice, st));
+    SB_NCCL(nccl().AllGather(d_my.ptr, d_all.ptr, (size_t)PS, ncclInt64, c.comm, st));
+    SB_CUDA(cudaMemcpyAsync(all_counts.data(), d_all.ptr, (size_t)R * PS * 8, cudaMemcpyDeviceToHost, st));
   }
   SB_CUDA(cudaStreamSynchronize(st));
+  uint64_t any_mask = 0;
+  for (int r = 0; r < R; r++) any_mask |= (uint64_t)all_counts[(size_t)r * PS + P];
+  auto nullable = [&](size_t ci) { return ((any_mask >> ci) & 1) != 0; };
   // 2. layout of what this rank receives: [source rank][owned partitions]
   const int lo = part_lo(c.rank, P, R), hi = part_lo(c.rank + 1, P, R);
   std::vector<int64_t> recv_rows(R), recv_off(R + 1, 0), send_rows(R), send_off(R);
   for (int src = 0; src < R; src++) {
     int64_t rows = 0;
-    for (int p = lo; p < hi; p++) rows += all_counts[(size_t)src * P + p];
+    for (int p = lo; p < hi; p++) rows += all_counts[(size_t)src * PS + p];
     recv_rows[src] = rows;
     recv_off[src + 1] = recv_off[src] + rows;
   }
@@ -331,7 +346,7 @@ int sb_all_to_all(const sb_table *in, const int64_t *part_offsets_host, int32_t 
   for (int p = 0; p < P; p++) {
     int64_t rows = 0;
     if (p >= lo && p < hi)
-      for (int src = 0; src < R; src++) rows += all_counts[(size_t)src * P + p];
+      for (int src = 0; src < R; src++) rows += all_counts[(size_t)src * PS + p];
     out_part_offsets_host[p + 1] = out_part_offsets_host[p] + rows;
   }
   // 3. data path.  Window layout of a receiver d: the columns one after the other (256-byte aligned), each laid out like the
@@ -342,14 +357,14 @@ int sb_all_to_all(const sb_table *in, const int64_t *part_offsets_host, int32_t 
     int64_t rows = 0;
     const int dl = part_lo(d, P, R), dh = part_lo(d + 1, P, R);
     for (int src = 0; src < R; src++)
-      for (int p = dl; p < dh; p++) rows += all_counts[(size_t)src * P + p];
+      for (int p = dl; p < dh; p++) rows += all_counts[(size_t)src * PS + p];
     return rows;
   };
   auto recv_off_of = [&](int d, int src_rank) {   // first row of src_rank's segment in d's columns
     int64_t rows = 0;
     const int dl = part_lo(d, P, R), dh = part_lo(d + 1, P, R);
     for (int sr = 0; sr < src_rank; sr++)
-      for (int p = dl; p < dh; p++) rows += all_counts[(size_t)sr * P + p];
+      for (int p = dl; p < dh; p++) rows += all_counts[(size_t)sr * PS + p];
     return rows;
   };
   auto window_layout = [&](int64_t rows, std::vector<size_t> &col_off, std::vector<size_t> &val_off) {
@@ -359,7 +374,7 @@ int sb_all_to_all(const sb_table *in, const int64_t *part_offsets_host, int32_t 
     for (size_t ci = 0; ci < in->cols.size(); ci++) {
       col_off[ci] = cur;
       cur += ((size_t)rows * type_width(in->cols[ci].type) + 255) / 256 * 256;
-      if (in->cols[ci].validity) {
+      if (nullable(ci)) {
         val_off[ci] = cur;
         cur += ((size_t)rows + 255) / 256 * 256;
       }
@@ -385,8 +400,8 @@ int sb_all_to_all(const sb_table *in, const int64_t *part_offsets_host, int32_t 
       t->cols.reserve(in->cols.size());
       for (size_t ci = 0; ci < in->cols.size(); ci++) {
         const Column &col = in->cols[ci];
-        t->cols.push_back(column_alloc(col.type, col.scale, nrecv, col.validity != nullptr, st));
-        if (col.validity) {
+        t->cols.push_back(column_alloc(col.type, col.scale, nrecv, nullable(ci), st));
+        if (nullable(ci)) {
           Scratch *sb = new Scratch(in->nrows + 16, st);
           temps.push_back(sb);
           bitmap_to_bytes(col.v(), in->nrows, sb->as<uint8_t>(), st);
@@ -408,7 +423,7 @@ int sb_all_to_all(const sb_table *in, const int64_t *part_offsets_host, int32_t 
           char *dst_base = d == me ? (char *)t->cols[ci].data->ptr : (char *)w.remote[d] + co[ci];
           SB_CUDA(cudaMemcpyAsync(dst_base + roff * wd, (const char *)col.d() + send_off[d] * wd, (size_t)(send_rows[d] * wd),
                                   cudaMemcpyDeviceToDevice, ps));
-          if (col.validity && d != me)
+          if (nullable(ci) && d != me)
             SB_CUDA(cudaMemcpyAsync((char *)w.remote[d] + vo[ci] + roff, send_bytes[ci] + send_off[d], (size_t)send_rows[d],
                                     cudaMemcpyDeviceToDevice, ps));
         }
@@ -433,7 +448,7 @@ int sb_all_to_all(const sb_table *in, const int64_t *part_offsets_host, int32_t 
           const int64_t a0 = recv_off[me], a1 = recv_off[me + 1];
           if (a0 > 0) SB_CUDA(cudaMemcpyAsync(outp, win, (size_t)(a0 * wd), cudaMemcpyDeviceToDevice, st));
           if (nrecv > a1) SB_CUDA(cudaMemcpyAsync(outp + a1 * wd, win + a1 * wd, (size_t)((nrecv - a1) * wd), cudaMemcpyDeviceToDevice, st));
-          if (col.validity) {
+          if (nullable(ci)) {
             // own rows' validity bytes join the others in the window, then the whole column is re-packed into a bitmap
             uint8_t *vwin = (uint8_t *)w.local + vo[ci];
             if (a1 > a0) SB_CUDA(cudaMemcpyAsync(vwin + a0, send_bytes[ci] + send_off[me], (size_t)(a1 - a0), cudaMemcpyDeviceToDevice, st));
@@ -459,9 +474,10 @@ int sb_all_to_all(const sb_table *in, const int64_t *part_offsets_host, int32_t 
     std::vector<Pending> pend;
     std::vector<std::pair<const uint8_t *, uint8_t *>> self_valid;   // (send bytes, recv bytes) of every nullable column
     t->cols.reserve(in->cols.size());
-    for (auto &col : in->cols) {
+    for (size_t ci = 0; ci < in->cols.size(); ci++) {
+      const Column &col = in->cols[ci];
       if (col.type == SB_STRING) fail(SB_ERR_UNSUPPORTED, "all-to-all of string columns is not implemented (dictionary-encode them)");
-      t->cols.push_back(column_alloc(col.type, col.scale, nrecv, col.validity != nullptr, st));
+      t->cols.push_back(column_alloc(col.type, col.scale, nrecv, nullable(ci), st));
     }
     KernelTimer kt_transfer("a2a_transfer", st);
     SB_NCCL(nccl().GroupStart());
@@ -476,7 +492,7 @@ int sb_all_to_all(const sb_table *in, const int64_t *part_offsets_host, int32_t 
         if (recv_rows[peer] > 0)
           SB_NCCL(nccl().Recv((char *)dst.data->ptr + recv_off[peer] * w, (size_t)(recv_rows[peer] * w), ncclUint8, peer, c.comm, st));
       }
-      if (src.validity) {
+      if (nullable(ci)) {
         Scratch *sb = new Scratch(in->nrows + 16, st), *rb = new Scratch(nrecv + 16, st);
         temps.push_back(sb);
         temps.push_back(rb);
@@ -558,6 +574,7 @@ int sb_all_gather(const sb_table *in, sb_stream *s, sb_table **out) {
       a.width[ci] = type_width(col.type);
       a.src[ci] = col.d();
       a.src_valid[ci] = col.v();
+      if (col.validity) a.my_valid_mask |= 1ull << ci;
       a.data_off[ci] = cur;
       cur += (AG_PACK_ROWS * a.width[ci] + 15) / 16 * 16;
       a.valid_off[ci] = cur;
@@ -569,16 +586,19 @@ int sb_all_gather(const sb_table *in, sb_stream *s, sb_table **out) {
     SB_LAUNCH_CHECK();
     SB_NCCL(nccl().AllGather(msg.ptr, all.ptr, (size_t)a.stride, ncclUint8, c.comm, st));
     count_launch();
-    std::vector<int64_t> hdr(R);
-    SB_CUDA(cudaMemcpy2DAsync(hdr.data(), 8, all.ptr, (size_t)a.stride, 8, (size_t)R, cudaMemcpyDeviceToHost, st));
+    std::vector<int64_t> hdr(2 * R);
+    SB_CUDA(cudaMemcpy2DAsync(hdr.data(), 16, all.ptr, (size_t)a.stride, 16, (size_t)R, cudaMemcpyDeviceToHost, st));
     SB_CUDA(cudaStreamSynchronize(st));
     bool fits = true;
     int64_t total = 0;
+    uint64_t any_valid = 0;   // a column is nullable in the result if it is on ANY rank (a rank whose rows happen to hold no NULL
+                              // may have dropped the bitmap)
     for (int r = 0; r < R; r++) {
-      fits = fits && hdr[r] <= AG_PACK_ROWS;
-      a.rows[r] = hdr[r];
+      fits = fits && hdr[2 * r] <= AG_PACK_ROWS;
+      a.rows[r] = hdr[2 * r];
       a.off[r] = total;
-      total += hdr[r];
+      total += hdr[2 * r];
+      any_valid |= (uint64_t)hdr[2 * r + 1];
     }
     if (fits) {
       sb_table *t = table_new(total);
@@ -586,10 +606,11 @@ int sb_all_gather(const sb_table *in, sb_stream *s, sb_table **out) {
         std::vector<Scratch *> temps;
         for (int ci = 0; ci < a.ncols; ci++) {
           const Column &col = in->cols[ci];
-          t->cols.push_back(column_alloc(col.type, col.scale, total, col.validity != nullptr, st));
+          const bool nullable = (any_valid >> ci) & 1;
+          t->cols.push_back(column_alloc(col.type, col.scale, total, nullable, st));
           a.dst[ci] = t->cols[ci].data->ptr;
           a.dst_valid_bytes[ci] = nullptr;
-          if (col.validity) {
+          if (nullable) {
             Scratch *vb = new Scratch(total + 16, st);
             temps.push_back(vb);
             a.dst_valid_bytes[ci] = vb->as<uint8_t>();
@@ -611,13 +632,22 @@ int sb_all_gather(const sb_table *in, sb_stream *s, sb_table **out) {
     }
     // some rank's table did not fit: every rank saw that and continues with the general protocol
   }
-  std::vector<int64_t> rows(R), off(R + 1, 0);
-  Scratch d_my(8, st), d_all(R * 8, st);
-  SB_CUDA(cudaMemcpyAsync(d_my.ptr, &my, 8, cudaMemcpyHostToDevice, st));
-  SB_NCCL(nccl().AllGather(d_my.ptr, d_all.ptr, 1, ncclInt64, c.comm, st));
-  SB_CUDA(cudaMemcpyAsync(rows.data(), d_all.ptr, (size_t)R * 8, cudaMemcpyDeviceToHost, st));
+  std::vector<int64_t> rows(R), off(R + 1, 0), hdr2(2 * R);
+  uint64_t my_mask = 0, any_mask = 0;   // nullable in the result = nullable on any rank (see the packed path)
+  for (size_t ci = 0; ci < in->cols.size() && ci < 64; ci++)
+    if (in->cols[ci].validity) my_mask |= 1ull << ci;
+  int64_t my_hdr[2] = {my, (int64_t)my_mask};
+  Scratch d_my(16, st), d_all(R * 16, st);
+  SB_CUDA(cudaMemcpyAsync(d_my.ptr, my_hdr, 16, cudaMemcpyHostToDevice, st));
+  SB_NCCL(nccl().AllGather(d_my.ptr, d_all.ptr, 2, ncclInt64, c.comm, st));
+  SB_CUDA(cudaMemcpyAsync(hdr2.data(), d_all.ptr, (size_t)R * 16, cudaMemcpyDeviceToHost, st));
   SB_CUDA(cudaStreamSynchronize(st));
-  for (int r = 0; r < R; r++) off[r + 1] = off[r] + rows[r];
+  for (int r = 0; r < R; r++) {
+    rows[r] = hdr2[2 * r];
+    any_mask |= (uint64_t)hdr2[2 * r + 1];
+    off[r + 1] = off[r] + rows[r];
+  }
+  SB_REQUIRE(in->cols.size() <= 64, "all-gather supports up to 64 columns");
   const int64_t total = off[R];
   sb_table *t = table_new(total);
   try {
@@ -625,9 +655,10 @@ int sb_all_gather(const sb_table *in, sb_stream *s, sb_table **out) {
     struct Pending { Column *col; uint8_t *bytes; };
     std::vector<Pending> pend;
     t->cols.reserve(in->cols.size());
-    for (auto &col : in->cols) {
+    for (size_t ci = 0; ci < in->cols.size(); ci++) {
+      const Column &col = in->cols[ci];
       if (col.type == SB_STRING) fail(SB_ERR_UNSUPPORTED, "all-gather of string columns is not implemented (dictionary-encode them)");
-      t->cols.push_back(column_alloc(col.type, col.scale, total, col.validity != nullptr, st));
+      t->cols.push_back(column_alloc(col.type, col.scale, total, (any_mask >> ci) & 1, st));
     }
     SB_NCCL(nccl().GroupStart());
     for (size_t ci = 0; ci < in->cols.size(); ci++) {
@@ -638,11 +669,11 @@ int sb_all_gather(const sb_table *in, sb_stream *s, sb_table **out) {
         if (my > 0) SB_NCCL(nccl().Send(src.d(), (size_t)(my * w), ncclUint8, peer, c.comm, st));
         if (rows[peer] > 0) SB_NCCL(nccl().Recv((char *)dst.data->ptr + off[peer] * w, (size_t)(rows[peer] * w), ncclUint8, peer, c.comm, st));
       }
-      if (src.validity) {
+      if ((any_mask >> ci) & 1) {
         Scratch *sb = new Scratch(my + 16, st), *rb = new Scratch(total + 16, st);
         temps.push_back(sb);
         temps.push_back(rb);
-        bitmap_to_bytes(src.v(), my, sb->as<uint8_t>(), st);
+        bitmap_to_bytes(src.v(), my, sb->as<uint8_t>(), st);   // no bitmap on this rank: all ones
         for (int peer = 0; peer < R; peer++) {
           if (my > 0) SB_NCCL(nccl().Send(sb->as<uint8_t>(), (size_t)my, ncclUint8, peer, c.comm, st));
           if (rows[peer] > 0) SB_NCCL(nccl().Recv(rb->as<uint8_t>() + off[peer], (size_t)rows[peer], ncclUint8, peer, c.comm, st));
