@@ -74,7 +74,7 @@ struct AggArgs {
   uint64_t *tkeys;       // [nwords][cap + 2]   slot cap = NULL key, slot cap+1 = key equal to the EMPTY sentinel
   uint64_t *tacc;        // [nslots][cap + 2]
   int32_t *flags;        // [0] abort (table too small), [1] NULL-key slot used, [2] sentinel-key slot used,
-                         // [6] the dictionary tier met a shape it should not handle (see gate)
+                         // [6] / [7] the first / second dictionary kernel met a shape it should not handle (see gate)
   int64_t cap;
   // Automatic tier choice, no host round trip: the dictionary kernel runs with gate = 1; the first warp whose rows do not all
   // resolve in its block's dictionary (more than AGG_DICT groups, or NULL / sentinel keys) raises flags[6], every block stops at
@@ -82,8 +82,10 @@ struct AggArgs {
   // right behind it with gate = 2: it returns at once when flags[6] is clear, otherwise it picks up the unfinished tiles.
   int32_t gate;          // 0: plain; 1: dictionary kernel, watch and yield; 2: shared-memory kernel, take over
   int32_t scap;          // shared-memory tier: table capacity (power of two)
-  int32_t *progress;     // [dict_grid]
+  int32_t *progress;     // [dict_grid][warps]: tiles finished by every warp of the FIRST dictionary kernel's blocks
+  int32_t *progress2;    // same shape, left by the second dictionary kernel (which works on the first one's tile geometry)
   int32_t dict_grid, dict_items;
+  int32_t last_flag;     // index in flags of the yield flag of the LAST dictionary kernel of the chain (6 or 7)
   int32_t combine;       // shared-memory tier: combine same-entry rows of a warp before the atomics
 };
 
@@ -566,7 +568,7 @@ __device__ __forceinline__ void tile_keys(const AggArgs &a, const TileCtx &t, bo
   }
 }
 
-template <class P, int ITEMS, bool FULL, bool STAGED, bool YIELD = false>
+template <class P, int ITEMS, bool FULL, bool STAGED, bool YIELD = false, int D = AGG_DICT>
 __device__ __forceinline__ bool process_tile(const AggArgs &a, const TileCtx &t, uint64_t *dict_keys, uint64_t *acc, int tid, int64_t stride) {
   const PlanMeta &m = P::meta(a);
   const int ns = m.nslots;
@@ -577,26 +579,40 @@ __device__ __forceinline__ bool process_tile(const AggArgs &a, const TileCtx &t,
   // ---- where does each row accumulate? ---------------------------------------------------------------------
   int64_t dst[ITEMS];
   int doff[ITEMS];
-  const int trash = AGG_DICT * ns * AGG_THREADS + tid;
+  const int trash = D * ns * AGG_THREADS + tid;
   bool all_dict = true;
+  // The dictionary's keys are compared in REGISTERS: D shared-memory loads per tile instead of a hashed probe loop per row.  A
+  // row that matches none of the cached keys takes the slow path (linear probing with an atomicCAS claim, which also finds
+  // entries other warps inserted since the snapshot) and refreshes the snapshot.
+  uint64_t dk[D];
+#pragma unroll
+  for (int i = 0; i < D; i++) dk[i] = *(volatile uint64_t *)&dict_keys[i];
 #pragma unroll
   for (int k = 0; k < ITEMS; k++) {
     dst[k] = -1;
     doff[k] = -1;
     if (!keep[k]) continue;
+    if (YIELD && !all_dict) continue;   // this warp is going to yield: no point in resolving the rest of its rows
     int gid = -1;
     if (special[k] == 0) {
-      // linear probing over the AGG_DICT entries from a key-dependent start: a resident key is normally the first probe
-      const uint32_t h0 = ((uint32_t)key[k] ^ (uint32_t)(key[k] >> 32)) * 0x9E3779B1u >> 29;
+#pragma unroll
+      for (int i = 0; i < D; i++) gid = dk[i] == key[k] ? i : gid;
+      if (gid < 0) {
+        constexpr int LOG_D = D == 4 ? 2 : (D == 8 ? 3 : (D == 16 ? 4 : 5));
+        static_assert(D == 4 || D == 8 || D == 16 || D == 32, "dictionary sizes are powers of two");
+        const uint32_t h0 = ((uint32_t)key[k] ^ (uint32_t)(key[k] >> 32)) * 0x9E3779B1u >> (32 - LOG_D);
 #pragma unroll 1
-      for (int i = 0; i < AGG_DICT; i++) {
-        const int g = (h0 + i) & (AGG_DICT - 1);
-        uint64_t dk = dict_keys[g];
-        if (dk == EMPTY_KEY) {
-          uint64_t old = atomicCAS((unsigned long long *)&dict_keys[g], (unsigned long long)EMPTY_KEY, (unsigned long long)key[k]);
-          dk = old == EMPTY_KEY ? key[k] : old;
+        for (int i = 0; i < D; i++) {
+          const int g = (h0 + i) & (D - 1);
+          uint64_t cur = *(volatile uint64_t *)&dict_keys[g];
+          if (cur == EMPTY_KEY) {
+            uint64_t old = atomicCAS((unsigned long long *)&dict_keys[g], (unsigned long long)EMPTY_KEY, (unsigned long long)key[k]);
+            cur = old == EMPTY_KEY ? key[k] : old;
+          }
+          if (cur == key[k]) { gid = g; break; }
         }
-        if (dk == key[k]) { gid = g; break; }
+#pragma unroll
+        for (int i = 0; i < D; i++) dk[i] = *(volatile uint64_t *)&dict_keys[i];
       }
     }
     if (gid >= 0) doff[k] = gid * ns * AGG_THREADS + tid;
@@ -622,24 +638,24 @@ __device__ __forceinline__ bool process_tile(const AggArgs &a, const TileCtx &t,
   return true;
 }
 
-template <class P>
+template <class P, int D = AGG_DICT>
 __device__ __forceinline__ void dict_init(const AggArgs &a, uint64_t *dict_keys, uint64_t *acc, int tid) {
   const PlanMeta &m = P::meta(a);
   const int ns = m.nslots;
-  if (tid < AGG_DICT) dict_keys[tid] = EMPTY_KEY;
+  if (tid < D) dict_keys[tid] = EMPTY_KEY;
   for (int s = 0; s < ns; s++) {
     uint64_t id = slot_identity(m.slot_kind[s]);
-    for (int g = 0; g <= AGG_DICT; g++) acc[(g * ns + s) * AGG_THREADS + tid] = id;
+    for (int g = 0; g <= D; g++) acc[(g * ns + s) * AGG_THREADS + tid] = id;
   }
 }
 // merge the block dictionary into the HBM table: one warp per GROUP -- one find-or-insert for the group, then a shuffle tree
 // and one fire-and-forget RED per slot (a probe per (group, slot) pair made the kernel's tail a chain of L2 round trips)
-template <class P>
+template <class P, int D = AGG_DICT>
 __device__ __forceinline__ void dict_merge(const AggArgs &a, const uint64_t *dict_keys, const uint64_t *acc, int tid, int64_t stride) {
   const PlanMeta &m = P::meta(a);
   const int ns = m.nslots;
   const int lane = tid & 31, warp = tid >> 5, nwarps = AGG_THREADS / 32;
-  for (int g = warp; g < AGG_DICT; g += nwarps) {
+  for (int g = warp; g < D; g += nwarps) {
     const uint64_t key = dict_keys[g];
     if (key == EMPTY_KEY) continue;
     int64_t slot = 0;
@@ -679,42 +695,79 @@ __device__ __forceinline__ void prefetch_tile(const AggArgs &a, int64_t row0) {
 }
 
 // ---- direct kernel: columns are read straight from HBM --------------------------------------------------------------
-template <class P, int ITEMS, bool PREFETCH = false, bool YIELD = false, bool FAT = false>
+// MODE 0: plain (rows the dictionary cannot hold go to the HBM table).
+// MODE 1: watch and yield -- the first kernel of the automatic chain: a warp whose rows do not all resolve in the D-entry
+//         dictionary leaves them untouched, raises flags[6] and records its progress; everybody else stops at the next tile.
+// MODE 2: take over and yield -- the second kernel of the chain (a larger dictionary, lower occupancy): returns at once unless
+//         flags[6] is set, then walks the warp slices the first kernel left behind (same tile geometry), and yields in turn
+//         (flags[7], progress2) to the shared-memory kernel.
+// Lane-private accumulators cost D x slots x 8 bytes per thread, so the dictionary size sets the occupancy: Q1 (6 slots) keeps
+// 28 warps per SM with D = 4 against 16 with D = 8 -- the 4-group query runs at 0.57 instead of 0.64 ms -- and a 5..8-group
+// input costs one extra launch.
+enum { AGG_MODE_PLAIN = 0, AGG_MODE_YIELD = 1, AGG_MODE_TAKEOVER = 2 };
+template <class P, int ITEMS, bool PREFETCH = false, int MODE = AGG_MODE_PLAIN, bool FAT = false, int D = AGG_DICT>
 __global__ void __launch_bounds__(AGG_THREADS) agg_update_kernel(const __grid_constant__ AggArgs a) {
   extern __shared__ __align__(128) uint64_t sm_direct[];
   uint64_t *dict_keys = sm_direct;
-  uint64_t *acc = sm_direct + AGG_DICT;
+  uint64_t *acc = sm_direct + D;
   const int tid = threadIdx.x;
-  dict_init<P>(a, dict_keys, acc, tid);
+  if (MODE == AGG_MODE_TAKEOVER && *(volatile int32_t *)&a.flags[6] == 0) return;   // the first kernel finished the job
+  dict_init<P, D>(a, dict_keys, acc, tid);
   __syncthreads();
   constexpr int64_t TILE = (int64_t)AGG_THREADS * ITEMS;
+  constexpr bool YIELD = MODE != AGG_MODE_PLAIN;
   const int64_t stride = a.cap + 2;
+  volatile int32_t *yield_flag = &a.flags[MODE == AGG_MODE_TAKEOVER ? 7 : 6];
   // The abort / yield flags are sampled while a tile is being processed and acted on before the next one, so their L2 round trip
   // hides behind the tile's own loads.  Yielding is per WARP (no block barrier in the hot loop): a warp records how many tiles
-  // it finished; the shared-memory kernel mirrors the tile geometry and picks up exactly the warp slices left behind.
-  int32_t tiles_done = 0, stop = 0;
-  for (int64_t base = (int64_t)blockIdx.x * TILE; base < a.n && !stop; base += (int64_t)gridDim.x * TILE) {
-    stop = *(volatile int32_t *)a.flags;                      // another block found the table too small: give up early
-    if (YIELD) stop |= *(volatile int32_t *)&a.flags[6];      // not a few-groups input: yield
+  // it finished; the next kernel mirrors the tile geometry and picks up exactly the warp slices left behind.
+  int32_t stop = 0;
+  auto one_tile = [&](int64_t base, int64_t next) -> bool {   // false: this warp yields (the tile is untouched)
+    stop = *(volatile int32_t *)a.flags;                       // another block found the table too small: give up early
+    if (YIELD) stop |= *yield_flag;                            // somebody met rows this tier should not handle
     TileCtx t{nullptr, base + tid, a.n - 1};
-    const int64_t next = base + (int64_t)gridDim.x * TILE;
     if (PREFETCH && next + TILE <= a.n) prefetch_tile<P, ITEMS>(a, next + tid);
-    if (FAT && a.gate == 3) {   // never taken; see SB_AGG_Q1_VARIANT=8pf in aggregate.cu
-      process_tile<P, ITEMS, true, false>(a, t, dict_keys, acc, tid, stride);
+    if (FAT && a.gate == 3) {   // never taken; see SB_AGG_Q1_VARIANT in aggregate.cu
+      process_tile<P, ITEMS, true, false, false, D>(a, t, dict_keys, acc, tid, stride);
     } else if constexpr (YIELD) {
-      const bool done = base + TILE <= a.n ? process_tile<P, ITEMS, true, false, true>(a, t, dict_keys, acc, tid, stride)
-                                           : process_tile<P, ITEMS, false, false, true>(a, t, dict_keys, acc, tid, stride);
+      const bool done = base + TILE <= a.n ? process_tile<P, ITEMS, true, false, true, D>(a, t, dict_keys, acc, tid, stride)
+                                           : process_tile<P, ITEMS, false, false, true, D>(a, t, dict_keys, acc, tid, stride);
       if (!done) {
-        *(volatile int32_t *)&a.flags[6] = 1;
-        break;
+        *yield_flag = 1;
+        return false;
       }
-    } else if (base + TILE <= a.n) process_tile<P, ITEMS, true, false>(a, t, dict_keys, acc, tid, stride);
-    else process_tile<P, ITEMS, false, false>(a, t, dict_keys, acc, tid, stride);
-    tiles_done++;
+    } else if (base + TILE <= a.n) process_tile<P, ITEMS, true, false, false, D>(a, t, dict_keys, acc, tid, stride);
+    else process_tile<P, ITEMS, false, false, false, D>(a, t, dict_keys, acc, tid, stride);
+    return true;
+  };
+  if constexpr (MODE == AGG_MODE_TAKEOVER) {
+    const int w = tid >> 5, lane = tid & 31;
+    constexpr int NW = AGG_THREADS / 32;
+    bool yielded = false;
+    for (int64_t b = blockIdx.x; b < a.dict_grid; b += gridDim.x) {   // the first kernel's block b, this warp's slice of its tiles
+      int64_t j = a.progress[b * NW + w];
+      if (!yielded) {
+        for (;; j++) {
+          const int64_t base = (b + j * a.dict_grid) * TILE;
+          if (base >= a.n) break;
+          if (stop || !one_tile(base, base + (int64_t)a.dict_grid * TILE)) {
+            yielded = true;
+            break;
+          }
+        }
+      }
+      if (lane == 0) a.progress2[b * NW + w] = (int32_t)j;
+    }
+  } else {
+    int32_t tiles_done = 0;
+    for (int64_t base = (int64_t)blockIdx.x * TILE; base < a.n && !stop; base += (int64_t)gridDim.x * TILE) {
+      if (!one_tile(base, base + (int64_t)gridDim.x * TILE)) break;
+      tiles_done++;
+    }
+    if (YIELD && (tid & 31) == 0) a.progress[blockIdx.x * (AGG_THREADS / 32) + (tid >> 5)] = tiles_done;
   }
-  if (YIELD && (tid & 31) == 0) a.progress[blockIdx.x * (AGG_THREADS / 32) + (tid >> 5)] = tiles_done;
   __syncthreads();
-  dict_merge<P>(a, dict_keys, acc, tid, stride);
+  dict_merge<P, D>(a, dict_keys, acc, tid, stride);
 }
 
 // ---- shared-memory tier: medium cardinality ----------------------------------------------------------------------------------
@@ -878,7 +931,7 @@ __device__ __forceinline__ void process_tile_smem(const AggArgs &a, const TileCt
 template <class P, int ITEMS>
 __global__ void __launch_bounds__(AGGS_THREADS) agg_update_smem_kernel(const __grid_constant__ AggArgs a) {
   extern __shared__ __align__(128) uint64_t sm_tab[];
-  if (a.gate == 2 && *(volatile int32_t *)&a.flags[6] == 0) return;   // the dictionary tier finished the job
+  if (a.gate == 2 && *(volatile int32_t *)&a.flags[a.last_flag] == 0) return;   // the dictionary tiers finished the job
   const PlanMeta &m = P::meta(a);
   const int ns = m.nslots;
   const uint32_t C = (uint32_t)a.scap;
@@ -904,7 +957,7 @@ __global__ void __launch_bounds__(AGGS_THREADS) agg_update_smem_kernel(const __g
     const int64_t dtile = (int64_t)AGG_THREADS * a.dict_items;
     const int w = tid >> 5;
     for (int64_t b = vb; b < a.dict_grid; b += nvb)
-      for (int64_t j = a.progress[b * (AGG_THREADS / 32) + w];; j++) {   // this warp's slice of dict block b's tiles j, j+1, ...
+      for (int64_t j = a.progress2[b * (AGG_THREADS / 32) + w];; j++) {   // this warp's slice of dict block b's tiles j, j+1, ...
         const int64_t base0 = (b + j * a.dict_grid) * dtile;
         if (base0 >= a.n || *(volatile int32_t *)a.flags) break;
         for (int64_t base = base0; base < base0 + dtile && base < a.n; base += TILE) one_tile(base);

@@ -24,6 +24,7 @@
 //     counts of non-nullable averages share one counter).
 // Floating SUM/AVG are order-dependent in the reference too (partials merge in fetch order); parity is
 // 1e-6 relative for them, exact for keys/counts/integer sums/min/max.
+#include <algorithm>
 #include <math.h>
 #include <stdlib.h>
 #include <memory>
@@ -78,52 +79,62 @@ constexpr int ITEMS_STAGED = 4;   // staged path (512-row tiles keep two blocks 
 typedef void (*AggKernel)(const AggArgs);
 constexpr int ITEMS_SMEM = 4;     // shared-memory tier: 512 threads x 4 rows
 struct KernelChoice {
-  AggKernel direct, staged;
+  AggKernel direct, staged;           // plain dictionary kernel (8 entries) and its TMA variant
   int items_direct;
   const char *name;
   AggKernel smem = agg_update_smem_kernel<DynPlan, ITEMS_SMEM>;
-  AggKernel direct_yield = nullptr;   // the same kernel in watch-and-yield mode (AggArgs::gate == 1)
+  // the automatic chain: k1 watches and yields (dictionary of k1_dict entries, k1_items rows per thread), k2 (optional, 8
+  // entries, same tile geometry) takes over and yields in turn, smem finishes
+  AggKernel k1 = nullptr, k2 = nullptr;
+  int k1_dict = 4, k1_items = ITEMS_DIRECT;
+  AggKernel k1_wide = nullptr;        // 8-entry watch-and-yield kernel: the whole dictionary tier when 8 entries cost no occupancy
 };
-static KernelChoice choose_kernels_base(const PlanMeta &m);
-static KernelChoice choose_kernels(const PlanMeta &m) {
-  KernelChoice kc = choose_kernels_base(m);
-  if (!kc.direct_yield) kc.direct_yield = agg_update_kernel<DynPlan, ITEMS_DIRECT, false, true>;
-  return kc;
+template <class P, int ITEMS, bool PREFETCH>
+static void default_chain(KernelChoice &kc) {
+  kc.k1 = agg_update_kernel<P, ITEMS, PREFETCH, AGG_MODE_YIELD, false, 4>;
+  kc.k2 = agg_update_kernel<P, ITEMS, PREFETCH, AGG_MODE_TAKEOVER, false, 8>;
+  kc.k1_wide = agg_update_kernel<P, ITEMS, PREFETCH, AGG_MODE_YIELD, false, 8>;
+  kc.k1_dict = 4;
+  kc.k1_items = ITEMS;
 }
-static KernelChoice choose_kernels_base(const PlanMeta &m) {
+static KernelChoice choose_kernels(const PlanMeta &m) {
   if (getenv("SB_AGG_DISABLE_STATIC") == nullptr) {
-    const char *v = getenv("SB_AGG_Q1_VARIANT");   // tuning knob: "8pf" (default) | "8p" | "8" | "4p" | "4" (rows per thread, p = L2 prefetch, f = fat build)
+    // tuning knob: "4" (default: 4 rows per thread, 4-entry then 8-entry dictionary) | "4p" (+ L2 prefetch of the next tile) |
+    // "8pf" | "8p" | "8" (single 8-entry dictionary kernel, 8 rows per thread; f = fat build: the never-taken general path raises
+    // ptxas's register target from 56 to 117).  Measured on SF10: 0.461 / 0.470 / 0.491 ms for "4" / "4p" / "8pf".
+    const char *v = getenv("SB_AGG_Q1_VARIANT");
     if (memcmp(&m, &kHostMetaQ1Partial, sizeof(PlanMeta)) == 0) {
       using Q1 = StaticPlan<&kDevMetaQ1Partial>;
-      KernelChoice q1{agg_update_kernel<Q1, 8, true>, agg_update_staged_kernel<Q1, ITEMS_STAGED>, 8, "static:q1_partial/8pf"};
-      // Default "8pf": 8 rows per thread, L2 prefetch of the next tile, and the watch-and-yield kernel built "fat": it also
-      // contains the (never taken) general path, which raises ptxas's register target from 56 to 117 -- with that budget it
-      // hoists every load of a tile above the first accumulate and the kernel runs 3 % faster (0.646 vs 0.665 ms on SF10).
-      q1.direct_yield = agg_update_kernel<Q1, 8, true, true, true>;
-      if (v && strcmp(v, "8p") == 0) { q1.direct_yield = agg_update_kernel<Q1, 8, true, true>; q1.name = "static:q1_partial/8p"; }
-      if (v && strcmp(v, "8") == 0) {
-        q1.direct = agg_update_kernel<Q1, 8, false>; q1.direct_yield = agg_update_kernel<Q1, 8, false, true>; q1.name = "static:q1_partial/8";
-      }
+      KernelChoice q1{agg_update_kernel<Q1, 8, true>, agg_update_staged_kernel<Q1, ITEMS_STAGED>, 8, "static:q1_partial/4"};
+      default_chain<Q1, 4, false>(q1);
+      auto single = [&](AggKernel k, int items, const char *name) { q1.k1 = k; q1.k2 = nullptr; q1.k1_wide = nullptr; q1.k1_dict = 8; q1.k1_items = items; q1.name = name; };
+      if (v && strcmp(v, "8pf") == 0) single(agg_update_kernel<Q1, 8, true, AGG_MODE_YIELD, true, 8>, 8, "static:q1_partial/8pf");
+      if (v && strcmp(v, "8p") == 0) single(agg_update_kernel<Q1, 8, true, AGG_MODE_YIELD, false, 8>, 8, "static:q1_partial/8p");
+      if (v && strcmp(v, "8") == 0) single(agg_update_kernel<Q1, 8, false, AGG_MODE_YIELD, false, 8>, 8, "static:q1_partial/8");
       if (v && strcmp(v, "4p") == 0) {
-        q1.direct = agg_update_kernel<Q1, 4, true>; q1.direct_yield = agg_update_kernel<Q1, 4, true, true>; q1.items_direct = 4;
+        default_chain<Q1, 4, true>(q1);
         q1.name = "static:q1_partial/4p";
-      }
-      if (v && strcmp(v, "4") == 0) {
-        q1.direct = agg_update_kernel<Q1, 4, false>; q1.direct_yield = agg_update_kernel<Q1, 4, false, true>; q1.items_direct = 4;
-        q1.name = "static:q1_partial/4";
       }
       return q1;
     }
-    if (memcmp(&m, &kHostMetaC1I64, sizeof(PlanMeta)) == 0)
-      return {agg_update_kernel<StaticPlan<&kDevMetaC1I64>, ITEMS_DIRECT>, agg_update_staged_kernel<StaticPlan<&kDevMetaC1I64>, ITEMS_STAGED>,
-              ITEMS_DIRECT, "static:groupby_i64_sum_i64", agg_update_smem_kernel<StaticPlan<&kDevMetaC1I64>, ITEMS_SMEM>,
-              agg_update_kernel<StaticPlan<&kDevMetaC1I64>, ITEMS_DIRECT, false, true>};
-    if (memcmp(&m, &kHostMetaC1F64, sizeof(PlanMeta)) == 0)
-      return {agg_update_kernel<StaticPlan<&kDevMetaC1F64>, ITEMS_DIRECT>, agg_update_staged_kernel<StaticPlan<&kDevMetaC1F64>, ITEMS_STAGED>,
-              ITEMS_DIRECT, "static:groupby_i64_sum_f64", agg_update_smem_kernel<StaticPlan<&kDevMetaC1F64>, ITEMS_SMEM>,
-              agg_update_kernel<StaticPlan<&kDevMetaC1F64>, ITEMS_DIRECT, false, true>};
+    if (memcmp(&m, &kHostMetaC1I64, sizeof(PlanMeta)) == 0) {
+      using C1 = StaticPlan<&kDevMetaC1I64>;
+      KernelChoice kc{agg_update_kernel<C1, ITEMS_DIRECT>, agg_update_staged_kernel<C1, ITEMS_STAGED>, ITEMS_DIRECT, "static:groupby_i64_sum_i64",
+                      agg_update_smem_kernel<C1, ITEMS_SMEM>};
+      default_chain<C1, ITEMS_DIRECT, false>(kc);
+      return kc;
+    }
+    if (memcmp(&m, &kHostMetaC1F64, sizeof(PlanMeta)) == 0) {
+      using C1 = StaticPlan<&kDevMetaC1F64>;
+      KernelChoice kc{agg_update_kernel<C1, ITEMS_DIRECT>, agg_update_staged_kernel<C1, ITEMS_STAGED>, ITEMS_DIRECT, "static:groupby_i64_sum_f64",
+                      agg_update_smem_kernel<C1, ITEMS_SMEM>};
+      default_chain<C1, ITEMS_DIRECT, false>(kc);
+      return kc;
+    }
   }
-  return {agg_update_kernel<DynPlan, ITEMS_DIRECT>, agg_update_staged_kernel<DynPlan, ITEMS_STAGED>, ITEMS_DIRECT, "dynamic"};
+  KernelChoice kc{agg_update_kernel<DynPlan, ITEMS_DIRECT>, agg_update_staged_kernel<DynPlan, ITEMS_STAGED>, ITEMS_DIRECT, "dynamic"};
+  default_chain<DynPlan, ITEMS_DIRECT, false>(kc);
+  return kc;
 }
 
 __global__ void occupied_kernel(const uint64_t *__restrict__ tkeys, int64_t cap, const int32_t *__restrict__ flags,
@@ -699,11 +710,34 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
   const size_t smem_acc = (size_t)(AGG_DICT + (size_t)(AGG_DICT + 1) * ns * AGG_THREADS) * 8;   // dictionary + accumulators
   SB_REQUIRE(smem_acc <= 200 * 1024, "aggregate needs %zu bytes of shared memory", smem_acc);
   SB_CUDA(cudaFuncSetAttribute(kc.direct, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  SB_CUDA(cudaFuncSetAttribute(kc.direct_yield, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  int blocks_per_sm = (int)((228 * 1024) / (smem_acc + 1024));
-  if (blocks_per_sm < 1) blocks_per_sm = 1;
-  if (blocks_per_sm > 8) blocks_per_sm = 8;
+  auto dict_smem = [&](int d) { return (size_t)(d + (size_t)(d + 1) * ns * AGG_THREADS) * 8; };
+  auto dict_blocks_per_sm = [&](int d) {
+    int b = (int)((228 * 1024) / (dict_smem(d) + 1024));
+    return b < 1 ? 1 : (b > 8 ? 8 : b);
+  };
+  // persistent grids are sized from the kernel's REAL residency (registers may allow fewer blocks than shared memory does: a
+  // grid of 8 blocks per SM over a kernel that fits 6 runs a second, mostly idle wave)
+  auto resident_blocks = [&](AggKernel k, size_t smem, int upper) {
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, AGG_THREADS, smem) != cudaSuccess || nb < 1) {
+      cudaGetLastError();
+      nb = 1;
+    }
+    return nb < upper ? nb : upper;
+  };
+  int blocks_per_sm = resident_blocks(kc.direct, smem_acc, dict_blocks_per_sm(AGG_DICT));
   int grid = grid_for(n, AGG_THREADS * kc.items_direct, rt().num_sms * blocks_per_sm);
+  // the automatic chain's geometry (k1 defines the tiles; k2 walks k1's tiles with fewer, fatter blocks)
+  if (kc.k1_wide && dict_blocks_per_sm(8) == dict_blocks_per_sm(4)) {   // few slots: the 8-entry dictionary is free, skip a level
+    kc.k1 = kc.k1_wide;
+    kc.k2 = nullptr;
+    kc.k1_dict = 8;
+  }
+  const size_t smem_k1 = dict_smem(kc.k1_dict), smem_k2 = dict_smem(8);
+  SB_CUDA(cudaFuncSetAttribute(kc.k1, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  if (kc.k2) SB_CUDA(cudaFuncSetAttribute(kc.k2, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  const int grid_k1 = grid_for(n, AGG_THREADS * kc.k1_items, rt().num_sms * resident_blocks(kc.k1, smem_k1, dict_blocks_per_sm(kc.k1_dict)));
+  const int grid_k2 = kc.k2 ? std::min(grid_k1, rt().num_sms * resident_blocks(kc.k2, smem_k2, dict_blocks_per_sm(8))) : 0;
   // ---- tiers: "dict" (lane-private dictionary + HBM table), "smem" (shared-memory table + HBM table), or "auto": the
   // dictionary kernel starts, yields as soon as the input turns out not to be a few-groups shape, and the shared-memory kernel
   // launched behind it finishes the job (AggArgs::gate) -- no sample pass, no host round trip.
@@ -771,7 +805,7 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
     } else staged = false;
   }
 
-  Scratch flags(32, st), progress((int64_t)grid * (AGG_THREADS / 32) * 4 + 16, st);
+  Scratch flags(32, st), progress((int64_t)grid_k1 * (AGG_THREADS / 32) * 4 + 16, st), progress2((int64_t)grid_k1 * (AGG_THREADS / 32) * 4 + 16, st);
   std::unique_ptr<Scratch> slot_ids_buf;
   int64_t ngroups = 0;
   void *tkeys = nullptr, *tacc = nullptr;
@@ -807,10 +841,16 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
       else if (a.nwords == 1) {
         a.gate = 1;
         a.progress = progress.as<int32_t>();
-        a.dict_grid = grid;
-        a.dict_items = kc.items_direct;
-        kc.direct_yield<<<grid, AGG_THREADS, smem_acc, st>>>(a);
+        a.progress2 = kc.k2 ? progress2.as<int32_t>() : progress.as<int32_t>();
+        a.last_flag = kc.k2 ? 7 : 6;
+        a.dict_grid = grid_k1;
+        a.dict_items = kc.k1_items;
+        kc.k1<<<grid_k1, AGG_THREADS, smem_k1, st>>>(a);
         SB_LAUNCH_CHECK();
+        if (kc.k2) {
+          kc.k2<<<grid_k2, AGG_THREADS, smem_k2, st>>>(a);
+          SB_LAUNCH_CHECK();
+        }
         a.gate = 2;
         kc.smem<<<grid_smem, AGGS_THREADS, smem_tab, st>>>(a);
       }

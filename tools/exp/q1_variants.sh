@@ -1,4 +1,4 @@
-for v in 8p 16p 8pf; do
+for v in 4p 4 8pf; do
   echo "== $v"
   SB_AGG_Q1_VARIANT=$v timeout 200 python bench.py --steps 100 2>/dev/null | tail -1 | python -c "
 import sys,json
