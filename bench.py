@@ -328,8 +328,8 @@ def main():
                              "frac": achieved / peak, "frac_of_8tbs_nominal": achieved / 8000.0, "peak_source": peak_src,
                              "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes,
                              # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel at SF10 (ncu --set full,
-                             # profiles/r01_agg_update.md): 2.4115 GB + 3.8 MB; reported only for the configuration it was captured on
-                             "traffic": 2439818624 if n == Q1_ROWS_SF10 else None},
+                             # profiles/r01_agg_update_final_ncu.txt): 2.2796 GB + 3.3 MB; reported only for the configuration it was captured on
+                             "traffic": 2282970560 if n == Q1_ROWS_SF10 else None},
                 "cpu_baseline": cpu,
                 "e2e": {"value": e2e_value, "unit": "rows/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": alg_bytes,
                         "d2h_bytes_per_step": d2h},

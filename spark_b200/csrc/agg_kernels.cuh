@@ -743,9 +743,15 @@ __global__ void __launch_bounds__(AGG_THREADS) agg_update_kernel(const __grid_co
   if constexpr (MODE == AGG_MODE_TAKEOVER) {
     const int w = tid >> 5, lane = tid & 31;
     constexpr int NW = AGG_THREADS / 32;
+    __shared__ int next_b;
     bool yielded = false;
-    for (int64_t b = blockIdx.x; b < a.dict_grid; b += gridDim.x) {   // the first kernel's block b, this warp's slice of its tiles
-      int64_t j = a.progress[b * NW + w];
+    for (;;) {   // the first kernel's blocks are handed out dynamically (its grid is not a multiple of ours)
+      if (tid == 0) next_b = atomicAdd(&a.flags[3], 1);
+      __syncthreads();
+      const int64_t b = next_b;
+      __syncthreads();
+      if (b >= a.dict_grid) break;
+      int64_t j = a.progress[b * NW + w];   // this warp's slice of block b's tiles j, j + 1, ...
       if (!yielded) {
         for (;; j++) {
           const int64_t base = (b + j * a.dict_grid) * TILE;
@@ -953,15 +959,19 @@ __global__ void __launch_bounds__(AGGS_THREADS) agg_update_smem_kernel(const __g
     if (base + TILE <= a.n) process_tile_smem<P, ITEMS, true>(a, t, skeys, sacc, sctl, stride);
     else process_tile_smem<P, ITEMS, false>(a, t, skeys, sacc, sctl, stride);
   };
-  if (a.gate == 2) {   // the tiles the dictionary kernel's blocks left behind (its tile = dict_items / ITEMS of ours)
+  if (a.gate == 2) {   // the tiles the dictionary kernels left behind (their tile = dict_items / ITEMS of ours)
+    // every sub-block walks ALL dictionary tiles in its own strided order and skips, warp by warp, what is already done: the
+    // work stays balanced whatever the dictionary kernels' grid was
     const int64_t dtile = (int64_t)AGG_THREADS * a.dict_items;
+    const int64_t ndtiles = (a.n + dtile - 1) / dtile;
     const int w = tid >> 5;
-    for (int64_t b = vb; b < a.dict_grid; b += nvb)
-      for (int64_t j = a.progress2[b * (AGG_THREADS / 32) + w];; j++) {   // this warp's slice of dict block b's tiles j, j+1, ...
-        const int64_t base0 = (b + j * a.dict_grid) * dtile;
-        if (base0 >= a.n || *(volatile int32_t *)a.flags) break;
-        for (int64_t base = base0; base < base0 + dtile && base < a.n; base += TILE) one_tile(base);
-      }
+    for (int64_t t = vb; t < ndtiles; t += nvb) {
+      if (*(volatile int32_t *)a.flags) break;
+      const int64_t b = t % a.dict_grid, j = t / a.dict_grid;
+      if (j < a.progress2[b * (AGG_THREADS / 32) + w]) continue;
+      const int64_t base0 = t * dtile;
+      for (int64_t base = base0; base < base0 + dtile && base < a.n; base += TILE) one_tile(base);
+    }
   } else {
     for (int64_t base = vb * TILE; base < a.n; base += nvb * TILE) {
       if (*(volatile int32_t *)a.flags) break;
