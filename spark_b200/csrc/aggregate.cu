@@ -709,7 +709,7 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
   KernelChoice kc = choose_kernels(m);
   const size_t smem_acc = (size_t)(AGG_DICT + (size_t)(AGG_DICT + 1) * ns * AGG_THREADS) * 8;   // dictionary + accumulators
   SB_REQUIRE(smem_acc <= 200 * 1024, "aggregate needs %zu bytes of shared memory", smem_acc);
-  SB_CUDA(cudaFuncSetAttribute(kc.direct, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  SB_CUDA(cudaFuncSetAttribute(kc.direct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_acc));
   auto dict_smem = [&](int d) { return (size_t)(d + (size_t)(d + 1) * ns * AGG_THREADS) * 8; };
   auto dict_blocks_per_sm = [&](int d) {
     int b = (int)((228 * 1024) / (dict_smem(d) + 1024));
@@ -734,8 +734,8 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
     kc.k1_dict = 8;
   }
   const size_t smem_k1 = dict_smem(kc.k1_dict), smem_k2 = dict_smem(8);
-  SB_CUDA(cudaFuncSetAttribute(kc.k1, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  if (kc.k2) SB_CUDA(cudaFuncSetAttribute(kc.k2, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  SB_CUDA(cudaFuncSetAttribute(kc.k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_k1));
+  if (kc.k2) SB_CUDA(cudaFuncSetAttribute(kc.k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_k2));
   const int grid_k1 = grid_for(n, AGG_THREADS * kc.k1_items, rt().num_sms * resident_blocks(kc.k1, smem_k1, dict_blocks_per_sm(kc.k1_dict)));
   const int grid_k2 = kc.k2 ? std::min(grid_k1, rt().num_sms * resident_blocks(kc.k2, smem_k2, dict_blocks_per_sm(8))) : 0;
   // ---- tiers: "dict" (lane-private dictionary + HBM table), "smem" (shared-memory table + HBM table), or "auto": the
