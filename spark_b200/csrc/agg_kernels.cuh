@@ -86,6 +86,7 @@ struct AggArgs {
   int32_t *progress2;    // same shape, left by the second dictionary kernel (which works on the first one's tile geometry)
   int32_t dict_grid, dict_items;
   int32_t last_flag;     // index in flags of the yield flag of the LAST dictionary kernel of the chain (6 or 7)
+  int32_t start_bypassed;   // shared-memory kernel: do not use the shared-memory table at all (tiny inputs: latency, not bandwidth)
   int32_t combine;       // shared-memory tier: combine same-entry rows of a warp before the atomics
 };
 
@@ -948,7 +949,7 @@ __global__ void __launch_bounds__(AGGS_THREADS) agg_update_smem_kernel(const __g
     skeys[i] = EMPTY_KEY;
     for (int s = 0; s < ns; s++) sacc[(size_t)s * (C + 2) + i] = slot_identity(m.slot_kind[s]);
   }
-  if (threadIdx.x < CTL_WORDS) sctl[threadIdx.x] = 0;
+  if (threadIdx.x < CTL_WORDS) sctl[threadIdx.x] = (threadIdx.x == CTL_BYPASS && a.start_bypassed) ? 1u : 0u;
   __syncthreads();
   constexpr int64_t TILE = (int64_t)AGG_THREADS * ITEMS;
   const int64_t stride = a.cap + 2;

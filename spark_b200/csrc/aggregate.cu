@@ -747,6 +747,14 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
   else if (tier_env && !strcmp(tier_env, "smem")) tier = 2;
   int32_t scap = 8192;
   while (scap > 512 && (size_t)(scap + 2) * (1 + ns) * 8 + 64 > 200 * 1024) scap >>= 1;
+  // tiny inputs (the Final stage of a few-group aggregate: a handful of rows) are pure latency: one block, rows straight into
+  // the HBM table -- no dictionary to initialise and merge, no chain of launches
+  const bool tiny = tier == 0 && n <= AGG_THREADS * ITEMS_SMEM * AGGS_SUB;
+  if (tiny) {
+    tier = 2;
+    scap = 512;
+  }
+  a.start_bypassed = tiny ? 1 : 0;
   if (tier == 0 && plan->expected_groups > 0)   // the caller knows: few -> dictionary, else the shared-memory kernel (which bypasses its table when the hit rate is poor)
     tier = plan->expected_groups <= AGG_DICT ? 1 : 2;
   const size_t smem_tab = (size_t)(scap + 2) * (1 + ns) * 8 + 64;
