@@ -500,7 +500,7 @@ __device__ __forceinline__ void accumulate_slots_dict(const AggArgs &a, const Ti
   });
 }
 
-// Shared memory of the update kernels: uint64 dict_keys[AGG_DICT]; uint64 acc[(AGG_DICT + 1) * nslots][AGG_THREADS]
+// Shared memory of the update kernels: uint64 dict_keys[D]; uint64 fill; uint64 acc[(D + 1) * nslots][AGG_THREADS]
 // (last group = trash); the staged kernel puts the column stages and the mbarriers in front.
 // keep / packed group key / special-slot class of the thread's rows
 template <class P, int ITEMS, bool FULL, bool STAGED>
@@ -585,9 +585,13 @@ __device__ __forceinline__ bool process_tile(const AggArgs &a, const TileCtx &t,
   // The dictionary's keys are compared in REGISTERS: D shared-memory loads per tile instead of a hashed probe loop per row.  A
   // row that matches none of the cached keys takes the slow path (linear probing with an atomicCAS claim, which also finds
   // entries other warps inserted since the snapshot) and refreshes the snapshot.
-  uint64_t dk[D];
+  constexpr bool SNAPSHOT = D <= 8;        // larger dictionaries (light plans only) are probed by hash: 2 x D registers is too many
+  constexpr int DS = SNAPSHOT ? D : 1;
+  uint64_t dk[DS];
+  if constexpr (SNAPSHOT) {
 #pragma unroll
-  for (int i = 0; i < D; i++) dk[i] = *(volatile uint64_t *)&dict_keys[i];
+    for (int i = 0; i < DS; i++) dk[i] = *(volatile uint64_t *)&dict_keys[i];
+  }
 #pragma unroll
   for (int k = 0; k < ITEMS; k++) {
     dst[k] = -1;
@@ -596,24 +600,35 @@ __device__ __forceinline__ bool process_tile(const AggArgs &a, const TileCtx &t,
     if (YIELD && !all_dict) continue;   // this warp is going to yield: no point in resolving the rest of its rows
     int gid = -1;
     if (special[k] == 0) {
+      if constexpr (SNAPSHOT) {
 #pragma unroll
-      for (int i = 0; i < D; i++) gid = dk[i] == key[k] ? i : gid;
+        for (int i = 0; i < DS; i++) gid = dk[i] == key[k] ? i : gid;
+      }
       if (gid < 0) {
         constexpr int LOG_D = D == 4 ? 2 : (D == 8 ? 3 : (D == 16 ? 4 : 5));
         static_assert(D == 4 || D == 8 || D == 16 || D == 32, "dictionary sizes are powers of two");
         const uint32_t h0 = ((uint32_t)key[k] ^ (uint32_t)(key[k] >> 32)) * 0x9E3779B1u >> (32 - LOG_D);
+        // a hash-probed dictionary gives up after 8 steps (inserts obey the same window, so lookups stay exact): near-full
+        // tables would otherwise cost tens of probes per row -- with 32 keys in 32 entries the kernel ran 4x slower than the
+        // shared-memory tier it is meant to beat
+        constexpr int PROBES = D <= 8 ? D : 8;
 #pragma unroll 1
-        for (int i = 0; i < D; i++) {
+        for (int i = 0; i < PROBES; i++) {
           const int g = (h0 + i) & (D - 1);
           uint64_t cur = *(volatile uint64_t *)&dict_keys[g];
           if (cur == EMPTY_KEY) {
+            // measured: a 32-entry dictionary holding 26+ keys runs 1.5-4x slower than the shared-memory tier; it stops at 20
+            if (!SNAPSHOT && *(volatile uint64_t *)&dict_keys[D] >= (uint64_t)(D * 5 / 8)) break;
             uint64_t old = atomicCAS((unsigned long long *)&dict_keys[g], (unsigned long long)EMPTY_KEY, (unsigned long long)key[k]);
+            if (old == EMPTY_KEY && !SNAPSHOT) atomicAdd((unsigned long long *)&dict_keys[D], 1ull);
             cur = old == EMPTY_KEY ? key[k] : old;
           }
           if (cur == key[k]) { gid = g; break; }
         }
+        if constexpr (SNAPSHOT) {
 #pragma unroll
-        for (int i = 0; i < D; i++) dk[i] = *(volatile uint64_t *)&dict_keys[i];
+          for (int i = 0; i < DS; i++) dk[i] = *(volatile uint64_t *)&dict_keys[i];
+        }
       }
     }
     if (gid >= 0) doff[k] = gid * ns * AGG_THREADS + tid;
@@ -644,6 +659,7 @@ __device__ __forceinline__ void dict_init(const AggArgs &a, uint64_t *dict_keys,
   const PlanMeta &m = P::meta(a);
   const int ns = m.nslots;
   if (tid < D) dict_keys[tid] = EMPTY_KEY;
+  if (tid == 0) dict_keys[D] = 0;   // number of keys inserted (hash-probed dictionaries stop inserting at 5/8 load)
   for (int s = 0; s < ns; s++) {
     uint64_t id = slot_identity(m.slot_kind[s]);
     for (int g = 0; g <= D; g++) acc[(g * ns + s) * AGG_THREADS + tid] = id;
@@ -710,7 +726,7 @@ template <class P, int ITEMS, bool PREFETCH = false, int MODE = AGG_MODE_PLAIN, 
 __global__ void __launch_bounds__(AGG_THREADS) agg_update_kernel(const __grid_constant__ AggArgs a) {
   extern __shared__ __align__(128) uint64_t sm_direct[];
   uint64_t *dict_keys = sm_direct;
-  uint64_t *acc = sm_direct + D;
+  uint64_t *acc = sm_direct + D + 1;   // [D] keys, one fill counter, accumulators
   const int tid = threadIdx.x;
   if (MODE == AGG_MODE_TAKEOVER && *(volatile int32_t *)&a.flags[6] == 0) return;   // the first kernel finished the job
   dict_init<P, D>(a, dict_keys, acc, tid);
@@ -1020,7 +1036,7 @@ __global__ void __launch_bounds__(AGG_THREADS) agg_update_staged_kernel(const __
   uint8_t *stages = sm_staged;
   uint64_t *bars = (uint64_t *)(sm_staged + (size_t)S * a.stage_bytes);
   uint64_t *dict_keys = bars + 8;
-  uint64_t *acc = dict_keys + AGG_DICT;
+  uint64_t *acc = dict_keys + AGG_DICT + 1;
   const int tid = threadIdx.x;
   const int64_t stride = a.cap + 2;
   const int64_t full_tiles = a.n / TILE;

@@ -87,13 +87,16 @@ struct KernelChoice {
   // entries, same tile geometry) takes over and yields in turn, smem finishes
   AggKernel k1 = nullptr, k2 = nullptr;
   int k1_dict = 4, k1_items = ITEMS_DIRECT;
-  AggKernel k1_wide = nullptr;        // 8-entry watch-and-yield kernel: the whole dictionary tier when 8 entries cost no occupancy
+  AggKernel k1_wide = nullptr;        // 8-entry watch-and-yield kernel: the first level when 8 entries cost no occupancy ...
+  AggKernel k2_big = nullptr;         // ... followed by a 32-entry (hash-probed) take-over kernel: light plans with 9..32 groups
+  int k2_dict = 8;
 };
 template <class P, int ITEMS, bool PREFETCH>
 static void default_chain(KernelChoice &kc) {
   kc.k1 = agg_update_kernel<P, ITEMS, PREFETCH, AGG_MODE_YIELD, false, 4>;
   kc.k2 = agg_update_kernel<P, ITEMS, PREFETCH, AGG_MODE_TAKEOVER, false, 8>;
   kc.k1_wide = agg_update_kernel<P, ITEMS, PREFETCH, AGG_MODE_YIELD, false, 8>;
+  kc.k2_big = agg_update_kernel<P, ITEMS, PREFETCH, AGG_MODE_TAKEOVER, false, 32>;
   kc.k1_dict = 4;
   kc.k1_items = ITEMS;
 }
@@ -107,7 +110,7 @@ static KernelChoice choose_kernels(const PlanMeta &m) {
       using Q1 = StaticPlan<&kDevMetaQ1Partial>;
       KernelChoice q1{agg_update_kernel<Q1, 8, true>, agg_update_staged_kernel<Q1, ITEMS_STAGED>, 8, "static:q1_partial/4"};
       default_chain<Q1, 4, false>(q1);
-      auto single = [&](AggKernel k, int items, const char *name) { q1.k1 = k; q1.k2 = nullptr; q1.k1_wide = nullptr; q1.k1_dict = 8; q1.k1_items = items; q1.name = name; };
+      auto single = [&](AggKernel k, int items, const char *name) { q1.k1 = k; q1.k2 = nullptr; q1.k1_wide = nullptr; q1.k2_big = nullptr; q1.k1_dict = 8; q1.k1_items = items; q1.name = name; };
       if (v && strcmp(v, "8pf") == 0) single(agg_update_kernel<Q1, 8, true, AGG_MODE_YIELD, true, 8>, 8, "static:q1_partial/8pf");
       if (v && strcmp(v, "8p") == 0) single(agg_update_kernel<Q1, 8, true, AGG_MODE_YIELD, false, 8>, 8, "static:q1_partial/8p");
       if (v && strcmp(v, "8") == 0) single(agg_update_kernel<Q1, 8, false, AGG_MODE_YIELD, false, 8>, 8, "static:q1_partial/8");
@@ -707,10 +710,10 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
   if (cap < 1024) cap = 1024;
   if (cap > cap_max) cap = cap_max;
   KernelChoice kc = choose_kernels(m);
-  const size_t smem_acc = (size_t)(AGG_DICT + (size_t)(AGG_DICT + 1) * ns * AGG_THREADS) * 8;   // dictionary + accumulators
+  const size_t smem_acc = (size_t)(AGG_DICT + 1 + (size_t)(AGG_DICT + 1) * ns * AGG_THREADS) * 8;   // dictionary + fill counter + accumulators
   SB_REQUIRE(smem_acc <= 200 * 1024, "aggregate needs %zu bytes of shared memory", smem_acc);
   SB_CUDA(cudaFuncSetAttribute(kc.direct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_acc));
-  auto dict_smem = [&](int d) { return (size_t)(d + (size_t)(d + 1) * ns * AGG_THREADS) * 8; };
+  auto dict_smem = [&](int d) { return (size_t)(d + 1 + (size_t)(d + 1) * ns * AGG_THREADS) * 8; };
   auto dict_blocks_per_sm = [&](int d) {
     int b = (int)((228 * 1024) / (dict_smem(d) + 1024));
     return b < 1 ? 1 : (b > 8 ? 8 : b);
@@ -728,16 +731,20 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
   int blocks_per_sm = resident_blocks(kc.direct, smem_acc, dict_blocks_per_sm(AGG_DICT));
   int grid = grid_for(n, AGG_THREADS * kc.items_direct, rt().num_sms * blocks_per_sm);
   // the automatic chain's geometry (k1 defines the tiles; k2 walks k1's tiles with fewer, fatter blocks)
-  if (kc.k1_wide && dict_blocks_per_sm(8) == dict_blocks_per_sm(4)) {   // few slots: the 8-entry dictionary is free, skip a level
-    kc.k1 = kc.k1_wide;
-    kc.k2 = nullptr;
-    kc.k1_dict = 8;
+  if (kc.k1_wide && dict_blocks_per_sm(8) == dict_blocks_per_sm(4)) {   // light plan: the 8-entry dictionary costs no occupancy, so
+    kc.k1 = kc.k1_wide;                                                 // it goes first and a 32-entry one (if it keeps >= 4
+    kc.k1_dict = 8;                                                     // blocks per SM) catches 9..32 groups before the
+    kc.k2 = nullptr;                                                    // shared-memory tier and its atomics
+    if (kc.k2_big && dict_blocks_per_sm(32) >= 4) {
+      kc.k2 = kc.k2_big;
+      kc.k2_dict = 32;
+    }
   }
-  const size_t smem_k1 = dict_smem(kc.k1_dict), smem_k2 = dict_smem(8);
+  const size_t smem_k1 = dict_smem(kc.k1_dict), smem_k2 = dict_smem(kc.k2_dict);
   SB_CUDA(cudaFuncSetAttribute(kc.k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_k1));
   if (kc.k2) SB_CUDA(cudaFuncSetAttribute(kc.k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_k2));
   const int grid_k1 = grid_for(n, AGG_THREADS * kc.k1_items, rt().num_sms * resident_blocks(kc.k1, smem_k1, dict_blocks_per_sm(kc.k1_dict)));
-  const int grid_k2 = kc.k2 ? std::min(grid_k1, rt().num_sms * resident_blocks(kc.k2, smem_k2, dict_blocks_per_sm(8))) : 0;
+  const int grid_k2 = kc.k2 ? std::min(grid_k1, rt().num_sms * resident_blocks(kc.k2, smem_k2, dict_blocks_per_sm(kc.k2_dict))) : 0;
   // ---- tiers: "dict" (lane-private dictionary + HBM table), "smem" (shared-memory table + HBM table), or "auto": the
   // dictionary kernel starts, yields as soon as the input turns out not to be a few-groups shape, and the shared-memory kernel
   // launched behind it finishes the job (AggArgs::gate) -- no sample pass, no host round trip.

@@ -253,7 +253,7 @@ def test_cardinality_tiers_agree_with_the_oracle(gpu, stream, groups, tier, monk
     assert_tables_equal(got, want, key_cols=["k"])
 
 
-@pytest.mark.parametrize("groups", [3, 1024])
+@pytest.mark.parametrize("groups", [3, 20, 1024])
 @pytest.mark.parametrize("vtype", ["i64", "f64"])
 def test_groupby_sum_static_shapes_through_both_tiers(gpu, stream, groups, vtype):
     """BASELINE configs[0] shape (k int64, v int64/double, no NULLs): the plan-specialised kernels of both tiers."""
