@@ -927,17 +927,24 @@ __device__ __forceinline__ void process_tile_smem(const AggArgs &a, const TileCt
     uint64_t *gacc = a.tacc + (int64_t)s * stride;
     const int kind = m.slot_kind[s];
     if (heavy && kind != K_ADD_I64) {
+      // every lane walks the OTHER members of its entry's group, lowest lane first; the trip count is the largest group of
+      // the warp (uniform, so the shuffles stay convergent) -- a fixed 32-step loop cost 2500 thread-instructions per row
       const uint64_t ident = slot_identity(kind);
 #pragma unroll
       for (int k = 0; k < ITEMS; k++) {
         const uint64_t x = ok[k] ? v[k] : ident;
-        const bool leader = (grp[k] & lanemask_lt()) == 0;
+        uint32_t m = grp[k] & ~(1u << lane);
+        const int trips = __reduce_max_sync(0xffffffffu, __popc(m));
         uint64_t acc = x;
-#pragma unroll 4
-        for (int i = 0; i < 32; i++) {
-          const uint64_t o = __shfl_sync(0xffffffffu, x, i);
-          if (leader && i != lane && ((grp[k] >> i) & 1)) acc = apply_op(kind, acc, o);
+#pragma unroll 1
+        for (int t = 0; t < trips; t++) {
+          const bool more = m != 0;
+          const int src = more ? __ffs(m) - 1 : lane;
+          m &= m - 1;
+          const uint64_t o = __shfl_sync(0xffffffffu, x, src);
+          if (more) acc = apply_op(kind, acc, o);
         }
+        const bool leader = (grp[k] & lanemask_lt()) == 0;
         v[k] = acc;
         ok[k] = leader && (dst[k] >= 0 || soff[k] >= 0);
       }
