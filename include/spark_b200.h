@@ -223,7 +223,8 @@ typedef struct sb_agg_plan {
   int32_t pad;
   const sb_agg_spec *aggs;
   const sb_expr *filter;       /* fused FilterExec predicate or NULL */
-  int64_t expected_groups;     /* sizing hint (0 = unknown) */
+  int64_t expected_groups;     /* hint, 0 = unknown (the usual case: the engine finds the right tier by itself); > 0 sizes the
+                                  hash table and picks the tier directly (<= 8: dictionary, else shared-memory / HBM table) */
 } sb_agg_plan;
 
 /* Output: key columns, then per aggregate either its buffer columns (Partial: sum -> [sum];

@@ -16,10 +16,12 @@
 //     TPC-H style price*(1-disc)*(1+tax) arithmetic; anything else is materialised first by expr.cu);
 //   * group keys packed into one 64-bit word (fixed-width columns + null bits, or one raw 64-bit
 //     column with reserved slots for NULL and for the EMPTY sentinel value);
-//   * tier 1: a per-block dictionary of the first 8 distinct keys with LANE-PRIVATE shared-memory
-//     accumulators (no atomics, no bank conflicts) -- this is what makes 4-group aggregates (Q1) run
-//     at memory speed; tier 2: open-addressing table in HBM (linear probing, atomicCAS on the key word,
-//     RED/ATOM on the accumulators);
+//   * three tiers, picked on the device by a chain of kernels that yield to one another (agg_kernels.cuh):
+//     tier 1: per-block dictionary of the first 4 / 8 (light plans: 32) distinct keys with LANE-PRIVATE
+//     shared-memory accumulators (no atomics, no bank conflicts) and the keys compared in registers -- this is
+//     what makes 4-group aggregates (Q1) run at memory speed; tier 2: per-SM open-addressing table in shared
+//     memory (hundreds to thousands of groups); tier 3: open-addressing table in HBM (linear probing,
+//     atomicCAS on the key word, RED on the accumulators);
 //   * identical accumulator slots are de-duplicated (sum(x) and avg(x) share their sum; count(*) and the
 //     counts of non-nullable averages share one counter).
 // Floating SUM/AVG are order-dependent in the reference too (partials merge in fetch order); parity is

@@ -1,4 +1,5 @@
-// comm.cu -- the exchange between executors (one process per GPU): NCCL over NVLink 5 / NVSwitch.
+// comm.cu -- the exchange between executors (one process per GPU) over NVLink 5 / NVSwitch: copy engines push bucket slices
+// into peer-mapped receive windows (CUDA IPC), NCCL carries the control messages and is the fallback data path.
 //
 // Replaces, for this path only, the reference's shuffle transport: SortShuffleManager writers ->
 // local disk -> Netty fetch (core/src/main/scala/org/apache/spark/shuffle/sort/SortShuffleManager.scala:70,

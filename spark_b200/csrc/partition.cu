@@ -105,7 +105,9 @@ constexpr int SCATTER_MAX_COLS = 16;
 // generalised to any set of fixed-width columns).  At most RG_MAX_NB buckets per pass; larger fan-outs run two passes
 // (low digit, then high digit -- "LSB radix partition").
 //
-// A block owns a contiguous chunk of rows and walks it in tiles of RG_TILE rows.  Per tile:
+// This first kernel is the load/store version: it is what runs when a source column is not 16-byte aligned (the copy engine
+// needs that) or with SB_REGROUP_PATH=ldst; the default is regroup_tma_kernel further down, which shares phases A-D.
+// A block owns a chunk of rows (one histogram column) and walks it in tiles of RGL_TILE rows.  Per tile:
 //   A  every warp owns a contiguous 1/16 of the tile and walks it 32 rows at a time: same-bucket rows are ranked with
 //      __match_any_sync + popcount on top of a per-warp shared-memory counter  -> (bucket, rank inside the warp's segment);
 //   B  per bucket: exclusive prefix of the per-warp counts (order of the warps = order of the rows) and the tile total;
