@@ -114,4 +114,143 @@ JNIEXPORT jlong JNICALL Java_org_apache_spark_sql_b200_Native_joinProbe(JNIEnv *
   throw_if(env, rc);
   return (jlong)(intptr_t)out;
 }
-/* sort / topN / filterProject / allToAll / allGather / expr* follow the same pattern (arrays in, one sb_* call, throw_if). */
+
+/* ---- the rest of Native.java, same pattern: arrays in, one sb_* call, throw_if ------------------------------------------------- */
+#define NATIVE(ret, name) JNIEXPORT ret JNICALL Java_org_apache_spark_sql_b200_Native_##name
+#define TBL(x) ((sb_table *)(intptr_t)(x))
+#define STR(x) ((sb_stream *)(intptr_t)(x))
+
+NATIVE(void, shutdown)(JNIEnv *env, jclass c) { throw_if(env, sb_shutdown()); }
+
+NATIVE(jbyteArray, commGetUniqueId)(JNIEnv *env, jclass c) {
+  uint8_t id[SB_UNIQUE_ID_BYTES];
+  throw_if(env, sb_comm_get_unique_id(id));
+  jbyteArray out = (*env)->NewByteArray(env, SB_UNIQUE_ID_BYTES);
+  (*env)->SetByteArrayRegion(env, out, 0, SB_UNIQUE_ID_BYTES, (const jbyte *)id);
+  return out;
+}
+
+NATIVE(void, commInit)(JNIEnv *env, jclass c, jint rank, jint nranks, jbyteArray uniqueId) {
+  uint8_t id[SB_UNIQUE_ID_BYTES];
+  (*env)->GetByteArrayRegion(env, uniqueId, 0, SB_UNIQUE_ID_BYTES, (jbyte *)id);
+  throw_if(env, sb_comm_init(rank, nranks, id));
+}
+
+NATIVE(void, streamDestroy)(JNIEnv *env, jclass c, jlong stream) { throw_if(env, sb_stream_destroy(STR(stream))); }
+
+NATIVE(jlong, tableNumRows)(JNIEnv *env, jclass c, jlong table) {
+  int64_t n = 0;
+  throw_if(env, sb_table_num_rows(TBL(table), &n));
+  return (jlong)n;
+}
+
+/* D2H of one result column into buffers the JVM owns (OffHeapColumnVector / ArrowBuf addresses) */
+NATIVE(void, tableExportHost)(JNIEnv *env, jclass c, jlong table, jint column, jlong data, jlong validity, jlong offsets, jlong stream) {
+  int64_t nulls = 0;
+  throw_if(env, sb_table_export_host(TBL(table), column, (void *)(intptr_t)data, (uint8_t *)(intptr_t)validity,
+                                     (int32_t *)(intptr_t)offsets, &nulls, STR(stream)));
+}
+
+NATIVE(jlong, exprCreate)(JNIEnv *env, jclass c, jintArray ops, jintArray vtypes, jintArray args, jlongArray literals, jint outType) {
+  jsize n = (*env)->GetArrayLength(env, ops);
+  jint *o = (*env)->GetIntArrayElements(env, ops, NULL), *v = (*env)->GetIntArrayElements(env, vtypes, NULL);
+  jint *a = (*env)->GetIntArrayElements(env, args, NULL);
+  jlong *l = (*env)->GetLongArrayElements(env, literals, NULL);          /* doubles travel as their bit pattern */
+  sb_expr *e = (sb_expr *)malloc(sizeof(sb_expr));
+  sb_expr_node *nodes = (sb_expr_node *)calloc((size_t)(n ? n : 1), sizeof(sb_expr_node));
+  for (jsize i = 0; i < n; i++) {
+    nodes[i].op = o[i]; nodes[i].vtype = v[i]; nodes[i].arg = a[i]; nodes[i].lit.i = l[i];
+  }
+  e->nodes = nodes; e->n = n; e->out_type = outType;
+  (*env)->ReleaseIntArrayElements(env, ops, o, JNI_ABORT);
+  (*env)->ReleaseIntArrayElements(env, vtypes, v, JNI_ABORT);
+  (*env)->ReleaseIntArrayElements(env, args, a, JNI_ABORT);
+  (*env)->ReleaseLongArrayElements(env, literals, l, JNI_ABORT);
+  return (jlong)(intptr_t)e;
+}
+
+NATIVE(void, exprFree)(JNIEnv *env, jclass c, jlong expr) {
+  sb_expr *e = (sb_expr *)(intptr_t)expr;
+  if (e) {
+    free((void *)e->nodes);
+    free(e);
+  }
+}
+
+NATIVE(jlong, filterProject)(JNIEnv *env, jclass c, jlong table, jlong predicateExpr, jlongArray projectionExprs, jlong stream) {
+  jsize np = (*env)->GetArrayLength(env, projectionExprs);
+  jlong *p = (*env)->GetLongArrayElements(env, projectionExprs, NULL);
+  sb_expr *proj = (sb_expr *)calloc((size_t)(np ? np : 1), sizeof(sb_expr));
+  for (jsize i = 0; i < np; i++) proj[i] = *(const sb_expr *)(intptr_t)p[i];
+  sb_table *out = NULL;
+  int rc = sb_filter_project(TBL(table), (const sb_expr *)(intptr_t)predicateExpr, proj, np, STR(stream), &out);
+  free(proj);
+  (*env)->ReleaseLongArrayElements(env, projectionExprs, p, JNI_ABORT);
+  throw_if(env, rc);
+  return (jlong)(intptr_t)out;
+}
+
+NATIVE(jlong, roundRobinPartition)(JNIEnv *env, jclass c, jlong table, jint start, jint n, jlong stream, jlongArray offsetsOut) {
+  jlong *offs = (*env)->GetLongArrayElements(env, offsetsOut, NULL);
+  sb_table *out = NULL;
+  int rc = sb_round_robin_partition(TBL(table), start, n, STR(stream), &out, (int64_t *)offs);
+  (*env)->ReleaseLongArrayElements(env, offsetsOut, offs, 0);
+  throw_if(env, rc);
+  return (jlong)(intptr_t)out;
+}
+
+static sb_sort_order *make_orders(JNIEnv *env, jintArray cols, jbooleanArray asc, jbooleanArray nullsFirst, jsize *n_out) {
+  jsize n = (*env)->GetArrayLength(env, cols);
+  jint *cidx = (*env)->GetIntArrayElements(env, cols, NULL);
+  jboolean *a = (*env)->GetBooleanArrayElements(env, asc, NULL), *nf = (*env)->GetBooleanArrayElements(env, nullsFirst, NULL);
+  sb_sort_order *o = (sb_sort_order *)calloc((size_t)(n ? n : 1), sizeof(sb_sort_order));
+  for (jsize i = 0; i < n; i++) {
+    o[i].col = cidx[i]; o[i].ascending = a[i] ? 1 : 0; o[i].nulls_first = nf[i] ? 1 : 0;
+  }
+  (*env)->ReleaseIntArrayElements(env, cols, cidx, JNI_ABORT);
+  (*env)->ReleaseBooleanArrayElements(env, asc, a, JNI_ABORT);
+  (*env)->ReleaseBooleanArrayElements(env, nullsFirst, nf, JNI_ABORT);
+  *n_out = n;
+  return o;
+}
+
+NATIVE(jlong, sort)(JNIEnv *env, jclass c, jlong table, jintArray cols, jbooleanArray asc, jbooleanArray nullsFirst, jlong stream) {
+  jsize n;
+  sb_sort_order *o = make_orders(env, cols, asc, nullsFirst, &n);
+  sb_table *out = NULL;
+  int rc = sb_sort(TBL(table), o, n, STR(stream), &out);
+  free(o);
+  throw_if(env, rc);
+  return (jlong)(intptr_t)out;
+}
+
+NATIVE(jlong, topN)(JNIEnv *env, jclass c, jlong table, jintArray cols, jbooleanArray asc, jbooleanArray nullsFirst, jlong k, jlong stream) {
+  jsize n;
+  sb_sort_order *o = make_orders(env, cols, asc, nullsFirst, &n);
+  sb_table *out = NULL;
+  int rc = sb_top_n(TBL(table), o, n, k, STR(stream), &out);
+  free(o);
+  throw_if(env, rc);
+  return (jlong)(intptr_t)out;
+}
+
+NATIVE(void, hashTableRelease)(JNIEnv *env, jclass c, jlong relation) {
+  throw_if(env, sb_hash_table_release((sb_hash_table *)(intptr_t)relation));
+}
+
+NATIVE(jlong, allToAll)(JNIEnv *env, jclass c, jlong table, jlongArray partOffsets, jint n, jlong stream, jlongArray outPartOffsets) {
+  jlong *in = (*env)->GetLongArrayElements(env, partOffsets, NULL), *po = (*env)->GetLongArrayElements(env, outPartOffsets, NULL);
+  sb_table *out = NULL;
+  int rc = sb_all_to_all(TBL(table), (const int64_t *)in, n, STR(stream), &out, (int64_t *)po);
+  (*env)->ReleaseLongArrayElements(env, partOffsets, in, JNI_ABORT);
+  (*env)->ReleaseLongArrayElements(env, outPartOffsets, po, 0);
+  throw_if(env, rc);
+  return (jlong)(intptr_t)out;
+}
+
+NATIVE(jlong, allGather)(JNIEnv *env, jclass c, jlong table, jlong stream) {
+  sb_table *out = NULL;
+  throw_if(env, sb_all_gather(TBL(table), STR(stream), &out));
+  return (jlong)(intptr_t)out;
+}
+

@@ -1,6 +1,7 @@
 """CPU-side checks of the drop-in boundary: the shared library loads, exports every symbol
 include/spark_b200.h declares, and refuses to run without a GPU (no CPU fallback)."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -71,3 +72,21 @@ def test_expression_lowering_and_fusion_rule():
     assert isinstance(fused, HashAggregateExec) and fused.child is leaf
     assert fused.condition.sexpr()[0] == "le"
     assert fused.aggregateExpressions[0][0].child.sexpr() == ("mul", ("col", "p"), ("col", "d"))
+
+
+def test_jni_shim_typechecks_against_the_header():
+    """scala/src/main/native/sparkb200_jni.c cannot be built here (no JDK), but it must at least agree with include/spark_b200.h:
+    gcc -fsyntax-only with a stand-in jni.h catches signature drift between the C ABI and the JNI face, and every `native`
+    method of Native.java must have its Java_..._Native_<name> definition."""
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    shim = os.path.join(root, "scala/src/main/native/sparkb200_jni.c")
+    r = subprocess.run(["/usr/bin/gcc", "-fsyntax-only", "-Wall", "-Werror", "-I" + os.path.join(root, "scala/src/main/native/jni_stub"),
+                        "-I" + os.path.join(root, "include"), shim], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    java = open(os.path.join(root, "scala/src/main/java/org/apache/spark/sql/b200/Native.java")).read()
+    declared = set(re.findall(r"public static native [\w\[\]]+ (\w+)\(", java))
+    src = open(shim).read()
+    defined = set(re.findall(r"Java_org_apache_spark_sql_b200_Native_(\w+)\(", src)) | set(re.findall(r"NATIVE\(\w+, (\w+)\)", src))
+    assert declared and declared <= defined, sorted(declared - defined)
