@@ -91,6 +91,15 @@ int sb_profile_enable(int32_t on);
 int sb_profile_reset(void);
 int sb_profile_get(const char *kernel_name, double *out_total_ms, int64_t *out_launches);
 
+/* library-wide settings (tests and experiments; production needs none):
+ *   "agg_rtc"           1 (default) compile plan-specialised aggregate kernels with NVRTC when a plan first meets a large
+ *                       input (the GPU analogue of WholeStageCodegenExec + Janino), 0 = always run the generic kernels
+ *   "agg_rtc_min_rows"  inputs with fewer rows run the generic kernels (default 2^20)
+ *   "agg_tier"          0 auto, 1 dictionary tier only, 2 shared-memory tier only
+ *   "agg_staged", "agg_verbose", "expr_interpret_only", "regroup_ldst", "exchange_nccl"   0/1 */
+int sb_config_set(const char *key, int64_t value);
+int sb_config_get(const char *key, int64_t *out);
+
 /* pinned host buffers for columns that cross PCIe (the JVM side allocates its off-heap column
  * buffers here so H2D/D2H copies are true DMA) */
 int sb_host_alloc(int64_t bytes, void **out);
@@ -207,6 +216,7 @@ int sb_round_robin_partition(const sb_table *in, int32_t start, int32_t num_part
 #define SB_AGG_MODE_PARTIAL 1   /* input rows -> keys ++ buffers  (AggUtils.scala:131-208) */
 #define SB_AGG_MODE_FINAL 2     /* keys ++ buffers -> keys ++ results */
 #define SB_AGG_MODE_COMPLETE 3  /* input rows -> keys ++ results */
+#define SB_AGG_MODE_PARTIAL_MERGE 4  /* keys ++ buffers -> keys ++ buffers (AggUtils.scala PartialMerge) */
 
 typedef struct sb_agg_spec {
   int32_t func;        /* SB_AGG_* */
@@ -230,6 +240,29 @@ typedef struct sb_agg_plan {
 /* Output: key columns, then per aggregate either its buffer columns (Partial: sum -> [sum];
  * avg -> [sum f64, count i64]; count -> [count]; min/max -> [value]) or its result column. */
 int sb_hash_aggregate(const sb_table *in, const sb_agg_plan *plan, sb_stream *s, sb_table **out);
+/* build check without a device: compiles the run-time specialisation of a plan given as its raw PlanMeta int32 words
+ * (sb_agg_plan_meta_words() of them; layout = csrc/agg_kernels.cuh) and returns the compiler's verdict */
+int sb_agg_rtc_compile_check(const int32_t *plan_meta_words, int32_t nwords, char *log, int32_t log_len);
+int32_t sb_agg_plan_meta_words(void);
+/* kernels the calling thread's last aggregate ran: "generic" or "rtc:<plan hash>" (run-time specialised) */
+const char *sb_hash_aggregate_last_plan(void);
+
+/* Aggregation state across the iterator of batches of one partition -- the role of the map that
+ * TungstenAggregationIterator.processInputs fills row by row (SQLX/aggregate/TungstenAggregationIterator.scala:206-281):
+ *   create(plan)            plan->mode says what finish() returns: PARTIAL / PARTIAL_MERGE -> keys ++ buffers,
+ *                           COMPLETE / FINAL -> keys ++ results.  The plan is deep-copied.
+ *   update(state, batch)    folds one batch in (PARTIAL / COMPLETE: input rows; FINAL / PARTIAL_MERGE: keys ++ buffers at
+ *                           the plan's key_cols / positional buffers).  The batch may be released right after the call.
+ *   merge(state, partial)   folds in a table that already has the Partial layout (keys first, then buffers), e.g. the
+ *                           finish() of another state or the reduce side of an exchange.
+ *   finish(state, &out)     one table for everything seen so far; the state stays usable.
+ * No input-sized concatenation happens anywhere (HBM holds one batch plus one row per group seen so far). */
+typedef struct sb_agg_state sb_agg_state;
+int sb_hash_agg_create(const sb_agg_plan *plan, sb_agg_state **out);
+int sb_hash_agg_update(sb_agg_state *state, const sb_table *batch, sb_stream *s);
+int sb_hash_agg_merge(sb_agg_state *state, const sb_table *partial, sb_stream *s);
+int sb_hash_agg_finish(sb_agg_state *state, sb_stream *s, sb_table **out);
+int sb_hash_agg_destroy(sb_agg_state *state);
 
 /* ---- SortExec (SQLX/SortExec.scala:39): stable sort of one partition.  Ordering and NULL
  *      placement follow SortPrefix / PrefixComparators / UnsafeInMemorySorter
@@ -270,6 +303,12 @@ int sb_join_build(const sb_table *build, const int32_t *key_cols, int32_t nkeys,
 int sb_join_probe(const sb_hash_table *ht, const sb_table *probe, const int32_t *key_cols, int32_t nkeys,
                   int32_t join_type, sb_stream *s, sb_table **out);
 int sb_hash_table_release(sb_hash_table *ht);
+
+/* ---- synthetic TPC-H-shaped columns (include/sb_synth.h defines the dataset; SURVEY.md 8d: the reference ships no data
+ *      generator, BASELINE.json configs[3] asks for on-device generation from a counter-based RNG).  Rows
+ *      [first_row, first_row + nrows) of `columns` of table SB_SYNTH_* for a database of n_orders orders. ---- */
+int sb_synth_table(int32_t table, const int32_t *columns, int32_t ncols, int64_t n_orders, int64_t first_row,
+                   int64_t nrows, uint64_t seed, sb_stream *s, sb_table **out);
 
 /* ---- multi-GPU: one executor process per GPU; the exchange is an NCCL all-to-all over NVLink
  *      instead of shuffle files + Netty fetch (core/.../shuffle/sort/SortShuffleManager.scala:70,

@@ -42,7 +42,9 @@ def build(force: bool = False) -> str:
     """Compile the C restatement (gcc) next to its source."""
     so = os.path.join(_HERE, "libspark_oracle.so")
     src = os.path.join(_HERE, "spark_oracle.c")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    hdr = os.path.join(_HERE, "..", "include", "sb_synth.h")   # the synthetic dataset's definition (pure functions)
+    newest = max(os.path.getmtime(src), os.path.getmtime(hdr))
+    if force or not os.path.exists(so) or os.path.getmtime(so) < newest:
         cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
         base = [cc, "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-o", so, src, "-lm"]
         r = subprocess.run(base[:2] + ["-fopenmp"] + base[2:], capture_output=True, text=True)
@@ -83,6 +85,12 @@ def lib():
         L.so_hash_join.restype = i64; L.so_hash_join.argtypes = [p, p, i32, i64, i64, i32, p, p]
         L.so_q1_partial_final.restype = i32
         L.so_q1_partial_final.argtypes = [p, p, p, p, p, p, p, i64, i32, i32, p, p, p, p]
+        L.so_synth_fill.restype = None; L.so_synth_fill.argtypes = [i32, i32, i64, i64, i64, C.c_uint64, p]
+        L.so_synth_rows.restype = i64; L.so_synth_rows.argtypes = [i32, i64]
+        L.so_q3.restype = i32
+        L.so_q3.argtypes = [p, p, i64, p, p, p, p, i64, p, p, p, p, i64, i32, i32, i32, p, p, p, p, p]
+        L.so_q5.restype = None
+        L.so_q5.argtypes = [p, p, i64, p, p, p, i64, p, p, p, p, i64, p, p, i64, p, i32, i32, i32, p, p]
         _LIB = L
     return _LIB
 

@@ -659,3 +659,195 @@ int32_t so_q1_partial_final(const double *qty, const double *price, const double
   free(maps);
   return ng;
 }
+
+/* =====================================================================
+ * Synthetic dataset on the host (include/sb_synth.h is the dataset's definition, shared with the
+ * GPU generator as a header of pure functions; nothing of the product library is called).
+ * The fill is an OpenMP static loop, so each page is first touched by the thread that will scan
+ * it in the baseline loops below (NUMA placement follows the scan).
+ * ===================================================================== */
+#include "../include/sb_synth.h"
+
+void so_synth_fill(int32_t table, int32_t col, int64_t n_orders, int64_t first, int64_t n, uint64_t seed, void *out) {
+  const int w = sbs_width(table, col);
+  const int is_f = table == SB_SYNTH_LINEITEM && sbs_lineitem_is_f64(col);
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; i++) {
+    const int64_t row = first + i;
+    if (is_f) { ((double *)out)[i] = sbs_lineitem_f64(seed, col, row); continue; }
+    int64_t v;
+    if (table == SB_SYNTH_LINEITEM) v = sbs_lineitem_i64(seed, col, row, n_orders);
+    else if (table == SB_SYNTH_ORDERS) v = sbs_orders_i64(seed, col, row, n_orders);
+    else if (table == SB_SYNTH_CUSTOMER) v = sbs_customer_i64(seed, col, row);
+    else v = sbs_supplier_i64(seed, col, row);
+    if (w == 1) ((int8_t *)out)[i] = (int8_t)v;
+    else if (w == 4) ((int32_t *)out)[i] = (int32_t)v;
+    else ((int64_t *)out)[i] = v;
+  }
+}
+int64_t so_synth_rows(int32_t table, int64_t n_orders) {
+  return table == SB_SYNTH_LINEITEM ? sbs_lineitem_rows(n_orders) : table == SB_SYNTH_ORDERS ? n_orders
+       : table == SB_SYNTH_CUSTOMER ? sbs_customer_rows(n_orders) : sbs_supplier_rows(n_orders);
+}
+
+/* =====================================================================
+ * TPC-H Q3 / Q5 as whole-stage restatements of the physical plans the GPU engine runs
+ * (spark_b200/tpch.py q3_plan / q5_plan; shapes follow tpch-plan-stability/q3|q5/simplified.txt):
+ * BroadcastHashJoin build sides become open-addressing relations keyed like LongToUnsafeRowMap
+ * (HashedRelation.scala:594-622: h = k * 0x9E3779B9; slot = (h ^ h>>32) & mask, linear probing),
+ * dense keys (customer, supplier) use its dense-array mode (:865-887); the streamed side is one
+ * fused loop per stage: filter -> probe -> probe -> partial aggregate (HashAggregateExec.scala:907).
+ * Every stage is an OpenMP loop (= local[N] tasks).  The aggregate buffer of a group lives next to the
+ * build-side slot that determines it and is updated atomically, which is cheaper than Spark's
+ * Partial -> Exchange -> Final and therefore generous to the CPU side of the comparison.
+ * ===================================================================== */
+typedef struct { int64_t key; int32_t a, b; } rel_slot;   /* key = -1: empty */
+static inline uint64_t rel_hash(int64_t k) { uint64_t h = (uint64_t)k * 0x9E3779B9ull; return h ^ (h >> 32); }
+
+static rel_slot *rel_alloc(int64_t n, int64_t *cap_out) {
+  int64_t cap = 1024; while (cap < 2 * n) cap *= 2;
+  rel_slot *t = (rel_slot *)malloc(sizeof(rel_slot) * (size_t)cap);
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < cap; i++) t[i].key = -1;
+  *cap_out = cap;
+  return t;
+}
+static inline int64_t rel_insert(rel_slot *t, int64_t cap, int64_t key) {   /* unique keys; returns the slot */
+  uint64_t pos = rel_hash(key) & (uint64_t)(cap - 1);
+  for (;;) {
+    int64_t cur = __atomic_load_n(&t[pos].key, __ATOMIC_RELAXED);
+    if (cur == -1) {
+      int64_t exp = -1;
+      if (__atomic_compare_exchange_n(&t[pos].key, &exp, key, 0, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) return (int64_t)pos;
+      cur = exp;
+    }
+    if (cur == key) return (int64_t)pos;
+    pos = (pos + 1) & (uint64_t)(cap - 1);
+  }
+}
+static inline int64_t rel_find(const rel_slot *t, int64_t cap, int64_t key) {
+  uint64_t pos = rel_hash(key) & (uint64_t)(cap - 1);
+  for (;;) {
+    int64_t cur = t[pos].key;
+    if (cur == key) return (int64_t)pos;
+    if (cur == -1) return -1;
+    pos = (pos + 1) & (uint64_t)(cap - 1);
+  }
+}
+static inline void atomic_add_f64(double *p, double v) {
+  uint64_t old = __atomic_load_n((uint64_t *)p, __ATOMIC_RELAXED), neu;
+  do { double d; memcpy(&d, &old, 8); d += v; memcpy(&neu, &d, 8); }
+  while (!__atomic_compare_exchange_n((uint64_t *)p, &old, neu, 1, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
+}
+
+/* q3.sql: revenue per (l_orderkey, o_orderdate, o_shippriority) for segment customers, orders before `date`,
+ * lines shipped after `date`; ORDER BY revenue DESC, o_orderdate LIMIT k.  Returns the number of result rows;
+ * out_groups = number of groups before the limit. */
+int32_t so_q3(const int64_t *c_custkey, const int8_t *c_mktsegment, int64_t n_cust,
+              const int64_t *o_orderkey, const int64_t *o_custkey, const int32_t *o_orderdate, const int32_t *o_shippriority, int64_t n_ord,
+              const int64_t *l_orderkey, const double *l_extendedprice, const double *l_discount, const int32_t *l_shipdate, int64_t n_li,
+              int32_t segment, int32_t date, int32_t k,
+              int64_t *out_orderkey, double *out_revenue, int32_t *out_orderdate, int32_t *out_shippriority, int64_t *out_groups) {
+  /* build 1: filtered customer -> key set (dense: c_custkey is 1..n) */
+  int64_t maxc = 0;
+  for (int64_t i = 0; i < n_cust; i++) if (c_custkey[i] > maxc) maxc = c_custkey[i];
+  uint8_t *cust_ok = (uint8_t *)calloc((size_t)maxc + 2, 1);
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n_cust; i++) if (c_mktsegment[i] == segment) cust_ok[c_custkey[i]] = 1;
+  /* stage 2: orders: filter, probe customers, build relation 2 (orderkey -> date, priority) */
+  int64_t cap;
+  rel_slot *rel = rel_alloc(n_ord / 2 + 16, &cap);
+  double *rev = (double *)calloc((size_t)cap, sizeof(double));
+  uint8_t *touched = (uint8_t *)calloc((size_t)cap, 1);
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n_ord; i++) {
+    if (!(o_orderdate[i] < date)) continue;
+    int64_t c = o_custkey[i];
+    if (c < 0 || c > maxc || !cust_ok[c]) continue;
+    int64_t s = rel_insert(rel, cap, o_orderkey[i]);
+    rel[s].a = o_orderdate[i]; rel[s].b = o_shippriority[i];
+  }
+  /* stage 3: lineitem: filter, probe, aggregate */
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n_li; i++) {
+    if (!(l_shipdate[i] > date)) continue;
+    int64_t s = rel_find(rel, cap, l_orderkey[i]);
+    if (s < 0) continue;
+    atomic_add_f64(&rev[s], l_extendedprice[i] * (1.0 - l_discount[i]));
+    touched[s] = 1;
+  }
+  /* TakeOrderedAndProject (limit.scala:347-386): bounded selection of the k best */
+  int32_t nres = 0; int64_t groups = 0;
+  for (int64_t s = 0; s < cap; s++) {
+    if (!touched[s]) continue;
+    groups++;
+    int32_t pos = nres;
+    while (pos > 0 && (out_revenue[pos - 1] < rev[s] || (out_revenue[pos - 1] == rev[s] && out_orderdate[pos - 1] > rel[s].a))) pos--;
+    if (pos >= k) continue;
+    int32_t last = nres < k ? nres : k - 1;
+    for (int32_t j = last; j > pos; j--) {
+      out_orderkey[j] = out_orderkey[j - 1]; out_revenue[j] = out_revenue[j - 1];
+      out_orderdate[j] = out_orderdate[j - 1]; out_shippriority[j] = out_shippriority[j - 1];
+    }
+    out_orderkey[pos] = rel[s].key; out_revenue[pos] = rev[s]; out_orderdate[pos] = rel[s].a; out_shippriority[pos] = rel[s].b;
+    if (nres < k) nres++;
+  }
+  if (out_groups) *out_groups = groups;
+  free(cust_ok); free(rel); free(rev); free(touched);
+  return nres;
+}
+
+/* q5.sql: revenue per nation of `region` for orders in [date_lo, date_hi) where customer and supplier share the nation.
+ * nation_region[25] maps n_nationkey -> n_regionkey.  out_revenue[25] indexed by nation key (0 where absent), out_seen[25]. */
+void so_q5(const int64_t *c_custkey, const int64_t *c_nationkey, int64_t n_cust,
+           const int64_t *o_orderkey, const int64_t *o_custkey, const int32_t *o_orderdate, int64_t n_ord,
+           const int64_t *l_orderkey, const int64_t *l_suppkey, const double *l_extendedprice, const double *l_discount, int64_t n_li,
+           const int64_t *s_suppkey, const int64_t *s_nationkey, int64_t n_supp,
+           const int32_t *nation_region, int32_t region, int32_t date_lo, int32_t date_hi,
+           double *out_revenue, uint8_t *out_seen) {
+  int64_t maxc = 0, maxs = 0;
+  for (int64_t i = 0; i < n_cust; i++) if (c_custkey[i] > maxc) maxc = c_custkey[i];
+  for (int64_t i = 0; i < n_supp; i++) if (s_suppkey[i] > maxs) maxs = s_suppkey[i];
+  int8_t *cnat = (int8_t *)malloc((size_t)maxc + 2), *snat = (int8_t *)malloc((size_t)maxs + 2);
+  memset(cnat, -1, (size_t)maxc + 2); memset(snat, -1, (size_t)maxs + 2);
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n_cust; i++) cnat[c_custkey[i]] = (int8_t)c_nationkey[i];
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n_supp; i++)                      /* supplier |x| nation |x| region(filtered) */
+    if (nation_region[s_nationkey[i]] == region) snat[s_suppkey[i]] = (int8_t)s_nationkey[i];
+  int64_t cap;
+  rel_slot *rel = rel_alloc(n_ord / 4 + 16, &cap);
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n_ord; i++) {
+    if (!(o_orderdate[i] >= date_lo && o_orderdate[i] < date_hi)) continue;
+    int64_t c = o_custkey[i];
+    if (c < 0 || c > maxc || cnat[c] < 0) continue;
+    int64_t s = rel_insert(rel, cap, o_orderkey[i]);
+    rel[s].a = cnat[c];
+  }
+  int nt = so_threads();
+  double *part = (double *)calloc((size_t)nt * 32, sizeof(double));
+  uint8_t *pseen = (uint8_t *)calloc((size_t)nt * 32, 1);
+#pragma omp parallel
+  {
+#ifdef _OPENMP
+    int t = omp_get_thread_num();
+#else
+    int t = 0;
+#endif
+    double *p = part + (size_t)t * 32; uint8_t *ps = pseen + (size_t)t * 32;
+#pragma omp for schedule(static)
+    for (int64_t i = 0; i < n_li; i++) {
+      int64_t s = rel_find(rel, cap, l_orderkey[i]);
+      if (s < 0) continue;
+      int64_t sk = l_suppkey[i];
+      if (sk < 0 || sk > maxs || snat[sk] < 0) continue;
+      if (snat[sk] != rel[s].a) continue;                     /* c_nationkey = s_nationkey */
+      p[snat[sk]] += l_extendedprice[i] * (1.0 - l_discount[i]);
+      ps[snat[sk]] = 1;
+    }
+  }
+  for (int g = 0; g < 25; g++) { out_revenue[g] = 0; out_seen[g] = 0; }
+  for (int t = 0; t < nt; t++) for (int g = 0; g < 25; g++) { out_revenue[g] += part[(size_t)t * 32 + g]; out_seen[g] |= pseen[(size_t)t * 32 + g]; }
+  free(cnat); free(snat); free(rel); free(part); free(pseen);
+}

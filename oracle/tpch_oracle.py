@@ -50,3 +50,27 @@ def q5(customer, orders, lineitem, supplier, nation, region, region_code, date_l
     p = O.project(same, [("n_name", ("col", "n_name")), ("rev", _REV)])
     agg = O.hash_aggregate(p, ["n_name"], [("sum", "rev", "revenue")])
     return O.sort(agg, [("revenue", False, False)])
+
+
+# ------------------------------------------------------------------------------------------ synthetic dataset on the host
+def synth_host(table: str, columns, n_orders: int, seed: int = 42, first_row: int = 0, nrows: int = None, out: dict = None) -> dict:
+    """Columns of the synthetic dataset (include/sb_synth.h) filled on the host by so_synth_fill (OpenMP, parallel first
+    touch): the CPU-side twin of spark_b200.tpch.synth_batch, bit-identical by construction and checked in the tests."""
+    from spark_b200 import tpch as T        # names / ids of the synthetic columns only (no GPU code is touched)
+    L = O.lib()
+    if nrows is None:
+        nrows = T.synth_rows(table, n_orders) - first_row
+    res = {}
+    for c in columns:
+        a = out[c] if out is not None else np.empty(nrows, T.synth_dtype(c))
+        L.so_synth_fill(T.SYNTH_TABLE[table], T.SYNTH_COLUMNS[table].index(c), n_orders, first_row, nrows, seed, a.ctypes.data)
+        res[c] = a
+    return res
+
+
+def synth_arrow(table: str, columns, n_orders: int, seed: int = 42):
+    """Host Arrow table of the synthetic dataset (input of the oracle pipelines in the tests)."""
+    import pyarrow as pa
+    from spark_b200 import tpch as T
+    cols = synth_host(table, columns, n_orders, seed)
+    return pa.table({c: (pa.array(cols[c]).cast(pa.date32()) if c in T._DATE_COLS else cols[c]) for c in columns})

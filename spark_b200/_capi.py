@@ -21,7 +21,7 @@ SB_OP = dict(COL=1, LIT_I64=2, LIT_F64=3, LIT_NULL=4, ADD=10, SUB=11, MUL=12, DI
              LE=23, GT=24, GE=25, AND=30, OR=31, NOT=32, ISNULL=33, ISNOTNULL=34, CAST_F64=40, CAST_I64=41, CAST_I32=42)
 SB_VT_BOOL, SB_VT_I32, SB_VT_I64, SB_VT_F64 = 1, 2, 3, 4
 SB_AGG = dict(sum=1, avg=2, count=3, count_star=4, min=5, max=6)
-SB_AGG_MODE = dict(partial=1, final=2, complete=3)
+SB_AGG_MODE = dict(partial=1, final=2, complete=3, partial_merge=4)
 SB_JOIN = dict(inner=0, left_outer=1, left_semi=2, left_anti=3)
 SB_UNIQUE_ID_BYTES = 128
 
@@ -77,6 +77,8 @@ _i32, _i64 = C.c_int32, C.c_int64
 _SIGNATURES = {
     "sb_init": [_i32], "sb_shutdown": [], "sb_last_error": [], "sb_abi_version": [],
     "sb_device_info": [C.POINTER(_i64)], "sb_kernel_launch_count": [],
+    "sb_config_set": [C.c_char_p, _i64], "sb_config_get": [C.c_char_p, C.POINTER(_i64)], "sb_hash_aggregate_last_plan": [],
+    "sb_agg_rtc_compile_check": [C.POINTER(_i32), _i32, C.c_char_p, _i32], "sb_agg_plan_meta_words": [],
     "sb_profile_enable": [_i32], "sb_profile_reset": [], "sb_profile_get": [C.c_char_p, C.POINTER(C.c_double), C.POINTER(_i64)],
     "sb_host_alloc": [_i64, _pp], "sb_host_free": [_p],
     "sb_stream_create": [_pp], "sb_stream_destroy": [_p], "sb_stream_synchronize": [_p],
@@ -95,6 +97,9 @@ _SIGNATURES = {
     "sb_round_robin_partition": [_p, _i32, _i32, _p, _pp, C.POINTER(_i64)],
     "sb_range_partition": [_p, C.POINTER(sb_sort_order), _p, _p, _pp, C.POINTER(_i64)],
     "sb_hash_aggregate": [_p, C.POINTER(sb_agg_plan), _p, _pp],
+    "sb_hash_agg_create": [C.POINTER(sb_agg_plan), _pp], "sb_hash_agg_update": [_p, _p, _p],
+    "sb_hash_agg_merge": [_p, _p, _p], "sb_hash_agg_finish": [_p, _p, _pp], "sb_hash_agg_destroy": [_p],
+    "sb_synth_table": [_i32, C.POINTER(_i32), _i32, _i64, _i64, _i64, C.c_uint64, _p, _pp],
     "sb_sort": [_p, C.POINTER(sb_sort_order), _i32, _p, _pp],
     "sb_sort_permutation": [_p, C.POINTER(sb_sort_order), _i32, _p, _p],
     "sb_top_n": [_p, C.POINTER(sb_sort_order), _i32, _i64, _p, _pp],
@@ -107,7 +112,7 @@ _SIGNATURES = {
     "sb_all_to_all": [_p, C.POINTER(_i64), _i32, _p, _pp, C.POINTER(_i64)],
     "sb_all_gather": [_p, _p, _pp],
 }
-_RESTYPE = {"sb_last_error": C.c_char_p, "sb_abi_version": _i32, "sb_kernel_launch_count": _i64}
+_RESTYPE = {"sb_agg_plan_meta_words": _i32, "sb_hash_aggregate_last_plan": C.c_char_p, "sb_last_error": C.c_char_p, "sb_abi_version": _i32, "sb_kernel_launch_count": _i64}
 
 
 def declared_symbols():
@@ -152,3 +157,13 @@ def init(device_ordinal=None):
 
 def kernel_launch_count():
     return int(load().sb_kernel_launch_count())
+
+
+def config_set(key: str, value: int):
+    check(load().sb_config_set(key.encode(), int(value)))
+
+
+def config_get(key: str) -> int:
+    v = _i64()
+    check(load().sb_config_get(key.encode(), C.byref(v)))
+    return int(v.value)

@@ -5,11 +5,16 @@
 //                    one binary serves every plan.
 //   StaticPlan<&M>   metadata comes from a `__device__ const PlanMeta` table: after inlining, every descriptor loop has
 //                    a constant trip count and unrolls, every type / mode / kind switch folds, and what is left per
-//                    row is loads + arithmetic -- the same effect whole-stage codegen has on the reference's CPU path,
-//                    obtained with C++ templates instead of a runtime compiler.  Plans whose PlanMeta matches a
-//                    registered table run the specialised kernel, everything else runs DynPlan (same code, same results).
+//                    row is loads + arithmetic -- the same effect whole-stage codegen has on the reference's CPU path.
+//                    The table and the instantiations are generated and compiled at run time (NVRTC, rtc.cu) when a
+//                    plan first meets a large input; until then, and wherever NVRTC is unavailable, DynPlan runs (same
+//                    code, same results).
 #pragma once
+#ifdef __CUDACC_RTC__
+#include "device_helpers.cuh"   // run-time compilation (rtc.cu): device side only, headers come from the embedded copies
+#else
 #include "common.cuh"
+#endif
 
 namespace sb {
 

@@ -30,61 +30,36 @@
 #include <math.h>
 #include <stdlib.h>
 #include <memory>
+#include <thread>
 #include "agg_kernels.cuh"
 #include "expr.cuh"
 #include "primitives.cuh"
+#include "rtc.cuh"
 
 namespace sb {
 
-// ---- pre-specialised plans ------------------------------------------------------------------------------------------
-// A plan whose PlanMeta equals one of these tables runs the StaticPlan instantiation (descriptor loops unrolled, type /
-// mode / kind switches folded at compile time); every other plan runs DynPlan.  The tables only describe *shapes*:
-// "one int32-class <= term, two non-null int8 keys, double sums of col / col*(lit-col) / col*(lit-col)*(lit+col), a
-// counter" -- which is the shape of TPC-H Q1's partial aggregate, whatever the column names, literals or data.
-#define SB_F64 SB_FLOAT64
-#define SB_META_Q1_PARTIAL                                                                                              \
-  {                                                                                                                     \
-    /* has_mask, nterms, single64, nkeys, nslots, pad */ 0, 1, 0, 2, 6, 0,                                              \
-    /* term_type */ {SB_DATE32, 0, 0, 0}, /* term_op */ {T_LE, 0, 0, 0}, /* term_f64 */ {0, 0, 0, 0}, /* term_valid */ {0, 0, 0, 0}, \
-    /* key_type */ {SB_INT8, SB_INT8, 0, 0, 0, 0}, /* key_bits */ {8, 8, 0, 0, 0, 0}, /* key_shift */ {0, 8, 0, 0, 0, 0}, \
-    /* key_nshift */ {-1, -1, 0, 0, 0, 0}, /* key_valid */ {0, 0, 0, 0, 0, 0},                                           \
-    /* slot_kind */ {K_ADD_F64, K_ADD_F64, K_ADD_F64, K_ADD_F64, K_ADD_I64, K_ADD_F64},                                  \
-    /* slot_nf */ {1, 1, 2, 3, 0, 1}, /* slot_one */ {0, 0, 0, 0, 1, 0}, /* slot_xform */ {0},                           \
-    /* slot_cls */ {CLS_F64_PRODUCT, CLS_F64_PRODUCT, CLS_F64_PRODUCT, CLS_F64_PRODUCT, CLS_ONE, CLS_F64_PRODUCT},        \
-    /* slot_anyvalid */ {0},                                                                                            \
-    /* f_type */ {{SB_F64, 0, 0}, {SB_F64, 0, 0}, {SB_F64, SB_F64, 0}, {SB_F64, SB_F64, SB_F64}, {0, 0, 0}, {SB_F64, 0, 0}}, \
-    /* f_mode */ {{F_COL, 0, 0}, {F_COL, 0, 0}, {F_COL, F_LIT_MINUS_COL, 0}, {F_COL, F_LIT_MINUS_COL, F_LIT_PLUS_COL}, {0, 0, 0}, {F_COL, 0, 0}}, \
-    /* f_valid */ {{0}},                                                                                                \
-    /* ncols, mask_col */ 7, 0,                                                                                         \
-    /* col_type: shipdate, returnflag, linestatus, quantity, extendedprice, discount, tax */                            \
-    {SB_DATE32, SB_INT8, SB_INT8, SB_F64, SB_F64, SB_F64, SB_F64},                                                       \
-    /* term_col */ {0, 0, 0, 0}, /* key_col */ {1, 2, 0, 0, 0, 0},                                                      \
-    /* f_col */ {{3, 0, 0}, {4, 0, 0}, {4, 5, 0}, {4, 5, 6}, {0, 0, 0}, {5, 0, 0}}                                       \
-  }
-__device__ const PlanMeta kDevMetaQ1Partial = SB_META_Q1_PARTIAL;
-static const PlanMeta kHostMetaQ1Partial = SB_META_Q1_PARTIAL;
-// the group-by-one-int64-key, sum-one-column shape of BASELINE.json configs[0] (k int64, v int64 / double, no NULLs)
-#define SB_META_C1(VKIND, VTYPE, VCLS)                                                                                  \
-  {                                                                                                                     \
-    0, 0, 1, 1, 1, 0, {0}, {0}, {0}, {0}, {SB_INT64, 0, 0, 0, 0, 0}, {64, 0, 0, 0, 0, 0}, {0}, {-1, 0, 0, 0, 0, 0}, {0}, \
-    {VKIND}, {1}, {0}, {0}, {VCLS}, {0}, {{VTYPE, 0, 0}}, {{F_COL, 0, 0}}, {{0}},                                        \
-    2, 0, {SB_INT64, VTYPE}, {0}, {0}, {{1, 0, 0}}                                                                      \
-  }
-__device__ const PlanMeta kDevMetaC1I64 = SB_META_C1(K_ADD_I64, SB_INT64, CLS_GENERIC);
-static const PlanMeta kHostMetaC1I64 = SB_META_C1(K_ADD_I64, SB_INT64, CLS_GENERIC);
-__device__ const PlanMeta kDevMetaC1F64 = SB_META_C1(K_ADD_F64, SB_FLOAT64, CLS_F64_PRODUCT);
-static const PlanMeta kHostMetaC1F64 = SB_META_C1(K_ADD_F64, SB_FLOAT64, CLS_F64_PRODUCT);
-
+// ---- plan-specialised kernels, generated when a plan first runs ------------------------------------------------------
+// Every update kernel is a template over a plan policy (agg_kernels.cuh).  The generic instantiation (DynPlan) is compiled
+// ahead of time and serves any plan.  When a plan first meets an input large enough for it to matter, its PlanMeta is
+// printed into a `__device__ const` table, the same templates are instantiated over StaticPlan<&table> by NVRTC (rtc.cu),
+// and the resulting kernels are cached by the plan's bytes (process + disk) -- what whole-stage codegen + Janino do for the
+// reference's CPU path.  Nothing in this file knows the shape of any particular query.
 constexpr int ITEMS_DIRECT = 8;   // rows per thread per tile, direct path (1024-row tiles)
 constexpr int ITEMS_STAGED = 4;   // staged path (512-row tiles keep two blocks per SM resident)
 
-typedef void (*AggKernel)(const AggArgs);
+typedef const void *AggKernel;    // a __global__ symbol or a cudaKernel_t from a run-time compiled library
+template <class K>
+static AggKernel kptr(K k) { return (const void *)k; }
+static void launch_agg(AggKernel k, int grid, int threads, size_t smem, cudaStream_t st, const AggArgs &a) {
+  void *args[] = {(void *)&a};
+  SB_CUDA(cudaLaunchKernel(k, dim3((unsigned)grid), dim3((unsigned)threads), args, smem, st));
+}
 constexpr int ITEMS_SMEM = 4;     // shared-memory tier: 512 threads x 4 rows
 struct KernelChoice {
   AggKernel direct, staged;           // plain dictionary kernel (8 entries) and its TMA variant
   int items_direct;
-  const char *name;
-  AggKernel smem = agg_update_smem_kernel<DynPlan, ITEMS_SMEM>;
+  std::string name;
+  AggKernel smem = kptr(agg_update_smem_kernel<DynPlan, ITEMS_SMEM>);
   // the automatic chain: k1 watches and yields (dictionary of k1_dict entries, k1_items rows per thread), k2 (optional, 8
   // entries, same tile geometry) takes over and yields in turn, smem finishes
   AggKernel k1 = nullptr, k2 = nullptr;
@@ -93,52 +68,104 @@ struct KernelChoice {
   AggKernel k2_big = nullptr;         // ... followed by a 32-entry (hash-probed) take-over kernel: light plans with 9..32 groups
   int k2_dict = 8;
 };
-template <class P, int ITEMS, bool PREFETCH>
-static void default_chain(KernelChoice &kc) {
-  kc.k1 = agg_update_kernel<P, ITEMS, PREFETCH, AGG_MODE_YIELD, false, 4>;
-  kc.k2 = agg_update_kernel<P, ITEMS, PREFETCH, AGG_MODE_TAKEOVER, false, 8>;
-  kc.k1_wide = agg_update_kernel<P, ITEMS, PREFETCH, AGG_MODE_YIELD, false, 8>;
-  kc.k2_big = agg_update_kernel<P, ITEMS, PREFETCH, AGG_MODE_TAKEOVER, false, 32>;
-  kc.k1_dict = 4;
-  kc.k1_items = ITEMS;
-}
-static KernelChoice choose_kernels(const PlanMeta &m) {
-  if (getenv("SB_AGG_DISABLE_STATIC") == nullptr) {
-    // tuning knob: "4" (default: 4 rows per thread, 4-entry then 8-entry dictionary) | "4p" (+ L2 prefetch of the next tile) |
-    // "8pf" | "8p" | "8" (single 8-entry dictionary kernel, 8 rows per thread; f = fat build: the never-taken general path raises
-    // ptxas's register target from 56 to 117).  Measured on SF10: 0.461 / 0.470 / 0.491 ms for "4" / "4p" / "8pf".
-    const char *v = getenv("SB_AGG_Q1_VARIANT");
-    if (memcmp(&m, &kHostMetaQ1Partial, sizeof(PlanMeta)) == 0) {
-      using Q1 = StaticPlan<&kDevMetaQ1Partial>;
-      KernelChoice q1{agg_update_kernel<Q1, 8, true>, agg_update_staged_kernel<Q1, ITEMS_STAGED>, 8, "static:q1_partial/4"};
-      default_chain<Q1, 4, false>(q1);
-      auto single = [&](AggKernel k, int items, const char *name) { q1.k1 = k; q1.k2 = nullptr; q1.k1_wide = nullptr; q1.k2_big = nullptr; q1.k1_dict = 8; q1.k1_items = items; q1.name = name; };
-      if (v && strcmp(v, "8pf") == 0) single(agg_update_kernel<Q1, 8, true, AGG_MODE_YIELD, true, 8>, 8, "static:q1_partial/8pf");
-      if (v && strcmp(v, "8p") == 0) single(agg_update_kernel<Q1, 8, true, AGG_MODE_YIELD, false, 8>, 8, "static:q1_partial/8p");
-      if (v && strcmp(v, "8") == 0) single(agg_update_kernel<Q1, 8, false, AGG_MODE_YIELD, false, 8>, 8, "static:q1_partial/8");
-      if (v && strcmp(v, "4p") == 0) {
-        default_chain<Q1, 4, true>(q1);
-        q1.name = "static:q1_partial/4p";
-      }
-      return q1;
-    }
-    if (memcmp(&m, &kHostMetaC1I64, sizeof(PlanMeta)) == 0) {
-      using C1 = StaticPlan<&kDevMetaC1I64>;
-      KernelChoice kc{agg_update_kernel<C1, ITEMS_DIRECT>, agg_update_staged_kernel<C1, ITEMS_STAGED>, ITEMS_DIRECT, "static:groupby_i64_sum_i64",
-                      agg_update_smem_kernel<C1, ITEMS_SMEM>};
-      default_chain<C1, ITEMS_DIRECT, false>(kc);
-      return kc;
-    }
-    if (memcmp(&m, &kHostMetaC1F64, sizeof(PlanMeta)) == 0) {
-      using C1 = StaticPlan<&kDevMetaC1F64>;
-      KernelChoice kc{agg_update_kernel<C1, ITEMS_DIRECT>, agg_update_staged_kernel<C1, ITEMS_STAGED>, ITEMS_DIRECT, "static:groupby_i64_sum_f64",
-                      agg_update_smem_kernel<C1, ITEMS_SMEM>};
-      default_chain<C1, ITEMS_DIRECT, false>(kc);
-      return kc;
-    }
+
+static thread_local std::string g_last_plan_name;
+
+// Plans that read many columns per row keep more loads in flight with 4 rows per thread (more resident warps); narrow plans
+// (group by k, sum v) prefer 8.
+static int chain_items(const PlanMeta &m) { return (m.ncols >= 5 || m.nslots >= 4) ? 4 : ITEMS_DIRECT; }
+
+enum { NEED_K1 = 1, NEED_K2 = 2, NEED_K1W = 4, NEED_K2B = 8, NEED_DIRECT = 16, NEED_SMEM = 32, NEED_ALL = 63 };
+
+// One NVRTC program per kernel (they compile concurrently, ~1.5 s each; a plan needs two or three of them).
+static std::string plan_source(const PlanMeta &m) {
+  std::string src = "#include \"agg_kernels.cuh\"\nnamespace sb {\n__device__ const PlanMeta kPlan = {";
+  static_assert(sizeof(PlanMeta) % 4 == 0, "PlanMeta is a table of int32");
+  const int32_t *w = (const int32_t *)&m;
+  for (size_t i = 0; i < sizeof(PlanMeta) / 4; i++) {
+    src += std::to_string(w[i]);
+    src += i + 1 < sizeof(PlanMeta) / 4 ? "," : "";
   }
-  KernelChoice kc{agg_update_kernel<DynPlan, ITEMS_DIRECT>, agg_update_staged_kernel<DynPlan, ITEMS_STAGED>, ITEMS_DIRECT, "dynamic"};
-  default_chain<DynPlan, ITEMS_DIRECT, false>(kc);
+  src += "};\nusing RP = StaticPlan<&kPlan>;\n}\n";
+  return src;
+}
+static std::string kernel_expr(int which, int items) {
+  const std::string it = std::to_string(items);
+  switch (which) {
+    case NEED_K1: return "sb::agg_update_kernel<sb::RP, " + it + ", false, 1, false, 4>";     // watch and yield, 4 entries
+    case NEED_K2: return "sb::agg_update_kernel<sb::RP, " + it + ", false, 2, false, 8>";     // take over, 8 entries
+    case NEED_K1W: return "sb::agg_update_kernel<sb::RP, " + it + ", false, 1, false, 8>";    // watch and yield, 8 entries
+    case NEED_K2B: return "sb::agg_update_kernel<sb::RP, " + it + ", false, 2, false, 32>";   // take over, 32 entries (hash probed)
+    case NEED_DIRECT: return "sb::agg_update_kernel<sb::RP, 8, true, 0, false, 8>";           // plain (caller knows: <= 8 groups)
+    default: return "sb::agg_update_smem_kernel<sb::RP, 4>";
+  }
+}
+// compiles (or fetches from the cache) the kernels in `need`; out[i] = kernel of bit i or nullptr.  Returns false when any failed.
+static bool specialise_kernels(const PlanMeta &m, int items, int need, bool load, const void *out[6], std::string *log, bool *all_cached) {
+  const std::string src = plan_source(m);
+  const std::string base((const char *)&m, sizeof(PlanMeta));
+  const RtcProgram *progs[6] = {nullptr};
+  std::vector<std::thread> workers;
+  for (int i = 0; i < 6; i++) {
+    if (!(need & (1 << i))) continue;
+    workers.emplace_back([&, i] {
+      const std::string expr = kernel_expr(1 << i, items);
+      progs[i] = rtc_compile(base + "/" + expr + (load ? "" : "/check"), src, {expr}, load);
+    });
+  }
+  for (auto &t : workers) t.join();
+  bool ok = true;
+  if (all_cached) *all_cached = true;
+  for (int i = 0; i < 6; i++) {
+    out[i] = nullptr;
+    if (!(need & (1 << i))) continue;
+    if (!progs[i]->ok) {
+      ok = false;
+      if (log) *log = progs[i]->log;
+      continue;
+    }
+    if (load) out[i] = progs[i]->kernels[0];
+    if (log && !load) *log += progs[i]->log + "; ";
+    if (all_cached && !progs[i]->from_disk_cache) *all_cached = false;
+  }
+  return ok;
+}
+
+static bool specialise(const PlanMeta &m, int64_t n, int need, KernelChoice &kc) {
+  const Config &cfg = config();
+  if (!cfg.agg_rtc || n < cfg.agg_rtc_min_rows) return false;
+  const int items = chain_items(m);
+  const void *k[6];
+  std::string log;
+  bool cached = false;
+  if (!specialise_kernels(m, items, need, true, k, &log, &cached)) {
+    if (cfg.agg_verbose) fprintf(stderr, "[sb_hash_aggregate] run-time specialisation unavailable, generic kernels used: %s\n", log.c_str());
+    return false;
+  }
+  if (k[0]) kc.k1 = k[0];
+  if (k[1]) kc.k2 = k[1];
+  if (k[2]) kc.k1_wide = k[2];
+  if (k[3]) kc.k2_big = k[3];
+  if (k[4]) { kc.direct = k[4]; kc.items_direct = 8; }
+  if (k[5]) kc.smem = k[5];
+  kc.k1_items = items;     // k1 / k2 / k1_wide / k2_big share one tile geometry: all of the chain's members are in `need`
+  char hex[32];
+  uint64_t h = 1469598103934665603ull;
+  for (size_t i = 0; i < sizeof(PlanMeta); i++) { h ^= ((const unsigned char *)&m)[i]; h *= 1099511628211ull; }
+  snprintf(hex, sizeof(hex), "%016llx", (unsigned long long)h);
+  kc.name = std::string("rtc:") + hex + (cached ? "(disk)" : "");
+  return true;
+}
+
+static KernelChoice choose_kernels(const PlanMeta &m, int64_t n, int need) {
+  KernelChoice kc{kptr(agg_update_kernel<DynPlan, ITEMS_DIRECT>), kptr(agg_update_staged_kernel<DynPlan, ITEMS_STAGED>), ITEMS_DIRECT, "generic"};
+  kc.k1 = kptr(agg_update_kernel<DynPlan, ITEMS_DIRECT, false, AGG_MODE_YIELD, false, 4>);
+  kc.k2 = kptr(agg_update_kernel<DynPlan, ITEMS_DIRECT, false, AGG_MODE_TAKEOVER, false, 8>);
+  kc.k1_wide = kptr(agg_update_kernel<DynPlan, ITEMS_DIRECT, false, AGG_MODE_YIELD, false, 8>);
+  kc.k2_big = kptr(agg_update_kernel<DynPlan, ITEMS_DIRECT, false, AGG_MODE_TAKEOVER, false, 32>);
+  kc.k1_dict = 4;
+  kc.k1_items = ITEMS_DIRECT;
+  specialise(m, n, need, kc);
   return kc;
 }
 
@@ -472,7 +499,7 @@ static int64_t next_pow2(int64_t x) {
 
 static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cudaStream_t st, sb_table **out) {
   SB_REQUIRE(in && plan && out, "null argument");
-  SB_REQUIRE(plan->mode >= SB_AGG_MODE_PARTIAL && plan->mode <= SB_AGG_MODE_COMPLETE, "bad aggregate mode %d", plan->mode);
+  SB_REQUIRE(plan->mode >= SB_AGG_MODE_PARTIAL && plan->mode <= SB_AGG_MODE_PARTIAL_MERGE, "bad aggregate mode %d", plan->mode);
   SB_REQUIRE(plan->nkeys >= 0 && plan->naggs >= 0, "bad plan");
   const int64_t n = in->nrows;
   AggBuilder b;
@@ -588,8 +615,9 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
   }
 
   // ---- aggregates -> accumulator slots + output plan -------------------------------------------
-  const bool final_mode = plan->mode == SB_AGG_MODE_FINAL;
-  const bool emit_buffers = plan->mode == SB_AGG_MODE_PARTIAL;
+  // AggUtils.scala:131-208: Partial / PartialMerge emit buffers, Final / PartialMerge read buffers positionally
+  const bool final_mode = plan->mode == SB_AGG_MODE_FINAL || plan->mode == SB_AGG_MODE_PARTIAL_MERGE;
+  const bool emit_buffers = plan->mode == SB_AGG_MODE_PARTIAL || plan->mode == SB_AGG_MODE_PARTIAL_MERGE;
   int next_buf_col = plan->nkeys;   // Final: buffers follow the keys positionally
   for (int i = 0; i < plan->naggs; i++) {
     const sb_agg_spec &sp = plan->aggs[i];
@@ -711,15 +739,20 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
   int64_t cap = plan->expected_groups > 0 ? next_pow2(4 * plan->expected_groups) : (1 << 18);   // no hint: 128K groups before the first retry
   if (cap < 1024) cap = 1024;
   if (cap > cap_max) cap = cap_max;
-  KernelChoice kc = choose_kernels(m);
-  const size_t smem_acc = (size_t)(AGG_DICT + 1 + (size_t)(AGG_DICT + 1) * ns * AGG_THREADS) * 8;   // dictionary + fill counter + accumulators
-  SB_REQUIRE(smem_acc <= 200 * 1024, "aggregate needs %zu bytes of shared memory", smem_acc);
-  SB_CUDA(cudaFuncSetAttribute(kc.direct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_acc));
   auto dict_smem = [&](int d) { return (size_t)(d + 1 + (size_t)(d + 1) * ns * AGG_THREADS) * 8; };
   auto dict_blocks_per_sm = [&](int d) {
     int b = (int)((228 * 1024) / (dict_smem(d) + 1024));
     return b < 1 ? 1 : (b > 8 ? 8 : b);
   };
+  // which members of the kernel family this call can reach (only those are specialised at run time)
+  const bool light_plan = dict_blocks_per_sm(8) == dict_blocks_per_sm(4), big_dict_ok = dict_blocks_per_sm(32) >= 4;
+  int need = light_plan ? (NEED_K1W | (big_dict_ok ? NEED_K2B : 0) | NEED_SMEM) : (NEED_K1 | NEED_K2 | NEED_SMEM);
+  if (config().agg_tier == 1 || (config().agg_tier == 0 && plan->expected_groups > 0 && plan->expected_groups <= AGG_DICT)) need = NEED_DIRECT;
+  else if (config().agg_tier == 2 || (config().agg_tier == 0 && plan->expected_groups > AGG_DICT)) need = NEED_SMEM;
+  KernelChoice kc = choose_kernels(m, a.nwords == 1 && !config().agg_staged ? n : 0, need);   // wide-key / staged kernels are not specialised
+  const size_t smem_acc = (size_t)(AGG_DICT + 1 + (size_t)(AGG_DICT + 1) * ns * AGG_THREADS) * 8;   // dictionary + fill counter + accumulators
+  SB_REQUIRE(smem_acc <= 200 * 1024, "aggregate needs %zu bytes of shared memory", smem_acc);
+  SB_CUDA(cudaFuncSetAttribute(kc.direct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_acc));
   // persistent grids are sized from the kernel's REAL residency (registers may allow fewer blocks than shared memory does: a
   // grid of 8 blocks per SM over a kernel that fits 6 runs a second, mostly idle wave)
   auto resident_blocks = [&](AggKernel k, size_t smem, int upper) {
@@ -733,11 +766,11 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
   int blocks_per_sm = resident_blocks(kc.direct, smem_acc, dict_blocks_per_sm(AGG_DICT));
   int grid = grid_for(n, AGG_THREADS * kc.items_direct, rt().num_sms * blocks_per_sm);
   // the automatic chain's geometry (k1 defines the tiles; k2 walks k1's tiles with fewer, fatter blocks)
-  if (kc.k1_wide && dict_blocks_per_sm(8) == dict_blocks_per_sm(4)) {   // light plan: the 8-entry dictionary costs no occupancy, so
+  if (kc.k1_wide && light_plan) {   // light plan: the 8-entry dictionary costs no occupancy, so
     kc.k1 = kc.k1_wide;                                                 // it goes first and a 32-entry one (if it keeps >= 4
     kc.k1_dict = 8;                                                     // blocks per SM) catches 9..32 groups before the
     kc.k2 = nullptr;                                                    // shared-memory tier and its atomics
-    if (kc.k2_big && dict_blocks_per_sm(32) >= 4) {
+    if (kc.k2_big && big_dict_ok) {
       kc.k2 = kc.k2_big;
       kc.k2_dict = 32;
     }
@@ -750,10 +783,7 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
   // ---- tiers: "dict" (lane-private dictionary + HBM table), "smem" (shared-memory table + HBM table), or "auto": the
   // dictionary kernel starts, yields as soon as the input turns out not to be a few-groups shape, and the shared-memory kernel
   // launched behind it finishes the job (AggArgs::gate) -- no sample pass, no host round trip.
-  const char *tier_env = getenv("SB_AGG_TIER");
-  int tier = 0;   // 0 auto, 1 dict only, 2 smem only
-  if (tier_env && !strcmp(tier_env, "dict")) tier = 1;
-  else if (tier_env && !strcmp(tier_env, "smem")) tier = 2;
+  int tier = config().agg_tier;   // 0 auto, 1 dict only, 2 smem only (tests force a tier through sb_config_set)
   int32_t scap = 8192;
   while (scap > 512 && (size_t)(scap + 2) * (1 + ns) * 8 + 64 > 200 * 1024) scap >>= 1;
   // tiny inputs (the Final stage of a few-group aggregate: a handful of rows) are pure latency: one block, rows straight into
@@ -774,9 +804,8 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
   a.scap = scap;
 
   // ---- staged (TMA) path: lay out one shared-memory stage holding the tile of every distinct referenced buffer ----
-  const char *path_env = getenv("SB_AGG_PATH");   // "direct" | "staged" (default: direct)
   const int64_t stile = (int64_t)AGG_THREADS * ITEMS_STAGED;
-  bool staged = a.nwords == 1 && n >= stile && path_env && strcmp(path_env, "staged") == 0;
+  bool staged = a.nwords == 1 && n >= stile && config().agg_staged != 0;   // experiment, off by default
   size_t smem_staged = 0;
   int grid_staged = 0;
   if (staged) {
@@ -852,9 +881,9 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
     if (n > 0) {
       KernelTimer kt(final_mode ? "agg_update_final" : "agg_update", st);
       a.gate = 0;
-      if (a.nwords == 1 && staged) kc.staged<<<grid_staged, AGG_THREADS, smem_staged, st>>>(a);
-      else if (a.nwords == 1 && tier == 1) kc.direct<<<grid, AGG_THREADS, smem_acc, st>>>(a);
-      else if (a.nwords == 1 && tier == 2) kc.smem<<<grid_smem, AGGS_THREADS, smem_tab, st>>>(a);
+      if (a.nwords == 1 && staged) launch_agg(kc.staged, grid_staged, AGG_THREADS, smem_staged, st, a);
+      else if (a.nwords == 1 && tier == 1) launch_agg(kc.direct, grid, AGG_THREADS, smem_acc, st, a);
+      else if (a.nwords == 1 && tier == 2) launch_agg(kc.smem, grid_smem, AGGS_THREADS, smem_tab, st, a);
       else if (a.nwords == 1) {
         a.gate = 1;
         a.progress = progress.as<int32_t>();
@@ -862,14 +891,14 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
         a.last_flag = kc.k2 ? 7 : 6;
         a.dict_grid = grid_k1;
         a.dict_items = kc.k1_items;
-        kc.k1<<<grid_k1, AGG_THREADS, smem_k1, st>>>(a);
+        launch_agg(kc.k1, grid_k1, AGG_THREADS, smem_k1, st, a);
         SB_LAUNCH_CHECK();
         if (kc.k2) {
-          kc.k2<<<grid_k2, AGG_THREADS, smem_k2, st>>>(a);
+          launch_agg(kc.k2, grid_k2, AGG_THREADS, smem_k2, st, a);
           SB_LAUNCH_CHECK();
         }
         a.gate = 2;
-        kc.smem<<<grid_smem, AGGS_THREADS, smem_tab, st>>>(a);
+        launch_agg(kc.smem, grid_smem, AGGS_THREADS, smem_tab, st, a);
       }
       else if (a.nwords == 2) agg_update_wide_kernel<2, 4><<<grid, AGG_THREADS, 0, st>>>(a);
       else if (a.nwords == 3) agg_update_wide_kernel<3, 4><<<grid, AGG_THREADS, 0, st>>>(a);
@@ -898,7 +927,8 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
     cudaFreeAsync(tacc, st); tacc = nullptr;
     cap = cap * 16 > cap_max ? cap_max : cap * 16;
   }
-  if (getenv("SB_AGG_VERBOSE")) fprintf(stderr, "[sb_hash_aggregate] n=%lld plan=%s path=%s tier=%s cap=%lld slots=%d scap=%d\n", (long long)n, kc.name,
+  g_last_plan_name = kc.name;
+  if (config().agg_verbose) fprintf(stderr, "[sb_hash_aggregate] n=%lld plan=%s path=%s tier=%s cap=%lld slots=%d scap=%d\n", (long long)n, kc.name.c_str(),
                                         a.nwords > 1 ? "wide" : (staged ? "staged" : "direct"), tier == 0 ? "auto" : (tier == 1 ? "dict" : "smem"),
                                         (long long)cap, ns, scap);
   Scratch &slot_ids = *slot_ids_buf;
@@ -967,9 +997,174 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
 
 using namespace sb;
 
+// Compile check of the run-time specialisation for a PlanMeta given as raw int32 words (no device needed): used by the
+// CPU-side build check so that a header change that breaks NVRTC compilation is caught without a GPU.
+extern "C" int sb_agg_rtc_compile_check(const int32_t *plan_meta_words, int32_t nwords, char *log, int32_t log_len) {
+  SB_API_BEGIN
+  SB_REQUIRE(plan_meta_words && nwords == (int32_t)(sizeof(PlanMeta) / 4), "expected %d PlanMeta words, got %d", (int)(sizeof(PlanMeta) / 4), nwords);
+  PlanMeta m;
+  memcpy(&m, plan_meta_words, sizeof(m));
+  const void *k[6];
+  std::string lg;
+  const bool ok = specialise_kernels(m, chain_items(m), NEED_ALL, false, k, &lg, nullptr);
+  if (log && log_len > 0) snprintf(log, (size_t)log_len, "%s", lg.c_str());
+  if (!ok) fail(SB_ERR_UNSUPPORTED, "run-time compilation failed: %s", lg.c_str());
+  SB_API_END
+}
+extern "C" int32_t sb_agg_plan_meta_words(void) { return (int32_t)(sizeof(PlanMeta) / 4); }
+
+// which kernels the calling thread's last sb_hash_aggregate ran: "generic" or "rtc:<plan hash>[(disk)]"
+extern "C" const char *sb_hash_aggregate_last_plan(void) { return g_last_plan_name.c_str(); }
+
 extern "C" int sb_hash_aggregate(const sb_table *in, const sb_agg_plan *plan, sb_stream *s, sb_table **out) {
   SB_API_BEGIN
   require_init();
   hash_aggregate_impl(in, plan, stream_of(s), out);
+  SB_API_END
+}
+
+// ---- aggregation state across an iterator of batches ----------------------------------------------------------------
+// TungstenAggregationIterator.processInputs (TungstenAggregationIterator.scala:206-281) folds every input row of the
+// partition into one map.  Here each batch is aggregated on its own (one pass, the kernels above) into a Partial table
+// (keys ++ buffers) that is parked in the state; parked tables are merged (PartialMerge: buffers -> buffers) whenever
+// they add up to more than kCompactRows rows, and once more in finish().  Nothing is concatenated at input size: a batch
+// can be released as soon as update() returns, and HBM holds one batch plus the groups seen so far.
+struct sb_agg_state {
+  sb_agg_plan plan;                       // deep copy (the arrays below back its pointers)
+  std::vector<int32_t> key_cols;
+  std::vector<sb_agg_spec> aggs;
+  std::vector<std::vector<sb_expr_node>> nodes;
+  sb_expr filter;
+  std::vector<sb_expr_node> filter_nodes;
+  std::vector<int32_t> merged_keys;       // 0..nkeys-1: where the keys sit in a Partial table
+  std::vector<sb_table *> parked;
+  int64_t parked_rows = 0;
+  std::mutex mu;
+};
+static constexpr int64_t kCompactRows = 1 << 22;
+static constexpr size_t kCompactTables = 64;
+
+static sb_table *agg_state_merge(sb_agg_state *st, int mode, cudaStream_t cs) {   // all parked tables -> one table of `mode`
+  sb_table *cat = nullptr;
+  if (st->parked.size() == 1) {
+    cat = st->parked[0];
+    cat->refs.fetch_add(1);
+  } else {
+    sb_stream tmp;
+    tmp.stream = cs;
+    int rc = sb_table_concat(st->parked.data(), (int32_t)st->parked.size(), &tmp, &cat);
+    if (rc != SB_OK) fail(rc, "%s", sb_last_error());
+  }
+  sb_agg_plan p = st->plan;
+  p.mode = mode;
+  p.key_cols = st->merged_keys.data();
+  p.filter = nullptr;
+  sb_table *out = nullptr;
+  try {
+    hash_aggregate_impl(cat, &p, cs, &out);
+  } catch (...) {
+    sb_table_release(cat);
+    throw;
+  }
+  sb_table_release(cat);
+  return out;
+}
+
+extern "C" int sb_hash_agg_create(const sb_agg_plan *plan, sb_agg_state **out) {
+  SB_API_BEGIN
+  require_init();
+  SB_REQUIRE(plan && out, "null argument");
+  SB_REQUIRE(plan->mode >= SB_AGG_MODE_PARTIAL && plan->mode <= SB_AGG_MODE_PARTIAL_MERGE, "bad aggregate mode %d", plan->mode);
+  SB_REQUIRE(plan->nkeys >= 0 && plan->naggs >= 0 && plan->nkeys <= AGG_MAX_KEYS, "bad plan");
+  std::unique_ptr<sb_agg_state> st(new sb_agg_state());
+  st->plan = *plan;
+  st->key_cols.assign(plan->key_cols, plan->key_cols + plan->nkeys);
+  st->aggs.assign(plan->aggs, plan->aggs + plan->naggs);
+  st->nodes.resize(plan->naggs);
+  for (int i = 0; i < plan->naggs; i++) {
+    const sb_expr &e = plan->aggs[i].input;
+    if (e.nodes && e.n > 0) {
+      st->nodes[i].assign(e.nodes, e.nodes + e.n);
+      st->aggs[i].input.nodes = st->nodes[i].data();
+    } else {
+      st->aggs[i].input.nodes = nullptr;
+      st->aggs[i].input.n = 0;
+    }
+  }
+  st->plan.key_cols = st->key_cols.data();
+  st->plan.aggs = st->aggs.data();
+  st->plan.filter = nullptr;
+  if (plan->filter) {
+    st->filter_nodes.assign(plan->filter->nodes, plan->filter->nodes + plan->filter->n);
+    st->filter = *plan->filter;
+    st->filter.nodes = st->filter_nodes.data();
+    st->plan.filter = &st->filter;
+  }
+  for (int i = 0; i < plan->nkeys; i++) st->merged_keys.push_back(i);
+  *out = st.release();
+  SB_API_END
+}
+
+static void agg_state_park(sb_agg_state *st, sb_table *t, cudaStream_t cs) {
+  st->parked.push_back(t);
+  st->parked_rows += t->nrows;
+  if (st->parked.size() > 1 && (st->parked_rows > kCompactRows || st->parked.size() >= kCompactTables)) {
+    sb_table *m = agg_state_merge(st, SB_AGG_MODE_PARTIAL_MERGE, cs);
+    for (auto *p : st->parked) sb_table_release(p);
+    st->parked.clear();
+    st->parked.push_back(m);
+    st->parked_rows = m->nrows;
+  }
+}
+
+extern "C" int sb_hash_agg_update(sb_agg_state *st, const sb_table *batch, sb_stream *s) {
+  SB_API_BEGIN
+  require_init();
+  SB_REQUIRE(st && batch, "null argument");
+  std::lock_guard<std::mutex> lk(st->mu);
+  cudaStream_t cs = stream_of(s);
+  sb_table *part = nullptr;
+  if (st->plan.mode == SB_AGG_MODE_FINAL || st->plan.mode == SB_AGG_MODE_PARTIAL_MERGE) {
+    // the input already is keys ++ buffers: bring the keys to the front so that parked tables share one layout
+    sb_agg_plan p = st->plan;
+    p.mode = SB_AGG_MODE_PARTIAL_MERGE;
+    hash_aggregate_impl(batch, &p, cs, &part);
+  } else {
+    sb_agg_plan p = st->plan;
+    p.mode = SB_AGG_MODE_PARTIAL;
+    hash_aggregate_impl(batch, &p, cs, &part);
+  }
+  agg_state_park(st, part, cs);
+  SB_API_END
+}
+
+extern "C" int sb_hash_agg_merge(sb_agg_state *st, const sb_table *partial, sb_stream *s) {
+  SB_API_BEGIN
+  require_init();
+  SB_REQUIRE(st && partial, "null argument");
+  std::lock_guard<std::mutex> lk(st->mu);
+  sb_table *t = const_cast<sb_table *>(partial);   // keys ++ buffers in Partial layout (another state's finish, an exchange)
+  t->refs.fetch_add(1);
+  agg_state_park(st, t, stream_of(s));
+  SB_API_END
+}
+
+extern "C" int sb_hash_agg_finish(sb_agg_state *st, sb_stream *s, sb_table **out) {
+  SB_API_BEGIN
+  require_init();
+  SB_REQUIRE(st && out, "null argument");
+  std::lock_guard<std::mutex> lk(st->mu);
+  SB_REQUIRE(!st->parked.empty(), "sb_hash_agg_finish before any batch (pass an empty batch for an empty partition)");
+  const bool results = st->plan.mode == SB_AGG_MODE_FINAL || st->plan.mode == SB_AGG_MODE_COMPLETE;
+  *out = agg_state_merge(st, results ? SB_AGG_MODE_FINAL : SB_AGG_MODE_PARTIAL_MERGE, stream_of(s));
+  SB_API_END
+}
+
+extern "C" int sb_hash_agg_destroy(sb_agg_state *st) {
+  SB_API_BEGIN
+  if (st) {
+    for (auto *p : st->parked) sb_table_release(p);
+    delete st;
+  }
   SB_API_END
 }

@@ -15,6 +15,7 @@
 #include <nccl.h>
 #include "common.cuh"
 #include "primitives.cuh"
+#include "rtc.cuh"
 
 namespace sb {
 
@@ -250,7 +251,8 @@ int sb_comm_init(int32_t rank, int32_t nranks, const uint8_t id_bytes[SB_UNIQUE_
   SB_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "bad rank %d of %d", rank, nranks);
   Comm &c = comm();
   SB_REQUIRE(c.comm == nullptr, "communicator already initialised");
-  if (nranks > 1) {
+  if (nranks > 1 || id_bytes) {   // a one-rank communicator is a real NCCL communicator too (self-exchange tests)
+    SB_REQUIRE(id_bytes, "sb_comm_init needs the unique id");
     ncclUniqueId id;
     memcpy(&id, id_bytes, SB_UNIQUE_ID_BYTES);
     SB_NCCL(nccl().CommInitRank(&c.comm, nranks, id, rank));
@@ -301,7 +303,7 @@ int sb_all_to_all(const sb_table *in, const int64_t *part_offsets_host, int32_t 
   require_init();
   SB_REQUIRE(in && part_offsets_host && out && out_part_offsets_host, "null argument");
   Comm &c = comm();
-  SB_REQUIRE(c.nranks > 1 && c.comm, "sb_all_to_all needs an initialised communicator with more than one rank");
+  SB_REQUIRE(c.comm, "sb_all_to_all needs an initialised communicator (sb_comm_init)");
   cudaStream_t st = stream_of(s);
   const int R = c.nranks;
   const int P = num_partitions;
@@ -382,7 +384,7 @@ int sb_all_to_all(const sb_table *in, const int64_t *part_offsets_host, int32_t 
     }
     return cur;
   };
-  static const bool force_nccl = [] { const char *e = getenv("SB_EXCHANGE"); return e && !strcmp(e, "nccl"); }();
+  const bool force_nccl = config().exchange_nccl != 0;
   bool peer_path = !force_nccl && !has_string;
   if (peer_path) {
     size_t need = 0;
@@ -552,7 +554,7 @@ int sb_all_gather(const sb_table *in, sb_stream *s, sb_table **out) {
   SB_REQUIRE(in && out, "null argument");
   Comm &c = comm();
   cudaStream_t st = stream_of(s);
-  if (c.nranks <= 1 || !c.comm) {   // single executor: the broadcast is the table itself
+  if (!c.comm) {   // no communicator: single executor, the broadcast is the table itself
     sb_table *t = table_new(in->nrows);
     for (auto &col : in->cols) t->cols.push_back(column_share(col));
     *out = t;

@@ -11,6 +11,7 @@
 #include <vector>
 #include "expr.cuh"
 #include "primitives.cuh"
+#include "rtc.cuh"
 
 namespace sb {
 
@@ -425,7 +426,7 @@ void eval_predicate(const sb_table *in, const sb_expr &pred, uint8_t *mask, cuda
   if (n == 0) return;
   KernelTimer kt("filter_project", st);
   SimplePred sp;
-  const bool no_fast = getenv("SB_EXPR_INTERPRET_ONLY") != nullptr;   // parity tests run both paths
+  const bool no_fast = config().expr_interpret_only != 0;   // parity tests run both paths
   if (!no_fast && ((uintptr_t)mask & 15) == 0 && match_simple_predicate(in, pred, sp)) {
     const int64_t threads = (n + SP_ROWS - 1) / SP_ROWS;
     simple_predicate_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(sp, n, mask);

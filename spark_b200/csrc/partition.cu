@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include "primitives.cuh"
 #include "multisplit.cuh"
+#include "rtc.cuh"
 
 namespace sb {
 
@@ -633,8 +634,8 @@ static void regroup_pass(const int32_t *bucket_dev, uint32_t *hist_dev, int32_t 
   while (first || done < ncols) {
     RegroupCols rc;
     rc.ncols = 0;
-    static const int max_cols = [] { const char *e = getenv("SB_RG_MAXCOLS"); int v = e ? atoi(e) : SCATTER_MAX_COLS; return v < 1 ? 1 : (v > SCATTER_MAX_COLS ? SCATTER_MAX_COLS : v); }();
-    static const int l2_stream = [] { const char *e = getenv("SB_RG_L2HINT"); return e ? atoi(e) : 0; }();
+    const int max_cols = SCATTER_MAX_COLS;
+    const int l2_stream = 0;
     while (done < ncols && rc.ncols < max_cols) {
       const SplitCol &c = cols[done++];
       int k = rc.ncols++;
@@ -646,8 +647,8 @@ static void regroup_pass(const int32_t *bucket_dev, uint32_t *hist_dev, int32_t 
     }
     if (rc.ncols > 0 || (first && perm_out)) {
       // the copy engine wants 16-byte aligned sources; anything else (a caller-provided, oddly offset device buffer) takes the
-      // load/store kernel.  SB_REGROUP_PATH=ldst forces it (A/B measurements).
-      static const bool force_ldst = [] { const char *e = getenv("SB_REGROUP_PATH"); return e && !strcmp(e, "ldst"); }();
+      // load/store kernel (sb_config_set("regroup_ldst", 1) forces it: the parity tests run both).
+      const bool force_ldst = config().regroup_ldst != 0;
       bool aligned = ((uintptr_t)bucket_dev & 15) == 0;
       for (int k = 0; k < rc.ncols; k++) aligned = aligned && ((uintptr_t)rc.src[k] & 15) == 0;
       KernelTimer kt("partition_scatter", st);
@@ -657,11 +658,8 @@ static void regroup_pass(const int32_t *bucket_dev, uint32_t *hist_dev, int32_t 
           SB_CUDA(cudaFuncSetAttribute(regroup_tma_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, RGT_STAGES * RG_TILE_SMALL * 8));
           SB_CUDA(cudaFuncSetAttribute(regroup_tma_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, RGT_STAGES * RG_TILE_BIG * 8));
         });
-        static const int bps_env = [] { const char *e = getenv("SB_RG_BLOCKS_PER_SM"); return e ? atoi(e) : 0; }();
-        static const int grid_override = [] { const char *e = getenv("SB_RG_GRID"); return e ? atoi(e) : 0; }();
-        const int bps = bps_env > 0 ? bps_env : (big ? 1 : 2);
-        int grid = g.nblocks < rt().num_sms * bps ? g.nblocks : rt().num_sms * bps;
-        if (grid_override > 0 && grid_override < grid) grid = grid_override;
+        const int bps = big ? 1 : 2;
+        const int grid = g.nblocks < rt().num_sms * bps ? g.nblocks : rt().num_sms * bps;
         if (big)
           regroup_tma_kernel<1024><<<grid, 1024, RGT_STAGES * RG_TILE_BIG * 8, st>>>(rc, bucket_dev, hist_dev, n, nb, (int64_t)g.nblocks,
                                                                                   first ? perm_out : nullptr, l2_stream);
@@ -747,8 +745,7 @@ static void partition_impl(const sb_table *in, const int32_t *key_cols, int32_t 
   if (mode == 0) keys = make_keys(in, key_cols, nkeys);
   int64_t rowbytes = 0;
   for (auto &c : in->cols) rowbytes += c.type == SB_STRING ? 8 : type_width(c.type);   // strings travel as row ids
-  static const int tile_env = [] { const char *e = getenv("SB_RG_TILE"); return e ? atoi(e) : 0; }();   // 4096 | 8192 (A/B measurements)
-  const bool big_tiles = tile_env ? tile_env == 8192 : (nparts >= 64 && rowbytes >= 32);
+  const bool big_tiles = nparts >= 64 && rowbytes >= 32;
   PartGeometry g = part_geometry(n, nparts, big_tiles);
   Scratch pid(n * 4 + 16, st);
   Scratch hist((int64_t)nparts * g.nblocks * 4 + 16, st);

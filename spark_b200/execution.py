@@ -165,6 +165,25 @@ class HashAggregateExec(SparkPlan):
         plan.expected_groups = self.expected_groups
         return plan, key_idx, (keep, key_arr, specs)
 
+    def new_state(self, first_batch: ColumnarBatch) -> "AggregationState":
+        return AggregationState(self, _schema_of(first_batch), first_batch.arrow_types)
+
+    def execute_batches(self, batches, stream=None) -> ColumnarBatch:
+        """doExecuteColumnar over an iterator of batches: every batch is folded into one state and closed."""
+        state = None
+        try:
+            for b in batches:
+                if state is None:
+                    state = self.new_state(b)
+                state.update(b, stream)
+                b.close()
+            if state is None:
+                raise capi.SparkB200Error(2, "execute_batches needs at least one (possibly empty) batch")
+            return state.finish(stream)
+        finally:
+            if state is not None:
+                state.close()
+
     def run(self, inp: ColumnarBatch, stream=None) -> ColumnarBatch:
         lib = capi.load()
         schema = _schema_of(inp)
@@ -178,6 +197,46 @@ class HashAggregateExec(SparkPlan):
         names = self.output_names()
         ats = [inp.arrow_types[i] for i in key_idx] + [None] * (len(names) - len(key_idx))
         return ColumnarBatch(h, names, ats)
+
+
+class AggregationState:
+    """The aggregation map a task keeps while it drains its iterator of batches
+    (TungstenAggregationIterator.processInputs, TungstenAggregationIterator.scala:206-281): sb_hash_agg_* state.
+    `update` folds one ColumnarBatch in and the batch can be closed right away; `finish` returns what the
+    operator's mode promises (partial: keys ++ buffers, complete / final: keys ++ results)."""
+
+    def __init__(self, agg: "HashAggregateExec", schema: Schema, arrow_types=None):
+        lib = capi.load()
+        self.agg = agg
+        self.plan, self.key_idx, self._keepalive = agg._compile(schema)
+        self.arrow_types = arrow_types
+        h = C.c_void_p()
+        capi.check(lib.sb_hash_agg_create(C.byref(self.plan), C.byref(h)))
+        self.handle = h
+
+    def update(self, batch: ColumnarBatch, stream=None):
+        capi.check(capi.load().sb_hash_agg_update(self.handle, batch.handle, _h(stream)))
+
+    def merge(self, partial: ColumnarBatch, stream=None):
+        capi.check(capi.load().sb_hash_agg_merge(self.handle, partial.handle, _h(stream)))
+
+    def finish(self, stream=None) -> ColumnarBatch:
+        h = C.c_void_p()
+        capi.check(capi.load().sb_hash_agg_finish(self.handle, _h(stream), C.byref(h)))
+        names = self.agg.output_names()
+        ats = [self.arrow_types[i] if self.arrow_types else None for i in self.key_idx] + [None] * (len(names) - len(self.key_idx))
+        return ColumnarBatch(h, names, ats)
+
+    def close(self):
+        if self.handle:
+            capi.load().sb_hash_agg_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class HashPartitioning:

@@ -233,3 +233,56 @@ def q5_plan(customer, orders, lineitem, supplier, nation, region) -> SparkPlan:
     aggs = [(Sum(col("l_extendedprice") * (Literal(1) - col("l_discount"))), "revenue")]
     agg = HashAggregateExec(["n_name"], aggs, HashAggregateExec(["n_name"], aggs, same_nation, mode="partial"), mode="final")
     return SortExec([("revenue", False, False)], agg)
+
+
+# ------------------------------------------------------------------------------------------ synthetic dataset (include/sb_synth.h)
+SYNTH_TABLE = {"lineitem": 1, "orders": 2, "customer": 3, "supplier": 4}
+SYNTH_COLUMNS = {
+    "lineitem": ["l_orderkey", "l_partkey", "l_suppkey", "l_linenumber", "l_quantity", "l_extendedprice", "l_discount", "l_tax",
+                 "l_returnflag", "l_linestatus", "l_shipdate", "l_commitdate", "l_receiptdate"],
+    "orders": ["o_orderkey", "o_custkey", "o_orderdate", "o_shippriority"],
+    "customer": ["c_custkey", "c_mktsegment", "c_nationkey"],
+    "supplier": ["s_suppkey", "s_nationkey"],
+}
+_SYNTH_NP = {8: np.int64, 4: np.int32, 1: np.int8}
+_F64_COLS = {"l_quantity", "l_extendedprice", "l_discount", "l_tax"}
+_DATE_COLS = {"l_shipdate", "l_commitdate", "l_receiptdate", "o_orderdate"}
+Q1_COLUMNS = ["l_quantity", "l_extendedprice", "l_discount", "l_tax", "l_returnflag", "l_linestatus", "l_shipdate"]
+CONFIG4_COLUMNS = SYNTH_COLUMNS["lineitem"]          # the 74 B/row fixed-width lineitem row of BASELINE.json configs[3]
+CONFIG4_BYTES_PER_ROW = 74
+
+
+def synth_width(name):
+    if name in _F64_COLS or name.endswith("key"):
+        return 8
+    if name in ("l_returnflag", "l_linestatus", "c_mktsegment"):
+        return 1
+    return 4
+
+
+def synth_dtype(name):
+    return np.float64 if name in _F64_COLS else _SYNTH_NP[synth_width(name)]
+
+
+def synth_rows(table: str, n_orders: int) -> int:
+    if table == "lineitem":
+        return (n_orders // 7) * 28 + [0, 1, 3, 6, 10, 15, 21][n_orders % 7]
+    if table == "orders":
+        return n_orders
+    return max(1, n_orders // (10 if table == "customer" else 150))
+
+
+def synth_batch(table: str, columns, n_orders: int, seed: int = 42, first_row: int = 0, nrows: int = None, stream=None):
+    """Columns of the synthetic dataset generated on the GPU (sb_synth_table): a ColumnarBatch resident in HBM."""
+    import ctypes as C
+    from . import _capi as capi
+    from .columnar import ColumnarBatch, _h
+    lib = capi.init()
+    ids = [SYNTH_COLUMNS[table].index(c) for c in columns]
+    arr = (C.c_int32 * len(ids))(*ids)
+    if nrows is None:
+        nrows = synth_rows(table, n_orders) - first_row
+    h = C.c_void_p()
+    capi.check(lib.sb_synth_table(SYNTH_TABLE[table], arr, len(ids), n_orders, first_row, nrows, seed, _h(stream), C.byref(h)))
+    ats = [pa.date32() if c in _DATE_COLS else pa.from_numpy_dtype(synth_dtype(c)) for c in columns]
+    return ColumnarBatch(h, list(columns), ats)

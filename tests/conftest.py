@@ -26,3 +26,18 @@ def stream(gpu):
     s = Stream()
     yield s
     s.close()
+
+
+@pytest.fixture()
+def sbconfig(gpu):
+    """sb_config_set with automatic restore (replaces the environment knobs of round 1)."""
+    from spark_b200 import _capi as capi
+    saved = {}
+
+    def set_(key, value):
+        if key not in saved:
+            saved[key] = capi.config_get(key)
+        capi.config_set(key, value)
+    yield set_
+    for k, v in saved.items():
+        capi.config_set(k, v)

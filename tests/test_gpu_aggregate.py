@@ -192,23 +192,28 @@ def test_filter_project_operator(gpu, stream):
     assert_tables_equal(got, want, ordered=True)
 
 
-@pytest.mark.parametrize("env", [{}, {"SB_AGG_DISABLE_STATIC": "1"}, {"SB_AGG_PATH": "staged"},
-                                 {"SB_AGG_PATH": "staged", "SB_AGG_DISABLE_STATIC": "1"}, {"SB_AGG_Q1_VARIANT": "4"},
-                                 {"SB_AGG_TIER": "smem"}, {"SB_AGG_TIER": "dict"}],
-                         ids=["static-direct", "dynamic-direct", "static-tma", "dynamic-tma", "static-direct-4rows", "smem-tier", "dict-tier"])
-def test_every_update_kernel_variant_matches_the_oracle(gpu, stream, env, monkeypatch):
-    """The plan-specialised (StaticPlan), generic (DynPlan), direct-load and TMA-staged update kernels share one code base;
-    each variant must produce the oracle's Q1 answer, including a ragged last tile and a NULL-able variant of the plan."""
+@pytest.mark.parametrize("env", [{"agg_rtc_min_rows": 0}, {"agg_rtc": 0}, {"agg_staged": 1},
+                                 {"agg_tier": 2, "agg_rtc_min_rows": 0}, {"agg_tier": 1, "agg_rtc_min_rows": 0}, {"agg_tier": 2, "agg_rtc": 0},
+                                 {"agg_tier": 1, "agg_rtc": 0}],
+                         ids=["rtc-chain", "generic-chain", "generic-tma", "rtc-smem-tier", "rtc-dict-tier", "generic-smem-tier", "generic-dict-tier"])
+def test_every_update_kernel_variant_matches_the_oracle(gpu, stream, env, sbconfig):
+    """The run-time specialised (NVRTC, StaticPlan), generic (DynPlan), direct-load and TMA-staged update kernels share one code
+    base; each variant must produce the oracle's Q1 answer, including a ragged last tile and a NULL-able variant of the plan."""
     from spark_b200 import tpch
     from spark_b200.columnar import ColumnarBatch
     from spark_b200.execution import HashAggregateExec, LocalTableScanExec
     from spark_b200.expressions import Average, Count, Literal, Max, Sum, col
+    from spark_b200 import _capi as capi
     for k, v in env.items():
-        monkeypatch.setenv(k, v)
+        sbconfig(k, v)
     t = tpch.lineitem_q1_table(300_017, seed=21)          # not a multiple of any tile size
     batch = ColumnarBatch.from_arrow(t, stream)
     got = tpch.q1_final_plan(tpch.q1_partial_plan(LocalTableScanExec(batch), fused=True), sort=False).collect(stream)
     assert_tables_equal(got, _q1_oracle(t), key_cols=["l_returnflag", "l_linestatus"])
+    if env.get("agg_rtc_min_rows") == 0:   # the specialised kernels really ran (the Final stage's 4 rows run generic: check the log of Partial)
+        part = tpch.q1_partial_plan(LocalTableScanExec(batch), fused=True).executeColumnar(stream)
+        part.close()
+        assert capi.load().sb_hash_aggregate_last_plan().decode().startswith("rtc:"), capi.load().sb_hash_aggregate_last_plan()
     # same shape with NULLs in a key, an input and the filter column -> never matches a static table, exercises validity staging
     rng = np.random.default_rng(3)
     n = t.num_rows
@@ -230,7 +235,7 @@ def test_every_update_kernel_variant_matches_the_oracle(gpu, stream, env, monkey
 
 @pytest.mark.parametrize("groups", [5, 1000, 6000, 200_000])
 @pytest.mark.parametrize("tier", ["auto", "smem", "dict"])
-def test_cardinality_tiers_agree_with_the_oracle(gpu, stream, groups, tier, monkeypatch):
+def test_cardinality_tiers_agree_with_the_oracle(gpu, stream, groups, tier, sbconfig):
     """Few groups (lane-private dictionary), a few thousand (shared-memory table), more than the shared-memory table holds
     (spill to the HBM table, then bypass): every tier and the sampled automatic choice give the oracle's answer.  Keys include
     NULL and -1 (the bit pattern of the table's EMPTY sentinel); inputs include NULLs; min/max/avg/count ride along."""
@@ -238,7 +243,7 @@ def test_cardinality_tiers_agree_with_the_oracle(gpu, stream, groups, tier, monk
     from spark_b200.execution import HashAggregateExec, LocalTableScanExec
     from spark_b200.expressions import Average, Count, Max, Min, Sum, col
     if tier != "auto":
-        monkeypatch.setenv("SB_AGG_TIER", tier)
+        sbconfig("agg_tier", {"dict": 1, "smem": 2}[tier])
     n = 400_037
     rng = np.random.default_rng(groups)
     k = rng.integers(-1, groups - 1, n)
@@ -255,8 +260,9 @@ def test_cardinality_tiers_agree_with_the_oracle(gpu, stream, groups, tier, monk
 
 @pytest.mark.parametrize("groups", [3, 20, 1024])
 @pytest.mark.parametrize("vtype", ["i64", "f64"])
-def test_groupby_sum_static_shapes_through_both_tiers(gpu, stream, groups, vtype):
-    """BASELINE configs[0] shape (k int64, v int64/double, no NULLs): the plan-specialised kernels of both tiers."""
+def test_groupby_sum_static_shapes_through_both_tiers(gpu, stream, groups, vtype, sbconfig):
+    """BASELINE configs[0] shape (k int64, v int64/double, no NULLs): the run-time specialised kernels of every tier."""
+    sbconfig("agg_rtc_min_rows", 0)
     from spark_b200.columnar import ColumnarBatch
     from spark_b200.execution import HashAggregateExec, LocalTableScanExec
     from spark_b200.expressions import Sum, col
@@ -271,14 +277,14 @@ def test_groupby_sum_static_shapes_through_both_tiers(gpu, stream, groups, vtype
 
 @pytest.mark.parametrize("interpret_only", [False, True], ids=["typed-fast-path", "interpreter"])
 @pytest.mark.parametrize("n", [1, 15, 16, 17, 4097, 100_003])
-def test_filter_predicates_of_every_type(gpu, stream, n, interpret_only, monkeypatch):
+def test_filter_predicates_of_every_type(gpu, stream, n, interpret_only, sbconfig):
     """FilterExec (basicPhysicalOperators.scala:245): conjunctions of column-vs-literal comparisons take the typed 16-rows-per-thread
     kernel, everything else the interpreter; both must keep exactly the oracle's rows (NULL comparisons drop the row, NaN is the
     largest double and equals itself, literal-on-the-left flips the operator), at sizes around the 16-row vector width."""
     from spark_b200.execution import FilterExec
     from spark_b200.expressions import Literal, col
     if interpret_only:
-        monkeypatch.setenv("SB_EXPR_INTERPRET_ONLY", "1")
+        sbconfig("expr_interpret_only", 1)
     rng = np.random.default_rng(n)
     d = rng.standard_normal(n)
     d[rng.random(n) < 0.1] = np.nan
