@@ -17,8 +17,9 @@ carries the same fields for q3, q5 and (N > 1) shuffle.  Per leg:
   value      lineitem rows / s with the columns already resident in HBM (CUDA events on the launching stream, max over ranks)
   e2e        the same plan through the public operator API from HOST buffers: H2D inside the timed region, result read back.
              Q1 reads Parquet-style encoded column chunks (dictionary + RLE/bit-packed pages, PLAIN doubles) and decodes them
-             on the GPU (sb_scan_decode) chunk by chunk into the streaming aggregate (sb_hash_agg_update); Q3/Q5 import plain
-             pinned columns.  h2d_bytes_per_step counts what actually crossed PCIe.
+             on the GPU (sb_scan_decode) row group by row group into the streaming aggregate (sb_hash_agg_update) -- the plain
+             38 B/row variant is reported next to it; Q3/Q5 import plain pinned columns.  h2d_bytes_per_step counts what
+             actually crossed PCIe.
   roofline   dominant kernel: algorithmic bytes / its CUDA-event time (sb_profile_*) vs MEASURED_PEAKS.json
   verified   the GPU result of the measured run equals the CPU oracle's answer on the same rows (keys / counts / order exact,
              floating sums 1e-6 relative); N > 1: checked per rank before the exchange-level merge, and the merged result
@@ -497,34 +498,39 @@ def main():
         v_ms, _, v_prof = time_resident(step_q1, max(3, args.steps // 4), 1, ("agg_update",))
         variants["generic_kernels"] = {"ms_per_step": v_ms, "agg_update_ms": v_prof["agg_update"][0] / max(1, max(3, args.steps // 4))}
         capi.config_set("agg_rtc", 1)
-        # the same query over NULLable columns handed over in another order (what a Parquet scan of a nullable schema gives Spark):
-        # a different PlanMeta, specialised at run time like any other plan
+        # the same query over NULLable columns handed over in another order (what a Parquet scan of a nullable schema gives Spark).
+        # (a) the batch declares null_count = 0 (ColumnVector.hasNull() == false): the bitmaps are never read, same kernels as the
+        #     headline; (b) null_count unknown: every referenced column's validity bitmap is read (another PlanMeta, specialised at
+        #     run time like any plan)
         order = ["l_shipdate", "l_tax", "l_linestatus", "l_discount", "l_returnflag", "l_extendedprice", "l_quantity"]
         ones = torch.full(((n_li + 7) // 8 + 64,), 255, dtype=torch.uint8, device="cuda")
-        descs = (capi.sb_column * len(order))()
-        for i, name in enumerate(order):
-            d = lineitem.column_desc(lineitem.column_index(name))
-            descs[i] = d
-            descs[i].validity = ones.data_ptr()
-            descs[i].null_count = 0
-        hN = C.c_void_p()
-        capi.check(lib.sb_table_import_device(descs, len(order), C.byref(hN)))
-        nullable = ColumnarBatch(hN, order, [lineitem.arrow_types[lineitem.column_index(c)] for c in order])
-        q1n_plan = tpch.q1_final_plan(AllGatherExec(tpch.q1_partial_plan(BatchSource(nullable), fused=True)), sort=True)
-
-        def step_q1n():
-            out = q1n_plan.executeColumnar(stream)
-            out.close()
         vsteps = max(3, args.steps // 4)
-        n_ms, _, n_prof = time_resident(step_q1n, vsteps, 2, ("agg_update",))
-        n_kernel = n_prof["agg_update"][0] / vsteps
-        n_bytes = n_li * (tpch.Q1_BYTES_PER_ROW + 7.0 / 8.0)
-        same = check_q1(q1_rows(q1n_plan.collect(stream)), q1_rows(q1_plan.collect(stream))) if world == 1 else None
-        variants["nullable_reordered_columns"] = {"ms_per_step": n_ms, "agg_update_ms": n_kernel, "agg_kernels": lib.sb_hash_aggregate_last_plan().decode(),
-                                                  "achieved_gbs": n_bytes / (n_kernel / 1000.0) / 1e9 if n_kernel else None,
-                                                  "frac": n_bytes / (n_kernel / 1000.0) / 1e9 / peak if n_kernel else None,
-                                                  "bytes_per_row": tpch.Q1_BYTES_PER_ROW + 7.0 / 8.0, "equals_headline_result": same}
-        nullable.close()
+        for vname, null_count in (("nullable_schema_no_nulls_reordered", 0), ("nullable_columns_bitmaps_read_reordered", -1)):
+            descs = (capi.sb_column * len(order))()
+            for i, name in enumerate(order):
+                descs[i] = lineitem.column_desc(lineitem.column_index(name))
+                descs[i].validity = ones.data_ptr()
+                descs[i].null_count = null_count
+            hN = C.c_void_p()
+            capi.check(lib.sb_table_import_device(descs, len(order), C.byref(hN)))
+            nullable = ColumnarBatch(hN, order, [lineitem.arrow_types[lineitem.column_index(c)] for c in order])
+            partial_n = tpch.q1_partial_plan(BatchSource(nullable), fused=True)
+            q1n_plan = tpch.q1_final_plan(AllGatherExec(partial_n), sort=True)
+
+            def step_q1n():
+                out = q1n_plan.executeColumnar(stream)
+                out.close()
+            n_ms, _, n_prof = time_resident(step_q1n, vsteps, 2, ("agg_update",))
+            p_once = partial_n.executeColumnar(stream); p_once.close()
+            n_name = lib.sb_hash_aggregate_last_plan().decode()
+            n_kernel = n_prof["agg_update"][0] / vsteps
+            n_bytes = n_li * (tpch.Q1_BYTES_PER_ROW + (7.0 / 8.0 if null_count else 0.0))
+            same = check_q1(q1_rows(q1n_plan.collect(stream)), q1_rows(q1_plan.collect(stream))) if world == 1 else None
+            variants[vname] = {"ms_per_step": n_ms, "agg_update_ms": n_kernel, "agg_kernels": n_name,
+                               "achieved_gbs": n_bytes / (n_kernel / 1000.0) / 1e9 if n_kernel else None,
+                               "frac": n_bytes / (n_kernel / 1000.0) / 1e9 / peak if n_kernel else None,
+                               "bytes_per_row": n_bytes / n_li, "equals_headline_result": same}
+            nullable.close()
         del ones
         legs["q1"] = {"value": world * n_li / (ms / 1000.0), "unit": "rows/s", "ms_per_step": ms, "steps": args.steps, "rows_per_gpu": n_li,
                       "gpu_launches": int(launches), "verified": verified, "agg_kernels": plan_name, "variants": variants,
@@ -660,12 +666,69 @@ def main():
 
 
 def run_q1_e2e(args, lib, capi, tpch, stream, lineitem, n_li, world, barrier, max_over_ranks, time_e2e, AllGatherExec, q1_rows, legs):
-    """Q1 from host memory through the scan boundary: pinned host columns are imported chunk by chunk (H2D inside the timed
-    region) and folded into one aggregation state (sb_hash_agg_update); the chunk is released before the next one arrives, so
-    HBM holds one chunk plus the groups."""
+    """Q1 from host memory through the scan boundary.  The rank's lineitem shard lies in pinned host memory as Parquet-style
+    column chunks, one set per row group: sorted dictionary + bit-packed RLE_DICTIONARY pages for the low-cardinality columns
+    (quantity, discount, tax, flags, ship date), PLAIN doubles for l_extendedprice (too many distinct values for a dictionary
+    page, as in a real file).  Timed per step: for every row group, the encoded bytes cross PCIe (one copy per column chunk),
+    sb_scan_decode rebuilds the Arrow columns in HBM, sb_hash_agg_update folds them into the aggregation state and the batch is
+    released; then Final + Sort and the 4 result rows come back.  For reference the same plan is also timed from plain (decoded)
+    pinned columns, 38 B/row over PCIe."""
     from spark_b200.columnar import ColumnarBatch, HostColumn, PinnedArray
     from spark_b200.execution import LocalTableScanExec
+    from spark_b200.scan import decode_chunks, encode_column
     cols = tpch.Q1_COLUMNS
+    ats = [lineitem.arrow_types[lineitem.column_index(c)] for c in cols]
+    rg_rows = 1 << 24
+    partial = tpch.q1_partial_plan(LocalTableScanExec(None), fused=True)
+    # ---- untimed: write the row groups (GPU encoder) into pinned host memory ------------------------------------------------
+    q1cols = lineitem.select(cols)
+    groups = []
+    for lo in range(0, n_li, rg_rows):
+        part = q1cols.slice(lo, min(n_li, lo + rg_rows), stream)
+        groups.append([encode_column(part, c, dictionary=c != "l_extendedprice", page_rows=1 << 19, stream=stream, pinned=True) for c in cols])
+        part.close()
+    stream.synchronize()
+    enc_bytes = int(sum(ch.nbytes for g in groups for ch in g))
+
+    from spark_b200.columnar import Stream
+    copy_streams = [stream, Stream()]
+
+    class EncodedPartial:
+        """Software pipeline over the row groups: the copy + decode of row group i + 1 is queued on the other stream before the
+        aggregate update of row group i waits for its own stream, so PCIe stays busy while the GPU decodes and aggregates."""
+
+        def executeColumnar(self, stream=None):
+            state = None
+            nxt = decode_chunks(cols, groups[0], copy_streams[0], ats)
+            try:
+                for i in range(len(groups)):
+                    cur, st_i = nxt, copy_streams[i % 2]
+                    nxt = decode_chunks(cols, groups[i + 1], copy_streams[(i + 1) % 2], ats) if i + 1 < len(groups) else None
+                    if state is None:
+                        state = partial.new_state(cur)
+                    state.update(cur, st_i)
+                    cur.close()
+                for st_i in copy_streams:
+                    st_i.synchronize()
+                return state.finish(stream)
+            finally:
+                if state is not None:
+                    state.close()
+
+    plan = tpch.q1_final_plan(AllGatherExec(EncodedPartial()), sort=True)
+    capi.check(lib.sb_profile_enable(1))
+    capi.check(lib.sb_profile_reset())
+    ms, res = time_e2e(lambda: plan.collect(stream), max(1, args.e2e_steps))
+    dms, dcnt = C.c_double(), C.c_int64()
+    capi.check(lib.sb_profile_get(b"scan_decode", C.byref(dms), C.byref(dcnt)))
+    capi.check(lib.sb_profile_enable(0))
+    d2h = int(sum(res.column(i).nbytes for i in range(res.num_columns)))
+    ok = None
+    if world == 1:
+        want = tpch.q1_final_plan(tpch.q1_partial_plan(LocalTableScanExec(q1cols), fused=True), sort=True).collect(stream)
+        ok = check_q1(q1_rows(res), q1_rows(want))
+    del groups
+    # ---- the same plan from plain pinned columns (38 B/row over PCIe) ----------------------------------------------------------
     pinned = {}
     for c in cols:
         p = PinnedArray(n_li, tpch.synth_dtype(c))
@@ -674,9 +737,7 @@ def run_q1_e2e(args, lib, capi, tpch, stream, lineitem, n_li, world, barrier, ma
     stream.synchronize()
     sbt = {"l_quantity": capi.SB_FLOAT64, "l_extendedprice": capi.SB_FLOAT64, "l_discount": capi.SB_FLOAT64, "l_tax": capi.SB_FLOAT64,
            "l_returnflag": capi.SB_INT8, "l_linestatus": capi.SB_INT8, "l_shipdate": capi.SB_DATE32}
-    ats = [lineitem.arrow_types[lineitem.column_index(c)] for c in cols]
     chunk = 1 << 25
-    partial = tpch.q1_partial_plan(LocalTableScanExec(None), fused=True)
 
     def chunks():
         for lo in range(0, n_li, chunk):
@@ -684,26 +745,24 @@ def run_q1_e2e(args, lib, capi, tpch, stream, lineitem, n_li, world, barrier, ma
             hc = [HostColumn(sbt[c], pinned[c].array[lo:hi]) for c in cols]
             yield ColumnarBatch.from_host_columns(cols, hc, stream, ats)
 
-    class Partial:
+    class PlainPartial:
         def executeColumnar(self, stream=None):
             return partial.execute_batches(chunks(), stream)
 
-    plan = tpch.q1_final_plan(AllGatherExec(Partial()), sort=True)
-
-    def step():
-        return plan.collect(stream)
-
-    ms, res = time_e2e(step, max(1, args.e2e_steps))
-    d2h = int(sum(res.column(i).nbytes for i in range(res.num_columns)))
-    h2d = int(sum(p.nbytes for p in pinned.values()))
-    ok = None
-    if world == 1 and legs["q1"].get("verified") is not None:
-        want = tpch.q1_final_plan(tpch.q1_partial_plan(LocalTableScanExec(lineitem.select(cols)), fused=True), sort=True).collect(stream)
-        ok = check_q1(q1_rows(res), q1_rows(want))
+    plain_plan = tpch.q1_final_plan(AllGatherExec(PlainPartial()), sort=True)
+    pms, pres = time_e2e(lambda: plain_plan.collect(stream), 1)
+    h2d_plain = int(sum(p.nbytes for p in pinned.values()))
     for p in pinned.values():
         p.close()
-    return {"value": world * n_li / (ms / 1000.0), "unit": "rows/s", "ms_per_step": ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-            "input": "plain pinned host columns, %d-row chunks streamed through sb_hash_agg_update" % chunk, "equals_resident_result": ok}
+    q1cols.close()
+    steps_run = max(1, args.e2e_steps) + 1
+    return {"value": world * n_li / (ms / 1000.0), "unit": "rows/s", "ms_per_step": ms, "h2d_bytes_per_step": enc_bytes, "d2h_bytes_per_step": d2h,
+            "input": "Parquet-style encoded column chunks in pinned host memory (%d-row row groups; RLE_DICTIONARY bit-packed pages, PLAIN doubles "
+                     "for l_extendedprice), decoded on the GPU (sb_scan_decode) and streamed through sb_hash_agg_update" % rg_rows,
+            "encoded_bytes_per_row": enc_bytes / n_li, "pcie_gbs": enc_bytes / (ms / 1000.0) / 1e9,
+            "scan_decode_ms_per_step": dms.value / steps_run, "equals_resident_result": ok,
+            "from_plain_columns": {"value": world * n_li / (pms / 1000.0), "ms_per_step": pms, "h2d_bytes_per_step": h2d_plain,
+                                   "input": "plain pinned host columns (38 B/row), %d-row chunks streamed through sb_hash_agg_update" % chunk}}
 
 
 def run_shuffle(args, lib, capi, tpch, stream, rank, world, n_orders, seed, barrier, max_over_ranks, all_true, time_resident, peak, peak_src):

@@ -137,6 +137,51 @@ int sb_table_slice(const sb_table *t, int64_t begin, int64_t end, sb_stream *s, 
 /* concatenation of tables with identical schemas (copies) */
 int sb_table_concat(const sb_table *const *tables, int32_t ntables, sb_stream *s, sb_table **out);
 
+/* ---- columnar scan boundary: Parquet column-chunk pages in host memory -> Arrow columns in HBM.  Replaces the CPU decode of
+ *      VectorizedParquetRecordReader.nextBatch / VectorizedColumnReader.readBatch / VectorizedRleValuesReader
+ *      (sql/core/src/main/java/org/apache/spark/sql/execution/datasources/parquet/) behind FileSourceScanExec.doExecuteColumnar
+ *      (SQLX/DataSourceScanExec.scala:735-760): the ENCODED bytes cross PCIe and the GPU decodes them. ------------------------ */
+#define SB_ENC_PLAIN 0
+#define SB_ENC_RLE_DICTIONARY 1   /* Parquet RLE_DICTIONARY / PLAIN_DICTIONARY data page: [bit width][RLE / bit-packed hybrid runs] */
+#define SB_ENC_RLE_BOOLEAN 2      /* BOOLEAN values as [4-byte length][hybrid runs, bit width 1] (data page V2 writers) */
+#define SB_PHYS_BOOLEAN 0         /* Parquet physical types (parquet.thrift Type) */
+#define SB_PHYS_INT32 1
+#define SB_PHYS_INT64 2
+#define SB_PHYS_FLOAT 4
+#define SB_PHYS_DOUBLE 5
+
+typedef struct sb_page {            /* one data page; offsets are relative to sb_column_chunk.data */
+  int32_t encoding;                 /* SB_ENC_* */
+  int32_t num_values;               /* rows of the page, NULLs included */
+  int64_t values_offset, values_bytes;
+  int64_t def_offset, def_bytes;    /* RLE hybrid of the definition levels (bit width 1, no length prefix); def_bytes == 0: none */
+} sb_page;
+
+typedef struct sb_column_chunk {
+  int32_t type;                     /* SB_* type of the decoded column */
+  int32_t scale;
+  int32_t physical_type;            /* SB_PHYS_* */
+  int32_t npages;
+  const uint8_t *data;              /* HOST bytes of the column chunk as they lie in the file (page headers included) */
+  int64_t data_bytes;
+  const sb_page *pages;
+  int64_t dict_offset;              /* PLAIN dictionary values, or -1 */
+  int32_t dict_count;
+  int32_t pad;
+} sb_column_chunk;
+
+/* host only (no device): page descriptors of a column chunk lying in a Parquet file: Thrift compact PageHeader walk (data page
+ * V1 / V2, dictionary page); compressed pages -> SB_ERR_UNSUPPORTED */
+int sb_parquet_chunk_pages(const uint8_t *chunk, int64_t nbytes, int32_t max_def_level, sb_page *out_pages, int32_t pages_cap,
+                           int32_t *out_npages, int64_t *out_dict_offset, int32_t *out_dict_count);
+/* one H2D copy per column chunk, then one decode kernel (a block per page) */
+int sb_scan_decode(const sb_column_chunk *chunks, int32_t ncols, sb_stream *s, sb_table **out);
+/* write-side twin (tests, bench.py): one NULL-free fixed-width column -> a column chunk on the device (out_chunk: one SB_INT8
+ * column of bytes) + page descriptors on the host.  dictionary: one-column table of the distinct values in ascending order,
+ * or NULL for PLAIN pages. */
+int sb_scan_encode(const sb_table *t, int32_t col, const sb_table *dictionary, int64_t page_rows, sb_stream *s, sb_table **out_chunk,
+                   sb_page *out_pages, int32_t pages_cap, int32_t *out_npages, int64_t *out_dict_offset, int32_t *out_dict_count);
+
 /* ---- expressions: FilterExec / ProjectExec payload (SQLX/basicPhysicalOperators.scala:47, 245),
  *      postfix programs over the input table's columns.  Null-propagating arithmetic and
  *      comparisons, Kleene AND/OR, non-ANSI wrap-around integers, Divide -> NULL on zero,

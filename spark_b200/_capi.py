@@ -34,6 +34,20 @@ class sb_column(C.Structure):
                 ("data", C.c_void_p), ("validity", C.c_void_p), ("offsets", C.c_void_p)]
 
 
+class sb_page(C.Structure):
+    _fields_ = [("encoding", C.c_int32), ("num_values", C.c_int32), ("values_offset", C.c_int64), ("values_bytes", C.c_int64),
+                ("def_offset", C.c_int64), ("def_bytes", C.c_int64)]
+
+
+class sb_column_chunk(C.Structure):
+    _fields_ = [("type", C.c_int32), ("scale", C.c_int32), ("physical_type", C.c_int32), ("npages", C.c_int32), ("data", C.c_void_p),
+                ("data_bytes", C.c_int64), ("pages", C.POINTER(sb_page)), ("dict_offset", C.c_int64), ("dict_count", C.c_int32), ("pad", C.c_int32)]
+
+
+SB_ENC_PLAIN, SB_ENC_RLE_DICTIONARY = 0, 1
+SB_PHYS = dict(BOOLEAN=0, INT32=1, INT64=2, FLOAT=4, DOUBLE=5)
+
+
 class _lit(C.Union):
     _fields_ = [("i", C.c_int64), ("d", C.c_double)]
 
@@ -91,6 +105,9 @@ _SIGNATURES = {
     "sb_table_retain": [_p], "sb_table_release": [_p],
     "sb_table_select": [_p, C.POINTER(_i32), _i32, _pp], "sb_table_zip": [_p, _p, _pp],
     "sb_table_slice": [_p, _i64, _i64, _p, _pp], "sb_table_concat": [_pp, _i32, _p, _pp],
+    "sb_parquet_chunk_pages": [_p, _i64, _i32, C.POINTER(sb_page), _i32, C.POINTER(_i32), C.POINTER(_i64), C.POINTER(_i32)],
+    "sb_scan_decode": [C.POINTER(sb_column_chunk), _i32, _p, _pp],
+    "sb_scan_encode": [_p, _i32, _p, _i64, _p, _pp, C.POINTER(sb_page), _i32, C.POINTER(_i32), C.POINTER(_i64), C.POINTER(_i32)],
     "sb_filter_project": [_p, C.POINTER(sb_expr), C.POINTER(sb_expr), _i32, _p, _pp],
     "sb_partition_ids": [_p, C.POINTER(_i32), _i32, _i32, _p, _p],
     "sb_hash_partition": [_p, C.POINTER(_i32), _i32, _i32, _p, _pp, C.POINTER(_i64)],

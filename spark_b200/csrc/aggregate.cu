@@ -29,6 +29,7 @@
 #include <algorithm>
 #include <math.h>
 #include <stdlib.h>
+#include <map>
 #include <memory>
 #include <thread>
 #include "agg_kernels.cuh"
@@ -131,17 +132,37 @@ static bool specialise_kernels(const PlanMeta &m, int items, int need, bool load
   return ok;
 }
 
+struct SpecialisedSet {
+  const void *k[6];
+  bool ok, from_disk;
+};
 static bool specialise(const PlanMeta &m, int64_t n, int need, KernelChoice &kc) {
   const Config &cfg = config();
   if (!cfg.agg_rtc || n < cfg.agg_rtc_min_rows) return false;
   const int items = chain_items(m);
-  const void *k[6];
-  std::string log;
-  bool cached = false;
-  if (!specialise_kernels(m, items, need, true, k, &log, &cached)) {
-    if (cfg.agg_verbose) fprintf(stderr, "[sb_hash_aggregate] run-time specialisation unavailable, generic kernels used: %s\n", log.c_str());
-    return false;
+  // per-call fast path: one map lookup keyed by the plan's bytes (building the source text and joining compiler threads
+  // on every batch cost more than the Final aggregate of a 4-group query)
+  static std::mutex mu;
+  static std::map<std::string, SpecialisedSet> known;
+  std::string key((const char *)&m, sizeof(PlanMeta));
+  key.push_back((char)need);
+  SpecialisedSet set;
+  bool have = false;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = known.find(key);
+    if (it != known.end()) { set = it->second; have = true; }
   }
+  if (!have) {
+    std::string log;
+    set.ok = specialise_kernels(m, items, need, true, set.k, &log, &set.from_disk);
+    if (!set.ok && cfg.agg_verbose) fprintf(stderr, "[sb_hash_aggregate] run-time specialisation unavailable, generic kernels used: %s\n", log.c_str());
+    std::lock_guard<std::mutex> lk(mu);
+    known[key] = set;
+  }
+  if (!set.ok) return false;
+  const void *const *k = set.k;
+  const bool cached = set.from_disk;
   if (k[0]) kc.k1 = k[0];
   if (k[1]) kc.k2 = k[1];
   if (k[2]) kc.k1_wide = k[2];
@@ -335,6 +356,10 @@ struct HostSlot {
   HostFactor f[AGG_MAX_FACT];
 };
 
+// A column whose validity buffer is present but known to hold no NULL (null_count == 0: what ColumnVector.hasNull() == false
+// is to the reference's readers) is treated as non-nullable: no bitmap is read for it.
+static const uint8_t *nulls_of(const Column &c) { return (c.validity && c.null_count != 0) ? c.v() : nullptr; }
+
 static bool is_f64_col(const sb_table *in, const ExprTree &n) { return n.op == SB_OP_COL && in->cols[n.arg].type == SB_FLOAT64; }
 static double lit_as_double(const ExprTree &n) {
   if (n.op == SB_OP_LIT_F64) { double d; memcpy(&d, &n.lit, 8); return d; }
@@ -346,7 +371,7 @@ static bool match_factor(const sb_table *in, const std::vector<ExprTree> &t, int
   const ExprTree &n = t[i];
   auto set_col = [&](const ExprTree &c) {
     const Column &col = in->cols[c.arg];
-    f.data = col.d(); f.valid = col.v(); f.type = col.type;
+    f.data = col.d(); f.valid = nulls_of(col); f.type = col.type;
   };
   if (is_f64_col(in, n)) { set_col(n); f.mode = F_COL; f.lit = 0; return true; }
   if (n.vtype != SB_VT_F64) return false;
@@ -391,8 +416,8 @@ static bool match_filter(const sb_table *in, const sb_expr &e, AggArgs &a, HostR
     if (m.nterms >= AGG_MAX_TERMS) return false;
     const int ti = m.nterms;
     auto set = [&](const Column &c, int op, int is_f64, int64_t lit) {
-      term_refs[ti] = {c.d(), c.v(), c.type};
-      m.term_type[ti] = c.type; m.term_op[ti] = op; m.term_f64[ti] = is_f64; m.term_valid[ti] = c.validity != nullptr;
+      term_refs[ti] = {c.d(), nulls_of(c), c.type};
+      m.term_type[ti] = c.type; m.term_op[ti] = op; m.term_f64[ti] = is_f64; m.term_valid[ti] = nulls_of(c) != nullptr;
       a.term_lit[ti] = lit;
       m.nterms++;
     };
@@ -466,7 +491,7 @@ struct AggBuilder {
       const Column &c = in->cols[col];
       if (c.type == SB_STRING) fail(SB_ERR_UNSUPPORTED, "aggregates over string columns are not supported");
       s.nf = 1;
-      s.f[0].data = c.d(); s.f[0].valid = c.v(); s.f[0].type = c.type; s.f[0].mode = F_COL;
+      s.f[0].data = c.d(); s.f[0].valid = nulls_of(c); s.f[0].type = c.type; s.f[0].mode = F_COL;
       *src_type = c.type;
       return s;
     }
@@ -478,7 +503,7 @@ struct AggBuilder {
     Column tmp = eval_projection(in, e, nullptr, in->nrows, st);   // general path: materialise
     temps.push_back(tmp);
     s.nf = 1;
-    s.f[0].data = tmp.d(); s.f[0].valid = tmp.v(); s.f[0].type = tmp.type; s.f[0].mode = F_COL;
+    s.f[0].data = tmp.d(); s.f[0].valid = nulls_of(tmp); s.f[0].type = tmp.type; s.f[0].mode = F_COL;
     *src_type = tmp.type;
     return s;
   }
@@ -543,12 +568,12 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
     SB_REQUIRE(ci >= 0 && ci < (int)in->cols.size(), "key column %d out of range", ci);
     const Column &c = in->cols[ci];
     if (c.type == SB_STRING) fail(SB_ERR_UNSUPPORTED, "string grouping keys are not supported (dictionary-encode them)");
-    key_refs[k] = {c.d(), c.v(), c.type};
+    key_refs[k] = {c.d(), nulls_of(c), c.type};
     m.key_type[k] = c.type;
     m.key_bits[k] = type_width(c.type) * 8;
-    m.key_valid[k] = c.validity != nullptr;
+    m.key_valid[k] = nulls_of(c) != nullptr;
     m.key_nshift[k] = -1;
-    total_bits += m.key_bits[k] + (c.validity ? 1 : 0);
+    total_bits += m.key_bits[k] + (m.key_valid[k] ? 1 : 0);
   }
   a.nwords = 1;
   if (plan->nkeys == 1 && m.key_bits[0] == 64) {
@@ -626,7 +651,7 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
       const Column &c = in->cols[col];
       HostSlot s;
       s.nf = 1;
-      s.f[0].data = c.d(); s.f[0].valid = c.v(); s.f[0].type = c.type; s.f[0].mode = F_COL;
+      s.f[0].data = c.d(); s.f[0].valid = nulls_of(c); s.f[0].type = c.type; s.f[0].mode = F_COL;
       return s;
     };
     switch (sp.func) {
@@ -955,7 +980,7 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
     e.ngroups = ngroups;
     for (int k = 0; k < plan->nkeys; k++) {
       const Column &src = in->cols[plan->key_cols[k]];
-      Column c = column_alloc(src.type, src.scale, ngroups, src.validity != nullptr, st);
+      Column c = column_alloc(src.type, src.scale, ngroups, m.key_valid[k] != 0, st);
       t->cols.push_back(c);
       e.key[k].out = c.data->ptr;
       e.key[k].out_valid = c.validity ? (uint32_t *)c.validity->ptr : nullptr;

@@ -466,33 +466,36 @@ class B200ColumnarRule:
                 setattr(plan, attr, self.preColumnarTransitions(getattr(plan, attr)))
         if hasattr(plan, "child"):
             plan.children = (plan.child,)
-        if isinstance(plan, HashAggregateExec) and plan.mode != "final":
+        if isinstance(plan, HashAggregateExec) and plan.mode not in ("final", "partial_merge"):
+            # Walk down the Project / Filter chain keeping ONE map from the names visible at the current level to expressions over
+            # the level below (composed top-down: an upper alias is rewritten through every Project met beneath it), and the
+            # conjunction of every Filter met so far rewritten the same way.  What is left at the bottom is expressed over the
+            # source's attributes, which is what the fused kernel evaluates.
             child = plan.child
-            subst = {}
+            agg_inputs = [fn.child for fn, _ in plan.aggregateExpressions]
+            groups = {g: AttributeReference(g) for g in plan.groupingExpressions}
             cond = plan.condition
             changed = False
             while True:
                 if isinstance(child, ProjectExec):
-                    m = {n: _substitute(e, subst) for n, e in child.projectList}
-                    subst = m
+                    m = {n: e for n, e in child.projectList}
+                    agg_inputs = [None if e is None else _substitute(e, m) for e in agg_inputs]
+                    groups = {g: _substitute(e, m) for g, e in groups.items()}
+                    if cond is not None:
+                        cond = _substitute(cond, m)
                     child = child.child
                     changed = True
-                elif isinstance(child, FilterExec) and cond is None:
-                    cond = child.condition   # filter sits below the projections: it sees source attributes
+                elif isinstance(child, FilterExec):
+                    cond = child.condition if cond is None else (cond & child.condition)
                     child = child.child
                     changed = True
                 else:
                     break
-            if changed:
-                group_ok = all(isinstance(subst.get(g, AttributeReference(g)), AttributeReference) and
-                               subst.get(g, AttributeReference(g)).name == g for g in plan.groupingExpressions) if subst else True
-                if group_ok:
-                    aggs = []
-                    for fn, name in plan.aggregateExpressions:
-                        if fn.child is not None and subst:
-                            fn = type(fn)(_substitute(fn.child, subst))
-                        aggs.append((fn, name))
-                    return HashAggregateExec(plan.groupingExpressions, aggs, child, plan.mode, cond, plan.expected_groups)
+            # grouping keys must still be plain attributes of the source under their own names (the native plan groups by input columns)
+            group_ok = all(isinstance(e, AttributeReference) and e.name == g for g, e in groups.items())
+            if changed and group_ok:
+                aggs = [(fn if e is None else type(fn)(e), name) for (fn, name), e in zip(plan.aggregateExpressions, agg_inputs)]
+                return HashAggregateExec(plan.groupingExpressions, aggs, child, plan.mode, cond, plan.expected_groups)
         return plan
 
     def postColumnarTransitions(self, plan: SparkPlan) -> SparkPlan:

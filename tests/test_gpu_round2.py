@@ -187,3 +187,29 @@ def test_bench_q5_equals_cpu_baseline(gpu, stream):
     _, want = bench.cpu_q5(_host(bench.CPU_TABLES["q5"]))
     rows = list(zip(got.column("n_name").to_pylist(), got.column("revenue").to_pylist()))
     assert len(rows) == 5 and bench.check_q5(rows, want), (rows, want)
+
+
+def test_columnar_rule_collapse_keeps_the_answer(gpu, stream):
+    """Agg(Filter(Project(Filter(Project)))) collapsed by B200ColumnarRule == the uncollapsed operators == the oracle."""
+    from spark_b200.columnar import ColumnarBatch
+    from spark_b200.execution import B200ColumnarRule, FilterExec, HashAggregateExec, LocalTableScanExec, ProjectExec
+    from spark_b200.expressions import Count, Literal, Sum, col
+    rng = np.random.default_rng(8)
+    n = 200_000
+    t = pa.table({"k": rng.integers(0, 7, n).astype(np.int32), "x": pa.array(rng.standard_normal(n) * 10, mask=rng.random(n) < 0.05)})
+    batch = ColumnarBatch.from_arrow(t, stream)
+
+    def plan():
+        inner = ProjectExec([("k", col("k")), ("y", col("x") + Literal(1.0))], LocalTableScanExec(batch))
+        mid = ProjectExec([("k", col("k")), ("rev", col("y") * Literal(3.0))], FilterExec(col("y") < Literal(5.0), inner))
+        return HashAggregateExec(["k"], [(Sum(col("rev")), "s"), (Count(), "n")], FilterExec(col("rev") > Literal(-20.0), mid))
+    plain = plan().collect(stream)
+    fused_plan = B200ColumnarRule().preColumnarTransitions(plan())
+    assert isinstance(fused_plan.child, LocalTableScanExec) and fused_plan.condition is not None
+    fused = fused_plan.collect(stream)
+    y = ("add", ("col", "x"), ("lit", 1.0))
+    rev = ("mul", y, ("lit", 3.0))
+    f = O.filter_table(t, ("and", ("gt", rev, ("lit", -20.0)), ("lt", y, ("lit", 5.0))))
+    want = O.hash_aggregate(O.project(f, [("k", ("col", "k")), ("rev", rev)]), ["k"], [("sum", "rev", "s"), ("count_star", None, "n")])
+    assert_tables_equal(plain, want, key_cols=["k"])
+    assert_tables_equal(fused, want, key_cols=["k"])
