@@ -330,11 +330,22 @@ int sb_top_n(const sb_table *in, const sb_sort_order *orders, int32_t norders, i
 
 /* RangePartitioning for a global sort (core/src/main/scala/org/apache/spark/Partitioner.scala:175-320, used by
  * ShuffleExchangeExec.scala:381-401): partition id = number of range bounds the row's key is strictly greater than under
- * the sort order (getPartition :241-260).  `bounds` is a one-column table holding the numPartitions-1 sorted bounds (the
- * sampling that picks them stays on the JVM side: RangePartitioner.sketch/determineBounds); rows are regrouped
+ * the sort order (getPartition :241-260).  `bounds` is a one-column table holding the numPartitions-1 sorted bounds (from
+ * sb_range_sample + sb_range_determine_bounds below, or any other source); rows are regrouped
  * partition-contiguously with arrival order kept, like sb_hash_partition.  One sort column, fixed-width type. */
 int sb_range_partition(const sb_table *in, const sb_sort_order *order, const sb_table *bounds, sb_stream *s,
                        sb_table **out, int64_t *out_offsets_host);
+
+/* The sampling half of RangePartitioner (Partitioner.scala:203-216 sketch, :357-388 determineBounds).
+ *   sb_range_sample            up to sample_size keys of the order's column drawn uniformly without replacement from this input
+ *                              partition, with the weight n / sample.length of :229 as a float32 second column.  The reference's
+ *                              reservoir is seeded from the RDD id (XORShiftRandom): which rows are drawn is unpinned.
+ *   sb_range_determine_bounds  the candidates of ALL input partitions (concatenate / sb_all_gather the samples) -> at most
+ *                              num_partitions - 1 bounds, exactly the reference's walk over the cumulative weights.
+ * sampleSizePerPartition = ceil(3 * min(samplePointsPerPartitionHint * partitions, 1e6) / inputPartitions) is the caller's
+ * (RangePartitioning in spark_b200/execution.py computes it like :208-211). */
+int sb_range_sample(const sb_table *in, const sb_sort_order *order, int64_t sample_size, uint64_t seed, sb_stream *s, sb_table **out);
+int sb_range_determine_bounds(const sb_table *sample, const sb_sort_order *order, int32_t num_partitions, sb_stream *s, sb_table **out);
 
 /* ---- joins: BroadcastHashJoinExec / ShuffledHashJoinExec / SortMergeJoinExec replacement
  *      (SQLX/joins/HashJoin.scala:184-400, HashedRelation.scala:136-168).  A row with any NULL key
@@ -343,10 +354,19 @@ int sb_range_partition(const sb_table *in, const sb_sort_order *order, const sb_
 #define SB_JOIN_LEFT_OUTER 1   /* streamed side preserved */
 #define SB_JOIN_LEFT_SEMI 2
 #define SB_JOIN_LEFT_ANTI 3
+#define SB_JOIN_FULL_OUTER 4              /* both sides preserved: pairs, streamed rows without a partner, then build rows without one
+                                             (ShuffledHashJoinExec.buildSideOrFullOuterJoin, SQLX/joins/ShuffledHashJoinExec.scala:130-330) */
+#define SB_JOIN_BUILD_OUTER 5             /* build side preserved (a RIGHT OUTER join whose right side is hashed): pairs + unmatched build rows */
+#define SB_JOIN_EXISTENCE 6               /* every streamed row ++ one BOOL column "exists" (HashJoin.existenceJoin, HashJoin.scala:301) */
+#define SB_JOIN_LEFT_ANTI_NULL_AWARE 7    /* NOT IN: BroadcastHashJoinExec.scala:137-162 (single key) */
 
 int sb_join_build(const sb_table *build, const int32_t *key_cols, int32_t nkeys, sb_stream *s, sb_hash_table **out);
 int sb_join_probe(const sb_hash_table *ht, const sb_table *probe, const int32_t *key_cols, int32_t nkeys,
                   int32_t join_type, sb_stream *s, sb_table **out);
+/* the same with a residual condition over the joined row (streamed columns ++ build columns): HashJoin.scala:144-172
+ * boundCondition -- only key matches for which it is TRUE are matches, for every join type */
+int sb_join_probe_condition(const sb_hash_table *ht, const sb_table *probe, const int32_t *key_cols, int32_t nkeys,
+                            int32_t join_type, const sb_expr *condition, sb_stream *s, sb_table **out);
 int sb_hash_table_release(sb_hash_table *ht);
 
 /* ---- synthetic TPC-H-shaped columns (include/sb_synth.h defines the dataset; SURVEY.md 8d: the reference ships no data
@@ -375,6 +395,18 @@ int sb_exchange_plan(const int64_t *part_offsets, int32_t num_partitions, int32_
  * partition id (only owned partitions are non-empty).  Collective: all ranks call it in the same order. */
 int sb_all_to_all(const sb_table *in, const int64_t *part_offsets_host, int32_t num_partitions, sb_stream *s,
                   sb_table **out, int64_t *out_part_offsets_host);
+/* ---- adaptive execution: the statistics of an exchange and the coalescing they drive --------------------------------------------
+ * sb_map_output_statistics  MapOutputStatistics.bytesByPartitionId (ShuffleExchangeExec.scala:235-262): bytes every reducer
+ *                           partition holds, summed over all map sides (ranks).  Collective when a communicator is up.
+ * sb_coalesce_partitions    ShufflePartitionsUtil.coalescePartitions without skew specs (SQLX/adaptive/ShufflePartitionsUtil.scala:
+ *                           45-126, 263-369), host only: CoalescedPartitionSpec(start, end) ranges + their data size per shuffle
+ *                           (out_data_size[shuffle * nspecs + spec]); *out_nspecs == 0 means "leave the layout as it is". */
+int sb_map_output_statistics(const sb_table *partitioned, const int64_t *part_offsets_host, int32_t num_partitions, sb_stream *s,
+                             int64_t *out_bytes_by_partition);
+int sb_coalesce_partitions(const int64_t *const *bytes_by_partition, int32_t nshuffles, int32_t num_partitions,
+                           int64_t advisory_target_size, int32_t min_num_partitions, int64_t min_partition_size,
+                           int32_t max_reducer_partitions_per_task, int32_t *out_start, int32_t *out_end, int64_t *out_data_size,
+                           int32_t *out_nspecs);
 /* BroadcastExchangeExec (SQLX/exchange/BroadcastExchangeExec.scala:45-279): every rank gets the
  * concatenation of all ranks' tables, in rank order. */
 int sb_all_gather(const sb_table *in, sb_stream *s, sb_table **out);

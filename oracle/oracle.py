@@ -460,6 +460,12 @@ def filter_table(table, predicate):
     return take_table(table, keep)
 
 
+def filter_mask(table, predicate):
+    """Boolean mask of the rows a FilterExec keeps (predicate TRUE, not NULL)."""
+    v, valid = eval_expr(predicate, table)
+    return v.astype(bool) & valid
+
+
 def project(table, named_exprs):
     """ProjectExec: named_exprs = [(name, expr)]; ("col", x) keeps the source type (dates, strings)."""
     out = {}
@@ -586,23 +592,57 @@ def hash_aggregate(table, key_cols, aggs, mode="complete"):
 JOIN_TYPES = {"inner": 0, "left_outer": 1, "left_semi": 2, "left_anti": 3}
 
 
-def hash_join(probe, build, probe_keys, build_keys, join_type="inner"):
+def hash_join(probe, build, probe_keys, build_keys, join_type="inner", condition=None):
     """Equi-join with `probe` as the streamed side and `build` as the hashed side
     (BroadcastHashJoinExec / ShuffledHashJoinExec; SortMergeJoinExec gives the same multiset).
-    Output columns: probe columns ++ build columns (semi/anti: probe columns only)."""
+    join_type: inner | left_outer | left_semi | left_anti | full_outer | build_outer (the hashed side preserved) | existence |
+    left_anti_null_aware.  `condition` (an expression over probe ++ build columns) is HashJoin.boundCondition
+    (HashJoin.scala:144-172): only key matches for which it is TRUE are matches.
+    Output columns: probe columns ++ build columns (semi/anti: probe columns only; existence: probe ++ `exists`)."""
     L = lib()
     pk = _cols(probe, probe_keys); bk = _cols(build, build_keys)
-    jt = JOIN_TYPES[join_type]
     pa_, ba_ = _carray(pk), _carray(bk)
-    cnt = L.so_hash_join(ba_, pa_, len(pk), build.num_rows, probe.num_rows, jt, None, None)
+    np_, nb_ = probe.num_rows, build.num_rows
+    cnt = L.so_hash_join(ba_, pa_, len(pk), nb_, np_, 0, None, None)          # every key match (inner pairs)
     pi = np.empty(cnt, np.int64); bi = np.empty(cnt, np.int64)
-    L.so_hash_join(ba_, pa_, len(pk), build.num_rows, probe.num_rows, jt, pi.ctypes.data, bi.ctypes.data)
-    names = list(probe.column_names)
-    cols = [Col.from_arrow(probe.column(n)).take(pi) for n in probe.column_names]
-    if jt in (0, 1):
-        for n in build.column_names:
-            names.append(n); cols.append(Col.from_arrow(build.column(n)).take(bi))
-    return table_from_cols(names, cols)
+    L.so_hash_join(ba_, pa_, len(pk), nb_, np_, 0, pi.ctypes.data, bi.ctypes.data)
+    names = list(probe.column_names) + list(build.column_names)
+
+    def joined(p_idx, b_idx):
+        cols = [Col.from_arrow(probe.column(n)).take(p_idx) for n in probe.column_names]
+        cols += [Col.from_arrow(build.column(n)).take(b_idx) for n in build.column_names]
+        return table_from_cols(names, cols)
+    if condition is not None and cnt:
+        keep = filter_mask(joined(pi, bi), condition)
+        pi, bi = pi[keep], bi[keep]
+    p_matched = np.zeros(np_, bool); p_matched[pi] = True
+    b_matched = np.zeros(nb_, bool); b_matched[bi] = True
+    if join_type == "inner":
+        return joined(pi, bi)
+    if join_type in ("left_semi", "left_anti", "left_anti_null_aware"):
+        if join_type == "left_semi":
+            sel = np.nonzero(p_matched)[0]
+        elif join_type == "left_anti":
+            sel = np.nonzero(~p_matched)[0]
+        else:   # BroadcastHashJoinExec.scala:137-162
+            bnull = np.zeros(nb_, bool)
+            for c in bk:
+                if c.valid is not None:
+                    bnull |= ~c.valid
+            pnull = np.zeros(np_, bool)
+            for c in pk:
+                if c.valid is not None:
+                    pnull |= ~c.valid
+            sel = np.arange(np_) if nb_ == 0 else (np.zeros(0, np.int64) if bnull.any() else np.nonzero(~p_matched & ~pnull)[0])
+        return table_from_cols(list(probe.column_names), [Col.from_arrow(probe.column(n)).take(sel.astype(np.int64)) for n in probe.column_names])
+    if join_type == "existence":
+        cols = [Col.from_arrow(probe.column(n)) for n in probe.column_names] + [Col(SO_BOOL, p_matched.astype(np.uint8))]
+        return table_from_cols(list(probe.column_names) + ["exists"], cols)
+    up = np.nonzero(~p_matched)[0] if join_type in ("left_outer", "full_outer") else np.zeros(0, np.int64)
+    ub = np.nonzero(~b_matched)[0] if join_type in ("build_outer", "full_outer") else np.zeros(0, np.int64)
+    p_idx = np.concatenate([pi, up, np.full(len(ub), -1)]).astype(np.int64)
+    b_idx = np.concatenate([bi, np.full(len(up), -1), ub]).astype(np.int64)
+    return joined(p_idx, b_idx)
 
 
 # --------------------------------------------------------------------------- comparison helpers
@@ -618,3 +658,86 @@ def canonical_rows(table, float_digits=None):
     def key(r):
         return tuple((x is None, 0 if x is None else (repr(x) if not isinstance(x, (int, float)) else x)) for x in r)
     return sorted(rows, key=lambda r: tuple((x is None, "" if x is None else str(type(x)), 0 if x is None else x) for x in r))
+
+
+# --------------------------------------------------------------------------- RangePartitioner.determineBounds
+def determine_bounds(candidates, partitions, key=None):
+    """RangePartitioner.determineBounds (core/src/main/scala/org/apache/spark/Partitioner.scala:357-388), line by line:
+    candidates = [(key, weight float32)], unordered; `key` maps a candidate key to its sort key (None = natural order).
+    Pinned by PartitioningSuite.scala:119-125 (tests/test_oracle_golden.py)."""
+    keyf = key or (lambda x: x)
+    ordered = sorted(candidates, key=lambda kw: keyf(kw[0]))           # sortBy(_._1) is stable, like sorted()
+    num = len(ordered)
+    sum_weights = sum(float(np.float32(w)) for _, w in ordered)
+    step = sum_weights / partitions if partitions else 0.0
+    cum, target = 0.0, step
+    bounds = []
+    i = j = 0
+    previous = None
+    have_prev = False
+    while i < num and j < partitions - 1:
+        k, w = ordered[i]
+        cum += float(np.float32(w))
+        if cum >= target:
+            if not have_prev or keyf(k) > keyf(previous):               # skip duplicate values
+                bounds.append(k)
+                target += step
+                j += 1
+                previous, have_prev = k, True
+        i += 1
+    return bounds
+
+
+# --------------------------------------------------------------------------- AQE: ShufflePartitionsUtil.coalescePartitions
+def coalesce_partitions(bytes_by_partition, advisory_target_size, min_num_partitions=1, min_partition_size=0,
+                        max_reducer_partitions_per_task=2 ** 31 - 1):
+    """ShufflePartitionsUtil.coalescePartitions without skew specs (sql/core/.../adaptive/ShufflePartitionsUtil.scala:45-126,
+    263-369).  bytes_by_partition: one list per shuffle.  Returns, per shuffle, [(start, end, dataSize)] or [] for "no coalescing".
+    Pinned by ShufflePartitionsUtilSuite.scala:54-300 (tests/test_oracle_golden.py)."""
+    import math
+    stats = [list(b) for b in bytes_by_partition]
+    if not stats:
+        return []
+    total = sum(sum(b) for b in stats)
+    max_target = int(math.ceil(total / float(min_num_partitions)))
+    target = max(min(max_target, advisory_target_size), min_partition_size)
+    if len({len(b) for b in stats}) > 1:
+        return []
+    n = len(stats[0])
+    specs = []
+    coalesced = latest_size = 0
+    i = latest_split = 0
+
+    def create(force=False):
+        if coalesced > 0 or force:
+            specs.append([latest_split, i])
+
+    def within(a, b):
+        return b - a <= max_reducer_partitions_per_task
+    while i < n:
+        cur = sum(b[i] for b in stats)
+        if i > latest_split and i - latest_split >= max_reducer_partitions_per_task:
+            create()
+            latest_split, latest_size, coalesced = i, coalesced, cur
+        elif i > latest_split and coalesced + cur > target:
+            if coalesced < min_partition_size:
+                if latest_size > 0 and latest_size < cur and within(specs[-1][0], i):
+                    specs[-1][1] = i
+                    latest_split = i
+                    latest_size += coalesced
+                    coalesced = cur
+                else:
+                    coalesced += cur
+            else:
+                create()
+                latest_split, latest_size, coalesced = i, coalesced, cur
+        else:
+            coalesced += cur
+        i += 1
+    if coalesced < min_partition_size and latest_size > 0 and within(specs[-1][0], n):
+        specs[-1][1] = n
+    else:
+        create(not specs)
+    if len(specs) >= n:
+        return []
+    return [[(a, b, sum(st[a:b])) for a, b in specs] for st in stats]

@@ -22,7 +22,7 @@ SB_OP = dict(COL=1, LIT_I64=2, LIT_F64=3, LIT_NULL=4, ADD=10, SUB=11, MUL=12, DI
 SB_VT_BOOL, SB_VT_I32, SB_VT_I64, SB_VT_F64 = 1, 2, 3, 4
 SB_AGG = dict(sum=1, avg=2, count=3, count_star=4, min=5, max=6)
 SB_AGG_MODE = dict(partial=1, final=2, complete=3, partial_merge=4)
-SB_JOIN = dict(inner=0, left_outer=1, left_semi=2, left_anti=3)
+SB_JOIN = dict(inner=0, left_outer=1, left_semi=2, left_anti=3, full_outer=4, build_outer=5, existence=6, left_anti_null_aware=7)
 SB_UNIQUE_ID_BYTES = 128
 
 TYPE_WIDTH = {SB_BOOL: 1, SB_INT8: 1, SB_INT16: 2, SB_INT32: 4, SB_INT64: 8, SB_FLOAT32: 4, SB_FLOAT64: 8,
@@ -113,6 +113,8 @@ _SIGNATURES = {
     "sb_hash_partition": [_p, C.POINTER(_i32), _i32, _i32, _p, _pp, C.POINTER(_i64)],
     "sb_round_robin_partition": [_p, _i32, _i32, _p, _pp, C.POINTER(_i64)],
     "sb_range_partition": [_p, C.POINTER(sb_sort_order), _p, _p, _pp, C.POINTER(_i64)],
+    "sb_range_sample": [_p, C.POINTER(sb_sort_order), _i64, C.c_uint64, _p, _pp],
+    "sb_range_determine_bounds": [_p, C.POINTER(sb_sort_order), _i32, _p, _pp],
     "sb_hash_aggregate": [_p, C.POINTER(sb_agg_plan), _p, _pp],
     "sb_hash_agg_create": [C.POINTER(sb_agg_plan), _pp], "sb_hash_agg_update": [_p, _p, _p],
     "sb_hash_agg_merge": [_p, _p, _p], "sb_hash_agg_finish": [_p, _p, _pp], "sb_hash_agg_destroy": [_p],
@@ -122,12 +124,16 @@ _SIGNATURES = {
     "sb_top_n": [_p, C.POINTER(sb_sort_order), _i32, _i64, _p, _pp],
     "sb_join_build": [_p, C.POINTER(_i32), _i32, _p, _pp],
     "sb_join_probe": [_p, _p, C.POINTER(_i32), _i32, _i32, _p, _pp],
+    "sb_join_probe_condition": [_p, _p, C.POINTER(_i32), _i32, _i32, C.POINTER(sb_expr), _p, _pp],
     "sb_hash_table_release": [_p],
     "sb_comm_get_unique_id": [C.c_char_p], "sb_comm_init": [_i32, _i32, C.c_char_p], "sb_comm_destroy": [],
     "sb_comm_rank": [C.POINTER(_i32), C.POINTER(_i32)],
     "sb_exchange_plan": [C.POINTER(_i64), _i32, _i32, C.POINTER(_i64)],
     "sb_all_to_all": [_p, C.POINTER(_i64), _i32, _p, _pp, C.POINTER(_i64)],
     "sb_all_gather": [_p, _p, _pp],
+    "sb_map_output_statistics": [_p, C.POINTER(_i64), _i32, _p, C.POINTER(_i64)],
+    "sb_coalesce_partitions": [C.POINTER(C.POINTER(_i64)), _i32, _i32, _i64, _i32, _i64, _i32, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i64),
+                               C.POINTER(_i32)],
 }
 _RESTYPE = {"sb_agg_plan_meta_words": _i32, "sb_hash_aggregate_last_plan": C.c_char_p, "sb_last_error": C.c_char_p, "sb_abi_version": _i32, "sb_kernel_launch_count": _i64}
 

@@ -548,6 +548,38 @@ int sb_all_to_all(const sb_table *in, const int64_t *part_offsets_host, int32_t 
   SB_API_END
 }
 
+// MapOutputStatistics.bytesByPartitionId of the exchange whose map side produced `partitioned` (ShuffleExchangeExec.scala:235-262):
+// rows x fixed row width (+ string arenas are not attributed to partitions), summed over the ranks with one all-gather.
+int sb_map_output_statistics(const sb_table *partitioned, const int64_t *part_offsets_host, int32_t num_partitions, sb_stream *s,
+                             int64_t *out_bytes_by_partition) {
+  SB_API_BEGIN
+  require_init();
+  SB_REQUIRE(partitioned && part_offsets_host && out_bytes_by_partition && num_partitions >= 1, "bad argument");
+  Comm &c = comm();
+  cudaStream_t st = stream_of(s);
+  int64_t row_bytes = 0;
+  for (auto &col : partitioned->cols) row_bytes += col.type == SB_STRING ? 4 : type_width(col.type);
+  std::vector<int64_t> mine(num_partitions), all;
+  for (int p = 0; p < num_partitions; p++) mine[p] = part_offsets_host[p + 1] - part_offsets_host[p];
+  if (c.comm) {
+    const int R = c.nranks;
+    all.resize((size_t)R * num_partitions);
+    Scratch d_my((int64_t)num_partitions * 8, st), d_all((int64_t)R * num_partitions * 8, st);
+    SB_CUDA(cudaMemcpyAsync(d_my.ptr, mine.data(), (size_t)num_partitions * 8, cudaMemcpyHostToDevice, st));
+    SB_NCCL(nccl().AllGather(d_my.ptr, d_all.ptr, (size_t)num_partitions, ncclInt64, c.comm, st));
+    SB_CUDA(cudaMemcpyAsync(all.data(), d_all.ptr, all.size() * 8, cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaStreamSynchronize(st));
+    for (int p = 0; p < num_partitions; p++) {
+      int64_t rows = 0;
+      for (int r = 0; r < R; r++) rows += all[(size_t)r * num_partitions + p];
+      out_bytes_by_partition[p] = rows * row_bytes;
+    }
+  } else {
+    for (int p = 0; p < num_partitions; p++) out_bytes_by_partition[p] = mine[p] * row_bytes;
+  }
+  SB_API_END
+}
+
 int sb_all_gather(const sb_table *in, sb_stream *s, sb_table **out) {
   SB_API_BEGIN
   require_init();

@@ -20,6 +20,7 @@
 //           pass 2 writes (probe row, build row) pairs in streamed-row order; rows with <= 1 match do not walk
 //           the table twice.  Output columns are gathered once from both sides.
 #include "common.cuh"
+#include "expr.cuh"
 #include "primitives.cuh"
 
 struct sb_hash_table {
@@ -31,6 +32,7 @@ struct sb_hash_table {
   int32_t key_type[4];
   int32_t key_bits[4];
   int32_t key_shift[4];
+  int32_t *null_key_flag = nullptr;   // device: set when a build row had a NULL key (null-aware anti join)
   cudaStream_t st = nullptr;
 };
 
@@ -85,11 +87,15 @@ __device__ __forceinline__ void load_slot(const JoinSlot *p, uint64_t &key, uint
   row = (uint32_t)v.y;
 }
 
-__global__ void __launch_bounds__(JOIN_THREADS) join_build_kernel(JoinKeys k, int64_t n, JoinSlot *__restrict__ slots, int64_t cap) {
+__global__ void __launch_bounds__(JOIN_THREADS) join_build_kernel(JoinKeys k, int64_t n, JoinSlot *__restrict__ slots, int64_t cap,
+                                                                  int32_t *__restrict__ null_key_flag) {
   int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= n) return;
   uint64_t key;
-  if (!join_key(k, row, key)) return;
+  if (!join_key(k, row, key)) {
+    *null_key_flag = 1;   // HashedRelation keeps no NULL keys; the null-aware anti join needs to know there was one
+    return;
+  }
   uint64_t mask = (uint64_t)cap - 1;
   uint64_t h = join_mix(key) & mask;
   for (;;) {
@@ -103,35 +109,40 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_build_kernel(JoinKeys k, in
 
 // pass 1: matches per streamed row (join-type adjusted) + first matching build row
 __global__ void __launch_bounds__(JOIN_THREADS) join_count_kernel(JoinKeys k, int64_t n, const JoinSlot *__restrict__ slots, int64_t cap,
-                                                                  int join_type, int32_t *__restrict__ counts, uint32_t *__restrict__ first,
-                                                                  int32_t *__restrict__ block_counts) {
+                                                                  int join_type, int null_aware, int32_t *__restrict__ counts, uint32_t *__restrict__ first,
+                                                                  int32_t *__restrict__ block_counts, uint8_t *__restrict__ matched) {
   __shared__ int32_t wsum[JOIN_THREADS / 32];
   int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool in_range = row < n;
   uint64_t key;
   int32_t matches = 0;
   uint32_t f = FREE_SLOT;
-  if (in_range && join_key(k, row, key)) {
-    uint64_t mask = (uint64_t)cap - 1;
-    uint64_t h = join_mix(key) & mask;
-    for (;;) {
-      uint64_t sk;
-      uint32_t r;
-      load_slot(&slots[h], sk, r);
-      if (r == FREE_SLOT) break;
-      if (sk == key) {
-        if (matches == 0) f = r;
-        matches++;
+  bool null_key = false;
+  if (in_range) {
+    if (join_key(k, row, key)) {
+      uint64_t mask = (uint64_t)cap - 1;
+      uint64_t h = join_mix(key) & mask;
+      for (;;) {
+        uint64_t sk;
+        uint32_t r;
+        load_slot(&slots[h], sk, r);
+        if (r == FREE_SLOT) break;
+        if (sk == key) {
+          if (matches == 0) f = r;
+          matches++;
+          if (matched) matched[r] = 1;   // build rows that found a partner (build-side-preserving outer joins)
+        }
+        h = (h + 1) & mask;
       }
-      h = (h + 1) & mask;
-    }
+    } else null_key = true;
   }
   int32_t c;
   switch (join_type) {
     case SB_JOIN_INNER: c = matches; break;
     case SB_JOIN_LEFT_OUTER: c = matches > 0 ? matches : 1; break;
     case SB_JOIN_LEFT_SEMI: c = matches > 0 ? 1 : 0; break;
-    default: c = matches > 0 ? 0 : 1; break;   // anti
+    case SB_JOIN_EXISTENCE: c = 1; break;      // every streamed row, `first` says whether it has a partner
+    default: c = matches > 0 || (null_aware && null_key) ? 0 : 1; break;   // anti (null-aware: a NULL key is neither in nor not in)
   }
   if (!in_range) c = 0;
   if (in_range) {
@@ -249,15 +260,18 @@ int sb_join_build(const sb_table *build, const int32_t *key_cols, int32_t nkeys,
   try {
     SB_CUDA(cudaMallocAsync((void **)&ht->slots, (size_t)cap * sizeof(JoinSlot), st));
     SB_CUDA(cudaMemsetAsync(ht->slots, 0xff, (size_t)cap * sizeof(JoinSlot), st));
+    SB_CUDA(cudaMallocAsync((void **)&ht->null_key_flag, 4, st));
+    SB_CUDA(cudaMemsetAsync(ht->null_key_flag, 0, 4, st));
     if (n > 0) {
       KernelTimer kt("join_build", st);
-      join_build_kernel<<<(unsigned)((n + JOIN_THREADS - 1) / JOIN_THREADS), JOIN_THREADS, 0, st>>>(k, n, ht->slots, cap);
+      join_build_kernel<<<(unsigned)((n + JOIN_THREADS - 1) / JOIN_THREADS), JOIN_THREADS, 0, st>>>(k, n, ht->slots, cap, ht->null_key_flag);
       SB_LAUNCH_CHECK();
     }
     ht->build = const_cast<sb_table *>(build);
     ht->build->refs.fetch_add(1);
   } catch (...) {
     if (ht->slots) cudaFreeAsync(ht->slots, st);
+    if (ht->null_key_flag) cudaFreeAsync(ht->null_key_flag, st);
     delete ht;
     throw;
   }
@@ -269,10 +283,24 @@ int sb_hash_table_release(sb_hash_table *ht) {
   SB_API_BEGIN
   if (ht) {
     if (ht->slots) cudaFreeAsync(ht->slots, ht->st);
+    if (ht->null_key_flag) cudaFreeAsync(ht->null_key_flag, ht->st);
     if (ht->build && ht->build->refs.fetch_sub(1) == 1) table_free(ht->build);
     delete ht;
   }
   SB_API_END
+}
+
+__global__ void exists_kernel(const uint32_t *__restrict__ first, int64_t n, uint8_t *__restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = first[i] != sb::FREE_SLOT;
+}
+__global__ void unmatched_kernel(const uint8_t *__restrict__ matched, int64_t n, uint8_t *__restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = !matched[i];
+}
+__global__ void fill_i64_kernel(int64_t *out, int64_t n, int64_t v) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = v;
 }
 
 int sb_join_probe(const sb_hash_table *ht, const sb_table *probe, const int32_t *key_cols, int32_t nkeys, int32_t join_type,
@@ -281,38 +309,102 @@ int sb_join_probe(const sb_hash_table *ht, const sb_table *probe, const int32_t 
   require_init();
   SB_REQUIRE(ht && probe && key_cols && out, "null argument");
   SB_REQUIRE(nkeys == ht->nkeys, "probe has %d key columns, the relation was built on %d", nkeys, ht->nkeys);
-  SB_REQUIRE(join_type >= SB_JOIN_INNER && join_type <= SB_JOIN_LEFT_ANTI, "unknown join type %d", join_type);
+  SB_REQUIRE(join_type >= SB_JOIN_INNER && join_type <= SB_JOIN_LEFT_ANTI_NULL_AWARE, "unknown join type %d", join_type);
   cudaStream_t st = stream_of(s);
-  const int64_t n = probe->nrows;
+  const int64_t n = probe->nrows, nbuild = ht->build->nrows;
   JoinKeys k = make_join_keys(probe, key_cols, nkeys, ht);
-  const bool pairs = join_type == SB_JOIN_INNER || join_type == SB_JOIN_LEFT_OUTER;
+  // the kernels know inner / streamed-outer / semi / anti / existence; the build-side-preserving joins are those plus the build
+  // rows nobody matched (ShuffledHashJoinExec.buildSideOrFullOuterJoin, SQLX/joins/ShuffledHashJoinExec.scala:130-330)
+  const bool build_rows_too = join_type == SB_JOIN_FULL_OUTER || join_type == SB_JOIN_BUILD_OUTER;
+  int kt_type = join_type;
+  if (join_type == SB_JOIN_FULL_OUTER) kt_type = SB_JOIN_LEFT_OUTER;
+  if (join_type == SB_JOIN_BUILD_OUTER) kt_type = SB_JOIN_INNER;
+  int null_aware = 0;
+  if (join_type == SB_JOIN_LEFT_ANTI_NULL_AWARE) {
+    // BroadcastHashJoinExec.scala:137-162: empty relation -> every streamed row; a NULL key in the relation -> no row;
+    // otherwise streamed rows with a NULL key are dropped and the rest is an anti join
+    SB_REQUIRE(nkeys == 1, "the null-aware anti join takes a single key (NOT IN subquery)");
+    kt_type = SB_JOIN_LEFT_ANTI;
+    int32_t flag = 0;
+    SB_CUDA(cudaMemcpyAsync(&flag, ht->null_key_flag, 4, cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaStreamSynchronize(st));
+    if (nbuild == 0) {
+      sb_table *t = table_new(n);
+      for (auto &c : probe->cols) t->cols.push_back(column_share(c));
+      *out = t;
+      return SB_OK;
+    }
+    if (flag) {
+      Scratch none(16, st);
+      *out = gather_table(probe, none.as<int64_t>(), 0, false, st);
+      return SB_OK;
+    }
+    null_aware = 1;
+  }
+  const bool pairs = kt_type == SB_JOIN_INNER || kt_type == SB_JOIN_LEFT_OUTER;
   unsigned nb = (unsigned)((n + JOIN_THREADS - 1) / JOIN_THREADS);
-  Scratch counts(n * 4 + 16, st), first(n * 4 + 16, st), block_counts((int64_t)nb * 4 + 16, st), offsets((int64_t)nb * 8 + 16, st), total(8, st);
+  Scratch counts(n * 4 + 16, st), first(n * 4 + 16, st), block_counts((int64_t)nb * 4 + 16, st), offsets((int64_t)nb * 8 + 16, st), total(16, st);
+  Scratch matched(build_rows_too ? nbuild + 16 : 0, st);
+  if (build_rows_too) SB_CUDA(cudaMemsetAsync(matched.ptr, 0, (size_t)nbuild + 16, st));
   if (n > 0) {
     KernelTimer kt("join_probe", st);
-    join_count_kernel<<<nb, JOIN_THREADS, 0, st>>>(k, n, ht->slots, ht->cap, join_type, counts.as<int32_t>(), first.as<uint32_t>(),
-                                                   block_counts.as<int32_t>());
+    join_count_kernel<<<nb, JOIN_THREADS, 0, st>>>(k, n, ht->slots, ht->cap, kt_type, null_aware, counts.as<int32_t>(), first.as<uint32_t>(),
+                                                   block_counts.as<int32_t>(), build_rows_too ? matched.as<uint8_t>() : nullptr);
     SB_LAUNCH_CHECK();
   }
+  if (join_type == SB_JOIN_EXISTENCE) {   // HashJoin.existenceJoin :301: the streamed row plus one boolean
+    sb_table *t = table_new(n);
+    try {
+      for (auto &c : probe->cols) t->cols.push_back(column_share(c));
+      Column e = column_alloc(SB_BOOL, 0, n, false, st);
+      t->cols.push_back(e);
+      if (n > 0) {
+        exists_kernel<<<nb, JOIN_THREADS, 0, st>>>(first.as<uint32_t>(), n, (uint8_t *)e.data->ptr);
+        SB_LAUNCH_CHECK();
+      }
+    } catch (...) {
+      table_free(t);
+      throw;
+    }
+    *out = t;
+    SB_CUDA(cudaStreamSynchronize(st));
+    return SB_OK;
+  }
   exclusive_scan_i32_to_i64(block_counts.as<int32_t>(), offsets.as<int64_t>(), nb, total.as<int64_t>(), st);
-  int64_t nout = 0;
-  SB_CUDA(cudaMemcpyAsync(&nout, total.ptr, 8, cudaMemcpyDeviceToHost, st));
+  // build rows without a partner, in build order (their count comes back with the pair count: one host round trip)
+  Scratch un_mask(build_rows_too ? nbuild + 16 : 0, st), un_idx(build_rows_too ? nbuild * 8 + 16 : 0, st),
+      un_f32(build_rows_too ? compact_tiles(nbuild) * 4 + 16 : 0, st), un_pos(build_rows_too ? compact_tiles(nbuild) * 8 + 16 : 0, st);
+  if (build_rows_too) {
+    if (nbuild > 0) {
+      unmatched_kernel<<<(unsigned)((nbuild + 255) / 256), 256, 0, st>>>(matched.as<uint8_t>(), nbuild, un_mask.as<uint8_t>());
+      SB_LAUNCH_CHECK();
+      compact_mask_async(un_mask.as<uint8_t>(), nbuild, un_idx.as<int64_t>(), un_f32.as<int32_t>(), un_pos.as<int64_t>(), total.as<int64_t>() + 1, st);
+    } else SB_CUDA(cudaMemsetAsync(total.as<int64_t>() + 1, 0, 8, st));
+  }
+  int64_t totals[2] = {0, 0};
+  SB_CUDA(cudaMemcpyAsync(totals, total.ptr, build_rows_too ? 16 : 8, cudaMemcpyDeviceToHost, st));
   SB_CUDA(cudaStreamSynchronize(st));
+  const int64_t npairs = totals[0], nun = build_rows_too ? totals[1] : 0, nout = npairs + nun;
   Scratch out_probe(nout * 8 + 16, st), out_build(pairs ? nout * 8 + 16 : 0, st);
-  if (n > 0 && nout > 0) {
+  if (n > 0 && npairs > 0) {
     KernelTimer kt("join_fill", st);
-    join_fill_kernel<<<nb, JOIN_THREADS, 0, st>>>(k, n, ht->slots, ht->cap, join_type, counts.as<int32_t>(),
+    join_fill_kernel<<<nb, JOIN_THREADS, 0, st>>>(k, n, ht->slots, ht->cap, kt_type, counts.as<int32_t>(),
                                                   offsets.as<int64_t>(), first.as<uint32_t>(), out_probe.as<int64_t>(),
                                                   pairs ? out_build.as<int64_t>() : nullptr);
     SB_LAUNCH_CHECK();
   }
-  sb_table *left = gather_table(probe, out_probe.as<int64_t>(), nout, false, st);
+  if (nun > 0) {
+    fill_i64_kernel<<<(unsigned)((nun + 255) / 256), 256, 0, st>>>(out_probe.as<int64_t>() + npairs, nun, -1);
+    SB_LAUNCH_CHECK();
+    SB_CUDA(cudaMemcpyAsync(out_build.as<int64_t>() + npairs, un_idx.ptr, (size_t)nun * 8, cudaMemcpyDeviceToDevice, st));
+  }
+  sb_table *left = gather_table(probe, out_probe.as<int64_t>(), nout, build_rows_too, st);
   if (!pairs) {
     *out = left;
   } else {
     sb_table *right = nullptr;
     try {
-      right = gather_table(ht->build, out_build.as<int64_t>(), nout, join_type == SB_JOIN_LEFT_OUTER, st);
+      right = gather_table(ht->build, out_build.as<int64_t>(), nout, kt_type == SB_JOIN_LEFT_OUTER, st);
     } catch (...) {
       table_free(left);
       throw;
@@ -322,6 +414,147 @@ int sb_join_probe(const sb_hash_table *ht, const sb_table *probe, const int32_t 
     table_free(right);
     *out = left;
   }
+  SB_CUDA(cudaStreamSynchronize(st));
+  SB_API_END
+}
+
+__global__ void scatter_flag_kernel(const int64_t *__restrict__ idx, int64_t n, uint8_t *__restrict__ flags) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && idx[i] >= 0) flags[idx[i]] = 1;
+}
+__global__ void invert_flag_kernel(uint8_t *flags, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flags[i] = !flags[i];
+}
+__global__ void gather_i64_kernel(const int64_t *__restrict__ src, const int64_t *__restrict__ idx, int64_t n, int64_t *__restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = src[idx[i]];
+}
+__global__ void null_key_rows_kernel(sb::JoinKeys k, int64_t n, uint8_t *__restrict__ flags) {   // flags[i] = 1 where the key is NULL
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t key;
+  if (i < n) flags[i] = !sb::join_key(k, i, key);
+}
+
+// Equi-join with a residual condition (HashJoin.scala:144-172 boundCondition): `condition` is evaluated on the joined row
+// (streamed columns ++ build columns) of every key match, and only pairs for which it is TRUE count as matches -- which matters
+// for every join type but inner: an outer row whose key matches but whose condition never holds is NULL-extended, a semi / anti /
+// existence row is judged by the surviving pairs.  condition == NULL is sb_join_probe.
+int sb_join_probe_condition(const sb_hash_table *ht, const sb_table *probe, const int32_t *key_cols, int32_t nkeys, int32_t join_type,
+                            const sb_expr *condition, sb_stream *s, sb_table **out) {
+  if (!condition) return sb_join_probe(ht, probe, key_cols, nkeys, join_type, s, out);
+  SB_API_BEGIN
+  require_init();
+  SB_REQUIRE(ht && probe && key_cols && out, "null argument");
+  SB_REQUIRE(join_type >= SB_JOIN_INNER && join_type <= SB_JOIN_LEFT_ANTI_NULL_AWARE, "unknown join type %d", join_type);
+  if (join_type == SB_JOIN_LEFT_ANTI_NULL_AWARE) fail(SB_ERR_UNSUPPORTED, "the null-aware anti join takes no residual condition (BroadcastHashJoinExec.scala:73-76)");
+  cudaStream_t st = stream_of(s);
+  const int64_t n = probe->nrows, nbuild = ht->build->nrows;
+  // 1. every key match as an inner pair table
+  sb_table *pairs_tbl = nullptr;
+  {
+    int rc = sb_join_probe(ht, probe, key_cols, nkeys, SB_JOIN_INNER, s, &pairs_tbl);
+    if (rc != SB_OK) fail(rc, "%s", sb_last_error());
+  }
+  // the pair indices are needed as well: recompute them cheaply by joining row-id columns would double the work, so the pair table
+  // is built again below from indices; here only the mask is taken from it
+  struct Guard { sb_table *&t; ~Guard() { if (t) sb::table_free(t); } } g1{pairs_tbl};
+  const int64_t npairs = pairs_tbl->nrows;
+  expr_validate(pairs_tbl, *condition);
+  Scratch mask(npairs + 16, st);
+  if (npairs > 0) eval_predicate(pairs_tbl, *condition, mask.as<uint8_t>(), st);
+  // pair indices: the same kernels again with index outputs only (count + fill), cheaper than carrying row ids through the gather
+  JoinKeys k = make_join_keys(probe, key_cols, nkeys, ht);
+  unsigned nb = (unsigned)((n + JOIN_THREADS - 1) / JOIN_THREADS);
+  Scratch counts(n * 4 + 16, st), first(n * 4 + 16, st), block_counts((int64_t)nb * 4 + 16, st), offsets((int64_t)nb * 8 + 16, st), total(8, st);
+  Scratch pi(npairs * 8 + 16, st), bi(npairs * 8 + 16, st);
+  if (n > 0) {
+    join_count_kernel<<<nb, JOIN_THREADS, 0, st>>>(k, n, ht->slots, ht->cap, SB_JOIN_INNER, 0, counts.as<int32_t>(), first.as<uint32_t>(),
+                                                   block_counts.as<int32_t>(), nullptr);
+    SB_LAUNCH_CHECK();
+    exclusive_scan_i32_to_i64(block_counts.as<int32_t>(), offsets.as<int64_t>(), nb, total.as<int64_t>(), st);
+    if (npairs > 0) {
+      join_fill_kernel<<<nb, JOIN_THREADS, 0, st>>>(k, n, ht->slots, ht->cap, SB_JOIN_INNER, counts.as<int32_t>(), offsets.as<int64_t>(),
+                                                    first.as<uint32_t>(), pi.as<int64_t>(), bi.as<int64_t>());
+      SB_LAUNCH_CHECK();
+    }
+  }
+  // 2. surviving pairs
+  Scratch keep(npairs * 8 + 16, st);
+  const int64_t nkeep = npairs > 0 ? compact_mask(mask.as<uint8_t>(), npairs, keep.as<int64_t>(), st) : 0;
+  Scratch spi(nkeep * 8 + 16, st), sbi(nkeep * 8 + 16, st);
+  if (nkeep > 0) {
+    gather_i64_kernel<<<(unsigned)((nkeep + 255) / 256), 256, 0, st>>>(pi.as<int64_t>(), keep.as<int64_t>(), nkeep, spi.as<int64_t>());
+    gather_i64_kernel<<<(unsigned)((nkeep + 255) / 256), 256, 0, st>>>(bi.as<int64_t>(), keep.as<int64_t>(), nkeep, sbi.as<int64_t>());
+    SB_LAUNCH_CHECK();
+  }
+  // 3. which streamed / build rows have a surviving pair
+  Scratch pflag(n + 16, st), bflag(nbuild + 16, st);
+  SB_CUDA(cudaMemsetAsync(pflag.ptr, 0, (size_t)n + 16, st));
+  SB_CUDA(cudaMemsetAsync(bflag.ptr, 0, (size_t)nbuild + 16, st));
+  if (nkeep > 0) {
+    scatter_flag_kernel<<<(unsigned)((nkeep + 255) / 256), 256, 0, st>>>(spi.as<int64_t>(), nkeep, pflag.as<uint8_t>());
+    scatter_flag_kernel<<<(unsigned)((nkeep + 255) / 256), 256, 0, st>>>(sbi.as<int64_t>(), nkeep, bflag.as<uint8_t>());
+    SB_LAUNCH_CHECK();
+  }
+  auto rows_where = [&](Scratch &flags, int64_t rows, bool want_set, Scratch &idx_out) -> int64_t {
+    if (rows == 0) return 0;
+    if (!want_set) {
+      invert_flag_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(flags.as<uint8_t>(), rows);
+      SB_LAUNCH_CHECK();
+    }
+    return compact_mask(flags.as<uint8_t>(), rows, idx_out.as<int64_t>(), st);
+  };
+  if (join_type == SB_JOIN_EXISTENCE) {
+    sb_table *t = table_new(n);
+    for (auto &c : probe->cols) t->cols.push_back(column_share(c));
+    Column e = column_alloc(SB_BOOL, 0, n, false, st);
+    t->cols.push_back(e);
+    if (n > 0) SB_CUDA(cudaMemcpyAsync(e.data->ptr, pflag.ptr, (size_t)n, cudaMemcpyDeviceToDevice, st));
+    *out = t;
+    SB_CUDA(cudaStreamSynchronize(st));
+    return SB_OK;
+  }
+  if (join_type == SB_JOIN_LEFT_SEMI || join_type == SB_JOIN_LEFT_ANTI) {
+    Scratch idx(n * 8 + 16, st);
+    const int64_t m = rows_where(pflag, n, join_type == SB_JOIN_LEFT_SEMI, idx);
+    *out = gather_table(probe, idx.as<int64_t>(), m, false, st);
+    SB_CUDA(cudaStreamSynchronize(st));
+    return SB_OK;
+  }
+  const bool keep_probe = join_type == SB_JOIN_LEFT_OUTER || join_type == SB_JOIN_FULL_OUTER;
+  const bool keep_build = join_type == SB_JOIN_BUILD_OUTER || join_type == SB_JOIN_FULL_OUTER;
+  Scratch up(keep_probe ? n * 8 + 16 : 0, st), ub(keep_build ? nbuild * 8 + 16 : 0, st);
+  const int64_t nup = keep_probe ? rows_where(pflag, n, false, up) : 0;
+  const int64_t nub = keep_build ? rows_where(bflag, nbuild, false, ub) : 0;
+  const int64_t nout = nkeep + nup + nub;
+  Scratch op(nout * 8 + 16, st), ob(nout * 8 + 16, st);
+  if (nkeep > 0) {
+    SB_CUDA(cudaMemcpyAsync(op.ptr, spi.ptr, (size_t)nkeep * 8, cudaMemcpyDeviceToDevice, st));
+    SB_CUDA(cudaMemcpyAsync(ob.ptr, sbi.ptr, (size_t)nkeep * 8, cudaMemcpyDeviceToDevice, st));
+  }
+  if (nup > 0) {
+    SB_CUDA(cudaMemcpyAsync(op.as<int64_t>() + nkeep, up.ptr, (size_t)nup * 8, cudaMemcpyDeviceToDevice, st));
+    fill_i64_kernel<<<(unsigned)((nup + 255) / 256), 256, 0, st>>>(ob.as<int64_t>() + nkeep, nup, -1);
+    SB_LAUNCH_CHECK();
+  }
+  if (nub > 0) {
+    fill_i64_kernel<<<(unsigned)((nub + 255) / 256), 256, 0, st>>>(op.as<int64_t>() + nkeep + nup, nub, -1);
+    SB_LAUNCH_CHECK();
+    SB_CUDA(cudaMemcpyAsync(ob.as<int64_t>() + nkeep + nup, ub.ptr, (size_t)nub * 8, cudaMemcpyDeviceToDevice, st));
+  }
+  sb_table *left = gather_table(probe, op.as<int64_t>(), nout, keep_build, st);
+  sb_table *right = nullptr;
+  try {
+    right = gather_table(ht->build, ob.as<int64_t>(), nout, keep_probe, st);
+  } catch (...) {
+    table_free(left);
+    throw;
+  }
+  for (auto &c : right->cols) left->cols.push_back(c);
+  right->cols.clear();
+  table_free(right);
+  *out = left;
   SB_CUDA(cudaStreamSynchronize(st));
   SB_API_END
 }

@@ -1,0 +1,249 @@
+// radix.cu -- the key sort under SortExec: stable LSD radix sort of (64-bit prefix, row id) pairs.
+//
+// Reference: RadixSort.sortKeyPrefixArray (core/src/main/java/org/apache/spark/util/collection/unsafe/sort/RadixSort.java:178-259):
+// LSD over 8-bit digits of the 64-bit prefix, (prefix, record pointer) pairs moved together, one counting pre-pass that also
+// tells which bytes are identical in every record so their passes are skipped (:213-236).  A stable sort's result does not
+// depend on how the passes are organised, so the GPU version keeps those rules and changes the machinery:
+//   * ONE read of the keys builds all eight 256-bin histograms (and so decides which passes run);
+//   * every pass is ONE kernel ("onesweep"): a block takes the next 4096-pair tile (ticket counter, so tiles run in memory
+//     order), ranks its keys stably per warp with match.any over per-warp digit counters, publishes the tile's 256 digit counts
+//     and obtains its exclusive prefix over all earlier tiles by DECOUPLED LOOK-BACK (64-bit status words: aggregate / inclusive
+//     prefix) -- no separate histogram + scan + scatter launches and no second read of the keys -- then stages the tile in
+//     shared memory in digit order and writes every digit's run contiguously (coalesced 8 + 4 byte stores).
+// HBM traffic per pass: pairs read once, written once (24 B per pair); algorithmic bytes of the whole sort: SURVEY.md 8d
+// counts 2 x 12 B per pair, passes are reported separately by the bench.
+#include "radix.cuh"
+#include "rtc.cuh"
+
+namespace sb {
+
+constexpr int RS_THREADS = 256;
+constexpr int RS_ITEMS = 16;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;   // 4096 pairs
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr size_t RS_SMEM = (size_t)RS_TILE * 12 + 256 * 8 + (size_t)RS_WARPS * 256 * 4 + 256 * 4;
+constexpr uint64_t RS_FLAG_AGG = 1ull << 62, RS_FLAG_INCL = 2ull << 62, RS_VALUE_MASK = (1ull << 62) - 1;
+
+// all eight digit histograms in one read of the keys; also used to skip constant bytes
+__global__ void __launch_bounds__(256) rs_histogram_kernel(const uint64_t *__restrict__ keys, int64_t n, unsigned long long *__restrict__ counts) {
+  __shared__ uint32_t sh[8 * 256];
+  for (int i = threadIdx.x; i < 8 * 256; i += 256) sh[i] = 0;
+  __syncthreads();
+  const int64_t stride = (int64_t)gridDim.x * 256;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) {
+    const uint64_t k = keys[i];
+#pragma unroll
+    for (int b = 0; b < 8; b++) atomicAdd(&sh[b * 256 + ((k >> (8 * b)) & 0xff)], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 8 * 256; i += 256)
+    if (sh[i]) atomicAdd(&counts[i], (unsigned long long)sh[i]);
+}
+
+// counts[8][256] -> exclusive bases per byte (in place)
+__global__ void __launch_bounds__(256) rs_scan_kernel(unsigned long long *__restrict__ counts) {
+  __shared__ unsigned long long s[256];
+  const int b = blockIdx.x, t = threadIdx.x;
+  const unsigned long long c = counts[b * 256 + t];
+  s[t] = c;
+  __syncthreads();
+  for (int d = 1; d < 256; d <<= 1) {
+    unsigned long long v = t >= d ? s[t - d] : 0;
+    __syncthreads();
+    s[t] += v;
+    __syncthreads();
+  }
+  counts[b * 256 + t] = s[t] - c;
+}
+
+__device__ __forceinline__ uint64_t ld_status(const uint64_t *p) {
+  uint64_t v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_status(uint64_t *p, uint64_t v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// One LSD pass over byte `byte`.  status: [tiles][256] zero-initialised; ticket: zero-initialised tile counter.
+__global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const uint64_t *__restrict__ in_keys, const uint32_t *__restrict__ in_vals,
+                                                                 uint64_t *__restrict__ out_keys, uint32_t *__restrict__ out_vals, int64_t n, int byte,
+                                                                 const unsigned long long *__restrict__ gbase /* [256] of this byte */,
+                                                                 uint64_t *__restrict__ status, uint32_t *__restrict__ ticket) {
+  extern __shared__ __align__(16) uint8_t rs_smem[];
+  uint64_t *s_keys = (uint64_t *)rs_smem;                                   // [RS_TILE]
+  int64_t *s_dst_off = (int64_t *)(s_keys + RS_TILE);                       // [256] global position of sorted tile position p with digit d: s_dst_off[d] + p
+  uint32_t *s_vals = (uint32_t *)(s_dst_off + 256);                         // [RS_TILE]
+  uint32_t(*s_whist)[256] = (uint32_t(*)[256])(s_vals + RS_TILE);           // [RS_WARPS][256] per-warp digit counters, then exclusive prefixes over the warps
+  uint32_t *s_bin_start = (uint32_t *)(s_whist + RS_WARPS);                 // [256] first tile-local position of every digit
+  __shared__ uint32_t s_tile;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+  for (int i = tid; i < RS_WARPS * 256; i += RS_THREADS) (&s_whist[0][0])[i] = 0;
+  __syncthreads();
+  const int64_t tile = s_tile;
+  const int64_t tile_base = tile * RS_TILE;
+  const int tile_n = (int)(n - tile_base < RS_TILE ? n - tile_base : RS_TILE);
+  const int shift = 8 * byte;
+  // ---- load (warp-striped: warp w owns rows [w * 512, (w + 1) * 512) of the tile; item k of lane l is row w * 512 + k * 32 + l) ----
+  uint64_t key[RS_ITEMS];
+  uint32_t val[RS_ITEMS];
+  uint16_t rank[RS_ITEMS];
+  const int seg = warp * (32 * RS_ITEMS);
+#pragma unroll
+  for (int k = 0; k < RS_ITEMS; k++) {
+    const int r = seg + k * 32 + lane;
+    if (r < tile_n) {
+      key[k] = in_keys[tile_base + r];
+      val[k] = in_vals[tile_base + r];
+    } else {
+      key[k] = ~0ull;
+      val[k] = 0;
+    }
+  }
+  // ---- stable rank inside the warp's segment: (k, lane) order is memory order -----------------------------------------------------
+  uint32_t *wh = s_whist[warp];
+#pragma unroll
+  for (int k = 0; k < RS_ITEMS; k++) {
+    const bool valid = seg + k * 32 + lane < tile_n;
+    const uint32_t d = valid ? (uint32_t)((key[k] >> shift) & 0xff) : 0xffffffffu;   // invalid rows only match each other
+    const uint32_t peers = __match_any_sync(0xffffffffu, d);
+    const int leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if (lane == leader && valid) {
+      base = wh[d];
+      wh[d] = base + __popc(peers);
+    }
+    base = __shfl_sync(0xffffffffu, base, leader);
+    rank[k] = (uint16_t)(base + __popc(peers & ((1u << lane) - 1)));
+    __syncwarp();
+  }
+  __syncthreads();
+  // ---- per digit (thread t owns digit t): exclusive prefix over the warps, tile count, look-back -------------------------------------
+  uint32_t count = 0;
+#pragma unroll
+  for (int w = 0; w < RS_WARPS; w++) {
+    const uint32_t c = s_whist[w][tid];
+    s_whist[w][tid] = count;
+    count += c;
+  }
+  uint64_t *my_status = status + tile * 256 + tid;
+  st_status(my_status, RS_FLAG_AGG | count);
+  // tile-local exclusive scan of the digit counts (block scan over 256 values)
+  s_bin_start[tid] = count;
+  __syncthreads();
+  for (int d = 1; d < 256; d <<= 1) {
+    const uint32_t v = tid >= d ? s_bin_start[tid - d] : 0;
+    __syncthreads();
+    s_bin_start[tid] += v;
+    __syncthreads();
+  }
+  const uint32_t bin_start = s_bin_start[tid] - count;
+  __syncthreads();
+  s_bin_start[tid] = bin_start;
+  // decoupled look-back: sum the aggregates of earlier tiles until one carries an inclusive prefix
+  uint64_t excl = 0;
+  for (int64_t t = tile - 1; t >= 0;) {
+    const uint64_t s = ld_status(status + t * 256 + tid);
+    const uint64_t flag = s & ~RS_VALUE_MASK;
+    if (flag == 0) continue;   // not published yet: the tile holding ticket t is running (tickets are handed out in order)
+    excl += s & RS_VALUE_MASK;
+    if (flag == RS_FLAG_INCL) break;
+    t--;
+  }
+  st_status(my_status, RS_FLAG_INCL | (excl + count));
+  s_dst_off[tid] = (int64_t)gbase[tid] + (int64_t)excl - (int64_t)bin_start;
+  __syncthreads();
+  // ---- stage the tile in digit order ------------------------------------------------------------------------------------------------
+#pragma unroll
+  for (int k = 0; k < RS_ITEMS; k++) {
+    if (seg + k * 32 + lane < tile_n) {
+      const uint32_t d = (uint32_t)((key[k] >> shift) & 0xff);
+      const uint32_t p = s_bin_start[d] + s_whist[warp][d] + rank[k];
+      s_keys[p] = key[k];
+      s_vals[p] = val[k];
+    }
+  }
+  __syncthreads();
+  // ---- every digit's run goes out contiguously ------------------------------------------------------------------------------------------
+#pragma unroll
+  for (int k = 0; k < RS_ITEMS; k++) {
+    const int p = k * RS_THREADS + tid;
+    if (p < tile_n) {
+      const uint64_t kk = s_keys[p];
+      const int64_t dst = s_dst_off[(kk >> shift) & 0xff] + p;
+      out_keys[dst] = kk;
+      out_vals[dst] = s_vals[p];
+    }
+  }
+}
+
+// Tiny inputs (the 4-row result of Q1, top-N candidates): one block ranks every element by counting -- rank = #keys smaller +
+// #equal keys with a smaller position -- which is a stable sort in one launch with no host round trip.
+constexpr int SMALL_SORT_MAX = 2048;
+__global__ void __launch_bounds__(256) small_sort_kernel(uint64_t *keys, uint32_t *vals, int n) {
+  __shared__ uint64_t sk[SMALL_SORT_MAX];
+  __shared__ uint32_t sv[SMALL_SORT_MAX];
+  for (int i = threadIdx.x; i < n; i += 256) { sk[i] = keys[i]; sv[i] = vals[i]; }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const uint64_t k = sk[i];
+    int rank = 0;
+    for (int j = 0; j < n; j++) rank += (sk[j] < k) || (sk[j] == k && j < i);
+    keys[rank] = k;
+    vals[rank] = sv[i];
+  }
+}
+
+int radix_sort_pairs(uint64_t *keys, uint32_t *vals, int64_t n, cudaStream_t st) {
+  if (n <= 1) return 0;
+  if (n <= SMALL_SORT_MAX) {
+    small_sort_kernel<<<1, 256, 0, st>>>(keys, vals, (int)n);
+    SB_LAUNCH_CHECK();
+    return 1;
+  }
+  Scratch counts(8 * 256 * 8, st);
+  SB_CUDA(cudaMemsetAsync(counts.ptr, 0, 8 * 256 * 8, st));
+  {
+    KernelTimer kt("sort_histogram", st);
+    const int grid = grid_for(n, 256 * 16, rt().num_sms * 8);
+    rs_histogram_kernel<<<grid, 256, 0, st>>>(keys, n, counts.as<unsigned long long>());
+    SB_LAUNCH_CHECK();
+  }
+  std::vector<unsigned long long> h(8 * 256);
+  SB_CUDA(cudaMemcpyAsync(h.data(), counts.ptr, 8 * 256 * 8, cudaMemcpyDeviceToHost, st));
+  rs_scan_kernel<<<8, 256, 0, st>>>(counts.as<unsigned long long>());   // runs while the host looks at the counts
+  SB_LAUNCH_CHECK();
+  SB_CUDA(cudaStreamSynchronize(st));
+  int bytes[8], passes = 0;
+  for (int b = 0; b < 8; b++) {
+    bool varies = true;
+    for (int d = 0; d < 256; d++)
+      if (h[b * 256 + d] == (unsigned long long)n) varies = false;   // every record shares this byte: skip the pass (RadixSort.java:213-236)
+    if (varies) bytes[passes++] = b;
+  }
+  if (passes == 0) return 0;
+  const int64_t tiles = (n + RS_TILE - 1) / RS_TILE;
+  Scratch keys2(n * 8 + 16, st), vals2(n * 4 + 16, st), status((int64_t)passes * tiles * 256 * 8 + 16, st), tickets(8 * 4, st);
+  SB_CUDA(cudaMemsetAsync(status.ptr, 0, (size_t)passes * tiles * 256 * 8, st));
+  SB_CUDA(cudaMemsetAsync(tickets.ptr, 0, 32, st));
+  uint64_t *ik = keys, *ok = keys2.as<uint64_t>();
+  uint32_t *iv = vals, *ov = vals2.as<uint32_t>();
+  if (passes & 1) {   // the sorted values must land in `vals`: an odd number of passes starts from the scratch copy
+    SB_CUDA(cudaMemcpyAsync(vals2.ptr, vals, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+    std::swap(iv, ov);
+  }
+  static std::once_flag once;
+  std::call_once(once, [] { SB_CUDA(cudaFuncSetAttribute(rs_onesweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM)); });
+  KernelTimer kt("sort_passes", st);
+  for (int p = 0; p < passes; p++) {
+    rs_onesweep_kernel<<<(unsigned)tiles, RS_THREADS, RS_SMEM, st>>>(ik, iv, ok, ov, n, bytes[p], counts.as<unsigned long long>() + bytes[p] * 256,
+                                                              status.as<uint64_t>() + (int64_t)p * tiles * 256, tickets.as<uint32_t>() + p);
+    SB_LAUNCH_CHECK();
+    std::swap(ik, ok);
+    std::swap(iv, ov);
+  }
+  return passes;   // scratch buffers are freed in stream order
+}
+
+}  // namespace sb

@@ -67,83 +67,115 @@ __device__ __forceinline__ void store_value(void *out, int width, int64_t i, uin
   }
 }
 
+// unsigned LEB128 at p[pos] (bounded by nbytes); returns the value, *len = bytes consumed
+__device__ __forceinline__ uint32_t read_uvarint(const uint8_t *__restrict__ p, int64_t pos, int64_t nbytes, int *len) {
+  uint32_t v = 0;
+  int shift = 0, l = 0;
+  while (pos + l < nbytes) {
+    const uint8_t b = p[pos + l++];
+    v |= (uint32_t)(b & 0x7f) << shift;
+    shift += 7;
+    if (!(b & 0x80) || shift > 28) break;
+  }
+  *len = l;
+  return v;
+}
+
 // Walks an RLE / bit-packed hybrid stream (VectorizedRleValuesReader.readNextGroup) and calls emit(index, value) for the first
 // max_values values.  Block-cooperative; returns the number of values produced (same in every thread).
+//   * Run headers form a chain (a header says where the next one is), and every link costs a memory round trip.  Writers emit
+//     long stretches of identical runs (parquet-mr: bit-packed runs of 504 values, header 0x7F), so warp 0 walks the chain
+//     SPECULATIVELY: it reads the header at the cursor, then lane l checks that the same header sits l run-lengths further
+//     on; the leading lanes that agree are 32 links resolved in two round trips instead of 32.  Irregular streams degrade to
+//     one link per step, never to a wrong answer.
+//   * Up to 64 runs form a batch; the batch's values are decoded by the whole block (value i finds its run by binary search
+//     in the batch's prefix sums).  part / nparts stripes the BATCHES of one page over several blocks: every block walks the
+//     whole chain (cheap), but decodes only its own batches, so a page of a million values is not one block's job.
 template <class Emit>
-__device__ int64_t hybrid_decode(const uint8_t *__restrict__ p, int64_t nbytes, int bw, int64_t max_values, Emit emit) {
-  __shared__ uint32_t s_count[SCAN_RUNS];      // values of the run (clamped to what is still wanted)
+__device__ int64_t hybrid_decode(const uint8_t *__restrict__ p, int64_t nbytes, int bw, int64_t max_values, int part, int nparts, Emit emit) {
   __shared__ uint64_t s_arg[SCAN_RUNS];        // RLE: the value; packed: byte offset of the run's first group
   __shared__ uint8_t s_rle[SCAN_RUNS];
   __shared__ uint32_t s_pref[SCAN_RUNS + 1];
   __shared__ int s_nruns;
   __shared__ int64_t s_pos;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31;
   if (tid == 0) s_pos = 0;
   __syncthreads();
   int64_t produced = 0;
   if (bw == 0) {   // a dictionary of one entry: every value is 0 (initFromPage :109-113)
-    for (int64_t i = tid; i < max_values; i += SCAN_THREADS) emit(i, 0ull);
+    if (part == 0)
+      for (int64_t i = tid; i < max_values; i += SCAN_THREADS) emit(i, 0ull);
     return max_values;
   }
   const int vbytes = (bw + 7) >> 3;
-  while (produced < max_values) {
-    if (tid == 0) {
+  for (int batch = 0; produced < max_values; batch++) {
+    if (tid < 32) {
       int64_t pos = s_pos;
       int n = 0;
-      uint32_t acc = 0;
-      int64_t want = max_values - produced;
-      s_pref[0] = 0;
-      while (n < SCAN_RUNS && pos < nbytes && (int64_t)acc < want && acc < (1u << 30)) {
-        uint32_t header = 0;
-        int shift = 0;
-        for (;;) {   // unsigned LEB128
-          const uint8_t b = p[pos++];
-          header |= (uint32_t)(b & 0x7f) << shift;
-          shift += 7;
-          if (!(b & 0x80) || pos >= nbytes || shift > 28) break;
+      int64_t acc = 0;
+      const int64_t want = max_values - produced;
+      if (lane == 0) s_pref[0] = 0;
+      while (n < SCAN_RUNS && pos < nbytes && acc < want) {
+        int hlen;
+        const uint32_t header = read_uvarint(p, pos, nbytes, &hlen);
+        const bool packed = header & 1;
+        const int64_t c = packed ? (int64_t)(header >> 1) * 8 : (int64_t)(header >> 1);
+        const int64_t run_bytes = hlen + (packed ? (int64_t)(header >> 1) * bw : vbytes);
+        if (c <= 0) {   // empty run: nothing to decode, step over it
+          pos += run_bytes;
+          continue;
         }
-        uint32_t cnt;
-        if (header & 1) {
-          const uint32_t groups = header >> 1;
-          cnt = groups * 8;
-          s_rle[n] = 0;
-          s_arg[n] = (uint64_t)pos;
-          pos += (int64_t)groups * bw;
-        } else {
-          cnt = header >> 1;
-          s_rle[n] = 1;
-          s_arg[n] = pos + vbytes <= nbytes ? load_le(p + pos, vbytes) : 0;
-          pos += vbytes;
+        const int64_t q = pos + (int64_t)lane * run_bytes;
+        bool same = lane == 0;
+        if (lane > 0 && q + hlen <= nbytes) {
+          int hl2;
+          same = read_uvarint(p, q, nbytes, &hl2) == header && hl2 == hlen;
         }
-        if ((int64_t)cnt > want - (int64_t)acc) cnt = (uint32_t)(want - (int64_t)acc);   // the last packed group may be padded
-        s_count[n] = cnt;
-        acc += cnt;
-        n++;
-        s_pref[n] = acc;
+        const uint32_t ball = __ballot_sync(0xffffffffu, same);
+        int cnt = ball == 0xffffffffu ? 32 : __ffs(~ball) - 1;
+        if (cnt > SCAN_RUNS - n) cnt = SCAN_RUNS - n;
+        const int64_t needed = (want - acc + c - 1) / c;   // runs until the page's value count is reached
+        if (cnt > needed) cnt = (int)needed;
+        if (lane < cnt) {
+          s_rle[n + lane] = packed ? 0 : 1;
+          s_arg[n + lane] = packed ? (uint64_t)(q + hlen) : (q + hlen + vbytes <= nbytes ? load_le(p + q + hlen, vbytes) : 0);
+          int64_t upto = acc + (int64_t)(lane + 1) * c;
+          if (upto > want) upto = want;                    // the last packed group may be padded
+          s_pref[n + lane + 1] = (uint32_t)upto;
+        }
+        n += cnt;
+        pos += (int64_t)cnt * run_bytes;
+        acc += (int64_t)cnt * c;
+        if (acc > want) acc = want;
+        if (acc >= (1ll << 30)) break;                     // keep the batch's prefix sums in 32 bits
       }
-      s_nruns = n;
-      s_pos = pos;
+      if (lane == 0) {
+        s_nruns = n;
+        s_pos = pos;
+      }
     }
     __syncthreads();
     const int nruns = s_nruns;
-    const uint32_t total = s_pref[nruns];
+    const uint32_t total = nruns ? s_pref[nruns] : 0;
     if (nruns == 0 || total == 0) break;   // stream exhausted (malformed page: fewer values than announced)
-    for (uint32_t i = tid; i < total; i += SCAN_THREADS) {
-      int lo = 0, hi = nruns;               // last run with pref <= i
-      while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (s_pref[mid] <= i) lo = mid; else hi = mid;
+    if (batch % nparts == part) {
+      for (uint32_t i = tid; i < total; i += SCAN_THREADS) {
+        int lo = 0, hi = nruns;               // last run with pref <= i
+        while (hi - lo > 1) {
+          const int mid = (lo + hi) >> 1;
+          if (s_pref[mid] <= i) lo = mid; else hi = mid;
+        }
+        uint64_t v;
+        if (s_rle[lo]) v = s_arg[lo];
+        else {
+          const uint64_t bit = (uint64_t)(i - s_pref[lo]) * (uint64_t)bw;
+          const int64_t byte = (int64_t)s_arg[lo] + (int64_t)(bit >> 3);
+          const int need = (int)(((bit & 7) + bw + 7) >> 3);
+          const int avail = (int)(nbytes - byte < need ? (nbytes - byte > 0 ? nbytes - byte : 0) : need);
+          v = (load_le(p + byte, avail) >> (bit & 7)) & ((bw >= 64) ? ~0ull : ((1ull << bw) - 1));
+        }
+        emit(produced + i, v);
       }
-      uint64_t v;
-      if (s_rle[lo]) v = s_arg[lo];
-      else {
-        const uint64_t bit = (uint64_t)(i - s_pref[lo]) * (uint64_t)bw;
-        const int64_t byte = (int64_t)s_arg[lo] + (int64_t)(bit >> 3);
-        const int need = (int)(((bit & 7) + bw + 7) >> 3);
-        const int avail = (int)(nbytes - byte < need ? (nbytes - byte > 0 ? nbytes - byte : 0) : need);
-        v = (load_le(p + byte, avail) >> (bit & 7)) & ((bw >= 64) ? ~0ull : ((1ull << bw) - 1));
-      }
-      emit(produced + i, v);
     }
     produced += total;
     __syncthreads();
@@ -151,17 +183,22 @@ __device__ int64_t hybrid_decode(const uint8_t *__restrict__ p, int64_t nbytes, 
   return produced;
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS) scan_decode_kernel(const PageTask *__restrict__ pages, const ColTask *__restrict__ cols) {
-  const PageTask pg = pages[blockIdx.x];
+__global__ void __launch_bounds__(SCAN_THREADS) scan_decode_kernel(const PageTask *__restrict__ pages, const ColTask *__restrict__ cols, int nparts) {
+  const PageTask pg = pages[blockIdx.x / nparts];
+  int part = blockIdx.x % nparts;
   const ColTask c = cols[pg.col];
   const int tid = threadIdx.x;
   const int64_t n = pg.num_values;
   // ---- (1) definition levels -> validity bytes -------------------------------------------------------------------------
   uint8_t *vb = c.valid_bytes ? c.valid_bytes + pg.row_start : nullptr;
   const bool page_nullable = pg.def != nullptr && pg.def_bytes > 0;
-  if (vb) {
+  if (page_nullable || pg.encoding != SB_ENC_RLE_DICTIONARY) {   // only hybrid-encoded, NULL-free pages are striped over several blocks
+    if (part != 0) return;
+    nparts = 1;
+  }
+  if (vb && part == 0) {
     if (page_nullable) {
-      const int64_t got = hybrid_decode(pg.def, pg.def_bytes, 1, n, [&](int64_t i, uint64_t v) { vb[i] = (uint8_t)(v & 1); });
+      const int64_t got = hybrid_decode(pg.def, pg.def_bytes, 1, n, 0, 1, [&](int64_t i, uint64_t v) { vb[i] = (uint8_t)(v & 1); });
       for (int64_t i = got + tid; i < n; i += SCAN_THREADS) vb[i] = 0;
     } else {
       for (int64_t i = tid; i < n; i += SCAN_THREADS) vb[i] = 1;
@@ -195,12 +232,12 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_decode_kernel(const PageTas
     }
   } else if (pg.encoding == SB_ENC_RLE_BOOLEAN) {   // BOOLEAN values as RLE (data page V2 writers): [4-byte length][hybrid, bit width 1]
     if (pg.values_bytes > 4)
-      hybrid_decode(pg.values + 4, pg.values_bytes - 4, 1, n, [&](int64_t i, uint64_t v) { ((uint8_t *)dense)[i] = (uint8_t)(v & 1); });
+      hybrid_decode(pg.values + 4, pg.values_bytes - 4, 1, n, 0, 1, [&](int64_t i, uint64_t v) { ((uint8_t *)dense)[i] = (uint8_t)(v & 1); });
   } else {   // RLE_DICTIONARY: [bit width][hybrid runs of dictionary indices]
     const int bw = pg.values_bytes > 0 ? pg.values[0] : 0;
     const uint8_t *dict = c.dict;
     const int pw = c.phys_width, dcount = c.dict_count;
-    hybrid_decode(pg.values + 1, pg.values_bytes - 1, bw, n, [&](int64_t i, uint64_t idx) {
+    hybrid_decode(pg.values + 1, pg.values_bytes - 1, bw, n, part, nparts, [&](int64_t i, uint64_t idx) {
       uint64_t v = 0;
       if ((int64_t)idx < dcount) v = pw == 0 ? dict[idx] : load_le(dict + idx * pw, pw);
       if (pw == 4 && ow == 8) v = (uint64_t)(int64_t)(int32_t)v;
@@ -587,7 +624,10 @@ extern "C" int sb_scan_decode(const sb_column_chunk *chunks, int32_t ncols, sb_s
       SB_CUDA(cudaMemcpyAsync(d_cols.ptr, ctasks.data(), (size_t)ncols * sizeof(ColTask), cudaMemcpyHostToDevice, st));
       {
         KernelTimer kt("scan_decode", st);
-        scan_decode_kernel<<<(unsigned)tasks.size(), SCAN_THREADS, 0, st>>>(d_pages.as<PageTask>(), d_cols.as<ColTask>());
+        // enough blocks to fill the machine: pages of hybrid-encoded values are striped over `nparts` blocks each
+        int nparts = (int)((rt().num_sms * 6 + (int64_t)tasks.size() - 1) / (int64_t)tasks.size());
+        nparts = nparts < 1 ? 1 : (nparts > 16 ? 16 : nparts);
+        scan_decode_kernel<<<(unsigned)(tasks.size() * nparts), SCAN_THREADS, 0, st>>>(d_pages.as<PageTask>(), d_cols.as<ColTask>(), nparts);
         SB_LAUNCH_CHECK();
       }
       for (int ci = 0; ci < ncols; ci++)

@@ -13,13 +13,15 @@
 // GPU design: every sort column is turned into an order-preserving unsigned 64-bit key (signed -> flip the sign
 // bit, double -> PrefixComparators transform, DESC -> bitwise complement), so one ascending stable LSD pass
 // implementation covers all four (ASC|DESC) x (NULLS FIRST|LAST) orders with the reference's tie order.
-// Each 8-bit pass = digit histogram kernel + the stable multisplit of partition.cu over (key, row id) pairs;
-// constant bytes are skipped like the reference does.  Multi-column orders run column by column from the
+// The key sort itself is csrc/radix.cu (one histogram read, then one "onesweep" kernel per varying byte; constant bytes
+// are skipped like the reference does).  Multi-column orders run column by column from the
 // last to the first (stable passes compose into the lexicographic order TimSort + RowOrdering produces).
 // Payload columns are gathered once at the end.
+#include <algorithm>
 #include "common.cuh"
 #include "multisplit.cuh"
 #include "primitives.cuh"
+#include "radix.cuh"
 
 namespace sb {
 
@@ -54,40 +56,6 @@ __global__ void __launch_bounds__(SORT_THREADS) make_keys_kernel(const void *dat
   if (isnull) isnull[i] = !v;
 }
 
-// one read pass: the eight 256-bin digit histograms (to know which bytes vary, RadixSort.java:213-236)
-__global__ void __launch_bounds__(SORT_THREADS) digit_counts_kernel(const uint64_t *__restrict__ keys, int64_t n,
-                                                                    unsigned long long *__restrict__ counts /* [8][256] */) {
-  __shared__ uint32_t sh[8 * 256];
-  for (int i = threadIdx.x; i < 8 * 256; i += SORT_THREADS) sh[i] = 0;
-  __syncthreads();
-  for (int64_t i = (int64_t)blockIdx.x * SORT_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * SORT_THREADS) {
-    uint64_t k = keys[i];
-#pragma unroll
-    for (int b = 0; b < 8; b++) atomicAdd(&sh[b * 256 + ((k >> (8 * b)) & 0xff)], 1u);
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 8 * 256; i += SORT_THREADS)
-    if (sh[i]) atomicAdd(&counts[i], (unsigned long long)sh[i]);
-}
-
-// bucket id = digit `byte` of the key, plus the per-block histogram in the layout multisplit_scatter expects
-__global__ void __launch_bounds__(SORT_THREADS) digit_hist_kernel(const uint64_t *__restrict__ keys, int64_t n, int byte,
-                                                                  int64_t chunk, int32_t *__restrict__ bucket,
-                                                                  uint32_t *__restrict__ hist) {
-  __shared__ uint32_t sh[256];
-  sh[threadIdx.x] = 0;
-  __syncthreads();
-  int64_t begin = (int64_t)blockIdx.x * chunk;
-  int64_t end = begin + chunk < n ? begin + chunk : n;
-  for (int64_t i = begin + threadIdx.x; i < end; i += SORT_THREADS) {
-    int d = (int)((keys[i] >> (8 * byte)) & 0xff);
-    bucket[i] = d;
-    atomicAdd(&sh[d], 1u);
-  }
-  __syncthreads();
-  hist[(int64_t)threadIdx.x * gridDim.x + blockIdx.x] = sh[threadIdx.x];
-}
-
 // 1-bit stable split used for NULL placement in multi-column orders
 __global__ void __launch_bounds__(SORT_THREADS) flag_hist_kernel(const uint8_t *__restrict__ flag, int invert, int64_t n,
                                                                  int64_t chunk, int32_t *__restrict__ bucket,
@@ -104,67 +72,6 @@ __global__ void __launch_bounds__(SORT_THREADS) flag_hist_kernel(const uint8_t *
   }
   __syncthreads();
   if (threadIdx.x < 2) hist[(int64_t)threadIdx.x * gridDim.x + blockIdx.x] = sh[threadIdx.x];
-}
-
-// Tiny inputs (the 4-row result of Q1, top-N candidates): one block ranks every element by counting -- rank = #keys smaller +
-// #equal keys with a smaller position -- which is a stable sort in one launch with no host round trip.
-constexpr int SMALL_SORT_MAX = 2048;
-__global__ void __launch_bounds__(256) small_sort_kernel(uint64_t *keys, uint32_t *vals, int n) {
-  __shared__ uint64_t sk[SMALL_SORT_MAX];
-  __shared__ uint32_t sv[SMALL_SORT_MAX];
-  for (int i = threadIdx.x; i < n; i += 256) { sk[i] = keys[i]; sv[i] = vals[i]; }
-  __syncthreads();
-  for (int i = threadIdx.x; i < n; i += 256) {
-    const uint64_t k = sk[i];
-    int rank = 0;
-    for (int j = 0; j < n; j++) rank += (sk[j] < k) || (sk[j] == k && j < i);
-    keys[rank] = k;
-    vals[rank] = sv[i];
-  }
-}
-
-// Stable ascending LSD radix sort of (keys, vals) in place (ping-pong buffers inside).  Returns passes run.
-static int radix_sort_pairs(uint64_t *keys, uint32_t *vals, int64_t n, cudaStream_t st) {
-  if (n <= 1) return 0;
-  if (n <= SMALL_SORT_MAX) {
-    small_sort_kernel<<<1, 256, 0, st>>>(keys, vals, (int)n);
-    SB_LAUNCH_CHECK();
-    return 1;
-  }
-  Scratch counts(8 * 256 * 8, st);
-  SB_CUDA(cudaMemsetAsync(counts.ptr, 0, 8 * 256 * 8, st));
-  int grid = grid_for(n, SORT_THREADS * 8, rt().num_sms * 8);
-  digit_counts_kernel<<<grid, SORT_THREADS, 0, st>>>(keys, n, counts.as<unsigned long long>());
-  SB_LAUNCH_CHECK();
-  std::vector<unsigned long long> h(8 * 256);
-  SB_CUDA(cudaMemcpyAsync(h.data(), counts.ptr, 8 * 256 * 8, cudaMemcpyDeviceToHost, st));
-  SB_CUDA(cudaStreamSynchronize(st));
-  bool varies[8];
-  for (int b = 0; b < 8; b++) {
-    varies[b] = true;
-    for (int d = 0; d < 256; d++)
-      if (h[b * 256 + d] == (unsigned long long)n) varies[b] = false;   // every record shares this byte: skip the pass
-  }
-  PartGeometry g = part_geometry(n, 256);
-  Scratch keys2(n * 8 + 16, st), vals2(n * 4 + 16, st), bucket(n * 4 + 16, st), hist((int64_t)256 * g.nblocks * 4 + 16, st);
-  uint64_t *ik = keys, *ok = keys2.as<uint64_t>();
-  uint32_t *iv = vals, *ov = vals2.as<uint32_t>();
-  int passes = 0;
-  for (int b = 0; b < 8; b++) {
-    if (!varies[b]) continue;
-    digit_hist_kernel<<<g.nblocks, SORT_THREADS, 0, st>>>(ik, n, b, g.chunk, bucket.as<int32_t>(), hist.as<uint32_t>());
-    SB_LAUNCH_CHECK();
-    SplitCol cols[2] = {{8, ik, ok, nullptr, nullptr}, {4, iv, ov, nullptr, nullptr}};
-    multisplit_scatter(bucket.as<int32_t>(), hist.as<uint32_t>(), 256, g, cols, 2, n, nullptr, nullptr, st);
-    std::swap(ik, ok);
-    std::swap(iv, ov);
-    passes++;
-  }
-  if (ik != keys) {
-    SB_CUDA(cudaMemcpyAsync(keys, ik, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
-    SB_CUDA(cudaMemcpyAsync(vals, iv, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
-  }
-  return passes;   // scratch buffers are freed in stream order
 }
 
 // stable split of vals by a 0/1 flag (flag[i] belongs to vals[i]): zeros first unless invert
@@ -262,6 +169,26 @@ __global__ void __launch_bounds__(SORT_THREADS) range_pid_hist_kernel(const void
   }
   __syncthreads();
   for (int i = threadIdx.x; i <= nbounds; i += SORT_THREADS) hist[(int64_t)i * gridDim.x + blockIdx.x] = sh[i];
+}
+
+// ---- radix select for TakeOrderedAndProject: which keys can be among the k smallest? -------------------------------------------
+// 256-bin histogram of the byte below the `bits` already fixed high bits, over the rows whose key starts with `prefix`
+__global__ void __launch_bounds__(SORT_THREADS) select_hist_kernel(const void *data, int32_t type, int desc, int64_t n, uint64_t prefix, int bits,
+                                                                   uint32_t *__restrict__ hist) {
+  __shared__ uint32_t sh[256];
+  sh[threadIdx.x] = 0;
+  __syncthreads();
+  const int shift = 56 - bits;
+  for (int64_t i = (int64_t)blockIdx.x * SORT_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * SORT_THREADS) {
+    const uint64_t k = sort_key(data, type, i, desc != 0);
+    if (bits == 0 || (k >> (64 - bits)) == (prefix >> (64 - bits))) atomicAdd(&sh[(k >> shift) & 0xff], 1u);
+  }
+  __syncthreads();
+  if (sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
+}
+__global__ void __launch_bounds__(SORT_THREADS) select_mask_kernel(const void *data, int32_t type, int desc, int64_t n, uint64_t hi, uint8_t *__restrict__ mask) {
+  const int64_t i = (int64_t)blockIdx.x * SORT_THREADS + threadIdx.x;
+  if (i < n) mask[i] = sort_key(data, type, i, desc != 0) <= hi;
 }
 
 static bool radix_eligible(int32_t type) { return type != SB_STRING; }
@@ -449,22 +376,199 @@ int sb_range_partition(const sb_table *in, const sb_sort_order *order, const sb_
   SB_API_END
 }
 
+// ---- RangePartitioner, sampling half (core/src/main/scala/org/apache/spark/Partitioner.scala:175-320, 334-357) -----------------------
+// sketch(): every input partition contributes up to sampleSizePerPartition keys drawn uniformly without replacement plus its row
+// count; the weight of a candidate is n / sample.length (:229).  The reference draws with a reservoir seeded from the RDD id
+// (XORShiftRandom: parity unpinned, like the round-robin start); here row j of the sample is a jittered-stratified draw
+// floor((j + u_j) * n / k), which gives every row the same inclusion probability k / n.
+__global__ void range_sample_idx_kernel(int64_t n, int64_t k, uint64_t seed, int64_t *__restrict__ idx) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= k) return;
+  uint64_t x = seed + 0x9e3779b97f4a7c15ull * (uint64_t)(j + 1);
+  x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull; x ^= x >> 27; x *= 0x94d049bb133111ebull; x ^= x >> 31;
+  const double u = (double)(x >> 11) * (1.0 / 9007199254740992.0);
+  int64_t r = (int64_t)(((double)j + u) * (double)n / (double)k);
+  idx[j] = r < 0 ? 0 : (r >= n ? n - 1 : r);
+}
+__global__ void fill_f32_kernel(float *out, int64_t n, float v) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = v;
+}
+
+int sb_range_sample(const sb_table *in, const sb_sort_order *order, int64_t sample_size, uint64_t seed, sb_stream *s, sb_table **out) {
+  SB_API_BEGIN
+  require_init();
+  SB_REQUIRE(in && order && out && sample_size > 0, "bad argument");
+  SB_REQUIRE(order->col >= 0 && order->col < (int)in->cols.size(), "sort column %d out of range", order->col);
+  cudaStream_t st = stream_of(s);
+  const int64_t n = in->nrows, k = n < sample_size ? n : sample_size;
+  const Column &c = in->cols[order->col];
+  if (!radix_eligible(c.type)) fail(SB_ERR_UNSUPPORTED, "range partitioning on string columns is not implemented");
+  Scratch idx(k * 8 + 16, st);
+  if (k > 0) {
+    if (k == n) iota_i64(idx.as<int64_t>(), k, 0, st);
+    else {
+      range_sample_idx_kernel<<<nblk(k), 256, 0, st>>>(n, k, seed, idx.as<int64_t>());
+      SB_LAUNCH_CHECK();
+    }
+  }
+  sb_table *t = table_new(k);
+  try {
+    t->cols.push_back(gather_column(c, idx.as<int64_t>(), k, false, st));
+    Column w = column_alloc(SB_FLOAT32, 0, k, false, st);
+    t->cols.push_back(w);
+    if (k > 0) {
+      fill_f32_kernel<<<nblk(k), 256, 0, st>>>((float *)w.data->ptr, k, (float)((double)n / (double)k));   // (n.toDouble / sample.length).toFloat
+      SB_LAUNCH_CHECK();
+    }
+  } catch (...) {
+    table_free(t);
+    throw;
+  }
+  *out = t;
+  SB_API_END
+}
+
+// determineBounds (:357-388): candidates sorted by key; walk the cumulative weight in steps of sumWeights / partitions and take
+// the candidate that crosses each step as a bound, skipping keys equal to the previous bound.  `sample` = (key, weight float32)
+// rows of every input partition (after the all-gather in a multi-GPU job); returns a one-column table of <= partitions - 1 bounds.
+int sb_range_determine_bounds(const sb_table *sample, const sb_sort_order *order, int32_t num_partitions, sb_stream *s, sb_table **out) {
+  SB_API_BEGIN
+  require_init();
+  SB_REQUIRE(sample && order && out && sample->cols.size() == 2 && sample->cols[1].type == SB_FLOAT32, "sample must be (key, float32 weight)");
+  SB_REQUIRE(num_partitions >= 0, "bad partition count");
+  cudaStream_t st = stream_of(s);
+  const Column &c = sample->cols[0];
+  const int64_t m = sample->nrows;
+  const int partitions = (int)std::min<int64_t>(num_partitions, m);    // math.min(partitions, candidates.size)
+  std::vector<int64_t> picked;
+  if (m > 0 && partitions > 1) {
+    Scratch keys(m * 8 + 16, st), isnull(m + 16, st);
+    make_keys_kernel<<<nblk(m), SORT_THREADS, 0, st>>>(c.d(), c.v(), c.type, !order->ascending, nullptr, m, keys.as<uint64_t>(), isnull.as<uint8_t>());
+    SB_LAUNCH_CHECK();
+    std::vector<uint64_t> hk((size_t)m);
+    std::vector<uint8_t> hn((size_t)m);
+    std::vector<float> hw((size_t)m);
+    SB_CUDA(cudaMemcpyAsync(hk.data(), keys.ptr, (size_t)m * 8, cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaMemcpyAsync(hn.data(), isnull.ptr, (size_t)m, cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaMemcpyAsync(hw.data(), sample->cols[1].d(), (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaStreamSynchronize(st));
+    const int null_rank = order->nulls_first ? 0 : 2;
+    auto rank_of = [&](int64_t i) { return hn[i] ? null_rank : 1; };
+    auto less = [&](int64_t a, int64_t b) {
+      const int ra = rank_of(a), rb = rank_of(b);
+      if (ra != rb) return ra < rb;
+      return ra == 1 && hk[a] < hk[b];
+    };
+    std::vector<int64_t> ord((size_t)m);
+    for (int64_t i = 0; i < m; i++) ord[i] = i;
+    std::stable_sort(ord.begin(), ord.end(), less);                    // candidates.sortBy(_._1)
+    double sum = 0;
+    for (int64_t i = 0; i < m; i++) sum += (double)hw[i];
+    const double step = sum / partitions;
+    double cum = 0, target = step;
+    int64_t prev = -1;
+    for (int64_t i = 0, j = 0; i < m && j < partitions - 1; i++) {
+      const int64_t cand = ord[i];
+      cum += (double)hw[cand];
+      if (cum >= target) {
+        if (prev < 0 || less(prev, cand)) {                            // skip duplicate values
+          picked.push_back(cand);
+          target += step;
+          j++;
+          prev = cand;
+        }
+      }
+    }
+  }
+  const int64_t nb = (int64_t)picked.size();
+  Scratch idx(nb * 8 + 16, st);
+  if (nb > 0) {
+    SB_CUDA(cudaMemcpyAsync(idx.ptr, picked.data(), (size_t)nb * 8, cudaMemcpyHostToDevice, st));
+  }
+  sb_table *t = table_new(nb);
+  try {
+    t->cols.push_back(gather_column(c, idx.as<int64_t>(), nb, false, st));
+    SB_CUDA(cudaStreamSynchronize(st));   // `picked` backs the copy above
+  } catch (...) {
+    table_free(t);
+    throw;
+  }
+  *out = t;
+  SB_API_END
+}
+
 // TakeOrderedAndProjectExec: the reference keeps a bounded priority queue per partition and merges
 // (limit.scala:347-386); the result is the first k rows of the total order, which is what this returns.
 int sb_top_n(const sb_table *in, const sb_sort_order *orders, int32_t norders, int64_t k, sb_stream *s, sb_table **out) {
   SB_API_BEGIN
   require_init();
   SB_REQUIRE(in && out && k >= 0, "bad argument");
+  SB_REQUIRE(norders >= 1 && orders, "top-n needs at least one order");
   cudaStream_t st = stream_of(s);
   int64_t n = in->nrows;
   int64_t take = k < n ? k : n;
-  Scratch perm(n * 4 + 16, st), perm64(take * 8 + 16, st);
-  sort_permutation_impl(in, orders, norders, perm.as<uint32_t>(), st);
-  if (take > 0) {
-    u32_to_i64_kernel<<<nblk(take), 256, 0, st>>>(perm.as<uint32_t>(), take, perm64.as<int64_t>());
-    SB_LAUNCH_CHECK();
+  SB_REQUIRE(orders[0].col >= 0 && orders[0].col < (int)in->cols.size(), "sort column %d out of range", orders[0].col);
+  const Column &c0 = in->cols[orders[0].col];
+  const sb_table *src = in;
+  sb_table *cand = nullptr;
+  // Bounded selection instead of a full sort (the reference keeps a k-element heap per partition, Utils.takeOrdered): a radix
+  // select on the FIRST sort column finds a key bound such that the rows at or below it number >= k but few; only those rows are
+  // sorted (by all the sort columns, stably), so the answer is the first k rows of the full stable sort.
+  if (take > 0 && n > 65536 && take * 8 <= n && !c0.validity && radix_eligible(c0.type)) {
+    const int desc = !orders[0].ascending;
+    Scratch hist(256 * 4, st);
+    uint32_t h[256];
+    uint64_t prefix = 0;
+    int bits = 0;
+    int64_t below = 0, k_rem = take, in_bucket = n;
+    const int64_t budget = std::max<int64_t>(4 * take, 65536);
+    const int grid = grid_for(n, SORT_THREADS * 8, rt().num_sms * 8);
+    while (bits < 64 && below + in_bucket > budget) {
+      SB_CUDA(cudaMemsetAsync(hist.ptr, 0, 256 * 4, st));
+      select_hist_kernel<<<grid, SORT_THREADS, 0, st>>>(c0.d(), c0.type, desc, n, prefix, bits, hist.as<uint32_t>());
+      SB_LAUNCH_CHECK();
+      SB_CUDA(cudaMemcpyAsync(h, hist.ptr, 256 * 4, cudaMemcpyDeviceToHost, st));
+      SB_CUDA(cudaStreamSynchronize(st));
+      int64_t cum = 0;
+      int b = 0;
+      for (; b < 255; b++) {
+        if (cum + h[b] >= k_rem) break;
+        cum += h[b];
+      }
+      below += cum;
+      k_rem -= cum;
+      in_bucket = h[b];
+      prefix |= (uint64_t)b << (56 - bits);
+      bits += 8;
+    }
+    if (bits > 0 && below + in_bucket < n) {
+      const uint64_t hi = bits >= 64 ? prefix : (prefix | ((1ull << (64 - bits)) - 1));
+      const int64_t ncand = below + in_bucket;
+      Scratch mask(n + 16, st), f32(compact_tiles(n) * 4 + 16, st), pos(compact_tiles(n) * 8 + 16, st), total(8, st);
+      select_mask_kernel<<<nblk(n), SORT_THREADS, 0, st>>>(c0.d(), c0.type, desc, n, hi, mask.as<uint8_t>());
+      SB_LAUNCH_CHECK();
+      // the candidate count is known from the histograms: no read-back
+      Scratch idx_full(n * 8 + 16, st);
+      compact_mask_async(mask.as<uint8_t>(), n, idx_full.as<int64_t>(), f32.as<int32_t>(), pos.as<int64_t>(), total.as<int64_t>(), st);
+      cand = gather_table(in, idx_full.as<int64_t>(), ncand, false, st);   // candidates in row order: the stable sort below keeps tie order
+      src = cand;
+      n = ncand;
+    }
   }
-  *out = gather_table(in, perm64.as<int64_t>(), take, false, st);
+  try {
+    Scratch perm(n * 4 + 16, st), perm64(take * 8 + 16, st);
+    sort_permutation_impl(src, orders, norders, perm.as<uint32_t>(), st);
+    if (take > 0) {
+      u32_to_i64_kernel<<<nblk(take), 256, 0, st>>>(perm.as<uint32_t>(), take, perm64.as<int64_t>());
+      SB_LAUNCH_CHECK();
+    }
+    *out = gather_table(src, perm64.as<int64_t>(), take, false, st);
+  } catch (...) {
+    if (cand) table_free(cand);
+    throw;
+  }
+  if (cand) table_free(cand);
   SB_API_END
 }
 

@@ -265,6 +265,38 @@ class RangePartitioning:
         self.numPartitions = bounds.num_rows + 1
 
 
+def range_bounds(batch: ColumnarBatch, ordering, numPartitions: int, stream=None, samplePointsPerPartitionHint: int = 100,
+                 inputPartitions: int = None, seed: int = 0) -> ColumnarBatch:
+    """RangePartitioner's bounds for a global sort (Partitioner.scala:203-236; ShuffleExchangeExec.scala:381-401 uses
+    spark.sql.execution.rangeExchange.sampleSizePerPartition = 100): sample this rank's batch, all-gather the candidates when a
+    communicator is up, determineBounds.  Returns the one-column bounds batch RangePartitioning takes."""
+    import math
+    lib = capi.load()
+    ordering = ordering if isinstance(ordering, SortOrder) else SortOrder(*ordering)
+    rank, world = C.c_int32(), C.c_int32()
+    capi.check(lib.sb_comm_rank(C.byref(rank), C.byref(world)))
+    nin = inputPartitions or max(1, world.value)
+    sample_size = min(float(samplePointsPerPartitionHint) * numPartitions, 1e6)
+    per_partition = int(math.ceil(3.0 * sample_size / nin))
+    orders = _orders_c(batch, [ordering])
+    h = C.c_void_p()
+    capi.check(lib.sb_range_sample(batch.handle, orders, per_partition, seed + rank.value, _h(stream), C.byref(h)))
+    sample = ColumnarBatch(h, [ordering.child, "weight"], [batch.arrow_types[batch.column_index(ordering.child)], None])
+    try:
+        if world.value > 1:
+            g = C.c_void_p()
+            capi.check(lib.sb_all_gather(sample.handle, _h(stream), C.byref(g)))
+            sample.close()
+            sample = ColumnarBatch(g, [ordering.child, "weight"], sample.arrow_types)
+        o2 = (capi.sb_sort_order * 1)()
+        o2[0].col, o2[0].ascending, o2[0].nulls_first = 0, int(ordering.ascending), int(ordering.nulls_first)
+        b = C.c_void_p()
+        capi.check(lib.sb_range_determine_bounds(sample.handle, o2, numPartitions, _h(stream), C.byref(b)))
+        return ColumnarBatch(b, [ordering.child], [sample.arrow_types[0]])
+    finally:
+        sample.close()
+
+
 class ShuffleExchangeExec(SparkPlan):
     """Map side always runs on the local GPU (partition ids + regrouping).  With a communicator
     (sb_comm_init done, world size > 1) the buckets are exchanged with the NCCL all-to-all and the
@@ -320,6 +352,25 @@ class ShuffleExchangeExec(SparkPlan):
         finally:
             part.close()
 
+    # ---- ShuffleExchangeLike members AQE reads (ShuffleExchangeExec.scala:55-151, 235-262) --------------------------------------
+    @property
+    def numPartitions(self):
+        return self.outputPartitioning.numPartitions
+
+    def mapOutputStatistics(self, inp: ColumnarBatch, stream=None) -> np.ndarray:
+        """MapOutputStatistics.bytesByPartitionId of this exchange for the given input: runs the map side and sums the
+        partition sizes over all ranks (sb_map_output_statistics; collective when a communicator is up)."""
+        lib = capi.load()
+        part, offs = self.map_side(inp, stream)
+        try:
+            n = self.numPartitions
+            in_offs = (C.c_int64 * (n + 1))(*offs.tolist())
+            out = (C.c_int64 * n)()
+            capi.check(lib.sb_map_output_statistics(part.handle, in_offs, n, _h(stream), out))
+            return np.array(list(out), dtype=np.int64)
+        finally:
+            part.close()
+
     def partition_ids(self, inp: ColumnarBatch, stream=None) -> np.ndarray:
         """Partition id of every input row (for parity checks against Pmod(Murmur3Hash(keys), n))."""
         import torch
@@ -331,6 +382,60 @@ class ShuffleExchangeExec(SparkPlan):
         capi.check(lib.sb_partition_ids(inp.handle, arr, len(idx), p.numPartitions, _h(stream), C.c_void_p(out.data_ptr())))
         capi.check(lib.sb_stream_synchronize(_h(stream)))
         return out[: inp.num_rows].cpu().numpy()
+
+
+class CoalescedPartitionSpec:
+    """CoalescedPartitionSpec(startReducerIndex, endReducerIndex, dataSize) (SQLX/ShufflePartitionSpec... in ShuffledRowRDD.scala)."""
+
+    def __init__(self, start, end, dataSize=None):
+        self.startReducerIndex, self.endReducerIndex, self.dataSize = start, end, dataSize
+
+    def __eq__(self, o):
+        return (self.startReducerIndex, self.endReducerIndex, self.dataSize) == (o.startReducerIndex, o.endReducerIndex, o.dataSize)
+
+    def __repr__(self):
+        return "CoalescedPartitionSpec(%d, %d, %r)" % (self.startReducerIndex, self.endReducerIndex, self.dataSize)
+
+
+def coalesce_shuffle_partitions(bytes_by_partition, advisoryTargetSize=64 << 20, minNumPartitions=1, minPartitionSize=1 << 20,
+                                maxReducerPartitionsPerTask=2 ** 31 - 1):
+    """CoalesceShufflePartitions (SQLX/adaptive/CoalesceShufflePartitions.scala) for one coalesce group: bytes_by_partition is one
+    array per shuffle of the group.  Returns per shuffle a list of CoalescedPartitionSpec, or [] when the layout stays as it is.
+    Defaults are the reference's: advisoryPartitionSizeInBytes 64 MB, coalescePartitions.minPartitionSize 1 MB."""
+    lib = capi.load()
+    arrs = [np.ascontiguousarray(b, dtype=np.int64) for b in bytes_by_partition]
+    ns, npart = len(arrs), len(arrs[0]) if arrs else 0
+    if ns == 0 or any(len(a) != npart for a in arrs):
+        return []
+    ptrs = (C.POINTER(C.c_int64) * ns)(*[a.ctypes.data_as(C.POINTER(C.c_int64)) for a in arrs])
+    st, en = (C.c_int32 * max(1, npart))(), (C.c_int32 * max(1, npart))()
+    sizes = (C.c_int64 * max(1, ns * npart))()
+    n = C.c_int32()
+    capi.check(lib.sb_coalesce_partitions(ptrs, ns, npart, advisoryTargetSize, minNumPartitions, minPartitionSize, maxReducerPartitionsPerTask,
+                                          st, en, sizes, C.byref(n)))
+    return [[CoalescedPartitionSpec(st[k], en[k], sizes[s * n.value + k]) for k in range(n.value)] for s in range(ns)] if n.value else []
+
+
+class AQEShuffleReadExec(SparkPlan):
+    """AQEShuffleReadExec over coalesced specs (SQLX/adaptive/AQEShuffleReadExec.scala:268-284): hands out the exchange's output
+    as one batch per CoalescedPartitionSpec (a partition-contiguous exchange result makes every spec one row slice)."""
+
+    def __init__(self, child: "ShuffleExchangeExec", partitionSpecs):
+        self.child = child
+        self.partitionSpecs = list(partitionSpecs)
+        self.children = (child,)
+
+    def batches(self, stream=None):
+        out = self.child.executeColumnar(stream)
+        try:
+            offs = self.child.partition_offsets
+            for spec in self.partitionSpecs:
+                yield out.slice(int(offs[spec.startReducerIndex]), int(offs[spec.endReducerIndex]), stream)
+        finally:
+            out.close()
+
+    def executeColumnar(self, stream=None):
+        return self.child.executeColumnar(stream)
 
 
 def _orders_c(batch: ColumnarBatch, sortOrder):
@@ -396,6 +501,7 @@ class HashedRelation:
         self.handle = h
         self.names = batch.names
         self.arrow_types = batch.arrow_types
+        self.types = [batch.column_desc(i).type for i in range(len(batch.names))]
 
     def close(self):
         if self.handle:
@@ -409,51 +515,87 @@ class HashedRelation:
             pass
 
 
-class BroadcastHashJoinExec(SparkPlan):
-    """leftKeys/rightKeys: attribute names; joinType: inner | left_outer | left_semi | left_anti;
-    buildSide: 'right' (the left side is streamed).  Output: left ++ right columns (HashJoin.scala:55-70)."""
+_STREAM_LEFT = {"inner": "inner", "left_outer": "left_outer", "left_semi": "left_semi", "left_anti": "left_anti", "full_outer": "full_outer",
+                "right_outer": "build_outer", "existence": "existence", "left_anti_null_aware": "left_anti_null_aware"}
+_STREAM_RIGHT = {"inner": "inner", "right_outer": "left_outer", "left_outer": "build_outer", "full_outer": "full_outer"}
 
-    def __init__(self, leftKeys, rightKeys, joinType, buildSide, left: SparkPlan, right: SparkPlan):
-        if buildSide != "right":
-            raise capi.SparkB200Error(5, "only buildSide='right' is implemented (swap the children)")
+
+class BroadcastHashJoinExec(SparkPlan):
+    """leftKeys / rightKeys: attribute names; joinType: inner | left_outer | right_outer | full_outer | left_semi | left_anti |
+    existence | left_anti_null_aware; buildSide: 'right' (left is streamed) or 'left'; condition: residual predicate over
+    left ++ right attributes (HashJoin.boundCondition).  Output: left ++ right columns whatever the build side is
+    (HashJoin.scala:55-70); existence: left columns ++ `exists`."""
+
+    def __init__(self, leftKeys, rightKeys, joinType, buildSide, left: SparkPlan, right: SparkPlan, condition=None):
         self.leftKeys, self.rightKeys = list(leftKeys), list(rightKeys)
-        self.joinType = joinType
+        table = _STREAM_LEFT if buildSide == "right" else _STREAM_RIGHT
+        if buildSide not in ("left", "right") or joinType not in table:
+            raise capi.SparkB200Error(5, "join type %r with buildSide=%r is not supported" % (joinType, buildSide))
+        self.joinType, self.buildSide, self.condition = joinType, buildSide, condition
+        self.native_type = table[joinType]
         self.left, self.right = left, right
         self.children = (left, right)
 
     def executeColumnar(self, stream=None):
-        build = self.right.executeColumnar(stream)
+        build_plan, stream_plan = (self.right, self.left) if self.buildSide == "right" else (self.left, self.right)
+        build_keys, stream_keys = (self.rightKeys, self.leftKeys) if self.buildSide == "right" else (self.leftKeys, self.rightKeys)
+        build = build_plan.executeColumnar(stream)
         try:
-            rel = HashedRelation(build, self.rightKeys, stream)
+            rel = HashedRelation(build, build_keys, stream)
         finally:
             build.close()
         try:
-            probe = self.left.executeColumnar(stream)
+            probe = stream_plan.executeColumnar(stream)
             try:
-                return probe_join(rel, probe, self.leftKeys, self.joinType, stream)
+                out = probe_join(rel, probe, stream_keys, self.native_type, stream, self.condition, streamed_is_left=self.buildSide == "right")
             finally:
                 probe.close()
         finally:
             rel.close()
+        if self.buildSide == "left":      # streamed ++ build came back: restore left ++ right
+            nl = len(rel.names)
+            order = list(range(len(out.names) - nl, len(out.names))) + list(range(len(out.names) - nl))
+            arr = (C.c_int32 * len(order))(*order)
+            h = C.c_void_p()
+            try:
+                capi.check(capi.load().sb_table_select(out.handle, arr, len(order), C.byref(h)))
+                return ColumnarBatch(h, [out.names[i] for i in order], [out.arrow_types[i] for i in order])
+            finally:
+                out.close()
+        return out
 
 
-def probe_join(rel: HashedRelation, probe: ColumnarBatch, keys, joinType, stream=None) -> ColumnarBatch:
+def probe_join(rel: HashedRelation, probe: ColumnarBatch, keys, joinType, stream=None, condition=None, streamed_is_left=True) -> ColumnarBatch:
     lib = capi.load()
     idx = [probe.column_index(k) for k in keys]
     arr = (C.c_int32 * max(1, len(idx)))(*idx)
     h = C.c_void_p()
-    capi.check(lib.sb_join_probe(rel.handle, probe.handle, arr, len(idx), capi.SB_JOIN[joinType], _h(stream), C.byref(h)))
-    if joinType in ("left_semi", "left_anti"):
+    if condition is not None:
+        # the residual condition sees the joined row as the kernels lay it out: streamed columns ++ build columns
+        schema = Schema(probe.names + rel.names, [probe.column_desc(i).type for i in range(len(probe.names))] + rel.types)
+        ce = CompiledExpr(condition, schema)
+        capi.check(lib.sb_join_probe_condition(rel.handle, probe.handle, arr, len(idx), capi.SB_JOIN[joinType], C.byref(ce.c), _h(stream), C.byref(h)))
+    else:
+        capi.check(lib.sb_join_probe(rel.handle, probe.handle, arr, len(idx), capi.SB_JOIN[joinType], _h(stream), C.byref(h)))
+    if joinType in ("left_semi", "left_anti", "left_anti_null_aware"):
         return ColumnarBatch(h, probe.names, probe.arrow_types)
+    if joinType == "existence":
+        import pyarrow as pa
+        return ColumnarBatch(h, probe.names + ["exists"], probe.arrow_types + [pa.bool_()])
     return ColumnarBatch(h, probe.names + rel.names, probe.arrow_types + rel.arrow_types)
+
+
+class ShuffledHashJoinExec(BroadcastHashJoinExec):
+    """ShuffledHashJoinExec (SQLX/joins/ShuffledHashJoinExec.scala:38-130): the same build / probe over co-partitioned children;
+    unlike the broadcast join it may preserve the build side (full outer, and outer joins that hash the preserved side)."""
 
 
 class SortMergeJoinExec(BroadcastHashJoinExec):
     """The reference sorts both sides and merges (SortMergeJoinExec.scala:1213-1360); the GPU engine produces
     the same multiset with a hash build/probe and therefore does not report an outputOrdering."""
 
-    def __init__(self, leftKeys, rightKeys, joinType, left, right):
-        super().__init__(leftKeys, rightKeys, joinType, "right", left, right)
+    def __init__(self, leftKeys, rightKeys, joinType, left, right, condition=None):
+        super().__init__(leftKeys, rightKeys, joinType, "right", left, right, condition)
 
 
 class B200ColumnarRule:

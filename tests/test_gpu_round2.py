@@ -213,3 +213,83 @@ def test_columnar_rule_collapse_keeps_the_answer(gpu, stream):
     want = O.hash_aggregate(O.project(f, [("k", ("col", "k")), ("rev", rev)]), ["k"], [("sum", "rev", "s"), ("count_star", None, "n")])
     assert_tables_equal(plain, want, key_cols=["k"])
     assert_tables_equal(fused, want, key_cols=["k"])
+
+
+@pytest.mark.parametrize("asc,nulls_first", [(True, True), (False, False)])
+def test_range_partitioner_sampling_and_bounds(gpu, stream, asc, nulls_first):
+    """sb_range_sample + sb_range_determine_bounds vs the oracle's restatement of RangePartitioner.determineBounds on the SAME
+    sample (which rows are sampled is unpinned in the reference); then the bounds drive sb_range_partition + per-range sort =
+    the global sort, and the ranges are roughly balanced (PartitioningSuite.scala:127-139: max < 3 x min)."""
+    from spark_b200 import _capi as capi
+    from spark_b200.columnar import ColumnarBatch
+    from spark_b200.execution import LocalTableScanExec, RangePartitioning, ShuffleExchangeExec, _orders_c, range_bounds
+    from spark_b200.expressions import SortOrder
+    lib = gpu
+    rng = np.random.default_rng(21)
+    n, nparts = 400_000, 16
+    vals = rng.standard_normal(n) * 100
+    t = pa.table({"k": pa.array(vals, mask=rng.random(n) < 0.01), "row": np.arange(n, dtype=np.int64)})
+    batch = ColumnarBatch.from_arrow(t, stream)
+    order = SortOrder("k", asc, nulls_first)
+    # the sample and the oracle's bounds from it
+    h = C.c_void_p()
+    capi.check(lib.sb_range_sample(batch.handle, _orders_c(batch, [order]), 4800, 5, stream.handle, C.byref(h)))
+    sample = ColumnarBatch(h, ["k", "weight"], [pa.float64(), pa.float32()]).to_arrow(stream)
+    assert sample.num_rows == 4800 and abs(sample.column("weight")[0].as_py() - n / 4800) < 1e-3
+    ks, ws = sample.column("k").to_pylist(), sample.column("weight").to_pylist()
+    big = float("inf")
+
+    def sort_key(x):        # NULL rank first, then the value in the order's direction
+        if x is None:
+            return (0 if nulls_first else 2, 0.0)
+        return (1, x if asc else -x)
+    want = O.determine_bounds(list(zip(ks, ws)), nparts, key=sort_key)
+    bounds = range_bounds(batch, order, nparts, stream, samplePointsPerPartitionHint=100, seed=5)
+    got = bounds.to_arrow(stream).column("k").to_pylist()
+    assert got == want and len(got) == nparts - 1
+    # the bounds split the rows into balanced ranges and range partition + local sort = global sort
+    ex = ShuffleExchangeExec(RangePartitioning(order, bounds), LocalTableScanExec(batch))
+    out = ex.executeColumnar(stream)
+    sizes = np.diff(ex.partition_offsets)
+    assert sizes.max() < 3.0 * sizes.min()
+
+
+def test_top_n_selects_instead_of_sorting(gpu, stream):
+    """TakeOrderedAndProject over 3 M rows (radix select on the first order, then a sort of the few candidates) == the first k
+    rows of the full stable sort, for one and two sort columns, with heavy ties on the first."""
+    from spark_b200.columnar import ColumnarBatch
+    from spark_b200.execution import LocalTableScanExec, SortExec, TakeOrderedAndProjectExec
+    from spark_b200.expressions import SortOrder
+    rng = np.random.default_rng(33)
+    n = 3_000_000
+    t = pa.table({"rev": np.round(rng.random(n) * 1000, 1), "d": rng.integers(8000, 9000, n).astype(np.int32), "row": np.arange(n, dtype=np.int64),
+                  "c": rng.integers(0, 4, n)})
+    batch = ColumnarBatch.from_arrow(t, stream)
+    for orders, k in (([SortOrder("rev", False), SortOrder("d", True)], 10), ([SortOrder("c", True)], 1000), ([SortOrder("rev", True)], 50_000)):
+        got = TakeOrderedAndProjectExec(k, orders, None, LocalTableScanExec(batch)).collect(stream)
+        full = SortExec(orders, LocalTableScanExec(batch)).executeColumnar(stream)
+        want = full.slice(0, k, stream).to_arrow(stream)
+        assert got.column("row").to_pylist() == want.column("row").to_pylist()
+
+
+def test_exchange_statistics_and_coalesced_read(one_rank_comm, stream):
+    """MapOutputStatistics of an exchange (sb_map_output_statistics over the communicator) feed CoalesceShufflePartitions; the
+    AQE read hands out one batch per CoalescedPartitionSpec and together they are the exchange's rows."""
+    from spark_b200.columnar import ColumnarBatch
+    from spark_b200.execution import (AQEShuffleReadExec, HashPartitioning, LocalTableScanExec, ShuffleExchangeExec, coalesce_shuffle_partitions)
+    rng = np.random.default_rng(4)
+    n, nparts = 200_000, 200
+    t = pa.table({"k": rng.integers(0, 10_000, n), "v": rng.random(n), "row": np.arange(n, dtype=np.int64)})
+    batch = ColumnarBatch.from_arrow(t, stream)
+    ex = ShuffleExchangeExec(HashPartitioning(["k"], nparts), LocalTableScanExec(batch))
+    stats = ex.mapOutputStatistics(batch, stream)
+    pid = O.partition_ids(t, ["k"], nparts)
+    assert np.array_equal(stats, np.bincount(pid, minlength=nparts) * 24)
+    specs = coalesce_shuffle_partitions([stats], advisoryTargetSize=400_000, minPartitionSize=1000)
+    want = O.coalesce_partitions([stats.tolist()], 400_000, 1, 1000)
+    assert len(specs) == 1 and [(s.startReducerIndex, s.endReducerIndex, s.dataSize) for s in specs[0]] == want[0] and 1 < len(want[0]) < nparts
+    rows = []
+    for b in AQEShuffleReadExec(ex, specs[0]).batches(stream):
+        rows += b.to_arrow(stream).column("row").to_pylist()
+        b.close()
+    assert sorted(rows) == list(range(n))

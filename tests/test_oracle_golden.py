@@ -271,3 +271,29 @@ def test_q1_wscg_restatement_matches_operator_oracle():
         assert c_ == r[9]
         np.testing.assert_allclose([s[0], s[1], s[2], s[3]], r[2:6], rtol=1e-9)
         np.testing.assert_allclose([s[0] / c_, s[1] / c_, s[4] / c_], r[6:9], rtol=1e-9)
+
+
+def test_determine_bounds_reference_vector():
+    """PartitioningSuite.scala:119-125: determineBounds of the literal candidate list with 3 partitions is (0.4, 0.7); an empty
+    candidate set has no bounds."""
+    assert O.determine_bounds([], 10) == []
+    cands = [(0.7, 2.0), (0.1, 1.0), (0.4, 1.0), (0.3, 1.0), (0.2, 1.0), (0.5, 1.0), (1.0, 3.0)]
+    assert O.determine_bounds(cands, 3) == [0.4, 0.7]
+
+
+def test_outer_and_existence_join_reference_answers():
+    """The oracle's join (all types, residual condition) reproduces the literal answers of OuterJoinSuite.scala:191-258 and
+    ExistenceJoinSuite.scala:356-461 on their literal inputs (tests/join_fixtures.py)."""
+    import join_fixtures as F
+    for how, want in F.OUTER_CASES.items():
+        if how == "right_outer":     # the right side is preserved: hash the right side (build_outer)
+            got = O.hash_join(F.OUTER_LEFT, F.OUTER_RIGHT, ["a"], ["c"], "build_outer", F.COND_B_LT_D)
+        else:
+            got = O.hash_join(F.OUTER_LEFT, F.OUTER_RIGHT, ["a"], ["c"], how, F.COND_B_LT_D)
+        assert F.multiset(F.rows_of(got)) == F.multiset(want), how
+    for how, cond, want in F.EXIST_CASES:
+        got = O.hash_join(F.EXIST_LEFT, F.EXIST_RIGHT, ["a"], ["c"], how, cond)
+        assert F.multiset(F.rows_of(got)) == F.multiset(want), (how, cond)
+    # existence join: one boolean per streamed row = membership in the semi join's answer
+    ex = O.hash_join(F.EXIST_LEFT, F.EXIST_RIGHT, ["a"], ["c"], "existence", F.COND_B_LT_D)
+    assert ex.column("exists").to_pylist() == [False, False, True, True, False, False, False, False]

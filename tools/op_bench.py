@@ -110,8 +110,34 @@ def main():
         b = ColumnarBatch.from_numpy({"k": rng.integers(-2 ** 63, 2 ** 63 - 1, n)}, stream)
         stream.synchronize()
         srt = SortExec([("k", True, True)], LocalTableScanExec(b))
-        ms, k = timed(lib, stream, lambda: srt.executeColumnar(stream).close(), ["partition_rank", "partition_scatter"])
-        emit("sort int64 keys", n, 2 * 8 * n, ms, k, {"note": "8 LSD passes of (8 B key + 4 B row id); algorithmic = one read + one write of the key column"})
+        ms, k = timed(lib, stream, lambda: srt.executeColumnar(stream).close(), ["sort_histogram", "sort_passes", "gather"])
+        emit("sort int64 keys (full range)", n, 2 * 8 * n, ms, k, {"note": "8 onesweep passes of (8 B key + 4 B row id) + key histogram + payload gather; algorithmic = one read + one write of the key column",
+                                                       "pass_traffic_gbs": 8 * 24 * n / (k["sort_passes"][0] / 1e3) / 1e9 if k["sort_passes"][0] else None})
+        b.close()
+        b = ColumnarBatch.from_numpy({"k": rng.integers(0, 1 << 40, n)}, stream)
+        stream.synchronize()
+        srt = SortExec([("k", True, True)], LocalTableScanExec(b))
+        ms, k = timed(lib, stream, lambda: srt.executeColumnar(stream).close(), ["sort_histogram", "sort_passes", "gather"])
+        emit("sort int64 keys (40 significant bits: 3 constant bytes skipped)", n, 2 * 8 * n, ms, k)
+        from spark_b200.execution import TakeOrderedAndProjectExec
+        from spark_b200.expressions import SortOrder
+        top = TakeOrderedAndProjectExec(10, [SortOrder("k", False)], None, LocalTableScanExec(b))
+        ms, k = timed(lib, stream, lambda: top.executeColumnar(stream).close(), ["sort_passes"])
+        emit("take_ordered(10) of int64 keys", n, 8 * n, ms, k, {"note": "radix select on the first sort column, then a sort of the candidates"})
+        b.close()
+
+    if only in ("", "scan"):
+        # ---- scan: RLE_DICTIONARY pages (6-bit and 12-bit domains) and PLAIN doubles, decoded on the device ----------------------------
+        from spark_b200 import tpch
+        from spark_b200.scan import decode_chunks, encode_column
+        cols = tpch.Q1_COLUMNS
+        b = tpch.synth_batch("lineitem", cols, 6_000_000, 42, stream=stream)      # 24 M rows
+        n = b.num_rows
+        chunks = [encode_column(b, c, dictionary=c != "l_extendedprice", page_rows=1 << 19, stream=stream, pinned=True) for c in cols]
+        enc = sum(ch.nbytes for ch in chunks)
+        ms, k = timed(lib, stream, lambda: decode_chunks(cols, chunks, stream, b.arrow_types).close(), ["scan_decode"])
+        emit("scan_decode Q1 columns (H2D of the encoded bytes included in ms)", n, enc + 38 * n, ms, k,
+             {"encoded_bytes": enc, "decode_kernel_gbs": (enc + 38 * n) / (k["scan_decode"][0] / 1e3) / 1e9 if k["scan_decode"][0] else None})
         b.close()
 
     if only in ("", "join"):
