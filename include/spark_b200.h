@@ -401,6 +401,8 @@ int sb_all_to_all(const sb_table *in, const int64_t *part_offsets_host, int32_t 
  * sb_coalesce_partitions    ShufflePartitionsUtil.coalescePartitions without skew specs (SQLX/adaptive/ShufflePartitionsUtil.scala:
  *                           45-126, 263-369), host only: CoalescedPartitionSpec(start, end) ranges + their data size per shuffle
  *                           (out_data_size[shuffle * nspecs + spec]); *out_nspecs == 0 means "leave the layout as it is". */
+/* rows of every (rank, partition): out_counts[rank * num_partitions + p]; collective (one all-gather); no communicator: this rank's */
+int sb_exchange_counts(const int64_t *part_offsets_host, int32_t num_partitions, sb_stream *s, int64_t *out_counts);
 int sb_map_output_statistics(const sb_table *partitioned, const int64_t *part_offsets_host, int32_t num_partitions, sb_stream *s,
                              int64_t *out_bytes_by_partition);
 int sb_coalesce_partitions(const int64_t *const *bytes_by_partition, int32_t nshuffles, int32_t num_partitions,

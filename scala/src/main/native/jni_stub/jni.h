@@ -22,4 +22,6 @@ struct JNINativeInterface_ {
   jbyteArray (*NewByteArray)(JNIEnv *, jsize);
   void (*SetByteArrayRegion)(JNIEnv *, jbyteArray, jsize, jsize, const jbyte *);
   void (*GetByteArrayRegion)(JNIEnv *, jbyteArray, jsize, jsize, jbyte *);
+  jlongArray (*NewLongArray)(JNIEnv *, jsize);
+  void (*SetLongArrayRegion)(JNIEnv *, jlongArray, jsize, jsize, const jlong *);
 };

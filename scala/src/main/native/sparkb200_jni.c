@@ -145,10 +145,11 @@ NATIVE(jlong, tableNumRows)(JNIEnv *env, jclass c, jlong table) {
 }
 
 /* D2H of one result column into buffers the JVM owns (OffHeapColumnVector / ArrowBuf addresses) */
-NATIVE(void, tableExportHost)(JNIEnv *env, jclass c, jlong table, jint column, jlong data, jlong validity, jlong offsets, jlong stream) {
+NATIVE(jlong, tableExportHost)(JNIEnv *env, jclass c, jlong table, jint column, jlong data, jlong validity, jlong offsets, jlong stream) {
   int64_t nulls = 0;
   throw_if(env, sb_table_export_host(TBL(table), column, (void *)(intptr_t)data, (uint8_t *)(intptr_t)validity,
                                      (int32_t *)(intptr_t)offsets, &nulls, STR(stream)));
+  return (jlong)nulls;
 }
 
 NATIVE(jlong, exprCreate)(JNIEnv *env, jclass c, jintArray ops, jintArray vtypes, jintArray args, jlongArray literals, jint outType) {
@@ -254,3 +255,146 @@ NATIVE(jlong, allGather)(JNIEnv *env, jclass c, jlong table, jlong stream) {
   return (jlong)(intptr_t)out;
 }
 
+
+/* ---- round 2 additions ---------------------------------------------------------------------------------------------------------- */
+NATIVE(void, streamSynchronize)(JNIEnv *env, jclass c, jlong stream) { throw_if(env, sb_stream_synchronize(STR(stream))); }
+
+NATIVE(jlong, hostAlloc)(JNIEnv *env, jclass c, jlong bytes) {
+  void *p = NULL;
+  throw_if(env, sb_host_alloc(bytes, &p));
+  return (jlong)(intptr_t)p;
+}
+NATIVE(void, hostFree)(JNIEnv *env, jclass c, jlong address) { throw_if(env, sb_host_free((void *)(intptr_t)address)); }
+
+NATIVE(jint, tableNumColumns)(JNIEnv *env, jclass c, jlong table) {
+  int32_t n = 0;
+  throw_if(env, sb_table_num_columns(TBL(table), &n));
+  return n;
+}
+NATIVE(jlong, columnNullCount)(JNIEnv *env, jclass c, jlong table, jint column) {
+  sb_column d;
+  throw_if(env, sb_table_column(TBL(table), column, &d));
+  return (jlong)(d.validity ? d.null_count : 0);
+}
+NATIVE(void, tableRetain)(JNIEnv *env, jclass c, jlong table) { throw_if(env, sb_table_retain(TBL(table))); }
+
+NATIVE(jlong, tableSelect)(JNIEnv *env, jclass c, jlong table, jintArray columns) {
+  jsize n = (*env)->GetArrayLength(env, columns);
+  jint *k = (*env)->GetIntArrayElements(env, columns, NULL);
+  sb_table *out = NULL;
+  int rc = sb_table_select(TBL(table), (const int32_t *)k, n, &out);
+  (*env)->ReleaseIntArrayElements(env, columns, k, JNI_ABORT);
+  throw_if(env, rc);
+  return (jlong)(intptr_t)out;
+}
+NATIVE(jlong, tableSlice)(JNIEnv *env, jclass c, jlong table, jlong begin, jlong end, jlong stream) {
+  sb_table *out = NULL;
+  throw_if(env, sb_table_slice(TBL(table), begin, end, STR(stream), &out));
+  return (jlong)(intptr_t)out;
+}
+NATIVE(jlong, tableConcat)(JNIEnv *env, jclass c, jlongArray tables, jlong stream) {
+  jsize n = (*env)->GetArrayLength(env, tables);
+  jlong *t = (*env)->GetLongArrayElements(env, tables, NULL);
+  const sb_table **ptrs = (const sb_table **)calloc((size_t)(n ? n : 1), sizeof(*ptrs));
+  for (jsize i = 0; i < n; i++) ptrs[i] = TBL(t[i]);
+  sb_table *out = NULL;
+  int rc = sb_table_concat(ptrs, n, STR(stream), &out);
+  free(ptrs);
+  (*env)->ReleaseLongArrayElements(env, tables, t, JNI_ABORT);
+  throw_if(env, rc);
+  return (jlong)(intptr_t)out;
+}
+
+NATIVE(jlong, rangePartition)(JNIEnv *env, jclass c, jlong table, jint col, jboolean asc, jboolean nullsFirst, jlong bounds, jlong stream,
+                              jlongArray offsetsOut) {
+  sb_sort_order o = {col, asc ? 1 : 0, nullsFirst ? 1 : 0, 0};
+  jlong *offs = (*env)->GetLongArrayElements(env, offsetsOut, NULL);
+  sb_table *out = NULL;
+  int rc = sb_range_partition(TBL(table), &o, TBL(bounds), STR(stream), &out, (int64_t *)offs);
+  (*env)->ReleaseLongArrayElements(env, offsetsOut, offs, 0);
+  throw_if(env, rc);
+  return (jlong)(intptr_t)out;
+}
+NATIVE(jlong, rangeSample)(JNIEnv *env, jclass c, jlong table, jint col, jboolean asc, jboolean nullsFirst, jlong sampleSize, jlong seed,
+                           jlong stream) {
+  sb_sort_order o = {col, asc ? 1 : 0, nullsFirst ? 1 : 0, 0};
+  sb_table *out = NULL;
+  throw_if(env, sb_range_sample(TBL(table), &o, sampleSize, (uint64_t)seed, STR(stream), &out));
+  return (jlong)(intptr_t)out;
+}
+NATIVE(jlong, rangeDetermineBounds)(JNIEnv *env, jclass c, jlong sample, jboolean asc, jboolean nullsFirst, jint numPartitions, jlong stream) {
+  sb_sort_order o = {0, asc ? 1 : 0, nullsFirst ? 1 : 0, 0};
+  sb_table *out = NULL;
+  throw_if(env, sb_range_determine_bounds(TBL(sample), &o, numPartitions, STR(stream), &out));
+  return (jlong)(intptr_t)out;
+}
+
+NATIVE(jlongArray, mapOutputStatistics)(JNIEnv *env, jclass c, jlong table, jlongArray partOffsets, jint n, jlong stream) {
+  jlong *in = (*env)->GetLongArrayElements(env, partOffsets, NULL);
+  int64_t *bytes = (int64_t *)calloc((size_t)(n > 0 ? n : 1), sizeof(int64_t));
+  int rc = sb_map_output_statistics(TBL(table), (const int64_t *)in, n, STR(stream), bytes);
+  (*env)->ReleaseLongArrayElements(env, partOffsets, in, JNI_ABORT);
+  jlongArray out = (*env)->NewLongArray(env, n);
+  if (rc == SB_OK) (*env)->SetLongArrayRegion(env, out, 0, n, (const jlong *)bytes);
+  free(bytes);
+  throw_if(env, rc);
+  return out;
+}
+
+/* aggregation state: the plan is deep-copied by sb_hash_agg_create, so the temporaries die here */
+NATIVE(jlong, aggCreate)(JNIEnv *env, jclass c, jint mode, jintArray keyCols, jintArray funcs, jlongArray inputExprs, jlong filterExpr,
+                         jlong expectedGroups) {
+  jsize nk = (*env)->GetArrayLength(env, keyCols), na = (*env)->GetArrayLength(env, funcs);
+  jint *k = (*env)->GetIntArrayElements(env, keyCols, NULL), *f = (*env)->GetIntArrayElements(env, funcs, NULL);
+  jlong *in = (*env)->GetLongArrayElements(env, inputExprs, NULL);
+  sb_agg_spec *specs = (sb_agg_spec *)calloc((size_t)(na ? na : 1), sizeof(sb_agg_spec));
+  for (jsize i = 0; i < na; i++) {
+    specs[i].func = f[i];
+    if (in[i]) specs[i].input = *(const sb_expr *)(intptr_t)in[i];
+  }
+  sb_agg_plan plan = {mode, nk, (const int32_t *)k, na, 0, specs, (const sb_expr *)(intptr_t)filterExpr, expectedGroups};
+  sb_agg_state *st = NULL;
+  int rc = sb_hash_agg_create(&plan, &st);
+  free(specs);
+  (*env)->ReleaseIntArrayElements(env, keyCols, k, JNI_ABORT);
+  (*env)->ReleaseIntArrayElements(env, funcs, f, JNI_ABORT);
+  (*env)->ReleaseLongArrayElements(env, inputExprs, in, JNI_ABORT);
+  throw_if(env, rc);
+  return (jlong)(intptr_t)st;
+}
+NATIVE(void, aggUpdate)(JNIEnv *env, jclass c, jlong state, jlong table, jlong stream) {
+  throw_if(env, sb_hash_agg_update((sb_agg_state *)(intptr_t)state, TBL(table), STR(stream)));
+}
+NATIVE(void, aggMerge)(JNIEnv *env, jclass c, jlong state, jlong table, jlong stream) {
+  throw_if(env, sb_hash_agg_merge((sb_agg_state *)(intptr_t)state, TBL(table), STR(stream)));
+}
+NATIVE(jlong, aggFinish)(JNIEnv *env, jclass c, jlong state, jlong stream) {
+  sb_table *out = NULL;
+  throw_if(env, sb_hash_agg_finish((sb_agg_state *)(intptr_t)state, STR(stream), &out));
+  return (jlong)(intptr_t)out;
+}
+NATIVE(void, aggDestroy)(JNIEnv *env, jclass c, jlong state) { throw_if(env, sb_hash_agg_destroy((sb_agg_state *)(intptr_t)state)); }
+
+NATIVE(jlong, joinProbeCondition)(JNIEnv *env, jclass c, jlong rel, jlong probe, jintArray keyCols, jint joinType, jlong cond, jlong stream) {
+  jsize nk = (*env)->GetArrayLength(env, keyCols);
+  jint *k = (*env)->GetIntArrayElements(env, keyCols, NULL);
+  sb_table *out = NULL;
+  int rc = sb_join_probe_condition((const sb_hash_table *)(intptr_t)rel, TBL(probe), (const int32_t *)k, nk, joinType,
+                                   (const sb_expr *)(intptr_t)cond, STR(stream), &out);
+  (*env)->ReleaseIntArrayElements(env, keyCols, k, JNI_ABORT);
+  throw_if(env, rc);
+  return (jlong)(intptr_t)out;
+}
+
+NATIVE(jlongArray, exchangeCounts)(JNIEnv *env, jclass c, jlongArray partOffsets, jint n, jint nranks, jlong stream) {
+  jlong *in = (*env)->GetLongArrayElements(env, partOffsets, NULL);
+  const jsize total = (jsize)n * (nranks > 0 ? nranks : 1);
+  int64_t *counts = (int64_t *)calloc((size_t)(total > 0 ? total : 1), sizeof(int64_t));
+  int rc = sb_exchange_counts((const int64_t *)in, n, STR(stream), counts);
+  (*env)->ReleaseLongArrayElements(env, partOffsets, in, JNI_ABORT);
+  jlongArray out = (*env)->NewLongArray(env, total);
+  if (rc == SB_OK) (*env)->SetLongArrayRegion(env, out, 0, total, (const jlong *)counts);
+  free(counts);
+  throw_if(env, rc);
+  return out;
+}

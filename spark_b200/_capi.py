@@ -131,6 +131,7 @@ _SIGNATURES = {
     "sb_exchange_plan": [C.POINTER(_i64), _i32, _i32, C.POINTER(_i64)],
     "sb_all_to_all": [_p, C.POINTER(_i64), _i32, _p, _pp, C.POINTER(_i64)],
     "sb_all_gather": [_p, _p, _pp],
+    "sb_exchange_counts": [C.POINTER(_i64), _i32, _p, C.POINTER(_i64)],
     "sb_map_output_statistics": [_p, C.POINTER(_i64), _i32, _p, C.POINTER(_i64)],
     "sb_coalesce_partitions": [C.POINTER(C.POINTER(_i64)), _i32, _i32, _i64, _i32, _i64, _i32, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i64),
                                C.POINTER(_i32)],

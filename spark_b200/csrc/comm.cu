@@ -580,6 +580,28 @@ int sb_map_output_statistics(const sb_table *partitioned, const int64_t *part_of
   SB_API_END
 }
 
+// Rows every rank holds for every partition (the all-gather sb_all_to_all starts with): out_counts[rank * num_partitions + p].
+// The reduce side needs it to cut one reducer partition out of a received table, whose rows are grouped by SOURCE rank.
+int sb_exchange_counts(const int64_t *part_offsets_host, int32_t num_partitions, sb_stream *s, int64_t *out_counts) {
+  SB_API_BEGIN
+  require_init();
+  SB_REQUIRE(part_offsets_host && out_counts && num_partitions >= 1, "bad argument");
+  Comm &c = comm();
+  cudaStream_t st = stream_of(s);
+  std::vector<int64_t> mine(num_partitions);
+  for (int p = 0; p < num_partitions; p++) mine[p] = part_offsets_host[p + 1] - part_offsets_host[p];
+  if (!c.comm) {
+    memcpy(out_counts, mine.data(), (size_t)num_partitions * 8);
+    return SB_OK;
+  }
+  Scratch d_my((int64_t)num_partitions * 8, st), d_all((int64_t)c.nranks * num_partitions * 8, st);
+  SB_CUDA(cudaMemcpyAsync(d_my.ptr, mine.data(), (size_t)num_partitions * 8, cudaMemcpyHostToDevice, st));
+  SB_NCCL(nccl().AllGather(d_my.ptr, d_all.ptr, (size_t)num_partitions, ncclInt64, c.comm, st));
+  SB_CUDA(cudaMemcpyAsync(out_counts, d_all.ptr, (size_t)c.nranks * num_partitions * 8, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaStreamSynchronize(st));
+  SB_API_END
+}
+
 int sb_all_gather(const sb_table *in, sb_stream *s, sb_table **out) {
   SB_API_BEGIN
   require_init();
