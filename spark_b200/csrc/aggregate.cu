@@ -659,6 +659,8 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
         int32_t src_type;
         HostSlot s = final_mode ? buffer_source(next_buf_col) : b.source_for(sp.input, &src_type);
         if (final_mode) { src_type = in->cols[next_buf_col].type; next_buf_col++; }
+        // Sum(decimal(p, s)) is decimal(p + 10, s) with an isEmpty flag and overflow -> NULL (Sum.scala:80-135): not an int64 sum
+        if (src_type == SB_DECIMAL64) fail(SB_ERR_UNSUPPORTED, "SUM over a DECIMAL column is not implemented on the GPU path (needs decimal(p + 10, s) accumulation)");
         bool f64 = is_float_type(src_type) || s.nf > 1 || s.f[0].mode != F_COL;
         s.kind = f64 ? K_ADD_F64 : K_ADD_I64;
         // a global aggregate (no keys) over zero rows yields NULL, so it always tracks "seen"
@@ -687,6 +689,8 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
         } else {
           int32_t src_type;
           HostSlot s = b.source_for(sp.input, &src_type);
+          // Average(decimal(p, s)) is decimal(p + 4, s + 4) (Average.scala:80-135): dividing the unscaled sum would be off by 10^s
+          if (src_type == SB_DECIMAL64) fail(SB_ERR_UNSUPPORTED, "AVG over a DECIMAL column is not implemented on the GPU path");
           s.kind = K_ADD_F64;
           sum_slot = b.add_slot(s);
           HostSlot c = s;

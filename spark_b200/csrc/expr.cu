@@ -51,6 +51,18 @@ bool expr_is_column(const sb_expr &e, int *col) {
 void expr_validate(const sb_table *in, const sb_expr &e) {
   SB_REQUIRE(e.nodes && e.n >= 1 && e.n <= EXPR_MAX_NODES, "expression must have 1..%d nodes (got %d)", EXPR_MAX_NODES, e.n);
   int depth = 0;
+  // Decimal columns carry unscaled integers: arithmetic and comparisons on them would need the rescaling / precision rules of
+  // DecimalPrecision (sql/catalyst/.../analysis/DecimalPrecision.scala) and are rejected rather than evaluated on the unscaled
+  // values (they used to be silently wrong).  Bare references and IS [NOT] NULL are fine.
+  bool has_decimal = false, only_null_tests = true;
+  for (int i = 0; i < e.n; i++) {
+    const sb_expr_node &nd = e.nodes[i];
+    if (nd.op == SB_OP_COL && nd.arg >= 0 && nd.arg < (int)in->cols.size() && in->cols[nd.arg].type == SB_DECIMAL64) has_decimal = true;
+    if (nd.op != SB_OP_COL && nd.op != SB_OP_ISNULL && nd.op != SB_OP_ISNOTNULL && nd.op != SB_OP_AND && nd.op != SB_OP_OR && nd.op != SB_OP_NOT)
+      only_null_tests = false;
+  }
+  if (has_decimal && e.n > 1 && !only_null_tests)
+    fail(SB_ERR_UNSUPPORTED, "arithmetic / comparison on DECIMAL columns is not implemented on the GPU path (unscaled values would ignore the scale)");
   for (int i = 0; i < e.n; i++) {
     const sb_expr_node &nd = e.nodes[i];
     switch (nd.op) {

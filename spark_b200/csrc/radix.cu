@@ -17,11 +17,6 @@
 
 namespace sb {
 
-constexpr int RS_THREADS = 256;
-constexpr int RS_ITEMS = 16;
-constexpr int RS_TILE = RS_THREADS * RS_ITEMS;   // 4096 pairs
-constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr size_t RS_SMEM = (size_t)RS_TILE * 12 + 256 * 8 + (size_t)RS_WARPS * 256 * 4 + 256 * 4;
 constexpr uint64_t RS_FLAG_AGG = 1ull << 62, RS_FLAG_INCL = 2ull << 62, RS_VALUE_MASK = (1ull << 62) - 1;
 
 // all eight digit histograms in one read of the keys; also used to skip constant bytes
@@ -66,10 +61,14 @@ __device__ __forceinline__ void st_status(uint64_t *p, uint64_t v) {
 }
 
 // One LSD pass over byte `byte`.  status: [tiles][256] zero-initialised; ticket: zero-initialised tile counter.
+// RS_THREADS x RS_ITEMS pairs per tile (a warp owns 32 x RS_ITEMS consecutive rows); digit d is owned by thread d (RS_THREADS >= 256).
+template <int RS_THREADS, int RS_ITEMS>
 __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const uint64_t *__restrict__ in_keys, const uint32_t *__restrict__ in_vals,
                                                                  uint64_t *__restrict__ out_keys, uint32_t *__restrict__ out_vals, int64_t n, int byte,
                                                                  const unsigned long long *__restrict__ gbase /* [256] of this byte */,
                                                                  uint64_t *__restrict__ status, uint32_t *__restrict__ ticket) {
+  constexpr int RS_TILE = RS_THREADS * RS_ITEMS, RS_WARPS = RS_THREADS / 32;
+  static_assert(RS_THREADS >= 256 && RS_THREADS % 32 == 0, "one thread per digit");
   extern __shared__ __align__(16) uint8_t rs_smem[];
   uint64_t *s_keys = (uint64_t *)rs_smem;                                   // [RS_TILE]
   int64_t *s_dst_off = (int64_t *)(s_keys + RS_TILE);                       // [256] global position of sorted tile position p with digit d: s_dst_off[d] + p
@@ -120,39 +119,49 @@ __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const uint64_t 
   }
   __syncthreads();
   // ---- per digit (thread t owns digit t): exclusive prefix over the warps, tile count, look-back -------------------------------------
+  const bool digit_owner = tid < 256;
   uint32_t count = 0;
+  uint64_t *my_status = status + tile * 256 + (digit_owner ? tid : 0);
+  if (digit_owner) {
 #pragma unroll
-  for (int w = 0; w < RS_WARPS; w++) {
-    const uint32_t c = s_whist[w][tid];
-    s_whist[w][tid] = count;
-    count += c;
+    for (int w = 0; w < RS_WARPS; w++) {
+      const uint32_t c = s_whist[w][tid];
+      s_whist[w][tid] = count;
+      count += c;
+    }
+    st_status(my_status, RS_FLAG_AGG | count);
+    s_bin_start[tid] = count;
   }
-  uint64_t *my_status = status + tile * 256 + tid;
-  st_status(my_status, RS_FLAG_AGG | count);
-  // tile-local exclusive scan of the digit counts (block scan over 256 values)
-  s_bin_start[tid] = count;
+  // tile-local exclusive scan of the 256 digit counts: warp scans + a scan of the eight warp totals
+  __shared__ uint32_t s_wsum[8];
+  uint32_t incl = count;
+  if (digit_owner) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += o;
+    }
+    if (lane == 31) s_wsum[warp] = incl;
+  }
   __syncthreads();
-  for (int d = 1; d < 256; d <<= 1) {
-    const uint32_t v = tid >= d ? s_bin_start[tid - d] : 0;
-    __syncthreads();
-    s_bin_start[tid] += v;
-    __syncthreads();
+  uint32_t bin_start = 0;
+  if (digit_owner) {
+    for (int w = 0; w < warp; w++) bin_start += s_wsum[w];
+    bin_start += incl - count;
+    s_bin_start[tid] = bin_start;
+    // decoupled look-back: sum the aggregates of earlier tiles until one carries an inclusive prefix
+    uint64_t excl = 0;
+    for (int64_t t = tile - 1; t >= 0;) {
+      const uint64_t s = ld_status(status + t * 256 + tid);
+      const uint64_t flag = s & ~RS_VALUE_MASK;
+      if (flag == 0) continue;   // not published yet: the tile holding ticket t is running (tickets are handed out in order)
+      excl += s & RS_VALUE_MASK;
+      if (flag == RS_FLAG_INCL) break;
+      t--;
+    }
+    st_status(my_status, RS_FLAG_INCL | (excl + count));
+    s_dst_off[tid] = (int64_t)gbase[tid] + (int64_t)excl - (int64_t)bin_start;
   }
-  const uint32_t bin_start = s_bin_start[tid] - count;
-  __syncthreads();
-  s_bin_start[tid] = bin_start;
-  // decoupled look-back: sum the aggregates of earlier tiles until one carries an inclusive prefix
-  uint64_t excl = 0;
-  for (int64_t t = tile - 1; t >= 0;) {
-    const uint64_t s = ld_status(status + t * 256 + tid);
-    const uint64_t flag = s & ~RS_VALUE_MASK;
-    if (flag == 0) continue;   // not published yet: the tile holding ticket t is running (tickets are handed out in order)
-    excl += s & RS_VALUE_MASK;
-    if (flag == RS_FLAG_INCL) break;
-    t--;
-  }
-  st_status(my_status, RS_FLAG_INCL | (excl + count));
-  s_dst_off[tid] = (int64_t)gbase[tid] + (int64_t)excl - (int64_t)bin_start;
   __syncthreads();
   // ---- stage the tile in digit order ------------------------------------------------------------------------------------------------
 #pragma unroll
@@ -223,9 +232,20 @@ int radix_sort_pairs(uint64_t *keys, uint32_t *vals, int64_t n, cudaStream_t st)
     if (varies) bytes[passes++] = b;
   }
   if (passes == 0) return 0;
-  const int64_t tiles = (n + RS_TILE - 1) / RS_TILE;
-  Scratch keys2(n * 8 + 16, st), vals2(n * 4 + 16, st), status((int64_t)passes * tiles * 256 * 8 + 16, st), tickets(8 * 4, st);
-  SB_CUDA(cudaMemsetAsync(status.ptr, 0, (size_t)passes * tiles * 256 * 8, st));
+  // tile geometry (sb_config_set("sort_variant", v) for experiments): threads x items
+  struct Variant { const void *fn; int threads, items; };
+  static const Variant variants[] = {
+      {(const void *)rs_onesweep_kernel<256, 16>, 256, 16}, {(const void *)rs_onesweep_kernel<512, 8>, 512, 8},
+      {(const void *)rs_onesweep_kernel<256, 8>, 256, 8},   {(const void *)rs_onesweep_kernel<512, 16>, 512, 16},
+      {(const void *)rs_onesweep_kernel<384, 12>, 384, 12}, {(const void *)rs_onesweep_kernel<1024, 8>, 1024, 8}};
+  int vi = config().sort_variant;
+  if (vi < 0 || vi >= (int)(sizeof(variants) / sizeof(variants[0]))) vi = 0;
+  const Variant &V = variants[vi];
+  const int tile_rows = V.threads * V.items;
+  const size_t smem = (size_t)tile_rows * 12 + 256 * 8 + (size_t)(V.threads / 32) * 256 * 4 + 256 * 4;
+  SB_CUDA(cudaFuncSetAttribute(V.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t tiles = (n + tile_rows - 1) / tile_rows;
+  Scratch keys2(n * 8 + 16, st), vals2(n * 4 + 16, st), status(tiles * 256 * 8 + 16, st), tickets(8 * 4, st);
   SB_CUDA(cudaMemsetAsync(tickets.ptr, 0, 32, st));
   uint64_t *ik = keys, *ok = keys2.as<uint64_t>();
   uint32_t *iv = vals, *ov = vals2.as<uint32_t>();
@@ -233,13 +253,16 @@ int radix_sort_pairs(uint64_t *keys, uint32_t *vals, int64_t n, cudaStream_t st)
     SB_CUDA(cudaMemcpyAsync(vals2.ptr, vals, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
     std::swap(iv, ov);
   }
-  static std::once_flag once;
-  std::call_once(once, [] { SB_CUDA(cudaFuncSetAttribute(rs_onesweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM)); });
   KernelTimer kt("sort_passes", st);
   for (int p = 0; p < passes; p++) {
-    rs_onesweep_kernel<<<(unsigned)tiles, RS_THREADS, RS_SMEM, st>>>(ik, iv, ok, ov, n, bytes[p], counts.as<unsigned long long>() + bytes[p] * 256,
-                                                              status.as<uint64_t>() + (int64_t)p * tiles * 256, tickets.as<uint32_t>() + p);
-    SB_LAUNCH_CHECK();
+    SB_CUDA(cudaMemsetAsync(status.ptr, 0, (size_t)tiles * 256 * 8, st));   // one status array, re-armed per pass (passes are stream-ordered)
+    const unsigned long long *gb = counts.as<unsigned long long>() + bytes[p] * 256;
+    uint64_t *stp = status.as<uint64_t>();
+    uint32_t *tk = tickets.as<uint32_t>() + p;
+    int byte = bytes[p];
+    void *args[] = {&ik, &iv, &ok, &ov, (void *)&n, &byte, &gb, &stp, &tk};
+    SB_CUDA(cudaLaunchKernel(V.fn, dim3((unsigned)tiles), dim3((unsigned)V.threads), args, smem, st));
+    count_launch();
     std::swap(ik, ok);
     std::swap(iv, ov);
   }

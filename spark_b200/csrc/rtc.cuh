@@ -33,6 +33,7 @@ struct Config {
   int expr_interpret_only = 0;
   int regroup_ldst = 0;             // load/store multisplit instead of the copy-engine one
   int exchange_nccl = 0;            // NCCL send/recv data path instead of peer windows
+  int sort_variant = 0;             // onesweep tile geometry (experiments)
 };
 Config &config();
 
