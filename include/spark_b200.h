@@ -361,6 +361,22 @@ int sb_range_determine_bounds(const sb_table *sample, const sb_sort_order *order
 #define SB_JOIN_LEFT_ANTI_NULL_AWARE 7    /* NOT IN: BroadcastHashJoinExec.scala:137-162 (single key) */
 
 int sb_join_build(const sb_table *build, const int32_t *key_cols, int32_t nkeys, sb_stream *s, sb_hash_table **out);
+/* the FilterExec below the build side fused into the build: rows for which `filter` is not TRUE stay out of the relation and
+ * the filtered table is never materialised (payload is gathered from `build` by row id at probe time) */
+int sb_join_build_filtered(const sb_table *build, const int32_t *key_cols, int32_t nkeys, const sb_expr *filter, sb_stream *s,
+                           sb_hash_table **out);
+/* what whole-stage codegen fuses around a join on the CPU path (the FilterExec below the streamed side, the ProjectExec above
+ * the join), as options of the probe: nothing between scan and join output is materialised */
+typedef struct sb_join_options {
+  const sb_expr *probe_filter;     /* over the streamed table: rows for which it is not TRUE are not part of the input; or NULL */
+  const sb_expr *condition;        /* residual condition over streamed ++ build columns (HashJoin.boundCondition); or NULL */
+  const int32_t *probe_out_cols;   /* streamed columns that reach the output (NULL: all) */
+  int32_t n_probe_out;
+  int32_t n_build_out;
+  const int32_t *build_out_cols;   /* build columns that reach the output (NULL: all) */
+} sb_join_options;
+int sb_join_probe_ex(const sb_hash_table *ht, const sb_table *probe, const int32_t *key_cols, int32_t nkeys, int32_t join_type,
+                     const sb_join_options *options, sb_stream *s, sb_table **out);
 int sb_join_probe(const sb_hash_table *ht, const sb_table *probe, const int32_t *key_cols, int32_t nkeys,
                   int32_t join_type, sb_stream *s, sb_table **out);
 /* the same with a residual condition over the joined row (streamed columns ++ build columns): HashJoin.scala:144-172

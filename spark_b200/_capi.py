@@ -70,6 +70,11 @@ class sb_agg_plan(C.Structure):
                 ("expected_groups", C.c_int64)]
 
 
+class sb_join_options(C.Structure):
+    _fields_ = [("probe_filter", C.POINTER(sb_expr)), ("condition", C.POINTER(sb_expr)), ("probe_out_cols", C.POINTER(C.c_int32)),
+                ("n_probe_out", C.c_int32), ("n_build_out", C.c_int32), ("build_out_cols", C.POINTER(C.c_int32))]
+
+
 class sb_sort_order(C.Structure):
     _fields_ = [("col", C.c_int32), ("ascending", C.c_int32), ("nulls_first", C.c_int32), ("pad", C.c_int32)]
 
@@ -124,6 +129,8 @@ _SIGNATURES = {
     "sb_top_n": [_p, C.POINTER(sb_sort_order), _i32, _i64, _p, _pp],
     "sb_join_build": [_p, C.POINTER(_i32), _i32, _p, _pp],
     "sb_join_probe": [_p, _p, C.POINTER(_i32), _i32, _i32, _p, _pp],
+    "sb_join_build_filtered": [_p, C.POINTER(_i32), _i32, C.POINTER(sb_expr), _p, _pp],
+    "sb_join_probe_ex": [_p, _p, C.POINTER(_i32), _i32, _i32, C.POINTER(sb_join_options), _p, _pp],
     "sb_join_probe_condition": [_p, _p, C.POINTER(_i32), _i32, _i32, C.POINTER(sb_expr), _p, _pp],
     "sb_hash_table_release": [_p],
     "sb_comm_get_unique_id": [C.c_char_p], "sb_comm_init": [_i32, _i32, C.c_char_p], "sb_comm_destroy": [],

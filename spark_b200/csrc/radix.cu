@@ -63,7 +63,7 @@ __device__ __forceinline__ void st_status(uint64_t *p, uint64_t v) {
 // One LSD pass over byte `byte`.  status: [tiles][256] zero-initialised; ticket: zero-initialised tile counter.
 // RS_THREADS x RS_ITEMS pairs per tile (a warp owns 32 x RS_ITEMS consecutive rows); digit d is owned by thread d (RS_THREADS >= 256).
 template <int RS_THREADS, int RS_ITEMS>
-__global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const uint64_t *__restrict__ in_keys, const uint32_t *__restrict__ in_vals,
+__global__ void __launch_bounds__(RS_THREADS, (RS_THREADS * RS_ITEMS <= 4096 ? 768 : 1024) / RS_THREADS) rs_onesweep_kernel(const uint64_t *__restrict__ in_keys, const uint32_t *__restrict__ in_vals,
                                                                  uint64_t *__restrict__ out_keys, uint32_t *__restrict__ out_vals, int64_t n, int byte,
                                                                  const unsigned long long *__restrict__ gbase /* [256] of this byte */,
                                                                  uint64_t *__restrict__ status, uint32_t *__restrict__ ticket) {
@@ -101,20 +101,36 @@ __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const uint64_t 
     }
   }
   // ---- stable rank inside the warp's segment: (k, lane) order is memory order -----------------------------------------------------
+  // Which lanes hold the same digit?  match.any answers in one instruction but with a long, serialising latency (ncu, round 2:
+  // 17 of 27 warp-stall samples per issue were the instruction after MATCH waiting for it).  Eight ballots -- one per digit
+  // bit, all independent across bits AND across the thread's RS_ITEMS keys -- give the same mask and pipeline freely.
   uint32_t *wh = s_whist[warp];
+  uint32_t peers[RS_ITEMS];
 #pragma unroll
   for (int k = 0; k < RS_ITEMS; k++) {
     const bool valid = seg + k * 32 + lane < tile_n;
-    const uint32_t d = valid ? (uint32_t)((key[k] >> shift) & 0xff) : 0xffffffffu;   // invalid rows only match each other
-    const uint32_t peers = __match_any_sync(0xffffffffu, d);
-    const int leader = __ffs(peers) - 1;
-    uint32_t base = 0;
-    if (lane == leader && valid) {
-      base = wh[d];
-      wh[d] = base + __popc(peers);
+    const uint32_t d = (uint32_t)((key[k] >> shift) & 0xff);
+    uint32_t m = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+      const uint32_t bal = __ballot_sync(0xffffffffu, (d >> b) & 1);
+      m &= ((d >> b) & 1) ? bal : ~bal;
     }
-    base = __shfl_sync(0xffffffffu, base, leader);
-    rank[k] = (uint16_t)(base + __popc(peers & ((1u << lane) - 1)));
+    peers[k] = valid ? m : 0u;
+  }
+  const uint32_t lt = (1u << lane) - 1;
+#pragma unroll
+  for (int k = 0; k < RS_ITEMS; k++) {
+    const uint32_t p = peers[k];
+    const uint32_t d = (uint32_t)((key[k] >> shift) & 0xff);
+    const int leader = __ffs(p) - 1;                    // -1 for rows past the end of the tile
+    uint32_t base = 0;
+    if (lane == leader) {
+      base = wh[d];
+      wh[d] = base + __popc(p);
+    }
+    base = __shfl_sync(0xffffffffu, base, leader < 0 ? lane : leader);
+    rank[k] = (uint16_t)(base + __popc(p & lt));
     __syncwarp();
   }
   __syncthreads();

@@ -490,18 +490,26 @@ class TakeOrderedAndProjectExec(SparkPlan):
 
 
 class HashedRelation:
-    """Build side resident in HBM (HashedRelation.scala:136-168): sb_hash_table handle."""
+    """Build side resident in HBM (HashedRelation.scala:136-168): sb_hash_table handle.  `condition` is the FilterExec below the
+    build side fused into the build (rows failing it stay out of the relation; nothing is materialised); `out_names` the columns
+    of the build batch that reach the join output (the ProjectExec below / above, fused)."""
 
-    def __init__(self, batch: ColumnarBatch, keys, stream=None):
+    def __init__(self, batch: ColumnarBatch, keys, stream=None, condition=None, out_names=None):
         lib = capi.load()
         idx = [batch.column_index(k) for k in keys]
         arr = (C.c_int32 * max(1, len(idx)))(*idx)
         h = C.c_void_p()
-        capi.check(lib.sb_join_build(batch.handle, arr, len(idx), _h(stream), C.byref(h)))
+        if condition is not None:
+            ce = CompiledExpr(condition, _schema_of(batch))
+            capi.check(lib.sb_join_build_filtered(batch.handle, arr, len(idx), C.byref(ce.c), _h(stream), C.byref(h)))
+        else:
+            capi.check(lib.sb_join_build(batch.handle, arr, len(idx), _h(stream), C.byref(h)))
         self.handle = h
-        self.names = batch.names
-        self.arrow_types = batch.arrow_types
-        self.types = [batch.column_desc(i).type for i in range(len(batch.names))]
+        self.out_cols = None if out_names is None else [batch.column_index(n) for n in out_names]
+        sel = range(len(batch.names)) if self.out_cols is None else self.out_cols
+        self.names = [batch.names[i] for i in sel]
+        self.arrow_types = [batch.arrow_types[i] for i in sel]
+        self.types = [batch.column_desc(i).type for i in sel]
 
     def close(self):
         if self.handle:
@@ -513,6 +521,19 @@ class HashedRelation:
             self.close()
         except Exception:
             pass
+
+
+def _peel(plan):
+    """(source, condition, names): `plan` seen as [ProjectExec of bare attributes] over [FilterExec] over source -- the part of
+    the pipeline below a join that whole-stage codegen fuses into it on the CPU path (no rename, no computed column)."""
+    names = cond = None
+    if isinstance(plan, ProjectExec) and all(isinstance(e, AttributeReference) and e.name == n for n, e in plan.projectList):
+        names = [n for n, _ in plan.projectList]
+        plan = plan.child
+    if isinstance(plan, FilterExec):
+        cond = plan.condition
+        plan = plan.child
+    return plan, cond, names
 
 
 _STREAM_LEFT = {"inner": "inner", "left_outer": "left_outer", "left_semi": "left_semi", "left_anti": "left_anti", "full_outer": "full_outer",
@@ -539,21 +560,26 @@ class BroadcastHashJoinExec(SparkPlan):
     def executeColumnar(self, stream=None):
         build_plan, stream_plan = (self.right, self.left) if self.buildSide == "right" else (self.left, self.right)
         build_keys, stream_keys = (self.rightKeys, self.leftKeys) if self.buildSide == "right" else (self.leftKeys, self.rightKeys)
-        build = build_plan.executeColumnar(stream)
+        # Filter / Project directly below the join are fused into build and probe (nothing between scan and join output is
+        # materialised); a residual condition keeps the children as they are
+        fuse = self.condition is None and self.native_type not in ("existence", "left_anti_null_aware")
+        b_src, b_cond, b_names = _peel(build_plan) if fuse else (build_plan, None, None)
+        s_src, s_cond, s_names = _peel(stream_plan) if fuse else (stream_plan, None, None)
+        build = b_src.executeColumnar(stream)
         try:
-            rel = HashedRelation(build, build_keys, stream)
+            rel = HashedRelation(build, build_keys, stream, b_cond, b_names)
         finally:
             build.close()
         try:
-            probe = stream_plan.executeColumnar(stream)
+            probe = s_src.executeColumnar(stream)
             try:
-                out = probe_join(rel, probe, stream_keys, self.native_type, stream, self.condition, streamed_is_left=self.buildSide == "right")
+                out = probe_join(rel, probe, stream_keys, self.native_type, stream, self.condition, probe_filter=s_cond, probe_out=s_names)
             finally:
                 probe.close()
         finally:
             rel.close()
-        if self.buildSide == "left":      # streamed ++ build came back: restore left ++ right
-            nl = len(rel.names)
+        if self.buildSide == "left" and self.native_type in ("inner", "left_outer", "build_outer", "full_outer"):
+            nl = len(rel.names)      # streamed ++ build came back: restore left ++ right
             order = list(range(len(out.names) - nl, len(out.names))) + list(range(len(out.names) - nl))
             arr = (C.c_int32 * len(order))(*order)
             h = C.c_void_p()
@@ -565,24 +591,46 @@ class BroadcastHashJoinExec(SparkPlan):
         return out
 
 
-def probe_join(rel: HashedRelation, probe: ColumnarBatch, keys, joinType, stream=None, condition=None, streamed_is_left=True) -> ColumnarBatch:
+def probe_join(rel: HashedRelation, probe: ColumnarBatch, keys, joinType, stream=None, condition=None, probe_filter=None, probe_out=None,
+               **_ignored) -> ColumnarBatch:
     lib = capi.load()
     idx = [probe.column_index(k) for k in keys]
     arr = (C.c_int32 * max(1, len(idx)))(*idx)
     h = C.c_void_p()
+    p_sel = list(range(len(probe.names))) if probe_out is None else [probe.column_index(n) for n in probe_out]
+    p_names = [probe.names[i] for i in p_sel]
+    p_types = [probe.arrow_types[i] for i in p_sel]
     if condition is not None:
         # the residual condition sees the joined row as the kernels lay it out: streamed columns ++ build columns
         schema = Schema(probe.names + rel.names, [probe.column_desc(i).type for i in range(len(probe.names))] + rel.types)
         ce = CompiledExpr(condition, schema)
         capi.check(lib.sb_join_probe_condition(rel.handle, probe.handle, arr, len(idx), capi.SB_JOIN[joinType], C.byref(ce.c), _h(stream), C.byref(h)))
+    elif probe_filter is not None or probe_out is not None or rel.out_cols is not None:
+        opt = capi.sb_join_options()
+        keep = []
+        if probe_filter is not None:
+            fe = CompiledExpr(probe_filter, _schema_of(probe))
+            keep.append(fe)
+            opt.probe_filter = C.pointer(fe.c)
+        if probe_out is not None:
+            pa_ = (C.c_int32 * max(1, len(p_sel)))(*p_sel)
+            keep.append(pa_)
+            opt.probe_out_cols = C.cast(pa_, C.POINTER(C.c_int32))
+            opt.n_probe_out = len(p_sel)
+        if rel.out_cols is not None:
+            ba_ = (C.c_int32 * max(1, len(rel.out_cols)))(*rel.out_cols)
+            keep.append(ba_)
+            opt.build_out_cols = C.cast(ba_, C.POINTER(C.c_int32))
+            opt.n_build_out = len(rel.out_cols)
+        capi.check(lib.sb_join_probe_ex(rel.handle, probe.handle, arr, len(idx), capi.SB_JOIN[joinType], C.byref(opt), _h(stream), C.byref(h)))
     else:
         capi.check(lib.sb_join_probe(rel.handle, probe.handle, arr, len(idx), capi.SB_JOIN[joinType], _h(stream), C.byref(h)))
     if joinType in ("left_semi", "left_anti", "left_anti_null_aware"):
-        return ColumnarBatch(h, probe.names, probe.arrow_types)
+        return ColumnarBatch(h, p_names, p_types)
     if joinType == "existence":
         import pyarrow as pa
-        return ColumnarBatch(h, probe.names + ["exists"], probe.arrow_types + [pa.bool_()])
-    return ColumnarBatch(h, probe.names + rel.names, probe.arrow_types + rel.arrow_types)
+        return ColumnarBatch(h, p_names + ["exists"], p_types + [pa.bool_()])
+    return ColumnarBatch(h, p_names + rel.names, p_types + rel.arrow_types)
 
 
 class ShuffledHashJoinExec(BroadcastHashJoinExec):

@@ -307,3 +307,40 @@ def test_filter_predicates_of_every_type(gpu, stream, n, interpret_only, sbconfi
         got = _run(lambda scan: FilterExec(cond, scan), t, stream)
         want = O.filter_table(t, cond.sexpr())
         assert got.column("row").to_pylist() == want.column("row").to_pylist(), cond.sexpr()
+
+
+def test_reference_sql_golden_answers(gpu, stream):
+    """The aggregate answers the reference prints in group-by.sql.out / having.sql.out (tests/sql_goldens.py), computed by the GPU
+    operators: Project (computed grouping keys) -> HashAggregate -> Filter (HAVING)."""
+    import sql_goldens as G
+    from spark_b200.columnar import ColumnarBatch
+    from spark_b200.execution import FilterExec, HashAggregateExec, LocalTableScanExec, ProjectExec
+    from spark_b200.expressions import Average, Count, Literal, Max, Min, Sum, col
+    fns = {"count": lambda c: Count(col(c)), "count_star": lambda c: Count(), "sum": lambda c: Sum(col(c)), "avg": lambda c: Average(col(c)),
+           "min": lambda c: Min(col(c)), "max": lambda c: Max(col(c))}
+
+    def expr(e):
+        if e[0] == "col":
+            return col(e[1])
+        if e[0] == "lit":
+            return Literal(bool(e[1]) if e[2] is np.bool_ else e[1])
+        l, r = expr(e[1]), expr(e[2])
+        return {"add": lambda: l + r, "gt": lambda: l > r, "eq": lambda: l.eq(r)}[e[0]]()
+    for name, table, keys, proj, aggs, post, want, where in G.CASES:
+        plan = LocalTableScanExec(ColumnarBatch.from_arrow(table, stream))
+        if proj:
+            plan = ProjectExec([(c, col(c)) for c in table.column_names] + [(n, expr(e)) for n, e in proj], plan)
+        plan = HashAggregateExec(keys or [], [(fns[f](c), n) for f, c, n in aggs], plan)
+        if post is not None and post != "drop_keys":
+            plan = FilterExec(expr(post), plan)
+        got = plan.collect(stream)
+        if post == "drop_keys":
+            got = got.select([n for _, _, n in aggs])
+        rows = list(zip(*[got.column(i).to_pylist() for i in range(got.num_columns)])) if got.num_rows else []
+        assert len(rows) == len(want), (name, where, rows, want)
+        for g, w in zip(G.norm(rows), G.norm(want)):
+            for x, y in zip(g, w):
+                if isinstance(y, float):
+                    assert abs(x - y) <= 1e-6 * abs(y), (name, where, x, y)
+                else:
+                    assert x == y, (name, where, g, w)

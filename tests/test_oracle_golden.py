@@ -297,3 +297,33 @@ def test_outer_and_existence_join_reference_answers():
     # existence join: one boolean per streamed row = membership in the semi join's answer
     ex = O.hash_join(F.EXIST_LEFT, F.EXIST_RIGHT, ["a"], ["c"], "existence", F.COND_B_LT_D)
     assert ex.column("exists").to_pylist() == [False, False, True, True, False, False, False, False]
+
+
+def _golden_oracle(case):
+    import sql_goldens as G
+    name, table, keys, proj, aggs, post, want, where = case
+    t = table
+    if proj:
+        t = O.project(t, [(c, ("col", c)) for c in table.column_names] + proj)
+    out = O.hash_aggregate(t, keys or [], aggs)
+    if post == "drop_keys":
+        out = out.select([n for _, _, n in aggs])
+    elif post is not None:
+        out = O.filter_table(out, post)
+    return out
+
+
+def test_aggregate_answers_of_the_reference_sql_goldens():
+    """group-by.sql.out / having.sql.out (tests/sql_goldens.py): the oracle's aggregate reproduces the rows the reference prints."""
+    import sql_goldens as G
+    for case in G.CASES:
+        got = _golden_oracle(case)
+        rows = list(zip(*[got.column(i).to_pylist() for i in range(got.num_columns)])) if got.num_rows else []
+        want = case[6]
+        assert len(rows) == len(want), (case[0], rows, want)
+        for g, w in zip(G.norm(rows), G.norm(want)):
+            for x, y in zip(g, w):
+                if isinstance(y, float):
+                    assert abs(x - y) <= 1e-15 * abs(y), (case[0], case[7], x, y)       # the golden prints 17 significant digits
+                else:
+                    assert x == y, (case[0], case[7], g, w)

@@ -1,0 +1,16 @@
+#!/bin/bash
+cd /root/repo
+mkdir -p gpurun_out
+python -m pytest tests/test_gpu_join.py tests/test_gpu_tpch.py tests/test_gpu_sort.py tests/test_gpu_aggregate.py tests/test_gpu_round2.py -x -q -m gpu > gpurun_out/r5_tests.log 2>&1
+echo "tests rc=$?"; tail -25 gpurun_out/r5_tests.log
+python tools/exp/sort_variants.py > gpurun_out/r5_sort_variants.jsonl 2> gpurun_out/r5_sort_variants.err; echo "variants rc=$?"; cat gpurun_out/r5_sort_variants.jsonl; tail -3 gpurun_out/r5_sort_variants.err
+timeout 900 python bench.py --steps 5 --legs q3,q5 --no-cpu-baseline > gpurun_out/r5_bench_q3q5_sf100.json 2> gpurun_out/r5_bench_q3q5.err
+echo "bench q3q5 rc=$?"; python - <<'PY'
+import json
+try:
+    d=json.loads(open('gpurun_out/r5_bench_q3q5_sf100.json').read().strip().splitlines()[-1])
+    for k,l in d["legs"].items(): print(k, l["ms_per_step"], l["verified"], l["kernel_ms_per_step"], l["e2e"]["ms_per_step"], l["roofline"]["frac"])
+except Exception as e: print("ERR",e)
+PY
+tail -5 gpurun_out/r5_bench_q3q5.err
+timeout 600 python tools/op_bench.py join > gpurun_out/r5_op_join.jsonl 2> gpurun_out/r5_op_join.err; echo "join rc=$?"; cat gpurun_out/r5_op_join.jsonl | cut -c1-600
