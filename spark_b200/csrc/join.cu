@@ -19,6 +19,7 @@
 //   probe : pass 1 counts matches per streamed row (and remembers the first match), exclusive scan,
 //           pass 2 writes (probe row, build row) pairs in streamed-row order; rows with <= 1 match do not walk
 //           the table twice.  Output columns are gathered once from both sides.
+#include <memory>
 #include "common.cuh"
 #include "expr.cuh"
 #include "primitives.cuh"
@@ -125,10 +126,14 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_build_kernel(JoinKeys k, in
 __global__ void __launch_bounds__(JOIN_THREADS) join_count_kernel(JoinKeys k, int64_t n, const JoinSlot *__restrict__ slots, int64_t cap,
                                                                   int join_type, int null_aware, int32_t *__restrict__ counts, uint32_t *__restrict__ first,
                                                                   int32_t *__restrict__ block_counts, uint8_t *__restrict__ matched,
-                                                                  const uint8_t *__restrict__ row_mask, const uint32_t *__restrict__ bloom, uint64_t bloom_mask) {
+                                                                  const uint8_t *__restrict__ row_mask, const uint32_t *__restrict__ bloom, uint64_t bloom_mask,
+                                                                  const int64_t *__restrict__ rows) {
   __shared__ int32_t wsum[JOIN_THREADS / 32];
-  int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool in_range = row < n && (!row_mask || row_mask[row]);   // fused FilterExec below the streamed side
+  // `rows` (optional): the candidate list of join_candidate_kernel -- item i stands for streamed row rows[i]; counts / first are
+  // indexed by item
+  const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t row = rows && item < n ? rows[item] : item;
+  const bool in_range = item < n && (!row_mask || row_mask[row]);   // fused FilterExec below the streamed side
   uint64_t key;
   int32_t matches = 0;
   uint32_t f = FREE_SLOT;
@@ -164,9 +169,9 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_count_kernel(JoinKeys k, in
     default: c = matches > 0 || (null_aware && null_key) ? 0 : 1; break;   // anti (null-aware: a NULL key is neither in nor not in)
   }
   if (!in_range) c = 0;
-  if (row < n) {
-    first[row] = f;
-    counts[row] = c;
+  if (item < n) {
+    first[item] = f;
+    counts[item] = c;
   }
   // output rows of this block: the scan that turns counts into offsets runs over blocks, not rows (join_fill_kernel redoes
   // the in-block prefix in shared memory), which saves an 8-byte offset per streamed row and two passes over them
@@ -185,11 +190,13 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_count_kernel(JoinKeys k, in
 __global__ void __launch_bounds__(JOIN_THREADS) join_fill_kernel(JoinKeys k, int64_t n, const JoinSlot *__restrict__ slots, int64_t cap,
                                                                  int join_type, const int32_t *__restrict__ counts,
                                                                  const int64_t *__restrict__ block_offsets, const uint32_t *__restrict__ first,
-                                                                 int64_t *__restrict__ out_probe, int64_t *__restrict__ out_build) {
+                                                                 int64_t *__restrict__ out_probe, int64_t *__restrict__ out_build,
+                                                                 const int64_t *__restrict__ rows) {
   __shared__ int32_t wsum[JOIN_THREADS / 32];
-  int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t row = rows && item < n ? rows[item] : item;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int32_t c = row < n ? counts[row] : 0;
+  const int32_t c = item < n ? counts[item] : 0;
   int32_t x = c;   // inclusive prefix inside the warp
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
@@ -202,7 +209,7 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_fill_kernel(JoinKeys k, int
   for (int w = 0; w < warp; w++) woff += wsum[w];
   if (c == 0) return;
   int64_t o = block_offsets[blockIdx.x] + woff + (x - c);
-  uint32_t f = first[row];
+  uint32_t f = first[item];
   if (c == 1 || join_type == SB_JOIN_LEFT_SEMI || join_type == SB_JOIN_LEFT_ANTI) {
     out_probe[o] = row;
     if (out_build) out_build[o] = (f == FREE_SLOT || join_type >= SB_JOIN_LEFT_SEMI) ? -1 : (int64_t)f;
@@ -224,6 +231,28 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_fill_kernel(JoinKeys k, int
     }
     h = (h + 1) & mask;
   }
+}
+
+// Selective joins over a long streamed side (Q3: 600 M lineitem rows, one in twenty survives filter + Bloom test): one pass over
+// (filter mask, key, Bloom word) marks the rows that can produce output at all; only those -- as a compacted row list -- go through
+// the count / fill passes with their per-row bookkeeping.  needs_key: inner / semi joins drop NULL-key and Bloom-negative rows here;
+// outer / anti joins keep every row the filter keeps (those rows are output even without a partner).
+__global__ void __launch_bounds__(JOIN_THREADS) join_candidate_kernel(JoinKeys k, int64_t n, const uint8_t *__restrict__ row_mask,
+                                                                      const uint32_t *__restrict__ bloom, uint64_t bloom_mask, int needs_key,
+                                                                      uint8_t *__restrict__ out) {
+  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n) return;
+  bool c = !row_mask || row_mask[row];
+  if (c && needs_key) {
+    uint64_t key;
+    c = join_key(k, row, key);
+    if (c && bloom) {
+      const uint64_t hh = join_mix(key);
+      const uint32_t bb = bloom_bits(hh);
+      c = (__ldg(&bloom[bloom_word(hh, bloom_mask)]) & bb) == bb;
+    }
+  }
+  out[row] = c;
 }
 
 static JoinKeys make_join_keys(const sb_table *t, const int32_t *key_cols, int32_t nkeys, const sb_hash_table *ht) {
@@ -429,11 +458,29 @@ int sb_join_probe_ex(const sb_hash_table *ht, const sb_table *probe, const int32
     expr_validate(probe, *probe_filter);
     if (n > 0) eval_predicate(probe, *probe_filter, pmask.as<uint8_t>(), st);
   }
-  if (n > 0) {
+  // candidate list (see join_candidate_kernel): worth its pass when the streamed side is long
+  const bool use_cand = n >= (1 << 20) && join_type != SB_JOIN_EXISTENCE;
+  const bool needs_key = kt_type == SB_JOIN_INNER || kt_type == SB_JOIN_LEFT_SEMI;
+  int64_t nitems = n;
+  std::unique_ptr<Scratch> cand_rows;
+  if (use_cand) {
+    KernelTimer kt("join_candidates", st);
+    Scratch cmask(n + 16, st), f32(compact_tiles(n) * 4 + 16, st), pos(compact_tiles(n) * 8 + 16, st), tot(8, st);
+    cand_rows.reset(new Scratch(n * 8 + 16, st));
+    join_candidate_kernel<<<nb, JOIN_THREADS, 0, st>>>(k, n, probe_filter ? pmask.as<uint8_t>() : nullptr, ht->bloom, ht->bloom_mask, needs_key ? 1 : 0,
+                                                      cmask.as<uint8_t>());
+    SB_LAUNCH_CHECK();
+    compact_mask_async(cmask.as<uint8_t>(), n, cand_rows->as<int64_t>(), f32.as<int32_t>(), pos.as<int64_t>(), tot.as<int64_t>(), st);
+    SB_CUDA(cudaMemcpyAsync(&nitems, tot.ptr, 8, cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaStreamSynchronize(st));
+    nb = (unsigned)((nitems + JOIN_THREADS - 1) / JOIN_THREADS);
+  }
+  const int64_t *rows = use_cand ? cand_rows->as<int64_t>() : nullptr;
+  if (nitems > 0) {
     KernelTimer kt("join_probe", st);
-    join_count_kernel<<<nb, JOIN_THREADS, 0, st>>>(k, n, ht->slots, ht->cap, kt_type, null_aware, counts.as<int32_t>(), first.as<uint32_t>(),
+    join_count_kernel<<<nb, JOIN_THREADS, 0, st>>>(k, nitems, ht->slots, ht->cap, kt_type, null_aware, counts.as<int32_t>(), first.as<uint32_t>(),
                                                    block_counts.as<int32_t>(), build_rows_too ? matched.as<uint8_t>() : nullptr,
-                                                   probe_filter ? pmask.as<uint8_t>() : nullptr, ht->bloom, ht->bloom_mask);
+                                                   use_cand ? nullptr : (probe_filter ? pmask.as<uint8_t>() : nullptr), ht->bloom, ht->bloom_mask, rows);
     SB_LAUNCH_CHECK();
   }
   if (join_type == SB_JOIN_EXISTENCE) {   // HashJoin.existenceJoin :301: the streamed row plus one boolean
@@ -471,11 +518,11 @@ int sb_join_probe_ex(const sb_hash_table *ht, const sb_table *probe, const int32
   SB_CUDA(cudaStreamSynchronize(st));
   const int64_t npairs = totals[0], nun = build_rows_too ? totals[1] : 0, nout = npairs + nun;
   Scratch out_probe(nout * 8 + 16, st), out_build(pairs ? nout * 8 + 16 : 0, st);
-  if (n > 0 && npairs > 0) {
+  if (nitems > 0 && npairs > 0) {
     KernelTimer kt("join_fill", st);
-    join_fill_kernel<<<nb, JOIN_THREADS, 0, st>>>(k, n, ht->slots, ht->cap, kt_type, counts.as<int32_t>(),
+    join_fill_kernel<<<nb, JOIN_THREADS, 0, st>>>(k, nitems, ht->slots, ht->cap, kt_type, counts.as<int32_t>(),
                                                   offsets.as<int64_t>(), first.as<uint32_t>(), out_probe.as<int64_t>(),
-                                                  pairs ? out_build.as<int64_t>() : nullptr);
+                                                  pairs ? out_build.as<int64_t>() : nullptr, rows);
     SB_LAUNCH_CHECK();
   }
   if (nun > 0) {
@@ -555,12 +602,12 @@ int sb_join_probe_condition(const sb_hash_table *ht, const sb_table *probe, cons
   Scratch pi(npairs * 8 + 16, st), bi(npairs * 8 + 16, st);
   if (n > 0) {
     join_count_kernel<<<nb, JOIN_THREADS, 0, st>>>(k, n, ht->slots, ht->cap, SB_JOIN_INNER, 0, counts.as<int32_t>(), first.as<uint32_t>(),
-                                                   block_counts.as<int32_t>(), nullptr, nullptr, ht->bloom, ht->bloom_mask);
+                                                   block_counts.as<int32_t>(), nullptr, nullptr, ht->bloom, ht->bloom_mask, nullptr);
     SB_LAUNCH_CHECK();
     exclusive_scan_i32_to_i64(block_counts.as<int32_t>(), offsets.as<int64_t>(), nb, total.as<int64_t>(), st);
     if (npairs > 0) {
       join_fill_kernel<<<nb, JOIN_THREADS, 0, st>>>(k, n, ht->slots, ht->cap, SB_JOIN_INNER, counts.as<int32_t>(), offsets.as<int64_t>(),
-                                                    first.as<uint32_t>(), pi.as<int64_t>(), bi.as<int64_t>());
+                                                    first.as<uint32_t>(), pi.as<int64_t>(), bi.as<int64_t>(), nullptr);
       SB_LAUNCH_CHECK();
     }
   }

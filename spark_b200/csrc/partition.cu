@@ -101,6 +101,7 @@ __global__ void __launch_bounds__(PART_THREADS) pid_hist_kernel(KeyCols keys, in
 }
 
 constexpr int SCATTER_MAX_COLS = 16;
+constexpr int REMOTE_MAX_BUCKETS = 16;   // destinations of the fused exchange scatter (ranks on one NVSwitch domain)
 
 // K2: stable multisplit of a group of columns with shared-memory regrouping (the scatter of an LSD radix sort pass,
 // generalised to any set of fixed-width columns).  At most RG_MAX_NB buckets per pass; larger fan-outs run two passes
@@ -338,10 +339,31 @@ __device__ __forceinline__ void regroup_drain_column(const uint8_t *__restrict__
     if (FULLT || ((gmask >> it) & 1)) ((T *)dst)[gdest[it]] = v[it];
 }
 
-template <int RG_THREADS>
+// REMOTE drain: the run of bucket b goes to bucket b's OWN base address (a peer GPU's receive window mapped over NVLink, or
+// this GPU's own window): ptrs[b] is pre-biased so that the element for global sorted position g lands at ptrs[b] + g * sizeof(T).
+template <typename T, bool FULLT>
+__device__ __forceinline__ void regroup_drain_column_remote(const uint8_t *__restrict__ stage, const uint64_t *__restrict__ ptrs,
+                                                            const uint32_t (&src2)[RG_ITEMS / 2], const uint32_t (&gdest)[RG_ITEMS],
+                                                            const uint32_t (&bk2)[RG_ITEMS / 4], uint32_t gmask) {
+  const T *s = (const T *)stage;
+  T v[RG_ITEMS];
+#pragma unroll
+  for (int it = 0; it < RG_ITEMS; it++) v[it] = s[(src2[it >> 1] >> ((it & 1) * 16)) & 0xFFFFu];
+#pragma unroll
+  for (int it = 0; it < RG_ITEMS; it++)
+    if (FULLT || ((gmask >> it) & 1)) {
+      T *dst = (T *)(uintptr_t)ptrs[(bk2[it >> 2] >> ((it & 3) * 8)) & 0xFFu];
+      dst[gdest[it]] = v[it];
+    }
+}
+
+// REMOTE = the fused exchange scatter (sb_shuffle_exchange): buckets are destination ranks and every bucket's rows are stored
+// straight into that rank's receive window (`bptr`: [ncols][nb] pre-biased byte addresses) -- the multisplit IS the transport.
+template <int RG_THREADS, bool REMOTE = false>
 __global__ void __launch_bounds__(RG_THREADS, 1024 / RG_THREADS) regroup_tma_kernel(const __grid_constant__ RegroupCols cols, const int32_t *__restrict__ bucket,
                                                                                  const uint32_t *__restrict__ base, int64_t n, int32_t nb, int64_t ntiles,
-                                                                                 int64_t *__restrict__ perm_out, int l2_stream) {
+                                                                                 int64_t *__restrict__ perm_out, int l2_stream,
+                                                                                 const uint64_t *__restrict__ bptr = nullptr) {
   constexpr int RG_WARPS = RG_THREADS / 32, RG_TILE = RG_THREADS * RG_ITEMS;
   constexpr int RGT_STAGE_BYTES = RG_TILE * 8;   // one 8-byte column tile
   static_assert(RG_TILE / RG_WARPS == RG_SEG, "a warp ranks 256 rows");
@@ -358,7 +380,10 @@ __global__ void __launch_bounds__(RG_THREADS, 1024 / RG_THREADS) regroup_tma_ker
   static_assert(RG_WARPS * RG_MAX_NB <= RG_TILE, "wcnt must fit in the ssrc storage");
   __shared__ uint32_t cursor[RG_MAX_NB];
   __shared__ uint32_t warp_sums[RG_WARPS];
+  __shared__ uint64_t s_bptr[REMOTE ? SCATTER_MAX_COLS * REMOTE_MAX_BUCKETS : 1];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (REMOTE)
+    for (int i = tid; i < cols.ncols * nb; i += RG_THREADS) s_bptr[i] = bptr[i];
   // Tiles are dealt round-robin (block b: tiles b, b + grid, ...), so at any moment the grid works on ~grid CONSECUTIVE tiles:
   // their runs are adjacent inside every bucket, which lets L2 complete the sectors two tiles share before eviction and keeps
   // the DRAM write stream to (buckets x columns) compact regions instead of (blocks x buckets x columns) scattered ones.
@@ -507,6 +532,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1024 / RG_THREADS) regroup_tma_ker
     __syncthreads();
     uint32_t gdest[RG_ITEMS];        // output row of sorted position j = it * RG_THREADS + tid
     uint32_t src2[RG_ITEMS / 2];     // tile row that lands at sorted position j, two per register
+    uint32_t bk2[RG_ITEMS / 4] = {0};   // REMOTE: bucket of sorted position j, four per register
     uint32_t gmask = 0;
 #pragma unroll
     for (int it = 0; it < RG_ITEMS; it++) {
@@ -517,6 +543,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1024 / RG_THREADS) regroup_tma_ker
         gdest[it] = cursor[b] + (uint32_t)(j - first[b]);
         srow = ssrc[j];
         gmask |= 1u << it;
+        if (REMOTE) bk2[it >> 2] |= (uint32_t)b << ((it & 3) * 8);
       } else gdest[it] = 0;
       if (it & 1) src2[it >> 1] |= srow << 16;
       else src2[it >> 1] = srow;
@@ -533,8 +560,11 @@ __global__ void __launch_bounds__(RG_THREADS, 1024 / RG_THREADS) regroup_tma_ker
       const int w = cols.width[c];
       void *dst = cols.dst[c];
       const uint8_t *cs = acquire(cols.src[c], w, tbase, tile_n);
-#define SB_DRAIN(T)                                                             \
-  if (fullt) regroup_drain_column<T, true>(cs, dst, src2, gdest, gmask);       \
+#define SB_DRAIN(T)                                                                                            \
+  if (REMOTE) {                                                                                                \
+    if (fullt) regroup_drain_column_remote<T, true>(cs, s_bptr + c * nb, src2, gdest, bk2, gmask);           \
+    else regroup_drain_column_remote<T, false>(cs, s_bptr + c * nb, src2, gdest, bk2, gmask);                \
+  } else if (fullt) regroup_drain_column<T, true>(cs, dst, src2, gdest, gmask);                              \
   else regroup_drain_column<T, false>(cs, dst, src2, gdest, gmask);
       switch (w) {
         case 1: SB_DRAIN(uint8_t) break;
@@ -543,7 +573,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1024 / RG_THREADS) regroup_tma_ker
         default: SB_DRAIN(uint64_t) break;
       }
 #undef SB_DRAIN
-      if (cols.dst_valid[c]) {   // NULLs: clear the destination bit (rare, scattered)
+      if (!REMOTE && cols.dst_valid[c]) {   // NULLs: clear the destination bit (rare, scattered)
         const uint8_t *sv = cols.src_valid[c];
 #pragma unroll
         for (int it = 0; it < RG_ITEMS; it++) {

@@ -74,11 +74,12 @@ __global__ void __launch_bounds__(RS_THREADS, (RS_THREADS * RS_ITEMS <= 4096 ? 7
   int64_t *s_dst_off = (int64_t *)(s_keys + RS_TILE);                       // [256] global position of sorted tile position p with digit d: s_dst_off[d] + p
   uint32_t *s_vals = (uint32_t *)(s_dst_off + 256);                         // [RS_TILE]
   uint32_t(*s_whist)[256] = (uint32_t(*)[256])(s_vals + RS_TILE);           // [RS_WARPS][256] per-warp digit counters, then exclusive prefixes over the warps
-  uint32_t *s_bin_start = (uint32_t *)(s_whist + RS_WARPS);                 // [256] first tile-local position of every digit
+  uint32_t(*s_wrun)[256] = s_whist + RS_WARPS;                              // [RS_WARPS][256] running per-warp counters of the ranking phase
+  uint32_t *s_bin_start = (uint32_t *)(s_wrun + RS_WARPS);                  // [256] first tile-local position of every digit
   __shared__ uint32_t s_tile;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_tile = atomicAdd(ticket, 1u);
-  for (int i = tid; i < RS_WARPS * 256; i += RS_THREADS) (&s_whist[0][0])[i] = 0;
+  for (int i = tid; i < 2 * RS_WARPS * 256; i += RS_THREADS) (&s_whist[0][0])[i] = 0;   // s_whist and s_wrun
   __syncthreads();
   const int64_t tile = s_tile;
   const int64_t tile_base = tile * RS_TILE;
@@ -100,11 +101,30 @@ __global__ void __launch_bounds__(RS_THREADS, (RS_THREADS * RS_ITEMS <= 4096 ? 7
       val[k] = 0;
     }
   }
+  // ---- early counts: per-warp digit histograms by shared-memory atomics, so the tile's 256 counts can be PUBLISHED before the
+  // (long) ranking phase -- successors then find an aggregate, or already an inclusive prefix, when they look back -----------------
+  uint32_t *wh = s_whist[warp];
+#pragma unroll
+  for (int k = 0; k < RS_ITEMS; k++)
+    if (seg + k * 32 + lane < tile_n) atomicAdd(&wh[(uint32_t)((key[k] >> shift) & 0xff)], 1u);
+  __syncthreads();
+  const bool digit_owner = tid < 256;
+  uint32_t count = 0;
+  uint64_t *my_status = status + tile * 256 + (digit_owner ? tid : 0);
+  if (digit_owner) {
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; w++) {   // per-warp counts -> exclusive prefix over the warps (order of the warps = order of the rows)
+      const uint32_t c = s_whist[w][tid];
+      s_whist[w][tid] = count;
+      count += c;
+    }
+    st_status(my_status, RS_FLAG_AGG | count);
+  }
   // ---- stable rank inside the warp's segment: (k, lane) order is memory order -----------------------------------------------------
   // Which lanes hold the same digit?  match.any answers in one instruction but with a long, serialising latency (ncu, round 2:
   // 17 of 27 warp-stall samples per issue were the instruction after MATCH waiting for it).  Eight ballots -- one per digit
   // bit, all independent across bits AND across the thread's RS_ITEMS keys -- give the same mask and pipeline freely.
-  uint32_t *wh = s_whist[warp];
+  uint32_t *wr = s_wrun[warp];
   uint32_t peers[RS_ITEMS];
 #pragma unroll
   for (int k = 0; k < RS_ITEMS; k++) {
@@ -126,29 +146,14 @@ __global__ void __launch_bounds__(RS_THREADS, (RS_THREADS * RS_ITEMS <= 4096 ? 7
     const int leader = __ffs(p) - 1;                    // -1 for rows past the end of the tile
     uint32_t base = 0;
     if (lane == leader) {
-      base = wh[d];
-      wh[d] = base + __popc(p);
+      base = wr[d];
+      wr[d] = base + __popc(p);
     }
     base = __shfl_sync(0xffffffffu, base, leader < 0 ? lane : leader);
     rank[k] = (uint16_t)(base + __popc(p & lt));
     __syncwarp();
   }
-  __syncthreads();
-  // ---- per digit (thread t owns digit t): exclusive prefix over the warps, tile count, look-back -------------------------------------
-  const bool digit_owner = tid < 256;
-  uint32_t count = 0;
-  uint64_t *my_status = status + tile * 256 + (digit_owner ? tid : 0);
-  if (digit_owner) {
-#pragma unroll
-    for (int w = 0; w < RS_WARPS; w++) {
-      const uint32_t c = s_whist[w][tid];
-      s_whist[w][tid] = count;
-      count += c;
-    }
-    st_status(my_status, RS_FLAG_AGG | count);
-    s_bin_start[tid] = count;
-  }
-  // tile-local exclusive scan of the 256 digit counts: warp scans + a scan of the eight warp totals
+  // ---- tile-local exclusive scan of the 256 digit counts: warp scans + a scan of the eight warp totals ----------------------------
   __shared__ uint32_t s_wsum[8];
   uint32_t incl = count;
   if (digit_owner) {
@@ -165,15 +170,24 @@ __global__ void __launch_bounds__(RS_THREADS, (RS_THREADS * RS_ITEMS <= 4096 ? 7
     for (int w = 0; w < warp; w++) bin_start += s_wsum[w];
     bin_start += incl - count;
     s_bin_start[tid] = bin_start;
-    // decoupled look-back: sum the aggregates of earlier tiles until one carries an inclusive prefix
+    // decoupled look-back: sum the aggregates of earlier tiles until one carries an inclusive prefix.  Four predecessors are
+    // fetched per round trip: with hundreds of tiles in flight the walk is long, and one L2 latency per step made it the
+    // critical path of a pass.
     uint64_t excl = 0;
-    for (int64_t t = tile - 1; t >= 0;) {
-      const uint64_t s = ld_status(status + t * 256 + tid);
-      const uint64_t flag = s & ~RS_VALUE_MASK;
-      if (flag == 0) continue;   // not published yet: the tile holding ticket t is running (tickets are handed out in order)
-      excl += s & RS_VALUE_MASK;
-      if (flag == RS_FLAG_INCL) break;
-      t--;
+    int64_t t = tile - 1;
+    bool done = t < 0;
+    while (!done) {
+      uint64_t sv[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) sv[j] = t - j >= 0 ? ld_status(status + (t - j) * 256 + tid) : RS_FLAG_INCL;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const uint64_t flag = sv[j] & ~RS_VALUE_MASK;
+        if (flag == 0) break;             // not published yet (the tile holding that ticket is running): fetch again from here
+        excl += sv[j] & RS_VALUE_MASK;
+        t--;
+        if (flag == RS_FLAG_INCL) { done = true; break; }
+      }
     }
     st_status(my_status, RS_FLAG_INCL | (excl + count));
     s_dst_off[tid] = (int64_t)gbase[tid] + (int64_t)excl - (int64_t)bin_start;
@@ -258,7 +272,7 @@ int radix_sort_pairs(uint64_t *keys, uint32_t *vals, int64_t n, cudaStream_t st)
   if (vi < 0 || vi >= (int)(sizeof(variants) / sizeof(variants[0]))) vi = 0;
   const Variant &V = variants[vi];
   const int tile_rows = V.threads * V.items;
-  const size_t smem = (size_t)tile_rows * 12 + 256 * 8 + (size_t)(V.threads / 32) * 256 * 4 + 256 * 4;
+  const size_t smem = (size_t)tile_rows * 12 + 256 * 8 + (size_t)(V.threads / 32) * 256 * 4 * 2 + 256 * 4;
   SB_CUDA(cudaFuncSetAttribute(V.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t tiles = (n + tile_rows - 1) / tile_rows;
   Scratch keys2(n * 8 + 16, st), vals2(n * 4 + 16, st), status(tiles * 256 * 8 + 16, st), tickets(8 * 4, st);
