@@ -90,6 +90,7 @@ int64_t sb_kernel_launch_count(void);
 int sb_profile_enable(int32_t on);
 int sb_profile_reset(void);
 int sb_profile_get(const char *kernel_name, double *out_total_ms, int64_t *out_launches);
+int sb_profile_dump(char *buf, int32_t len);   /* "name=total_ms/launches;..." of every timed section since the last reset */
 
 /* library-wide settings (tests and experiments; production needs none):
  *   "agg_rtc"           1 (default) compile plan-specialised aggregate kernels with NVRTC when a plan first meets a large
@@ -425,6 +426,13 @@ int sb_coalesce_partitions(const int64_t *const *bytes_by_partition, int32_t nsh
                            int64_t advisory_target_size, int32_t min_num_partitions, int64_t min_partition_size,
                            int32_t max_reducer_partitions_per_task, int32_t *out_start, int32_t *out_end, int64_t *out_data_size,
                            int32_t *out_nspecs);
+/* ShuffleExchangeExec(HashPartitioning) with map side and transport FUSED: one stable multisplit over the destination ranks whose
+ * runs are stored straight into the owners' receive windows (remote stores over NVLink -- the scatter kernel is the transport;
+ * no local partition-contiguous copy, no push, no copy-out), then one local multisplit into the owned partitions.  The result
+ * is partition-contiguous over the owned partitions (rows of a partition: by source rank, arrival order inside a source).
+ * Collective.  Same answer as sb_hash_partition + sb_all_to_all up to the order of the source blocks. */
+int sb_shuffle_exchange(const sb_table *in, const int32_t *key_cols, int32_t nkeys, int32_t num_partitions, sb_stream *s,
+                        sb_table **out, int64_t *out_part_offsets_host);
 /* BroadcastExchangeExec (SQLX/exchange/BroadcastExchangeExec.scala:45-279): every rank gets the
  * concatenation of all ranks' tables, in rank order. */
 int sb_all_gather(const sb_table *in, sb_stream *s, sb_table **out);

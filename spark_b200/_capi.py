@@ -98,6 +98,7 @@ _SIGNATURES = {
     "sb_device_info": [C.POINTER(_i64)], "sb_kernel_launch_count": [],
     "sb_config_set": [C.c_char_p, _i64], "sb_config_get": [C.c_char_p, C.POINTER(_i64)], "sb_hash_aggregate_last_plan": [],
     "sb_agg_rtc_compile_check": [C.POINTER(_i32), _i32, C.c_char_p, _i32], "sb_agg_plan_meta_words": [],
+    "sb_profile_dump": [C.c_char_p, _i32],
     "sb_profile_enable": [_i32], "sb_profile_reset": [], "sb_profile_get": [C.c_char_p, C.POINTER(C.c_double), C.POINTER(_i64)],
     "sb_host_alloc": [_i64, _pp], "sb_host_free": [_p],
     "sb_stream_create": [_pp], "sb_stream_destroy": [_p], "sb_stream_synchronize": [_p],
@@ -138,6 +139,7 @@ _SIGNATURES = {
     "sb_exchange_plan": [C.POINTER(_i64), _i32, _i32, C.POINTER(_i64)],
     "sb_all_to_all": [_p, C.POINTER(_i64), _i32, _p, _pp, C.POINTER(_i64)],
     "sb_all_gather": [_p, _p, _pp],
+    "sb_shuffle_exchange": [_p, C.POINTER(_i32), _i32, _i32, _p, _pp, C.POINTER(_i64)],
     "sb_exchange_counts": [C.POINTER(_i64), _i32, _p, C.POINTER(_i64)],
     "sb_map_output_statistics": [_p, C.POINTER(_i64), _i32, _p, C.POINTER(_i64)],
     "sb_coalesce_partitions": [C.POINTER(C.POINTER(_i64)), _i32, _i32, _i64, _i32, _i64, _i32, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i64),
@@ -154,10 +156,29 @@ def declared_symbols():
     return sorted(set(re.findall(r"\b(sb_[a-z0-9_]+)\s*\(", text)))
 
 
+def _preload_nccl():
+    """libsparkb200 resolves NCCL with dlopen("libnccl.so.2") when a communicator is first needed.  In a Python process that
+    also imports torch LATER, the loader would hand torch whatever libnccl.so.2 is already mapped -- the system copy (2.27) instead
+    of the newer one torch bundles and needs (undefined symbol ncclDevCommCreate).  Mapping torch's bundled copy first makes both
+    sides share it.  A JVM executor has no such neighbour and simply uses the system library."""
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia")
+        for base in (list(spec.submodule_search_locations) if spec and spec.submodule_search_locations else []):
+            cand = os.path.join(base, "nccl", "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                C.CDLL(cand, mode=C.RTLD_GLOBAL)
+                return cand
+    except Exception:
+        pass
+    return None
+
+
 def load():
     """dlopen libsparkb200.so and attach signatures.  Raises if the extension has not been built."""
     global _lib
     if _lib is None:
+        _preload_nccl()
         if not os.path.exists(LIB_PATH):
             raise SparkB200Error(-1, "libsparkb200.so is not built (run `python -m spark_b200.build`); there is no CPU fallback")
         lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
@@ -198,3 +219,16 @@ def config_get(key: str) -> int:
     v = _i64()
     check(load().sb_config_get(key.encode(), C.byref(v)))
     return int(v.value)
+
+
+def profile_dump() -> dict:
+    """{section: (total_ms, launches)} of every device-timed section since sb_profile_reset."""
+    buf = C.create_string_buffer(1 << 14)
+    check(load().sb_profile_dump(buf, len(buf)))
+    out = {}
+    for item in buf.value.decode().split(";"):
+        if "=" in item:
+            k, v = item.split("=")
+            ms, n = v.split("/")
+            out[k] = (float(ms), int(n))
+    return out

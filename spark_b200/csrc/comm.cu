@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "primitives.cuh"
 #include "rtc.cuh"
+#include "comm.cuh"
 
 namespace sb {
 
@@ -228,6 +229,44 @@ __global__ void ag_unpack_kernel(const __grid_constant__ AgPackArgs a, const uin
   for (int64_t i = threadIdx.x; i < bytes; i += blockDim.x) out[i] = msg[a.data_off[c] + i];
   if (a.dst_valid_bytes[c])
     for (int64_t i = threadIdx.x; i < a.rows[r]; i += blockDim.x) a.dst_valid_bytes[c][a.off[r] + i] = msg[a.valid_off[c] + i];
+}
+
+CommInfo comm_info() {
+  Comm &c = comm();
+  CommInfo i;
+  i.rank = c.rank;
+  i.nranks = c.nranks;
+  i.up = c.comm != nullptr;
+  return i;
+}
+void comm_allgather_host(const int64_t *mine, int64_t count, int64_t *all, cudaStream_t st) {
+  Comm &c = comm();
+  if (!c.comm) {
+    memcpy(all, mine, (size_t)count * 8);
+    return;
+  }
+  Scratch d_my(count * 8 + 8, st), d_all((int64_t)c.nranks * count * 8 + 8, st);
+  SB_CUDA(cudaMemcpyAsync(d_my.ptr, mine, (size_t)count * 8, cudaMemcpyHostToDevice, st));
+  SB_NCCL(nccl().AllGather(d_my.ptr, d_all.ptr, (size_t)count, ncclInt64, c.comm, st));
+  SB_CUDA(cudaMemcpyAsync(all, d_all.ptr, (size_t)c.nranks * count * 8, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaStreamSynchronize(st));
+}
+void comm_barrier_enqueue(cudaStream_t st) {
+  Comm &c = comm();
+  if (!c.comm) return;
+  Scratch a(8, st), b(8 * c.nranks, st);
+  SB_CUDA(cudaMemsetAsync(a.ptr, 0, 8, st));
+  SB_NCCL(nccl().AllGather(a.ptr, b.ptr, 1, ncclInt64, c.comm, st));
+  count_launch();
+}
+bool comm_window(size_t need, cudaStream_t st, std::vector<void *> &bases) {
+  Comm &c = comm();
+  if (!c.comm) return false;
+  if (!window_ensure(need, st)) return false;
+  PeerWindow &w = window();
+  bases.assign(c.nranks, nullptr);
+  for (int r = 0; r < c.nranks; r++) bases[r] = r == c.rank ? w.local : w.remote[r];
+  return true;
 }
 
 }  // namespace sb

@@ -22,6 +22,8 @@
 #include "primitives.cuh"
 #include "multisplit.cuh"
 #include "rtc.cuh"
+#include "comm.cuh"
+#include <memory>
 
 namespace sb {
 
@@ -820,6 +822,218 @@ static void partition_impl(const sb_table *in, const int32_t *key_cols, int32_t 
   *out = t;
 }
 
+// ---- fused exchange: the multisplit IS the transport ----------------------------------------------------------------------------
+// destination rank of every row (owner of its partition id: contiguous ownership ranges) + the per-tile histogram over ranks
+struct OwnerBounds { int32_t first[REMOTE_MAX_BUCKETS + 1]; };   // rank r owns partitions [first[r], first[r + 1])
+__global__ void __launch_bounds__(PDH_THREADS) owner_hist_kernel(const int32_t *__restrict__ pid, int64_t n, OwnerBounds ob, int32_t nranks, int64_t chunk,
+                                                                 int32_t *__restrict__ bucket, uint32_t *__restrict__ hist) {
+  __shared__ uint32_t sh[REMOTE_MAX_BUCKETS];
+  if (threadIdx.x < REMOTE_MAX_BUCKETS) sh[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t begin = (int64_t)blockIdx.x * chunk, end = begin + chunk < n ? begin + chunk : n;
+  for (int64_t i = begin + threadIdx.x; i < end; i += PDH_THREADS) {
+    const int32_t p = pid[i];
+    int d = 0;
+#pragma unroll 1
+    for (int r = 1; r < nranks; r++) d += p >= ob.first[r];
+    bucket[i] = d;
+    atomicAdd(&sh[d], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < nranks) hist[(int64_t)threadIdx.x * gridDim.x + blockIdx.x] = sh[threadIdx.x];
+}
+// local partition index (pid - first owned partition) of every received row + per-tile histogram in multisplit layout
+__global__ void __launch_bounds__(PDH_THREADS) local_pid_hist_kernel(const int32_t *__restrict__ pid, int64_t n, int32_t lo, int32_t nb, int64_t chunk,
+                                                                     int32_t *__restrict__ bucket, uint32_t *__restrict__ hist) {
+  extern __shared__ uint32_t lph_sh[];
+  for (int p = threadIdx.x; p < nb; p += PDH_THREADS) lph_sh[p] = 0;
+  __syncthreads();
+  const int64_t begin = (int64_t)blockIdx.x * chunk, end = begin + chunk < n ? begin + chunk : n;
+  for (int64_t i = begin + threadIdx.x; i < end; i += PDH_THREADS) {
+    const int32_t b = pid[i] - lo;
+    bucket[i] = b;
+    atomicAdd(&lph_sh[b], 1u);
+  }
+  __syncthreads();
+  for (int p = threadIdx.x; p < nb; p += PDH_THREADS) hist[(int64_t)p * gridDim.x + blockIdx.x] = lph_sh[p];
+}
+
+static inline int32_t owner_first(int32_t r, int32_t nparts, int32_t nranks) { return (int32_t)(((int64_t)r * nparts + nranks - 1) / nranks); }
+
+// Returns false when peer windows are unavailable (the caller falls back to sb_hash_partition + sb_all_to_all).
+static bool shuffle_exchange_impl(const sb_table *in, const int32_t *key_cols, int32_t nkeys, int32_t nparts, cudaStream_t st, sb_table **out,
+                                  int64_t *out_part_offsets_host) {
+  const CommInfo ci = comm_info();
+  const int R = ci.nranks, me = ci.rank;
+  SB_REQUIRE(ci.up, "sb_shuffle_exchange needs an initialised communicator (sb_comm_init)");
+  SB_REQUIRE(R <= REMOTE_MAX_BUCKETS, "the fused exchange supports up to %d ranks", REMOTE_MAX_BUCKETS);
+  SB_REQUIRE(nparts >= 1 && nparts <= MULTISPLIT_MAX_BUCKETS, "num_partitions out of range");
+  const int64_t n = in->nrows;
+  SB_REQUIRE(n < 0xFFFFFFFFll, "tables of 2^32 rows or more must be exchanged in chunks");
+  for (auto &c : in->cols)
+    if (c.type == SB_STRING) fail(SB_ERR_UNSUPPORTED, "the fused exchange moves fixed-width columns (string columns: sb_hash_partition + sb_all_to_all)");
+  OwnerBounds ob;
+  for (int r = 0; r <= R; r++) ob.first[r] = owner_first(r, nparts, R);
+  // 1. partition ids, destination ranks, per-tile histogram over the ranks
+  KeyCols keys = make_keys(in, key_cols, nkeys);
+  int64_t rowbytes = 4;
+  for (auto &c : in->cols) rowbytes += type_width(c.type);
+  const PartGeometry g = part_geometry(n, R, rowbytes >= 32);
+  Scratch pid(n * 4 + 16, st), dest(n * 4 + 16, st), hist((int64_t)R * g.nblocks * 4 + 16, st), offs_dev((R + 1) * 8, st);
+  if (n > 0) {
+    const PartGeometry gp = part_geometry(n, nparts);
+    pid_hist_kernel<<<gp.nblocks, PART_THREADS, 0, st>>>(keys, n, nparts, gp.chunk, pid.as<int32_t>(), nullptr, 0, 0);
+    SB_LAUNCH_CHECK();
+    owner_hist_kernel<<<g.nblocks, PDH_THREADS, 0, st>>>(pid.as<int32_t>(), n, ob, R, g.chunk, dest.as<int32_t>(), hist.as<uint32_t>());
+    SB_LAUNCH_CHECK();
+  } else SB_CUDA(cudaMemsetAsync(hist.ptr, 0, (size_t)R * g.nblocks * 4, st));
+  exclusive_scan_i32((const int32_t *)hist.ptr, (int32_t *)hist.ptr, (int64_t)R * g.nblocks, nullptr, st);
+  part_offsets_kernel<<<(R + 1 + 255) / 256, 256, 0, st>>>(hist.as<uint32_t>(), R, g.nblocks, n, offs_dev.as<int64_t>());
+  SB_LAUNCH_CHECK();
+  std::vector<int64_t> lstart(R + 1);
+  SB_CUDA(cudaMemcpyAsync(lstart.data(), offs_dev.ptr, (size_t)(R + 1) * 8, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaStreamSynchronize(st));
+  // 2. everybody learns everybody's send counts: C[src][dst].  A rank whose column carries no bitmap still has to agree on the
+  //    layout, so "nullable" is decided over all ranks (bit mask in the last word, like sb_all_to_all)
+  SB_REQUIRE(in->cols.size() <= 62, "the exchange supports up to 62 columns");
+  std::vector<int64_t> mine(R + 1), all((size_t)R * (R + 1));
+  for (int d = 0; d < R; d++) mine[d] = lstart[d + 1] - lstart[d];
+  uint64_t my_mask = 0;
+  for (size_t ci2 = 0; ci2 < in->cols.size(); ci2++)
+    if (in->cols[ci2].validity) my_mask |= 1ull << ci2;
+  mine[R] = (int64_t)my_mask;
+  comm_allgather_host(mine.data(), R + 1, all.data(), st);
+  uint64_t any_mask = 0;
+  for (int r = 0; r < R; r++) any_mask |= (uint64_t)all[(size_t)r * (R + 1) + R];
+  auto C = [&](int src, int dst) { return all[(size_t)src * (R + 1) + dst]; };
+  std::vector<int64_t> T(R, 0);
+  for (int d = 0; d < R; d++)
+    for (int sr = 0; sr < R; sr++) T[d] += C(sr, d);
+  // 3. window layout of a receiver holding `rows` rows: data columns, the partition-id column, one validity byte column per
+  //    nullable column; every piece 256-byte aligned
+  struct Piece { int width; const void *src; int col; bool is_valid; };
+  std::vector<Piece> pieces;
+  std::vector<std::unique_ptr<Scratch>> temps;
+  for (size_t i = 0; i < in->cols.size(); i++) pieces.push_back({type_width(in->cols[i].type), in->cols[i].d(), (int)i, false});
+  pieces.push_back({4, pid.ptr, -1, false});
+  for (size_t i = 0; i < in->cols.size(); i++)
+    if ((any_mask >> i) & 1) {
+      Scratch *vb = new Scratch(n + 16, st);
+      temps.emplace_back(vb);
+      bitmap_to_bytes(in->cols[i].v(), n, vb->as<uint8_t>(), st);   // no bitmap on this rank: all ones
+      pieces.push_back({1, vb->ptr, (int)i, true});
+    }
+  auto layout = [&](int64_t rows, std::vector<size_t> &off) {
+    size_t cur = 0;
+    off.resize(pieces.size());
+    for (size_t k = 0; k < pieces.size(); k++) {
+      off[k] = cur;
+      cur += ((size_t)rows * pieces[k].width + 255) / 256 * 256;
+    }
+    return cur;
+  };
+  size_t need = 0;
+  std::vector<std::vector<size_t>> offs_of(R);
+  for (int d = 0; d < R; d++) need = std::max(need, layout(T[d], offs_of[d]));
+  std::vector<void *> bases;
+  if (!comm_window(need, st, bases)) return false;
+  // 4. the scatter: every destination's run is stored straight into that rank's window (remote stores over NVLink); rows from
+  //    source rank s occupy [roff, roff + C[s][d]) of every piece, in arrival order
+  if (n > 0) {
+    const bool big = g.chunk == RG_TILE_BIG;
+    static std::once_flag once;
+    std::call_once(once, [] {
+      SB_CUDA(cudaFuncSetAttribute(regroup_tma_kernel<512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RGT_STAGES * RG_TILE_SMALL * 8));
+      SB_CUDA(cudaFuncSetAttribute(regroup_tma_kernel<1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RGT_STAGES * RG_TILE_BIG * 8));
+    });
+    const int bps = big ? 1 : 2;
+    const int grid = g.nblocks < rt().num_sms * bps ? g.nblocks : rt().num_sms * bps;
+    KernelTimer kt("exchange_scatter", st);
+    for (size_t done = 0; done < pieces.size();) {
+      RegroupCols rc;
+      memset(&rc, 0, sizeof(rc));
+      std::vector<uint64_t> hp;
+      while (done < pieces.size() && rc.ncols < SCATTER_MAX_COLS) {
+        const Piece &pc = pieces[done];
+        const int k = rc.ncols++;
+        rc.width[k] = pc.width;
+        rc.src[k] = pc.src;
+        for (int d = 0; d < R; d++) {
+          int64_t roff = 0;
+          for (int sr = 0; sr < me; sr++) roff += C(sr, d);
+          // biased so that global sorted position g of the LOCAL bucket order lands at window position roff + (g - lstart[d])
+          const intptr_t addr = (intptr_t)bases[d] + (intptr_t)offs_of[d][done] + (intptr_t)(roff - lstart[d]) * pc.width;
+          hp.push_back((uint64_t)addr);
+        }
+        done++;
+      }
+      Scratch *dp = new Scratch((int64_t)hp.size() * 8 + 8, st);
+      temps.emplace_back(dp);
+      SB_CUDA(cudaMemcpyAsync(dp->ptr, hp.data(), hp.size() * 8, cudaMemcpyHostToDevice, st));
+      SB_CUDA(cudaStreamSynchronize(st));   // hp is a temporary
+      if (big)
+        regroup_tma_kernel<1024, true><<<grid, 1024, RGT_STAGES * RG_TILE_BIG * 8, st>>>(rc, dest.as<int32_t>(), hist.as<uint32_t>(), n, R, (int64_t)g.nblocks,
+                                                                                         nullptr, 0, dp->as<uint64_t>());
+      else
+        regroup_tma_kernel<512, true><<<grid, 512, RGT_STAGES * RG_TILE_SMALL * 8, st>>>(rc, dest.as<int32_t>(), hist.as<uint32_t>(), n, R, (int64_t)g.nblocks,
+                                                                                        nullptr, 0, dp->as<uint64_t>());
+      SB_LAUNCH_CHECK();
+    }
+  }
+  // 5. every rank's stores have landed once every rank has passed this point on its stream
+  comm_barrier_enqueue(st);
+  // 6. receiver side: split the window's rows (grouped by source rank) into the owned partitions -- the second, local pass
+  const int64_t nrecv = T[me];
+  const int32_t lo = ob.first[me], hi = ob.first[me + 1], nb2 = hi - lo;
+  const uint8_t *win = (const uint8_t *)bases[me];
+  const std::vector<size_t> &woff = offs_of[me];
+  sb_table *t = table_new(nrecv);
+  try {
+    std::vector<SplitCol> sc;
+    std::vector<std::pair<size_t, Scratch *>> vbytes;   // (column, received validity bytes in output order)
+    for (size_t i = 0; i < in->cols.size(); i++) {
+      const Column &c = in->cols[i];
+      Column r = column_alloc(c.type, c.scale, nrecv, ((any_mask >> i) & 1) != 0, st);
+      t->cols.push_back(r);
+      sc.push_back({type_width(c.type), win + woff[i], r.data->ptr, nullptr, nullptr});
+    }
+    const size_t pid_piece = in->cols.size();
+    for (size_t k = pid_piece + 1; k < pieces.size(); k++) {
+      Scratch *vb = new Scratch(nrecv + 16, st);
+      temps.emplace_back(vb);
+      vbytes.push_back({(size_t)pieces[k].col, vb});
+      sc.push_back({1, win + woff[k], vb->ptr, nullptr, nullptr});
+    }
+    std::vector<int64_t> offs2((size_t)std::max(nb2, 1) + 1, 0);
+    if (nrecv > 0 && nb2 > 0) {
+      const PartGeometry g2 = part_geometry(nrecv, nb2, rowbytes >= 32 && nb2 >= 64);
+      Scratch bucket2(nrecv * 4 + 16, st), hist2((int64_t)nb2 * g2.nblocks * 4 + 16, st), offs2_dev((int64_t)(nb2 + 1) * 8, st);
+      static bool attr = false;
+      if (!attr) {
+        SB_CUDA(cudaFuncSetAttribute(local_pid_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        attr = true;
+      }
+      local_pid_hist_kernel<<<g2.nblocks, PDH_THREADS, (size_t)nb2 * 4, st>>>((const int32_t *)(win + woff[pid_piece]), nrecv, lo, nb2, g2.chunk,
+                                                                            bucket2.as<int32_t>(), hist2.as<uint32_t>());
+      SB_LAUNCH_CHECK();
+      multisplit_scatter(bucket2.as<int32_t>(), hist2.as<uint32_t>(), nb2, g2, sc.data(), (int)sc.size(), nrecv, nullptr, offs2_dev.as<int64_t>(), st);
+      SB_CUDA(cudaMemcpyAsync(offs2.data(), offs2_dev.ptr, (size_t)(nb2 + 1) * 8, cudaMemcpyDeviceToHost, st));
+    }
+    for (auto &vb : vbytes) bytes_to_bitmap(vb.second->as<uint8_t>(), nrecv, (uint32_t *)t->cols[vb.first].validity->ptr, st);
+    SB_CUDA(cudaStreamSynchronize(st));
+    out_part_offsets_host[0] = 0;
+    for (int p = 0; p < nparts; p++) {
+      const int64_t rows = (p >= lo && p < hi) ? offs2[p - lo + 1] - offs2[p - lo] : 0;
+      out_part_offsets_host[p + 1] = out_part_offsets_host[p] + rows;
+    }
+  } catch (...) {
+    table_free(t);
+    throw;
+  }
+  *out = t;
+  return true;
+}
+
 }  // namespace sb
 
 using namespace sb;
@@ -848,6 +1062,26 @@ int sb_hash_partition(const sb_table *in, const int32_t *key_cols, int32_t nkeys
   SB_API_BEGIN
   require_init();
   partition_impl(in, key_cols, nkeys, num_partitions, 0, 0, stream_of(s), out, out_offsets_host);
+  SB_API_END
+}
+
+// ShuffleExchangeExec with HashPartitioning in ONE call: map side and transport fused (see shuffle_exchange_impl).  Falls back to
+// sb_hash_partition + sb_all_to_all when peer windows cannot be mapped.
+int sb_shuffle_exchange(const sb_table *in, const int32_t *key_cols, int32_t nkeys, int32_t num_partitions, sb_stream *s, sb_table **out,
+                        int64_t *out_part_offsets_host) {
+  SB_API_BEGIN
+  require_init();
+  SB_REQUIRE(in && out && out_part_offsets_host, "null argument");
+  bool has_string = false;
+  for (auto &c : in->cols) has_string |= c.type == SB_STRING;
+  if (!has_string && !config().exchange_nccl && shuffle_exchange_impl(in, key_cols, nkeys, num_partitions, stream_of(s), out, out_part_offsets_host))
+    return SB_OK;
+  sb_table *parted = nullptr;
+  std::vector<int64_t> offs((size_t)num_partitions + 1);
+  partition_impl(in, key_cols, nkeys, num_partitions, 0, 0, stream_of(s), &parted, offs.data());
+  const int rc = sb_all_to_all(parted, offs.data(), num_partitions, s, out, out_part_offsets_host);
+  sb_table_release(parted);
+  if (rc != SB_OK) return rc;
   SB_API_END
 }
 

@@ -175,6 +175,19 @@ extern "C" int sb_profile_reset(void) {
   g_prof_totals.clear();
   return SB_OK;
 }
+// every timed section since the last reset as "name=ms/launches;..." (truncated to len)
+extern "C" int sb_profile_dump(char *buf, int32_t len) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  prof_drain();
+  std::string out;
+  for (auto &x : g_prof_totals) {
+    char tmp[160];
+    snprintf(tmp, sizeof(tmp), "%s=%.6f/%lld;", x.name.c_str(), x.ms, (long long)x.launches);
+    out += tmp;
+  }
+  if (buf && len > 0) snprintf(buf, (size_t)len, "%s", out.c_str());
+  return SB_OK;
+}
 extern "C" int sb_profile_get(const char *kernel_name, double *out_total_ms, int64_t *out_launches) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
   prof_drain();

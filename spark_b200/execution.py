@@ -302,11 +302,14 @@ class ShuffleExchangeExec(SparkPlan):
     (sb_comm_init done, world size > 1) the buckets are exchanged with the NCCL all-to-all and the
     result holds the partitions this rank owns (partition p -> rank p % world)."""
 
-    def __init__(self, outputPartitioning, child: SparkPlan):
+    def __init__(self, outputPartitioning, child: SparkPlan, fused=None):
         self.outputPartitioning = outputPartitioning
         self.child = child
         self.children = (child,)
         self.partition_offsets = None
+        # fused: map side and transport in one call (sb_shuffle_exchange: the multisplit's stores go straight into the owners'
+        # receive windows over NVLink).  None = whenever more than one rank is up and the partitioning is a hash partitioning.
+        self.fused = fused
 
     def executeColumnar(self, stream=None):
         inp = self.child.executeColumnar(stream)
@@ -335,9 +338,19 @@ class ShuffleExchangeExec(SparkPlan):
 
     def run(self, inp: ColumnarBatch, stream=None) -> ColumnarBatch:
         lib = capi.load()
-        part, offs = self.map_side(inp, stream)
         rank, world = C.c_int32(), C.c_int32()
         capi.check(lib.sb_comm_rank(C.byref(rank), C.byref(world)))
+        p = self.outputPartitioning
+        if isinstance(p, HashPartitioning) and (self.fused or (self.fused is None and world.value > 1)):
+            n = p.numPartitions
+            idx = [inp.column_index(k) for k in p.expressions]
+            arr = (C.c_int32 * max(1, len(idx)))(*idx)
+            out_offs = (C.c_int64 * (n + 1))()
+            h = C.c_void_p()
+            capi.check(lib.sb_shuffle_exchange(inp.handle, arr, len(idx), n, _h(stream), C.byref(h), out_offs))
+            self.partition_offsets = np.array(list(out_offs), dtype=np.int64)
+            return ColumnarBatch(h, inp.names, inp.arrow_types)
+        part, offs = self.map_side(inp, stream)
         if world.value <= 1:
             self.partition_offsets = offs
             return part

@@ -293,3 +293,27 @@ def test_exchange_statistics_and_coalesced_read(one_rank_comm, stream):
         rows += b.to_arrow(stream).column("row").to_pylist()
         b.close()
     assert sorted(rows) == list(range(n))
+
+
+@pytest.mark.parametrize("nparts", [1, 7, 200, 2048])
+def test_fused_exchange_on_a_one_rank_communicator(one_rank_comm, stream, nparts):
+    """sb_shuffle_exchange (the multisplit's stores go straight into the receive window, then one local split) on a one-rank NCCL
+    communicator: the window, the REMOTE scatter kernel, the barrier and the receiver-side split all run; the rank owns every
+    partition, so the result is the oracle's shuffle: partition-contiguous, arrival order kept inside a partition, NULLs intact."""
+    from spark_b200.columnar import ColumnarBatch
+    from spark_b200.execution import HashPartitioning, LocalTableScanExec, ShuffleExchangeExec
+    rng = np.random.default_rng(nparts)
+    n = 250_013
+    t = pa.table({"k": pa.array(rng.integers(0, 60_000, n), mask=rng.random(n) < 0.03),
+                  "d": pa.array(rng.integers(8000, 9000, n).astype(np.int32)).cast(pa.date32()),
+                  "v": pa.array(rng.random(n), mask=rng.random(n) < 0.05),
+                  "f": rng.integers(0, 3, n).astype(np.int8), "w": rng.integers(0, 1000, n).astype(np.int16), "row": np.arange(n, dtype=np.int64)})
+    batch = ColumnarBatch.from_arrow(t, stream)
+    ex = ShuffleExchangeExec(HashPartitioning(["k", "d"], nparts), LocalTableScanExec(batch), fused=True)
+    got = ex.executeColumnar(stream).to_arrow(stream)
+    offs = ex.partition_offsets
+    pid = O.partition_ids(t, ["k", "d"], nparts)
+    want = t.take(pa.array(np.argsort(pid, kind="stable")))
+    assert offs[0] == 0 and offs[-1] == n and np.array_equal(np.diff(offs), np.bincount(pid, minlength=nparts))
+    assert got.column("row").to_pylist() == want.column("row").to_pylist()
+    assert_tables_equal(got, want, ordered=True)
