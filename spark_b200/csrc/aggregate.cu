@@ -765,7 +765,9 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
 
   // ---- launch geometry -------------------------------------------------------------------------------------
   int64_t cap_max = next_pow2(n > 512 ? 2 * n : 1024);
-  int64_t cap = plan->expected_groups > 0 ? next_pow2(4 * plan->expected_groups) : (1 << 18);   // no hint: 128K groups before the first retry
+  // no hint: 128K groups before the first retry -- except for inputs small enough that a table for "every row its own group"
+  // costs less to clear than a failed attempt costs to run (the join outputs Q3 / Q5 aggregate, a Final over Partial rows)
+  int64_t cap = plan->expected_groups > 0 ? next_pow2(4 * plan->expected_groups) : (n <= (1 << 23) ? cap_max : (1 << 18));
   if (cap < 1024) cap = 1024;
   if (cap > cap_max) cap = cap_max;
   auto dict_smem = [&](int d) { return (size_t)(d + 1 + (size_t)(d + 1) * ns * AGG_THREADS) * 8; };

@@ -22,7 +22,9 @@
 #include <memory>
 #include "common.cuh"
 #include "expr.cuh"
+#include "simple_pred.cuh"
 #include "primitives.cuh"
+#include "rtc.cuh"
 
 struct sb_hash_table {
   sb_table *build = nullptr;        // retained build-side batch (payload gathered at probe time)
@@ -34,8 +36,17 @@ struct sb_hash_table {
   int32_t key_bits[4];
   int32_t key_shift[4];
   int32_t *null_key_flag = nullptr;   // device: set when a build row had a NULL key (null-aware anti join)
-  uint32_t *bloom = nullptr;          // blocked Bloom filter over the build keys: one 32-bit word per key hash, 3 bits set
-  uint64_t bloom_mask = 0;            // words - 1 (power of two); sized to stay resident in L2 (<= 64 MB)
+  // prefilter in front of the table, one of:
+  //   exact  -- a bitmap over [fmin, fmin + frange) of the packed key: bit (key - fmin) set <=> the key is in the relation.  Chosen
+  //             when the key range is dense enough (<= 64 bits per key); the analogue of LongToUnsafeRowMap's dense mode
+  //             (SQLX/joins/HashedRelation.scala:535-1010, optimize()), used as a filter in front of the open-addressing table.
+  //             A streamed side clustered on the key (lineitem by l_orderkey) walks it sequentially.
+  //   Bloom  -- blocked: one 32-bit word per key hash, 3 bits set; at most 64 MB so that it stays L2-resident
+  uint32_t *bloom = nullptr;
+  uint64_t bloom_mask = 0;            // Bloom: words - 1 (power of two)
+  int exact = 0;
+  uint64_t fmin = 0, frange = 0;
+  int64_t nkeys_in = 0;               // build rows that entered the relation (filter TRUE, keys not NULL)
   cudaStream_t st = nullptr;
 };
 
@@ -91,6 +102,22 @@ __device__ __forceinline__ uint32_t bloom_bits(uint64_t h) {
 }
 __device__ __forceinline__ uint64_t bloom_word(uint64_t h, uint64_t mask) { return (h >> 20) & mask; }
 
+struct KeyFilter {
+  const uint32_t *words;
+  uint64_t mask, fmin, frange;
+  int exact;
+};
+__device__ __forceinline__ bool filter_test(const KeyFilter &f, uint64_t key) {
+  if (!f.words) return true;
+  if (f.exact) {
+    const uint64_t d = key - f.fmin;
+    return d < f.frange && ((__ldg(&f.words[d >> 5]) >> (d & 31)) & 1u);
+  }
+  const uint64_t hh = join_mix(key);
+  const uint32_t bb = bloom_bits(hh);
+  return (__ldg(&f.words[bloom_word(hh, f.mask)]) & bb) == bb;
+}
+
 typedef sb_hash_table::Slot JoinSlot;
 __device__ __forceinline__ void load_slot(const JoinSlot *p, uint64_t &key, uint32_t &row) {
   const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(p);
@@ -100,7 +127,7 @@ __device__ __forceinline__ void load_slot(const JoinSlot *p, uint64_t &key, uint
 
 __global__ void __launch_bounds__(JOIN_THREADS) join_build_kernel(JoinKeys k, int64_t n, JoinSlot *__restrict__ slots, int64_t cap,
                                                                   int32_t *__restrict__ null_key_flag, const uint8_t *__restrict__ row_mask,
-                                                                  uint32_t *__restrict__ bloom, uint64_t bloom_mask) {
+                                                                  KeyFilter kf) {
   int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= n) return;
   if (row_mask && !row_mask[row]) return;   // fused FilterExec below the build side: the row is not part of the relation
@@ -112,7 +139,11 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_build_kernel(JoinKeys k, in
   uint64_t mask = (uint64_t)cap - 1;
   const uint64_t hh = join_mix(key);
   uint64_t h = hh & mask;
-  if (bloom) atomicOr(&bloom[bloom_word(hh, bloom_mask)], bloom_bits(hh));
+  uint32_t *fw = const_cast<uint32_t *>(kf.words);
+  if (kf.exact) {
+    const uint64_t d = key - kf.fmin;
+    atomicOr(&fw[d >> 5], 1u << (d & 31));
+  } else if (fw) atomicOr(&fw[bloom_word(hh, kf.mask)], bloom_bits(hh));
   for (;;) {
     if (slots[h].row == FREE_SLOT && atomicCAS(&slots[h].row, FREE_SLOT, (uint32_t)row) == FREE_SLOT) {
       slots[h].key = key;
@@ -126,7 +157,7 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_build_kernel(JoinKeys k, in
 __global__ void __launch_bounds__(JOIN_THREADS) join_count_kernel(JoinKeys k, int64_t n, const JoinSlot *__restrict__ slots, int64_t cap,
                                                                   int join_type, int null_aware, int32_t *__restrict__ counts, uint32_t *__restrict__ first,
                                                                   int32_t *__restrict__ block_counts, uint8_t *__restrict__ matched,
-                                                                  const uint8_t *__restrict__ row_mask, const uint32_t *__restrict__ bloom, uint64_t bloom_mask,
+                                                                  const uint8_t *__restrict__ row_mask, KeyFilter kf,
                                                                   const int64_t *__restrict__ rows) {
   __shared__ int32_t wsum[JOIN_THREADS / 32];
   // `rows` (optional): the candidate list of join_candidate_kernel -- item i stands for streamed row rows[i]; counts / first are
@@ -143,8 +174,7 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_count_kernel(JoinKeys k, in
       uint64_t mask = (uint64_t)cap - 1;
       const uint64_t hh = join_mix(key);
       uint64_t h = hh & mask;
-      const uint32_t bb = bloom_bits(hh);
-      if (!bloom || (__ldg(&bloom[bloom_word(hh, bloom_mask)]) & bb) == bb) {
+      if (filter_test(kf, key)) {
         for (;;) {
           uint64_t sk;
           uint32_t r;
@@ -233,26 +263,141 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_fill_kernel(JoinKeys k, int
   }
 }
 
-// Selective joins over a long streamed side (Q3: 600 M lineitem rows, one in twenty survives filter + Bloom test): one pass over
-// (filter mask, key, Bloom word) marks the rows that can produce output at all; only those -- as a compacted row list -- go through
-// the count / fill passes with their per-row bookkeeping.  needs_key: inner / semi joins drop NULL-key and Bloom-negative rows here;
-// outer / anti joins keep every row the filter keeps (those rows are output even without a partner).
-__global__ void __launch_bounds__(JOIN_THREADS) join_candidate_kernel(JoinKeys k, int64_t n, const uint8_t *__restrict__ row_mask,
-                                                                      const uint32_t *__restrict__ bloom, uint64_t bloom_mask, int needs_key,
-                                                                      uint8_t *__restrict__ out) {
-  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= n) return;
-  bool c = !row_mask || row_mask[row];
-  if (c && needs_key) {
-    uint64_t key;
-    c = join_key(k, row, key);
-    if (c && bloom) {
-      const uint64_t hh = join_mix(key);
-      const uint32_t bb = bloom_bits(hh);
-      c = (__ldg(&bloom[bloom_word(hh, bloom_mask)]) & bb) == bb;
+// Selective joins over a long streamed side (Q3: 600 M lineitem rows, one in twenty survives filter + prefilter): ONE pass over
+// (pushed-down filter, key, prefilter word) marks the rows that can produce output at all; only those -- as a compacted row list --
+// go through the count / fill passes with their per-row bookkeeping.  A thread owns 16 consecutive rows (16-byte loads), writes
+// their verdicts as one 16-bit word and the block leaves its candidate count for the scan, so the list is produced by one more
+// pass over 1 bit per row.  needs_key: inner / semi joins drop NULL-key and prefilter-negative rows here; outer / anti joins keep
+// every row the filter keeps (those rows are output even without a partner).
+constexpr int CAND_ROWS = SP_ROWS;
+constexpr int CAND_TILE = JOIN_THREADS * CAND_ROWS;
+__global__ void __launch_bounds__(JOIN_THREADS) join_candidate_kernel(JoinKeys k, int64_t n, const __grid_constant__ SimplePred sp,
+                                                                      const uint8_t *__restrict__ row_mask, KeyFilter kf, int needs_key,
+                                                                      int fast_key, uint16_t *__restrict__ bits_out,
+                                                                      int32_t *__restrict__ block_counts) {
+  __shared__ int32_t wsum[JOIN_THREADS / 32];
+  const int64_t row0 = ((int64_t)blockIdx.x * JOIN_THREADS + threadIdx.x) * CAND_ROWS;
+  uint32_t keep = 0;
+  if (row0 < n) {
+    keep = row0 + CAND_ROWS <= n ? 0xFFFFu : (1u << (int)(n - row0)) - 1u;
+    if (sp.nterms > 0) keep &= simple_pred_eval16(sp, row0, n);
+    if (row_mask) {
+      uint32_t mbits = 0;
+      if (row0 + CAND_ROWS <= n) {   // scratch masks are 16-byte aligned and row0 is a multiple of 16
+        const uint4 q = __ldg(reinterpret_cast<const uint4 *>(row_mask + row0));
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int j = 0; j < CAND_ROWS; j++) mbits |= (((w[j >> 2] >> (8 * (j & 3))) & 0xFFu) ? 1u : 0u) << j;
+      } else {
+        for (int j = 0; row0 + j < n; j++) mbits |= (row_mask[row0 + j] ? 1u : 0u) << j;
+      }
+      keep &= mbits;
     }
+    if (needs_key) {
+      uint64_t key[CAND_ROWS];
+      if (fast_key) {   // one NULL-free integer key column: the 16 keys arrive as 16-byte loads whatever `keep` says
+        int64_t x[CAND_ROWS];
+        switch (k.type[0]) {
+          case SB_INT8: sp_load16<int8_t>(k.data[0], row0, n, x); break;
+          case SB_INT16: sp_load16<int16_t>(k.data[0], row0, n, x); break;
+          case SB_INT32: case SB_DATE32: sp_load16<int32_t>(k.data[0], row0, n, x); break;
+          default: sp_load16<int64_t>(k.data[0], row0, n, x); break;
+        }
+        const uint64_t km = k.bits[0] < 64 ? (1ull << k.bits[0]) - 1 : ~0ull;
+#pragma unroll
+        for (int j = 0; j < CAND_ROWS; j++) key[j] = (uint64_t)x[j] & km;
+      } else {
+        uint32_t has = 0;
+#pragma unroll
+        for (int j = 0; j < CAND_ROWS; j++) {
+          key[j] = 0;
+          if (((keep >> j) & 1u) && join_key(k, row0 + j, key[j])) has |= 1u << j;
+        }
+        keep &= has;
+      }
+      if (kf.words) {
+        uint32_t pass = 0;
+#pragma unroll
+        for (int j = 0; j < CAND_ROWS; j++)
+          if (((keep >> j) & 1u) && filter_test(kf, key[j])) pass |= 1u << j;
+        keep = pass;
+      }
+    }
+    bits_out[row0 / CAND_ROWS] = (uint16_t)keep;
   }
-  out[row] = c;
+  int32_t t = __reduce_add_sync(0xffffffffu, __popc(keep));
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int32_t b = 0;
+#pragma unroll
+    for (int w = 0; w < JOIN_THREADS / 32; w++) b += wsum[w];
+    block_counts[blockIdx.x] = b;
+  }
+}
+
+// the candidate list in row order: same tiling as join_candidate_kernel, block_offsets = exclusive scan of its block counts
+__global__ void __launch_bounds__(JOIN_THREADS) candidate_rows_kernel(const uint16_t *__restrict__ bits, int64_t nwords,
+                                                                      const int64_t *__restrict__ block_offsets, int64_t *__restrict__ rows) {
+  __shared__ int32_t wsum[JOIN_THREADS / 32];
+  const int64_t t = (int64_t)blockIdx.x * JOIN_THREADS + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t b = t < nwords ? bits[t] : 0u;
+  const int32_t c = __popc(b);
+  int32_t x = c;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int32_t y = __shfl_up_sync(0xffffffffu, x, d);
+    if (lane >= d) x += y;
+  }
+  if (lane == 31) wsum[warp] = x;
+  __syncthreads();
+  int32_t woff = 0;
+  for (int w = 0; w < warp; w++) woff += wsum[w];
+  int64_t o = block_offsets[blockIdx.x] + woff + (x - c);
+  const int64_t row0 = t * CAND_ROWS;
+  while (b) {
+    const int j = __ffs(b) - 1;
+    b &= b - 1;
+    rows[o++] = row0 + j;
+  }
+}
+
+// what the relation will hold: packed-key range and row count of the build rows that pass the filter with non-NULL keys
+__global__ void __launch_bounds__(JOIN_THREADS) build_stats_kernel(JoinKeys k, int64_t n, const uint8_t *__restrict__ row_mask,
+                                                                   long long *__restrict__ stats) {
+  long long lo = 0x7FFFFFFFFFFFFFFFll, hi = -0x7FFFFFFFFFFFFFFFll - 1, cnt = 0;
+  for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += (int64_t)gridDim.x * blockDim.x) {
+    if (row_mask && !row_mask[row]) continue;
+    uint64_t key;
+    if (!join_key(k, row, key)) continue;
+    const long long v = (long long)key;
+    lo = v < lo ? v : lo;
+    hi = v > hi ? v : hi;
+    cnt++;
+  }
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) {
+    const long long l2 = __shfl_xor_sync(0xffffffffu, lo, d), h2 = __shfl_xor_sync(0xffffffffu, hi, d);
+    lo = l2 < lo ? l2 : lo;
+    hi = h2 > hi ? h2 : hi;
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+  }
+  if ((threadIdx.x & 31) == 0 && cnt > 0) {
+    atomicMin(&stats[0], lo);
+    atomicMax(&stats[1], hi);
+    atomicAdd((unsigned long long *)&stats[2], (unsigned long long)cnt);
+  }
+}
+
+static KeyFilter key_filter_of(const sb_hash_table *ht) {
+  KeyFilter f;
+  f.words = ht->bloom;
+  f.mask = ht->bloom_mask;
+  f.fmin = ht->fmin;
+  f.frange = ht->frange;
+  f.exact = ht->exact;
+  return f;
 }
 
 static JoinKeys make_join_keys(const sb_table *t, const int32_t *key_cols, int32_t nkeys, const sb_hash_table *ht) {
@@ -311,12 +456,34 @@ int sb_join_build_filtered(const sb_table *build, const int32_t *key_cols, int32
     ht->key_bits[i] = k.bits[i];
     ht->key_shift[i] = k.shift[i];
   }
+  // size everything by what will actually be inserted: one pass over the keys (and the fused filter's mask)
+  long long stats[3] = {0x7FFFFFFFFFFFFFFFll, -0x7FFFFFFFFFFFFFFFll - 1, 0};
+  if (n > 0) {
+    Scratch dstats(32, st);
+    SB_CUDA(cudaMemcpyAsync(dstats.ptr, stats, 24, cudaMemcpyHostToDevice, st));
+    int64_t g = (n + JOIN_THREADS * 8 - 1) / (JOIN_THREADS * 8);
+    if (g > (int64_t)rt().num_sms * 16) g = (int64_t)rt().num_sms * 16;
+    build_stats_kernel<<<(unsigned)g, JOIN_THREADS, 0, st>>>(k, n, filter ? mask.as<uint8_t>() : nullptr, dstats.as<long long>());
+    SB_LAUNCH_CHECK();
+    SB_CUDA(cudaMemcpyAsync(stats, dstats.ptr, 24, cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaStreamSynchronize(st));
+  }
+  const int64_t nin = stats[2];
+  ht->nkeys_in = nin;
   int64_t cap = 1024;
-  while (cap < 2 * n) cap <<= 1;
+  while (cap < 2 * nin) cap <<= 1;
   ht->cap = cap;
   int64_t bwords = 1024;
-  while (bwords < n && bwords < (16ll << 20)) bwords <<= 1;   // ~1 key per 32-bit word, at most 64 MB (L2-resident)
-  ht->bloom_mask = (uint64_t)bwords - 1;
+  const uint64_t range = nin > 0 ? (uint64_t)stats[1] - (uint64_t)stats[0] + 1 : 0;
+  if (nin > 0 && range != 0 && range <= (1ull << 31) && (range <= (1ull << 23) || range <= 64ull * (uint64_t)nin)) {
+    ht->exact = 1;
+    ht->fmin = (uint64_t)stats[0];
+    ht->frange = range;
+    bwords = (int64_t)(range / 32 + 1);
+  } else {
+    while (bwords < nin && bwords < (16ll << 20)) bwords <<= 1;   // ~1 key per 32-bit word, at most 64 MB (L2-resident)
+    ht->bloom_mask = (uint64_t)bwords - 1;
+  }
   try {
     SB_CUDA(cudaMallocAsync((void **)&ht->slots, (size_t)cap * sizeof(JoinSlot), st));
     SB_CUDA(cudaMemsetAsync(ht->slots, 0xff, (size_t)cap * sizeof(JoinSlot), st));
@@ -327,7 +494,7 @@ int sb_join_build_filtered(const sb_table *build, const int32_t *key_cols, int32
     if (n > 0) {
       KernelTimer kt("join_build", st);
       join_build_kernel<<<(unsigned)((n + JOIN_THREADS - 1) / JOIN_THREADS), JOIN_THREADS, 0, st>>>(
-          k, n, ht->slots, cap, ht->null_key_flag, filter ? mask.as<uint8_t>() : nullptr, ht->bloom, ht->bloom_mask);
+          k, n, ht->slots, cap, ht->null_key_flag, filter ? mask.as<uint8_t>() : nullptr, key_filter_of(ht));
       SB_LAUNCH_CHECK();
     }
     ht->build = const_cast<sb_table *>(build);
@@ -450,37 +617,54 @@ int sb_join_probe_ex(const sb_hash_table *ht, const sb_table *probe, const int32
   }
   const bool pairs = kt_type == SB_JOIN_INNER || kt_type == SB_JOIN_LEFT_OUTER;
   unsigned nb = (unsigned)((n + JOIN_THREADS - 1) / JOIN_THREADS);
-  Scratch counts(n * 4 + 16, st), first(n * 4 + 16, st), block_counts((int64_t)nb * 4 + 16, st), offsets((int64_t)nb * 8 + 16, st), total(16, st);
+  Scratch total(16, st);
   Scratch matched(build_rows_too ? nbuild + 16 : 0, st);
   if (build_rows_too) SB_CUDA(cudaMemsetAsync(matched.ptr, 0, (size_t)nbuild + 16, st));
-  Scratch pmask(probe_filter ? n + 16 : 0, st);
-  if (probe_filter) {   // the FilterExec below the streamed side, fused: rows failing it are not part of the input
-    expr_validate(probe, *probe_filter);
-    if (n > 0) eval_predicate(probe, *probe_filter, pmask.as<uint8_t>(), st);
-  }
   // candidate list (see join_candidate_kernel): worth its pass when the streamed side is long
   const bool use_cand = n >= (1 << 20) && join_type != SB_JOIN_EXISTENCE;
   const bool needs_key = kt_type == SB_JOIN_INNER || kt_type == SB_JOIN_LEFT_SEMI;
+  const KeyFilter kf = key_filter_of(ht);
+  // the FilterExec below the streamed side, fused: rows failing it are not part of the input.  A conjunction of column-vs-literal
+  // comparisons is evaluated inside the candidate pass itself; anything else becomes a byte mask first.
+  SimplePred sp;
+  sp.nterms = 0;
+  bool pred_in_pass = false;
+  if (probe_filter) {
+    expr_validate(probe, *probe_filter);
+    pred_in_pass = use_cand && !config().expr_interpret_only && match_simple_predicate(probe, *probe_filter, sp);
+    if (!pred_in_pass) sp.nterms = 0;
+  }
+  Scratch pmask(probe_filter && !pred_in_pass ? n + 16 : 0, st);
+  if (probe_filter && !pred_in_pass && n > 0) eval_predicate(probe, *probe_filter, pmask.as<uint8_t>(), st);
+  const uint8_t *pmask_dev = probe_filter && !pred_in_pass ? pmask.as<uint8_t>() : nullptr;
   int64_t nitems = n;
   std::unique_ptr<Scratch> cand_rows;
   if (use_cand) {
     KernelTimer kt("join_candidates", st);
-    Scratch cmask(n + 16, st), f32(compact_tiles(n) * 4 + 16, st), pos(compact_tiles(n) * 8 + 16, st), tot(8, st);
-    cand_rows.reset(new Scratch(n * 8 + 16, st));
-    join_candidate_kernel<<<nb, JOIN_THREADS, 0, st>>>(k, n, probe_filter ? pmask.as<uint8_t>() : nullptr, ht->bloom, ht->bloom_mask, needs_key ? 1 : 0,
-                                                      cmask.as<uint8_t>());
+    const int64_t nwords = (n + CAND_ROWS - 1) / CAND_ROWS;
+    const unsigned cb = (unsigned)((n + CAND_TILE - 1) / CAND_TILE);
+    Scratch bits(nwords * 2 + 16, st), bcount((int64_t)cb * 4 + 16, st), boff((int64_t)cb * 8 + 16, st), tot(8, st);
+    const int fast_key = k.n == 1 && !k.valid[0] && k.type[0] != SB_FLOAT32 && k.type[0] != SB_FLOAT64 && k.type[0] != SB_BOOL &&
+                         ((uintptr_t)k.data[0] & 15) == 0;
+    join_candidate_kernel<<<cb, JOIN_THREADS, 0, st>>>(k, n, sp, pmask_dev, kf, needs_key ? 1 : 0, fast_key, bits.as<uint16_t>(), bcount.as<int32_t>());
     SB_LAUNCH_CHECK();
-    compact_mask_async(cmask.as<uint8_t>(), n, cand_rows->as<int64_t>(), f32.as<int32_t>(), pos.as<int64_t>(), tot.as<int64_t>(), st);
+    exclusive_scan_i32_to_i64(bcount.as<int32_t>(), boff.as<int64_t>(), cb, tot.as<int64_t>(), st);
     SB_CUDA(cudaMemcpyAsync(&nitems, tot.ptr, 8, cudaMemcpyDeviceToHost, st));
     SB_CUDA(cudaStreamSynchronize(st));
+    cand_rows.reset(new Scratch(nitems * 8 + 16, st));
+    if (nitems > 0) {
+      candidate_rows_kernel<<<cb, JOIN_THREADS, 0, st>>>(bits.as<uint16_t>(), nwords, boff.as<int64_t>(), cand_rows->as<int64_t>());
+      SB_LAUNCH_CHECK();
+    }
     nb = (unsigned)((nitems + JOIN_THREADS - 1) / JOIN_THREADS);
   }
   const int64_t *rows = use_cand ? cand_rows->as<int64_t>() : nullptr;
+  Scratch counts(nitems * 4 + 16, st), first(nitems * 4 + 16, st), block_counts((int64_t)nb * 4 + 16, st), offsets((int64_t)nb * 8 + 16, st);
   if (nitems > 0) {
     KernelTimer kt("join_probe", st);
     join_count_kernel<<<nb, JOIN_THREADS, 0, st>>>(k, nitems, ht->slots, ht->cap, kt_type, null_aware, counts.as<int32_t>(), first.as<uint32_t>(),
                                                    block_counts.as<int32_t>(), build_rows_too ? matched.as<uint8_t>() : nullptr,
-                                                   use_cand ? nullptr : (probe_filter ? pmask.as<uint8_t>() : nullptr), ht->bloom, ht->bloom_mask, rows);
+                                                   use_cand ? nullptr : pmask_dev, kf, rows);
     SB_LAUNCH_CHECK();
   }
   if (join_type == SB_JOIN_EXISTENCE) {   // HashJoin.existenceJoin :301: the streamed row plus one boolean
@@ -602,7 +786,7 @@ int sb_join_probe_condition(const sb_hash_table *ht, const sb_table *probe, cons
   Scratch pi(npairs * 8 + 16, st), bi(npairs * 8 + 16, st);
   if (n > 0) {
     join_count_kernel<<<nb, JOIN_THREADS, 0, st>>>(k, n, ht->slots, ht->cap, SB_JOIN_INNER, 0, counts.as<int32_t>(), first.as<uint32_t>(),
-                                                   block_counts.as<int32_t>(), nullptr, nullptr, ht->bloom, ht->bloom_mask, nullptr);
+                                                   block_counts.as<int32_t>(), nullptr, nullptr, key_filter_of(ht), nullptr);
     SB_LAUNCH_CHECK();
     exclusive_scan_i32_to_i64(block_counts.as<int32_t>(), offsets.as<int64_t>(), nb, total.as<int64_t>(), st);
     if (npairs > 0) {

@@ -121,17 +121,22 @@ __global__ void __launch_bounds__(RS_THREADS, (RS_THREADS * RS_ITEMS <= 4096 ? 7
     st_status(my_status, RS_FLAG_AGG | count);
   }
   // ---- stable rank inside the warp's segment: (k, lane) order is memory order -----------------------------------------------------
-  // Which lanes hold the same digit?  match.any answers in one instruction but with a long latency: inside the chained loop
-  // below it serialised (ncu, round 2: 17 of 27 warp-stall samples per issue were the instruction after MATCH), and eight
-  // ballots per key instead made the kernel issue-bound (2.3 x the instructions).  So: all the MATCHes first, independent of
-  // one another, then the chain over the per-warp running counters.
+  // Which lanes hold the same digit?  match.any answers in one instruction but with a long, serialising latency (ncu, round 2:
+  // 17 of 27 warp-stall samples per issue were the instruction after MATCH waiting for it).  Eight ballots -- one per digit
+  // bit, all independent across bits AND across the thread's RS_ITEMS keys -- give the same mask and pipeline freely.
+  // (Measured, 25 M keys, 8 passes: ballots 1.82 ms; RS_ITEMS independent MATCHes issued back to back 2.69 ms.)
   uint32_t *wr = s_wrun[warp];
   uint32_t peers[RS_ITEMS];
 #pragma unroll
-  for (int k = 0; k < RS_ITEMS; k++) {   // RS_ITEMS independent MATCH instructions back to back: their latencies overlap
+  for (int k = 0; k < RS_ITEMS; k++) {
     const bool valid = seg + k * 32 + lane < tile_n;
-    const uint32_t d = valid ? (uint32_t)((key[k] >> shift) & 0xff) : 0x100u + lane;
-    const uint32_t m = __match_any_sync(0xffffffffu, d);
+    const uint32_t d = (uint32_t)((key[k] >> shift) & 0xff);
+    uint32_t m = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+      const uint32_t bal = __ballot_sync(0xffffffffu, (d >> b) & 1);
+      m &= ((d >> b) & 1) ? bal : ~bal;
+    }
     peers[k] = valid ? m : 0u;
   }
   const uint32_t lt = (1u << lane) - 1;

@@ -143,3 +143,40 @@ def test_random_build_preserving_joins(gpu, stream, how, with_condition):
         right_null = pa.table({"k2": pa.array([1, None], type=pa.int64()), "rv": pa.array([1, 2], type=pa.int64())})
         assert _plan_join(left, right_null, ["k"], ["k2"], how, stream).num_rows == 0
         assert _plan_join(left, right.slice(0, 0), ["k"], ["k2"], how, stream).num_rows == nl
+
+
+@pytest.mark.parametrize("how", ["inner", "left_outer", "left_semi", "left_anti"])
+@pytest.mark.parametrize("keys", ["dense", "sparse", "negative", "nullable"])
+def test_long_streamed_side_goes_through_the_candidate_pass(gpu, stream, how, keys):
+    """>= 2^20 streamed rows: one fused pass (pushed-down filter + key + prefilter) marks the candidates.  `dense` keys make the
+    prefilter an exact key-range bitmap, `sparse` (60-bit) keys a Bloom filter; `negative` crosses zero; `nullable` takes the
+    general key path.  The streamed row count is not a multiple of 16 (ragged tail), the filter is either a conjunction of
+    comparisons (evaluated inside the pass) or an OR (evaluated to a mask first)."""
+    from spark_b200.columnar import ColumnarBatch
+    from spark_b200.execution import BroadcastHashJoinExec, FilterExec, LocalTableScanExec
+    from spark_b200.expressions import col, lit
+    rng = np.random.default_rng(11)
+    nb, npr = 50_000, (1 << 20) + 12345
+    if keys == "sparse":
+        universe = rng.integers(0, 1 << 60, 4 * nb)
+    elif keys == "negative":
+        universe = np.arange(-2 * nb, 2 * nb, dtype=np.int64)
+    else:
+        universe = np.arange(1000, 1000 + 4 * nb, dtype=np.int64)
+    bk = rng.choice(universe, nb, replace=keys == "sparse")
+    bk[:100] = bk[100:200]                                     # duplicate build keys: the count / fill passes still see them
+    pk = rng.choice(universe, npr)
+    pmask = rng.random(npr) < 0.03 if keys == "nullable" else None
+    build = pa.table({"id": pa.array(bk, type=pa.int64()), "payload": np.arange(nb, dtype=np.int64)})
+    probe = pa.table({"fk": pa.array(pk, type=pa.int64(), mask=pmask), "v": rng.integers(0, 100, npr).astype(np.int32),
+                      "row": np.arange(npr, dtype=np.int64)})
+    for cond in ((col("v") < lit(40)) & (col("row") >= lit(7)), (col("v") < lit(10)) | (col("v") > lit(80))):
+        lb, rb = ColumnarBatch.from_arrow(probe, stream), ColumnarBatch.from_arrow(build, stream)
+        plan = BroadcastHashJoinExec(["fk"], ["id"], how, "right", FilterExec(cond, LocalTableScanExec(lb)), LocalTableScanExec(rb))
+        got = plan.collect(stream)
+        want = O.hash_join(O.filter_table(probe, cond.sexpr()), build, ["fk"], ["id"], how)
+        assert got.num_rows == want.num_rows
+        assert_tables_equal(got, want, key_cols=list(want.column_names))
+        if how in ("inner", "left_semi", "left_anti"):   # streamed order is preserved
+            r = np.asarray(got.column("row"))
+            assert np.all(r[1:] >= r[:-1])

@@ -42,19 +42,28 @@ def main():
     dist.broadcast(idbuf, 0)
     capi.check(lib.sb_comm_init(rank, world, bytes(idbuf.cpu().numpy().tobytes())))
     stream = Stream()
-    nparts = 200
     mine = shard(rank)
     batch = ColumnarBatch.from_arrow(mine, stream)
-    ex = ShuffleExchangeExec(HashPartitioning(["k", "d"], nparts), LocalTableScanExec(batch))
-    got = ex.executeColumnar(stream).to_arrow(stream)
     whole = pa.concat_tables([shard(r) for r in range(world)])
-    pid = O.partition_ids(whole, ["k", "d"], nparts)
-    lo = [-(-r * nparts // world) for r in range(world + 1)]
-    owned = np.nonzero((pid >= lo[rank]) & (pid < lo[rank + 1]))[0]
-    want = O.take_table(whole, owned)
     key = lambda t: sorted(zip(*[t.column(i).to_pylist() for i in range(t.num_columns)]), key=lambda r: tuple((x is None, x if x is not None else 0) for x in r))
-    assert got.num_rows == want.num_rows, (rank, got.num_rows, want.num_rows)
-    assert key(got) == key(want), "rank %d: exchanged rows differ from the oracle's shuffle" % rank
+    # both transports -- fused (sb_shuffle_exchange: the multisplit's stores land in the owners' windows) and two-step
+    # (sb_hash_partition + sb_all_to_all) -- at several fan-outs, against the oracle's shuffle of the whole table
+    for nparts in (200, 2048, 7):
+        pid = O.partition_ids(whole, ["k", "d"], nparts)
+        lo = [-(-r * nparts // world) for r in range(world + 1)]
+        owned = np.nonzero((pid >= lo[rank]) & (pid < lo[rank + 1]))[0]
+        want = O.take_table(whole, owned)
+        for fused in (True, False):
+            ex = ShuffleExchangeExec(HashPartitioning(["k", "d"], nparts), LocalTableScanExec(batch), fused=fused)
+            got = ex.executeColumnar(stream).to_arrow(stream)
+            assert got.num_rows == want.num_rows, (rank, nparts, fused, got.num_rows, want.num_rows)
+            assert key(got) == key(want), "rank %d: exchanged rows differ from the oracle's shuffle (nparts=%d fused=%s)" % (rank, nparts, fused)
+            offs = ex.partition_offsets
+            counts = np.bincount(pid[owned], minlength=nparts)
+            assert np.array_equal(np.diff(offs), counts), (rank, nparts, fused)
+            if fused:      # partition-contiguous over the owned partitions
+                gp = O.partition_ids(got, ["k", "d"], nparts)
+                assert np.all(np.diff(gp) >= 0), "rank %d: fused exchange output is not partition-contiguous" % rank
     # all-gather (broadcast build side)
     h = C.c_void_p()
     small = ColumnarBatch.from_arrow(mine.slice(0, 1000 + rank), stream)
