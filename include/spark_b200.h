@@ -138,6 +138,19 @@ int sb_table_slice(const sb_table *t, int64_t begin, int64_t end, sb_stream *s, 
 /* concatenation of tables with identical schemas (copies) */
 int sb_table_concat(const sb_table *const *tables, int32_t ntables, sb_stream *s, sb_table **out);
 
+/* ---- string keys: order-preserving dictionary codes (csrc/strings.cu).  Grouping, join and sort keys of type SB_STRING are
+ *      compared by Spark byte-wise (UTF8String.equals / compareTo -> ByteArray.compareBinary: unsigned bytes, a proper prefix first;
+ *      common/unsafe/src/main/java/org/apache/spark/unsafe/types/UTF8String.java).  sb_hash_aggregate, sb_sort / sb_top_n /
+ *      sb_sort_permutation and sb_join_build / sb_join_probe* accept such key columns directly and do this internally; the
+ *      entry points are public for hosts that want to keep a column encoded across operators.
+ *      encode: out_codes = one SB_INT32 column (validity shared with the input: NULL stays NULL) holding each value's rank among
+ *              the column's distinct values; out_dictionary = one SB_STRING column, the distinct values in ascending order.
+ *      lookup: codes of column `col` in an EXISTING dictionary; a value that is not in it gets -1.
+ *      decode: codes -> strings (NULL, negative or >= dictionary size -> NULL). */
+int sb_dictionary_encode(const sb_table *t, int32_t col, sb_stream *s, sb_table **out_codes, sb_table **out_dictionary);
+int sb_dictionary_lookup(const sb_table *t, int32_t col, const sb_table *dictionary, sb_stream *s, sb_table **out_codes);
+int sb_dictionary_decode(const sb_table *codes, int32_t col, const sb_table *dictionary, sb_stream *s, sb_table **out);
+
 /* ---- columnar scan boundary: Parquet column-chunk pages in host memory -> Arrow columns in HBM.  Replaces the CPU decode of
  *      VectorizedParquetRecordReader.nextBatch / VectorizedColumnReader.readBatch / VectorizedRleValuesReader
  *      (sql/core/src/main/java/org/apache/spark/sql/execution/datasources/parquet/) behind FileSourceScanExec.doExecuteColumnar

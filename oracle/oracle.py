@@ -741,3 +741,56 @@ def coalesce_partitions(bytes_by_partition, advisory_target_size, min_num_partit
     if len(specs) >= n:
         return []
     return [[(a, b, sum(st[a:b])) for a, b in specs] for st in stats]
+
+
+# --------------------------------------------------------------------------- string keys
+def binary_compare(a: bytes, b: bytes) -> int:
+    """UTF8String.binaryCompare (common/unsafe/.../types/UTF8String.java:2075) -> ByteArray.compareBinary
+    (common/unsafe/.../types/ByteArray.java): compare as UNSIGNED bytes up to the shorter length, then the shorter one first."""
+    m = min(len(a), len(b))
+    for i in range(m):
+        if a[i] != b[i]:
+            return (a[i] & 0xFF) - (b[i] & 0xFF)
+    return len(a) - len(b)
+
+
+def string_codes(column):
+    """Order-preserving dictionary codes of a string column: (int32 arrow array, NULL where the string is NULL; the sorted list
+    of distinct values as bytes).  code(a) < code(b) <=> binary_compare(a, b) < 0 -- how grouping (equality), joins (equality) and
+    sorts (SortOrder on StringType: UTF8String.compareTo) see the column."""
+    import functools
+    vals = [None if v is None else (v if isinstance(v, bytes) else v.encode("utf-8")) for v in column.to_pylist()]
+    dictionary = sorted({v for v in vals if v is not None}, key=functools.cmp_to_key(binary_compare))
+    rank = {v: i for i, v in enumerate(dictionary)}
+    return pa.array([None if v is None else rank[v] for v in vals], type=pa.int32()), dictionary
+
+
+def encode_string_columns(table, cols, dictionaries=None):
+    """table with the string columns `cols` replaced by their codes; returns (table, {col: dictionary}).  dictionaries: encode
+    against existing ones instead (values outside get -1, like a probe-side key the build side never saw)."""
+    out, dicts = table, {}
+    for c in cols:
+        i = table.column_names.index(c)
+        if dictionaries is None:
+            codes, d = string_codes(table.column(c))
+        else:
+            d = dictionaries[c]
+            rank = {v: k for k, v in enumerate(d)}
+            vals = [None if v is None else (v if isinstance(v, bytes) else v.encode("utf-8")) for v in table.column(c).to_pylist()]
+            codes = pa.array([None if v is None else rank.get(v, -1) for v in vals], type=pa.int32())
+        out = out.set_column(i, c, codes)
+        dicts[c] = d
+    return out, dicts
+
+
+def decode_string_columns(table, dicts, as_type=None):
+    out = table
+    for c, d in dicts.items():
+        if c not in table.column_names:
+            continue
+        i = table.column_names.index(c)
+        codes = table.column(c).to_pylist()
+        vals = [None if (k is None or k < 0) else d[k] for k in codes]
+        t = as_type or pa.string()
+        out = out.set_column(i, c, pa.array([None if v is None else (v.decode("utf-8") if t == pa.string() else v) for v in vals], type=t))
+    return out

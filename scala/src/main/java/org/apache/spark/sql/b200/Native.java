@@ -36,6 +36,13 @@ public final class Native {
   public static native long tableSlice(long table, long begin, long end, long stream);
   public static native long tableConcat(long[] tables, long stream);
 
+  // ---- string keys as order-preserving dictionary codes (the operators do this internally; public for hosts that keep a column
+  //      encoded across operators) ---------------------------------------------------------------------------------------------
+  /** returns {codes table (one int32 column), dictionary table (one string column, distinct values ascending)} */
+  public static native long[] dictionaryEncode(long table, int column, long stream);
+  public static native long dictionaryLookup(long table, int column, long dictionary, long stream);
+  public static native long dictionaryDecode(long codes, int column, long dictionary, long stream);
+
   // ---- expressions, FilterExec / ProjectExec --------------------------------------------------------------------------------
   /** postfix sb_expr program built by ExprCompiler; returns a native handle freed with exprFree. */
   public static native long exprCreate(int[] ops, int[] vtypes, int[] args, long[] literals, int outType);

@@ -305,6 +305,28 @@ NATIVE(jlong, tableConcat)(JNIEnv *env, jclass c, jlongArray tables, jlong strea
   return (jlong)(intptr_t)out;
 }
 
+NATIVE(jlongArray, dictionaryEncode)(JNIEnv *env, jclass c, jlong table, jint column, jlong stream) {
+  sb_table *codes = NULL, *dict = NULL;
+  int rc = sb_dictionary_encode(TBL(table), column, STR(stream), &codes, &dict);
+  jlongArray out = (*env)->NewLongArray(env, 2);
+  if (rc == SB_OK) {
+    const jlong h[2] = {(jlong)(intptr_t)codes, (jlong)(intptr_t)dict};
+    (*env)->SetLongArrayRegion(env, out, 0, 2, h);
+  }
+  throw_if(env, rc);
+  return out;
+}
+NATIVE(jlong, dictionaryLookup)(JNIEnv *env, jclass c, jlong table, jint column, jlong dictionary, jlong stream) {
+  sb_table *out = NULL;
+  throw_if(env, sb_dictionary_lookup(TBL(table), column, TBL(dictionary), STR(stream), &out));
+  return (jlong)(intptr_t)out;
+}
+NATIVE(jlong, dictionaryDecode)(JNIEnv *env, jclass c, jlong codes, jint column, jlong dictionary, jlong stream) {
+  sb_table *out = NULL;
+  throw_if(env, sb_dictionary_decode(TBL(codes), column, TBL(dictionary), STR(stream), &out));
+  return (jlong)(intptr_t)out;
+}
+
 NATIVE(jlong, rangePartition)(JNIEnv *env, jclass c, jlong table, jint col, jboolean asc, jboolean nullsFirst, jlong bounds, jlong stream,
                               jlongArray offsetsOut) {
   sb_sort_order o = {col, asc ? 1 : 0, nullsFirst ? 1 : 0, 0};

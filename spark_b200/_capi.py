@@ -111,6 +111,8 @@ _SIGNATURES = {
     "sb_table_retain": [_p], "sb_table_release": [_p],
     "sb_table_select": [_p, C.POINTER(_i32), _i32, _pp], "sb_table_zip": [_p, _p, _pp],
     "sb_table_slice": [_p, _i64, _i64, _p, _pp], "sb_table_concat": [_pp, _i32, _p, _pp],
+    "sb_dictionary_encode": [_p, _i32, _p, _pp, _pp], "sb_dictionary_lookup": [_p, _i32, _p, _p, _pp],
+    "sb_dictionary_decode": [_p, _i32, _p, _p, _pp],
     "sb_parquet_chunk_pages": [_p, _i64, _i32, C.POINTER(sb_page), _i32, C.POINTER(_i32), C.POINTER(_i64), C.POINTER(_i32)],
     "sb_scan_decode": [C.POINTER(sb_column_chunk), _i32, _p, _pp],
     "sb_scan_encode": [_p, _i32, _p, _i64, _p, _pp, C.POINTER(sb_page), _i32, C.POINTER(_i32), C.POINTER(_i64), C.POINTER(_i32)],

@@ -36,6 +36,7 @@
 #include "expr.cuh"
 #include "primitives.cuh"
 #include "rtc.cuh"
+#include "strings.cuh"
 
 namespace sb {
 
@@ -522,7 +523,7 @@ static int64_t next_pow2(int64_t x) {
   return p;
 }
 
-static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cudaStream_t st, sb_table **out) {
+static void hash_aggregate_fixed(const sb_table *in, const sb_agg_plan *plan, cudaStream_t st, sb_table **out) {
   SB_REQUIRE(in && plan && out, "null argument");
   SB_REQUIRE(plan->mode >= SB_AGG_MODE_PARTIAL && plan->mode <= SB_AGG_MODE_PARTIAL_MERGE, "bad aggregate mode %d", plan->mode);
   SB_REQUIRE(plan->nkeys >= 0 && plan->naggs >= 0, "bad plan");
@@ -567,7 +568,7 @@ static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cud
     int ci = plan->key_cols[k];
     SB_REQUIRE(ci >= 0 && ci < (int)in->cols.size(), "key column %d out of range", ci);
     const Column &c = in->cols[ci];
-    if (c.type == SB_STRING) fail(SB_ERR_UNSUPPORTED, "string grouping keys are not supported (dictionary-encode them)");
+    SB_REQUIRE(c.type != SB_STRING, "string grouping keys reach the kernels as dictionary codes");
     key_refs[k] = {c.d(), nulls_of(c), c.type};
     m.key_type[k] = c.type;
     m.key_bits[k] = type_width(c.type) * 8;
@@ -1043,6 +1044,39 @@ extern "C" int sb_agg_rtc_compile_check(const int32_t *plan_meta_words, int32_t 
   SB_API_END
 }
 extern "C" int32_t sb_agg_plan_meta_words(void) { return (int32_t)(sizeof(PlanMeta) / 4); }
+
+// String grouping keys (HashAggregateExec groups UTF8String keys by their bytes): the key column is replaced by its
+// order-preserving dictionary codes (csrc/strings.cu), the fixed-width kernels group the codes, and the key columns of the result
+// are decoded back.  Every mode works the same way -- a Final / PartialMerge input carries decoded strings again.
+static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cudaStream_t st, sb_table **out) {
+  SB_REQUIRE(in && plan && out, "null argument");
+  std::vector<int> scols;
+  for (int k = 0; k < plan->nkeys; k++) {
+    const int ci = plan->key_cols[k];
+    if (ci >= 0 && ci < (int)in->cols.size() && in->cols[ci].type == SB_STRING) scols.push_back(ci);
+  }
+  if (scols.empty()) {
+    hash_aggregate_fixed(in, plan, st, out);
+    return;
+  }
+  EncodedView ev;
+  encode_string_columns(in, scols, nullptr, st, ev);
+  sb_table *res = nullptr;
+  hash_aggregate_fixed(ev.view, plan, st, &res);
+  try {
+    for (int k = 0; k < plan->nkeys; k++) {
+      const Column *dict = ev.dictionary_of(plan->key_cols[k]);
+      if (!dict) continue;
+      Column decoded = dictionary_decode(res->cols[k], *dict, st);
+      column_release(res->cols[k]);
+      res->cols[k] = decoded;
+    }
+  } catch (...) {
+    table_free(res);
+    throw;
+  }
+  *out = res;
+}
 
 // which kernels the calling thread's last sb_hash_aggregate ran: "generic" or "rtc:<plan hash>[(disk)]"
 extern "C" const char *sb_hash_aggregate_last_plan(void) { return g_last_plan_name.c_str(); }

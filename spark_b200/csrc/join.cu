@@ -25,6 +25,7 @@
 #include "simple_pred.cuh"
 #include "primitives.cuh"
 #include "rtc.cuh"
+#include "strings.cuh"
 
 struct sb_hash_table {
   sb_table *build = nullptr;        // retained build-side batch (payload gathered at probe time)
@@ -47,6 +48,9 @@ struct sb_hash_table {
   int exact = 0;
   uint64_t fmin = 0, frange = 0;
   int64_t nkeys_in = 0;               // build rows that entered the relation (filter TRUE, keys not NULL)
+  // string key columns join as int32 codes in the BUILD side's dictionaries (csrc/strings.cu): has_dict[i] says key i is one
+  bool has_dict[4] = {false, false, false, false};
+  sb::Column dict[4];
   cudaStream_t st = nullptr;
 };
 
@@ -408,7 +412,7 @@ static JoinKeys make_join_keys(const sb_table *t, const int32_t *key_cols, int32
   for (int i = 0; i < nkeys; i++) {
     SB_REQUIRE(key_cols[i] >= 0 && key_cols[i] < (int)t->cols.size(), "join key column %d out of range", key_cols[i]);
     const Column &c = t->cols[key_cols[i]];
-    if (c.type == SB_STRING) fail(SB_ERR_UNSUPPORTED, "string join keys are not supported (dictionary-encode them)");
+    SB_REQUIRE(c.type != SB_STRING, "string join keys reach the kernels as dictionary codes");
     k.data[i] = c.d();
     k.valid[i] = c.v();
     k.type[i] = c.type;
@@ -423,6 +427,27 @@ static JoinKeys make_join_keys(const sb_table *t, const int32_t *key_cols, int32
   }
   if (pos > 64) fail(SB_ERR_UNSUPPORTED, "join keys need %d bits; at most 64 bits of fixed-width keys are packed (HashJoin.rewriteKeyExpr)", pos);
   return k;
+}
+
+// The table the streamed side's keys are read from: `probe` itself, or a view in which the string key columns hold their codes in
+// the relation's dictionaries (a string the build side never saw gets -1: it equals no build code, so outer / anti joins still
+// emit the row).
+static const sb_table *probe_key_source(const sb_hash_table *ht, const sb_table *probe, const int32_t *key_cols, int32_t nkeys, cudaStream_t st,
+                                        EncodedView &ev) {
+  std::vector<int> cols;
+  std::vector<const Column *> dicts;
+  for (int i = 0; i < nkeys && i < JOIN_MAX_KEYS; i++) {
+    SB_REQUIRE(key_cols[i] >= 0 && key_cols[i] < (int)probe->cols.size(), "join key column %d out of range", key_cols[i]);
+    const bool is_str = probe->cols[key_cols[i]].type == SB_STRING;
+    SB_REQUIRE(is_str == ht->has_dict[i], "join key %d: one side is a string column, the other is not", i);
+    if (is_str) {
+      cols.push_back(key_cols[i]);
+      dicts.push_back(&ht->dict[i]);
+    }
+  }
+  if (cols.empty()) return probe;
+  encode_string_columns(probe, cols, &dicts, st, ev);
+  return ev.view;
 }
 
 }  // namespace sb
@@ -442,7 +467,15 @@ int sb_join_build_filtered(const sb_table *build, const int32_t *key_cols, int32
   cudaStream_t st = stream_of(s);
   int64_t n = build->nrows;
   SB_REQUIRE(n < 0xFFFFFFFFll, "build side has too many rows for one relation");
-  JoinKeys k = make_join_keys(build, key_cols, nkeys, nullptr);
+  SB_REQUIRE(nkeys >= 1 && nkeys <= JOIN_MAX_KEYS, "joins support 1..%d key columns (got %d)", JOIN_MAX_KEYS, nkeys);
+  EncodedView ev;   // string key columns -> codes; the dictionaries move into the relation below
+  {
+    std::vector<int> scols;
+    for (int i = 0; i < nkeys; i++)
+      if (key_cols[i] >= 0 && key_cols[i] < (int)build->cols.size() && build->cols[key_cols[i]].type == SB_STRING) scols.push_back(key_cols[i]);
+    if (!scols.empty()) encode_string_columns(build, scols, nullptr, st, ev);
+  }
+  JoinKeys k = make_join_keys(ev.view ? ev.view : build, key_cols, nkeys, nullptr);
   Scratch mask(filter ? n + 16 : 0, st);
   if (filter) {
     expr_validate(build, *filter);
@@ -452,6 +485,10 @@ int sb_join_build_filtered(const sb_table *build, const int32_t *key_cols, int32
   ht->st = st;
   ht->nkeys = nkeys;
   for (int i = 0; i < nkeys; i++) {
+    if (const Column *d = ev.view ? ev.dictionary_of(key_cols[i]) : nullptr) {
+      ht->has_dict[i] = true;
+      ht->dict[i] = column_share(*d);
+    }
     ht->key_type[i] = k.type[i];
     ht->key_bits[i] = k.bits[i];
     ht->key_shift[i] = k.shift[i];
@@ -503,6 +540,8 @@ int sb_join_build_filtered(const sb_table *build, const int32_t *key_cols, int32
     if (ht->slots) cudaFreeAsync(ht->slots, st);
     if (ht->null_key_flag) cudaFreeAsync(ht->null_key_flag, st);
     if (ht->bloom) cudaFreeAsync(ht->bloom, st);
+    for (int i = 0; i < 4; i++)
+      if (ht->has_dict[i]) column_release(ht->dict[i]);
     delete ht;
     throw;
   }
@@ -521,6 +560,8 @@ int sb_hash_table_release(sb_hash_table *ht) {
     if (ht->null_key_flag) cudaFreeAsync(ht->null_key_flag, ht->st);
     if (ht->bloom) cudaFreeAsync(ht->bloom, ht->st);
     if (ht->build && ht->build->refs.fetch_sub(1) == 1) table_free(ht->build);
+    for (int i = 0; i < 4; i++)
+      if (ht->has_dict[i]) column_release(ht->dict[i]);
     delete ht;
   }
   SB_API_END
@@ -585,7 +626,8 @@ int sb_join_probe_ex(const sb_hash_table *ht, const sb_table *probe, const int32
   SB_REQUIRE(join_type >= SB_JOIN_INNER && join_type <= SB_JOIN_LEFT_ANTI_NULL_AWARE, "unknown join type %d", join_type);
   cudaStream_t st = stream_of(s);
   const int64_t n = probe->nrows, nbuild = ht->build->nrows;
-  JoinKeys k = make_join_keys(probe, key_cols, nkeys, ht);
+  EncodedView key_view;
+  JoinKeys k = make_join_keys(probe_key_source(ht, probe, key_cols, nkeys, st, key_view), key_cols, nkeys, ht);
   // the kernels know inner / streamed-outer / semi / anti / existence; the build-side-preserving joins are those plus the build
   // rows nobody matched (ShuffledHashJoinExec.buildSideOrFullOuterJoin, SQLX/joins/ShuffledHashJoinExec.scala:130-330)
   const bool build_rows_too = join_type == SB_JOIN_FULL_OUTER || join_type == SB_JOIN_BUILD_OUTER;
@@ -780,7 +822,8 @@ int sb_join_probe_condition(const sb_hash_table *ht, const sb_table *probe, cons
   Scratch mask(npairs + 16, st);
   if (npairs > 0) eval_predicate(pairs_tbl, *condition, mask.as<uint8_t>(), st);
   // pair indices: the same kernels again with index outputs only (count + fill), cheaper than carrying row ids through the gather
-  JoinKeys k = make_join_keys(probe, key_cols, nkeys, ht);
+  EncodedView key_view;
+  JoinKeys k = make_join_keys(probe_key_source(ht, probe, key_cols, nkeys, st, key_view), key_cols, nkeys, ht);
   unsigned nb = (unsigned)((n + JOIN_THREADS - 1) / JOIN_THREADS);
   Scratch counts(n * 4 + 16, st), first(n * 4 + 16, st), block_counts((int64_t)nb * 4 + 16, st), offsets((int64_t)nb * 8 + 16, st), total(8, st);
   Scratch pi(npairs * 8 + 16, st), bi(npairs * 8 + 16, st);

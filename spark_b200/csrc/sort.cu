@@ -22,6 +22,7 @@
 #include "multisplit.cuh"
 #include "primitives.cuh"
 #include "radix.cuh"
+#include "strings.cuh"
 
 namespace sb {
 
@@ -198,12 +199,20 @@ static void sort_permutation_impl(const sb_table *in, const sb_sort_order *order
   const int64_t n = in->nrows;
   SB_REQUIRE(n < (1ll << 32), "tables of 2^32 rows or more must be sorted in chunks");
   SB_REQUIRE(norders >= 1 && orders, "sort needs at least one order");
+  std::vector<int> scols;
   for (int k = 0; k < norders; k++) {
     SB_REQUIRE(orders[k].col >= 0 && orders[k].col < (int)in->cols.size(), "sort column %d out of range", orders[k].col);
-    if (!radix_eligible(in->cols[orders[k].col].type))
-      fail(SB_ERR_UNSUPPORTED, "sorting on string columns is not implemented (dictionary-encode them)");
+    if (!radix_eligible(in->cols[orders[k].col].type)) scols.push_back(orders[k].col);
   }
   if (n == 0) return;
+  if (!scols.empty()) {
+    // string sort keys: their order-preserving dictionary codes sort exactly like UTF8String.compareTo sorts the strings
+    // (csrc/strings.cu), NULLs stay NULLs -- so the radix path below runs on the codes
+    EncodedView ev;
+    encode_string_columns(in, scols, nullptr, st, ev);
+    sort_permutation_impl(ev.view, orders, norders, perm, st);
+    return;
+  }
   if (norders == 1) {
     // ---- the reference's radix path --------------------------------------------------------------
     const Column &c = in->cols[orders[0].col];
