@@ -47,6 +47,11 @@ struct sb_hash_table {
   uint64_t bloom_mask = 0;            // Bloom: words - 1 (power of two)
   int exact = 0;
   uint64_t fmin = 0, frange = 0;
+  // exact relations know whether their keys are unique (a bit that is already set when a key arrives = a duplicate).  Unique keys
+  // turn the probe into one lookup per candidate (no count / scan / fill); a dense key range (<= 8 slots of range per key) also
+  // replaces the open-addressing table by a direct-address one, row_of[key - fmin] -- LongToUnsafeRowMap's dense mode proper.
+  int unique = 0;
+  uint32_t *row_of = nullptr;         // dense mode: [frange], FREE_SLOT = no such key; slots is NULL then
   int64_t nkeys_in = 0;               // build rows that entered the relation (filter TRUE, keys not NULL)
   // string key columns join as int32 codes in the BUILD side's dictionaries (csrc/strings.cu): has_dict[i] says key i is one
   bool has_dict[4] = {false, false, false, false};
@@ -110,6 +115,7 @@ struct KeyFilter {
   const uint32_t *words;
   uint64_t mask, fmin, frange;
   int exact;
+  const uint32_t *row_of;   // dense direct-address table (implies exact, unique keys)
 };
 __device__ __forceinline__ bool filter_test(const KeyFilter &f, uint64_t key) {
   if (!f.words) return true;
@@ -146,7 +152,12 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_build_kernel(JoinKeys k, in
   uint32_t *fw = const_cast<uint32_t *>(kf.words);
   if (kf.exact) {
     const uint64_t d = key - kf.fmin;
-    atomicOr(&fw[d >> 5], 1u << (d & 31));
+    const uint32_t bit = 1u << (d & 31);
+    if (atomicOr(&fw[d >> 5], bit) & bit) null_key_flag[1] = 1;   // the key was there already: the relation is not unique
+    if (kf.row_of) {   // dense mode: the direct-address table is the relation (a duplicate voids it; the host rebuilds)
+      const_cast<uint32_t *>(kf.row_of)[d] = (uint32_t)row;
+      return;
+    }
   } else if (fw) atomicOr(&fw[bloom_word(hh, kf.mask)], bloom_bits(hh));
   for (;;) {
     if (slots[h].row == FREE_SLOT && atomicCAS(&slots[h].row, FREE_SLOT, (uint32_t)row) == FREE_SLOT) {
@@ -179,6 +190,11 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_count_kernel(JoinKeys k, in
       const uint64_t hh = join_mix(key);
       uint64_t h = hh & mask;
       if (filter_test(kf, key)) {
+        if (kf.row_of) {   // dense, unique: the prefilter said the key exists
+          f = __ldg(&kf.row_of[key - kf.fmin]);
+          matches = 1;
+          if (matched) matched[f] = 1;
+        } else
         for (;;) {
           uint64_t sk;
           uint32_t r;
@@ -271,12 +287,19 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_fill_kernel(JoinKeys k, int
 // (pushed-down filter, key, prefilter word) marks the rows that can produce output at all; only those -- as a compacted row list --
 // go through the count / fill passes with their per-row bookkeeping.  A thread owns 16 consecutive rows (16-byte loads), writes
 // their verdicts as one 16-bit word and the block leaves its candidate count for the scan, so the list is produced by one more
-// pass over 1 bit per row.  needs_key: inner / semi joins drop NULL-key and prefilter-negative rows here; outer / anti joins keep
+// pass over 1 bit per row.  mode (CandMode): inner / semi joins drop NULL-key and prefilter-negative rows here; outer / anti joins keep
 // every row the filter keeps (those rows are output even without a partner).
 constexpr int CAND_ROWS = SP_ROWS;
+// which rows the candidate pass keeps, next to the pushed-down filter
+enum CandMode {
+  CAND_ALL = 0,           // every row (outer joins; anti joins behind a Bloom filter, which cannot prove absence)
+  CAND_PRESENT = 1,       // non-NULL key that passes the prefilter (inner, semi)
+  CAND_ABSENT = 2,        // exact prefilter only: NULL key or key not in the relation (anti join: these rows ARE the answer)
+  CAND_ABSENT_KEYED = 3   // exact prefilter only: non-NULL key not in the relation (null-aware anti join)
+};
 constexpr int CAND_TILE = JOIN_THREADS * CAND_ROWS;
 __global__ void __launch_bounds__(JOIN_THREADS) join_candidate_kernel(JoinKeys k, int64_t n, const __grid_constant__ SimplePred sp,
-                                                                      const uint8_t *__restrict__ row_mask, KeyFilter kf, int needs_key,
+                                                                      const uint8_t *__restrict__ row_mask, KeyFilter kf, int mode,
                                                                       int fast_key, uint16_t *__restrict__ bits_out,
                                                                       int32_t *__restrict__ block_counts) {
   __shared__ int32_t wsum[JOIN_THREADS / 32];
@@ -297,8 +320,9 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_candidate_kernel(JoinKeys k
       }
       keep &= mbits;
     }
-    if (needs_key) {
+    if (mode != CAND_ALL) {
       uint64_t key[CAND_ROWS];
+      uint32_t has = 0xFFFFu;
       if (fast_key) {   // one NULL-free integer key column: the 16 keys arrive as 16-byte loads whatever `keep` says
         int64_t x[CAND_ROWS];
         switch (k.type[0]) {
@@ -311,21 +335,21 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_candidate_kernel(JoinKeys k
 #pragma unroll
         for (int j = 0; j < CAND_ROWS; j++) key[j] = (uint64_t)x[j] & km;
       } else {
-        uint32_t has = 0;
+        has = 0;
 #pragma unroll
         for (int j = 0; j < CAND_ROWS; j++) {
           key[j] = 0;
           if (((keep >> j) & 1u) && join_key(k, row0 + j, key[j])) has |= 1u << j;
         }
-        keep &= has;
       }
+      uint32_t present = has;   // rows whose key is (or, with a Bloom filter, may be) in the relation
       if (kf.words) {
-        uint32_t pass = 0;
+        present = 0;
 #pragma unroll
         for (int j = 0; j < CAND_ROWS; j++)
-          if (((keep >> j) & 1u) && filter_test(kf, key[j])) pass |= 1u << j;
-        keep = pass;
+          if (((keep & has) >> j) & 1u) present |= (filter_test(kf, key[j]) ? 1u : 0u) << j;
       }
+      keep &= mode == CAND_PRESENT ? present : mode == CAND_ABSENT ? ~present : (has & ~present);
     }
     bits_out[row0 / CAND_ROWS] = (uint16_t)keep;
   }
@@ -367,6 +391,37 @@ __global__ void __launch_bounds__(JOIN_THREADS) candidate_rows_kernel(const uint
   }
 }
 
+// Relations with unique keys behind an exact prefilter: one lookup per candidate gives its partner -- no count / scan / fill.
+// outer: candidates without a partner (NULL key or key not in the relation) get -1.
+__global__ void __launch_bounds__(JOIN_THREADS) join_lookup_kernel(JoinKeys k, const int64_t *__restrict__ rows, int64_t nitems,
+                                                                   const JoinSlot *__restrict__ slots, int64_t cap, KeyFilter kf, int outer,
+                                                                   int64_t *__restrict__ out_build) {
+  const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= nitems) return;
+  const int64_t row = rows[item];
+  uint64_t key;
+  int64_t found = -1;
+  if (join_key(k, row, key) && (!outer || filter_test(kf, key))) {   // not outer: the candidate pass has done the test
+    if (kf.row_of) found = (int64_t)__ldg(&kf.row_of[key - kf.fmin]);
+    else {
+      const uint64_t mask = (uint64_t)cap - 1;
+      uint64_t h = join_mix(key) & mask;
+      for (;;) {
+        uint64_t sk;
+        uint32_t r;
+        load_slot(&slots[h], sk, r);
+        if (r == FREE_SLOT) break;
+        if (sk == key) {
+          found = (int64_t)r;
+          break;
+        }
+        h = (h + 1) & mask;
+      }
+    }
+  }
+  out_build[item] = found;
+}
+
 // what the relation will hold: packed-key range and row count of the build rows that pass the filter with non-NULL keys
 __global__ void __launch_bounds__(JOIN_THREADS) build_stats_kernel(JoinKeys k, int64_t n, const uint8_t *__restrict__ row_mask,
                                                                    long long *__restrict__ stats) {
@@ -401,6 +456,7 @@ static KeyFilter key_filter_of(const sb_hash_table *ht) {
   f.fmin = ht->fmin;
   f.frange = ht->frange;
   f.exact = ht->exact;
+  f.row_of = ht->row_of;
   return f;
 }
 
@@ -522,17 +578,47 @@ int sb_join_build_filtered(const sb_table *build, const int32_t *key_cols, int32
     ht->bloom_mask = (uint64_t)bwords - 1;
   }
   try {
-    SB_CUDA(cudaMallocAsync((void **)&ht->slots, (size_t)cap * sizeof(JoinSlot), st));
-    SB_CUDA(cudaMemsetAsync(ht->slots, 0xff, (size_t)cap * sizeof(JoinSlot), st));
-    SB_CUDA(cudaMallocAsync((void **)&ht->null_key_flag, 4, st));
-    SB_CUDA(cudaMemsetAsync(ht->null_key_flag, 0, 4, st));
+    const unsigned nblocks = (unsigned)((n + JOIN_THREADS - 1) / JOIN_THREADS);
+    const uint8_t *mask_dev = filter ? mask.as<uint8_t>() : nullptr;
+    SB_CUDA(cudaMallocAsync((void **)&ht->null_key_flag, 8, st));   // [0] a NULL key was seen, [1] a key arrived twice
+    SB_CUDA(cudaMemsetAsync(ht->null_key_flag, 0, 8, st));
     SB_CUDA(cudaMallocAsync((void **)&ht->bloom, (size_t)bwords * 4, st));
     SB_CUDA(cudaMemsetAsync(ht->bloom, 0, (size_t)bwords * 4, st));
-    if (n > 0) {
-      KernelTimer kt("join_build", st);
-      join_build_kernel<<<(unsigned)((n + JOIN_THREADS - 1) / JOIN_THREADS), JOIN_THREADS, 0, st>>>(
-          k, n, ht->slots, cap, ht->null_key_flag, filter ? mask.as<uint8_t>() : nullptr, key_filter_of(ht));
-      SB_LAUNCH_CHECK();
+    int32_t hflags[2] = {0, 0};
+    bool built = false;
+    if (ht->exact && range <= 8ull * (uint64_t)nin) {   // dense: try the direct-address table; a duplicate key voids the attempt
+      SB_CUDA(cudaMallocAsync((void **)&ht->row_of, (size_t)range * 4, st));
+      SB_CUDA(cudaMemsetAsync(ht->row_of, 0xff, (size_t)range * 4, st));
+      {
+        KernelTimer kt("join_build", st);
+        join_build_kernel<<<nblocks, JOIN_THREADS, 0, st>>>(k, n, nullptr, cap, ht->null_key_flag, mask_dev, key_filter_of(ht));
+        SB_LAUNCH_CHECK();
+      }
+      SB_CUDA(cudaMemcpyAsync(hflags, ht->null_key_flag, 8, cudaMemcpyDeviceToHost, st));
+      SB_CUDA(cudaStreamSynchronize(st));
+      if (!hflags[1]) {
+        built = true;
+        ht->unique = 1;
+      } else {
+        cudaFreeAsync(ht->row_of, st);
+        ht->row_of = nullptr;
+        SB_CUDA(cudaMemsetAsync(ht->bloom, 0, (size_t)bwords * 4, st));
+        SB_CUDA(cudaMemsetAsync(ht->null_key_flag, 0, 8, st));
+      }
+    }
+    if (!built) {
+      SB_CUDA(cudaMallocAsync((void **)&ht->slots, (size_t)cap * sizeof(JoinSlot), st));
+      SB_CUDA(cudaMemsetAsync(ht->slots, 0xff, (size_t)cap * sizeof(JoinSlot), st));
+      if (n > 0) {
+        KernelTimer kt("join_build", st);
+        join_build_kernel<<<nblocks, JOIN_THREADS, 0, st>>>(k, n, ht->slots, cap, ht->null_key_flag, mask_dev, key_filter_of(ht));
+        SB_LAUNCH_CHECK();
+      }
+      if (ht->exact) {   // unique keys? (the answer picks the probe strategy, so it is worth one round trip here)
+        SB_CUDA(cudaMemcpyAsync(hflags, ht->null_key_flag, 8, cudaMemcpyDeviceToHost, st));
+        SB_CUDA(cudaStreamSynchronize(st));
+        ht->unique = hflags[1] ? 0 : 1;
+      }
     }
     ht->build = const_cast<sb_table *>(build);
     ht->build->refs.fetch_add(1);
@@ -540,6 +626,7 @@ int sb_join_build_filtered(const sb_table *build, const int32_t *key_cols, int32
     if (ht->slots) cudaFreeAsync(ht->slots, st);
     if (ht->null_key_flag) cudaFreeAsync(ht->null_key_flag, st);
     if (ht->bloom) cudaFreeAsync(ht->bloom, st);
+    if (ht->row_of) cudaFreeAsync(ht->row_of, st);
     for (int i = 0; i < 4; i++)
       if (ht->has_dict[i]) column_release(ht->dict[i]);
     delete ht;
@@ -559,6 +646,7 @@ int sb_hash_table_release(sb_hash_table *ht) {
     if (ht->slots) cudaFreeAsync(ht->slots, ht->st);
     if (ht->null_key_flag) cudaFreeAsync(ht->null_key_flag, ht->st);
     if (ht->bloom) cudaFreeAsync(ht->bloom, ht->st);
+    if (ht->row_of) cudaFreeAsync(ht->row_of, ht->st);
     if (ht->build && ht->build->refs.fetch_sub(1) == 1) table_free(ht->build);
     for (int i = 0; i < 4; i++)
       if (ht->has_dict[i]) column_release(ht->dict[i]);
@@ -664,8 +752,14 @@ int sb_join_probe_ex(const sb_hash_table *ht, const sb_table *probe, const int32
   if (build_rows_too) SB_CUDA(cudaMemsetAsync(matched.ptr, 0, (size_t)nbuild + 16, st));
   // candidate list (see join_candidate_kernel): worth its pass when the streamed side is long
   const bool use_cand = n >= (1 << 20) && join_type != SB_JOIN_EXISTENCE;
-  const bool needs_key = kt_type == SB_JOIN_INNER || kt_type == SB_JOIN_LEFT_SEMI;
   const KeyFilter kf = key_filter_of(ht);
+  // what the candidate pass can settle by itself.  Behind an EXACT prefilter a candidate is a row whose key is in the relation, so
+  // semi / anti joins are finished by the pass, and with unique keys inner / outer joins need one lookup per candidate
+  // (no count / scan / fill).
+  const bool settled = use_cand && ht->exact && !build_rows_too &&
+                       (kt_type == SB_JOIN_LEFT_SEMI || kt_type == SB_JOIN_LEFT_ANTI || (ht->unique && pairs));
+  int cand_mode = kt_type == SB_JOIN_INNER || kt_type == SB_JOIN_LEFT_SEMI ? CAND_PRESENT : CAND_ALL;
+  if (settled && kt_type == SB_JOIN_LEFT_ANTI) cand_mode = null_aware ? CAND_ABSENT_KEYED : CAND_ABSENT;
   // the FilterExec below the streamed side, fused: rows failing it are not part of the input.  A conjunction of column-vs-literal
   // comparisons is evaluated inside the candidate pass itself; anything else becomes a byte mask first.
   SimplePred sp;
@@ -688,7 +782,7 @@ int sb_join_probe_ex(const sb_hash_table *ht, const sb_table *probe, const int32
     Scratch bits(nwords * 2 + 16, st), bcount((int64_t)cb * 4 + 16, st), boff((int64_t)cb * 8 + 16, st), tot(8, st);
     const int fast_key = k.n == 1 && !k.valid[0] && k.type[0] != SB_FLOAT32 && k.type[0] != SB_FLOAT64 && k.type[0] != SB_BOOL &&
                          ((uintptr_t)k.data[0] & 15) == 0;
-    join_candidate_kernel<<<cb, JOIN_THREADS, 0, st>>>(k, n, sp, pmask_dev, kf, needs_key ? 1 : 0, fast_key, bits.as<uint16_t>(), bcount.as<int32_t>());
+    join_candidate_kernel<<<cb, JOIN_THREADS, 0, st>>>(k, n, sp, pmask_dev, kf, cand_mode, fast_key, bits.as<uint16_t>(), bcount.as<int32_t>());
     SB_LAUNCH_CHECK();
     exclusive_scan_i32_to_i64(bcount.as<int32_t>(), boff.as<int64_t>(), cb, tot.as<int64_t>(), st);
     SB_CUDA(cudaMemcpyAsync(&nitems, tot.ptr, 8, cudaMemcpyDeviceToHost, st));
@@ -701,6 +795,32 @@ int sb_join_probe_ex(const sb_hash_table *ht, const sb_table *probe, const int32
     nb = (unsigned)((nitems + JOIN_THREADS - 1) / JOIN_THREADS);
   }
   const int64_t *rows = use_cand ? cand_rows->as<int64_t>() : nullptr;
+  if (settled) {
+    // the candidate list IS the streamed half of the output; partners (inner / outer) come from one lookup each
+    const int64_t nout = nitems;
+    Scratch out_build(pairs ? nout * 8 + 16 : 0, st);
+    if (pairs && nout > 0) {
+      KernelTimer kt("join_probe", st);
+      join_lookup_kernel<<<nb, JOIN_THREADS, 0, st>>>(k, rows, nout, ht->slots, ht->cap, kf, kt_type == SB_JOIN_LEFT_OUTER ? 1 : 0, out_build.as<int64_t>());
+      SB_LAUNCH_CHECK();
+    }
+    sb_table *left = gather_table(probe_view.t, rows, nout, false, st);
+    if (pairs) {
+      sb_table *right = nullptr;
+      try {
+        right = gather_table(build_view.t, out_build.as<int64_t>(), nout, kt_type == SB_JOIN_LEFT_OUTER, st);
+      } catch (...) {
+        table_free(left);
+        throw;
+      }
+      for (auto &c : right->cols) left->cols.push_back(c);
+      right->cols.clear();
+      table_free(right);
+    }
+    *out = left;
+    SB_CUDA(cudaStreamSynchronize(st));
+    return SB_OK;
+  }
   Scratch counts(nitems * 4 + 16, st), first(nitems * 4 + 16, st), block_counts((int64_t)nb * 4 + 16, st), offsets((int64_t)nb * 8 + 16, st);
   if (nitems > 0) {
     KernelTimer kt("join_probe", st);

@@ -145,12 +145,15 @@ def test_random_build_preserving_joins(gpu, stream, how, with_condition):
         assert _plan_join(left, right.slice(0, 0), ["k"], ["k2"], how, stream).num_rows == nl
 
 
-@pytest.mark.parametrize("how", ["inner", "left_outer", "left_semi", "left_anti"])
-@pytest.mark.parametrize("keys", ["dense", "sparse", "negative", "nullable"])
-def test_long_streamed_side_goes_through_the_candidate_pass(gpu, stream, how, keys):
+@pytest.mark.parametrize("how", ["inner", "left_outer", "left_semi", "left_anti", "left_anti_null_aware"])
+@pytest.mark.parametrize("keys", ["dense", "mid", "sparse", "negative", "nullable"])
+@pytest.mark.parametrize("unique", [False, True])
+def test_long_streamed_side_goes_through_the_candidate_pass(gpu, stream, how, keys, unique):
     """>= 2^20 streamed rows: one fused pass (pushed-down filter + key + prefilter) marks the candidates.  `dense` keys make the
     prefilter an exact key-range bitmap, `sparse` (60-bit) keys a Bloom filter; `negative` crosses zero; `nullable` takes the
-    general key path.  The streamed row count is not a multiple of 16 (ragged tail), the filter is either a conjunction of
+    general key path; `mid` is a key range too sparse for the direct-address table but dense enough for the bitmap.  With `unique`
+    build keys an exact prefilter settles semi / anti joins in the pass and inner / outer joins take one lookup per candidate (a
+    dense range through row_of[key - min]); duplicates go through count / scan / fill.  The streamed row count is not a multiple of 16 (ragged tail), the filter is either a conjunction of
     comparisons (evaluated inside the pass) or an OR (evaluated to a mask first)."""
     from spark_b200.columnar import ColumnarBatch
     from spark_b200.execution import BroadcastHashJoinExec, FilterExec, LocalTableScanExec
@@ -161,10 +164,13 @@ def test_long_streamed_side_goes_through_the_candidate_pass(gpu, stream, how, ke
         universe = rng.integers(0, 1 << 60, 4 * nb)
     elif keys == "negative":
         universe = np.arange(-2 * nb, 2 * nb, dtype=np.int64)
+    elif keys == "mid":
+        universe = np.arange(0, 20 * nb, dtype=np.int64) * 3 + 17
     else:
         universe = np.arange(1000, 1000 + 4 * nb, dtype=np.int64)
-    bk = rng.choice(universe, nb, replace=keys == "sparse")
-    bk[:100] = bk[100:200]                                     # duplicate build keys: the count / fill passes still see them
+    bk = rng.choice(universe, nb, replace=False)
+    if not unique:
+        bk[:100] = bk[100:200]                                 # duplicate build keys: the count / fill passes still see them
     pk = rng.choice(universe, npr)
     pmask = rng.random(npr) < 0.03 if keys == "nullable" else None
     build = pa.table({"id": pa.array(bk, type=pa.int64()), "payload": np.arange(nb, dtype=np.int64)})
@@ -177,6 +183,6 @@ def test_long_streamed_side_goes_through_the_candidate_pass(gpu, stream, how, ke
         want = O.hash_join(O.filter_table(probe, cond.sexpr()), build, ["fk"], ["id"], how)
         assert got.num_rows == want.num_rows
         assert_tables_equal(got, want, key_cols=list(want.column_names))
-        if how in ("inner", "left_semi", "left_anti"):   # streamed order is preserved
+        if how in ("inner", "left_semi", "left_anti", "left_anti_null_aware"):   # streamed order is preserved
             r = np.asarray(got.column("row"))
             assert np.all(r[1:] >= r[:-1])

@@ -147,7 +147,7 @@ def main():
             probe = ColumnarBatch.from_numpy({"fk": rng.integers(0, nb, npr), "x": np.arange(npr, dtype=np.int64)}, stream)
             stream.synchronize()
             j = BroadcastHashJoinExec(["fk"], ["id"], "inner", "right", LocalTableScanExec(probe), LocalTableScanExec(build))
-            ms, k = timed(lib, stream, lambda: j.executeColumnar(stream).close(), ["join_build", "join_probe", "join_fill"])
+            ms, k = timed(lib, stream, lambda: j.executeColumnar(stream).close(), ["join_build", "join_candidates", "join_probe", "join_fill", "gather"])
             emit("hash_join inner probe=%d build=%d" % (npr, nb), npr, nb * 16 + npr * 16 + npr * 32, ms, k)
             build.close(); probe.close()
 
