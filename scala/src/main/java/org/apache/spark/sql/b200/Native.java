@@ -83,4 +83,21 @@ public final class Native {
   public static native long joinProbe(long relation, long probe, int[] keyCols, int joinType, long stream);
   public static native long joinProbeCondition(long relation, long probe, int[] keyCols, int joinType, long conditionExpr, long stream);
   public static native void hashTableRelease(long relation);
+  /** the FilterExec below the build side fused into the build (rows failing it never enter the relation); filterExpr 0 = none */
+  public static native long joinBuildFiltered(long table, int[] keyCols, long filterExpr, long stream);
+  /** FilterExec below the streamed side and ProjectExec above the join fused into the probe; 0 / null = none / all columns */
+  public static native long joinProbeFused(long relation, long probe, int[] keyCols, int joinType, long probeFilterExpr,
+                                           int[] probeOutCols, int[] buildOutCols, long stream);
+
+  // ---- fused exchange: map side + transport in one collective (sb_shuffle_exchange) --------------------------------------------
+  public static native long shuffleExchange(long table, int[] keyCols, int numPartitions, long stream, long[] outPartOffsets);
+
+  // ---- columnar scan: Parquet column-chunk pages in pinned host memory -> Arrow columns in HBM ---------------------------------
+  /** page table of one column chunk: rows of {encoding, numValues, valuesOffset, valuesBytes, defOffset, defBytes}; the last row is
+   *  {dictOffset, dictCount, 0, 0, 0, 0} */
+  public static native long[] parquetChunkPages(long chunkAddress, long chunkBytes, int maxDefLevel);
+  /** one entry per column: decoded type / scale / Parquet physical type, the chunk's host address and size, and its page table as
+   *  parquetChunkPages returned it */
+  public static native long scanDecode(int[] types, int[] scales, int[] physicalTypes, long[] chunkAddresses, long[] chunkBytes,
+                                       long[][] pageTables, long stream);
 }

@@ -3,7 +3,7 @@
 #include <stdint.h>
 #include <stddef.h>
 typedef int32_t jint; typedef int64_t jlong; typedef int8_t jbyte; typedef uint8_t jboolean; typedef jint jsize;
-typedef void *jobject; typedef jobject jclass; typedef jobject jarray; typedef jarray jintArray; typedef jarray jlongArray; typedef jarray jbyteArray; typedef jarray jbooleanArray;
+typedef void *jobject; typedef jobject jclass; typedef jobject jarray; typedef jarray jintArray; typedef jarray jlongArray; typedef jarray jbyteArray; typedef jarray jbooleanArray; typedef jarray jobjectArray;
 #define JNIEXPORT
 #define JNICALL
 #define JNI_ABORT 2
@@ -24,4 +24,5 @@ struct JNINativeInterface_ {
   void (*GetByteArrayRegion)(JNIEnv *, jbyteArray, jsize, jsize, jbyte *);
   jlongArray (*NewLongArray)(JNIEnv *, jsize);
   void (*SetLongArrayRegion)(JNIEnv *, jlongArray, jsize, jsize, const jlong *);
+  jobject (*GetObjectArrayElement)(JNIEnv *, jobjectArray, jsize);
 };

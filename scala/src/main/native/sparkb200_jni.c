@@ -7,6 +7,7 @@
  */
 #include <jni.h>
 #include <stdlib.h>
+#include <string.h>
 #include "spark_b200.h"
 
 static void throw_if(JNIEnv *env, int rc) {
@@ -404,6 +405,124 @@ NATIVE(jlong, joinProbeCondition)(JNIEnv *env, jclass c, jlong rel, jlong probe,
   int rc = sb_join_probe_condition((const sb_hash_table *)(intptr_t)rel, TBL(probe), (const int32_t *)k, nk, joinType,
                                    (const sb_expr *)(intptr_t)cond, STR(stream), &out);
   (*env)->ReleaseIntArrayElements(env, keyCols, k, JNI_ABORT);
+  throw_if(env, rc);
+  return (jlong)(intptr_t)out;
+}
+
+NATIVE(jlong, joinBuildFiltered)(JNIEnv *env, jclass c, jlong table, jintArray keyCols, jlong filter, jlong stream) {
+  jsize nk = (*env)->GetArrayLength(env, keyCols);
+  jint *k = (*env)->GetIntArrayElements(env, keyCols, NULL);
+  sb_hash_table *out = NULL;
+  int rc = sb_join_build_filtered(TBL(table), (const int32_t *)k, nk, (const sb_expr *)(intptr_t)filter, STR(stream), &out);
+  (*env)->ReleaseIntArrayElements(env, keyCols, k, JNI_ABORT);
+  throw_if(env, rc);
+  return (jlong)(intptr_t)out;
+}
+NATIVE(jlong, joinProbeFused)(JNIEnv *env, jclass c, jlong rel, jlong probe, jintArray keyCols, jint joinType, jlong probeFilter,
+                              jintArray probeOut, jintArray buildOut, jlong stream) {
+  jsize nk = (*env)->GetArrayLength(env, keyCols);
+  jint *k = (*env)->GetIntArrayElements(env, keyCols, NULL);
+  jint *po = probeOut ? (*env)->GetIntArrayElements(env, probeOut, NULL) : NULL;
+  jint *bo = buildOut ? (*env)->GetIntArrayElements(env, buildOut, NULL) : NULL;
+  sb_join_options opt;
+  memset(&opt, 0, sizeof(opt));
+  opt.probe_filter = (const sb_expr *)(intptr_t)probeFilter;
+  opt.probe_out_cols = (const int32_t *)po;
+  opt.n_probe_out = po ? (*env)->GetArrayLength(env, probeOut) : 0;
+  opt.build_out_cols = (const int32_t *)bo;
+  opt.n_build_out = bo ? (*env)->GetArrayLength(env, buildOut) : 0;
+  sb_table *out = NULL;
+  int rc = sb_join_probe_ex((const sb_hash_table *)(intptr_t)rel, TBL(probe), (const int32_t *)k, nk, joinType, &opt, STR(stream), &out);
+  if (bo) (*env)->ReleaseIntArrayElements(env, buildOut, bo, JNI_ABORT);
+  if (po) (*env)->ReleaseIntArrayElements(env, probeOut, po, JNI_ABORT);
+  (*env)->ReleaseIntArrayElements(env, keyCols, k, JNI_ABORT);
+  throw_if(env, rc);
+  return (jlong)(intptr_t)out;
+}
+
+NATIVE(jlong, shuffleExchange)(JNIEnv *env, jclass c, jlong table, jintArray keyCols, jint n, jlong stream, jlongArray offsetsOut) {
+  jsize nk = (*env)->GetArrayLength(env, keyCols);
+  jint *k = (*env)->GetIntArrayElements(env, keyCols, NULL);
+  jlong *offs = (*env)->GetLongArrayElements(env, offsetsOut, NULL);
+  sb_table *out = NULL;
+  int rc = sb_shuffle_exchange(TBL(table), (const int32_t *)k, nk, n, STR(stream), &out, (int64_t *)offs);
+  (*env)->ReleaseIntArrayElements(env, keyCols, k, JNI_ABORT);
+  (*env)->ReleaseLongArrayElements(env, offsetsOut, offs, 0);
+  throw_if(env, rc);
+  return (jlong)(intptr_t)out;
+}
+
+/* page tables travel as long[6 * (npages + 1)]: npages rows of sb_page fields, then {dict_offset, dict_count, 0, 0, 0, 0} */
+#define SB_JNI_MAX_PAGES 65536
+NATIVE(jlongArray, parquetChunkPages)(JNIEnv *env, jclass c, jlong chunk, jlong nbytes, jint maxDef) {
+  sb_page *pages = (sb_page *)calloc(SB_JNI_MAX_PAGES, sizeof(sb_page));
+  int32_t npages = 0, dict_count = 0;
+  int64_t dict_offset = -1;
+  int rc = sb_parquet_chunk_pages((const uint8_t *)(intptr_t)chunk, nbytes, maxDef, pages, SB_JNI_MAX_PAGES, &npages, &dict_offset, &dict_count);
+  jlongArray out = NULL;
+  if (rc == SB_OK) {
+    jlong *flat = (jlong *)calloc((size_t)(npages + 1) * 6, sizeof(jlong));
+    for (int32_t i = 0; i < npages; i++) {
+      flat[6 * i + 0] = pages[i].encoding;
+      flat[6 * i + 1] = pages[i].num_values;
+      flat[6 * i + 2] = pages[i].values_offset;
+      flat[6 * i + 3] = pages[i].values_bytes;
+      flat[6 * i + 4] = pages[i].def_offset;
+      flat[6 * i + 5] = pages[i].def_bytes;
+    }
+    flat[6 * npages + 0] = dict_offset;
+    flat[6 * npages + 1] = dict_count;
+    out = (*env)->NewLongArray(env, (npages + 1) * 6);
+    (*env)->SetLongArrayRegion(env, out, 0, (npages + 1) * 6, flat);
+    free(flat);
+  }
+  free(pages);
+  throw_if(env, rc);
+  return out;
+}
+NATIVE(jlong, scanDecode)(JNIEnv *env, jclass c, jintArray types, jintArray scales, jintArray phys, jlongArray addrs, jlongArray sizes,
+                          jobjectArray pageTables, jlong stream) {
+  jsize ncols = (*env)->GetArrayLength(env, types);
+  jint *ty = (*env)->GetIntArrayElements(env, types, NULL), *sc = (*env)->GetIntArrayElements(env, scales, NULL);
+  jint *ph = (*env)->GetIntArrayElements(env, phys, NULL);
+  jlong *ad = (*env)->GetLongArrayElements(env, addrs, NULL), *sz = (*env)->GetLongArrayElements(env, sizes, NULL);
+  sb_column_chunk *chunks = (sb_column_chunk *)calloc((size_t)(ncols ? ncols : 1), sizeof(sb_column_chunk));
+  sb_page **owned = (sb_page **)calloc((size_t)(ncols ? ncols : 1), sizeof(sb_page *));
+  for (jsize i = 0; i < ncols; i++) {
+    jlongArray pt = (jlongArray)(*env)->GetObjectArrayElement(env, pageTables, i);
+    jsize words = (*env)->GetArrayLength(env, pt);
+    jlong *flat = (*env)->GetLongArrayElements(env, pt, NULL);
+    int32_t npages = (int32_t)(words / 6) - 1;
+    owned[i] = (sb_page *)calloc((size_t)(npages > 0 ? npages : 1), sizeof(sb_page));
+    for (int32_t p = 0; p < npages; p++) {
+      owned[i][p].encoding = (int32_t)flat[6 * p + 0];
+      owned[i][p].num_values = (int32_t)flat[6 * p + 1];
+      owned[i][p].values_offset = flat[6 * p + 2];
+      owned[i][p].values_bytes = flat[6 * p + 3];
+      owned[i][p].def_offset = flat[6 * p + 4];
+      owned[i][p].def_bytes = flat[6 * p + 5];
+    }
+    chunks[i].type = ty[i];
+    chunks[i].scale = sc[i];
+    chunks[i].physical_type = ph[i];
+    chunks[i].npages = npages;
+    chunks[i].data = (const uint8_t *)(intptr_t)ad[i];
+    chunks[i].data_bytes = sz[i];
+    chunks[i].pages = owned[i];
+    chunks[i].dict_offset = flat[6 * npages + 0];
+    chunks[i].dict_count = (int32_t)flat[6 * npages + 1];
+    (*env)->ReleaseLongArrayElements(env, pt, flat, JNI_ABORT);
+  }
+  sb_table *out = NULL;
+  int rc = sb_scan_decode(chunks, ncols, STR(stream), &out);
+  for (jsize i = 0; i < ncols; i++) free(owned[i]);
+  free(owned);
+  free(chunks);
+  (*env)->ReleaseLongArrayElements(env, sizes, sz, JNI_ABORT);
+  (*env)->ReleaseLongArrayElements(env, addrs, ad, JNI_ABORT);
+  (*env)->ReleaseIntArrayElements(env, phys, ph, JNI_ABORT);
+  (*env)->ReleaseIntArrayElements(env, scales, sc, JNI_ABORT);
+  (*env)->ReleaseIntArrayElements(env, types, ty, JNI_ABORT);
   throw_if(env, rc);
   return (jlong)(intptr_t)out;
 }

@@ -94,6 +94,44 @@ __device__ __forceinline__ uint32_t simple_pred_eval16(const SimplePred &sp, int
   }
   return keep & 0xFFFFu;
 }
+// the same predicate for ONE row (lane-strided kernels: the 32 lanes of a warp read 32 consecutive rows, so plain loads coalesce)
+__device__ __forceinline__ bool simple_pred_row(const SimplePred &sp, int64_t row) {
+  bool keep = true;
+#pragma unroll 1
+  for (int t = 0; t < sp.nterms; t++) {
+    if (sp.valid[t]) keep = keep && ((sp.valid[t][row >> 3] >> (row & 7)) & 1);
+    const int op = sp.op[t];
+    if (op == SP_NOTNULL) continue;
+    int64_t x;
+    switch (sp.type[t]) {
+      case SB_BOOL: x = ((const uint8_t *)sp.data[t])[row]; break;
+      case SB_INT8: x = ((const int8_t *)sp.data[t])[row]; break;
+      case SB_INT16: x = ((const int16_t *)sp.data[t])[row]; break;
+      case SB_INT32: case SB_DATE32: case SB_FLOAT32: x = ((const int32_t *)sp.data[t])[row]; break;
+      default: x = ((const int64_t *)sp.data[t])[row]; break;
+    }
+    int c;
+    if (sp.f64[t]) {   // SQLOrderingUtil.compareDoubles: NaN equals NaN and is larger than anything else
+      const double y = __longlong_as_double(sp.lit[t]);
+      const double d = sp.type[t] == SB_FLOAT32 ? (double)__int_as_float((int32_t)x) : __longlong_as_double(x);
+      const bool dn = d != d, yn = y != y;
+      c = d == y ? 0 : (dn || yn) ? (int)dn - (int)yn : (d < y ? -1 : 1);
+    } else {
+      c = x == sp.lit[t] ? 0 : (x < sp.lit[t] ? -1 : 1);
+    }
+    bool ok;
+    switch (op) {
+      case SP_EQ: ok = c == 0; break;
+      case SP_NE: ok = c != 0; break;
+      case SP_LT: ok = c < 0; break;
+      case SP_LE: ok = c <= 0; break;
+      case SP_GT: ok = c > 0; break;
+      default: ok = c >= 0; break;
+    }
+    keep = keep && ok;
+  }
+  return keep;
+}
 #endif
 
 }  // namespace sb
