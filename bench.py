@@ -292,6 +292,7 @@ def main():
     ap.add_argument("--shuffle-rows", type=int, default=96_000_000, help="rows per GPU of the shuffle leg (74 B/row)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-verify", action="store_true")
+    ap.add_argument("--profile-host", action="store_true", help="cProfile one untimed step of every join leg to stderr (debugging)")
     args = ap.parse_args()
     args.legs = [x for x in args.legs.split(",") if x]
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -407,18 +408,23 @@ def main():
         capi.check(lib.sb_profile_reset())
         barrier()
         l0 = capi.kernel_launch_count()
-        stream.record_start()
-        for _ in range(steps):
+        total_ms, per_step = 0.0, []
+        for _ in range(steps):                           # CUDA events on the operators' stream around every step
+            stream.record_start()
             step()
-        stream.record_stop()
-        total_ms = stream.elapsed_ms()
+            stream.record_stop()
+            per_step.append(stream.elapsed_ms())
+            total_ms += per_step[-1]
         barrier()
         launches = capi.kernel_launch_count() - l0
         prof = capi.profile_dump()                       # every device-timed section of the library
         for k in kernel_names:
             prof.setdefault(k, (0.0, 0))
         capi.check(lib.sb_profile_enable(0))
+        last_step_ms[:] = per_step
         return max_over_ranks(total_ms / steps), launches, prof
+
+    last_step_ms = []
 
     def time_e2e(step, steps):
         step()          # warm-up (allocator pools, compiled plans)
@@ -585,6 +591,16 @@ def main():
             out.close()
 
         steps = max(1, min(args.steps, args.leg_steps))
+        if args.profile_host and rank == 0:
+            import cProfile
+            import pstats
+            step_join()
+            pr = cProfile.Profile()
+            pr.enable()
+            step_join()
+            stream.synchronize()
+            pr.disable()
+            pstats.Stats(pr, stream=sys.stderr).sort_stats("cumulative").print_stats(25)
         ms, launches, prof = time_resident(step_join, steps, 2, ("join_build", "join_probe", "join_fill", "gather", "filter_project", "agg_update"))
         alg_bytes = sum(tpch.synth_rows(t, n_orders) * sum(tpch.synth_width(c) for c in cols) for t, cols in used.items())
         achieved = alg_bytes / (ms / 1000.0) / 1e9
@@ -623,7 +639,7 @@ def main():
         for p in pinned.values():
             p.close()
         legs[leg] = {"value": world * n_li / (ms / 1000.0), "unit": "rows/s", "ms_per_step": ms, "steps": steps, "rows_per_gpu": n_li,
-                     "gpu_launches": int(launches), "verified": verified,
+                     "gpu_launches": int(launches), "verified": verified, "step_ms": [round(x, 3) for x in last_step_ms],
                      "kernel_ms_per_step": {k: v[0] / steps for k, v in prof.items()},
                      "roofline": {"bound": "hbm", "kernel": "whole plan (sum of operator algorithmic bytes, SURVEY.md 8d: one read of every referenced column)",
                                   "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "frac_of_8tbs_nominal": achieved / 8000.0,
