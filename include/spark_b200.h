@@ -361,6 +361,46 @@ int sb_range_partition(const sb_table *in, const sb_sort_order *order, const sb_
 int sb_range_sample(const sb_table *in, const sb_sort_order *order, int64_t sample_size, uint64_t seed, sb_stream *s, sb_table **out);
 int sb_range_determine_bounds(const sb_table *sample, const sb_sort_order *order, int32_t num_partitions, sb_stream *s, sb_table **out);
 
+/* ---- WindowExec (SQLX/window/WindowExec.scala:90, WindowFunctionFrame.scala) and ExpandExec (SQLX/ExpandExec.scala:36) --------
+ *      sb_window: rows sorted by (partition columns ASC NULLS FIRST, orders) -- the child ordering the reference requires and the
+ *      order it emits -- followed by one column per window expression.  Ranking functions ignore the frame.  Frames: ROWS with any
+ *      bounds (lower / upper are row offsets, negative = PRECEDING, 0 = CURRENT ROW); RANGE with UNBOUNDED / CURRENT ROW bounds (0)
+ *      -- i.e. the default frames "RANGE UNBOUNDED PRECEDING .. CURRENT ROW" (with ORDER BY: peers included) and the whole
+ *      partition; min / max need lower = SB_UNBOUNDED_PRECEDING.  Result types: row_number / rank / dense_rank / ntile int32,
+ *      percent_rank / cume_dist double, count int64, sum int64 (integral input) or double, avg double, the rest the input type. */
+#define SB_WIN_ROW_NUMBER 1
+#define SB_WIN_RANK 2
+#define SB_WIN_DENSE_RANK 3
+#define SB_WIN_PERCENT_RANK 4
+#define SB_WIN_CUME_DIST 5
+#define SB_WIN_NTILE 6          /* param = buckets */
+#define SB_WIN_LAG 7            /* param = offset; NULL outside the partition */
+#define SB_WIN_LEAD 8
+#define SB_WIN_SUM 9
+#define SB_WIN_COUNT 10
+#define SB_WIN_AVG 11
+#define SB_WIN_MIN 12
+#define SB_WIN_MAX 13
+#define SB_WIN_FIRST_VALUE 14   /* respect nulls */
+#define SB_WIN_LAST_VALUE 15
+#define SB_FRAME_ROWS 0
+#define SB_FRAME_RANGE 1
+#define SB_UNBOUNDED_PRECEDING INT64_MIN
+#define SB_UNBOUNDED_FOLLOWING INT64_MAX
+typedef struct sb_window_spec {
+  int32_t func;         /* SB_WIN_* */
+  int32_t col;          /* input column (ignored by the ranking functions) */
+  int32_t frame_type;   /* SB_FRAME_* */
+  int32_t pad;
+  int64_t lower, upper;
+  int64_t param;
+} sb_window_spec;
+int sb_window(const sb_table *in, const int32_t *partition_cols, int32_t npart, const sb_sort_order *orders, int32_t norders,
+              const sb_window_spec *specs, int32_t nspecs, sb_stream *s, sb_table **out);
+/* ExpandExec: nlists projection lists of ncols expressions each (projections[l * ncols + c]); every input row yields nlists output
+ * rows, list 0 first (the reference's iteration order).  Column c must have one type in every list (NULL literals carry theirs). */
+int sb_expand(const sb_table *in, const sb_expr *projections, int32_t nlists, int32_t ncols, sb_stream *s, sb_table **out);
+
 /* ---- joins: BroadcastHashJoinExec / ShuffledHashJoinExec / SortMergeJoinExec replacement
  *      (SQLX/joins/HashJoin.scala:184-400, HashedRelation.scala:136-168).  A row with any NULL key
  *      never matches.  Output = probe(streamed) columns ++ build columns; semi/anti = probe only. ---- */

@@ -794,3 +794,195 @@ def decode_string_columns(table, dicts, as_type=None):
         t = as_type or pa.string()
         out = out.set_column(i, c, pa.array([None if v is None else (v.decode("utf-8") if t == pa.string() else v) for v in vals], type=t))
     return out
+
+
+# --------------------------------------------------------------------------- ExpandExec / WindowExec (test sizes: plain Python loops)
+def expand(table, projections, names):
+    """ExpandExec.doExecute (sql/core/.../execution/ExpandExec.scala:85-97): `iter.flatMap { input => groups.iterator.map(_(input)) }`:
+    for every input row, one output row per projection list, list 0 first.  projections: lists of expression s-exprs (eval_expr)."""
+    n = table.num_rows
+    cols = []
+    for c in range(len(names)):
+        per_list = []
+        for plist in projections:
+            e = plist[c]
+            if e[0] == "col":
+                per_list.append(table.column(e[1]).to_pylist())
+            else:
+                v, valid = eval_expr(e, table)
+                per_list.append([v[i].item() if valid[i] else None for i in range(n)])
+        cols.append([per_list[l][r] for r in range(n) for l in range(len(projections))])
+    out = {}
+    for c, name in enumerate(names):
+        e0 = projections[0][c]
+        t = table.column(e0[1]).type if e0[0] == "col" else None
+        out[name] = pa.array(cols[c], type=t) if t is not None else pa.array(cols[c])
+    return pa.table(out)
+
+
+def _norm_key(v):
+    if isinstance(v, float):
+        if v != v:
+            return ("nan",)
+        if v == 0.0:
+            return 0.0
+    return v
+
+
+def window(table, partition_cols, orders, specs):
+    """WindowExec (sql/core/.../window/WindowExec.scala:90-110 + WindowEvaluatorFactoryBase + WindowFunctionFrame.scala), one
+    partition at a time, the way the reference's frame classes walk it: growing frames accumulate as their upper bound moves,
+    shrinking frames are accumulated from the partition's end, sliding frames are re-evaluated over their rows.
+    orders: [(col, ascending, nulls_first)]; specs: [(func, col, (kind, lower, upper) | None, param, out_name)] with kind 'rows' |
+    'range', None bound = UNBOUNDED, 0 = CURRENT ROW, negative = PRECEDING (rows).  Default frame
+    (SpecifiedWindowFrame.defaultWindowFrame, windowExpressions.scala): RANGE UNBOUNDED PRECEDING..CURRENT ROW with an ORDER BY,
+    the whole partition without.  Output: rows sorted by partition keys (ASC NULLS FIRST) ++ orders, plus one column per spec."""
+    key_cols = list(partition_cols) + [o[0] for o in orders]
+    str_cols = [c for c in dict.fromkeys(key_cols) if pa.types.is_string(table.column(c).type) or pa.types.is_binary(table.column(c).type)]
+    enc, _ = encode_string_columns(table, str_cols) if str_cols else (table, {})
+    sort_orders = [(c, True, True) for c in partition_cols] + list(orders)
+    n = table.num_rows
+    perm = sort_permutation(enc, sort_orders) if sort_orders and n else np.arange(n, dtype=np.int64)
+    srt = take_table(table, perm)
+    senc = take_table(enc, perm)
+    pk = list(zip(*[[_norm_key(v) for v in senc.column(c).to_pylist()] for c in partition_cols])) if partition_cols else [()] * n
+    ok = list(zip(*[[_norm_key(v) for v in senc.column(o[0]).to_pylist()] for o in orders])) if orders else [()] * n
+    seg_start, seg_end, peer_start, peer_end = [0] * n, [0] * n, [0] * n, [0] * n
+    i = 0
+    while i < n:
+        j = i
+        while j < n and pk[j] == pk[i]:
+            j += 1
+        a = i
+        while a < j:
+            b = a
+            while b < j and ok[b] == ok[a]:
+                b += 1
+            for r in range(a, b):
+                seg_start[r], seg_end[r], peer_start[r], peer_end[r] = i, j, a, b
+            a = b
+        i = j
+    out = {name: srt.column(name) for name in srt.column_names}
+    import functools
+    fkey = functools.cmp_to_key(lambda x, y: int(_dcmp(x, y)))
+    seg_bounds = []
+    i = 0
+    while i < n:
+        seg_bounds.append((i, seg_end[i]))
+        i = seg_end[i]
+
+    def better(func, x, y):   # is y a better min / max than x?  doubles order like SQLOrderingUtil.compareDoubles
+        c = int(_dcmp(y, x)) if isinstance(x, float) else (y > x) - (y < x)
+        return c < 0 if func == "min" else c > 0
+
+    for func, col, frame, param, name in specs:
+        vals = srt.column(col).to_pylist() if col is not None else None
+        if frame is None:
+            frame = ("range", None, 0) if orders else ("rows", None, None)
+        kind, lower, upper = frame
+        res = [None] * n
+        for s, e in seg_bounds:
+            size = e - s
+            if func in ("row_number", "rank", "dense_rank", "percent_rank", "cume_dist", "ntile"):
+                dense = 0
+                bs, pad = (size // param, size % param) if func == "ntile" else (0, 0)
+                row_number = bucket = threshold = 0                       # NTile state (windowExpressions.scala NTile)
+                for r in range(s, e):
+                    rank = peer_start[r] - s + 1
+                    if peer_start[r] == r:
+                        dense += 1                                        # DenseRank: +1 at every change of the order key
+                    if func == "row_number":
+                        res[r] = r - s + 1
+                    elif func == "rank":
+                        res[r] = rank
+                    elif func == "dense_rank":
+                        res[r] = dense
+                    elif func == "percent_rank":                          # (rank - 1) / (n - 1), 0.0 for a single row
+                        res[r] = (rank - 1) / (size - 1) if size > 1 else 0.0
+                    elif func == "cume_dist":                             # rows up to and including the peers / n
+                        res[r] = (peer_end[r] - s) / size
+                    else:
+                        over = row_number >= threshold
+                        nb = bucket + (1 if over else 0)
+                        threshold = threshold + ((bs + (1 if bucket < pad else 0)) if over else 0)
+                        bucket = nb
+                        row_number += 1
+                        res[r] = bucket
+                continue
+            if func in ("lag", "lead"):                                   # FrameLessOffsetWindowFunctionFrame: NULL outside the partition
+                for r in range(s, e):
+                    q = r - param if func == "lag" else r + param
+                    res[r] = vals[q] if s <= q < e else None
+                continue
+
+            def bounds(r):
+                if kind == "range":
+                    return (s if lower is None else peer_start[r]), (e - 1 if upper is None else peer_end[r] - 1)
+                return (s if lower is None else max(s, r + lower)), (e - 1 if upper is None else min(e - 1, r + upper))
+
+            if func in ("first_value", "last_value"):
+                for r in range(s, e):
+                    lo, hi = bounds(r)
+                    res[r] = None if lo > hi else vals[lo if func == "first_value" else hi]
+                continue
+
+            def finish(acc_sum, acc_cnt, acc_best):
+                if func == "count":
+                    return acc_cnt
+                if func == "sum":
+                    return None if acc_cnt == 0 else (float(acc_sum) if is_f else _wrap64(acc_sum))
+                if func == "avg":
+                    return None if acc_cnt == 0 else acc_sum / acc_cnt
+                return acc_best
+
+            is_f = pa.types.is_floating(srt.column(col).type)
+            zero = 0.0 if (is_f or func == "avg") else 0
+            conv = (lambda x: float(x)) if (is_f or func == "avg") else (lambda x: x)
+
+            def fold(rows_iter, acc):
+                sm, cnt, best = acc
+                for q in rows_iter:
+                    x = vals[q]
+                    if x is None:
+                        continue
+                    sm += conv(x)
+                    cnt += 1
+                    if func in ("min", "max") and (best is None or better(func, best, x)):
+                        best = x
+                return sm, cnt, best
+
+            if lower is None:            # growing frame (UnboundedPrecedingWindowFunctionFrame): rows are added as the upper bound moves
+                acc, nxt = (zero, 0, None), s
+                for r in range(s, e):
+                    lo, hi = bounds(r)
+                    acc = fold(range(nxt, hi + 1), acc)
+                    nxt = max(nxt, hi + 1)
+                    res[r] = finish(*acc)
+            elif upper is None:          # shrinking frame (UnboundedFollowingWindowFunctionFrame), accumulated from the partition's end
+                acc, nxt = (zero, 0, None), e - 1
+                for r in range(e - 1, s - 1, -1):
+                    lo, hi = bounds(r)
+                    acc = fold(range(nxt, lo - 1, -1), acc)
+                    nxt = min(nxt, lo - 1)
+                    res[r] = finish(*acc)
+            else:                        # sliding frame (SlidingWindowFunctionFrame): re-evaluated over its rows
+                for r in range(s, e):
+                    lo, hi = bounds(r)
+                    res[r] = finish(*fold(range(lo, hi + 1), (zero, 0, None)))
+        if func in ("row_number", "rank", "dense_rank", "ntile"):
+            out[name] = pa.array(res, type=pa.int32())
+        elif func in ("percent_rank", "cume_dist", "avg"):
+            out[name] = pa.array(res, type=pa.float64())
+        elif func == "count":
+            out[name] = pa.array(res, type=pa.int64())
+        elif func == "sum":
+            t = srt.column(col).type
+            out[name] = pa.array(res, type=pa.float64() if pa.types.is_floating(t) else pa.int64())
+        else:
+            out[name] = pa.array(res, type=srt.column(col).type)
+    return pa.table(out)
+
+
+def _wrap64(x):
+    x &= (1 << 64) - 1
+    return x - (1 << 64) if x >= (1 << 63) else x

@@ -79,6 +79,17 @@ class sb_sort_order(C.Structure):
     _fields_ = [("col", C.c_int32), ("ascending", C.c_int32), ("nulls_first", C.c_int32), ("pad", C.c_int32)]
 
 
+class sb_window_spec(C.Structure):
+    _fields_ = [("func", C.c_int32), ("col", C.c_int32), ("frame_type", C.c_int32), ("pad", C.c_int32), ("lower", C.c_int64),
+                ("upper", C.c_int64), ("param", C.c_int64)]
+
+
+SB_WIN = {"row_number": 1, "rank": 2, "dense_rank": 3, "percent_rank": 4, "cume_dist": 5, "ntile": 6, "lag": 7, "lead": 8, "sum": 9,
+          "count": 10, "avg": 11, "min": 12, "max": 13, "first_value": 14, "last_value": 15}
+SB_FRAME_ROWS, SB_FRAME_RANGE = 0, 1
+SB_UNBOUNDED_PRECEDING, SB_UNBOUNDED_FOLLOWING = -(1 << 63), (1 << 63) - 1
+
+
 class SparkB200Error(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("libsparkb200 error %d: %s" % (code, msg))
@@ -113,6 +124,7 @@ _SIGNATURES = {
     "sb_table_slice": [_p, _i64, _i64, _p, _pp], "sb_table_concat": [_pp, _i32, _p, _pp],
     "sb_dictionary_encode": [_p, _i32, _p, _pp, _pp], "sb_dictionary_lookup": [_p, _i32, _p, _p, _pp],
     "sb_dictionary_decode": [_p, _i32, _p, _p, _pp],
+    "sb_window": [_p, C.POINTER(C.c_int32), _i32, C.POINTER(sb_sort_order), _i32, C.POINTER(sb_window_spec), _i32, _p, _pp], "sb_expand": [_p, _p, _i32, _i32, _p, _pp],
     "sb_parquet_chunk_pages": [_p, _i64, _i32, C.POINTER(sb_page), _i32, C.POINTER(_i32), C.POINTER(_i64), C.POINTER(_i32)],
     "sb_scan_decode": [C.POINTER(sb_column_chunk), _i32, _p, _pp],
     "sb_scan_encode": [_p, _i32, _p, _i64, _p, _pp, C.POINTER(sb_page), _i32, C.POINTER(_i32), C.POINTER(_i64), C.POINTER(_i32)],

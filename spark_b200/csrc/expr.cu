@@ -418,3 +418,52 @@ extern "C" int sb_filter_project(const sb_table *in, const sb_expr *predicate, c
   *out = t;
   SB_API_END
 }
+
+// ---- ExpandExec (SQLX/ExpandExec.scala:36-110): every projection list is evaluated over the whole input (nlists tables of n rows),
+// the tables are concatenated and one gather interleaves them so that row r of the input yields output rows r * nlists + l --
+// the order of the reference's `iter.flatMap { input => groups.iterator.map(_(input)) }`.
+__global__ void interleave_index_kernel(int64_t n, int32_t k, int64_t *__restrict__ idx) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n * k) idx[j] = (j % k) * n + j / k;
+}
+
+extern "C" int sb_expand(const sb_table *in, const sb_expr *projections, int32_t nlists, int32_t ncols, sb_stream *s, sb_table **out) {
+  SB_API_BEGIN
+  require_init();
+  SB_REQUIRE(in && out && projections && nlists >= 1 && ncols >= 1, "bad argument");
+  cudaStream_t st = stream_of(s);
+  const int64_t n = in->nrows;
+  std::vector<sb_table *> parts;
+  struct Free {
+    std::vector<sb_table *> &v;
+    ~Free() { for (auto *t : v) table_free(t); }
+  } guard{parts};
+  for (int l = 0; l < nlists; l++) {
+    sb_table *t = table_new(n);
+    parts.push_back(t);
+    for (int c = 0; c < ncols; c++) {
+      const sb_expr &e = projections[(int64_t)l * ncols + c];
+      expr_validate(in, e);
+      t->cols.push_back(eval_projection(in, e, nullptr, n, st));
+      if (l > 0) SB_REQUIRE(t->cols[c].type == parts[0]->cols[c].type, "expand: column %d has type %d in list %d and %d in list 0", c, t->cols[c].type, l, parts[0]->cols[c].type);
+    }
+  }
+  if (nlists == 1) {
+    *out = parts[0];
+    parts.clear();
+    return SB_OK;
+  }
+  sb_table *cat = nullptr;
+  {
+    int rc = sb_table_concat(parts.data(), nlists, s, &cat);
+    if (rc != SB_OK) fail(rc, "%s", sb_last_error());
+  }
+  struct FreeOne { sb_table *t; ~FreeOne() { if (t) table_free(t); } } g2{cat};
+  Scratch idx(n * nlists * 8 + 16, st);
+  if (n > 0) {
+    interleave_index_kernel<<<(unsigned)((n * nlists + 255) / 256), 256, 0, st>>>(n, nlists, idx.as<int64_t>());
+    SB_LAUNCH_CHECK();
+  }
+  *out = gather_table(cat, idx.as<int64_t>(), n * nlists, false, st);
+  SB_API_END
+}

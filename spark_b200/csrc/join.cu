@@ -33,6 +33,7 @@ struct sb_hash_table {
   Slot *slots = nullptr;            // [cap]; row == 0xFFFFFFFF means free
   int64_t cap = 0;
   int32_t nkeys = 0;
+  int32_t key_col[4];                 // build-side column index of every key
   int32_t key_type[4];
   int32_t key_bits[4];
   int32_t key_shift[4];
@@ -543,6 +544,7 @@ int sb_join_build_filtered(const sb_table *build, const int32_t *key_cols, int32
       ht->has_dict[i] = true;
       ht->dict[i] = column_share(*d);
     }
+    ht->key_col[i] = key_cols[i];
     ht->key_type[i] = k.type[i];
     ht->key_bits[i] = k.bits[i];
     ht->key_shift[i] = k.shift[i];
@@ -800,17 +802,56 @@ int sb_join_probe_ex(const sb_hash_table *ht, const sb_table *probe, const int32
       join_lookup_kernel<<<nb, JOIN_THREADS, 0, st>>>(k, rows, nout, ht->slots, ht->cap, kf, kt_type == SB_JOIN_LEFT_OUTER ? 1 : 0, out_build.as<int64_t>());
       SB_LAUNCH_CHECK();
     }
-    sb_table *left = gather_table(probe_view.t, rows, nout, false, st);
+    // every streamed row a candidate: the streamed half of the output is the input (shared buffers, no gather)
+    const bool identity = nout == n;
+    auto take_streamed = [&](const Column &c) { return identity ? column_share(c) : gather_column(c, rows, nout, false, st); };
+    sb_table *left = nullptr;
+    if (identity) {
+      left = table_new(n);
+      for (auto &c : probe_view.t->cols) left->cols.push_back(column_share(c));
+    } else {
+      left = gather_table(probe_view.t, rows, nout, false, st);
+    }
     if (pairs) {
+      // inner join: a build-side KEY column of the output holds, row for row, the values of the streamed side's key column
+      // (integer keys of one type compare equal only when they are the same bits), so it is taken from there -- a sequential
+      // read instead of a random gather over the build table
+      const int nb_cols = (int)build_view.t->cols.size();
+      std::vector<int> from_streamed(nb_cols, -1);
+      std::vector<Column> keyed;
+      sb_table *rest = table_new(ht->build->nrows);
       sb_table *right = nullptr;
       try {
-        right = gather_table(build_view.t, out_build.as<int64_t>(), nout, kt_type == SB_JOIN_LEFT_OUTER, st);
+        for (int j = 0; j < nb_cols; j++) {
+          const int bj = opt && opt->build_out_cols ? opt->build_out_cols[j] : j;
+          if (kt_type == SB_JOIN_INNER)
+            for (int i = 0; i < nkeys; i++) {
+              const Column &pc = probe->cols[key_cols[i]];
+              const int32_t t = ht->build->cols[bj].type;
+              if (ht->key_col[i] == bj && !ht->has_dict[i] && pc.type == t && t != SB_FLOAT32 && t != SB_FLOAT64 && t != SB_STRING) from_streamed[j] = key_cols[i];
+            }
+          if (from_streamed[j] < 0) rest->cols.push_back(column_share(build_view.t->cols[j]));
+        }
+        right = gather_table(rest, out_build.as<int64_t>(), nout, kt_type == SB_JOIN_LEFT_OUTER, st);
+        for (int j = 0; j < nb_cols; j++) {
+          if (from_streamed[j] < 0) continue;
+          const Column &bc = ht->build->cols[opt && opt->build_out_cols ? opt->build_out_cols[j] : j];
+          Column c = take_streamed(probe->cols[from_streamed[j]]);
+          c.type = bc.type;
+          c.scale = bc.scale;
+          keyed.push_back(c);
+        }
       } catch (...) {
+        for (auto &c : keyed) column_release(c);
+        table_free(rest);
+        if (right) table_free(right);
         table_free(left);
         throw;
       }
-      for (auto &c : right->cols) left->cols.push_back(c);
+      size_t next = 0, next_keyed = 0;   // nothing below throws
+      for (int j = 0; j < nb_cols; j++) left->cols.push_back(from_streamed[j] >= 0 ? keyed[next_keyed++] : right->cols[next++]);
       right->cols.clear();
+      table_free(rest);
       table_free(right);
     }
     *out = left;

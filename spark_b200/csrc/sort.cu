@@ -23,6 +23,7 @@
 #include "primitives.cuh"
 #include "radix.cuh"
 #include "strings.cuh"
+#include "sort.cuh"
 
 namespace sb {
 
@@ -195,7 +196,7 @@ __global__ void __launch_bounds__(SORT_THREADS) select_mask_kernel(const void *d
 static bool radix_eligible(int32_t type) { return type != SB_STRING; }
 
 // writes the sorted permutation (uint32 row ids) into perm (n entries)
-static void sort_permutation_impl(const sb_table *in, const sb_sort_order *orders, int32_t norders, uint32_t *perm, cudaStream_t st) {
+void sort_permutation_impl(const sb_table *in, const sb_sort_order *orders, int32_t norders, uint32_t *perm, cudaStream_t st) {
   const int64_t n = in->nrows;
   SB_REQUIRE(n < (1ll << 32), "tables of 2^32 rows or more must be sorted in chunks");
   SB_REQUIRE(norders >= 1 && orders, "sort needs at least one order");

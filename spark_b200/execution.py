@@ -718,3 +718,91 @@ def _substitute(e: Expression, mapping):
     elif hasattr(e2, "child"):
         e2.children = (e2.child,)
     return e2
+
+
+# ------------------------------------------------------------------------------------------------ f4: Expand / SortAggregate / Window
+class ExpandExec(SparkPlan):
+    """ExpandExec(projections, output, child) (sql/core/.../execution/ExpandExec.scala:36): every input row yields one output row
+    per projection list, list 0 first.  projections: [[Expression, ...], ...]; output: the column names.  ROLLUP / CUBE /
+    GROUPING SETS and multi-DISTINCT aggregates plan it below a HashAggregateExec."""
+
+    def __init__(self, projections, output, child: SparkPlan):
+        self.projections = [list(p) for p in projections]
+        self.output = list(output)
+        assert all(len(p) == len(self.output) for p in self.projections), "every projection list must produce the output schema"
+        self.child = child
+        self.children = (child,)
+
+    def executeColumnar(self, stream=None):
+        inp = self.child.executeColumnar(stream)
+        try:
+            schema = _schema_of(inp)
+            compiled = [CompiledExpr(e, schema) for p in self.projections for e in p]
+            arr = (capi.sb_expr * len(compiled))()
+            for i, c in enumerate(compiled):
+                arr[i] = c.c
+            h = C.c_void_p()
+            capi.check(capi.load().sb_expand(inp.handle, arr, len(self.projections), len(self.output), _h(stream), C.byref(h)))
+            ats = []
+            for c in range(len(self.output)):
+                e = self.projections[0][c]
+                ats.append(inp.arrow_types[schema.index(e.name)] if isinstance(e, AttributeReference) else None)
+            return ColumnarBatch(h, self.output, ats)
+        finally:
+            inp.close()
+
+
+class SortAggregateExec(HashAggregateExec):
+    """SortAggregateExec (sql/core/.../aggregate/SortAggregateExec.scala): the planner's choice when an aggregation buffer is not
+    mutable in an UnsafeRow (AggUtils.createAggregate).  It differs from HashAggregateExec in HOW groups are found (sorted input,
+    adjacent rows), not in what comes out -- one row per group, same buffer algebra -- so the device operator is the same."""
+
+
+class WindowFunction:
+    """One window expression: func in row_number | rank | dense_rank | percent_rank | cume_dist | ntile | lag | lead | sum |
+    count | avg | min | max | first_value | last_value; child = input column name (None for the ranking functions);
+    frame = ('rows' | 'range', lower, upper) with None = UNBOUNDED, 0 = CURRENT ROW, negative = PRECEDING (rows only);
+    default frame like SpecifiedWindowFrame.defaultWindowFrame: with ORDER BY range(UNBOUNDED, CURRENT ROW), else the partition."""
+
+    def __init__(self, func, child=None, frame=None, param=0, name=None):
+        self.func, self.child, self.frame, self.param = func, child, frame, param
+        self.name = name or func
+
+
+class WindowExec(SparkPlan):
+    """WindowExec(windowExpression, partitionSpec, orderSpec, child) (sql/core/.../window/WindowExec.scala:90).  Output: the
+    child's rows sorted by partitionSpec ++ orderSpec (the child ordering the reference requires) ++ one column per window
+    expression."""
+
+    def __init__(self, windowExpression, partitionSpec, orderSpec, child: SparkPlan):
+        self.windowExpression = list(windowExpression)
+        self.partitionSpec = list(partitionSpec)
+        self.orderSpec = [o if isinstance(o, SortOrder) else SortOrder(*o) for o in orderSpec]
+        self.child = child
+        self.children = (child,)
+
+    def executeColumnar(self, stream=None):
+        inp = self.child.executeColumnar(stream)
+        try:
+            part = (C.c_int32 * max(1, len(self.partitionSpec)))(*[inp.column_index(c) for c in self.partitionSpec])
+            specs = (capi.sb_window_spec * max(1, len(self.windowExpression)))()
+            out_types = []
+            for i, w in enumerate(self.windowExpression):
+                frame = w.frame
+                if frame is None:
+                    frame = ("range", None, 0) if self.orderSpec else ("rows", None, None)
+                kind, lo, hi = frame
+                specs[i].func = capi.SB_WIN[w.func]
+                specs[i].col = inp.column_index(w.child) if w.child is not None else 0
+                specs[i].frame_type = capi.SB_FRAME_RANGE if kind == "range" else capi.SB_FRAME_ROWS
+                specs[i].lower = capi.SB_UNBOUNDED_PRECEDING if lo is None else lo
+                specs[i].upper = capi.SB_UNBOUNDED_FOLLOWING if hi is None else hi
+                specs[i].param = w.param
+                keeps = w.func in ("lag", "lead", "min", "max", "first_value", "last_value")
+                out_types.append(inp.arrow_types[inp.column_index(w.child)] if keeps else None)
+            h = C.c_void_p()
+            capi.check(capi.load().sb_window(inp.handle, part, len(self.partitionSpec), _orders_c(inp, self.orderSpec), len(self.orderSpec),
+                                             specs, len(self.windowExpression), _h(stream), C.byref(h)))
+            return ColumnarBatch(h, inp.names + [w.name for w in self.windowExpression], inp.arrow_types + out_types)
+        finally:
+            inp.close()
