@@ -89,6 +89,15 @@ public final class Native {
   public static native long joinProbeFused(long relation, long probe, int[] keyCols, int joinType, long probeFilterExpr,
                                            int[] probeOutCols, int[] buildOutCols, long stream);
 
+  // ---- WindowExec / ExpandExec -------------------------------------------------------------------------------------------------------
+  /** one entry per window expression: SB_WIN_* code, input column, frame type (0 rows / 1 range), bounds (Long.MIN_VALUE /
+   *  Long.MAX_VALUE = UNBOUNDED, 0 = CURRENT ROW, negative = PRECEDING), parameter (ntile buckets, lag / lead offset) */
+  public static native long window(long table, int[] partitionCols, int[] orderCols, boolean[] ascending, boolean[] nullsFirst,
+                                   int[] funcs, int[] inputCols, int[] frameTypes, long[] lowers, long[] uppers, long[] params,
+                                   long stream);
+  /** projectionExprs: nlists * ncols expression handles, list-major */
+  public static native long expand(long table, long[] projectionExprs, int nlists, int ncols, long stream);
+
   // ---- fused exchange: map side + transport in one collective (sb_shuffle_exchange) --------------------------------------------
   public static native long shuffleExchange(long table, int[] keyCols, int numPartitions, long stream, long[] outPartOffsets);
 

@@ -409,6 +409,61 @@ NATIVE(jlong, joinProbeCondition)(JNIEnv *env, jclass c, jlong rel, jlong probe,
   return (jlong)(intptr_t)out;
 }
 
+NATIVE(jlong, window)(JNIEnv *env, jclass c, jlong table, jintArray partCols, jintArray orderCols, jbooleanArray asc, jbooleanArray nullsFirst,
+                      jintArray funcs, jintArray inputs, jintArray frameTypes, jlongArray lowers, jlongArray uppers, jlongArray params,
+                      jlong stream) {
+  jsize np = (*env)->GetArrayLength(env, partCols), no = (*env)->GetArrayLength(env, orderCols), ns = (*env)->GetArrayLength(env, funcs);
+  jint *pc = (*env)->GetIntArrayElements(env, partCols, NULL), *oc = (*env)->GetIntArrayElements(env, orderCols, NULL);
+  jboolean *a = (*env)->GetBooleanArrayElements(env, asc, NULL), *nf = (*env)->GetBooleanArrayElements(env, nullsFirst, NULL);
+  jint *fn = (*env)->GetIntArrayElements(env, funcs, NULL), *in = (*env)->GetIntArrayElements(env, inputs, NULL);
+  jint *ft = (*env)->GetIntArrayElements(env, frameTypes, NULL);
+  jlong *lo = (*env)->GetLongArrayElements(env, lowers, NULL), *hi = (*env)->GetLongArrayElements(env, uppers, NULL);
+  jlong *pa = (*env)->GetLongArrayElements(env, params, NULL);
+  sb_sort_order *orders = (sb_sort_order *)calloc((size_t)(no ? no : 1), sizeof(sb_sort_order));
+  sb_window_spec *specs = (sb_window_spec *)calloc((size_t)(ns ? ns : 1), sizeof(sb_window_spec));
+  for (jsize i = 0; i < no; i++) {
+    orders[i].col = oc[i];
+    orders[i].ascending = a[i] ? 1 : 0;
+    orders[i].nulls_first = nf[i] ? 1 : 0;
+  }
+  for (jsize i = 0; i < ns; i++) {
+    specs[i].func = fn[i];
+    specs[i].col = in[i];
+    specs[i].frame_type = ft[i];
+    specs[i].lower = lo[i];
+    specs[i].upper = hi[i];
+    specs[i].param = pa[i];
+  }
+  sb_table *out = NULL;
+  int rc = sb_window(TBL(table), (const int32_t *)pc, np, orders, no, specs, ns, STR(stream), &out);
+  free(specs);
+  free(orders);
+  (*env)->ReleaseLongArrayElements(env, params, pa, JNI_ABORT);
+  (*env)->ReleaseLongArrayElements(env, uppers, hi, JNI_ABORT);
+  (*env)->ReleaseLongArrayElements(env, lowers, lo, JNI_ABORT);
+  (*env)->ReleaseIntArrayElements(env, frameTypes, ft, JNI_ABORT);
+  (*env)->ReleaseIntArrayElements(env, inputs, in, JNI_ABORT);
+  (*env)->ReleaseIntArrayElements(env, funcs, fn, JNI_ABORT);
+  (*env)->ReleaseBooleanArrayElements(env, nullsFirst, nf, JNI_ABORT);
+  (*env)->ReleaseBooleanArrayElements(env, asc, a, JNI_ABORT);
+  (*env)->ReleaseIntArrayElements(env, orderCols, oc, JNI_ABORT);
+  (*env)->ReleaseIntArrayElements(env, partCols, pc, JNI_ABORT);
+  throw_if(env, rc);
+  return (jlong)(intptr_t)out;
+}
+NATIVE(jlong, expand)(JNIEnv *env, jclass c, jlong table, jlongArray exprs, jint nlists, jint ncols, jlong stream) {
+  jsize n = (*env)->GetArrayLength(env, exprs);
+  jlong *e = (*env)->GetLongArrayElements(env, exprs, NULL);
+  sb_expr *progs = (sb_expr *)calloc((size_t)(n ? n : 1), sizeof(sb_expr));
+  for (jsize i = 0; i < n; i++) progs[i] = *(const sb_expr *)(intptr_t)e[i];
+  sb_table *out = NULL;
+  int rc = n == (jsize)nlists * ncols ? sb_expand(TBL(table), progs, nlists, ncols, STR(stream), &out) : SB_ERR_INVALID;
+  free(progs);
+  (*env)->ReleaseLongArrayElements(env, exprs, e, JNI_ABORT);
+  throw_if(env, rc);
+  return (jlong)(intptr_t)out;
+}
+
 NATIVE(jlong, joinBuildFiltered)(JNIEnv *env, jclass c, jlong table, jintArray keyCols, jlong filter, jlong stream) {
   jsize nk = (*env)->GetArrayLength(env, keyCols);
   jint *k = (*env)->GetIntArrayElements(env, keyCols, NULL);

@@ -20,7 +20,8 @@ package org.apache.spark.sql.b200
 import org.apache.spark.sql.SparkSessionExtensions
 import org.apache.spark.sql.catalyst.rules.Rule
 import org.apache.spark.sql.execution._
-import org.apache.spark.sql.execution.aggregate.HashAggregateExec
+import org.apache.spark.sql.execution.aggregate.{HashAggregateExec, SortAggregateExec}
+import org.apache.spark.sql.execution.window.WindowExec
 import org.apache.spark.sql.execution.exchange.{BroadcastExchangeExec, ShuffleExchangeExec}
 import org.apache.spark.sql.execution.joins.{BroadcastHashJoinExec, ShuffledHashJoinExec, SortMergeJoinExec}
 
@@ -43,6 +44,11 @@ object B200ColumnarRule extends ColumnarRule {
       case agg: HashAggregateExec if GpuSupport.supports(agg) =>
         val collapsed = GpuSupport.collapse(agg)          // (condition, aggregate inputs over source attributes, source plan)
         GpuHashAggregateExec(agg, collapsed.condition, collapsed.inputs, collapsed.source)
+      case agg: SortAggregateExec if GpuSupport.supports(agg) =>           // same answer as the hash aggregate: one device operator
+        val collapsed = GpuSupport.collapse(agg)
+        GpuHashAggregateExec(agg, collapsed.condition, collapsed.inputs, collapsed.source)
+      case e: ExpandExec if GpuSupport.supports(e) => GpuExpandExec(e.projections, e.output, e.child)
+      case w: WindowExec if GpuSupport.supports(w) => GpuWindowExec(w.windowExpression, w.partitionSpec, w.orderSpec, w.child)
       case s: SortExec if GpuSupport.supports(s) => GpuSortExec(s.sortOrder, s.global, s.child)
       case t: TakeOrderedAndProjectExec if GpuSupport.supports(t) =>
         GpuTakeOrderedAndProjectExec(t.limit, t.sortOrder, t.projectList, t.child)

@@ -6,7 +6,7 @@ import org.apache.spark.sql.catalyst.optimizer.{BuildLeft, BuildRight, BuildSide
 import org.apache.spark.sql.catalyst.plans._
 import org.apache.spark.sql.catalyst.plans.physical._
 import org.apache.spark.sql.execution._
-import org.apache.spark.sql.execution.aggregate.HashAggregateExec
+import org.apache.spark.sql.execution.aggregate.BaseAggregateExec
 import org.apache.spark.sql.execution.metric.{SQLMetric, SQLMetrics}
 import org.apache.spark.sql.types.DataType
 import org.apache.spark.sql.vectorized.ColumnarBatch
@@ -18,7 +18,7 @@ import org.apache.spark.sql.vectorized.ColumnarBatch
  * concatenated.  `condition` / `inputs` are the Filter / Project chain GpuSupport.collapse folded into the aggregate.
  */
 case class GpuHashAggregateExec(
-    cpu: HashAggregateExec,
+    cpu: BaseAggregateExec,                   // HashAggregateExec, or SortAggregateExec (same answer, same device operator)
     condition: Option[Expression],
     inputs: Seq[Option[Expression]],          // one per aggregate function: its argument over `child`'s attributes (None: count(*))
     child: SparkPlan) extends UnaryExecNode with GpuExec {
@@ -230,6 +230,57 @@ case class GpuHashJoinExec(
     }
   }
   override protected def withNewChildrenInternal(l: SparkPlan, r: SparkPlan): SparkPlan = copy(left = l, right = r)
+}
+
+/**
+ * ExpandExec (SQLX/ExpandExec.scala:36): every input row yields one output row per projection list, list 0 first -- sb_expand.
+ * ROLLUP / CUBE / GROUPING SETS and multi-DISTINCT aggregates plan it below an aggregate.
+ */
+case class GpuExpandExec(projections: Seq[Seq[Expression]], output: Seq[Attribute], child: SparkPlan) extends UnaryExecNode with GpuExec {
+  override def outputPartitioning: Partitioning = UnknownPartitioning(0)                         // ExpandExec.scala:55-61
+  override protected def doExecuteColumnar(): RDD[ColumnarBatch] = {
+    val childTypes = child.output.map(_.dataType).toArray
+    val outTypes = output.map(_.dataType).toArray
+    val programs = projections.flatten.map(e => ExprCompiler.compile(e, child.output))
+    val (nlists, ncols) = (projections.length, output.length)
+    child.executeColumnar().mapPartitions { batches =>
+      val stream = taskStream()
+      val exprs = programs.map(_.create()).toArray
+      Option(org.apache.spark.TaskContext.get()).foreach(_.addTaskCompletionListener[Unit](_ => exprs.foreach(Native.exprFree)))
+      batches.map { b =>
+        val in = DeviceTransfer.toDevice(b, childTypes, stream)
+        try new DeviceBatch(Native.expand(in.table, exprs, nlists, ncols, stream), outTypes): ColumnarBatch finally in.close()
+      }
+    }
+  }
+  override protected def withNewChildInternal(c: SparkPlan): SparkPlan = copy(child = c)
+}
+
+/**
+ * WindowExec (SQLX/window/WindowExec.scala:90) -- sb_window.  The reference requires its child sorted by partitionSpec ++ orderSpec
+ * (WindowExecBase.requiredChildOrdering) and plans a SortExec for that; the device operator sorts the partition itself, so only the
+ * clustering requirement is kept and the output carries the ordering.
+ */
+case class GpuWindowExec(windowExpression: Seq[NamedExpression], partitionSpec: Seq[Expression], orderSpec: Seq[SortOrder], child: SparkPlan)
+  extends UnaryExecNode with GpuExec {
+  override def output: Seq[Attribute] = child.output ++ windowExpression.map(_.toAttribute)
+  override def outputPartitioning: Partitioning = child.outputPartitioning
+  override def outputOrdering: Seq[SortOrder] = partitionSpec.map(SortOrder(_, Ascending)) ++ orderSpec
+  override def requiredChildDistribution: Seq[Distribution] =                                    // WindowExecBase.scala
+    if (partitionSpec.isEmpty) AllTuples :: Nil else ClusteredDistribution(partitionSpec) :: Nil
+  override protected def doExecuteColumnar(): RDD[ColumnarBatch] = {
+    val childTypes = child.output.map(_.dataType).toArray
+    val outTypes = output.map(_.dataType).toArray
+    val w = GpuSupport.lowerWindow(org.apache.spark.sql.execution.window.WindowExec(windowExpression, partitionSpec, orderSpec, child)).get
+    child.executeColumnar().mapPartitions { batches =>
+      val stream = taskStream()
+      val in = GpuSupport.concatToDevice(batches, childTypes, stream)      // a window needs the whole partition
+      if (in == null) Iterator.empty
+      else try Iterator.single(new DeviceBatch(Native.window(in.table, w.partition, w.orderCols, w.asc, w.nullsFirst, w.funcs, w.inputs,
+        w.frameTypes, w.lowers, w.uppers, w.params, stream), outTypes): ColumnarBatch) finally in.close()
+    }
+  }
+  override protected def withNewChildInternal(c: SparkPlan): SparkPlan = copy(child = c)
 }
 
 /** RowToColumnarExec replacement (Columnar.scala:503-546): the child's host batches become HBM batches. */

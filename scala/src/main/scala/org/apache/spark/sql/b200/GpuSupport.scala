@@ -9,7 +9,8 @@ import org.apache.spark.sql.catalyst.optimizer.{BuildLeft, BuildRight, BuildSide
 import org.apache.spark.sql.catalyst.plans._
 import org.apache.spark.sql.catalyst.plans.physical._
 import org.apache.spark.sql.execution._
-import org.apache.spark.sql.execution.aggregate.HashAggregateExec
+import org.apache.spark.sql.execution.aggregate.{BaseAggregateExec, HashAggregateExec, SortAggregateExec}
+import org.apache.spark.sql.execution.window.WindowExec
 import org.apache.spark.sql.execution.exchange.{BroadcastExchangeExec, ShuffleExchangeExec}
 import org.apache.spark.sql.execution.joins.{BroadcastHashJoinExec, ShuffledHashJoinExec, SortMergeJoinExec}
 import org.apache.spark.sql.internal.SQLConf
@@ -27,10 +28,15 @@ object GpuSupport {
   private def fixedWidth(dt: DataType): Boolean = typeOk(dt) && dt != StringType && dt != BinaryType
   private def outputOk(p: SparkPlan): Boolean = p.output.forall(a => typeOk(a.dataType))
   private def exprOk(e: Expression): Boolean = ExprCompiler.supported(e)
+  /** grouping / join / sort keys: fixed-width types, and strings (order-preserving dictionary codes inside the library) */
+  private def keyOk(dt: DataType): Boolean = fixedWidth(dt) || dt == StringType
 
-  def supports(agg: HashAggregateExec): Boolean =
+  def supports(agg: HashAggregateExec): Boolean = aggregateOk(agg)
+  /** SortAggregateExec differs from HashAggregateExec in how groups are found, not in what comes out: same device operator */
+  def supports(agg: SortAggregateExec): Boolean = aggregateOk(agg)
+  private def aggregateOk(agg: BaseAggregateExec): Boolean =
     !agg.isStreaming && outputOk(agg.child) &&
-      agg.groupingExpressions.forall(g => g.isInstanceOf[AttributeReference] && fixedWidth(g.dataType)) &&
+      agg.groupingExpressions.forall(g => g.isInstanceOf[AttributeReference] && keyOk(g.dataType)) &&
       agg.groupingExpressions.length <= 6 &&
       agg.aggregateExpressions.forall { ae =>
         !ae.isDistinct && ae.filter.isEmpty && (ae.aggregateFunction match {
@@ -43,13 +49,13 @@ object GpuSupport {
         })
       }
   def supports(s: SortExec): Boolean = outputOk(s.child) &&
-    s.sortOrder.forall(o => o.child.isInstanceOf[AttributeReference] && fixedWidth(o.child.dataType))
+    s.sortOrder.forall(o => o.child.isInstanceOf[AttributeReference] && keyOk(o.child.dataType))
   def supports(t: TakeOrderedAndProjectExec): Boolean = t.offset == 0 && outputOk(t.child) &&
-    t.sortOrder.forall(o => o.child.isInstanceOf[AttributeReference] && fixedWidth(o.child.dataType)) && t.projectList.forall(exprOk)
+    t.sortOrder.forall(o => o.child.isInstanceOf[AttributeReference] && keyOk(o.child.dataType)) && t.projectList.forall(exprOk)
   private def joinOk(leftKeys: Seq[Expression], rightKeys: Seq[Expression], jt: JoinType, cond: Option[Expression], l: SparkPlan,
                      r: SparkPlan): Boolean =
     outputOk(l) && outputOk(r) && leftKeys.length <= 4 &&
-      (leftKeys ++ rightKeys).forall(k => k.isInstanceOf[AttributeReference] && fixedWidth(k.dataType)) &&
+      (leftKeys ++ rightKeys).forall(k => k.isInstanceOf[AttributeReference] && keyOk(k.dataType)) &&
       leftKeys.map(k => keyBits(k.dataType)).sum <= 64 && cond.forall(exprOk) &&                 // HashJoin.rewriteKeyExpr packing
       (jt match { case _: InnerLike | LeftOuter | RightOuter | FullOuter | LeftSemi | LeftAnti | _: ExistenceJoin => true; case _ => false })
   def supports(j: BroadcastHashJoinExec): Boolean = joinOk(j.leftKeys, j.rightKeys, j.joinType, j.condition, j.left, j.right)
@@ -65,6 +71,65 @@ object GpuSupport {
     })
   def supports(b: BroadcastExchangeExec): Boolean = outputOk(b.child) && !b.child.output.exists(_.dataType == StringType)
   def supports(f: FilterExec): Boolean = outputOk(f.child) && exprOk(f.condition)
+  def supports(e: ExpandExec): Boolean = outputOk(e.child) && e.output.forall(a => fixedWidth(a.dataType) || a.dataType == StringType) &&
+    e.projections.forall(_.forall(exprOk))
+  def supports(w: WindowExec): Boolean = outputOk(w.child) && lowerWindow(w).isDefined
+
+  // ---- WindowExec -> sb_window_spec arrays ---------------------------------------------------------------------------------------
+  final case class WindowLowered(partition: Array[Int], orderCols: Array[Int], asc: Array[Boolean], nullsFirst: Array[Boolean],
+                                 funcs: Array[Int], inputs: Array[Int], frameTypes: Array[Int], lowers: Array[Long], uppers: Array[Long],
+                                 params: Array[Long])
+  private def bound(e: Expression, lower: Boolean): Option[Long] = e match {
+    case UnboundedPreceding => Some(Long.MinValue)                       // SB_UNBOUNDED_PRECEDING
+    case UnboundedFollowing => Some(Long.MaxValue)                       // SB_UNBOUNDED_FOLLOWING
+    case CurrentRow => Some(0L)
+    case Literal(v: Int, IntegerType) => Some(v.toLong)
+    case UnaryMinus(Literal(v: Int, IntegerType), _) => Some(-v.toLong)
+    case _ => None
+  }
+  /** None when some expression has no device form (value-offset RANGE frames, ignoreNulls, expression inputs, ...) */
+  def lowerWindow(w: WindowExec): Option[WindowLowered] = {
+    val in = w.child.output
+    def ord(e: Expression): Option[Int] = e match {
+      case a: AttributeReference => Some(in.indexWhere(_.exprId == a.exprId)).filter(_ >= 0)
+      case _ => None
+    }
+    if (!w.partitionSpec.forall(p => ord(p).isDefined && keyOk(p.dataType))) return None
+    if (!w.orderSpec.forall(o => ord(o.child).isDefined && keyOk(o.child.dataType))) return None
+    if (w.partitionSpec.length + w.orderSpec.length > 8) return None
+    val specs = w.windowExpression.map {
+      case Alias(WindowExpression(fn, WindowSpecDefinition(_, _, SpecifiedWindowFrame(ft, lo, hi))), _) =>
+        val frameType = if (ft == RangeFrame) 1 else 0
+        val bounds = for (l <- bound(lo, lower = true); h <- bound(hi, lower = false)) yield (l, h)
+        val rangeOk = frameType == 0 || bounds.exists { case (l, h) => (l == Long.MinValue || l == 0L) && (h == Long.MaxValue || h == 0L) }
+        def agg(code: Int, c: Expression): Option[(Int, Int, Int, Long, Long, Long)] =
+          for (i <- ord(c); (l, h) <- bounds if rangeOk && fixedWidth(c.dataType) && !c.dataType.isInstanceOf[DecimalType]) yield (code, i, frameType, l, h, 0L)
+        fn match {
+          case _: RowNumber => Some((1, 0, 0, 0L, 0L, 0L))
+          case _: Rank => Some((2, 0, 0, 0L, 0L, 0L))
+          case _: DenseRank => Some((3, 0, 0, 0L, 0L, 0L))
+          case _: PercentRank => Some((4, 0, 0, 0L, 0L, 0L))
+          case _: CumeDist => Some((5, 0, 0, 0L, 0L, 0L))
+          case NTile(Literal(n: Int, IntegerType)) => Some((6, 0, 0, 0L, 0L, n.toLong))
+          case Lag(c, Literal(k: Int, IntegerType), Literal(null, _), false) => ord(c).map(i => (7, i, 0, 0L, 0L, math.abs(k).toLong))
+          case Lead(c, Literal(k: Int, IntegerType), Literal(null, _), false) => ord(c).map(i => (8, i, 0, 0L, 0L, k.toLong))
+          case AggregateExpression(Sum(c, _), Complete, false, None, _) => agg(9, c)
+          case AggregateExpression(Count(Seq(c)), Complete, false, None, _) => agg(10, c)
+          case AggregateExpression(Average(c, _), Complete, false, None, _) => agg(11, c)
+          case AggregateExpression(Min(c), Complete, false, None, _) => agg(12, c).filter(_._4 == Long.MinValue)
+          case AggregateExpression(Max(c), Complete, false, None, _) => agg(13, c).filter(_._4 == Long.MinValue)
+          case AggregateExpression(First(c, false), Complete, false, None, _) => for (i <- ord(c); (l, h) <- bounds if rangeOk) yield (14, i, frameType, l, h, 0L)
+          case AggregateExpression(Last(c, false), Complete, false, None, _) => for (i <- ord(c); (l, h) <- bounds if rangeOk) yield (15, i, frameType, l, h, 0L)
+          case _ => None
+        }
+      case _ => None
+    }
+    if (specs.exists(_.isEmpty)) return None
+    val f = specs.map(_.get)
+    val (oc, asc, nf) = orders(w.orderSpec, in)
+    Some(WindowLowered(ordinals(w.partitionSpec, in), oc, asc, nf, f.map(_._1).toArray, f.map(_._2).toArray, f.map(_._3).toArray,
+      f.map(_._4).toArray, f.map(_._5).toArray, f.map(_._6).toArray))
+  }
   def supports(p: ProjectExec): Boolean = outputOk(p.child) && p.projectList.forall(e => exprOk(e) && typeOk(e.dataType))
 
   private def keyBits(dt: DataType): Int = dt match {
@@ -77,7 +142,7 @@ object GpuSupport {
   // ---- Filter / Project folding under an aggregate (composed top-down, like spark_b200/execution.py B200ColumnarRule) -------
   final case class Collapsed(condition: Option[Expression], inputs: Seq[Option[Expression]], source: SparkPlan)
 
-  def collapse(agg: HashAggregateExec): Collapsed = {
+  def collapse(agg: BaseAggregateExec): Collapsed = {
     // aggregate inputs: Partial / Complete read the function's children, Final / PartialMerge read the buffer columns positionally
     var inputs: Seq[Option[Expression]] = agg.aggregateExpressions.map { ae =>
       if (ae.mode == Final || ae.mode == PartialMerge) None else ae.aggregateFunction.children.headOption
