@@ -17,6 +17,7 @@
 #include "primitives.cuh"
 #include "rtc.cuh"
 #include "comm.cuh"
+#include "strings.cuh"
 
 namespace sb {
 
@@ -336,8 +337,8 @@ int sb_exchange_plan(const int64_t *part_offsets, int32_t num_partitions, int32_
   SB_API_END
 }
 
-int sb_all_to_all(const sb_table *in, const int64_t *part_offsets_host, int32_t num_partitions, sb_stream *s, sb_table **out,
-                  int64_t *out_part_offsets_host) {
+static int all_to_all_fixed(const sb_table *in, const int64_t *part_offsets_host, int32_t num_partitions, sb_stream *s, sb_table **out,
+                            int64_t *out_part_offsets_host) {
   SB_API_BEGIN
   require_init();
   SB_REQUIRE(in && part_offsets_host && out && out_part_offsets_host, "null argument");
@@ -641,7 +642,7 @@ int sb_exchange_counts(const int64_t *part_offsets_host, int32_t num_partitions,
   SB_API_END
 }
 
-int sb_all_gather(const sb_table *in, sb_stream *s, sb_table **out) {
+static int all_gather_fixed(const sb_table *in, sb_stream *s, sb_table **out) {
   SB_API_BEGIN
   require_init();
   SB_REQUIRE(in && out, "null argument");
@@ -789,6 +790,182 @@ int sb_all_gather(const sb_table *in, sb_stream *s, sb_table **out) {
     throw;
   }
   *out = t;
+  SB_API_END
+}
+
+// ---- string columns in the collectives ----------------------------------------------------------------------------------------------
+// The transports above move fixed-width columns.  Strings ride on them:
+//   all-gather : a string column travels as its int32 LENGTHS (a fixed-width column that keeps the validity) plus one more
+//                all-gather of the byte arena; rank order is row order, so the concatenated arenas are the result's arena and an
+//                exclusive scan of the lengths gives its offsets;
+//   all-to-all : the column is dictionary-encoded locally (csrc/strings.cu), the int32 codes are exchanged together with a hidden
+//                "source rank" column, the (small) dictionaries are all-gathered, every received code is rebased by its source's
+//                offset into the concatenation of the dictionaries and decoded.  Low-cardinality columns (flags, names, dates as
+//                text) move 4 bytes per row; a column of unique strings moves its dictionary to every rank -- correct, not cheap.
+__global__ void lengths_kernel(const int32_t *__restrict__ off, const uint8_t *__restrict__ valid, int64_t n, int32_t *__restrict__ len) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) len[i] = bit_valid(valid, i) ? off[i + 1] - off[i] : 0;
+}
+__global__ void fill_i32_kernel(int32_t *out, int64_t n, int32_t v) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = v;
+}
+__global__ void rebase_codes_kernel(int32_t *__restrict__ codes, const uint8_t *__restrict__ valid, const int32_t *__restrict__ src_rank,
+                                    const int64_t *__restrict__ base, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && bit_valid(valid, i)) codes[i] += (int32_t)base[src_rank[i]];
+}
+
+static bool has_string_column(const sb_table *t) {
+  for (auto &c : t->cols)
+    if (c.type == SB_STRING) return true;
+  return false;
+}
+static void check_rc(int rc) {
+  if (rc != SB_OK) fail(rc, "%s", sb_last_error());
+}
+struct TableHold {
+  sb_table *t = nullptr;
+  ~TableHold() { if (t) table_free(t); }
+};
+
+int sb_all_gather(const sb_table *in, sb_stream *s, sb_table **out) {
+  if (!in || !has_string_column(in) || !comm().comm) return all_gather_fixed(in, s, out);
+  SB_API_BEGIN
+  require_init();
+  SB_REQUIRE(out, "null argument");
+  cudaStream_t st = stream_of(s);
+  const int64_t n = in->nrows;
+  TableHold fixed, moved;
+  fixed.t = table_new(n);
+  for (auto &c : in->cols) {
+    if (c.type != SB_STRING) {
+      fixed.t->cols.push_back(column_share(c));
+      continue;
+    }
+    Column len = column_alloc(SB_INT32, 0, n, false, st);
+    if (n > 0) {
+      lengths_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c.o(), c.v(), n, (int32_t *)len.data->ptr);
+      SB_LAUNCH_CHECK();
+    }
+    if (c.validity) {
+      buffer_retain(c.validity);
+      len.validity = c.validity;
+      len.null_count = c.null_count;
+    }
+    fixed.t->cols.push_back(len);
+  }
+  check_rc(all_gather_fixed(fixed.t, s, &moved.t));
+  const int64_t total = moved.t->nrows;
+  SB_REQUIRE(total < (1ll << 31), "all-gather of a string column: too many rows");
+  for (size_t ci = 0; ci < in->cols.size(); ci++) {
+    const Column &c = in->cols[ci];
+    if (c.type != SB_STRING) continue;
+    TableHold bytes, bytes_all;
+    int64_t nbytes = 0;
+    if (n > 0) {   // bytes in use = offsets[n] (NULL rows own no bytes in a compact arena; a sparse one is shipped as it is)
+      int32_t last = 0;
+      SB_CUDA(cudaMemcpyAsync(&last, c.o() + n, 4, cudaMemcpyDeviceToHost, st));
+      SB_CUDA(cudaStreamSynchronize(st));
+      nbytes = last;
+    }
+    bytes.t = table_new(nbytes);
+    {
+      Column b;
+      b.type = SB_INT8;
+      b.length = nbytes;
+      b.null_count = 0;
+      b.data = c.data;
+      buffer_retain(b.data);
+      bytes.t->cols.push_back(b);
+    }
+    check_rc(all_gather_fixed(bytes.t, s, &bytes_all.t));
+    SB_REQUIRE(bytes_all.t->nrows < (1ll << 31), "all-gather of a string column: more than 2 GiB of characters");
+    Column &lens = moved.t->cols[ci];
+    Column r;
+    r.type = SB_STRING;
+    r.length = total;
+    r.null_count = lens.null_count;
+    r.string_bytes = bytes_all.t->nrows;
+    r.offsets = buffer_alloc((total + 1) * 4 + 16, st);
+    Scratch tot(4, st);
+    // NULL rows were given length 0 above, but their arena bytes (if any) travelled: offsets must follow the ARENA, so a sparse
+    // arena is not supported here -- producers in this library (gather, decode, import) write compact arenas
+    exclusive_scan_i32((const int32_t *)lens.d(), (int32_t *)r.offsets->ptr, total, tot.as<int32_t>(), st);
+    SB_CUDA(cudaMemcpyAsync((int32_t *)r.offsets->ptr + total, tot.ptr, 4, cudaMemcpyDeviceToDevice, st));
+    r.data = bytes_all.t->cols[0].data;
+    buffer_retain(r.data);
+    r.validity = lens.validity;
+    if (r.validity) buffer_retain(r.validity);
+    column_release(lens);
+    lens = r;
+  }
+  *out = moved.t;
+  moved.t = nullptr;
+  SB_CUDA(cudaStreamSynchronize(st));
+  SB_API_END
+}
+
+int sb_all_to_all(const sb_table *in, const int64_t *part_offsets_host, int32_t num_partitions, sb_stream *s, sb_table **out,
+                  int64_t *out_part_offsets_host) {
+  if (!in || !has_string_column(in)) return all_to_all_fixed(in, part_offsets_host, num_partitions, s, out, out_part_offsets_host);
+  SB_API_BEGIN
+  require_init();
+  SB_REQUIRE(out && part_offsets_host && out_part_offsets_host, "null argument");
+  Comm &c = comm();
+  SB_REQUIRE(c.comm, "sb_all_to_all needs an initialised communicator (sb_comm_init)");
+  cudaStream_t st = stream_of(s);
+  const int64_t n = in->nrows;
+  std::vector<int> scols;
+  for (size_t ci = 0; ci < in->cols.size(); ci++)
+    if (in->cols[ci].type == SB_STRING) scols.push_back((int)ci);
+  EncodedView ev;
+  encode_string_columns(in, scols, nullptr, st, ev);
+  TableHold fixed, moved;
+  fixed.t = table_new(n);
+  for (auto &col : ev.view->cols) fixed.t->cols.push_back(column_share(col));
+  {
+    Column src = column_alloc(SB_INT32, 0, n, false, st);
+    if (n > 0) {
+      fill_i32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((int32_t *)src.data->ptr, n, c.rank);
+      SB_LAUNCH_CHECK();
+    }
+    fixed.t->cols.push_back(src);
+  }
+  check_rc(all_to_all_fixed(fixed.t, part_offsets_host, num_partitions, s, &moved.t, out_part_offsets_host));
+  const int64_t m = moved.t->nrows;
+  const Column src_rank = moved.t->cols.back();
+  for (int ci : scols) {
+    const Column *dict = ev.dictionary_of(ci);
+    TableHold dt, dall;
+    dt.t = table_new(dict->length);
+    dt.t->cols.push_back(column_share(*dict));
+    check_rc(sb_all_gather(dt.t, s, &dall.t));
+    std::vector<int64_t> sizes(c.nranks), base(c.nranks);
+    const int64_t mine = dict->length;
+    comm_allgather_host(&mine, 1, sizes.data(), st);
+    int64_t acc = 0;
+    for (int r = 0; r < c.nranks; r++) {
+      base[r] = acc;
+      acc += sizes[r];
+    }
+    SB_REQUIRE(acc < (1ll << 31), "exchange of a string column: the dictionaries of all ranks exceed 2^31 entries");
+    Scratch dbase((int64_t)c.nranks * 8, st);
+    SB_CUDA(cudaMemcpyAsync(dbase.ptr, base.data(), (size_t)c.nranks * 8, cudaMemcpyHostToDevice, st));
+    Column &codes = moved.t->cols[ci];
+    if (m > 0) {
+      rebase_codes_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>((int32_t *)codes.data->ptr, codes.v(), (const int32_t *)src_rank.d(), dbase.as<int64_t>(), m);
+      SB_LAUNCH_CHECK();
+    }
+    Column decoded = dictionary_decode(codes, dall.t->cols[0], st);
+    SB_CUDA(cudaStreamSynchronize(st));   // `base` (host) and `dbase` are done with
+    column_release(codes);
+    codes = decoded;
+  }
+  column_release(moved.t->cols.back());
+  moved.t->cols.pop_back();
+  *out = moved.t;
+  moved.t = nullptr;
   SB_API_END
 }
 

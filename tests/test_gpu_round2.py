@@ -113,7 +113,11 @@ def test_self_exchange_through_the_communicator(one_rank_comm, stream, path, sbc
     t = pa.table({"k": pa.array(rng.integers(0, 50_000, n), mask=rng.random(n) < 0.03),
                   "d": pa.array(rng.integers(8000, 9000, n).astype(np.int32)).cast(pa.date32()),
                   "v": pa.array(rng.random(n), mask=rng.random(n) < 0.05),
-                  "f": rng.integers(0, 3, n).astype(np.int8), "row": np.arange(n, dtype=np.int64)})
+                  "f": rng.integers(0, 3, n).astype(np.int8), "row": np.arange(n, dtype=np.int64),
+                  # string columns ride on the fixed-width transport: dictionary codes in the all-to-all, lengths + arena in the
+                  # all-gather (csrc/comm.cu)
+                  "s": pa.array(np.array(["", "N", "R", "A", "BUILDING", "你好", "x" * 40])[rng.integers(0, 7, n)], type=pa.string(),
+                                mask=rng.random(n) < 0.04)})
     batch = ColumnarBatch.from_arrow(t, stream)
     ex = ShuffleExchangeExec(HashPartitioning(["k", "d"], nparts), LocalTableScanExec(batch))
     out = ex.executeColumnar(stream)

@@ -1,8 +1,8 @@
 #!/bin/bash
 cd /root/repo
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_join.py tests/test_gpu_round2.py -x -q -m gpu > gpurun_out/r11_tests.log 2>&1
-echo "tests rc=$?"; tail -6 gpurun_out/r11_tests.log
+python -m pytest tests/test_gpu_window.py tests/test_gpu_strings.py tests/test_gpu_join.py tests/test_gpu_round2.py -x -q -m gpu > gpurun_out/r11_tests.log 2>&1
+echo "tests rc=$?"; tail -12 gpurun_out/r11_tests.log
 timeout 900 python bench.py --steps 5 --legs q3,q5 --no-cpu-baseline --profile-host > gpurun_out/r11_bench_q35_sf100.json 2> gpurun_out/r11_bench_q35.err
 echo "bench rc=$?"; python - <<'PY'
 import json
@@ -11,5 +11,5 @@ try:
     for k,l in d["legs"].items(): print(k, l["ms_per_step"], l.get("step_ms"), l["verified"], {a:round(b,3) for a,b in l["kernel_ms_per_step"].items()}, l["e2e"]["ms_per_step"], l["roofline"]["frac"])
 except Exception as e: print("ERR",e)
 PY
-grep -v "^$" gpurun_out/r11_bench_q35.err | head -90 | cut -c1-200
+grep -v "^$" gpurun_out/r11_bench_q35.err | head -70 | cut -c1-200
 python tools/op_bench.py join > gpurun_out/r11_op_join.jsonl 2> gpurun_out/r11_op_join.err; echo "join rc=$?"; cut -c1-620 gpurun_out/r11_op_join.jsonl

@@ -26,7 +26,10 @@ def shard(rank, n=200_000):
                      "d": pa.array(rng.integers(8000, 9000, n).astype(np.int32)).cast(pa.date32()),
                      # NULLs on odd ranks only: even ranks ship this column without a validity bitmap, the exchange must still agree
                      "v": pa.array(rng.random(n), mask=(rng.random(n) < 0.05) if rank % 2 else None),
-                     "f": rng.integers(0, 3, n).astype(np.int8)})
+                     "f": rng.integers(0, 3, n).astype(np.int8),
+                     # a string column (rank-dependent vocabulary): codes + dictionaries in the all-to-all, lengths + arena in the all-gather
+                     "s": pa.array(np.array(["", "N", "R", "rank%d" % rank, "BUILDING", "你好", "x" * (20 + rank)])[rng.integers(0, 7, n)],
+                                   type=pa.string(), mask=rng.random(n) < 0.04)})
 
 
 def main():
