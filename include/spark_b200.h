@@ -57,11 +57,17 @@ extern "C" {
 #define SB_TIMESTAMP 9   /* microseconds, int64 */
 #define SB_DECIMAL64 10  /* precision <= 18: unscaled int64 + scale */
 #define SB_STRING 11     /* int32 offsets + byte arena */
+#define SB_DECIMAL128 12 /* precision <= 38: unscaled two's-complement int128, little endian (Arrow decimal128) + scale.  A payload /
+                            result type (import, export, gather, slice, concat, SUM / AVG buffers and results); not a key type. */
+/* decimal columns: sb_column.scale = scale | precision << 8 (precision 0 = not given: the type's maximum, 18 / 38) */
+#define SB_DECIMAL_SCALE(x) ((x) & 0xff)
+#define SB_DECIMAL_PRECISION(x) (((x) >> 8) & 0xff)
+#define SB_DECIMAL_TYPE(precision, scale) (((precision) << 8) | (scale))
 
 /* One column of a batch: the C image of a ColumnVector (CATJ/vectorized/ColumnVector.java:63-366). */
 typedef struct sb_column {
   int32_t type;             /* SB_* */
-  int32_t scale;            /* decimal scale, else 0 */
+  int32_t scale;            /* decimals: SB_DECIMAL_TYPE(precision, scale); else 0 */
   int64_t length;           /* rows */
   int64_t null_count;       /* -1 = unknown */
   const void *data;         /* values; SB_STRING: byte arena */

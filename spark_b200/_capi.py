@@ -16,7 +16,7 @@ HEADER_PATH = os.path.join(_HERE, "..", "include", "spark_b200.h")
 # ---- constants (mirrors of the #defines) -------------------------------------------------------
 SB_OK = 0
 (SB_BOOL, SB_INT8, SB_INT16, SB_INT32, SB_INT64, SB_FLOAT32, SB_FLOAT64, SB_DATE32, SB_TIMESTAMP, SB_DECIMAL64,
- SB_STRING) = range(1, 12)
+ SB_STRING, SB_DECIMAL128) = range(1, 13)
 SB_OP = dict(COL=1, LIT_I64=2, LIT_F64=3, LIT_NULL=4, ADD=10, SUB=11, MUL=12, DIV=13, NEG=14, EQ=20, NE=21, LT=22,
              LE=23, GT=24, GE=25, AND=30, OR=31, NOT=32, ISNULL=33, ISNOTNULL=34, CAST_F64=40, CAST_I64=41, CAST_I32=42)
 SB_VT_BOOL, SB_VT_I32, SB_VT_I64, SB_VT_F64 = 1, 2, 3, 4
@@ -26,7 +26,7 @@ SB_JOIN = dict(inner=0, left_outer=1, left_semi=2, left_anti=3, full_outer=4, bu
 SB_UNIQUE_ID_BYTES = 128
 
 TYPE_WIDTH = {SB_BOOL: 1, SB_INT8: 1, SB_INT16: 2, SB_INT32: 4, SB_INT64: 8, SB_FLOAT32: 4, SB_FLOAT64: 8,
-              SB_DATE32: 4, SB_TIMESTAMP: 8, SB_DECIMAL64: 8, SB_STRING: 0}
+              SB_DATE32: 4, SB_TIMESTAMP: 8, SB_DECIMAL64: 8, SB_STRING: 0, SB_DECIMAL128: 16}
 
 
 class sb_column(C.Structure):

@@ -29,6 +29,8 @@ _SB2NP = {capi.SB_BOOL: np.uint8, capi.SB_INT8: np.int8, capi.SB_INT16: np.int16
 def sb_type_of(arrow_type) -> int:
     if pa.types.is_timestamp(arrow_type):
         return capi.SB_TIMESTAMP
+    if pa.types.is_decimal(arrow_type):      # Decimal.scala: precision <= 18 is a long of unscaled values, else 128 bits
+        return capi.SB_DECIMAL64 if arrow_type.precision <= 18 else capi.SB_DECIMAL128
     try:
         return _ARROW2SB[arrow_type]
     except KeyError:
@@ -127,6 +129,20 @@ class HostColumn:
             offs = np.frombuffer(bufs[1], dtype=np.int32, count=n + 1).copy() if n else np.zeros(1, np.int32)
             data = np.frombuffer(bufs[2], dtype=np.uint8).copy() if bufs[2] is not None else np.zeros(0, np.uint8)
             return HostColumn(t, data, validity, offs, arr.null_count, n)
+        if t in (capi.SB_DECIMAL64, capi.SB_DECIMAL128):
+            # Arrow decimal128: 16-byte little-endian two's complement unscaled values
+            raw = np.frombuffer(pa.concat_arrays([arr]).buffers()[1], dtype=np.int64, count=2 * n).reshape(n, 2) if n else np.zeros((0, 2), np.int64)
+            vals = np.ascontiguousarray(raw[:, 0]) if t == capi.SB_DECIMAL64 else np.ascontiguousarray(raw).reshape(-1)
+            if arr.null_count:
+                vals = vals.copy()
+                nulls = ~np.asarray(arr.is_valid())
+                if t == capi.SB_DECIMAL64:
+                    vals[nulls] = 0
+                else:
+                    vals.reshape(n, 2)[nulls] = 0
+            h = HostColumn(t, vals, validity, None, arr.null_count, n)
+            h.scale = (arr.type.precision << 8) | arr.type.scale
+            return h
         if t == capi.SB_BOOL:
             vals = np.asarray(arr.fill_null(False)).astype(np.uint8)
         elif t == capi.SB_DATE32:
@@ -140,7 +156,7 @@ class HostColumn:
     def c(self) -> capi.sb_column:
         s = capi.sb_column()
         s.type = self.type
-        s.scale = 0
+        s.scale = getattr(self, "scale", 0)
         s.length = self.length
         s.null_count = self.null_count
         s.data = self.data.ctypes.data if self.data is not None and self.data.size else None
@@ -234,7 +250,7 @@ class ColumnarBatch:
                                                 offs.ctypes.data, C.byref(nulls), _h(stream)))
             vals = (offs, data[: int(sb.value)])
         else:
-            vals = np.zeros(n, _SB2NP[d.type])
+            vals = np.zeros(2 * n, np.int64) if d.type == capi.SB_DECIMAL128 else np.zeros(n, _SB2NP[d.type])
             capi.check(lib.sb_table_export_host(self.handle, i, vals.ctypes.data if n else None,
                                                 bm.ctypes.data if bm is not None else None, None, C.byref(nulls), _h(stream)))
         valid = None
@@ -252,6 +268,19 @@ class ColumnarBatch:
                 offs, data = vals
                 vb = None if valid is None else pa.py_buffer(np.packbits(valid, bitorder="little").tobytes())
                 arr = pa.Array.from_buffers(pa.string(), int(d.length), [vb, pa.py_buffer(offs.tobytes()), pa.py_buffer(data.tobytes())])
+            elif d.type in (capi.SB_DECIMAL64, capi.SB_DECIMAL128):
+                n = int(d.length)
+                prec, scale = (d.scale >> 8) & 0xff, d.scale & 0xff
+                if prec == 0:
+                    prec = 18 if d.type == capi.SB_DECIMAL64 else 38
+                if d.type == capi.SB_DECIMAL64:
+                    wide = np.empty((n, 2), np.int64)
+                    wide[:, 0] = vals
+                    wide[:, 1] = vals >> 63            # sign extension
+                else:
+                    wide = vals.reshape(n, 2)
+                vb = None if valid is None else pa.py_buffer(np.packbits(valid, bitorder="little").tobytes())
+                arr = pa.Array.from_buffers(pa.decimal128(prec, scale), n, [vb, pa.py_buffer(np.ascontiguousarray(wide).tobytes())])
             elif d.type == capi.SB_BOOL:
                 arr = pa.array(vals.astype(bool), mask=mask)
             elif d.type == capi.SB_DATE32:

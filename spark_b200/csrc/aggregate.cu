@@ -37,6 +37,7 @@
 #include "primitives.cuh"
 #include "rtc.cuh"
 #include "strings.cuh"
+#include "decimal.cuh"
 
 namespace sb {
 
@@ -491,6 +492,7 @@ struct AggBuilder {
       SB_REQUIRE(col >= 0 && col < (int)in->cols.size(), "aggregate input column %d out of range", col);
       const Column &c = in->cols[col];
       if (c.type == SB_STRING) fail(SB_ERR_UNSUPPORTED, "aggregates over string columns are not supported");
+      if (c.type == SB_DECIMAL128) fail(SB_ERR_UNSUPPORTED, "MIN / MAX / COUNT over decimal(p > 18) columns are not supported");
       s.nf = 1;
       s.f[0].data = c.d(); s.f[0].valid = nulls_of(c); s.f[0].type = c.type; s.f[0].mode = F_COL;
       *src_type = c.type;
@@ -569,6 +571,7 @@ static void hash_aggregate_fixed(const sb_table *in, const sb_agg_plan *plan, cu
     SB_REQUIRE(ci >= 0 && ci < (int)in->cols.size(), "key column %d out of range", ci);
     const Column &c = in->cols[ci];
     SB_REQUIRE(c.type != SB_STRING, "string grouping keys reach the kernels as dictionary codes");
+    if (c.type == SB_DECIMAL128) fail(SB_ERR_UNSUPPORTED, "decimal(p > 18) grouping keys are not supported");
     key_refs[k] = {c.d(), nulls_of(c), c.type};
     m.key_type[k] = c.type;
     m.key_bits[k] = type_width(c.type) * 8;
@@ -1048,7 +1051,17 @@ extern "C" int32_t sb_agg_plan_meta_words(void) { return (int32_t)(sizeof(PlanMe
 // String grouping keys (HashAggregateExec groups UTF8String keys by their bytes): the key column is replaced by its
 // order-preserving dictionary codes (csrc/strings.cu), the fixed-width kernels group the codes, and the key columns of the result
 // are decoded back.  Every mode works the same way -- a Final / PartialMerge input carries decoded strings again.
+static void hash_aggregate_strings(const sb_table *in, const sb_agg_plan *plan, cudaStream_t st, sb_table **out);
+// decimal SUM / AVG first (limb sums around the aggregate, csrc/decimal.cu), then string keys (dictionary codes), then the kernels
 static void hash_aggregate_impl(const sb_table *in, const sb_agg_plan *plan, cudaStream_t st, sb_table **out) {
+  SB_REQUIRE(in && plan && out, "null argument");
+  if (plan_has_decimal_sums(in, plan)) {
+    hash_aggregate_decimals(in, plan, st, hash_aggregate_strings, out);
+    return;
+  }
+  hash_aggregate_strings(in, plan, st, out);
+}
+static void hash_aggregate_strings(const sb_table *in, const sb_agg_plan *plan, cudaStream_t st, sb_table **out) {
   SB_REQUIRE(in && plan && out, "null argument");
   std::vector<int> scols;
   for (int k = 0; k < plan->nkeys; k++) {

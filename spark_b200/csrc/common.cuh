@@ -70,6 +70,7 @@ inline int type_width(int32_t t) {
     case SB_INT32: case SB_FLOAT32: case SB_DATE32: return 4;
     case SB_INT64: case SB_FLOAT64: case SB_TIMESTAMP: case SB_DECIMAL64: return 8;
     case SB_STRING: return 0;
+    case SB_DECIMAL128: return 16;
   }
   fail(SB_ERR_INVALID, "unknown column type %d", t);
 }

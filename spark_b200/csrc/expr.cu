@@ -58,7 +58,7 @@ void expr_validate(const sb_table *in, const sb_expr &e) {
   bool has_decimal = false, only_null_tests = true;
   for (int i = 0; i < e.n; i++) {
     const sb_expr_node &nd = e.nodes[i];
-    if (nd.op == SB_OP_COL && nd.arg >= 0 && nd.arg < (int)in->cols.size() && in->cols[nd.arg].type == SB_DECIMAL64) has_decimal = true;
+    if (nd.op == SB_OP_COL && nd.arg >= 0 && nd.arg < (int)in->cols.size() && (in->cols[nd.arg].type == SB_DECIMAL64 || in->cols[nd.arg].type == SB_DECIMAL128)) has_decimal = true;
     if (nd.op != SB_OP_COL && nd.op != SB_OP_ISNULL && nd.op != SB_OP_ISNOTNULL && nd.op != SB_OP_AND && nd.op != SB_OP_OR && nd.op != SB_OP_NOT)
       only_null_tests = false;
   }

@@ -776,7 +776,8 @@ static void partition_impl(const sb_table *in, const int32_t *key_cols, int32_t 
   keys.n = 0;
   if (mode == 0) keys = make_keys(in, key_cols, nkeys);
   int64_t rowbytes = 0;
-  for (auto &c : in->cols) rowbytes += c.type == SB_STRING ? 8 : type_width(c.type);   // strings travel as row ids
+  auto by_row_id = [](const Column &c) { return c.type == SB_STRING || c.type == SB_DECIMAL128; };   // moved by one gather at the end
+  for (auto &c : in->cols) rowbytes += by_row_id(c) ? 8 : type_width(c.type);
   const bool big_tiles = nparts >= 64 && rowbytes >= 32;
   PartGeometry g = part_geometry(n, nparts, big_tiles);
   Scratch pid(n * 4 + 16, st);
@@ -794,13 +795,13 @@ static void partition_impl(const sb_table *in, const int32_t *key_cols, int32_t 
   sb_table *t = table_new(n);
   try {
     bool need_perm = false;
-    for (auto &c : in->cols) need_perm |= c.type == SB_STRING;
+    for (auto &c : in->cols) need_perm |= by_row_id(c);
     Scratch perm(need_perm ? n * 8 + 8 : 0, st);
     t->cols.resize(in->cols.size());
     std::vector<SplitCol> sc;
     for (size_t i = 0; i < in->cols.size(); i++) {
       const Column &c = in->cols[i];
-      if (c.type == SB_STRING) continue;
+      if (by_row_id(c)) continue;
       Column r = column_alloc(c.type, c.scale, n, c.validity != nullptr, st);
       if (r.validity) SB_CUDA(cudaMemsetAsync(r.validity->ptr, 0xff, (size_t)bitmap_alloc_bytes(n), st));
       r.null_count = c.null_count;
@@ -811,7 +812,7 @@ static void partition_impl(const sb_table *in, const int32_t *key_cols, int32_t 
                        need_perm ? perm.as<int64_t>() : nullptr, offs_dev.as<int64_t>(), st);
     if (need_perm) {
       for (size_t i = 0; i < in->cols.size(); i++)
-        if (in->cols[i].type == SB_STRING) t->cols[i] = gather_column(in->cols[i], perm.as<int64_t>(), n, false, st);
+        if (by_row_id(in->cols[i])) t->cols[i] = gather_column(in->cols[i], perm.as<int64_t>(), n, false, st);
     }
     SB_CUDA(cudaMemcpyAsync(out_offsets_host, offs_dev.ptr, (size_t)(nparts + 1) * 8, cudaMemcpyDeviceToHost, st));
     SB_CUDA(cudaStreamSynchronize(st));
@@ -1073,7 +1074,7 @@ int sb_shuffle_exchange(const sb_table *in, const int32_t *key_cols, int32_t nke
   require_init();
   SB_REQUIRE(in && out && out_part_offsets_host, "null argument");
   bool has_string = false;
-  for (auto &c : in->cols) has_string |= c.type == SB_STRING;
+  for (auto &c : in->cols) has_string |= c.type == SB_STRING || c.type == SB_DECIMAL128;   // not moved by the fused kernels
   if (!has_string && !config().exchange_nccl && shuffle_exchange_impl(in, key_cols, nkeys, num_partitions, stream_of(s), out, out_part_offsets_host))
     return SB_OK;
   sb_table *parted = nullptr;

@@ -126,6 +126,7 @@ __global__ void __launch_bounds__(256) gather_fixed_kernel(GatherArgs a, const i
         case 1: ((uint8_t *)a.dst[c])[i] = ((const uint8_t *)a.src[c])[j]; break;
         case 2: ((uint16_t *)a.dst[c])[i] = ((const uint16_t *)a.src[c])[j]; break;
         case 4: ((uint32_t *)a.dst[c])[i] = ((const uint32_t *)a.src[c])[j]; break;
+        case 16: ((uint4 *)a.dst[c])[i] = ((const uint4 *)a.src[c])[j]; break;
         default: ((uint64_t *)a.dst[c])[i] = ((const uint64_t *)a.src[c])[j]; break;
       }
     } else if (in_range) {
@@ -133,6 +134,7 @@ __global__ void __launch_bounds__(256) gather_fixed_kernel(GatherArgs a, const i
         case 1: ((uint8_t *)a.dst[c])[i] = 0; break;
         case 2: ((uint16_t *)a.dst[c])[i] = 0; break;
         case 4: ((uint32_t *)a.dst[c])[i] = 0; break;
+        case 16: ((uint4 *)a.dst[c])[i] = make_uint4(0, 0, 0, 0); break;
         default: ((uint64_t *)a.dst[c])[i] = 0; break;
       }
     }

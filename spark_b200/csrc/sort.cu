@@ -203,6 +203,7 @@ void sort_permutation_impl(const sb_table *in, const sb_sort_order *orders, int3
   std::vector<int> scols;
   for (int k = 0; k < norders; k++) {
     SB_REQUIRE(orders[k].col >= 0 && orders[k].col < (int)in->cols.size(), "sort column %d out of range", orders[k].col);
+    if (in->cols[orders[k].col].type == SB_DECIMAL128) fail(SB_ERR_UNSUPPORTED, "decimal(p > 18) sort keys are not supported");
     if (!radix_eligible(in->cols[orders[k].col].type)) scols.push_back(orders[k].col);
   }
   if (n == 0) return;
