@@ -517,6 +517,7 @@ static bool is_float_type(int32_t t) { return t == SB_FLOAT32 || t == SB_FLOAT64
 struct OutPlan {   // one output column
   int op, out_type, slot, slot2, xform;
   bool nullable;
+  int32_t scale = 0;   // decimals: the source column's (precision, scale) for MIN / MAX
 };
 
 static int64_t next_pow2(int64_t x) {
@@ -729,7 +730,12 @@ static void hash_aggregate_fixed(const sb_table *in, const sb_agg_plan *plan, cu
       case SB_AGG_MIN: case SB_AGG_MAX: {
         int32_t src_type;
         HostSlot s = final_mode ? buffer_source(next_buf_col) : b.source_for(sp.input, &src_type);
-        if (final_mode) { src_type = in->cols[next_buf_col].type; next_buf_col++; }
+        int32_t src_scale = 0;
+        if (final_mode) { src_type = in->cols[next_buf_col].type; src_scale = in->cols[next_buf_col].scale; next_buf_col++; }
+        else {
+          int sc;
+          if (expr_is_column(sp.input, &sc) && sc >= 0 && sc < (int)in->cols.size()) src_scale = in->cols[sc].scale;
+        }
         if (s.nf != 1 || s.f[0].mode != F_COL) src_type = SB_FLOAT64;   // computed double expression
         s.kind = sp.func == SB_AGG_MIN ? K_MIN_U64 : K_MAX_U64;
         s.xform = is_float_type(src_type) ? X_DOUBLE : X_SIGNED;
@@ -737,7 +743,7 @@ static void hash_aggregate_fixed(const sb_table *in, const sb_agg_plan *plan, cu
         HostSlot c = s;
         c.kind = K_ADD_I64; c.is_one = 1; c.xform = X_NONE;
         int seen = b.add_slot(c);
-        outs.push_back({E_MINMAX, src_type, main, seen, s.xform, true});
+        outs.push_back({E_MINMAX, src_type, main, seen, s.xform, true, src_type == SB_DECIMAL64 ? src_scale : 0});
         break;
       }
       default: fail(SB_ERR_INVALID, "unknown aggregate function %d", sp.func);
@@ -1006,7 +1012,7 @@ static void hash_aggregate_fixed(const sb_table *in, const sb_agg_plan *plan, cu
     SB_REQUIRE(outs.size() <= 2 * AGG_MAX_SLOTS, "too many aggregate output columns");
     e.ncols = (int)outs.size();
     for (size_t i = 0; i < outs.size(); i++) {
-      Column c = column_alloc(outs[i].out_type, 0, ngroups, outs[i].nullable, st);
+      Column c = column_alloc(outs[i].out_type, outs[i].scale, ngroups, outs[i].nullable, st);
       t->cols.push_back(c);
       e.col[i].out = c.data->ptr;
       e.col[i].out_valid = c.validity ? (uint32_t *)c.validity->ptr : nullptr;

@@ -123,12 +123,25 @@ class HashAggregateExec(SparkPlan):
         self.condition = condition
         self.expected_groups = expected_groups
 
-    def output_names(self):
+    def output_names(self, schema=None):
+        """keys ++ buffers (partial) or results.  A decimal SUM carries Spark's (sum, isEmpty) buffer (Sum.scala:91-100): in
+        update modes that is known from the input column's type, in the merge modes from the Partial table's own columns."""
         names = list(self.groupingExpressions)
+        pos = len(names)
         for fn, name in self.aggregateExpressions:
-            if self.mode == "partial":
-                names += {"sum": [name + "#sum"], "avg": [name + "#sum", name + "#count"], "count": [name + "#count"],
-                          "count_star": [name + "#count"], "min": [name + "#val"], "max": [name + "#val"]}[fn.func]
+            dec = False
+            if schema is not None and fn.func in ("sum", "avg"):
+                if self.mode in ("final", "partial_merge"):
+                    dec = pos < len(schema.types) and schema.types[pos] in (capi.SB_DECIMAL64, capi.SB_DECIMAL128)
+                else:
+                    dec = isinstance(fn.child, AttributeReference) and schema.types[schema.index(fn.child.name)] in (capi.SB_DECIMAL64, capi.SB_DECIMAL128)
+            pos += 2 if (fn.func == "avg" or (dec and fn.func == "sum")) else 1
+            if self.mode in ("partial", "partial_merge"):
+                bufs = {"sum": [name + "#sum"], "avg": [name + "#sum", name + "#count"], "count": [name + "#count"],
+                        "count_star": [name + "#count"], "min": [name + "#val"], "max": [name + "#val"]}[fn.func]
+                if dec and fn.func == "sum":
+                    bufs = [name + "#sum", name + "#isEmpty"]
+                names += bufs
             else:
                 names.append(name)
         return names
@@ -194,7 +207,7 @@ class HashAggregateExec(SparkPlan):
         plan, key_idx, _keepalive = cache[sig]
         h = C.c_void_p()
         capi.check(lib.sb_hash_aggregate(inp.handle, C.byref(plan), _h(stream), C.byref(h)))
-        names = self.output_names()
+        names = self.output_names(schema)
         ats = [inp.arrow_types[i] for i in key_idx] + [None] * (len(names) - len(key_idx))
         return ColumnarBatch(h, names, ats)
 
@@ -209,6 +222,7 @@ class AggregationState:
         lib = capi.load()
         self.agg = agg
         self.plan, self.key_idx, self._keepalive = agg._compile(schema)
+        self.schema = schema
         self.arrow_types = arrow_types
         h = C.c_void_p()
         capi.check(lib.sb_hash_agg_create(C.byref(self.plan), C.byref(h)))
@@ -223,7 +237,7 @@ class AggregationState:
     def finish(self, stream=None) -> ColumnarBatch:
         h = C.c_void_p()
         capi.check(capi.load().sb_hash_agg_finish(self.handle, _h(stream), C.byref(h)))
-        names = self.agg.output_names()
+        names = self.agg.output_names(self.schema)
         ats = [self.arrow_types[i] if self.arrow_types else None for i in self.key_idx] + [None] * (len(names) - len(self.key_idx))
         return ColumnarBatch(h, names, ats)
 
