@@ -23,8 +23,8 @@ public final class Native {
 
   // ---- tables (ColumnarBatch images) --------------------------------------------------------------------------------------
   /** columns: parallel arrays describing Arrow buffers (type, length, nullCount, data / validity BITMAP / offsets addresses). */
-  public static native long tableImportHost(int[] types, long[] lengths, long[] nullCounts, long[] data, long[] validity,
-                                            long[] offsets, long stream);
+  public static native long tableImportHost(int[] types, int[] scales, long[] lengths, long[] nullCounts, long[] data, long[] validity,
+                                            long[] offsets, long stream);   // scales: decimals carry precision << 8 | scale, else 0
   public static native long tableNumRows(long table);
   public static native int tableNumColumns(long table);
   public static native long columnNullCount(long table, int column);    // -1 = unknown

@@ -27,16 +27,16 @@ JNIEXPORT jlong JNICALL Java_org_apache_spark_sql_b200_Native_streamCreate(JNIEn
 }
 
 JNIEXPORT jlong JNICALL Java_org_apache_spark_sql_b200_Native_tableImportHost(
-    JNIEnv *env, jclass c, jintArray types, jlongArray lengths, jlongArray nulls, jlongArray data, jlongArray validity,
+    JNIEnv *env, jclass c, jintArray types, jintArray scales, jlongArray lengths, jlongArray nulls, jlongArray data, jlongArray validity,
     jlongArray offsets, jlong stream) {
   jsize n = (*env)->GetArrayLength(env, types);
-  jint *t = (*env)->GetIntArrayElements(env, types, NULL);
+  jint *t = (*env)->GetIntArrayElements(env, types, NULL), *sc = (*env)->GetIntArrayElements(env, scales, NULL);
   jlong *len = (*env)->GetLongArrayElements(env, lengths, NULL), *nc = (*env)->GetLongArrayElements(env, nulls, NULL);
   jlong *d = (*env)->GetLongArrayElements(env, data, NULL), *v = (*env)->GetLongArrayElements(env, validity, NULL);
   jlong *o = (*env)->GetLongArrayElements(env, offsets, NULL);
   sb_column *cols = (sb_column *)calloc((size_t)n, sizeof(sb_column));
   for (jsize i = 0; i < n; i++) {
-    cols[i].type = t[i]; cols[i].length = len[i]; cols[i].null_count = nc[i];
+    cols[i].type = t[i]; cols[i].scale = sc[i]; cols[i].length = len[i]; cols[i].null_count = nc[i];
     cols[i].data = (const void *)(intptr_t)d[i];            /* OffHeapColumnVector / ArrowBuf address */
     cols[i].validity = (const uint8_t *)(intptr_t)v[i];
     cols[i].offsets = (const int32_t *)(intptr_t)o[i];
@@ -45,6 +45,7 @@ JNIEXPORT jlong JNICALL Java_org_apache_spark_sql_b200_Native_tableImportHost(
   int rc = sb_table_import_host(cols, n, (sb_stream *)(intptr_t)stream, &out);
   free(cols);
   (*env)->ReleaseIntArrayElements(env, types, t, JNI_ABORT);
+  (*env)->ReleaseIntArrayElements(env, scales, sc, JNI_ABORT);
   (*env)->ReleaseLongArrayElements(env, lengths, len, JNI_ABORT);
   (*env)->ReleaseLongArrayElements(env, nulls, nc, JNI_ABORT);
   (*env)->ReleaseLongArrayElements(env, data, d, JNI_ABORT);

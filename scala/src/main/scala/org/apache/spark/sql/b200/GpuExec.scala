@@ -47,7 +47,8 @@ object GpuExec {
     case DoubleType => 7
     case DateType => 8
     case TimestampType | TimestampNTZType => 9
-    case d: DecimalType if d.precision <= 18 => 10
+    case d: DecimalType if d.precision <= 18 => 10      // unscaled long (Decimal.scala: compact form), SB_DECIMAL64
+    case _: DecimalType => 12                           // 128-bit unscaled value, SB_DECIMAL128: results of SUM / AVG, payload only
     case StringType | BinaryType => 11
     case _ => -1
   }
@@ -104,6 +105,7 @@ object DeviceTransfer {
       val n = batch.numRows()
       val ncols = batch.numCols()
       val typeIds = new Array[Int](ncols)
+      val scales = types.map { case d: DecimalType => (d.precision << 8) | d.scale; case _ => 0 }
       val lengths = Array.fill[Long](ncols)(n.toLong)
       val nullCounts = new Array[Long](ncols)
       val data = new Array[Long](ncols)
@@ -119,7 +121,8 @@ object DeviceTransfer {
               "batches (spark.sql.columnVector.offheap.enabled=true) or ArrowColumnVector buffers")
           }
           typeIds(c) = GpuExec.typeId(types(c))
-          if (typeIds(c) < 0) throw new B200Exception(5, s"type ${types(c)} is not supported on the GPU path")
+          if (typeIds(c) < 0 || typeIds(c) == 12)    // OffHeapColumnVector keeps decimal(p > 18) as byte arrays, not as 16-byte values
+            throw new B200Exception(5, s"type ${types(c)} is not supported as an input of the GPU path")
           nullCounts(c) = v.numNulls()
           data(c) = v.valuesNativeAddress()
           if (v.hasNull) {
@@ -139,7 +142,7 @@ object DeviceTransfer {
           }
           c += 1
         }
-        val table = Native.tableImportHost(typeIds, lengths, nullCounts, data, validity, offsets, stream)
+        val table = Native.tableImportHost(typeIds, scales, lengths, nullCounts, data, validity, offsets, stream)
         Native.streamSynchronize(stream)          // the scratch bitmaps and the source vectors may go away after this call
         new DeviceBatch(table, types)
       } finally scratch.foreach(Native.hostFree)
@@ -157,7 +160,21 @@ object DeviceTransfer {
         val bitmapBytes = (n + 7) / 8 + 8
         val bm = Native.hostAlloc(bitmapBytes)
         try {
-          val nulls = Native.tableExportHost(d.table, c, v.valuesNativeAddress(), bm, 0L, stream)   // returns the NULL count
+          val wide = types(c) match { case dt: DecimalType if dt.precision > 18 => true; case _ => false }
+          val staging = if (wide) Native.hostAlloc(16L * math.max(n, 1)) else 0L   // decimal(p > 18): 16-byte little-endian values
+          val nulls = Native.tableExportHost(d.table, c, if (wide) staging else v.valuesNativeAddress(), bm, 0L, stream)   // returns the NULL count
+          if (wide) {
+            val dt = types(c).asInstanceOf[DecimalType]
+            val bytes = new Array[Byte](16)
+            var r = 0
+            while (r < n) {
+              var k = 0
+              while (k < 16) { bytes(15 - k) = Platform.getByte(null, staging + 16L * r + k); k += 1 }   // BigInteger wants big endian
+              v.putDecimal(r, Decimal(new java.math.BigDecimal(new java.math.BigInteger(bytes), dt.scale), dt.precision, dt.scale), dt.precision)
+              r += 1
+            }
+            Native.hostFree(staging)
+          }
           if (nulls > 0) {
             var r = 0
             while (r < n) {

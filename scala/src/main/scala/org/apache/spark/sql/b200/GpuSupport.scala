@@ -28,6 +28,12 @@ object GpuSupport {
   private def fixedWidth(dt: DataType): Boolean = typeOk(dt) && dt != StringType && dt != BinaryType
   private def outputOk(p: SparkPlan): Boolean = p.output.forall(a => typeOk(a.dataType))
   private def exprOk(e: Expression): Boolean = ExprCompiler.supported(e)
+  /** SUM / AVG over decimals: a bare decimal(p <= 18) column (128-bit limb sums inside the library, csrc/decimal.cu); decimal
+   *  arithmetic in the argument stays on the CPU */
+  private def decimalInputOk(c: Expression): Boolean = c.dataType match {
+    case d: DecimalType => d.precision <= 18 && c.isInstanceOf[AttributeReference]
+    case _ => true
+  }
   /** grouping / join / sort keys: fixed-width types, and strings (order-preserving dictionary codes inside the library) */
   private def keyOk(dt: DataType): Boolean = fixedWidth(dt) || dt == StringType
 
@@ -40,8 +46,8 @@ object GpuSupport {
       agg.groupingExpressions.length <= 6 &&
       agg.aggregateExpressions.forall { ae =>
         !ae.isDistinct && ae.filter.isEmpty && (ae.aggregateFunction match {
-          case Sum(c, _) => fixedWidth(c.dataType) && !c.dataType.isInstanceOf[DecimalType] && exprOk(c)
-          case Average(c, _) => fixedWidth(c.dataType) && !c.dataType.isInstanceOf[DecimalType] && exprOk(c)
+          case Sum(c, _) => fixedWidth(c.dataType) && decimalInputOk(c) && exprOk(c)
+          case Average(c, _) => fixedWidth(c.dataType) && decimalInputOk(c) && exprOk(c)
           case Count(cs) => cs.length <= 1 && cs.forall(exprOk)
           case Min(c) => fixedWidth(c.dataType) && exprOk(c)
           case Max(c) => fixedWidth(c.dataType) && exprOk(c)
