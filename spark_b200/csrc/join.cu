@@ -368,6 +368,110 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_candidate_kernel(JoinKeys k
   }
 }
 
+// Variant (sb_config_set("join_cand", 1)): lane-strided.  A warp owns 512 consecutive rows of the block's 4096 and visits them 32 at
+// a time -- lane l reads row base + l, so every column load is one coalesced warp-wide access -- 8 such groups per step, and inside
+// a step every stage issues ALL its loads before the first use (keys, then predicate terms one by one, then prefilter words), so
+// they overlap.  The verdicts of 32 rows are one ballot word = two of the 16-bit words candidate_rows_kernel reads (little endian),
+// so the bits buffer, the block counts and the second kernel are shared with the variant above.
+// KW: 0 = general keys (join_key per row), 4 / 8 = ONE NULL-free integer key column of that width.
+constexpr int CAND_STEP = 8;
+template <int KW>
+__global__ void __launch_bounds__(JOIN_THREADS) join_candidate_strided_kernel(JoinKeys k, int64_t n, const __grid_constant__ SimplePred sp,
+                                                                              const uint8_t *__restrict__ row_mask, KeyFilter kf, int mode,
+                                                                              uint32_t *__restrict__ bits_out, int32_t *__restrict__ block_counts) {
+  __shared__ int32_t wsum[JOIN_THREADS / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t wbase = (int64_t)blockIdx.x * CAND_TILE + (int64_t)warp * (CAND_TILE / (JOIN_THREADS / 32));
+  int32_t mine = 0;
+#pragma unroll 1
+  for (int c = 0; c < CAND_TILE / (JOIN_THREADS / 32) / 32; c += CAND_STEP) {
+    const int64_t r0 = wbase + (int64_t)c * 32 + lane;
+    if (wbase + (int64_t)c * 32 >= n) break;
+    bool keep[CAND_STEP], has[CAND_STEP];
+    uint64_t key[CAND_STEP];
+    int64_t rr[CAND_STEP];
+#pragma unroll
+    for (int j = 0; j < CAND_STEP; j++) {
+      const int64_t r = r0 + (int64_t)j * 32;
+      keep[j] = r < n;
+      rr[j] = r < n ? r : n - 1;
+      has[j] = true;
+    }
+    if (mode != CAND_ALL) {   // the key loads do not wait for the filter's verdict
+      if (KW == 8) {
+#pragma unroll
+        for (int j = 0; j < CAND_STEP; j++) key[j] = ((const uint64_t *)k.data[0])[rr[j]];
+      } else if (KW == 4) {
+#pragma unroll
+        for (int j = 0; j < CAND_STEP; j++) key[j] = (uint64_t)((const uint32_t *)k.data[0])[rr[j]];
+      } else {
+#pragma unroll
+        for (int j = 0; j < CAND_STEP; j++) {
+          key[j] = 0;
+          has[j] = join_key(k, rr[j], key[j]);
+        }
+      }
+    }
+    if (sp.nterms > 0) simple_pred_rows<CAND_STEP>(sp, r0, 32, n, keep);
+    if (row_mask) {
+      uint8_t m[CAND_STEP];
+#pragma unroll
+      for (int j = 0; j < CAND_STEP; j++) m[j] = row_mask[rr[j]];
+#pragma unroll
+      for (int j = 0; j < CAND_STEP; j++) keep[j] = keep[j] && m[j] != 0;
+    }
+    if (mode != CAND_ALL) {
+      bool present[CAND_STEP];
+#pragma unroll
+      for (int j = 0; j < CAND_STEP; j++) present[j] = has[j];
+      if (kf.words && kf.exact) {
+        uint32_t w[CAND_STEP];
+        uint64_t d[CAND_STEP];
+#pragma unroll
+        for (int j = 0; j < CAND_STEP; j++) {
+          d[j] = key[j] - kf.fmin;
+          present[j] = present[j] && keep[j] && d[j] < kf.frange;
+          w[j] = present[j] ? __ldg(&kf.words[d[j] >> 5]) : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < CAND_STEP; j++) present[j] = present[j] && ((w[j] >> (d[j] & 31)) & 1u);
+      } else if (kf.words) {
+        uint32_t w[CAND_STEP], bb[CAND_STEP];
+#pragma unroll
+        for (int j = 0; j < CAND_STEP; j++) {
+          const uint64_t hh = join_mix(key[j]);
+          bb[j] = bloom_bits(hh);
+          present[j] = present[j] && keep[j];
+          w[j] = present[j] ? __ldg(&kf.words[bloom_word(hh, kf.mask)]) : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < CAND_STEP; j++) present[j] = present[j] && (w[j] & bb[j]) == bb[j];
+      }
+#pragma unroll
+      for (int j = 0; j < CAND_STEP; j++)
+        keep[j] = keep[j] && (mode == CAND_PRESENT ? present[j] : mode == CAND_ABSENT ? !present[j] : (has[j] && !present[j]));
+    }
+#pragma unroll
+    for (int j = 0; j < CAND_STEP; j++) {
+      const uint32_t word = __ballot_sync(0xffffffffu, keep[j]);
+      const int64_t w = (wbase >> 5) + c + j;
+      if (lane == j && w * 32 < n) {
+        bits_out[w] = word;
+        mine += __popc(word);
+      }
+    }
+  }
+  const int32_t t = __reduce_add_sync(0xffffffffu, mine);
+  if (lane == 0) wsum[warp] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int32_t b = 0;
+#pragma unroll
+    for (int w = 0; w < JOIN_THREADS / 32; w++) b += wsum[w];
+    block_counts[blockIdx.x] = b;
+  }
+}
+
 // the candidate list in row order: same tiling as join_candidate_kernel, block_offsets = exclusive scan of its block counts
 __global__ void __launch_bounds__(JOIN_THREADS) candidate_rows_kernel(const uint16_t *__restrict__ bits, int64_t nwords,
                                                                       const int64_t *__restrict__ block_offsets, int64_t *__restrict__ rows) {
@@ -788,7 +892,16 @@ int sb_join_probe_ex(const sb_hash_table *ht, const sb_table *probe, const int32
     Scratch bits(nwords * 2 + 16, st), bcount((int64_t)cb * 4 + 16, st), boff((int64_t)cb * 8 + 16, st), tot(8, st);
     const int fast_key = k.n == 1 && !k.valid[0] && k.type[0] != SB_FLOAT32 && k.type[0] != SB_FLOAT64 && k.type[0] != SB_BOOL &&
                          ((uintptr_t)k.data[0] & 15) == 0;
-    join_candidate_kernel<<<cb, JOIN_THREADS, 0, st>>>(k, n, sp, pmask_dev, kf, cand_mode, fast_key, bits.as<uint16_t>(), bcount.as<int32_t>());
+    if (config().join_cand == 1) {
+      // the ballot words are written as uint32: the buffer must hold whole 32-row words (nwords is in 16-row units)
+      const bool int_key = k.n == 1 && !k.valid[0] && k.type[0] != SB_FLOAT32 && k.type[0] != SB_FLOAT64 && k.type[0] != SB_BOOL;
+      const int kw = !int_key ? 0 : (k.bits[0] == 64 ? 8 : k.bits[0] == 32 ? 4 : 0);
+      if (kw == 8) join_candidate_strided_kernel<8><<<cb, JOIN_THREADS, 0, st>>>(k, n, sp, pmask_dev, kf, cand_mode, bits.as<uint32_t>(), bcount.as<int32_t>());
+      else if (kw == 4) join_candidate_strided_kernel<4><<<cb, JOIN_THREADS, 0, st>>>(k, n, sp, pmask_dev, kf, cand_mode, bits.as<uint32_t>(), bcount.as<int32_t>());
+      else join_candidate_strided_kernel<0><<<cb, JOIN_THREADS, 0, st>>>(k, n, sp, pmask_dev, kf, cand_mode, bits.as<uint32_t>(), bcount.as<int32_t>());
+    } else {
+      join_candidate_kernel<<<cb, JOIN_THREADS, 0, st>>>(k, n, sp, pmask_dev, kf, cand_mode, fast_key, bits.as<uint16_t>(), bcount.as<int32_t>());
+    }
     SB_LAUNCH_CHECK();
     exclusive_scan_i32_to_i64(bcount.as<int32_t>(), boff.as<int64_t>(), cb, tot.as<int64_t>(), st);
     SB_CUDA(cudaMemcpyAsync(&nitems, tot.ptr, 8, cudaMemcpyDeviceToHost, st));

@@ -33,6 +33,7 @@ struct Config {
   int expr_interpret_only = 0;
   int regroup_ldst = 0;             // load/store multisplit instead of the copy-engine one
   int exchange_nccl = 0;            // NCCL send/recv data path instead of peer windows
+  int join_cand = 0;                // join candidate pass: 0 = 16 consecutive rows per thread (16-byte loads), 1 = lane-strided with batched loads
   int sort_variant = 4;             // onesweep tile geometry: 4 = 384 threads x 12 keys, the fastest measured (profiles/r02_sort_variants*.jsonl)
 };
 Config &config();

@@ -94,43 +94,66 @@ __device__ __forceinline__ uint32_t simple_pred_eval16(const SimplePred &sp, int
   }
   return keep & 0xFFFFu;
 }
-// the same predicate for ONE row (lane-strided kernels: the 32 lanes of a warp read 32 consecutive rows, so plain loads coalesce)
-__device__ __forceinline__ bool simple_pred_row(const SimplePred &sp, int64_t row) {
-  bool keep = true;
+// the same predicate for R rows row0, row0 + stride, ... (lane-strided kernels: the 32 lanes of a warp read 32 consecutive rows,
+// so plain loads coalesce).  Term by term: all R loads of a term are issued before the first comparison uses one, so they overlap;
+// the type switch is outside the row loop (uniform).  Rows >= n are clamped for the loads and masked by the caller.
+template <int R>
+__device__ __forceinline__ void simple_pred_rows(const SimplePred &sp, int64_t row0, int64_t stride, int64_t n, bool (&keep)[R]) {
+  int64_t rr[R];
+#pragma unroll
+  for (int j = 0; j < R; j++) {
+    const int64_t r = row0 + j * stride;
+    rr[j] = r < n ? r : n - 1;
+  }
 #pragma unroll 1
   for (int t = 0; t < sp.nterms; t++) {
-    if (sp.valid[t]) keep = keep && ((sp.valid[t][row >> 3] >> (row & 7)) & 1);
+    if (sp.valid[t]) {
+      uint8_t vb[R];
+#pragma unroll
+      for (int j = 0; j < R; j++) vb[j] = sp.valid[t][rr[j] >> 3];
+#pragma unroll
+      for (int j = 0; j < R; j++) keep[j] = keep[j] && ((vb[j] >> (rr[j] & 7)) & 1);
+    }
     const int op = sp.op[t];
     if (op == SP_NOTNULL) continue;
-    int64_t x;
+    int64_t x[R];
     switch (sp.type[t]) {
-      case SB_BOOL: x = ((const uint8_t *)sp.data[t])[row]; break;
-      case SB_INT8: x = ((const int8_t *)sp.data[t])[row]; break;
-      case SB_INT16: x = ((const int16_t *)sp.data[t])[row]; break;
-      case SB_INT32: case SB_DATE32: case SB_FLOAT32: x = ((const int32_t *)sp.data[t])[row]; break;
-      default: x = ((const int64_t *)sp.data[t])[row]; break;
+      case SB_BOOL: case SB_INT8:
+#pragma unroll
+        for (int j = 0; j < R; j++) x[j] = sp.type[t] == SB_BOOL ? (int64_t)((const uint8_t *)sp.data[t])[rr[j]] : (int64_t)((const int8_t *)sp.data[t])[rr[j]];
+        break;
+      case SB_INT16:
+#pragma unroll
+        for (int j = 0; j < R; j++) x[j] = ((const int16_t *)sp.data[t])[rr[j]];
+        break;
+      case SB_INT32: case SB_DATE32: case SB_FLOAT32:
+#pragma unroll
+        for (int j = 0; j < R; j++) x[j] = ((const int32_t *)sp.data[t])[rr[j]];
+        break;
+      default:
+#pragma unroll
+        for (int j = 0; j < R; j++) x[j] = ((const int64_t *)sp.data[t])[rr[j]];
+        break;
     }
-    int c;
-    if (sp.f64[t]) {   // SQLOrderingUtil.compareDoubles: NaN equals NaN and is larger than anything else
-      const double y = __longlong_as_double(sp.lit[t]);
-      const double d = sp.type[t] == SB_FLOAT32 ? (double)__int_as_float((int32_t)x) : __longlong_as_double(x);
-      const bool dn = d != d, yn = y != y;
-      c = d == y ? 0 : (dn || yn) ? (int)dn - (int)yn : (d < y ? -1 : 1);
-    } else {
-      c = x == sp.lit[t] ? 0 : (x < sp.lit[t] ? -1 : 1);
+    const int64_t lit = sp.lit[t];
+    const bool f64 = sp.f64[t] != 0, f32 = sp.type[t] == SB_FLOAT32;
+    // which signs of compare(x, lit) satisfy the operator: uniform per term, so the row loop below has no branch on `op`
+    const bool want_lt = op == SP_LT || op == SP_LE || op == SP_NE, want_eq = op == SP_EQ || op == SP_LE || op == SP_GE,
+               want_gt = op == SP_GT || op == SP_GE || op == SP_NE;
+#pragma unroll
+    for (int j = 0; j < R; j++) {
+      int c;
+      if (f64) {   // SQLOrderingUtil.compareDoubles: NaN equals NaN and is larger than anything else
+        const double y = __longlong_as_double(lit);
+        const double d = f32 ? (double)__int_as_float((int32_t)x[j]) : __longlong_as_double(x[j]);
+        const bool dn = d != d, yn = y != y;
+        c = d == y ? 0 : (dn || yn) ? (int)dn - (int)yn : (d < y ? -1 : 1);
+      } else {
+        c = x[j] == lit ? 0 : (x[j] < lit ? -1 : 1);
+      }
+      keep[j] = keep[j] && ((c < 0 && want_lt) || (c == 0 && want_eq) || (c > 0 && want_gt));
     }
-    bool ok;
-    switch (op) {
-      case SP_EQ: ok = c == 0; break;
-      case SP_NE: ok = c != 0; break;
-      case SP_LT: ok = c < 0; break;
-      case SP_LE: ok = c <= 0; break;
-      case SP_GT: ok = c > 0; break;
-      default: ok = c >= 0; break;
-    }
-    keep = keep && ok;
   }
-  return keep;
 }
 #endif
 
