@@ -293,6 +293,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-verify", action="store_true")
     ap.add_argument("--profile-host", action="store_true", help="cProfile one untimed step of every join leg to stderr (debugging)")
+    ap.add_argument("--config", action="append", default=[], metavar="KEY=VALUE", help="sb_config_set(KEY, VALUE) before the run (A/B experiments)")
     args = ap.parse_args()
     args.legs = [x for x in args.legs.split(",") if x]
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -320,6 +321,9 @@ def main():
     from spark_b200.expressions import SortOrder
 
     lib = capi.init(local_rank)
+    for kv in args.config:
+        k, v = kv.split("=", 1)
+        capi.config_set(k, int(v))
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))

@@ -465,10 +465,12 @@ int sb_comm_rank(int32_t *rank, int32_t *nranks);
 int sb_exchange_plan(const int64_t *part_offsets, int32_t num_partitions, int32_t nranks,
                      int64_t *out_send_rows /* nranks */);
 /* ShuffleExchangeExec, both sides: `in` is partition-contiguous (from sb_hash_partition) with
- * part_offsets_host; every rank receives the partitions it owns from all ranks.  The received rows are
- * grouped by SOURCE rank (fetch order is unspecified in the reference too), each source block being
- * partition-contiguous; out_part_offsets_host[num_partitions+1] accumulates the received rows per
- * partition id (only owned partitions are non-empty).  Collective: all ranks call it in the same order. */
+ * part_offsets_host; every rank receives the partitions it owns from all ranks.  The result is
+ * partition-contiguous (what AQEShuffleReadExec slices by partition offsets); inside a partition the rows
+ * are ordered by source rank, arrival order inside a source (fetch order is unspecified in the reference);
+ * out_part_offsets_host[num_partitions+1] = partition boundaries of the result (only owned partitions are
+ * non-empty).  String columns travel as dictionary codes (csrc/comm.cu).  Collective: all ranks call it in
+ * the same order. */
 int sb_all_to_all(const sb_table *in, const int64_t *part_offsets_host, int32_t num_partitions, sb_stream *s,
                   sb_table **out, int64_t *out_part_offsets_host);
 /* ---- adaptive execution: the statistics of an exchange and the coalescing they drive --------------------------------------------

@@ -337,8 +337,17 @@ int sb_exchange_plan(const int64_t *part_offsets, int32_t num_partitions, int32_
   SB_API_END
 }
 
-static int all_to_all_fixed(const sb_table *in, const int64_t *part_offsets_host, int32_t num_partitions, sb_stream *s, sb_table **out,
-                            int64_t *out_part_offsets_host) {
+struct TableHold {
+  sb_table *t = nullptr;
+  ~TableHold() { if (t) table_free(t); }
+};
+
+// rows per (source rank, partition) of the calling thread's last exchange: [R][P + 1] as all-gathered (all_to_all_by_source fills it)
+static thread_local std::vector<int64_t> g_last_counts;
+
+// the transport: received rows grouped by SOURCE rank, every source block partition-contiguous
+static int all_to_all_by_source(const sb_table *in, const int64_t *part_offsets_host, int32_t num_partitions, sb_stream *s, sb_table **out,
+                                int64_t *out_part_offsets_host) {
   SB_API_BEGIN
   require_init();
   SB_REQUIRE(in && part_offsets_host && out && out_part_offsets_host, "null argument");
@@ -366,6 +375,7 @@ static int all_to_all_fixed(const sb_table *in, const int64_t *part_offsets_host
     SB_CUDA(cudaMemcpyAsync(all_counts.data(), d_all.ptr, (size_t)R * PS * 8, cudaMemcpyDeviceToHost, st));
   }
   SB_CUDA(cudaStreamSynchronize(st));
+  g_last_counts = all_counts;
   uint64_t any_mask = 0;
   for (int r = 0; r < R; r++) any_mask |= (uint64_t)all_counts[(size_t)r * PS + P];
   auto nullable = [&](size_t ci) { return ((any_mask >> ci) & 1) != 0; };
@@ -585,6 +595,64 @@ static int all_to_all_fixed(const sb_table *in, const int64_t *part_offsets_host
     throw;
   }
   *out = t;
+  SB_API_END
+}
+
+// source-grouped row i -> its place in the partition-contiguous result: rows of partition p from source s start at
+// part_offset[p] + sum_{s' < s} count[s'][p].  One thread per row finds its (source, partition) segment by binary search.
+__global__ void regroup_index_kernel(const int64_t *__restrict__ seg_src, const int64_t *__restrict__ seg_dst, int32_t nseg, int64_t n,
+                                     int64_t *__restrict__ idx) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int lo = 0, hi = nseg - 1;   // last segment with seg_src <= i (empty segments share a start: any of them maps i correctly only
+  while (lo < hi) {            // if it is the LAST one with that start, which this search returns)
+    const int mid = (lo + hi + 1) >> 1;
+    if (seg_src[mid] <= i) lo = mid; else hi = mid - 1;
+  }
+  idx[seg_dst[lo] + (i - seg_src[lo])] = i;
+}
+
+// ShuffleExchangeExec's reduce side as its readers expect it: partition-contiguous over the owned partitions (a coalesced read of
+// AQEShuffleReadExec is a slice by partition offsets), rows of a partition ordered by source rank, arrival order inside a source.
+static int all_to_all_fixed(const sb_table *in, const int64_t *part_offsets_host, int32_t num_partitions, sb_stream *s, sb_table **out,
+                            int64_t *out_part_offsets_host) {
+  sb_table *by_source = nullptr;
+  int rc = all_to_all_by_source(in, part_offsets_host, num_partitions, s, &by_source, out_part_offsets_host);
+  if (rc != SB_OK) return rc;
+  const int R = comm().nranks, P = num_partitions, PS = P + 1, me = comm().rank;
+  if (R == 1) {
+    *out = by_source;
+    return SB_OK;
+  }
+  SB_API_BEGIN
+  TableHold hold;
+  hold.t = by_source;
+  cudaStream_t st = stream_of(s);
+  const int64_t n = by_source->nrows;
+  const int lo = part_lo(me, P, R), hi = part_lo(me + 1, P, R);
+  const int nseg = R * (hi - lo);
+  if (n == 0 || nseg == 0) {
+    *out = by_source;
+    hold.t = nullptr;
+    return SB_OK;
+  }
+  const std::vector<int64_t> &cnt = g_last_counts;
+  std::vector<int64_t> seg(2 * (size_t)nseg), before((size_t)(hi - lo), 0);
+  int64_t src = 0;
+  for (int r = 0; r < R; r++)
+    for (int p = lo; p < hi; p++) {
+      const size_t k = (size_t)r * (hi - lo) + (p - lo);
+      seg[k] = src;
+      seg[nseg + k] = out_part_offsets_host[p] + before[p - lo];
+      src += cnt[(size_t)r * PS + p];
+      before[p - lo] += cnt[(size_t)r * PS + p];
+    }
+  Scratch dseg((int64_t)seg.size() * 8, st), idx(n * 8 + 16, st);
+  SB_CUDA(cudaMemcpyAsync(dseg.ptr, seg.data(), seg.size() * 8, cudaMemcpyHostToDevice, st));
+  regroup_index_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dseg.as<int64_t>(), dseg.as<int64_t>() + nseg, nseg, n, idx.as<int64_t>());
+  SB_LAUNCH_CHECK();
+  *out = gather_table(by_source, idx.as<int64_t>(), n, false, st);
+  SB_CUDA(cudaStreamSynchronize(st));   // `seg` (host) is read by the copy above
   SB_API_END
 }
 
@@ -824,10 +892,6 @@ static bool has_string_column(const sb_table *t) {
 static void check_rc(int rc) {
   if (rc != SB_OK) fail(rc, "%s", sb_last_error());
 }
-struct TableHold {
-  sb_table *t = nullptr;
-  ~TableHold() { if (t) table_free(t); }
-};
 
 int sb_all_gather(const sb_table *in, sb_stream *s, sb_table **out) {
   if (!in || !has_string_column(in) || !comm().comm) return all_gather_fixed(in, s, out);

@@ -64,9 +64,8 @@ def main():
             offs = ex.partition_offsets
             counts = np.bincount(pid[owned], minlength=nparts)
             assert np.array_equal(np.diff(offs), counts), (rank, nparts, fused)
-            if fused:      # partition-contiguous over the owned partitions
-                gp = O.partition_ids(got, ["k", "d"], nparts)
-                assert np.all(np.diff(gp) >= 0), "rank %d: fused exchange output is not partition-contiguous" % rank
+            gp = O.partition_ids(got, ["k", "d"], nparts)      # partition-contiguous over the owned partitions, both transports
+            assert np.all(np.diff(gp) >= 0), "rank %d: exchange output is not partition-contiguous (nparts=%d fused=%s)" % (rank, nparts, fused)
     # all-gather (broadcast build side)
     h = C.c_void_p()
     small = ColumnarBatch.from_arrow(mine.slice(0, 1000 + rank), stream)
