@@ -109,6 +109,20 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------- host CPU side
+def ncu_traffic(kernel, rows):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel` from the committed `ncu --set full` capture of this
+    workload (profiles/r02_ncu_traffic.json, written from the capture by tools/ncu_traffic.py); null when the capture was taken at
+    another size (a profiler cannot run inside the timed region)."""
+    try:
+        rec = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02_ncu_traffic.json")))[kernel]
+    except Exception:
+        return {"traffic": None, "traffic_note": "no ncu capture committed for this kernel"}
+    if int(rec.get("rows", -1)) != int(rows):
+        return {"traffic": None, "traffic_note": "the committed ncu capture (%s) is for %s rows per launch, this run has %d"
+                % (rec.get("source"), rec.get("rows"), rows)}
+    return {"traffic": int(rec["dram_bytes"]), "traffic_note": "from %s" % rec.get("source")}
+
+
 def host_threads():
     """Threads the CPU arm may really use: the affinity mask capped by the cgroup's CPU quota (cpu.max)."""
     try:
@@ -544,8 +558,7 @@ def main():
                       "gpu_launches": int(launches), "verified": verified, "agg_kernels": plan_name, "variants": variants,
                       "roofline": {"bound": "hbm", "kernel": "agg_update_kernel (%s)" % plan_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                                    "frac": achieved / peak, "frac_of_8tbs_nominal": achieved / 8000.0, "peak_source": peak_src,
-                                   "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes, "traffic": None,
-                                   "traffic_note": "dram bytes per launch are in the ncu summary under profiles/ (not measured in this run)"}}
+                                   "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes, **ncu_traffic("agg_update_kernel", n_li)}}
 
     # ===================================================================================================== Q3 / Q5
     def q3_rows(tbl):
@@ -605,7 +618,7 @@ def main():
             stream.synchronize()
             pr.disable()
             pstats.Stats(pr, stream=sys.stderr).sort_stats("cumulative").print_stats(25)
-        ms, launches, prof = time_resident(step_join, steps, 2, ("join_build", "join_probe", "join_fill", "gather", "filter_project", "agg_update"))
+        ms, launches, prof = time_resident(step_join, steps, max(3, args.warmup), ("join_build", "join_probe", "join_fill", "gather", "filter_project", "agg_update"))
         alg_bytes = sum(tpch.synth_rows(t, n_orders) * sum(tpch.synth_width(c) for c in cols) for t, cols in used.items())
         achieved = alg_bytes / (ms / 1000.0) / 1e9
         verified = None
@@ -809,8 +822,8 @@ def run_shuffle(args, lib, capi, tpch, stream, rank, world, n_orders, seed, barr
 
     steps = max(1, min(args.steps, args.leg_steps))
     names = ("partition_ids", "exchange_scatter", "partition_scatter", "a2a_transfer", "a2a_counts")
-    ms2, _, prof2 = time_resident(make_step(ex2), steps, 2, names)
-    ms, launches, prof = time_resident(make_step(ex), steps, 2, names)
+    ms2, _, prof2 = time_resident(make_step(ex2), steps, max(3, args.warmup), names)
+    ms, launches, prof = time_resident(make_step(ex), steps, max(3, args.warmup), names)
     out = outs[-1]
     offs = ex.partition_offsets
     # ---- verification: (1) every received row belongs to a partition this rank owns (oracle Murmur3 on a sample), (2) rows and

@@ -371,8 +371,8 @@ int sb_range_determine_bounds(const sb_table *sample, const sb_sort_order *order
  *      sb_window: rows sorted by (partition columns ASC NULLS FIRST, orders) -- the child ordering the reference requires and the
  *      order it emits -- followed by one column per window expression.  Ranking functions ignore the frame.  Frames: ROWS with any
  *      bounds (lower / upper are row offsets, negative = PRECEDING, 0 = CURRENT ROW); RANGE with UNBOUNDED / CURRENT ROW bounds (0)
- *      -- i.e. the default frames "RANGE UNBOUNDED PRECEDING .. CURRENT ROW" (with ORDER BY: peers included) and the whole
- *      partition; min / max need lower = SB_UNBOUNDED_PRECEDING.  Result types: row_number / rank / dense_rank / ntile int32,
+ *      -- the default frames "RANGE UNBOUNDED PRECEDING .. CURRENT ROW" (with ORDER BY: peers included) and the whole
+ *      partition -- and with value offsets over one numeric / date ORDER BY column; min / max need lower = SB_UNBOUNDED_PRECEDING.  Result types: row_number / rank / dense_rank / ntile int32,
  *      percent_rank / cume_dist double, count int64, sum int64 (integral input) or double, avg double, the rest the input type. */
 #define SB_WIN_ROW_NUMBER 1
 #define SB_WIN_RANK 2
@@ -390,7 +390,9 @@ int sb_range_determine_bounds(const sb_table *sample, const sb_sort_order *order
 #define SB_WIN_FIRST_VALUE 14   /* respect nulls */
 #define SB_WIN_LAST_VALUE 15
 #define SB_FRAME_ROWS 0
-#define SB_FRAME_RANGE 1
+#define SB_FRAME_RANGE 1       /* bounds: UNBOUNDED, 0 = CURRENT ROW (peers included), or int64 VALUE offsets (negative = PRECEDING) over
+                                  the single integral / date ORDER BY column */
+#define SB_FRAME_RANGE_F64 2   /* the same over a float / double ORDER BY column: offsets are the bits of doubles */
 #define SB_UNBOUNDED_PRECEDING INT64_MIN
 #define SB_UNBOUNDED_FOLLOWING INT64_MAX
 typedef struct sb_window_spec {

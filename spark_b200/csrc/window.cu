@@ -12,8 +12,9 @@
 //   4. every function is a per-row formula over those bounds and over SEGMENTED inclusive scans of its input (sum / count /
 //      min / max restart at partition heads): a frame [lo, hi] of a row is turned into S[hi] - S[lo - 1] (sum, count, avg) or
 //      M[hi] (min / max of frames that start at the partition's first row), first / last values and lag / lead are gathers.
-// Frames: ROWS with any bounds; RANGE with UNBOUNDED / CURRENT ROW bounds (the default frames); min / max need a frame that
-// starts at UNBOUNDED PRECEDING.
+// Frames: ROWS with any bounds; RANGE with UNBOUNDED / CURRENT ROW bounds (the default frames) and with value offsets over one
+// numeric / date ORDER BY key (per-row binary searches in the sorted partition); min / max need a frame that starts at UNBOUNDED
+// PRECEDING.
 #include <memory>
 #include <vector>
 #include "common.cuh"
@@ -202,6 +203,10 @@ struct Bounds {
   const int32_t *seg_id, *peer_id;
   const int64_t *seg_first, *peer_first;
   int64_t nseg, npeer, n;
+  // the single ORDER BY key, for RANGE frames with value offsets
+  const void *okey;
+  const uint8_t *okey_valid;
+  int32_t okey_type, asc, nulls_first;
 };
 __device__ __forceinline__ int64_t seg_start_of(const Bounds &b, int64_t i) { return b.seg_first[b.seg_id[i]]; }
 __device__ __forceinline__ int64_t seg_end_of(const Bounds &b, int64_t i) {
@@ -213,12 +218,66 @@ __device__ __forceinline__ int64_t peer_end_of(const Bounds &b, int64_t i) {
   const int32_t g = b.peer_id[i];
   return g + 1 < b.npeer ? b.peer_first[g + 1] : b.n;
 }
+// Where does row j's order key sort relative to `bound` in the partition's order: -1 before, 0 equal, +1 after.  NULL keys sit
+// where the null ordering put them.  F64: keys and bounds are doubles (SQLOrderingUtil.compareDoubles: NaN largest).
+template <bool F64>
+__device__ __forceinline__ int key_vs(const Bounds &b, int64_t j, int64_t bound_i, double bound_d) {
+  if (!bit_valid(b.okey_valid, j)) return b.nulls_first ? -1 : 1;
+  int c;
+  if (F64) {
+    const double v = b.okey_type == SB_FLOAT32 ? (double)((const float *)b.okey)[j] : ((const double *)b.okey)[j];
+    const bool vn = v != v, bn = bound_d != bound_d;
+    c = v == bound_d ? 0 : (vn || bn) ? (int)vn - (int)bn : (v < bound_d ? -1 : 1);
+  } else {
+    const int64_t v = load_i64(b.okey, b.okey_type, j);
+    c = v == bound_i ? 0 : (v < bound_i ? -1 : 1);
+  }
+  return b.asc ? c : -c;
+}
+// first row of [s, e] whose key does not sort before the bound (AFTER = false) / first row whose key sorts after it (AFTER = true)
+template <bool F64, bool AFTER>
+__device__ __forceinline__ int64_t range_search(const Bounds &b, int64_t s, int64_t e, int64_t bound_i, double bound_d) {
+  int64_t lo = s, hi = e + 1;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    const int c = key_vs<F64>(b, mid, bound_i, bound_d);
+    if (AFTER ? c <= 0 : c < 0) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+__device__ __forceinline__ int64_t sat_add(int64_t a, int64_t x) {
+  const int64_t r = (int64_t)((uint64_t)a + (uint64_t)x);
+  if (x > 0 && r < a) return INT64_MAX;
+  if (x < 0 && r > a) return INT64_MIN;
+  return r;
+}
 // frame of row i as [lo, hi] (empty when lo > hi)
 __device__ __forceinline__ void frame_of(const Bounds &b, int64_t i, int frame_type, int64_t lower, int64_t upper, int64_t &lo, int64_t &hi) {
   const int64_t s = seg_start_of(b, i), e = seg_end_of(b, i) - 1;
-  if (frame_type == SB_FRAME_RANGE) {
-    lo = lower == SB_UNBOUNDED_PRECEDING ? s : peer_start_of(b, i);
-    hi = upper == SB_UNBOUNDED_FOLLOWING ? e : peer_end_of(b, i) - 1;
+  if (frame_type != SB_FRAME_ROWS) {
+    // RANGE: UNBOUNDED -> the partition's end, CURRENT ROW (0) -> the peer group's end, otherwise a VALUE offset: the bound is the
+    // row's key plus the offset in the direction of the ordering (WindowEvaluatorFactoryBase.createBoundOrdering: Add for ASC,
+    // Subtract for DESC) and the frame holds the rows whose keys lie between the two bounds; a NULL key has only its peers
+    const bool f64 = frame_type == SB_FRAME_RANGE_F64;
+    const bool null_key = b.okey && !bit_valid(b.okey_valid, i);
+    int64_t vi = 0;
+    double vd = 0.0;
+    if (b.okey && !null_key) {
+      if (f64) vd = b.okey_type == SB_FLOAT32 ? (double)((const float *)b.okey)[i] : ((const double *)b.okey)[i];
+      else vi = load_i64(b.okey, b.okey_type, i);
+    }
+    if (lower == SB_UNBOUNDED_PRECEDING) lo = s;
+    else if (lower == 0 || null_key || !b.okey) lo = peer_start_of(b, i);
+    else if (f64) {
+      const double off = __longlong_as_double(lower);
+      lo = range_search<true, false>(b, s, e, 0, b.asc ? vd + off : vd - off);
+    } else lo = range_search<false, false>(b, s, e, b.asc ? sat_add(vi, lower) : sat_add(vi, -lower), 0.0);
+    if (upper == SB_UNBOUNDED_FOLLOWING) hi = e;
+    else if (upper == 0 || null_key || !b.okey) hi = peer_end_of(b, i) - 1;
+    else if (f64) {
+      const double off = __longlong_as_double(upper);
+      hi = range_search<true, true>(b, s, e, 0, b.asc ? vd + off : vd - off) - 1;
+    } else hi = range_search<false, true>(b, s, e, b.asc ? sat_add(vi, upper) : sat_add(vi, -upper), 0.0) - 1;
     return;
   }
   lo = lower == SB_UNBOUNDED_PRECEDING ? s : i + lower;
@@ -413,7 +472,18 @@ extern "C" int sb_window(const sb_table *in, const int32_t *partition_cols, int3
     SB_CUDA(cudaMemcpyAsync(counts, totals.ptr, 8, cudaMemcpyDeviceToHost, st));
     SB_CUDA(cudaStreamSynchronize(st));
   }
-  Bounds b{seg_id.as<int32_t>(), peer_id.as<int32_t>(), seg_first.as<int64_t>(), peer_first.as<int64_t>(), counts[0], counts[1], n};
+  Bounds b{seg_id.as<int32_t>(), peer_id.as<int32_t>(), seg_first.as<int64_t>(), peer_first.as<int64_t>(), counts[0], counts[1], n,
+           nullptr, nullptr, 0, 1, 1};
+  if (norders == 1) {   // value-offset RANGE frames read the (single) order key
+    const Column &ok = sorted->cols[orders[0].col];
+    if (ok.type != SB_STRING && ok.type != SB_DECIMAL64 && ok.type != SB_DECIMAL128 && ok.type != SB_BOOL) {
+      b.okey = ok.d();
+      b.okey_valid = ok.v();
+      b.okey_type = ok.type;
+      b.asc = orders[0].ascending != 0;
+      b.nulls_first = orders[0].nulls_first != 0;
+    }
+  }
 
   // 3. output = sorted input ++ one column per window expression
   sb_table *t = table_new(n);
@@ -435,10 +505,16 @@ extern "C" int sb_window(const sb_table *in, const int32_t *partition_cols, int3
       }
       SB_REQUIRE(w.func >= SB_WIN_LAG && w.func <= SB_WIN_LAST_VALUE, "unknown window function %d", w.func);
       SB_REQUIRE(w.col >= 0 && w.col < ncols_in, "window function input column %d out of range", w.col);
-      SB_REQUIRE(w.frame_type == SB_FRAME_ROWS || w.frame_type == SB_FRAME_RANGE, "unknown frame type %d", w.frame_type);
-      if (w.frame_type == SB_FRAME_RANGE && w.func != SB_WIN_LAG && w.func != SB_WIN_LEAD)
-        if ((w.lower != SB_UNBOUNDED_PRECEDING && w.lower != 0) || (w.upper != SB_UNBOUNDED_FOLLOWING && w.upper != 0))
-          fail(SB_ERR_UNSUPPORTED, "RANGE frames with value offsets are not implemented (UNBOUNDED / CURRENT ROW bounds are)");
+      SB_REQUIRE(w.frame_type == SB_FRAME_ROWS || w.frame_type == SB_FRAME_RANGE || w.frame_type == SB_FRAME_RANGE_F64, "unknown frame type %d",
+                 w.frame_type);
+      if (w.frame_type != SB_FRAME_ROWS && w.func != SB_WIN_LAG && w.func != SB_WIN_LEAD) {
+        const bool offsets = (w.lower != SB_UNBOUNDED_PRECEDING && w.lower != 0) || (w.upper != SB_UNBOUNDED_FOLLOWING && w.upper != 0);
+        if (offsets) {   // SpecifiedWindowFrame with value bounds: exactly one numeric ORDER BY expression (windowExpressions.scala checkInputDataTypes)
+          if (!b.okey) fail(SB_ERR_UNSUPPORTED, "a RANGE frame with value offsets needs exactly one numeric / date ORDER BY column");
+          const bool fkey = b.okey_type == SB_FLOAT32 || b.okey_type == SB_FLOAT64;
+          SB_REQUIRE(fkey == (w.frame_type == SB_FRAME_RANGE_F64), "RANGE offsets are doubles (SB_FRAME_RANGE_F64) exactly when the ORDER BY column is floating point");
+        }
+      }
       const Column &src = sorted->cols[w.col];
       if (w.func == SB_WIN_LAG || w.func == SB_WIN_LEAD || w.func == SB_WIN_FIRST_VALUE || w.func == SB_WIN_LAST_VALUE) {
         if (w.func == SB_WIN_LAG || w.func == SB_WIN_LEAD) SB_REQUIRE(w.param >= 0, "lag / lead offset must not be negative");
