@@ -875,6 +875,11 @@ def window(table, partition_cols, orders, specs):
         c = int(_dcmp(y, x)) if isinstance(x, float) else (y > x) - (y < x)
         return c < 0 if func == "min" else c > 0
 
+    okey_vals = None
+    if len(orders) == 1:
+        okey_vals = srt.column(orders[0][0]).to_pylist()
+        if okey_vals and not isinstance(next((v for v in okey_vals if v is not None), 0), (int, float)):
+            okey_vals = [None if v is None else (v.toordinal() - 719163) for v in okey_vals] if pa.types.is_date(srt.column(orders[0][0]).type) else None
     for func, col, frame, param, name in specs:
         vals = srt.column(col).to_pylist() if col is not None else None
         if frame is None:
@@ -916,9 +921,46 @@ def window(table, partition_cols, orders, specs):
                 continue
 
             def bounds(r):
-                if kind == "range":
-                    return (s if lower is None else peer_start[r]), (e - 1 if upper is None else peer_end[r] - 1)
-                return (s if lower is None else max(s, r + lower)), (e - 1 if upper is None else min(e - 1, r + upper))
+                if kind != "range":
+                    return (s if lower is None else max(s, r + lower)), (e - 1 if upper is None else min(e - 1, r + upper))
+                # RANGE: UNBOUNDED -> partition end, CURRENT ROW (0) -> peer group end, else a VALUE offset over the single ORDER BY key:
+                # bound = key + offset for ASC, key - offset for DESC (WindowEvaluatorFactoryBase.createBoundOrdering); the frame is
+                # the rows whose keys lie between the bounds in the sort order; a NULL key has only its peers (RangeBoundOrdering)
+                ov = okey_vals[r] if okey_vals is not None else None
+                asc, nf = (orders[0][1], orders[0][2]) if orders else (True, True)
+
+                def side(q, bound):     # -1 the key of row q sorts before the bound, 0 equal, +1 after
+                    k = okey_vals[q]
+                    if k is None:
+                        return -1 if nf else 1
+                    c = int(_dcmp(float(k), float(bound))) if isinstance(k, float) or isinstance(bound, float) else (k > bound) - (k < bound)
+                    return c if asc else -c
+
+                def first(pred):        # first position in [s, e) where pred holds (pred is monotone over the sorted partition)
+                    a, b = s, e
+                    while a < b:
+                        m = (a + b) // 2
+                        if pred(m):
+                            b = m
+                        else:
+                            a = m + 1
+                    return a
+
+                if lower is None:
+                    lo = s
+                elif lower == 0 or ov is None:
+                    lo = peer_start[r]
+                else:
+                    bl = ov + lower if asc else ov - lower
+                    lo = first(lambda q: side(q, bl) >= 0)
+                if upper is None:
+                    hi = e - 1
+                elif upper == 0 or ov is None:
+                    hi = peer_end[r] - 1
+                else:
+                    bu = ov + upper if asc else ov - upper
+                    hi = first(lambda q: side(q, bu) > 0) - 1
+                return lo, hi
 
             if func in ("first_value", "last_value"):
                 for r in range(s, e):

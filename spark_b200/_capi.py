@@ -86,7 +86,7 @@ class sb_window_spec(C.Structure):
 
 SB_WIN = {"row_number": 1, "rank": 2, "dense_rank": 3, "percent_rank": 4, "cume_dist": 5, "ntile": 6, "lag": 7, "lead": 8, "sum": 9,
           "count": 10, "avg": 11, "min": 12, "max": 13, "first_value": 14, "last_value": 15}
-SB_FRAME_ROWS, SB_FRAME_RANGE = 0, 1
+SB_FRAME_ROWS, SB_FRAME_RANGE, SB_FRAME_RANGE_F64 = 0, 1, 2
 SB_UNBOUNDED_PRECEDING, SB_UNBOUNDED_FOLLOWING = -(1 << 63), (1 << 63) - 1
 
 

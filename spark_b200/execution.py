@@ -809,6 +809,13 @@ class WindowExec(SparkPlan):
                 specs[i].func = capi.SB_WIN[w.func]
                 specs[i].col = inp.column_index(w.child) if w.child is not None else 0
                 specs[i].frame_type = capi.SB_FRAME_RANGE if kind == "range" else capi.SB_FRAME_ROWS
+                if kind == "range" and self.orderSpec and any(b not in (None, 0) for b in (lo, hi)):
+                    # value offsets: doubles (as bits) over a floating-point ORDER BY key, integers otherwise
+                    kt = inp.column_desc(inp.column_index(self.orderSpec[0].child)).type
+                    if kt in (capi.SB_FLOAT32, capi.SB_FLOAT64):
+                        import struct
+                        specs[i].frame_type = capi.SB_FRAME_RANGE_F64
+                        lo, hi = [b if b in (None, 0) else struct.unpack("<q", struct.pack("<d", float(b)))[0] for b in (lo, hi)]
                 specs[i].lower = capi.SB_UNBOUNDED_PRECEDING if lo is None else lo
                 specs[i].upper = capi.SB_UNBOUNDED_FOLLOWING if hi is None else hi
                 specs[i].param = w.param

@@ -17,6 +17,8 @@ WINDOW_TEST_DATA = pa.table({
 })
 
 # (golden line, partitionSpec, orderSpec [(col, asc, nulls_first)], [(func, col, frame, param, name)], expected rows (val, cate, results...))
+# the first two output columns are (val, cate) unless a case says otherwise in WINDOW_CASE_COLUMNS
+WINDOW_CASE_COLUMNS = {159: ["val_long", "cate"], 176: ["val_double", "cate"]}
 WINDOW_CASES = [
     # :65  count(val) OVER(PARTITION BY cate ORDER BY val ROWS CURRENT ROW)
     (65, ["cate"], [("val", True, True)], [("count", "val", ("rows", 0, 0), 0, "c")],
@@ -40,6 +42,23 @@ WINDOW_CASES = [
       (1, "b", 1, 1, 1, 1, 1.0, 1, 1, 1, 1, 0.3333333333333333, 0.0, 1, 1),
       (2, "b", 2, 1, 2, 3, 1.5, 1, 2, 2, 2, 0.6666666666666666, 0.5, 1, 2),
       (3, "b", 3, 1, 3, 6, 2.0, 1, 3, 3, 3, 1.0, 1.0, 2, 3)]),
+    # :125 count(val) OVER(PARTITION BY cate ORDER BY val RANGE 1 PRECEDING): value offsets over the ORDER BY key
+    (125, ["cate"], [("val", True, True)], [("count", "val", ("range", -1, 0), 0, "c")],
+     [(N, N, 0), (3, N, 1), (N, "a", 0), (1, "a", 2), (1, "a", 2), (2, "a", 3), (1, "b", 1), (2, "b", 2), (3, "b", 2)]),
+    # :142 sum(val) OVER(PARTITION BY cate ORDER BY val RANGE BETWEEN CURRENT ROW AND 1 FOLLOWING)
+    (142, ["cate"], [("val", True, True)], [("sum", "val", ("range", 0, 1), 0, "s")],
+     [(N, N, N), (3, N, 3), (N, "a", N), (1, "a", 4), (1, "a", 4), (2, "a", 2), (1, "b", 3), (2, "b", 5), (3, "b", 3)]),
+    # :362 the same with ORDER BY val DESC: FOLLOWING means smaller values
+    (362, ["cate"], [("val", False, False)], [("sum", "val", ("range", 0, 1), 0, "s")],
+     [(N, N, N), (3, N, 3), (N, "a", N), (1, "a", 2), (1, "a", 2), (2, "a", 4), (1, "b", 1), (2, "b", 3), (3, "b", 5)]),
+    # :159 sum(val_long) OVER(PARTITION BY cate ORDER BY val_long RANGE BETWEEN CURRENT ROW AND 2147483648 FOLLOWING): a long offset
+    (159, ["cate"], [("val_long", True, True)], [("sum", "val_long", ("range", 0, 2147483648), 0, "s")],
+     [(N, N, N), (1, N, 1), (1, "a", 4), (1, "a", 4), (2, "a", 2147483652), (2147483650, "a", 2147483650), (N, "b", N), (3, "b", 2147483653),
+      (2147483650, "b", 2147483650)]),
+    # :176 sum(val_double) OVER(PARTITION BY cate ORDER BY val_double RANGE BETWEEN CURRENT ROW AND 2.5 FOLLOWING): a double offset
+    (176, ["cate"], [("val_double", True, True)], [("sum", "val_double", ("range", 0, 2.5), 0, "s")],
+     [(N, N, N), (1.0, N, 1.0), (1.0, "a", 4.5), (1.0, "a", 4.5), (2.5, "a", 2.5), (100.001, "a", 100.001), (1.0, "b", 4.3), (3.3, "b", 3.3),
+      (100.001, "b", 100.001)]),
     # :621 sum(val) OVER(), avg(val) OVER(): one partition, the whole-partition frame
     (621, [], [], [("sum", "val", None, 0, "s"), ("avg", "val", None, 0, "a")],
      [(N, N, 13, 1.8571428571428572), (3, N, 13, 1.8571428571428572), (N, "a", 13, 1.8571428571428572), (1, "a", 13, 1.8571428571428572),
