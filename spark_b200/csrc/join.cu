@@ -53,6 +53,9 @@ struct sb_hash_table {
   // replaces the open-addressing table by a direct-address one, row_of[key - fmin] -- LongToUnsafeRowMap's dense mode proper.
   int unique = 0;
   uint32_t *row_of = nullptr;         // dense mode: [frange], FREE_SLOT = no such key; slots is NULL then
+  // sorted mode: the build rows arrive with strictly ascending keys (the output of a join over a key-ordered scan, a primary-key
+  // scan ...), so the row of a key is its RANK among the set bits of the bitmap: rank[w] = set bits before word w.  No slots.
+  uint32_t *rank = nullptr;
   int64_t nkeys_in = 0;               // build rows that entered the relation (filter TRUE, keys not NULL)
   // string key columns join as int32 codes in the BUILD side's dictionaries (csrc/strings.cu): has_dict[i] says key i is one
   bool has_dict[4] = {false, false, false, false};
@@ -117,7 +120,14 @@ struct KeyFilter {
   uint64_t mask, fmin, frange;
   int exact;
   const uint32_t *row_of;   // dense direct-address table (implies exact, unique keys)
+  const uint32_t *rank;     // sorted mode: set bits before every bitmap word (implies exact, unique keys)
 };
+// build row of a key the exact prefilter has confirmed, for the relations that keep no slot table
+__device__ __forceinline__ uint32_t direct_row(const KeyFilter &f, uint64_t key) {
+  const uint64_t d = key - f.fmin;
+  if (f.row_of) return __ldg(&f.row_of[d]);
+  return __ldg(&f.rank[d >> 5]) + (uint32_t)__popc(__ldg(&f.words[d >> 5]) & ((1u << (d & 31)) - 1u));
+}
 __device__ __forceinline__ bool filter_test(const KeyFilter &f, uint64_t key) {
   if (!f.words) return true;
   if (f.exact) {
@@ -159,6 +169,7 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_build_kernel(JoinKeys k, in
       const_cast<uint32_t *>(kf.row_of)[d] = (uint32_t)row;
       return;
     }
+    if (!slots) return;   // sorted mode: the bitmap (+ its rank prefix) is the relation
   } else if (fw) atomicOr(&fw[bloom_word(hh, kf.mask)], bloom_bits(hh));
   for (;;) {
     if (slots[h].row == FREE_SLOT && atomicCAS(&slots[h].row, FREE_SLOT, (uint32_t)row) == FREE_SLOT) {
@@ -191,8 +202,8 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_count_kernel(JoinKeys k, in
       const uint64_t hh = join_mix(key);
       uint64_t h = hh & mask;
       if (filter_test(kf, key)) {
-        if (kf.row_of) {   // dense, unique: the prefilter said the key exists
-          f = __ldg(&kf.row_of[key - kf.fmin]);
+        if (kf.row_of || kf.rank) {   // dense / sorted, unique: the prefilter said the key exists
+          f = direct_row(kf, key);
           matches = 1;
           if (matched) matched[f] = 1;
         } else
@@ -510,7 +521,7 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_lookup_kernel(JoinKeys k, c
   uint64_t key;
   int64_t found = -1;
   if (join_key(k, row, key) && (!outer || filter_test(kf, key))) {   // not outer: the candidate pass has done the test
-    if (kf.row_of) found = (int64_t)__ldg(&kf.row_of[key - kf.fmin]);
+    if (kf.row_of || kf.rank) found = (int64_t)direct_row(kf, key);
     else {
       const uint64_t mask = (uint64_t)cap - 1;
       uint64_t h = join_mix(key) & mask;
@@ -531,13 +542,22 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_lookup_kernel(JoinKeys k, c
 }
 
 // what the relation will hold: packed-key range and row count of the build rows that pass the filter with non-NULL keys
+// stats[3] != 0: the rows do not arrive with strictly ascending keys (checked only without a filter: every row is in the relation)
 __global__ void __launch_bounds__(JOIN_THREADS) build_stats_kernel(JoinKeys k, int64_t n, const uint8_t *__restrict__ row_mask,
                                                                    long long *__restrict__ stats) {
   long long lo = 0x7FFFFFFFFFFFFFFFll, hi = -0x7FFFFFFFFFFFFFFFll - 1, cnt = 0;
+  bool unsorted = false;
   for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += (int64_t)gridDim.x * blockDim.x) {
     if (row_mask && !row_mask[row]) continue;
     uint64_t key;
-    if (!join_key(k, row, key)) continue;
+    if (!join_key(k, row, key)) {
+      unsorted = true;
+      continue;
+    }
+    if (!row_mask && row > 0) {
+      uint64_t prev;
+      if (!join_key(k, row - 1, prev) || (long long)prev >= (long long)key) unsorted = true;
+    }
     const long long v = (long long)key;
     lo = v < lo ? v : lo;
     hi = v > hi ? v : hi;
@@ -555,6 +575,11 @@ __global__ void __launch_bounds__(JOIN_THREADS) build_stats_kernel(JoinKeys k, i
     atomicMax(&stats[1], hi);
     atomicAdd((unsigned long long *)&stats[2], (unsigned long long)cnt);
   }
+  if (__any_sync(0xffffffffu, unsorted) && (threadIdx.x & 31) == 0) stats[3] = 1;
+}
+__global__ void word_popc_kernel(const uint32_t *__restrict__ words, int64_t n, int32_t *__restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __popc(words[i]);
 }
 
 static KeyFilter key_filter_of(const sb_hash_table *ht) {
@@ -565,6 +590,7 @@ static KeyFilter key_filter_of(const sb_hash_table *ht) {
   f.frange = ht->frange;
   f.exact = ht->exact;
   f.row_of = ht->row_of;
+  f.rank = ht->rank;
   return f;
 }
 
@@ -660,18 +686,19 @@ int sb_join_build_filtered(const sb_table *build, const int32_t *key_cols, int32
     ht->key_shift[i] = k.shift[i];
   }
   // size everything by what will actually be inserted: one pass over the keys (and the fused filter's mask)
-  long long stats[3] = {0x7FFFFFFFFFFFFFFFll, -0x7FFFFFFFFFFFFFFFll - 1, 0};
+  long long stats[4] = {0x7FFFFFFFFFFFFFFFll, -0x7FFFFFFFFFFFFFFFll - 1, 0, 0};
   if (n > 0) {
     Scratch dstats(32, st);
-    SB_CUDA(cudaMemcpyAsync(dstats.ptr, stats, 24, cudaMemcpyHostToDevice, st));
+    SB_CUDA(cudaMemcpyAsync(dstats.ptr, stats, 32, cudaMemcpyHostToDevice, st));
     int64_t g = (n + JOIN_THREADS * 8 - 1) / (JOIN_THREADS * 8);
     if (g > (int64_t)rt().num_sms * 16) g = (int64_t)rt().num_sms * 16;
     build_stats_kernel<<<(unsigned)g, JOIN_THREADS, 0, st>>>(k, n, filter ? mask.as<uint8_t>() : nullptr, dstats.as<long long>());
     SB_LAUNCH_CHECK();
-    SB_CUDA(cudaMemcpyAsync(stats, dstats.ptr, 24, cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaMemcpyAsync(stats, dstats.ptr, 32, cudaMemcpyDeviceToHost, st));
     SB_CUDA(cudaStreamSynchronize(st));
   }
   const int64_t nin = stats[2];
+  const bool ascending = !filter && nin == n && n > 0 && stats[3] == 0;   // strictly ascending, NULL-free: row = rank of the key
   ht->nkeys_in = nin;
   int64_t cap = 1024;
   while (cap < 2 * nin) cap <<= 1;
@@ -716,6 +743,20 @@ int sb_join_build_filtered(const sb_table *build, const int32_t *key_cols, int32
         SB_CUDA(cudaMemsetAsync(ht->null_key_flag, 0, 8, st));
       }
     }
+    if (!built && ht->exact && ascending) {   // sorted mode: bitmap + rank prefix, no slot table
+      {
+        KernelTimer kt("join_build", st);
+        join_build_kernel<<<nblocks, JOIN_THREADS, 0, st>>>(k, n, nullptr, cap, ht->null_key_flag, mask_dev, key_filter_of(ht));
+        SB_LAUNCH_CHECK();
+        Scratch pc(bwords * 4 + 16, st);
+        SB_CUDA(cudaMallocAsync((void **)&ht->rank, (size_t)bwords * 4 + 16, st));
+        word_popc_kernel<<<(unsigned)((bwords + 255) / 256), 256, 0, st>>>(ht->bloom, bwords, pc.as<int32_t>());
+        SB_LAUNCH_CHECK();
+        exclusive_scan_i32(pc.as<int32_t>(), (int32_t *)ht->rank, bwords, nullptr, st);
+      }
+      ht->unique = 1;
+      built = true;
+    }
     if (!built) {
       SB_CUDA(cudaMallocAsync((void **)&ht->slots, (size_t)cap * sizeof(JoinSlot), st));
       SB_CUDA(cudaMemsetAsync(ht->slots, 0xff, (size_t)cap * sizeof(JoinSlot), st));
@@ -737,6 +778,7 @@ int sb_join_build_filtered(const sb_table *build, const int32_t *key_cols, int32
     if (ht->null_key_flag) cudaFreeAsync(ht->null_key_flag, st);
     if (ht->bloom) cudaFreeAsync(ht->bloom, st);
     if (ht->row_of) cudaFreeAsync(ht->row_of, st);
+    if (ht->rank) cudaFreeAsync(ht->rank, st);
     for (int i = 0; i < 4; i++)
       if (ht->has_dict[i]) column_release(ht->dict[i]);
     delete ht;
@@ -757,6 +799,7 @@ int sb_hash_table_release(sb_hash_table *ht) {
     if (ht->null_key_flag) cudaFreeAsync(ht->null_key_flag, ht->st);
     if (ht->bloom) cudaFreeAsync(ht->bloom, ht->st);
     if (ht->row_of) cudaFreeAsync(ht->row_of, ht->st);
+    if (ht->rank) cudaFreeAsync(ht->rank, ht->st);
     if (ht->build && ht->build->refs.fetch_sub(1) == 1) table_free(ht->build);
     for (int i = 0; i < 4; i++)
       if (ht->has_dict[i]) column_release(ht->dict[i]);

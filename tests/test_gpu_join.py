@@ -146,13 +146,14 @@ def test_random_build_preserving_joins(gpu, stream, how, with_condition):
 
 
 @pytest.mark.parametrize("how", ["inner", "left_outer", "left_semi", "left_anti", "left_anti_null_aware"])
-@pytest.mark.parametrize("keys", ["dense", "mid", "sparse", "negative", "nullable"])
+@pytest.mark.parametrize("keys", ["dense", "mid", "sorted", "sparse", "negative", "nullable"])
 @pytest.mark.parametrize("unique", [False, True])
 @pytest.mark.parametrize("variant", [0, 1])
 def test_long_streamed_side_goes_through_the_candidate_pass(gpu, stream, how, keys, unique, variant, sbconfig):
     """>= 2^20 streamed rows: one fused pass (pushed-down filter + key + prefilter) marks the candidates.  `dense` keys make the
     prefilter an exact key-range bitmap, `sparse` (60-bit) keys a Bloom filter; `negative` crosses zero; `nullable` takes the
-    general key path; `mid` is a key range too sparse for the direct-address table but dense enough for the bitmap.  With `unique`
+    general key path; `mid` is a key range too sparse for the direct-address table but dense enough for the bitmap; `sorted` are
+    such keys arriving in ascending order (no slot table: the row of a key is its rank among the bitmap's set bits).  With `unique`
     build keys an exact prefilter settles semi / anti joins in the pass and inner / outer joins take one lookup per candidate (a
     dense range through row_of[key - min]); duplicates go through count / scan / fill.  The streamed row count is not a multiple of 16 (ragged tail), the filter is either a conjunction of
     comparisons (evaluated inside the pass) or an OR (evaluated to a mask first)."""
@@ -168,11 +169,15 @@ def test_long_streamed_side_goes_through_the_candidate_pass(gpu, stream, how, ke
         universe = rng.integers(0, 1 << 60, 4 * nb)
     elif keys == "negative":
         universe = np.arange(-2 * nb, 2 * nb, dtype=np.int64)
-    elif keys == "mid":
+    elif keys in ("mid", "sorted"):
         universe = np.arange(0, 20 * nb, dtype=np.int64) * 3 + 17
     else:
         universe = np.arange(1000, 1000 + 4 * nb, dtype=np.int64)
     bk = rng.choice(universe, nb, replace=False)
+    if keys == "sorted":                                       # strictly ascending build keys: the row of a key is its rank in the bitmap
+        if not unique:
+            pytest.skip("sorted mode needs unique keys")
+        bk = np.sort(bk)
     if not unique:
         bk[:100] = bk[100:200]                                 # duplicate build keys: the count / fill passes still see them
     pk = rng.choice(universe, npr)
@@ -193,3 +198,18 @@ def test_long_streamed_side_goes_through_the_candidate_pass(gpu, stream, how, ke
         if how in ("inner", "left_semi", "left_anti", "left_anti_null_aware"):   # streamed order is preserved
             r = np.asarray(got.column("row"))
             assert np.all(r[1:] >= r[:-1])
+
+
+@pytest.mark.parametrize("how", ["inner", "left_outer", "left_semi", "left_anti", "full_outer", "right_outer", "existence"])
+def test_short_streamed_side_over_a_sorted_relation(gpu, stream, how):
+    """Build keys in strictly ascending order (a key-ordered scan, the output of a join over one): the relation is a bitmap + rank
+    prefix without a slot table; a short streamed side goes through the general count / fill passes, which must find rows by rank."""
+    rng = np.random.default_rng(21)
+    nb, npr = 30_000, 50_000
+    bk = np.sort(rng.choice(np.arange(0, 40 * nb, dtype=np.int64), nb, replace=False))
+    build = pa.table({"id": pa.array(bk, type=pa.int64()), "payload": np.arange(nb, dtype=np.int64)})
+    probe = pa.table({"fk": pa.array(rng.integers(-5, 40 * nb + 5, npr), type=pa.int64(), mask=rng.random(npr) < 0.02), "row": np.arange(npr, dtype=np.int64)})
+    got = _plan_join(probe, build, ["fk"], ["id"], how, stream)
+    want = O.hash_join(probe, build, ["fk"], ["id"], how)
+    assert got.num_rows == want.num_rows
+    assert_tables_equal(got, want, key_cols=list(want.column_names))
