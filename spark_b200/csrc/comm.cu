@@ -12,6 +12,7 @@
 // in Spark, torch.distributed/gloo in the tests).
 #include <dlfcn.h>
 #include <algorithm>
+#include <memory>
 #include <nccl.h>
 #include "common.cuh"
 #include "primitives.cuh"
@@ -448,7 +449,7 @@ static int all_to_all_by_source(const sb_table *in, const int64_t *part_offsets_
     try {
       KernelTimer kt_transfer("a2a_transfer", st);
       const int me = c.rank;
-      std::vector<Scratch *> temps;
+      std::vector<std::unique_ptr<Scratch>> temps;   // released (stream-ordered) on every exit, an exception included
       std::vector<uint8_t *> send_bytes(in->cols.size(), nullptr);
       t->cols.reserve(in->cols.size());
       for (size_t ci = 0; ci < in->cols.size(); ci++) {
@@ -456,7 +457,7 @@ static int all_to_all_by_source(const sb_table *in, const int64_t *part_offsets_
         t->cols.push_back(column_alloc(col.type, col.scale, nrecv, nullable(ci), st));
         if (nullable(ci)) {
           Scratch *sb = new Scratch(in->nrows + 16, st);
-          temps.push_back(sb);
+          temps.emplace_back(sb);
           bitmap_to_bytes(col.v(), in->nrows, sb->as<uint8_t>(), st);
           send_bytes[ci] = sb->as<uint8_t>();
         }
@@ -510,7 +511,7 @@ static int all_to_all_by_source(const sb_table *in, const int64_t *part_offsets_
         }
         SB_CUDA(cudaStreamSynchronize(st));
       }
-      for (auto *x : temps) delete x;
+      temps.clear();
     } catch (...) {
       table_free(t);
       throw;
@@ -522,7 +523,7 @@ static int all_to_all_by_source(const sb_table *in, const int64_t *part_offsets_
   // one grouped send/recv per (column buffer, peer)
   sb_table *t = table_new(nrecv);
   try {
-    std::vector<Scratch *> temps;
+    std::vector<std::unique_ptr<Scratch>> temps;   // released (stream-ordered) on every exit, an exception included
     struct Pending { Column *col; uint8_t *recv_bytes; };
     std::vector<Pending> pend;
     std::vector<std::pair<const uint8_t *, uint8_t *>> self_valid;   // (send bytes, recv bytes) of every nullable column
@@ -547,8 +548,8 @@ static int all_to_all_by_source(const sb_table *in, const int64_t *part_offsets_
       }
       if (nullable(ci)) {
         Scratch *sb = new Scratch(in->nrows + 16, st), *rb = new Scratch(nrecv + 16, st);
-        temps.push_back(sb);
-        temps.push_back(rb);
+        temps.emplace_back(sb);
+        temps.emplace_back(rb);
         bitmap_to_bytes(src.v(), in->nrows, sb->as<uint8_t>(), st);
         for (int peer = 0; peer < R; peer++) {
           if (peer == c.rank) continue;
@@ -589,7 +590,7 @@ static int all_to_all_by_source(const sb_table *in, const int64_t *part_offsets_
       bytes_to_bitmap(p.recv_bytes, nrecv, (uint32_t *)p.col->validity->ptr, st);
     }
     SB_CUDA(cudaStreamSynchronize(st));
-    for (auto *x : temps) delete x;
+    temps.clear();
   } catch (...) {
     table_free(t);
     throw;
@@ -768,7 +769,7 @@ static int all_gather_fixed(const sb_table *in, sb_stream *s, sb_table **out) {
     if (fits) {
       sb_table *t = table_new(total);
       try {
-        std::vector<Scratch *> temps;
+        std::vector<std::unique_ptr<Scratch>> temps;   // released (stream-ordered) on every exit, an exception included
         for (int ci = 0; ci < a.ncols; ci++) {
           const Column &col = in->cols[ci];
           const bool nullable = (any_valid >> ci) & 1;
@@ -777,7 +778,7 @@ static int all_gather_fixed(const sb_table *in, sb_stream *s, sb_table **out) {
           a.dst_valid_bytes[ci] = nullptr;
           if (nullable) {
             Scratch *vb = new Scratch(total + 16, st);
-            temps.push_back(vb);
+            temps.emplace_back(vb);
             a.dst_valid_bytes[ci] = vb->as<uint8_t>();
           }
         }
@@ -787,7 +788,7 @@ static int all_gather_fixed(const sb_table *in, sb_stream *s, sb_table **out) {
           for (int ci = 0; ci < a.ncols; ci++)
             if (a.dst_valid_bytes[ci]) bytes_to_bitmap(a.dst_valid_bytes[ci], total, (uint32_t *)t->cols[ci].validity->ptr, st);
         }
-        for (auto *x : temps) delete x;   // stream-ordered frees
+        temps.clear();   // stream-ordered frees
       } catch (...) {
         table_free(t);
         throw;
@@ -816,7 +817,7 @@ static int all_gather_fixed(const sb_table *in, sb_stream *s, sb_table **out) {
   const int64_t total = off[R];
   sb_table *t = table_new(total);
   try {
-    std::vector<Scratch *> temps;
+    std::vector<std::unique_ptr<Scratch>> temps;   // released (stream-ordered) on every exit, an exception included
     struct Pending { Column *col; uint8_t *bytes; };
     std::vector<Pending> pend;
     t->cols.reserve(in->cols.size());
@@ -836,8 +837,8 @@ static int all_gather_fixed(const sb_table *in, sb_stream *s, sb_table **out) {
       }
       if ((any_mask >> ci) & 1) {
         Scratch *sb = new Scratch(my + 16, st), *rb = new Scratch(total + 16, st);
-        temps.push_back(sb);
-        temps.push_back(rb);
+        temps.emplace_back(sb);
+        temps.emplace_back(rb);
         bitmap_to_bytes(src.v(), my, sb->as<uint8_t>(), st);   // no bitmap on this rank: all ones
         for (int peer = 0; peer < R; peer++) {
           if (my > 0) SB_NCCL(nccl().Send(sb->as<uint8_t>(), (size_t)my, ncclUint8, peer, c.comm, st));
@@ -852,7 +853,7 @@ static int all_gather_fixed(const sb_table *in, sb_stream *s, sb_table **out) {
       bytes_to_bitmap(p.bytes, total, (uint32_t *)p.col->validity->ptr, st);
     }
     SB_CUDA(cudaStreamSynchronize(st));
-    for (auto *x : temps) delete x;
+    temps.clear();
   } catch (...) {
     table_free(t);
     throw;

@@ -773,6 +773,7 @@ int sb_join_build_filtered(const sb_table *build, const int32_t *key_cols, int32
     }
     ht->build = const_cast<sb_table *>(build);
     ht->build->refs.fetch_add(1);
+    SB_CUDA(cudaStreamSynchronize(st));   // a relation is handed to other task threads / streams (broadcast): complete on return
   } catch (...) {
     if (ht->slots) cudaFreeAsync(ht->slots, st);
     if (ht->null_key_flag) cudaFreeAsync(ht->null_key_flag, st);

@@ -314,7 +314,8 @@ def range_bounds(batch: ColumnarBatch, ordering, numPartitions: int, stream=None
 class ShuffleExchangeExec(SparkPlan):
     """Map side always runs on the local GPU (partition ids + regrouping).  With a communicator
     (sb_comm_init done, world size > 1) the buckets are exchanged with the NCCL all-to-all and the
-    result holds the partitions this rank owns (partition p -> rank p % world)."""
+    result holds the partitions this rank owns (contiguous ownership: rank r owns partitions [ceil(r n / R), ceil((r + 1) n / R)),
+    sb_exchange_plan), partition-contiguous."""
 
     def __init__(self, outputPartitioning, child: SparkPlan, fused=None):
         self.outputPartitioning = outputPartitioning

@@ -140,6 +140,47 @@ def main():
              {"encoded_bytes": enc, "decode_kernel_gbs": (enc + 38 * n) / (k["scan_decode"][0] / 1e3) / 1e9 if k["scan_decode"][0] else None})
         b.close()
 
+    if only in ("", "strings"):
+        # ---- string grouping keys (dictionary codes inside sb_hash_aggregate): 32 M rows, 25 and 1 M distinct strings ---------------------
+        import pyarrow as pa
+        n = 32_000_000
+        for distinct in (25, 1_000_000):
+            words = np.array(["key-%07d" % i for i in range(distinct)])
+            tbl = pa.table({"s": pa.array(words[rng.integers(0, distinct, n)], type=pa.string()), "v": rng.integers(0, 1000, n)})
+            b = ColumnarBatch.from_arrow(tbl, stream)
+            stream.synchronize()
+            agg = HashAggregateExec(["s"], [(Sum(col("v")), "t")], LocalTableScanExec(b))
+            ms, k = timed(lib, stream, lambda: agg.executeColumnar(stream).close(), ["dictionary_encode", "agg_update"])
+            emit("hash_aggregate sum(int64) by string key (11 B), %d distinct" % distinct, n, n * (11 + 4 + 8), ms, k)
+            b.close()
+
+    if only in ("", "window"):
+        # ---- WindowExec: 16 M rows, 1 M partitions, ORDER BY one int column: row_number + running sum + lag -----------------------------
+        from spark_b200.execution import WindowExec, WindowFunction
+        n = 16_000_000
+        b = ColumnarBatch.from_numpy({"p": rng.integers(0, 1_000_000, n), "o": rng.integers(0, 1 << 20, n).astype(np.int32), "v": rng.integers(0, 1000, n)}, stream)
+        stream.synchronize()
+        w = WindowExec([WindowFunction("row_number", None, None, 0, "rn"), WindowFunction("sum", "v", ("rows", None, 0), 0, "run"),
+                        WindowFunction("lag", "v", None, 1, "prev")], ["p"], [("o", True, True)], LocalTableScanExec(b))
+        ms, k = timed(lib, stream, lambda: w.executeColumnar(stream).close(), ["sort_passes", "gather"])
+        emit("window row_number + running sum + lag, 1 M partitions", n, n * (20 + 20 + 4 + 8 + 8), ms, k)
+        b.close()
+
+    if only in ("", "decimal"):
+        # ---- decimal(12, 2) SUM + AVG by 1 K groups, 32 M rows (limb sums around the aggregate) ---------------------------------------------
+        import pyarrow as pa
+        from spark_b200.expressions import Average
+        n = 32_000_000
+        raw = np.zeros((n, 2), np.int64)
+        raw[:, 0] = rng.integers(0, 10 ** 11, n)
+        dec = pa.Array.from_buffers(pa.decimal128(12, 2), n, [None, pa.py_buffer(raw.tobytes())])
+        b = ColumnarBatch.from_arrow(pa.table({"k": rng.integers(0, 1000, n).astype(np.int32), "d": dec}), stream)
+        stream.synchronize()
+        agg = HashAggregateExec(["k"], [(Sum(col("d")), "s"), (Average(col("d")), "a")], LocalTableScanExec(b))
+        ms, k = timed(lib, stream, lambda: agg.executeColumnar(stream).close(), ["agg_update"])
+        emit("hash_aggregate sum + avg(decimal(12, 2)) groups=1000", n, n * 12, ms, k)
+        b.close()
+
     if only in ("", "join"):
         # ---- hash join: 21M probe x 65k build (JoinBenchmark-results.txt:10) and a 16M-row build -----------------------------
         for nb, npr in ((65536, 21_000_000), (16_000_000, 64_000_000)):
