@@ -386,94 +386,120 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_candidate_kernel(JoinKeys k
 // so the bits buffer, the block counts and the second kernel are shared with the variant above.
 // KW: 0 = general keys (join_key per row), 4 / 8 = ONE NULL-free integer key column of that width.
 constexpr int CAND_STEP = 8;
+template <int KW, bool FULL>
+__device__ __forceinline__ uint32_t candidate_step(const JoinKeys &k, int64_t n, const SimplePred &sp, const uint8_t *__restrict__ row_mask,
+                                                   const KeyFilter &kf, int mode, int64_t g0, int lane, uint32_t (&words)[CAND_STEP]) {
+  // rows of this lane: g0 + lane + 32 j.  FULL: the whole step lies below n, so nothing is clamped and the column pointers are
+  // advanced once (the loads take constant offsets)
+  const int64_t r0 = g0 + lane;
+  bool keep[CAND_STEP], has[CAND_STEP];
+  uint64_t key[CAND_STEP];
+  int64_t rr[CAND_STEP];
+#pragma unroll
+  for (int j = 0; j < CAND_STEP; j++) {
+    const int64_t r = r0 + (int64_t)j * 32;
+    keep[j] = FULL || r < n;
+    rr[j] = FULL || r < n ? r : n - 1;
+    has[j] = true;
+  }
+  if (mode != CAND_ALL) {   // the key loads do not wait for the filter's verdict
+    if (KW == 8) {
+      const uint64_t *p = (const uint64_t *)k.data[0] + (FULL ? r0 : 0);
+#pragma unroll
+      for (int j = 0; j < CAND_STEP; j++) key[j] = FULL ? p[j * 32] : p[rr[j]];
+    } else if (KW == 4) {
+      const uint32_t *p = (const uint32_t *)k.data[0] + (FULL ? r0 : 0);
+#pragma unroll
+      for (int j = 0; j < CAND_STEP; j++) key[j] = (uint64_t)(FULL ? p[j * 32] : p[rr[j]]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < CAND_STEP; j++) {
+        key[j] = 0;
+        has[j] = join_key(k, rr[j], key[j]);
+      }
+    }
+  }
+  if (sp.nterms > 0) simple_pred_rows<CAND_STEP, FULL>(sp, r0, 32, n, keep);
+  if (row_mask) {
+    uint8_t m[CAND_STEP];
+#pragma unroll
+    for (int j = 0; j < CAND_STEP; j++) m[j] = row_mask[rr[j]];
+#pragma unroll
+    for (int j = 0; j < CAND_STEP; j++) keep[j] = keep[j] && m[j] != 0;
+  }
+  if (mode != CAND_ALL) {
+    bool present[CAND_STEP];
+#pragma unroll
+    for (int j = 0; j < CAND_STEP; j++) present[j] = has[j] && keep[j];
+    if (kf.words && kf.exact) {   // frange <= 2^31: inside the range the offset is a 32-bit number
+      uint32_t w[CAND_STEP], d[CAND_STEP];
+#pragma unroll
+      for (int j = 0; j < CAND_STEP; j++) {
+        const uint64_t d64 = key[j] - kf.fmin;
+        present[j] = present[j] && d64 < kf.frange;
+        d[j] = (uint32_t)d64;
+        w[j] = present[j] ? __ldg(&kf.words[d[j] >> 5]) : 0u;
+      }
+#pragma unroll
+      for (int j = 0; j < CAND_STEP; j++) present[j] = present[j] && ((w[j] >> (d[j] & 31)) & 1u);
+    } else if (kf.words) {
+      uint32_t w[CAND_STEP], bb[CAND_STEP];
+#pragma unroll
+      for (int j = 0; j < CAND_STEP; j++) {
+        const uint64_t hh = join_mix(key[j]);
+        bb[j] = bloom_bits(hh);
+        w[j] = present[j] ? __ldg(&kf.words[bloom_word(hh, kf.mask)]) : 0u;
+      }
+#pragma unroll
+      for (int j = 0; j < CAND_STEP; j++) present[j] = present[j] && (w[j] & bb[j]) == bb[j];
+    }
+    if (mode == CAND_PRESENT) {
+#pragma unroll
+      for (int j = 0; j < CAND_STEP; j++) keep[j] = present[j];          // present implies keep
+    } else if (mode == CAND_ABSENT) {
+#pragma unroll
+      for (int j = 0; j < CAND_STEP; j++) keep[j] = keep[j] && !present[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < CAND_STEP; j++) keep[j] = keep[j] && has[j] && !present[j];
+    }
+  }
+  uint32_t count = 0;
+#pragma unroll
+  for (int j = 0; j < CAND_STEP; j++) {
+    words[j] = __ballot_sync(0xffffffffu, keep[j]);
+    count += __popc(words[j]);
+  }
+  return count;
+}
+// the ragged last step of the input: kept out of line so that its clamping code costs the full steps no registers
+template <int KW>
+__device__ __noinline__ uint32_t candidate_step_tail(const JoinKeys &k, int64_t n, const SimplePred &sp, const uint8_t *__restrict__ row_mask,
+                                                     const KeyFilter &kf, int mode, int64_t g0, int lane, uint32_t (&words)[CAND_STEP]) {
+  return candidate_step<KW, false>(k, n, sp, row_mask, kf, mode, g0, lane, words);
+}
 template <int KW>
 __global__ void __launch_bounds__(JOIN_THREADS) join_candidate_strided_kernel(JoinKeys k, int64_t n, const __grid_constant__ SimplePred sp,
                                                                               const uint8_t *__restrict__ row_mask, KeyFilter kf, int mode,
                                                                               uint32_t *__restrict__ bits_out, int32_t *__restrict__ block_counts) {
   __shared__ int32_t wsum[JOIN_THREADS / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t wbase = (int64_t)blockIdx.x * CAND_TILE + (int64_t)warp * (CAND_TILE / (JOIN_THREADS / 32));
-  int32_t mine = 0;
+  constexpr int WARP_ROWS = CAND_TILE / (JOIN_THREADS / 32);
+  const int64_t wbase = (int64_t)blockIdx.x * CAND_TILE + (int64_t)warp * WARP_ROWS;
+  uint32_t mine = 0;
 #pragma unroll 1
-  for (int c = 0; c < CAND_TILE / (JOIN_THREADS / 32) / 32; c += CAND_STEP) {
-    const int64_t r0 = wbase + (int64_t)c * 32 + lane;
-    if (wbase + (int64_t)c * 32 >= n) break;
-    bool keep[CAND_STEP], has[CAND_STEP];
-    uint64_t key[CAND_STEP];
-    int64_t rr[CAND_STEP];
+  for (int c = 0; c < WARP_ROWS / 32; c += CAND_STEP) {
+    const int64_t g0 = wbase + (int64_t)c * 32;
+    if (g0 >= n) break;
+    uint32_t words[CAND_STEP];
+    const uint32_t cnt = g0 + CAND_STEP * 32 <= n ? candidate_step<KW, true>(k, n, sp, row_mask, kf, mode, g0, lane, words)
+                                                   : candidate_step_tail<KW>(k, n, sp, row_mask, kf, mode, g0, lane, words);
+    mine += cnt;   // the same on every lane
 #pragma unroll
-    for (int j = 0; j < CAND_STEP; j++) {
-      const int64_t r = r0 + (int64_t)j * 32;
-      keep[j] = r < n;
-      rr[j] = r < n ? r : n - 1;
-      has[j] = true;
-    }
-    if (mode != CAND_ALL) {   // the key loads do not wait for the filter's verdict
-      if (KW == 8) {
-#pragma unroll
-        for (int j = 0; j < CAND_STEP; j++) key[j] = ((const uint64_t *)k.data[0])[rr[j]];
-      } else if (KW == 4) {
-#pragma unroll
-        for (int j = 0; j < CAND_STEP; j++) key[j] = (uint64_t)((const uint32_t *)k.data[0])[rr[j]];
-      } else {
-#pragma unroll
-        for (int j = 0; j < CAND_STEP; j++) {
-          key[j] = 0;
-          has[j] = join_key(k, rr[j], key[j]);
-        }
-      }
-    }
-    if (sp.nterms > 0) simple_pred_rows<CAND_STEP>(sp, r0, 32, n, keep);
-    if (row_mask) {
-      uint8_t m[CAND_STEP];
-#pragma unroll
-      for (int j = 0; j < CAND_STEP; j++) m[j] = row_mask[rr[j]];
-#pragma unroll
-      for (int j = 0; j < CAND_STEP; j++) keep[j] = keep[j] && m[j] != 0;
-    }
-    if (mode != CAND_ALL) {
-      bool present[CAND_STEP];
-#pragma unroll
-      for (int j = 0; j < CAND_STEP; j++) present[j] = has[j];
-      if (kf.words && kf.exact) {
-        uint32_t w[CAND_STEP];
-        uint64_t d[CAND_STEP];
-#pragma unroll
-        for (int j = 0; j < CAND_STEP; j++) {
-          d[j] = key[j] - kf.fmin;
-          present[j] = present[j] && keep[j] && d[j] < kf.frange;
-          w[j] = present[j] ? __ldg(&kf.words[d[j] >> 5]) : 0u;
-        }
-#pragma unroll
-        for (int j = 0; j < CAND_STEP; j++) present[j] = present[j] && ((w[j] >> (d[j] & 31)) & 1u);
-      } else if (kf.words) {
-        uint32_t w[CAND_STEP], bb[CAND_STEP];
-#pragma unroll
-        for (int j = 0; j < CAND_STEP; j++) {
-          const uint64_t hh = join_mix(key[j]);
-          bb[j] = bloom_bits(hh);
-          present[j] = present[j] && keep[j];
-          w[j] = present[j] ? __ldg(&kf.words[bloom_word(hh, kf.mask)]) : 0u;
-        }
-#pragma unroll
-        for (int j = 0; j < CAND_STEP; j++) present[j] = present[j] && (w[j] & bb[j]) == bb[j];
-      }
-#pragma unroll
-      for (int j = 0; j < CAND_STEP; j++)
-        keep[j] = keep[j] && (mode == CAND_PRESENT ? present[j] : mode == CAND_ABSENT ? !present[j] : (has[j] && !present[j]));
-    }
-#pragma unroll
-    for (int j = 0; j < CAND_STEP; j++) {
-      const uint32_t word = __ballot_sync(0xffffffffu, keep[j]);
-      const int64_t w = (wbase >> 5) + c + j;
-      if (lane == j && w * 32 < n) {
-        bits_out[w] = word;
-        mine += __popc(word);
-      }
-    }
+    for (int j = 0; j < CAND_STEP; j++)
+      if (lane == j && g0 + (int64_t)j * 32 < n) bits_out[(g0 >> 5) + j] = words[j];
   }
-  const int32_t t = __reduce_add_sync(0xffffffffu, mine);
-  if (lane == 0) wsum[warp] = t;
+  if (lane == 0) wsum[warp] = (int32_t)mine;
   __syncthreads();
   if (threadIdx.x == 0) {
     int32_t b = 0;

@@ -2,6 +2,7 @@
 // FilterExec fast path (expr.cu) and the operators that fuse the filter below them into their own first pass (join.cu).
 #pragma once
 #include "common.cuh"
+#include <limits.h>
 
 namespace sb {
 
@@ -94,16 +95,31 @@ __device__ __forceinline__ uint32_t simple_pred_eval16(const SimplePred &sp, int
   }
   return keep & 0xFFFFu;
 }
+// keep[j] &&= x[j] <op> lit, the operator chosen once outside the row loop (uniform switch, one compare per row)
+template <typename T, int R>
+__device__ __forceinline__ void sp_compare_rows(const T (&x)[R], T lit, int op, bool (&keep)[R]) {
+  switch (op) {
+#define SB_SP_ROWS(COND) _Pragma("unroll") for (int j = 0; j < R; j++) keep[j] = keep[j] && (COND);
+    case SP_EQ: SB_SP_ROWS(x[j] == lit) break;
+    case SP_NE: SB_SP_ROWS(x[j] != lit) break;
+    case SP_LT: SB_SP_ROWS(x[j] < lit) break;
+    case SP_LE: SB_SP_ROWS(x[j] <= lit) break;
+    case SP_GT: SB_SP_ROWS(x[j] > lit) break;
+    default: SB_SP_ROWS(x[j] >= lit) break;
+#undef SB_SP_ROWS
+  }
+}
 // the same predicate for R rows row0, row0 + stride, ... (lane-strided kernels: the 32 lanes of a warp read 32 consecutive rows,
 // so plain loads coalesce).  Term by term: all R loads of a term are issued before the first comparison uses one, so they overlap;
-// the type switch is outside the row loop (uniform).  Rows >= n are clamped for the loads and masked by the caller.
-template <int R>
+// type and operator switches are outside the row loops (uniform).  FULL: every row is < n (no clamping); otherwise rows >= n are
+// clamped for the loads and masked by the caller.  32-bit columns against a literal that fits compare at 32 bits.
+template <int R, bool FULL>
 __device__ __forceinline__ void simple_pred_rows(const SimplePred &sp, int64_t row0, int64_t stride, int64_t n, bool (&keep)[R]) {
   int64_t rr[R];
 #pragma unroll
   for (int j = 0; j < R; j++) {
     const int64_t r = row0 + j * stride;
-    rr[j] = r < n ? r : n - 1;
+    rr[j] = FULL || r < n ? r : n - 1;
   }
 #pragma unroll 1
   for (int t = 0; t < sp.nterms; t++) {
@@ -116,11 +132,29 @@ __device__ __forceinline__ void simple_pred_rows(const SimplePred &sp, int64_t r
     }
     const int op = sp.op[t];
     if (op == SP_NOTNULL) continue;
+    const int64_t lit = sp.lit[t];
+    const bool f64 = sp.f64[t] != 0;
+    const int32_t ty = sp.type[t];
+    if (!f64 && (ty == SB_INT32 || ty == SB_DATE32)) {
+      int32_t x32[R];
+      const int32_t *p = (const int32_t *)sp.data[t];
+#pragma unroll
+      for (int j = 0; j < R; j++) x32[j] = p[rr[j]];
+      if (lit >= INT32_MIN && lit <= INT32_MAX) {
+        sp_compare_rows<int32_t, R>(x32, (int32_t)lit, op, keep);
+      } else {
+        int64_t x[R];
+#pragma unroll
+        for (int j = 0; j < R; j++) x[j] = x32[j];
+        sp_compare_rows<int64_t, R>(x, lit, op, keep);
+      }
+      continue;
+    }
     int64_t x[R];
-    switch (sp.type[t]) {
+    switch (ty) {
       case SB_BOOL: case SB_INT8:
 #pragma unroll
-        for (int j = 0; j < R; j++) x[j] = sp.type[t] == SB_BOOL ? (int64_t)((const uint8_t *)sp.data[t])[rr[j]] : (int64_t)((const int8_t *)sp.data[t])[rr[j]];
+        for (int j = 0; j < R; j++) x[j] = ty == SB_BOOL ? (int64_t)((const uint8_t *)sp.data[t])[rr[j]] : (int64_t)((const int8_t *)sp.data[t])[rr[j]];
         break;
       case SB_INT16:
 #pragma unroll
@@ -135,24 +169,21 @@ __device__ __forceinline__ void simple_pred_rows(const SimplePred &sp, int64_t r
         for (int j = 0; j < R; j++) x[j] = ((const int64_t *)sp.data[t])[rr[j]];
         break;
     }
-    const int64_t lit = sp.lit[t];
-    const bool f64 = sp.f64[t] != 0, f32 = sp.type[t] == SB_FLOAT32;
-    // which signs of compare(x, lit) satisfy the operator: uniform per term, so the row loop below has no branch on `op`
-    const bool want_lt = op == SP_LT || op == SP_LE || op == SP_NE, want_eq = op == SP_EQ || op == SP_LE || op == SP_GE,
-               want_gt = op == SP_GT || op == SP_GE || op == SP_NE;
+    if (!f64) {
+      sp_compare_rows<int64_t, R>(x, lit, op, keep);
+      continue;
+    }
+    // doubles: SQLOrderingUtil.compareDoubles (NaN equals NaN and is larger than anything else) as a three-way result
+    const double y = __longlong_as_double(lit);
+    const bool f32 = ty == SB_FLOAT32, yn = y != y;
+    int c[R];
 #pragma unroll
     for (int j = 0; j < R; j++) {
-      int c;
-      if (f64) {   // SQLOrderingUtil.compareDoubles: NaN equals NaN and is larger than anything else
-        const double y = __longlong_as_double(lit);
-        const double d = f32 ? (double)__int_as_float((int32_t)x[j]) : __longlong_as_double(x[j]);
-        const bool dn = d != d, yn = y != y;
-        c = d == y ? 0 : (dn || yn) ? (int)dn - (int)yn : (d < y ? -1 : 1);
-      } else {
-        c = x[j] == lit ? 0 : (x[j] < lit ? -1 : 1);
-      }
-      keep[j] = keep[j] && ((c < 0 && want_lt) || (c == 0 && want_eq) || (c > 0 && want_gt));
+      const double d = f32 ? (double)__int_as_float((int32_t)x[j]) : __longlong_as_double(x[j]);
+      const bool dn = d != d;
+      c[j] = d == y ? 0 : (dn || yn) ? (int)dn - (int)yn : (d < y ? -1 : 1);
     }
+    sp_compare_rows<int, R>(c, 0, op, keep);
   }
 }
 #endif

@@ -89,9 +89,9 @@ def test_window_functions_against_the_oracle(gpu, stream, n, nparts):
     # (the oracle re-evaluates every sliding frame: only where partitions are small)
     if n // nparts > 1000:
         return
-    for orders3, specs3 in (([("o", True, True)], [("sum", "v", ("range", -3, 2), 0, "s"), ("count", "d", ("range", -1, None), 0, "c"), ("max", "v", ("range", None, 4), 0, "m")]),
-                            ([("o", False, False)], [("sum", "v", ("range", -3, 2), 0, "s"), ("avg", "d", ("range", 0, 5), 0, "a")]),
-                            ([("d", True, False)], [("count", "v", ("range", -2.5, 0.75), 0, "c"), ("sum", "d", ("range", None, 1.5), 0, "s")])):
+    for orders3, specs3 in (([("o", True, True)], [("sum", "v", ("range", -3, 2), 0, "rs"), ("count", "d", ("range", -1, None), 0, "rc"), ("max", "v", ("range", None, 4), 0, "rm")]),
+                            ([("o", False, False)], [("sum", "v", ("range", -3, 2), 0, "rs"), ("avg", "d", ("range", 0, 5), 0, "ra")]),
+                            ([("d", True, False)], [("count", "v", ("range", -2.5, 0.75), 0, "rc"), ("sum", "d", ("range", None, 1.5), 0, "rs")])):
         got3 = _window(t, ["p"], orders3, specs3, stream)
         want3 = O.window(t, ["p"], orders3, specs3)
         assert_tables_equal(got3, want3, key_cols=["p", orders3[0][0], "row"])
