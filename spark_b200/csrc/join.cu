@@ -385,8 +385,7 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_candidate_kernel(JoinKeys k
 // they overlap.  The verdicts of 32 rows are one ballot word = two of the 16-bit words candidate_rows_kernel reads (little endian),
 // so the bits buffer, the block counts and the second kernel are shared with the variant above.
 // KW: 0 = general keys (join_key per row), 4 / 8 = ONE NULL-free integer key column of that width.
-constexpr int CAND_STEP = 8;
-template <int KW, bool FULL>
+template <int KW, bool FULL, int CAND_STEP>
 __device__ __forceinline__ uint32_t candidate_step(const JoinKeys &k, int64_t n, const SimplePred &sp, const uint8_t *__restrict__ row_mask,
                                                    const KeyFilter &kf, int mode, int64_t g0, int lane, uint32_t (&words)[CAND_STEP]) {
   // rows of this lane: g0 + lane + 32 j.  FULL: the whole step lies below n, so nothing is clamped and the column pointers are
@@ -473,13 +472,13 @@ __device__ __forceinline__ uint32_t candidate_step(const JoinKeys &k, int64_t n,
   return count;
 }
 // the ragged last step of the input: kept out of line so that its clamping code costs the full steps no registers
-template <int KW>
+template <int KW, int CAND_STEP>
 __device__ __noinline__ uint32_t candidate_step_tail(const JoinKeys &k, int64_t n, const SimplePred &sp, const uint8_t *__restrict__ row_mask,
                                                      const KeyFilter &kf, int mode, int64_t g0, int lane, uint32_t (&words)[CAND_STEP]) {
-  return candidate_step<KW, false>(k, n, sp, row_mask, kf, mode, g0, lane, words);
+  return candidate_step<KW, false, CAND_STEP>(k, n, sp, row_mask, kf, mode, g0, lane, words);
 }
-template <int KW>
-__global__ void __launch_bounds__(JOIN_THREADS) join_candidate_strided_kernel(JoinKeys k, int64_t n, const __grid_constant__ SimplePred sp,
+template <int KW, int CAND_STEP, int MINB>
+__global__ void __launch_bounds__(JOIN_THREADS, MINB) join_candidate_strided_kernel(JoinKeys k, int64_t n, const __grid_constant__ SimplePred sp,
                                                                               const uint8_t *__restrict__ row_mask, KeyFilter kf, int mode,
                                                                               uint32_t *__restrict__ bits_out, int32_t *__restrict__ block_counts) {
   __shared__ int32_t wsum[JOIN_THREADS / 32];
@@ -492,8 +491,8 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_candidate_strided_kernel(Jo
     const int64_t g0 = wbase + (int64_t)c * 32;
     if (g0 >= n) break;
     uint32_t words[CAND_STEP];
-    const uint32_t cnt = g0 + CAND_STEP * 32 <= n ? candidate_step<KW, true>(k, n, sp, row_mask, kf, mode, g0, lane, words)
-                                                   : candidate_step_tail<KW>(k, n, sp, row_mask, kf, mode, g0, lane, words);
+    const uint32_t cnt = g0 + CAND_STEP * 32 <= n ? candidate_step<KW, true, CAND_STEP>(k, n, sp, row_mask, kf, mode, g0, lane, words)
+                                                   : candidate_step_tail<KW, CAND_STEP>(k, n, sp, row_mask, kf, mode, g0, lane, words);
     mine += cnt;   // the same on every lane
 #pragma unroll
     for (int j = 0; j < CAND_STEP; j++)
@@ -962,13 +961,18 @@ int sb_join_probe_ex(const sb_hash_table *ht, const sb_table *probe, const int32
     Scratch bits(nwords * 2 + 16, st), bcount((int64_t)cb * 4 + 16, st), boff((int64_t)cb * 8 + 16, st), tot(8, st);
     const int fast_key = k.n == 1 && !k.valid[0] && k.type[0] != SB_FLOAT32 && k.type[0] != SB_FLOAT64 && k.type[0] != SB_BOOL &&
                          ((uintptr_t)k.data[0] & 15) == 0;
-    if (config().join_cand == 1) {
+    if (config().join_cand >= 1) {
       // the ballot words are written as uint32: the buffer must hold whole 32-row words (nwords is in 16-row units)
       const bool int_key = k.n == 1 && !k.valid[0] && k.type[0] != SB_FLOAT32 && k.type[0] != SB_FLOAT64 && k.type[0] != SB_BOOL;
       const int kw = !int_key ? 0 : (k.bits[0] == 64 ? 8 : k.bits[0] == 32 ? 4 : 0);
-      if (kw == 8) join_candidate_strided_kernel<8><<<cb, JOIN_THREADS, 0, st>>>(k, n, sp, pmask_dev, kf, cand_mode, bits.as<uint32_t>(), bcount.as<int32_t>());
-      else if (kw == 4) join_candidate_strided_kernel<4><<<cb, JOIN_THREADS, 0, st>>>(k, n, sp, pmask_dev, kf, cand_mode, bits.as<uint32_t>(), bcount.as<int32_t>());
-      else join_candidate_strided_kernel<0><<<cb, JOIN_THREADS, 0, st>>>(k, n, sp, pmask_dev, kf, cand_mode, bits.as<uint32_t>(), bcount.as<int32_t>());
+      uint32_t *bo = bits.as<uint32_t>();
+      int32_t *bc = bcount.as<int32_t>();
+#define SB_CAND(KW, STEP, MINB) join_candidate_strided_kernel<KW, STEP, MINB><<<cb, JOIN_THREADS, 0, st>>>(k, n, sp, pmask_dev, kf, cand_mode, bo, bc)
+      const int v = config().join_cand;   // 1: 8 rows per lane and step; 2: 4 rows, 4 blocks / SM; 3: 8 rows, 3 blocks / SM
+      if (v == 2) { if (kw == 8) SB_CAND(8, 4, 4); else if (kw == 4) SB_CAND(4, 4, 4); else SB_CAND(0, 4, 4); }
+      else if (v == 3) { if (kw == 8) SB_CAND(8, 8, 3); else if (kw == 4) SB_CAND(4, 8, 3); else SB_CAND(0, 8, 3); }
+      else { if (kw == 8) SB_CAND(8, 8, 1); else if (kw == 4) SB_CAND(4, 8, 1); else SB_CAND(0, 8, 1); }
+#undef SB_CAND
     } else {
       join_candidate_kernel<<<cb, JOIN_THREADS, 0, st>>>(k, n, sp, pmask_dev, kf, cand_mode, fast_key, bits.as<uint16_t>(), bcount.as<int32_t>());
     }

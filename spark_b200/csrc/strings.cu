@@ -154,16 +154,22 @@ __global__ void str_maxlen_kernel(const int32_t *__restrict__ offs, int64_t n, i
   len = __reduce_max_sync(0xffffffffu, len);
   if ((threadIdx.x & 31) == 0 && len > 0) atomicMax(out, len);
 }
-// key of the element at sorted position i: its group rank so far, then bytes [4 round, 4 round + 4) big-endian (zero padded), or
-// its length in the final round
+// key of the element at sorted position i.  Round 0 (nobody is separated yet): the first 8 bytes big-endian (zero padded).
+// Later rounds: the group rank so far, then the next 4 bytes (bytes [8 + 4 (round - 1), + 4)); the final round: rank, then length.
 __device__ __forceinline__ uint64_t refine_key(const StrView &s, const uint32_t *__restrict__ seg_of, uint32_t e, int round, int by_length) {
   const int32_t o = s.offs[e], len = s.offs[e + 1] - o;
+  if (round == 0 && !by_length) {
+    uint64_t chunk = 0;
+#pragma unroll
+    for (int b = 0; b < 8; b++) chunk = (chunk << 8) | (b < len ? (uint64_t)s.bytes[o + b] : 0ull);
+    return chunk;
+  }
   uint32_t chunk = 0;
   if (by_length) chunk = (uint32_t)len;
   else {
 #pragma unroll
     for (int b = 0; b < 4; b++) {
-      const int at = round * 4 + b;
+      const int at = 8 + (round - 1) * 4 + b;
       chunk = (chunk << 8) | (at < len ? (uint32_t)s.bytes[o + at] : 0u);
     }
   }
@@ -214,7 +220,7 @@ static void rank_distinct_strings(const Column &c, uint32_t *rank_of, cudaStream
   int32_t ml = 0;
   SB_CUDA(cudaMemcpyAsync(&ml, maxlen.ptr, 4, cudaMemcpyDeviceToHost, st));
   SB_CUDA(cudaStreamSynchronize(st));
-  const int rounds = (ml + 3) / 4;
+  const int rounds = ml <= 8 ? 1 : 1 + (ml - 8 + 3) / 4;   // 8 bytes in the first round, 4 in every later one
   const StrView s = view_of(c);
   Scratch perm(d * 4 + 16, st), keys(d * 8 + 16, st), head(d * 4 + 16, st), before(d * 4 + 16, st), total(4, st);
   iota32_kernel<<<blocks_for(d), 256, 0, st>>>(perm.as<uint32_t>(), d);
@@ -264,6 +270,24 @@ void dictionary_encode(const Column &c, cudaStream_t st, Column &codes_out, Colu
   while (cap_max < 2 * n) cap_max <<= 1;
   std::unique_ptr<Scratch> slots;
   int32_t hctl[2] = {0, 0};
+  // Size the table from a sample instead of discovering an overflow pass by pass (each failed pass hashes every row): the distinct
+  // count of the first 2^20 rows says whether the column is low-cardinality (table = 16 x what the sample saw) or not (table for
+  // "every row its own value")
+  constexpr int64_t kSample = 1 << 20;
+  if (n > 4 * kSample) {
+    Scratch sslots(2 * kSample * 8, st);
+    SB_CUDA(cudaMemsetAsync(sslots.ptr, 0xff, (size_t)2 * kSample * 8, st));
+    SB_CUDA(cudaMemsetAsync(ctl.ptr, 0, 8, st));
+    dict_insert_kernel<<<blocks_for(kSample, STR_THREADS), STR_THREADS, 0, st>>>(in, kSample, sslots.as<uint64_t>(), (uint64_t)2 * kSample - 1, pos.as<int32_t>(),
+                                                                                ctl.as<int32_t>(), (int32_t)(2 * kSample));
+    SB_LAUNCH_CHECK();
+    SB_CUDA(cudaMemcpyAsync(hctl, ctl.ptr, 8, cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaStreamSynchronize(st));
+    const int64_t seen = hctl[1];
+    if (seen > kSample / 4) cap = cap_max;
+    else
+      while (cap < 16 * seen && cap < cap_max) cap <<= 1;
+  }
   for (;;) {
     slots.reset(new Scratch(cap * 8, st));
     SB_CUDA(cudaMemsetAsync(slots->ptr, 0xff, (size_t)cap * 8, st));
