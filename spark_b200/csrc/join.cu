@@ -60,6 +60,10 @@ struct sb_hash_table {
   // string key columns join as int32 codes in the BUILD side's dictionaries (csrc/strings.cu): has_dict[i] says key i is one
   bool has_dict[4] = {false, false, false, false};
   sb::Column dict[4];
+  // wide keys (> 64 bits): the slots hold a hash; the key columns of the build side stay reachable for the verification
+  int wide = 0;
+  sb_table *key_table = nullptr;      // retained table the build key columns live in (the build table or its encoded view)
+  int32_t key_table_col[4] = {0, 0, 0, 0};
   cudaStream_t st = nullptr;
 };
 
@@ -76,6 +80,8 @@ struct JoinKeys {
   int32_t type[JOIN_MAX_KEYS];
   int32_t bits[JOIN_MAX_KEYS];
   int32_t shift[JOIN_MAX_KEYS];
+  int32_t wide;   // the key columns need more than 64 bits: join_key yields a 64-bit HASH of them and matches are verified
+                  // column by column against the build row (the general UnsafeHashedRelation case of HashedRelation.scala:136)
 };
 
 __device__ __forceinline__ uint64_t join_mix(uint64_t x) {
@@ -83,27 +89,42 @@ __device__ __forceinline__ uint64_t join_mix(uint64_t x) {
   return x;
 }
 
-// packed key of a row; false when any key column is NULL (such a row never matches)
+// normalised value of key column i of a row (-0.0 == 0.0, one NaN, like grouping keys), zero-extended to its width
+__device__ __forceinline__ uint64_t join_key_part(const JoinKeys &k, int i, int64_t row) {
+  if (k.type[i] == SB_FLOAT64) {
+    double d = ((const double *)k.data[i])[row];
+    return d == 0.0 ? 0ull : (uint64_t)double_bits_canonical(d);
+  }
+  if (k.type[i] == SB_FLOAT32) {
+    float f = ((const float *)k.data[i])[row];
+    return f == 0.0f ? 0u : (uint32_t)float_bits_canonical(f);
+  }
+  uint64_t v = (uint64_t)load_i64(k.data[i], k.type[i], row);
+  if (k.bits[i] < 64) v &= (1ull << k.bits[i]) - 1;
+  return v;
+}
+// packed key of a row (wide keys: a hash of the parts); false when any key column is NULL (such a row never matches)
 __device__ __forceinline__ bool join_key(const JoinKeys &k, int64_t row, uint64_t &out) {
   uint64_t w = 0;
 #pragma unroll
   for (int i = 0; i < JOIN_MAX_KEYS; i++) {
     if (i >= k.n) break;
     if (!bit_valid(k.valid[i], row)) return false;
-    uint64_t v;
-    if (k.type[i] == SB_FLOAT64) {          // join keys are normalised like grouping keys (-0.0 == 0.0, one NaN)
-      double d = ((const double *)k.data[i])[row];
-      v = d == 0.0 ? 0ull : (uint64_t)double_bits_canonical(d);
-    } else if (k.type[i] == SB_FLOAT32) {
-      float f = ((const float *)k.data[i])[row];
-      v = f == 0.0f ? 0u : (uint32_t)float_bits_canonical(f);
-    } else {
-      v = (uint64_t)load_i64(k.data[i], k.type[i], row);
-      if (k.bits[i] < 64) v &= (1ull << k.bits[i]) - 1;
-    }
-    w |= v << k.shift[i];
+    const uint64_t v = join_key_part(k, i, row);
+    if (k.wide) w = join_mix(w ^ v) + (uint64_t)i;
+    else w |= v << k.shift[i];
   }
   out = w;
+  return true;
+}
+// wide keys: do the key columns of streamed row `row` equal those of build row `brow`?  (narrow keys: the packed words did)
+__device__ __forceinline__ bool join_key_verify(const JoinKeys &k, int64_t row, const JoinKeys &bk, int64_t brow) {
+  if (!k.wide) return true;
+#pragma unroll
+  for (int i = 0; i < JOIN_MAX_KEYS; i++) {
+    if (i >= k.n) break;
+    if (join_key_part(k, i, row) != join_key_part(bk, i, brow)) return false;
+  }
   return true;
 }
 
@@ -185,7 +206,7 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_count_kernel(JoinKeys k, in
                                                                   int join_type, int null_aware, int32_t *__restrict__ counts, uint32_t *__restrict__ first,
                                                                   int32_t *__restrict__ block_counts, uint8_t *__restrict__ matched,
                                                                   const uint8_t *__restrict__ row_mask, KeyFilter kf,
-                                                                  const int64_t *__restrict__ rows) {
+                                                                  const int64_t *__restrict__ rows, JoinKeys bk) {
   __shared__ int32_t wsum[JOIN_THREADS / 32];
   // `rows` (optional): the candidate list of join_candidate_kernel -- item i stands for streamed row rows[i]; counts / first are
   // indexed by item
@@ -212,7 +233,7 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_count_kernel(JoinKeys k, in
           uint32_t r;
           load_slot(&slots[h], sk, r);
           if (r == FREE_SLOT) break;
-          if (sk == key) {
+          if (sk == key && join_key_verify(k, row, bk, r)) {
             if (matches == 0) f = r;
             matches++;
             if (matched) matched[r] = 1;   // build rows that found a partner (build-side-preserving outer joins)
@@ -253,7 +274,7 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_fill_kernel(JoinKeys k, int
                                                                  int join_type, const int32_t *__restrict__ counts,
                                                                  const int64_t *__restrict__ block_offsets, const uint32_t *__restrict__ first,
                                                                  int64_t *__restrict__ out_probe, int64_t *__restrict__ out_build,
-                                                                 const int64_t *__restrict__ rows) {
+                                                                 const int64_t *__restrict__ rows, JoinKeys bk) {
   __shared__ int32_t wsum[JOIN_THREADS / 32];
   const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t row = rows && item < n ? rows[item] : item;
@@ -286,7 +307,7 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_fill_kernel(JoinKeys k, int
     uint32_t r;
     load_slot(&slots[h], sk, r);
     if (r == FREE_SLOT) break;
-    if (sk == key) {
+    if (sk == key && join_key_verify(k, row, bk, r)) {
       out_probe[o] = row;
       out_build[o] = r;
       o++;
@@ -641,8 +662,29 @@ static JoinKeys make_join_keys(const sb_table *t, const int32_t *key_cols, int32
     k.shift[i] = pos;
     pos += bits;
   }
-  if (pos > 64) fail(SB_ERR_UNSUPPORTED, "join keys need %d bits; at most 64 bits of fixed-width keys are packed (HashJoin.rewriteKeyExpr)", pos);
+  // <= 64 bits: the key columns are packed into one word (HashJoin.rewriteKeyExpr, HashJoin.scala:715-760 -> LongHashedRelation);
+  // more: the slots hold a 64-bit hash and every hash match is verified against the build row's key columns (UnsafeHashedRelation)
+  k.wide = pos > 64;
+  if (ht) SB_REQUIRE((ht->wide != 0) == (k.wide != 0), "join keys: the streamed side packs to %d bits, the relation was built %s", pos, ht->wide ? "wide" : "narrow");
   return k;
+}
+
+// key columns of the BUILD side for the verification of wide-key matches (narrow keys: unused, a zeroed struct)
+static JoinKeys build_side_keys(const sb_hash_table *ht) {
+  JoinKeys bk;
+  memset(&bk, 0, sizeof(bk));
+  if (!ht->wide) return bk;
+  bk.n = ht->nkeys;
+  bk.wide = 1;
+  for (int i = 0; i < ht->nkeys; i++) {
+    const Column &c = ht->key_table->cols[ht->key_table_col[i]];
+    bk.data[i] = c.d();
+    bk.valid[i] = c.v();
+    bk.type[i] = c.type;
+    bk.bits[i] = ht->key_bits[i];
+    bk.shift[i] = 0;
+  }
+  return bk;
 }
 
 // The table the streamed side's keys are read from: `probe` itself, or a view in which the string key columns hold their codes in
@@ -700,6 +742,12 @@ int sb_join_build_filtered(const sb_table *build, const int32_t *key_cols, int32
   sb_hash_table *ht = new sb_hash_table();
   ht->st = st;
   ht->nkeys = nkeys;
+  ht->wide = k.wide;
+  if (k.wide) {   // the key columns must outlive the build: keep the table they live in (the build table, or its encoded view)
+    ht->key_table = ev.view ? ev.view : const_cast<sb_table *>(build);
+    ht->key_table->refs.fetch_add(1);
+    for (int i = 0; i < nkeys; i++) ht->key_table_col[i] = key_cols[i];
+  }
   for (int i = 0; i < nkeys; i++) {
     if (const Column *d = ev.view ? ev.dictionary_of(key_cols[i]) : nullptr) {
       ht->has_dict[i] = true;
@@ -805,6 +853,7 @@ int sb_join_build_filtered(const sb_table *build, const int32_t *key_cols, int32
     if (ht->bloom) cudaFreeAsync(ht->bloom, st);
     if (ht->row_of) cudaFreeAsync(ht->row_of, st);
     if (ht->rank) cudaFreeAsync(ht->rank, st);
+    if (ht->key_table && ht->key_table->refs.fetch_sub(1) == 1) table_free(ht->key_table);
     for (int i = 0; i < 4; i++)
       if (ht->has_dict[i]) column_release(ht->dict[i]);
     delete ht;
@@ -826,6 +875,7 @@ int sb_hash_table_release(sb_hash_table *ht) {
     if (ht->bloom) cudaFreeAsync(ht->bloom, ht->st);
     if (ht->row_of) cudaFreeAsync(ht->row_of, ht->st);
     if (ht->rank) cudaFreeAsync(ht->rank, ht->st);
+    if (ht->key_table && ht->key_table->refs.fetch_sub(1) == 1) table_free(ht->key_table);
     if (ht->build && ht->build->refs.fetch_sub(1) == 1) table_free(ht->build);
     for (int i = 0; i < 4; i++)
       if (ht->has_dict[i]) column_release(ht->dict[i]);
@@ -1058,7 +1108,7 @@ int sb_join_probe_ex(const sb_hash_table *ht, const sb_table *probe, const int32
     KernelTimer kt("join_probe", st);
     join_count_kernel<<<nb, JOIN_THREADS, 0, st>>>(k, nitems, ht->slots, ht->cap, kt_type, null_aware, counts.as<int32_t>(), first.as<uint32_t>(),
                                                    block_counts.as<int32_t>(), build_rows_too ? matched.as<uint8_t>() : nullptr,
-                                                   use_cand ? nullptr : pmask_dev, kf, rows);
+                                                   use_cand ? nullptr : pmask_dev, kf, rows, build_side_keys(ht));
     SB_LAUNCH_CHECK();
   }
   if (join_type == SB_JOIN_EXISTENCE) {   // HashJoin.existenceJoin :301: the streamed row plus one boolean
@@ -1100,7 +1150,7 @@ int sb_join_probe_ex(const sb_hash_table *ht, const sb_table *probe, const int32
     KernelTimer kt("join_fill", st);
     join_fill_kernel<<<nb, JOIN_THREADS, 0, st>>>(k, nitems, ht->slots, ht->cap, kt_type, counts.as<int32_t>(),
                                                   offsets.as<int64_t>(), first.as<uint32_t>(), out_probe.as<int64_t>(),
-                                                  pairs ? out_build.as<int64_t>() : nullptr, rows);
+                                                  pairs ? out_build.as<int64_t>() : nullptr, rows, build_side_keys(ht));
     SB_LAUNCH_CHECK();
   }
   if (nun > 0) {
@@ -1181,12 +1231,12 @@ int sb_join_probe_condition(const sb_hash_table *ht, const sb_table *probe, cons
   Scratch pi(npairs * 8 + 16, st), bi(npairs * 8 + 16, st);
   if (n > 0) {
     join_count_kernel<<<nb, JOIN_THREADS, 0, st>>>(k, n, ht->slots, ht->cap, SB_JOIN_INNER, 0, counts.as<int32_t>(), first.as<uint32_t>(),
-                                                   block_counts.as<int32_t>(), nullptr, nullptr, key_filter_of(ht), nullptr);
+                                                   block_counts.as<int32_t>(), nullptr, nullptr, key_filter_of(ht), nullptr, build_side_keys(ht));
     SB_LAUNCH_CHECK();
     exclusive_scan_i32_to_i64(block_counts.as<int32_t>(), offsets.as<int64_t>(), nb, total.as<int64_t>(), st);
     if (npairs > 0) {
       join_fill_kernel<<<nb, JOIN_THREADS, 0, st>>>(k, n, ht->slots, ht->cap, SB_JOIN_INNER, counts.as<int32_t>(), offsets.as<int64_t>(),
-                                                    first.as<uint32_t>(), pi.as<int64_t>(), bi.as<int64_t>(), nullptr);
+                                                    first.as<uint32_t>(), pi.as<int64_t>(), bi.as<int64_t>(), nullptr, build_side_keys(ht));
       SB_LAUNCH_CHECK();
     }
   }

@@ -33,7 +33,8 @@ struct Config {
   int expr_interpret_only = 0;
   int regroup_ldst = 0;             // load/store multisplit instead of the copy-engine one
   int exchange_nccl = 0;            // NCCL send/recv data path instead of peer windows
-  int join_cand = 0;                // join candidate pass: 0 = 16 consecutive rows per thread (16-byte loads), 1 = lane-strided with batched loads
+  int join_cand = 2;                // join candidate pass: 0 = 16 consecutive rows per thread (16-byte loads); lane-strided with batched loads:
+                                    // 1 = 8 rows per lane and step, 2 = 4 rows at 4 blocks / SM (default: fastest measured), 3 = 8 rows at 3 blocks / SM
   int sort_variant = 4;             // onesweep tile geometry: 4 = 384 threads x 12 keys, the fastest measured (profiles/r02_sort_variants*.jsonl)
 };
 Config &config();

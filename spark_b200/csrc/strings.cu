@@ -376,7 +376,7 @@ Column dictionary_decode(const Column &cc, const Column &dc, cudaStream_t st) {
 }
 
 EncodedView::~EncodedView() {
-  if (view) table_free(view);
+  if (view && view->refs.fetch_sub(1) == 1) table_free(view);   // a relation with wide keys keeps the view alive
   for (auto &d : dictionaries) column_release(d);
 }
 

@@ -228,8 +228,9 @@ def q5_plan(customer, orders, lineitem, supplier, nation, region) -> SparkPlan:
     lo = ProjectExec(["l_suppkey", "c_nationkey", "l_extendedprice", "l_discount"],
                      BroadcastHashJoinExec(["l_orderkey"], ["o_orderkey"], "inner", "right",
                                            ProjectExec(["l_orderkey", "l_suppkey", "l_extendedprice", "l_discount"], lineitem), oc))
-    los = BroadcastHashJoinExec(["l_suppkey"], ["s_suppkey"], "inner", "right", lo, sup)
-    same_nation = FilterExec(col("c_nationkey").eq(col("s_nationkey")), los)     # c_nationkey = s_nationkey (second join key)
+    # q5.sql: l_suppkey = s_suppkey AND c_nationkey = s_nationkey -- both are equi-join keys of the supplier join
+    # (ExtractEquiJoinKeys, sql/catalyst/.../planning/patterns.scala); together they need more than 64 bits: the wide-key relation
+    same_nation = BroadcastHashJoinExec(["l_suppkey", "c_nationkey"], ["s_suppkey", "s_nationkey"], "inner", "right", lo, sup)
     aggs = [(Sum(col("l_extendedprice") * (Literal(1) - col("l_discount"))), "revenue")]
     agg = HashAggregateExec(["n_name"], aggs, HashAggregateExec(["n_name"], aggs, same_nation, mode="partial"), mode="final")
     return SortExec([("revenue", False, False)], agg)

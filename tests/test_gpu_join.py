@@ -213,3 +213,26 @@ def test_short_streamed_side_over_a_sorted_relation(gpu, stream, how):
     want = O.hash_join(probe, build, ["fk"], ["id"], "build_outer" if how == "right_outer" else how)   # the build side is the right side
     assert got.num_rows == want.num_rows
     assert_tables_equal(got, want, key_cols=list(want.column_names))
+
+
+@pytest.mark.parametrize("how", ["inner", "left_outer", "left_semi", "left_anti", "full_outer", "right_outer", "existence"])
+@pytest.mark.parametrize("npr", [60_000, (1 << 20) + 777])
+def test_join_keys_wider_than_64_bits(gpu, stream, how, npr):
+    """Three key columns of 64 + 32 + 64 bits: they cannot be packed into one word (HashJoin.rewriteKeyExpr gives up too), so the
+    relation keeps a hash per slot and every hash match is verified against the build row's key columns.  Keys agree on two columns
+    and differ on the third, duplicates and NULLs on both sides; the long streamed side goes through the candidate pass."""
+    rng = np.random.default_rng(31)
+    nb = 20_000
+    def side(n, nulls):
+        a = rng.integers(0, 300, n)
+        b = rng.integers(0, 40, n).astype(np.int32)
+        c = rng.integers(-5, 5, n) * (1 << 40)
+        return pa.array(a, type=pa.int64(), mask=rng.random(n) < nulls), pa.array(b, type=pa.int32()), pa.array(c, type=pa.int64(), mask=rng.random(n) < nulls)
+    ba, bb, bc = side(nb, 0.01)
+    pa_, pb, pc = side(npr, 0.01)
+    build = pa.table({"a2": ba, "b2": bb, "c2": bc, "payload": np.arange(nb, dtype=np.int64)})
+    probe = pa.table({"a": pa_, "b": pb, "c": pc, "row": np.arange(npr, dtype=np.int64)})
+    got = _plan_join(probe, build, ["a", "b", "c"], ["a2", "b2", "c2"], how, stream)
+    want = O.hash_join(probe, build, ["a", "b", "c"], ["a2", "b2", "c2"], "build_outer" if how == "right_outer" else how)
+    assert got.num_rows == want.num_rows
+    assert_tables_equal(got, want, key_cols=list(want.column_names))
