@@ -62,7 +62,7 @@ object GpuSupport {
                      r: SparkPlan): Boolean =
     outputOk(l) && outputOk(r) && leftKeys.length <= 4 &&
       (leftKeys ++ rightKeys).forall(k => k.isInstanceOf[AttributeReference] && keyOk(k.dataType)) &&
-      leftKeys.map(k => keyBits(k.dataType)).sum <= 64 && cond.forall(exprOk) &&                 // HashJoin.rewriteKeyExpr packing
+      cond.forall(exprOk) &&       // keys of <= 64 bits are packed (HashJoin.rewriteKeyExpr), wider ones hashed and verified inside the library
       (jt match { case _: InnerLike | LeftOuter | RightOuter | FullOuter | LeftSemi | LeftAnti | _: ExistenceJoin => true; case _ => false })
   def supports(j: BroadcastHashJoinExec): Boolean = joinOk(j.leftKeys, j.rightKeys, j.joinType, j.condition, j.left, j.right)
   def supports(j: ShuffledHashJoinExec): Boolean = joinOk(j.leftKeys, j.rightKeys, j.joinType, j.condition, j.left, j.right)
