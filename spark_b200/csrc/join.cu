@@ -406,6 +406,66 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_candidate_kernel(JoinKeys k
 // they overlap.  The verdicts of 32 rows are one ballot word = two of the 16-bit words candidate_rows_kernel reads (little endian),
 // so the bits buffer, the block counts and the second kernel are shared with the variant above.
 // KW: 0 = general keys (join_key per row), 4 / 8 = ONE NULL-free integer key column of that width.
+// join_key for R rows at once, column by column: the R loads of a column are issued together and its type switch is outside the
+// row loop (the per-row join_key puts every load behind a branch).  has[j]: no key column of row j is NULL.
+template <int R>
+__device__ __forceinline__ void join_key_rows(const JoinKeys &k, const int64_t (&rr)[R], uint64_t (&key)[R], bool (&has)[R]) {
+#pragma unroll
+  for (int j = 0; j < R; j++) {
+    key[j] = 0;
+    has[j] = true;
+  }
+#pragma unroll
+  for (int i = 0; i < JOIN_MAX_KEYS; i++) {   // unrolled: the per-column fields of the kernel parameter are indexed statically
+    if (i >= k.n) break;
+    if (k.valid[i]) {
+      uint8_t vb[R];
+#pragma unroll
+      for (int j = 0; j < R; j++) vb[j] = k.valid[i][rr[j] >> 3];
+#pragma unroll
+      for (int j = 0; j < R; j++) has[j] = has[j] && ((vb[j] >> (rr[j] & 7)) & 1);
+    }
+    uint64_t v[R];
+    switch (k.type[i]) {
+      case SB_FLOAT64:
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+          const double d = ((const double *)k.data[i])[rr[j]];
+          v[j] = d == 0.0 ? 0ull : (uint64_t)double_bits_canonical(d);
+        }
+        break;
+      case SB_FLOAT32:
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+          const float f = ((const float *)k.data[i])[rr[j]];
+          v[j] = f == 0.0f ? 0u : (uint32_t)float_bits_canonical(f);
+        }
+        break;
+      case SB_INT64: case SB_TIMESTAMP: case SB_DECIMAL64:
+#pragma unroll
+        for (int j = 0; j < R; j++) v[j] = ((const uint64_t *)k.data[i])[rr[j]];
+        break;
+      case SB_INT32: case SB_DATE32:
+#pragma unroll
+        for (int j = 0; j < R; j++) v[j] = ((const uint32_t *)k.data[i])[rr[j]];
+        break;
+      default: {
+        const uint64_t m = k.bits[i] < 64 ? (1ull << k.bits[i]) - 1 : ~0ull;
+#pragma unroll
+        for (int j = 0; j < R; j++) v[j] = (uint64_t)load_i64(k.data[i], k.type[i], rr[j]) & m;
+      }
+    }
+    if (k.wide) {
+#pragma unroll
+      for (int j = 0; j < R; j++) key[j] = join_mix(key[j] ^ v[j]) + (uint64_t)i;
+    } else {
+      const int sh = k.shift[i];
+#pragma unroll
+      for (int j = 0; j < R; j++) key[j] |= v[j] << sh;
+    }
+  }
+}
+
 template <int KW, bool FULL, int CAND_STEP>
 __device__ __forceinline__ uint32_t candidate_step(const JoinKeys &k, int64_t n, const SimplePred &sp, const uint8_t *__restrict__ row_mask,
                                                    const KeyFilter &kf, int mode, int64_t g0, int lane, uint32_t (&words)[CAND_STEP]) {
@@ -432,11 +492,7 @@ __device__ __forceinline__ uint32_t candidate_step(const JoinKeys &k, int64_t n,
 #pragma unroll
       for (int j = 0; j < CAND_STEP; j++) key[j] = (uint64_t)(FULL ? p[j * 32] : p[rr[j]]);
     } else {
-#pragma unroll
-      for (int j = 0; j < CAND_STEP; j++) {
-        key[j] = 0;
-        has[j] = join_key(k, rr[j], key[j]);
-      }
+      join_key_rows<CAND_STEP>(k, rr, key, has);
     }
   }
   if (sp.nterms > 0) simple_pred_rows<CAND_STEP, FULL>(sp, r0, 32, n, keep);
