@@ -120,3 +120,17 @@ def test_join_on_string_keys(gpu, stream, how):
     want = want.set_column(want.column_names.index("who"), "who", pa.array([who[r] for r in want.column("row").to_pylist()], type=pa.string()))
     assert got.num_rows == want.num_rows
     assert_tables_equal(got, want, key_cols=list(want.column_names))
+
+
+def test_inner_join_on_int_and_string_keys_reference_golden(gpu, stream):
+    """sql-tests/results/inner-join.sql.out: SELECT tb.* FROM ta INNER JOIN tb ON ta.a = tb.a AND ta.tag = tb.tag with
+    ta = {(1,'a'),(1,'b')}, tb = {(1,'a'),(1,'a'),(1,'b'),(1,'b')} -> the four rows of tb (an int key and a string key together)."""
+    from spark_b200.columnar import ColumnarBatch
+    from spark_b200.execution import BroadcastHashJoinExec, LocalTableScanExec
+    ta = pa.table({"a": pa.array([1, 1], type=pa.int32()), "tag": pa.array(["a", "b"], type=pa.string())})
+    tb = pa.table({"a2": pa.array([1, 1, 1, 1], type=pa.int32()), "tag2": pa.array(["a", "a", "b", "b"], type=pa.string())})
+    for build_side, build in (("right", tb), ("left", ta)):
+        got = BroadcastHashJoinExec(["a", "tag"], ["a2", "tag2"], "inner", build_side, LocalTableScanExec(ColumnarBatch.from_arrow(ta, stream)),
+                                    LocalTableScanExec(ColumnarBatch.from_arrow(tb, stream))).collect(stream)
+        rows = sorted(zip(got.column("a2").to_pylist(), got.column("tag2").to_pylist()))
+        assert rows == [(1, "a"), (1, "a"), (1, "b"), (1, "b")]
