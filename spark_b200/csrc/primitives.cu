@@ -105,6 +105,7 @@ void exclusive_scan_i32_to_i64(const int32_t *in, int64_t *out, int64_t n, int64
 
 // ------------------------------------------------------------------------------------ gather
 constexpr int GATHER_MAX_COLS = 12;
+static inline unsigned gather_grid(int64_t nout) { return (unsigned)((nout + 256 * 8 - 1) / (256 * 8)); }
 struct GatherArgs {
   int ncols;
   int width[GATHER_MAX_COLS];
@@ -114,34 +115,69 @@ struct GatherArgs {
   uint32_t *dst_valid[GATHER_MAX_COLS];   // null -> no validity output
 };
 
+// A thread owns GATHER_ITEMS rows (block-strided, so every index load and every store is a coalesced sweep) and, column by column, issues
+// the loads of all its rows before the first store: a row gather is latency-bound (one 32-byte sector per value), what matters is how many
+// sectors are in flight.  (Round 2: one row per thread with the column loop not unrolled kept one load in flight per thread --
+// Q5's 91 M-row join output spent 3.3 ms in gathers.)
+constexpr int GATHER_ITEMS = 8;
+template <typename T>
+__device__ __forceinline__ void gather_rows(const void *__restrict__ src, void *__restrict__ dst, const int64_t (&j)[GATHER_ITEMS], int64_t i0, int64_t nout) {
+  T v[GATHER_ITEMS];
+#pragma unroll
+  for (int k = 0; k < GATHER_ITEMS; k++) v[k] = j[k] >= 0 ? __ldg((const T *)src + j[k]) : T{};
+#pragma unroll
+  for (int k = 0; k < GATHER_ITEMS; k++)
+    if (i0 + k * 256 < nout) ((T *)dst)[i0 + k * 256] = v[k];
+}
 __global__ void __launch_bounds__(256) gather_fixed_kernel(GatherArgs a, const int64_t *__restrict__ idx, int64_t nout) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  bool in_range = i < nout;
-  int64_t j = in_range ? idx[i] : -1;
-  bool has = j >= 0;
+  const int64_t i0 = (int64_t)blockIdx.x * (256 * GATHER_ITEMS) + threadIdx.x;
+  int64_t j[GATHER_ITEMS];
+#pragma unroll
+  for (int k = 0; k < GATHER_ITEMS; k++) j[k] = i0 + k * 256 < nout ? idx[i0 + k * 256] : -1;
 #pragma unroll 1
   for (int c = 0; c < a.ncols; c++) {
-    if (has) {
-      switch (a.width[c]) {
-        case 1: ((uint8_t *)a.dst[c])[i] = ((const uint8_t *)a.src[c])[j]; break;
-        case 2: ((uint16_t *)a.dst[c])[i] = ((const uint16_t *)a.src[c])[j]; break;
-        case 4: ((uint32_t *)a.dst[c])[i] = ((const uint32_t *)a.src[c])[j]; break;
-        case 16: ((uint4 *)a.dst[c])[i] = ((const uint4 *)a.src[c])[j]; break;
-        default: ((uint64_t *)a.dst[c])[i] = ((const uint64_t *)a.src[c])[j]; break;
+    switch (a.width[c]) {
+      case 1: gather_rows<uint8_t>(a.src[c], a.dst[c], j, i0, nout); break;
+      case 2: gather_rows<uint16_t>(a.src[c], a.dst[c], j, i0, nout); break;
+      case 4: gather_rows<uint32_t>(a.src[c], a.dst[c], j, i0, nout); break;
+      case 16: {
+#pragma unroll
+        for (int h = 0; h < 2; h++) {   // two halves: 16-byte values would double the register footprint
+          uint4 v[GATHER_ITEMS / 2];
+#pragma unroll
+          for (int k = 0; k < GATHER_ITEMS / 2; k++) {
+            const int64_t jj = j[h * (GATHER_ITEMS / 2) + k];
+            v[k] = jj >= 0 ? __ldg((const uint4 *)a.src[c] + jj) : make_uint4(0, 0, 0, 0);
+          }
+#pragma unroll
+          for (int k = 0; k < GATHER_ITEMS / 2; k++) {
+            const int64_t i = i0 + (h * (GATHER_ITEMS / 2) + k) * 256;
+            if (i < nout) ((uint4 *)a.dst[c])[i] = v[k];
+          }
+        }
+        break;
       }
-    } else if (in_range) {
-      switch (a.width[c]) {
-        case 1: ((uint8_t *)a.dst[c])[i] = 0; break;
-        case 2: ((uint16_t *)a.dst[c])[i] = 0; break;
-        case 4: ((uint32_t *)a.dst[c])[i] = 0; break;
-        case 16: ((uint4 *)a.dst[c])[i] = make_uint4(0, 0, 0, 0); break;
-        default: ((uint64_t *)a.dst[c])[i] = 0; break;
-      }
+      default: gather_rows<uint64_t>(a.src[c], a.dst[c], j, i0, nout); break;
     }
     if (a.dst_valid[c]) {
-      bool v = has && bit_valid(a.src_valid[c], j);
-      uint32_t word = __ballot_sync(0xffffffffu, v);
-      if ((threadIdx.x & 31) == 0 && (i - (i & 31)) < nout) a.dst_valid[c][i >> 5] = word;
+      const uint8_t *sv = a.src_valid[c];
+      bool v[GATHER_ITEMS];
+      if (sv) {
+        uint8_t b[GATHER_ITEMS];
+#pragma unroll
+        for (int k = 0; k < GATHER_ITEMS; k++) b[k] = j[k] >= 0 ? __ldg(sv + (j[k] >> 3)) : 0;
+#pragma unroll
+        for (int k = 0; k < GATHER_ITEMS; k++) v[k] = j[k] >= 0 && ((b[k] >> (j[k] & 7)) & 1);
+      } else {
+#pragma unroll
+        for (int k = 0; k < GATHER_ITEMS; k++) v[k] = j[k] >= 0;
+      }
+#pragma unroll
+      for (int k = 0; k < GATHER_ITEMS; k++) {
+        const uint32_t word = __ballot_sync(0xffffffffu, v[k]);
+        const int64_t i = i0 + k * 256;
+        if ((threadIdx.x & 31) == 0 && i < nout) a.dst_valid[c][i >> 5] = word;
+      }
     }
   }
 }
@@ -209,7 +245,7 @@ static Column gather_string(const Column &c, const int64_t *idx, int64_t nout, b
     if (nout > 0) {
       // src[j] read of 1 byte must be in-bounds: use the offsets buffer (>= 4*(n+1) bytes) instead
       a.src[0] = c.o();
-      gather_fixed_kernel<<<(unsigned)((nout + 255) / 256), 256, 0, st>>>(a, idx, nout);
+      gather_fixed_kernel<<<gather_grid(nout), 256, 0, st>>>(a, idx, nout);
       SB_LAUNCH_CHECK();
     }
   }
@@ -227,12 +263,12 @@ Column gather_column(const Column &c, const int64_t *idx, int64_t nout, bool neg
   a.dst[0] = r.data->ptr;
   a.src_valid[0] = c.v();
   a.dst_valid[0] = r.validity ? (uint32_t *)r.validity->ptr : nullptr;
-  gather_fixed_kernel<<<(unsigned)((nout + 255) / 256), 256, 0, st>>>(a, idx, nout);
+  gather_fixed_kernel<<<gather_grid(nout), 256, 0, st>>>(a, idx, nout);
   SB_LAUNCH_CHECK();
   return r;
 }
 
-sb_table *gather_table(const sb_table *in, const int64_t *idx, int64_t nout, bool neg, cudaStream_t st) {
+sb_table *gather_table(const sb_table *in, const int64_t *idx, int64_t nout, bool neg, cudaStream_t st, int skip_col) {
   KernelTimer kt("gather", st);
   sb_table *t = table_new(nout);
   try {
@@ -241,13 +277,14 @@ sb_table *gather_table(const sb_table *in, const int64_t *idx, int64_t nout, boo
     a.ncols = 0;
     auto flush = [&]() {
       if (a.ncols && nout > 0) {
-        gather_fixed_kernel<<<(unsigned)((nout + 255) / 256), 256, 0, st>>>(a, idx, nout);
+        gather_fixed_kernel<<<gather_grid(nout), 256, 0, st>>>(a, idx, nout);
         SB_LAUNCH_CHECK();
       }
       a.ncols = 0;
     };
     for (size_t i = 0; i < in->cols.size(); i++) {
       const Column &c = in->cols[i];
+      if ((int)i == skip_col) continue;
       if (c.type == SB_STRING) {
         t->cols[i] = gather_string(c, idx, nout, neg, st);
         continue;

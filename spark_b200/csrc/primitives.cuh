@@ -13,8 +13,9 @@ void exclusive_scan_i32_to_i64(const int32_t *in, int64_t *out, int64_t n, int64
 
 // Gather rows of every column of `in` at positions idx[0..nout) (idx < 0 -> NULL row, used for
 // outer-join padding).  Result columns carry validity when the source has it or idx may be negative.
+// skip_col >= 0: that column of the result is left empty for the caller to fill (SortExec rebuilds its key column from the sorted keys)
 sb_table *gather_table(const sb_table *in, const int64_t *idx_dev, int64_t nout, bool idx_may_be_negative,
-                       cudaStream_t st);
+                       cudaStream_t st, int skip_col = -1);
 Column gather_column(const Column &c, const int64_t *idx_dev, int64_t nout, bool idx_may_be_negative, cudaStream_t st);
 
 // indices of rows whose mask byte is non-zero, in row order; returns count (synchronizes the stream)

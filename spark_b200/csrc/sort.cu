@@ -134,6 +134,25 @@ __global__ void u32_to_i64_kernel(const uint32_t *__restrict__ in, int64_t n, in
 
 static inline unsigned nblk(int64_t n) { return (unsigned)((n + 255) / 256); }
 
+// The order-preserving key of an integer-typed column is a bijection of the value (sign flip, complement for DESC), so the sorted
+// column IS the sorted keys mapped back -- a sequential pass instead of a random gather through the permutation.
+static bool key_is_bijective(int32_t type) {
+  return type == SB_INT8 || type == SB_INT16 || type == SB_INT32 || type == SB_INT64 || type == SB_DATE32 || type == SB_TIMESTAMP || type == SB_DECIMAL64;
+}
+__global__ void __launch_bounds__(256) unkey_kernel(const uint64_t *__restrict__ keys, int64_t n, int desc, int width, void *__restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t k = keys[i];
+  if (desc) k = ~k;
+  k ^= 0x8000000000000000ull;
+  switch (width) {
+    case 1: ((uint8_t *)out)[i] = (uint8_t)k; break;
+    case 2: ((uint16_t *)out)[i] = (uint16_t)k; break;
+    case 4: ((uint32_t *)out)[i] = (uint32_t)k; break;
+    default: ((uint64_t *)out)[i] = k; break;
+  }
+}
+
 // RangePartitioner.getPartition (core/.../Partitioner.scala:241-260): partition = #bounds the key is strictly greater than.
 // Keys and bounds are compared as (null rank, order-preserving key): NULLs sort before everything when nulls_first, after
 // everything otherwise, exactly as the sort itself orders them.  Bounds are few (numPartitions - 1): binary search in shared memory.
@@ -196,7 +215,7 @@ __global__ void __launch_bounds__(SORT_THREADS) select_mask_kernel(const void *d
 static bool radix_eligible(int32_t type) { return type != SB_STRING; }
 
 // writes the sorted permutation (uint32 row ids) into perm (n entries)
-void sort_permutation_impl(const sb_table *in, const sb_sort_order *orders, int32_t norders, uint32_t *perm, cudaStream_t st) {
+void sort_permutation_impl(const sb_table *in, const sb_sort_order *orders, int32_t norders, uint32_t *perm, cudaStream_t st, SortedKeys *sk) {
   const int64_t n = in->nrows;
   SB_REQUIRE(n < (1ll << 32), "tables of 2^32 rows or more must be sorted in chunks");
   SB_REQUIRE(norders >= 1 && orders, "sort needs at least one order");
@@ -219,6 +238,18 @@ void sort_permutation_impl(const sb_table *in, const sb_sort_order *orders, int3
     // ---- the reference's radix path --------------------------------------------------------------
     const Column &c = in->cols[orders[0].col];
     const bool desc = !orders[0].ascending, nulls_first = orders[0].nulls_first != 0;
+    if (!c.validity && sk && key_is_bijective(c.type)) {   // the caller wants the sorted keys back (sb_sort: the key column of the result)
+      sk->a.reset(new Scratch(n * 8 + 16, st));
+      sk->b.reset(new Scratch(n * 8 + 16, st));
+      iota_u32_kernel<<<nblk(n), 256, 0, st>>>(perm, n);
+      SB_LAUNCH_CHECK();
+      make_keys_kernel<<<nblk(n), SORT_THREADS, 0, st>>>(c.d(), nullptr, c.type, desc, nullptr, n, sk->a->as<uint64_t>(), nullptr);
+      SB_LAUNCH_CHECK();
+      radix_sort_pairs(sk->a->as<uint64_t>(), perm, n, st, sk->b->as<uint64_t>(), &sk->sorted);
+      sk->col = orders[0].col;
+      sk->desc = desc;
+      return;
+    }
     Scratch keys(n * 8 + 16, st);
     if (!c.validity) {
       iota_u32_kernel<<<nblk(n), 256, 0, st>>>(perm, n);
@@ -334,12 +365,28 @@ int sb_sort(const sb_table *in, const sb_sort_order *orders, int32_t norders, sb
   cudaStream_t st = stream_of(s);
   int64_t n = in->nrows;
   Scratch perm(n * 4 + 16, st), perm64(n * 8 + 16, st);
-  sort_permutation_impl(in, orders, norders, perm.as<uint32_t>(), st);
-  if (n > 0) {
+  SortedKeys sk;
+  sort_permutation_impl(in, orders, norders, perm.as<uint32_t>(), st, &sk);
+  if (n > 0 && !(sk.sorted && in->cols.size() == 1)) {
     u32_to_i64_kernel<<<nblk(n), 256, 0, st>>>(perm.as<uint32_t>(), n, perm64.as<int64_t>());
     SB_LAUNCH_CHECK();
   }
-  *out = gather_table(in, perm64.as<int64_t>(), n, false, st);   // stream-ordered: no host synchronisation needed
+  sb_table *t = gather_table(in, perm64.as<int64_t>(), n, false, st, sk.sorted ? sk.col : -1);   // stream-ordered: no host synchronisation needed
+  if (sk.sorted) {
+    try {
+      KernelTimer kt("gather", st);
+      const Column &c = in->cols[sk.col];
+      Column r = column_alloc(c.type, c.scale, n, false, st);
+      r.null_count = 0;
+      unkey_kernel<<<nblk(n), 256, 0, st>>>(sk.sorted, n, sk.desc ? 1 : 0, type_width(c.type), r.data->ptr);
+      SB_LAUNCH_CHECK();
+      t->cols[sk.col] = r;
+    } catch (...) {
+      table_free(t);
+      throw;
+    }
+  }
+  *out = t;
   SB_API_END
 }
 

@@ -170,3 +170,35 @@ def test_range_partition_and_global_sort(gpu, stream, kind, asc, nulls_first):
     same = lambda a, b: (a is None and b is None) or (a is not None and b is not None and (a == b or (a != a and b != b)))
     assert len(gk) == len(rk) and all(same(a, b) for a, b in zip(gk, rk))
     assert sorted(glob.column("row").to_pylist()) == list(range(n))
+
+
+# The key column of a single integer-typed, NULL-free order is rebuilt from the sorted 64-bit keys (csrc/sort.cu: unkey_kernel), not
+# gathered: every column of the result must still equal the oracle's.
+@pytest.mark.parametrize("kind", ["int64", "int64_small", "int32", "int8", "date32"])
+@pytest.mark.parametrize("asc", [True, False])
+def test_sorted_key_column_rebuilt_from_keys(gpu, stream, kind, asc):
+    n = 70001
+    rng = np.random.default_rng(hash((kind, asc)) % 2 ** 32)
+    t = pa.table({"p": rng.random(n), "k": _col(kind, n, rng, 0.0), "row": np.arange(n, dtype=np.int64)})
+    assert_tables_equal(_sort(t, [("k", asc, True)], stream), O.sort(t, [("k", asc, True)]), ordered=True)
+    one = pa.table({"k": _col(kind, n, rng, 0.0)})
+    assert_tables_equal(_sort(one, [("k", asc, False)], stream), O.sort(one, [("k", asc, False)]), ordered=True)
+
+
+# every onesweep form / tile geometry (sb_config_set("sort_variant")) against the oracle: ragged sizes, full-range keys (8 passes) and
+# heavily duplicated keys (tie order across tiles and warps)
+@pytest.mark.parametrize("variant", [0, 4, 6, 7, 8, 9, 10, 11, 12, 13])
+def test_onesweep_variants_exact_order(gpu, stream, variant):
+    from spark_b200 import _capi as capi
+    prev = capi.config_get("sort_variant")
+    capi.config_set("sort_variant", variant)
+    try:
+        for n, hi in ((2049, 3), (4608 * 3 + 5, 2 ** 62), (300007, 700), (300007, 2 ** 62)):
+            rng = np.random.default_rng(n + variant)
+            t = pa.table({"k": rng.integers(-hi, hi, n), "row": np.arange(n, dtype=np.int64)})
+            got = _sort(t, [("k", True, True)], stream)
+            want = O.sort(t, [("k", True, True)])
+            assert got.column("row").to_pylist() == want.column("row").to_pylist(), (variant, n, hi)
+            assert got.column("k").to_pylist() == want.column("k").to_pylist(), (variant, n, hi)
+    finally:
+        capi.config_set("sort_variant", prev)
