@@ -445,6 +445,15 @@ typedef struct sb_join_options {
   int32_t n_probe_out;
   int32_t n_build_out;
   const int32_t *build_out_cols;   /* build columns that reach the output (NULL: all) */
+  /* Runtime filters -- the reference's InjectRuntimeFilter (sql/catalyst/.../optimizer/InjectRuntimeFilter.scala:47-100) plans a
+   * BloomFilterMightContain FilterExec on the application side of a join, built from the creation side's join key.  Here the creation
+   * side is a single-key relation (sb_join_build*) and its prefilter (exact bitmap or Bloom) is tested on streamed column
+   * runtime_filter_cols[i] inside the join's candidate pass: streamed rows whose value cannot be a key of the relation (or is NULL)
+   * are not part of the input.  INNER / LEFT_SEMI only; like the reference's filter it may let non-members through, so it is only
+   * planned where a later inner join on that column drops them anyway. */
+  int32_t n_runtime_filters;
+  const int32_t *runtime_filter_cols;
+  const sb_hash_table *const *runtime_filter_relations;
 } sb_join_options;
 int sb_join_probe_ex(const sb_hash_table *ht, const sb_table *probe, const int32_t *key_cols, int32_t nkeys, int32_t join_type,
                      const sb_join_options *options, sb_stream *s, sb_table **out);

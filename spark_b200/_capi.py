@@ -72,7 +72,8 @@ class sb_agg_plan(C.Structure):
 
 class sb_join_options(C.Structure):
     _fields_ = [("probe_filter", C.POINTER(sb_expr)), ("condition", C.POINTER(sb_expr)), ("probe_out_cols", C.POINTER(C.c_int32)),
-                ("n_probe_out", C.c_int32), ("n_build_out", C.c_int32), ("build_out_cols", C.POINTER(C.c_int32))]
+                ("n_probe_out", C.c_int32), ("n_build_out", C.c_int32), ("build_out_cols", C.POINTER(C.c_int32)),
+                ("n_runtime_filters", C.c_int32), ("runtime_filter_cols", C.POINTER(C.c_int32)), ("runtime_filter_relations", C.POINTER(C.c_void_p))]
 
 
 class sb_sort_order(C.Structure):

@@ -160,6 +160,18 @@ __device__ __forceinline__ bool filter_test(const KeyFilter &f, uint64_t key) {
   return (__ldg(&f.words[bloom_word(hh, f.mask)]) & bb) == bb;
 }
 
+// Runtime filters (the reference's InjectRuntimeFilter, sql/catalyst/.../optimizer/InjectRuntimeFilter.scala:47-100: a
+// BloomFilterMightContain FilterExec on the application side of a join, built from the creation side's join keys): here the filter
+// IS the prefilter of a single-key relation built on the creation side (exact bitmap or Bloom), tested inside the candidate pass on
+// one more streamed column -- loaded only for the rows the join's own prefilter lets through.
+constexpr int MAX_RUNTIME_FILTERS = 2;
+struct RuntimeFilters {
+  int n;
+  const void *col[MAX_RUNTIME_FILTERS];   // streamed column, NULL-free, 4 or 8 bytes wide (packed like a single join key of its type)
+  int width[MAX_RUNTIME_FILTERS];
+  KeyFilter f[MAX_RUNTIME_FILTERS];
+};
+
 typedef sb_hash_table::Slot JoinSlot;
 __device__ __forceinline__ void load_slot(const JoinSlot *p, uint64_t &key, uint32_t &row) {
   const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(p);
@@ -466,9 +478,10 @@ __device__ __forceinline__ void join_key_rows(const JoinKeys &k, const int64_t (
   }
 }
 
-template <int KW, bool FULL, int CAND_STEP>
+template <int KW, bool FULL, int CAND_STEP, bool RF = false>
 __device__ __forceinline__ uint32_t candidate_step(const JoinKeys &k, int64_t n, const SimplePred &sp, const uint8_t *__restrict__ row_mask,
-                                                   const KeyFilter &kf, int mode, int64_t g0, int lane, uint32_t (&words)[CAND_STEP]) {
+                                                   const KeyFilter &kf, int mode, int64_t g0, int lane, uint32_t (&words)[CAND_STEP],
+                                                   const RuntimeFilters *rf = nullptr) {
   // rows of this lane: g0 + lane + 32 j.  FULL: the whole step lies below n, so nothing is clamped and the column pointers are
   // advanced once (the loads take constant offsets)
   const int64_t r0 = g0 + lane;
@@ -529,6 +542,44 @@ __device__ __forceinline__ uint32_t candidate_step(const JoinKeys &k, int64_t n,
 #pragma unroll
       for (int j = 0; j < CAND_STEP; j++) present[j] = present[j] && (w[j] & bb[j]) == bb[j];
     }
+    if (RF) {   // runtime filters (CAND_PRESENT only): one more column, read where the row is still alive
+#pragma unroll 1
+      for (int f = 0; f < rf->n; f++) {
+        const KeyFilter &g = rf->f[f];
+        uint64_t v[CAND_STEP];
+        if (rf->width[f] == 8) {
+          const uint64_t *p = (const uint64_t *)rf->col[f];
+#pragma unroll
+          for (int j = 0; j < CAND_STEP; j++) v[j] = present[j] ? __ldg(p + rr[j]) : 0ull;
+        } else {
+          const uint32_t *p = (const uint32_t *)rf->col[f];
+#pragma unroll
+          for (int j = 0; j < CAND_STEP; j++) v[j] = present[j] ? (uint64_t)__ldg(p + rr[j]) : 0ull;
+        }
+        if (g.exact) {
+          uint32_t w[CAND_STEP], d[CAND_STEP];
+#pragma unroll
+          for (int j = 0; j < CAND_STEP; j++) {
+            const uint64_t d64 = v[j] - g.fmin;
+            present[j] = present[j] && d64 < g.frange;
+            d[j] = (uint32_t)d64;
+            w[j] = present[j] ? __ldg(&g.words[d[j] >> 5]) : 0u;
+          }
+#pragma unroll
+          for (int j = 0; j < CAND_STEP; j++) present[j] = present[j] && ((w[j] >> (d[j] & 31)) & 1u);
+        } else {
+          uint32_t w[CAND_STEP], bb[CAND_STEP];
+#pragma unroll
+          for (int j = 0; j < CAND_STEP; j++) {
+            const uint64_t hh = join_mix(v[j]);
+            bb[j] = bloom_bits(hh);
+            w[j] = present[j] ? __ldg(&g.words[bloom_word(hh, g.mask)]) : 0u;
+          }
+#pragma unroll
+          for (int j = 0; j < CAND_STEP; j++) present[j] = present[j] && (w[j] & bb[j]) == bb[j];
+        }
+      }
+    }
     if (mode == CAND_PRESENT) {
 #pragma unroll
       for (int j = 0; j < CAND_STEP; j++) keep[j] = present[j];          // present implies keep
@@ -549,15 +600,17 @@ __device__ __forceinline__ uint32_t candidate_step(const JoinKeys &k, int64_t n,
   return count;
 }
 // the ragged last step of the input: kept out of line so that its clamping code costs the full steps no registers
-template <int KW, int CAND_STEP>
+template <int KW, int CAND_STEP, bool RF>
 __device__ __noinline__ uint32_t candidate_step_tail(const JoinKeys &k, int64_t n, const SimplePred &sp, const uint8_t *__restrict__ row_mask,
-                                                     const KeyFilter &kf, int mode, int64_t g0, int lane, uint32_t (&words)[CAND_STEP]) {
-  return candidate_step<KW, false, CAND_STEP>(k, n, sp, row_mask, kf, mode, g0, lane, words);
+                                                     const KeyFilter &kf, int mode, int64_t g0, int lane, uint32_t (&words)[CAND_STEP],
+                                                     const RuntimeFilters *rf) {
+  return candidate_step<KW, false, CAND_STEP, RF>(k, n, sp, row_mask, kf, mode, g0, lane, words, rf);
 }
-template <int KW, int CAND_STEP, int MINB>
+template <int KW, int CAND_STEP, int MINB, bool RF = false>
 __global__ void __launch_bounds__(JOIN_THREADS, MINB) join_candidate_strided_kernel(JoinKeys k, int64_t n, const __grid_constant__ SimplePred sp,
                                                                               const uint8_t *__restrict__ row_mask, KeyFilter kf, int mode,
-                                                                              uint32_t *__restrict__ bits_out, int32_t *__restrict__ block_counts) {
+                                                                              uint32_t *__restrict__ bits_out, int32_t *__restrict__ block_counts,
+                                                                              const __grid_constant__ RuntimeFilters rf) {
   __shared__ int32_t wsum[JOIN_THREADS / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int WARP_ROWS = CAND_TILE / (JOIN_THREADS / 32);
@@ -568,8 +621,8 @@ __global__ void __launch_bounds__(JOIN_THREADS, MINB) join_candidate_strided_ker
     const int64_t g0 = wbase + (int64_t)c * 32;
     if (g0 >= n) break;
     uint32_t words[CAND_STEP];
-    const uint32_t cnt = g0 + CAND_STEP * 32 <= n ? candidate_step<KW, true, CAND_STEP>(k, n, sp, row_mask, kf, mode, g0, lane, words)
-                                                   : candidate_step_tail<KW, CAND_STEP>(k, n, sp, row_mask, kf, mode, g0, lane, words);
+    const uint32_t cnt = g0 + CAND_STEP * 32 <= n ? candidate_step<KW, true, CAND_STEP, RF>(k, n, sp, row_mask, kf, mode, g0, lane, words, &rf)
+                                                   : candidate_step_tail<KW, CAND_STEP, RF>(k, n, sp, row_mask, kf, mode, g0, lane, words, &rf);
     mine += cnt;   // the same on every lane
 #pragma unroll
     for (int j = 0; j < CAND_STEP; j++)
@@ -682,6 +735,15 @@ __global__ void __launch_bounds__(JOIN_THREADS) build_stats_kernel(JoinKeys k, i
 __global__ void word_popc_kernel(const uint32_t *__restrict__ words, int64_t n, int32_t *__restrict__ out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = __popc(words[i]);
+}
+
+// runtime filter outside the candidate pass (short streamed sides, nullable or odd-typed columns): a byte mask like a fused FilterExec's
+__global__ void __launch_bounds__(JOIN_THREADS) runtime_filter_mask_kernel(JoinKeys col, int64_t n, KeyFilter f, uint8_t *__restrict__ mask, int have_mask) {
+  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n) return;
+  if (have_mask && !mask[row]) return;
+  uint64_t key;
+  mask[row] = join_key(col, row, key) && filter_test(f, key) ? 1 : 0;   // might_contain(NULL) is NULL: the row is dropped
 }
 
 static KeyFilter key_filter_of(const sb_hash_table *ht) {
@@ -982,8 +1044,8 @@ int sb_join_probe(const sb_hash_table *ht, const sb_table *probe, const int32_t 
 int sb_join_probe_ex(const sb_hash_table *ht, const sb_table *probe, const int32_t *key_cols, int32_t nkeys, int32_t join_type,
                      const sb_join_options *opt, sb_stream *s, sb_table **out) {
   if (opt && opt->condition) {
-    if (opt->probe_filter || opt->probe_out_cols || opt->build_out_cols) {
-      sb::set_last_error("sb_join_probe_ex: a residual condition cannot be combined with a fused filter / projection yet");
+    if (opt->probe_filter || opt->probe_out_cols || opt->build_out_cols || opt->n_runtime_filters > 0) {
+      sb::set_last_error("sb_join_probe_ex: a residual condition cannot be combined with a fused filter / projection / runtime filter yet");
       return SB_ERR_UNSUPPORTED;
     }
     return sb_join_probe_condition(ht, probe, key_cols, nkeys, join_type, opt->condition, s, out);
@@ -1055,9 +1117,48 @@ int sb_join_probe_ex(const sb_hash_table *ht, const sb_table *probe, const int32
     pred_in_pass = use_cand && !config().expr_interpret_only && match_simple_predicate(probe, *probe_filter, sp);
     if (!pred_in_pass) sp.nterms = 0;
   }
-  Scratch pmask(probe_filter && !pred_in_pass ? n + 16 : 0, st);
-  if (probe_filter && !pred_in_pass && n > 0) eval_predicate(probe, *probe_filter, pmask.as<uint8_t>(), st);
-  const uint8_t *pmask_dev = probe_filter && !pred_in_pass ? pmask.as<uint8_t>() : nullptr;
+  // runtime filters (InjectRuntimeFilter): inside the candidate pass when they can be, else folded into the byte mask
+  RuntimeFilters rfs;
+  rfs.n = 0;
+  std::vector<JoinKeys> rf_keys;
+  std::vector<KeyFilter> rf_filters;
+  if (opt && opt->n_runtime_filters > 0) {
+    SB_REQUIRE(opt->runtime_filter_cols && opt->runtime_filter_relations, "runtime filters: null argument");
+    if (!(join_type == SB_JOIN_INNER || join_type == SB_JOIN_LEFT_SEMI))
+      fail(SB_ERR_UNSUPPORTED, "runtime filters drop streamed rows: only inner and left semi joins take them");
+    for (int i = 0; i < opt->n_runtime_filters; i++) {
+      const sb_hash_table *r = opt->runtime_filter_relations[i];
+      SB_REQUIRE(r, "runtime filter %d: null relation", i);
+      if (r->nkeys != 1 || r->wide || r->has_dict[0]) fail(SB_ERR_UNSUPPORTED, "runtime filter %d: the creation side must be a relation on one fixed-width key", i);
+      if (!r->bloom) continue;   // a relation without a prefilter: the filter is an optimisation, leaving it out changes nothing
+      const int32_t c = opt->runtime_filter_cols[i];
+      rf_keys.push_back(make_join_keys(probe, &c, 1, r));
+      rf_filters.push_back(key_filter_of(r));
+    }
+  }
+  bool rf_in_pass = !rf_keys.empty() && use_cand && config().join_cand == 2 && cand_mode == CAND_PRESENT && (int)rf_keys.size() <= MAX_RUNTIME_FILTERS;
+  for (auto &jk : rf_keys) {
+    const int32_t t = jk.type[0];
+    if (jk.valid[0] || !(t == SB_INT32 || t == SB_DATE32 || t == SB_INT64 || t == SB_TIMESTAMP || t == SB_DECIMAL64)) rf_in_pass = false;
+  }
+  if (rf_in_pass)
+    for (size_t i = 0; i < rf_keys.size(); i++) {
+      rfs.col[rfs.n] = rf_keys[i].data[0];
+      rfs.width[rfs.n] = rf_keys[i].bits[0] / 8;
+      rfs.f[rfs.n] = rf_filters[i];
+      rfs.n++;
+    }
+  const bool rf_mask = !rf_keys.empty() && !rf_in_pass;
+  const bool pred_mask = probe_filter && !pred_in_pass;
+  Scratch pmask(pred_mask || rf_mask ? n + 16 : 0, st);
+  if (pred_mask && n > 0) eval_predicate(probe, *probe_filter, pmask.as<uint8_t>(), st);
+  if (rf_mask && n > 0)
+    for (size_t i = 0; i < rf_keys.size(); i++) {
+      runtime_filter_mask_kernel<<<(unsigned)((n + JOIN_THREADS - 1) / JOIN_THREADS), JOIN_THREADS, 0, st>>>(rf_keys[i], n, rf_filters[i], pmask.as<uint8_t>(),
+                                                                                                     pred_mask || i > 0 ? 1 : 0);
+      SB_LAUNCH_CHECK();
+    }
+  const uint8_t *pmask_dev = pred_mask || rf_mask ? pmask.as<uint8_t>() : nullptr;
   int64_t nitems = n;
   std::unique_ptr<Scratch> cand_rows;
   if (use_cand) {
@@ -1073,12 +1174,15 @@ int sb_join_probe_ex(const sb_hash_table *ht, const sb_table *probe, const int32
       const int kw = !int_key ? 0 : (k.bits[0] == 64 ? 8 : k.bits[0] == 32 ? 4 : 0);
       uint32_t *bo = bits.as<uint32_t>();
       int32_t *bc = bcount.as<int32_t>();
-#define SB_CAND(KW, STEP, MINB) join_candidate_strided_kernel<KW, STEP, MINB><<<cb, JOIN_THREADS, 0, st>>>(k, n, sp, pmask_dev, kf, cand_mode, bo, bc)
+#define SB_CAND(KW, STEP, MINB) join_candidate_strided_kernel<KW, STEP, MINB><<<cb, JOIN_THREADS, 0, st>>>(k, n, sp, pmask_dev, kf, cand_mode, bo, bc, rfs)
+#define SB_CAND_RF(KW) join_candidate_strided_kernel<KW, 4, 3, true><<<cb, JOIN_THREADS, 0, st>>>(k, n, sp, pmask_dev, kf, cand_mode, bo, bc, rfs)
       const int v = config().join_cand;   // 1: 8 rows per lane and step; 2: 4 rows, 4 blocks / SM; 3: 8 rows, 3 blocks / SM
-      if (v == 2) { if (kw == 8) SB_CAND(8, 4, 4); else if (kw == 4) SB_CAND(4, 4, 4); else SB_CAND(0, 4, 4); }
+      if (rfs.n > 0) { if (kw == 8) SB_CAND_RF(8); else if (kw == 4) SB_CAND_RF(4); else SB_CAND_RF(0); }
+      else if (v == 2) { if (kw == 8) SB_CAND(8, 4, 4); else if (kw == 4) SB_CAND(4, 4, 4); else SB_CAND(0, 4, 4); }
       else if (v == 3) { if (kw == 8) SB_CAND(8, 8, 3); else if (kw == 4) SB_CAND(4, 8, 3); else SB_CAND(0, 8, 3); }
       else { if (kw == 8) SB_CAND(8, 8, 1); else if (kw == 4) SB_CAND(4, 8, 1); else SB_CAND(0, 8, 1); }
 #undef SB_CAND
+#undef SB_CAND_RF
     } else {
       join_candidate_kernel<<<cb, JOIN_THREADS, 0, st>>>(k, n, sp, pmask_dev, kf, cand_mode, fast_key, bits.as<uint16_t>(), bcount.as<int32_t>());
     }

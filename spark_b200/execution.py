@@ -569,13 +569,43 @@ _STREAM_LEFT = {"inner": "inner", "left_outer": "left_outer", "left_semi": "left
 _STREAM_RIGHT = {"inner": "inner", "right_outer": "left_outer", "left_outer": "build_outer", "full_outer": "full_outer"}
 
 
+class ReusedExchangeExec(SparkPlan):
+    """ReusedExchangeExec (SQLX/exchange/Exchange.scala:50-80): one subplan, several parents.  The child runs for the first parent that
+    asks; the batch is shared with the other `uses - 1` and released after the last (the creation side of a runtime filter and the
+    build side of the join it was derived from are the same broadcast)."""
+
+    def __init__(self, child: SparkPlan, uses: int = 2):
+        self.child, self.children, self.uses = child, (child,), uses
+        self._batch, self._left = None, 0
+
+    def executeColumnar(self, stream=None):
+        if self._batch is None:
+            self._batch, self._left = self.child.executeColumnar(stream), self.uses
+        out = self._batch.rename(self._batch.names)      # a new handle over the same buffers
+        self._left -= 1
+        if self._left == 0:
+            self._batch.close()
+            self._batch = None
+        return out
+
+
+class RuntimeFilter:
+    """What InjectRuntimeFilter (sql/catalyst/.../optimizer/InjectRuntimeFilter.scala:47-100) plans on the application side of a join:
+    `applicationKey IN (creation side's creationKey)`, evaluated as a might-contain test.  Here the creation side becomes a single-key
+    HashedRelation and its prefilter (exact bitmap or Bloom) is tested on the streamed column inside the join's candidate pass."""
+
+    def __init__(self, applicationKey: str, creationKey: str, creationPlan: SparkPlan):
+        self.applicationKey, self.creationKey, self.creationPlan = applicationKey, creationKey, creationPlan
+
+
 class BroadcastHashJoinExec(SparkPlan):
     """leftKeys / rightKeys: attribute names; joinType: inner | left_outer | right_outer | full_outer | left_semi | left_anti |
     existence | left_anti_null_aware; buildSide: 'right' (left is streamed) or 'left'; condition: residual predicate over
     left ++ right attributes (HashJoin.boundCondition).  Output: left ++ right columns whatever the build side is
     (HashJoin.scala:55-70); existence: left columns ++ `exists`."""
 
-    def __init__(self, leftKeys, rightKeys, joinType, buildSide, left: SparkPlan, right: SparkPlan, condition=None):
+    def __init__(self, leftKeys, rightKeys, joinType, buildSide, left: SparkPlan, right: SparkPlan, condition=None, runtimeFilters=None):
+        self.runtimeFilters = list(runtimeFilters or [])    # on the STREAMED side (inner / left semi joins)
         self.leftKeys, self.rightKeys = list(leftKeys), list(rightKeys)
         table = _STREAM_LEFT if buildSide == "right" else _STREAM_RIGHT
         if buildSide not in ("left", "right") or joinType not in table:
@@ -598,14 +628,24 @@ class BroadcastHashJoinExec(SparkPlan):
             rel = HashedRelation(build, build_keys, stream, b_cond, b_names)
         finally:
             build.close()
+        rf_rels = []
         try:
+            for rf in self.runtimeFilters:
+                cb = rf.creationPlan.executeColumnar(stream)
+                try:
+                    rf_rels.append((rf.applicationKey, HashedRelation(cb, [rf.creationKey], stream, None, [rf.creationKey])))
+                finally:
+                    cb.close()
             probe = s_src.executeColumnar(stream)
             try:
-                out = probe_join(rel, probe, stream_keys, self.native_type, stream, self.condition, probe_filter=s_cond, probe_out=s_names)
+                out = probe_join(rel, probe, stream_keys, self.native_type, stream, self.condition, probe_filter=s_cond, probe_out=s_names,
+                                 runtime_filters=rf_rels)
             finally:
                 probe.close()
         finally:
             rel.close()
+            for _, r in rf_rels:
+                r.close()
         if self.buildSide == "left" and self.native_type in ("inner", "left_outer", "build_outer", "full_outer"):
             nl = len(rel.names)      # streamed ++ build came back: restore left ++ right
             order = list(range(len(out.names) - nl, len(out.names))) + list(range(len(out.names) - nl))
@@ -620,7 +660,7 @@ class BroadcastHashJoinExec(SparkPlan):
 
 
 def probe_join(rel: HashedRelation, probe: ColumnarBatch, keys, joinType, stream=None, condition=None, probe_filter=None, probe_out=None,
-               **_ignored) -> ColumnarBatch:
+               runtime_filters=None, **_ignored) -> ColumnarBatch:
     lib = capi.load()
     idx = [probe.column_index(k) for k in keys]
     arr = (C.c_int32 * max(1, len(idx)))(*idx)
@@ -633,9 +673,16 @@ def probe_join(rel: HashedRelation, probe: ColumnarBatch, keys, joinType, stream
         schema = Schema(probe.names + rel.names, [probe.column_desc(i).type for i in range(len(probe.names))] + rel.types)
         ce = CompiledExpr(condition, schema)
         capi.check(lib.sb_join_probe_condition(rel.handle, probe.handle, arr, len(idx), capi.SB_JOIN[joinType], C.byref(ce.c), _h(stream), C.byref(h)))
-    elif probe_filter is not None or probe_out is not None or rel.out_cols is not None:
+    elif probe_filter is not None or probe_out is not None or rel.out_cols is not None or runtime_filters:
         opt = capi.sb_join_options()
         keep = []
+        if runtime_filters:
+            rc_ = (C.c_int32 * len(runtime_filters))(*[probe.column_index(k) for k, _ in runtime_filters])
+            rr_ = (C.c_void_p * len(runtime_filters))(*[r.handle for _, r in runtime_filters])
+            keep += [rc_, rr_]
+            opt.n_runtime_filters = len(runtime_filters)
+            opt.runtime_filter_cols = C.cast(rc_, C.POINTER(C.c_int32))
+            opt.runtime_filter_relations = C.cast(rr_, C.POINTER(C.c_void_p))
         if probe_filter is not None:
             fe = CompiledExpr(probe_filter, _schema_of(probe))
             keep.append(fe)

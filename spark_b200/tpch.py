@@ -215,19 +215,27 @@ def q3_plan(customer: SparkPlan, orders: SparkPlan, lineitem: SparkPlan, partial
                                      ["l_orderkey", "revenue", "o_orderdate", "o_shippriority"], agg)
 
 
-def q5_plan(customer, orders, lineitem, supplier, nation, region) -> SparkPlan:
-    """q5.sql: six-way join, filter on region and order date, group by nation name, order by revenue desc."""
-    from .execution import BroadcastHashJoinExec
+def q5_plan(customer, orders, lineitem, supplier, nation, region, runtime_filter=True) -> SparkPlan:
+    """q5.sql: six-way join, filter on region and order date, group by nation name, order by revenue desc.
+    runtime_filter: the supplier side (selective: one region of five) also filters lineitem's l_suppkey below the orders join, the way
+    InjectRuntimeFilter (sql/catalyst/.../optimizer/InjectRuntimeFilter.scala) puts a might-contain filter on the application side
+    of a join whose creation side has a selective predicate; the supplier subplan is a ReusedExchange of its two consumers."""
+    from .execution import BroadcastHashJoinExec, ReusedExchangeExec, RuntimeFilter
     reg = ProjectExec(["r_regionkey"], FilterExec(col("r_name").eq(Literal(Q5_REGION)), region))
     nat = ProjectExec(["n_nationkey", "n_name"], BroadcastHashJoinExec(["n_regionkey"], ["r_regionkey"], "inner", "right", nation, reg))
     sup = ProjectExec(["s_suppkey", "s_nationkey", "n_name"],
                       BroadcastHashJoinExec(["s_nationkey"], ["n_nationkey"], "inner", "right", supplier, nat))
+    rfs = None
+    if runtime_filter:
+        sup = ReusedExchangeExec(sup, uses=2)
+        rfs = [RuntimeFilter("l_suppkey", "s_suppkey", sup)]
     ord_f = FilterExec((col("o_orderdate") >= Literal(Q5_DATE_LO)) & (col("o_orderdate") < Literal(Q5_DATE_HI)), orders)
     oc = ProjectExec(["o_orderkey", "c_nationkey"],
                      BroadcastHashJoinExec(["o_custkey"], ["c_custkey"], "inner", "right", ord_f, ProjectExec(["c_custkey", "c_nationkey"], customer)))
     lo = ProjectExec(["l_suppkey", "c_nationkey", "l_extendedprice", "l_discount"],
                      BroadcastHashJoinExec(["l_orderkey"], ["o_orderkey"], "inner", "right",
-                                           ProjectExec(["l_orderkey", "l_suppkey", "l_extendedprice", "l_discount"], lineitem), oc))
+                                           ProjectExec(["l_orderkey", "l_suppkey", "l_extendedprice", "l_discount"], lineitem), oc,
+                                           runtimeFilters=rfs))
     # q5.sql: l_suppkey = s_suppkey AND c_nationkey = s_nationkey -- both are equi-join keys of the supplier join
     # (ExtractEquiJoinKeys, sql/catalyst/.../planning/patterns.scala); together they need more than 64 bits: the wide-key relation
     same_nation = BroadcastHashJoinExec(["l_suppkey", "c_nationkey"], ["s_suppkey", "s_nationkey"], "inner", "right", lo, sup)

@@ -236,3 +236,60 @@ def test_join_keys_wider_than_64_bits(gpu, stream, how, npr):
     want = O.hash_join(probe, build, ["a", "b", "c"], ["a2", "b2", "c2"], "build_outer" if how == "right_outer" else how)
     assert got.num_rows == want.num_rows
     assert_tables_equal(got, want, key_cols=list(want.column_names))
+
+
+# Runtime filters (InjectRuntimeFilter.scala:47-100: `applicationKey IN (creation side keys)` as a might-contain test below the join).
+# Exact creation sides (dense integer keys -> bitmap) make the filter an exact semi join: the result must equal the oracle's join of
+# the semi-joined streamed side.  Sparse creation keys take the Bloom filter, which may let non-members through: the result is
+# sandwiched between the filtered and the unfiltered join.
+@pytest.mark.parametrize("how", ["inner", "left_semi"])
+@pytest.mark.parametrize("n", [5000, (1 << 20) + 4097])        # byte-mask fallback / inside the candidate pass
+@pytest.mark.parametrize("rf_width", [8, 4])
+def test_runtime_filter_exact(gpu, stream, how, n, rf_width):
+    from spark_b200.columnar import ColumnarBatch
+    from spark_b200.execution import BroadcastHashJoinExec, LocalTableScanExec, RuntimeFilter
+    rng = np.random.default_rng(n + rf_width)
+    s = rng.integers(0, 1000, n)
+    s = s.astype(np.int64) if rf_width == 8 else s.astype(np.int32)
+    left = pa.table({"k": rng.integers(0, 60000, n), "s": s, "x": np.arange(n, dtype=np.int64)})
+    right = pa.table({"k2": rng.permutation(60000)[:20000].astype(np.int64), "rv": np.arange(20000, dtype=np.int32)})
+    ck = rng.permutation(1000)[:300]
+    creation = pa.table({"c": ck.astype(np.int64) if rf_width == 8 else ck.astype(np.int32)})
+    lb, rb, cb = (ColumnarBatch.from_arrow(t, stream) for t in (left, right, creation))
+    plan = BroadcastHashJoinExec(["k"], ["k2"], how, "right", LocalTableScanExec(lb), LocalTableScanExec(rb),
+                                 runtimeFilters=[RuntimeFilter("s", "c", LocalTableScanExec(cb))])
+    got = plan.collect(stream)
+    keep = np.isin(np.asarray(left.column("s")), ck)
+    want = O.hash_join(left.filter(pa.array(keep)), right, ["k"], ["k2"], how)
+    assert_tables_equal(got, want, key_cols=list(want.column_names))
+
+
+def test_runtime_filter_bloom_is_a_superset_filter(gpu, stream):
+    from spark_b200.columnar import ColumnarBatch
+    from spark_b200.execution import BroadcastHashJoinExec, LocalTableScanExec, RuntimeFilter
+    rng = np.random.default_rng(99)
+    n = (1 << 20) + 77
+    left = pa.table({"k": rng.integers(0, 50000, n), "s": rng.integers(0, 2 ** 62, n), "x": np.arange(n, dtype=np.int64)})
+    sv = np.asarray(left.column("s"))
+    right = pa.table({"k2": np.arange(50000, dtype=np.int64)})
+    ck = np.concatenate([sv[rng.permutation(n)[:100000]], rng.integers(0, 2 ** 62, 50000)])     # sparse 62-bit keys: Bloom prefilter
+    lb, rb, cb = (ColumnarBatch.from_arrow(t, stream) for t in (left, right, pa.table({"c": ck})))
+    got = BroadcastHashJoinExec(["k"], ["k2"], "left_semi", "right", LocalTableScanExec(lb), LocalTableScanExec(rb),
+                                runtimeFilters=[RuntimeFilter("s", "c", LocalTableScanExec(cb))]).collect(stream)
+    gx = np.sort(np.asarray(got.column("x")))
+    members = np.flatnonzero(np.isin(sv, ck))
+    assert len(np.unique(gx)) == len(gx)
+    assert np.all(np.isin(members, gx)), "a runtime filter must never drop a member"
+    assert len(gx) < 0.3 * n, "and it should drop most non-members (%d of %d rows kept, %d members)" % (len(gx), n, len(members))
+
+
+def test_runtime_filter_rejected_on_outer_joins(gpu, stream):
+    from spark_b200 import _capi as capi
+    from spark_b200.columnar import ColumnarBatch
+    from spark_b200.execution import BroadcastHashJoinExec, LocalTableScanExec, RuntimeFilter
+    t = pa.table({"k": np.arange(10, dtype=np.int64)})
+    b = [ColumnarBatch.from_arrow(t, stream) for _ in range(3)]
+    plan = BroadcastHashJoinExec(["k"], ["k"], "left_outer", "right", LocalTableScanExec(b[0]), LocalTableScanExec(b[1].rename(["k"])),
+                                 runtimeFilters=[RuntimeFilter("k", "k", LocalTableScanExec(b[2]))])
+    with pytest.raises(capi.SparkB200Error):
+        plan.collect(stream)
