@@ -88,6 +88,12 @@ public final class Native {
   /** FilterExec below the streamed side and ProjectExec above the join fused into the probe; 0 / null = none / all columns */
   public static native long joinProbeFused(long relation, long probe, int[] keyCols, int joinType, long probeFilterExpr,
                                            int[] probeOutCols, int[] buildOutCols, long stream);
+  /** joinProbeFused plus runtime filters (InjectRuntimeFilter.scala:47-100: the BloomFilterMightContain FilterExec the optimizer puts on
+   *  the application side): streamed column runtimeFilterCols[i] is tested against the prefilter of the single-key relation
+   *  runtimeFilterRelations[i] (built from the creation side with joinBuild) inside the candidate pass; INNER / LEFT_SEMI only */
+  public static native long joinProbeRuntimeFiltered(long relation, long probe, int[] keyCols, int joinType, long probeFilterExpr,
+                                                     int[] probeOutCols, int[] buildOutCols, int[] runtimeFilterCols,
+                                                     long[] runtimeFilterRelations, long stream);
 
   // ---- WindowExec / ExpandExec -------------------------------------------------------------------------------------------------------
   /** one entry per window expression: SB_WIN_* code, input column, frame type (0 rows / 1 range), bounds (Long.MIN_VALUE /

@@ -496,6 +496,39 @@ NATIVE(jlong, joinProbeFused)(JNIEnv *env, jclass c, jlong rel, jlong probe, jin
   return (jlong)(intptr_t)out;
 }
 
+NATIVE(jlong, joinProbeRuntimeFiltered)(JNIEnv *env, jclass c, jlong rel, jlong probe, jintArray keyCols, jint joinType, jlong probeFilter,
+                                        jintArray probeOut, jintArray buildOut, jintArray rfCols, jlongArray rfRelations, jlong stream) {
+  jsize nk = (*env)->GetArrayLength(env, keyCols);
+  jint *k = (*env)->GetIntArrayElements(env, keyCols, NULL);
+  jint *po = probeOut ? (*env)->GetIntArrayElements(env, probeOut, NULL) : NULL;
+  jint *bo = buildOut ? (*env)->GetIntArrayElements(env, buildOut, NULL) : NULL;
+  jsize nrf = rfCols ? (*env)->GetArrayLength(env, rfCols) : 0;
+  jint *rc = nrf ? (*env)->GetIntArrayElements(env, rfCols, NULL) : NULL;
+  jlong *rr = nrf ? (*env)->GetLongArrayElements(env, rfRelations, NULL) : NULL;
+  const sb_hash_table *rels[8];
+  sb_join_options opt;
+  memset(&opt, 0, sizeof(opt));
+  if (nrf > 8) nrf = 8;
+  for (jsize i = 0; i < nrf; i++) rels[i] = (const sb_hash_table *)(intptr_t)rr[i];
+  opt.probe_filter = (const sb_expr *)(intptr_t)probeFilter;
+  opt.probe_out_cols = (const int32_t *)po;
+  opt.n_probe_out = po ? (*env)->GetArrayLength(env, probeOut) : 0;
+  opt.build_out_cols = (const int32_t *)bo;
+  opt.n_build_out = bo ? (*env)->GetArrayLength(env, buildOut) : 0;
+  opt.n_runtime_filters = (int32_t)nrf;
+  opt.runtime_filter_cols = (const int32_t *)rc;
+  opt.runtime_filter_relations = rels;
+  sb_table *out = NULL;
+  int rcode = sb_join_probe_ex((const sb_hash_table *)(intptr_t)rel, TBL(probe), (const int32_t *)k, nk, joinType, &opt, STR(stream), &out);
+  if (rr) (*env)->ReleaseLongArrayElements(env, rfRelations, rr, JNI_ABORT);
+  if (rc) (*env)->ReleaseIntArrayElements(env, rfCols, rc, JNI_ABORT);
+  if (bo) (*env)->ReleaseIntArrayElements(env, buildOut, bo, JNI_ABORT);
+  if (po) (*env)->ReleaseIntArrayElements(env, probeOut, po, JNI_ABORT);
+  (*env)->ReleaseIntArrayElements(env, keyCols, k, JNI_ABORT);
+  throw_if(env, rcode);
+  return (jlong)(intptr_t)out;
+}
+
 NATIVE(jlong, shuffleExchange)(JNIEnv *env, jclass c, jlong table, jintArray keyCols, jint n, jlong stream, jlongArray offsetsOut) {
   jsize nk = (*env)->GetArrayLength(env, keyCols);
   jint *k = (*env)->GetIntArrayElements(env, keyCols, NULL);
