@@ -223,15 +223,20 @@ def q5_plan(customer, orders, lineitem, supplier, nation, region, runtime_filter
     from .execution import BroadcastHashJoinExec, ReusedExchangeExec, RuntimeFilter
     reg = ProjectExec(["r_regionkey"], FilterExec(col("r_name").eq(Literal(Q5_REGION)), region))
     nat = ProjectExec(["n_nationkey", "n_name"], BroadcastHashJoinExec(["n_regionkey"], ["r_regionkey"], "inner", "right", nation, reg))
+    if runtime_filter:
+        nat = ReusedExchangeExec(nat, uses=2)
     sup = ProjectExec(["s_suppkey", "s_nationkey", "n_name"],
                       BroadcastHashJoinExec(["s_nationkey"], ["n_nationkey"], "inner", "right", supplier, nat))
     rfs = None
+    cust = ProjectExec(["c_custkey", "c_nationkey"], customer)
     if runtime_filter:
         sup = ReusedExchangeExec(sup, uses=2)
         rfs = [RuntimeFilter("l_suppkey", "s_suppkey", sup)]
+        # c_nationkey = s_nationkey with s_nationkey confined to the region's nations: the same rule's IN-subquery on the customer
+        # side, planned as the semi join it logically is (the relation on 25 dense keys is an exact bitmap)
+        cust = BroadcastHashJoinExec(["c_nationkey"], ["n_nationkey"], "left_semi", "right", cust, ProjectExec(["n_nationkey"], nat))
     ord_f = FilterExec((col("o_orderdate") >= Literal(Q5_DATE_LO)) & (col("o_orderdate") < Literal(Q5_DATE_HI)), orders)
-    oc = ProjectExec(["o_orderkey", "c_nationkey"],
-                     BroadcastHashJoinExec(["o_custkey"], ["c_custkey"], "inner", "right", ord_f, ProjectExec(["c_custkey", "c_nationkey"], customer)))
+    oc = ProjectExec(["o_orderkey", "c_nationkey"], BroadcastHashJoinExec(["o_custkey"], ["c_custkey"], "inner", "right", ord_f, cust))
     lo = ProjectExec(["l_suppkey", "c_nationkey", "l_extendedprice", "l_discount"],
                      BroadcastHashJoinExec(["l_orderkey"], ["o_orderkey"], "inner", "right",
                                            ProjectExec(["l_orderkey", "l_suppkey", "l_extendedprice", "l_discount"], lineitem), oc,
