@@ -510,7 +510,7 @@ int radix_sort_pairs(uint64_t *keys, uint32_t *vals, int64_t n, cudaStream_t st,
       {(const void *)rs_onesweep2_kernel<544, 8, true, 2>, 544, 8, 2},      // 10
       {(const void *)rs_onesweep2_kernel<384, 12, true, 4>, 384, 12, 2},    // 11
       {(const void *)rs_onesweep2_kernel<288, 16, true, 2>, 288, 16, 2},    // 12
-      {(const void *)rs_onesweep2_kernel<1056, 8, true, 4>, 1056, 8, 2},    // 13: one block per SM
+      {(const void *)rs_onesweep2_kernel<1024, 8, true, 4>, 1024, 8, 2},    // 13: one block per SM
   };
   int vi = config().sort_variant;
   if (vi < 0 || vi >= (int)(sizeof(variants) / sizeof(variants[0]))) vi = 0;
