@@ -1132,6 +1132,9 @@ int sb_join_probe_ex(const sb_hash_table *ht, const sb_table *probe, const int32
       if (r->nkeys != 1 || r->wide || r->has_dict[0]) fail(SB_ERR_UNSUPPORTED, "runtime filter %d: the creation side must be a relation on one fixed-width key", i);
       if (!r->bloom) continue;   // a relation without a prefilter: the filter is an optimisation, leaving it out changes nothing
       const int32_t c = opt->runtime_filter_cols[i];
+      SB_REQUIRE(c >= 0 && c < (int)probe->cols.size(), "runtime filter %d: column %d out of range", i, c);
+      const int32_t ct = probe->cols[c].type;
+      if (ct == SB_STRING || ct == SB_DECIMAL128 || type_width(ct) * 8 != r->key_bits[0]) continue;   // differently packed: leave the filter out
       rf_keys.push_back(make_join_keys(probe, &c, 1, r));
       rf_filters.push_back(key_filter_of(r));
     }

@@ -766,6 +766,87 @@ class B200ColumnarRule:
     def postColumnarTransitions(self, plan: SparkPlan) -> SparkPlan:
         return plan
 
+    # ---- runtime filters -------------------------------------------------------------------------------------------------------
+    maxRuntimeFilters = 2      # per join (csrc/join.cu MAX_RUNTIME_FILTERS); the reference caps the whole query at 10
+
+    def injectRuntimeFilters(self, plan: SparkPlan) -> SparkPlan:
+        """The physical-plan face of InjectRuntimeFilter (sql/catalyst/.../optimizer/InjectRuntimeFilter.scala:196-260, 411-460): for an
+        inner join J2 whose streamed side is (Projects / Filters over) another inner or left-semi join J1, and whose build side has a
+        selective predicate (a FilterExec somewhere below it), rows of J1's STREAMED input whose J2 key cannot be in J2's build side
+        never reach the output -- so J1 tests that key against the relation's prefilter inside its candidate pass.  J2's build subplan
+        becomes a ReusedExchangeExec shared by J2 and the filter's creation side."""
+        for attr in ("child", "left", "right"):
+            if hasattr(plan, attr):
+                setattr(plan, attr, self.injectRuntimeFilters(getattr(plan, attr)))
+        if hasattr(plan, "child"):
+            plan.children = (plan.child,)
+        elif hasattr(plan, "left"):
+            plan.children = (plan.left, plan.right)
+        if not (isinstance(plan, BroadcastHashJoinExec) and plan.joinType == "inner" and plan.condition is None):
+            return plan
+        right_built = plan.buildSide == "right"
+        build, streamed = (plan.right, plan.left) if right_built else (plan.left, plan.right)
+        bkeys, skeys = (plan.rightKeys, plan.leftKeys) if right_built else (plan.leftKeys, plan.rightKeys)
+        if not _has_filter(build):
+            return plan
+        # walk down the streamed side through operators that pass the key attribute through unchanged
+        j1 = streamed
+        while True:
+            if isinstance(j1, ProjectExec):
+                passed = {n for n, e in j1.projectList if isinstance(e, AttributeReference) and e.name == n}
+                if not all(k in passed for k in skeys):
+                    return plan
+                j1 = j1.child
+            elif isinstance(j1, FilterExec):
+                j1 = j1.child
+            else:
+                break
+        if not (isinstance(j1, BroadcastHashJoinExec) and j1.joinType in ("inner", "left_semi") and j1.condition is None):
+            return plan
+        j1_streamed = j1.left if j1.buildSide == "right" else j1.right
+        names = _output_names(j1_streamed)
+        if names is None:
+            return plan
+        injected = False
+        for sk, bk in zip(skeys, bkeys):
+            if sk in names and len(j1.runtimeFilters) < self.maxRuntimeFilters and all(f.applicationKey != sk for f in j1.runtimeFilters):
+                if not isinstance(build, ReusedExchangeExec):
+                    build = ReusedExchangeExec(build, uses=1)
+                build.uses += 1
+                j1.runtimeFilters.append(RuntimeFilter(sk, bk, build))
+                injected = True
+        if injected:
+            if right_built:
+                plan.right = build
+            else:
+                plan.left = build
+            plan.children = (plan.left, plan.right)
+        return plan
+
+
+def _has_filter(plan) -> bool:
+    """hasSelectivePredicate's stand-in (InjectRuntimeFilter.scala:262-275): the mirror keeps no statistics, a FilterExec anywhere in the
+    creation side counts as selective."""
+    return isinstance(plan, FilterExec) or any(_has_filter(c) for c in getattr(plan, "children", ()))
+
+
+def _output_names(plan):
+    """Attribute names a plan produces, when they can be told without running it (None otherwise)."""
+    if isinstance(plan, LocalTableScanExec):
+        return list(plan.batch.names)
+    if isinstance(plan, ProjectExec):
+        return [n for n, _ in plan.projectList]
+    if isinstance(plan, (FilterExec, ReusedExchangeExec)):
+        return _output_names(plan.child)
+    if isinstance(plan, BroadcastHashJoinExec):
+        l = _output_names(plan.left)
+        if plan.joinType in ("left_semi", "left_anti", "left_anti_null_aware"):
+            return l
+        r = _output_names(plan.right)
+        return None if l is None or r is None else l + r
+    out = getattr(plan, "output_names", None)
+    return list(out) if out is not None else None
+
 
 def _substitute(e: Expression, mapping):
     import copy

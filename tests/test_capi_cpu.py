@@ -126,3 +126,39 @@ def test_scala_plugin_is_self_consistent():
     bcast = ex[ex.index("case class GpuBroadcastExchangeExec"):ex.index("object GpuBroadcastExchangeExec")]
     for member in ("runId", "relationFuture", "completionFuture", "runtimeStatistics", "doExecuteBroadcast", "doPrepare"):
         assert re.search(r"\b%s\b" % member, bcast), "GpuBroadcastExchangeExec lacks %s" % member
+
+
+def test_runtime_filter_injection_rule():
+    """B200ColumnarRule.injectRuntimeFilters: inner join over an inner join, creation side with a FilterExec -> the lower join gets a
+    RuntimeFilter on its streamed column and both consumers share one ReusedExchangeExec; no filter -> plan untouched; key coming from
+    the lower join's BUILD side -> untouched."""
+    from spark_b200.expressions import Literal, col
+    from spark_b200.execution import (B200ColumnarRule, BroadcastHashJoinExec, FilterExec, ProjectExec, ReusedExchangeExec, SparkPlan)
+
+    class Leaf(SparkPlan):
+        def __init__(self, names):
+            self.output_names = names
+    lineitem, orders, supplier = Leaf(["l_orderkey", "l_suppkey", "l_price"]), Leaf(["o_orderkey", "o_nation"]), Leaf(["s_suppkey", "s_region"])
+    sup_f = ProjectExec(["s_suppkey"], FilterExec(col("s_region").eq(Literal(2)), supplier))
+    j1 = BroadcastHashJoinExec(["l_orderkey"], ["o_orderkey"], "inner", "right", lineitem, orders)
+    j2 = BroadcastHashJoinExec(["l_suppkey"], ["s_suppkey"], "inner", "right", ProjectExec(["l_suppkey", "o_nation", "l_price"], j1), sup_f)
+    out = B200ColumnarRule().injectRuntimeFilters(j2)
+    assert out is j2 and isinstance(j2.right, ReusedExchangeExec) and j2.right.uses == 2 and j2.right.child is sup_f
+    assert len(j1.runtimeFilters) == 1
+    rf = j1.runtimeFilters[0]
+    assert (rf.applicationKey, rf.creationKey) == ("l_suppkey", "s_suppkey") and rf.creationPlan is j2.right
+    # no selective predicate on the creation side: nothing happens
+    j1b = BroadcastHashJoinExec(["l_orderkey"], ["o_orderkey"], "inner", "right", lineitem, orders)
+    j2b = BroadcastHashJoinExec(["l_suppkey"], ["s_suppkey"], "inner", "right", j1b, supplier)
+    B200ColumnarRule().injectRuntimeFilters(j2b)
+    assert j1b.runtimeFilters == [] and j2b.right is supplier
+    # the key is produced by the lower join's build side: a filter on the streamed input would test the wrong table
+    j1c = BroadcastHashJoinExec(["l_orderkey"], ["o_orderkey"], "inner", "right", lineitem, orders)
+    j2c = BroadcastHashJoinExec(["o_nation"], ["s_suppkey"], "inner", "right", j1c, sup_f)
+    B200ColumnarRule().injectRuntimeFilters(j2c)
+    assert j1c.runtimeFilters == []
+    # an outer join below: its streamed rows must all survive
+    j1d = BroadcastHashJoinExec(["l_orderkey"], ["o_orderkey"], "left_outer", "right", lineitem, orders)
+    j2d = BroadcastHashJoinExec(["l_suppkey"], ["s_suppkey"], "inner", "right", j1d, sup_f)
+    B200ColumnarRule().injectRuntimeFilters(j2d)
+    assert j1d.runtimeFilters == []
