@@ -6,7 +6,7 @@
 // depend on how the passes are organised, so the GPU version keeps those rules and changes the machinery:
 //   * ONE read of the keys builds all eight 256-bin histograms (and so decides which passes run);
 //   * every pass is ONE kernel ("onesweep"): a block takes the next 4096-pair tile (ticket counter, so tiles run in memory
-//     order), ranks its keys stably per warp with match.any over per-warp digit counters, publishes the tile's 256 digit counts
+//     order), ranks its keys stably per warp (eight ballots per key over per-warp digit counters), publishes the tile's 256 digit counts
 //     and obtains its exclusive prefix over all earlier tiles by DECOUPLED LOOK-BACK (64-bit status words: aggregate / inclusive
 //     prefix) -- no separate histogram + scan + scatter launches and no second read of the keys -- then stages the tile in
 //     shared memory in digit order and writes every digit's run contiguously (coalesced 8 + 4 byte stores).
@@ -60,45 +60,56 @@ __device__ __forceinline__ void st_status(uint64_t *p, uint64_t v) {
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// Lanes of the warp that hold the same 8-bit digit: eight ballots, one per digit bit.  One bit test feeds the vote AND the select
+// (LOP3.P, VOTE, SEL, LOP3 = 4 instructions per bit); written in PTX because the C form comes back from the optimiser as shift + mask +
+// compare per use (7 per bit; ncu, round 2: the pass is issue-bound at 173 thread-instructions per key).
+template <int B>
+__device__ __forceinline__ void peer_bit(uint32_t d, uint32_t &m) {
+  uint32_t bal, sel;
+  asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tand.b32 t, %2, %3;\n\tsetp.ne.u32 p, t, 0;\n\tvote.sync.ballot.b32 %0, p, 0xffffffff;\n\t"
+               "selp.b32 %1, 0, 0xffffffff, p;\n\t}" : "=r"(bal), "=r"(sel) : "r"(d), "n"(1 << B));
+  m &= bal ^ sel;
+}
+__device__ __forceinline__ uint32_t digit_peers(uint32_t d, uint32_t m) {
+  peer_bit<0>(d, m); peer_bit<1>(d, m); peer_bit<2>(d, m); peer_bit<3>(d, m);
+  peer_bit<4>(d, m); peer_bit<5>(d, m); peer_bit<6>(d, m); peer_bit<7>(d, m);
+  return m;
+}
+
 // One LSD pass over byte `byte`.  status: [tiles][256] zero-initialised; ticket: zero-initialised tile counter.
 // RS_THREADS x RS_ITEMS pairs per tile (a warp owns 32 x RS_ITEMS consecutive rows); digit d is owned by thread d (RS_THREADS >= 256).
-template <int RS_THREADS, int RS_ITEMS>
-__global__ void __launch_bounds__(RS_THREADS, (RS_THREADS * RS_ITEMS <= 4096 ? 768 : 1024) / RS_THREADS) rs_onesweep_kernel(const uint64_t *__restrict__ in_keys, const uint32_t *__restrict__ in_vals,
-                                                                 uint64_t *__restrict__ out_keys, uint32_t *__restrict__ out_vals, int64_t n, int byte,
-                                                                 const unsigned long long *__restrict__ gbase /* [256] of this byte */,
-                                                                 uint64_t *__restrict__ status, uint32_t *__restrict__ ticket) {
+// FULL = the tile holds RS_TILE pairs (all but the last one): no bounds predicates anywhere in the unrolled per-key code.
+// n < 2^32 (SortExec's row ids are 32-bit), so output positions are 32-bit numbers.
+template <int RS_THREADS, int RS_ITEMS, bool FULL>
+__device__ __forceinline__ void rs_onesweep_tile(const uint64_t *__restrict__ in_keys, const uint32_t *__restrict__ in_vals,
+                                                 uint64_t *__restrict__ out_keys, uint32_t *__restrict__ out_vals, int64_t tile, int tile_n, int shift,
+                                                 const unsigned long long *__restrict__ gbase, uint64_t *__restrict__ status, uint8_t *rs_smem) {
   constexpr int RS_TILE = RS_THREADS * RS_ITEMS, RS_WARPS = RS_THREADS / 32;
-  static_assert(RS_THREADS >= 256 && RS_THREADS % 32 == 0, "one thread per digit");
-  extern __shared__ __align__(16) uint8_t rs_smem[];
   uint64_t *s_keys = (uint64_t *)rs_smem;                                   // [RS_TILE]
-  int64_t *s_dst_off = (int64_t *)(s_keys + RS_TILE);                       // [256] global position of sorted tile position p with digit d: s_dst_off[d] + p
-  uint32_t *s_vals = (uint32_t *)(s_dst_off + 256);                         // [RS_TILE]
+  uint32_t *s_dst_off = (uint32_t *)(s_keys + RS_TILE);                     // [256] global position of sorted tile position p with digit d: s_dst_off[d] + p (mod 2^32)
+  uint32_t *s_bin_start = s_dst_off + 256;                                  // [256] first tile-local position of every digit
+  uint32_t *s_vals = s_bin_start + 256;                                     // [RS_TILE]
   uint32_t(*s_whist)[256] = (uint32_t(*)[256])(s_vals + RS_TILE);           // [RS_WARPS][256] per-warp digit counters, then exclusive prefixes over the warps
   uint32_t(*s_wrun)[256] = s_whist + RS_WARPS;                              // [RS_WARPS][256] running per-warp counters of the ranking phase
-  uint32_t *s_bin_start = (uint32_t *)(s_wrun + RS_WARPS);                  // [256] first tile-local position of every digit
-  __shared__ uint32_t s_tile;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_tile = atomicAdd(ticket, 1u);
-  for (int i = tid; i < 2 * RS_WARPS * 256; i += RS_THREADS) (&s_whist[0][0])[i] = 0;   // s_whist and s_wrun
-  __syncthreads();
-  const int64_t tile = s_tile;
   const int64_t tile_base = tile * RS_TILE;
-  const int tile_n = (int)(n - tile_base < RS_TILE ? n - tile_base : RS_TILE);
-  const int shift = 8 * byte;
-  // ---- load (warp-striped: warp w owns rows [w * 512, (w + 1) * 512) of the tile; item k of lane l is row w * 512 + k * 32 + l) ----
+  // ---- load (warp-striped: warp w owns rows [w * 32 * RS_ITEMS, ...) of the tile; item k of lane l is row seg + k * 32 + l) ----
   uint64_t key[RS_ITEMS];
   uint32_t val[RS_ITEMS];
   uint16_t rank[RS_ITEMS];
   const int seg = warp * (32 * RS_ITEMS);
+  {
+    const uint64_t *kp = in_keys + tile_base + seg + lane;
+    const uint32_t *vp = in_vals + tile_base + seg + lane;
 #pragma unroll
-  for (int k = 0; k < RS_ITEMS; k++) {
-    const int r = seg + k * 32 + lane;
-    if (r < tile_n) {
-      key[k] = in_keys[tile_base + r];
-      val[k] = in_vals[tile_base + r];
-    } else {
-      key[k] = ~0ull;
-      val[k] = 0;
+    for (int k = 0; k < RS_ITEMS; k++) {
+      if (FULL || seg + k * 32 + lane < tile_n) {
+        key[k] = kp[k * 32];
+        val[k] = vp[k * 32];
+      } else {
+        key[k] = ~0ull;
+        val[k] = 0;
+      }
     }
   }
   // ---- early counts: per-warp digit histograms by shared-memory atomics, so the tile's 256 counts can be PUBLISHED before the
@@ -106,7 +117,7 @@ __global__ void __launch_bounds__(RS_THREADS, (RS_THREADS * RS_ITEMS <= 4096 ? 7
   uint32_t *wh = s_whist[warp];
 #pragma unroll
   for (int k = 0; k < RS_ITEMS; k++)
-    if (seg + k * 32 + lane < tile_n) atomicAdd(&wh[(uint32_t)((key[k] >> shift) & 0xff)], 1u);
+    if (FULL || seg + k * 32 + lane < tile_n) atomicAdd(&wh[(uint32_t)(key[k] >> shift) & 0xffu], 1u);
   __syncthreads();
   const bool digit_owner = tid < 256;
   uint32_t count = 0;
@@ -129,28 +140,26 @@ __global__ void __launch_bounds__(RS_THREADS, (RS_THREADS * RS_ITEMS <= 4096 ? 7
   uint32_t peers[RS_ITEMS];
 #pragma unroll
   for (int k = 0; k < RS_ITEMS; k++) {
-    const bool valid = seg + k * 32 + lane < tile_n;
-    const uint32_t d = (uint32_t)((key[k] >> shift) & 0xff);
-    uint32_t m = __ballot_sync(0xffffffffu, valid);
-#pragma unroll
-    for (int b = 0; b < 8; b++) {
-      const uint32_t bal = __ballot_sync(0xffffffffu, (d >> b) & 1);
-      m &= ((d >> b) & 1) ? bal : ~bal;
+    const uint32_t d = (uint32_t)(key[k] >> shift) & 0xffu;
+    if (FULL) peers[k] = digit_peers(d, 0xffffffffu);
+    else {
+      const bool valid = seg + k * 32 + lane < tile_n;
+      const uint32_t m = digit_peers(d, __ballot_sync(0xffffffffu, valid));
+      peers[k] = valid ? m : 0u;
     }
-    peers[k] = valid ? m : 0u;
   }
   const uint32_t lt = (1u << lane) - 1;
 #pragma unroll
   for (int k = 0; k < RS_ITEMS; k++) {
     const uint32_t p = peers[k];
-    const uint32_t d = (uint32_t)((key[k] >> shift) & 0xff);
+    const uint32_t d = (uint32_t)(key[k] >> shift) & 0xffu;
     const int leader = __ffs(p) - 1;                    // -1 for rows past the end of the tile
     uint32_t base = 0;
     if (lane == leader) {
       base = wr[d];
       wr[d] = base + __popc(p);
     }
-    base = __shfl_sync(0xffffffffu, base, leader < 0 ? lane : leader);
+    base = __shfl_sync(0xffffffffu, base, FULL ? leader : (leader < 0 ? lane : leader));
     rank[k] = (uint16_t)(base + __popc(p & lt));
     __syncwarp();
   }
@@ -191,14 +200,14 @@ __global__ void __launch_bounds__(RS_THREADS, (RS_THREADS * RS_ITEMS <= 4096 ? 7
       }
     }
     st_status(my_status, RS_FLAG_INCL | (excl + count));
-    s_dst_off[tid] = (int64_t)gbase[tid] + (int64_t)excl - (int64_t)bin_start;
+    s_dst_off[tid] = (uint32_t)gbase[tid] + (uint32_t)excl - bin_start;
   }
   __syncthreads();
   // ---- stage the tile in digit order ------------------------------------------------------------------------------------------------
 #pragma unroll
   for (int k = 0; k < RS_ITEMS; k++) {
-    if (seg + k * 32 + lane < tile_n) {
-      const uint32_t d = (uint32_t)((key[k] >> shift) & 0xff);
+    if (FULL || seg + k * 32 + lane < tile_n) {
+      const uint32_t d = (uint32_t)(key[k] >> shift) & 0xffu;
       const uint32_t p = s_bin_start[d] + s_whist[warp][d] + rank[k];
       s_keys[p] = key[k];
       s_vals[p] = val[k];
@@ -209,246 +218,36 @@ __global__ void __launch_bounds__(RS_THREADS, (RS_THREADS * RS_ITEMS <= 4096 ? 7
 #pragma unroll
   for (int k = 0; k < RS_ITEMS; k++) {
     const int p = k * RS_THREADS + tid;
-    if (p < tile_n) {
+    if (FULL || p < tile_n) {
       const uint64_t kk = s_keys[p];
-      const int64_t dst = s_dst_off[(kk >> shift) & 0xff] + p;
+      const uint32_t dst = s_dst_off[(uint32_t)(kk >> shift) & 0xffu] + (uint32_t)p;
       out_keys[dst] = kk;
       out_vals[dst] = s_vals[p];
     }
   }
 }
 
-// ---- onesweep, second form: a dedicated LOOK-BACK WARP ----------------------------------------------------------------------------------
-// ncu of the first form showed the digit-owner threads spinning in the look-back after their ranking while the other warps sat at the
-// barrier.  Here the last warp of the block does nothing but the look-back (lane l owns digits l, l + 32, ... l + 224: eight coalesced
-// 256-byte status reads per predecessor, four predecessors per round trip), concurrently with the data warps' ranking and staging.  The
-// tile-local scan runs BEFORE the ranking, so the running per-warp counters start at the final tile positions and the ranking yields the
-// staging position directly (one LDS + one STS by the leader lane, no second lookup).  Status words carry the pass number (epoch), so
-// the status array is zeroed once per sort instead of once per pass.
-//   word = flag(2) | epoch(6) | value(56);  flag 1 = aggregate of the tile, 2 = inclusive prefix, 0 / other epoch = not published
-// EARLY = per-warp counts by shared-memory atomics before the ranking (published early, look-back overlaps the ranking); otherwise the
-// counts fall out of the ranking and the look-back overlaps only the staging.
-constexpr int RS2_EPOCH_SHIFT = 56;
-constexpr uint64_t RS2_VALUE_MASK = (1ull << RS2_EPOCH_SHIFT) - 1;
-template <int RS_THREADS, int RS_ITEMS, bool EARLY, int LB_W>
-__global__ void __launch_bounds__(RS_THREADS, ((RS_THREADS - 32) * RS_ITEMS <= 4608 ? 2 : 1)) rs_onesweep2_kernel(
-    const uint64_t *__restrict__ in_keys, const uint32_t *__restrict__ in_vals, uint64_t *__restrict__ out_keys, uint32_t *__restrict__ out_vals,
-    int64_t n, int byte, const unsigned long long *__restrict__ gbase, uint64_t *__restrict__ status, uint32_t *__restrict__ ticket, uint32_t epoch) {
-  constexpr int DT = RS_THREADS - 32, DW = DT / 32, RS_TILE = DT * RS_ITEMS;
-  static_assert(DT >= 256, "one data thread per digit");
+template <int RS_THREADS, int RS_ITEMS>
+__global__ void __launch_bounds__(RS_THREADS, (RS_THREADS * RS_ITEMS <= 4096 ? 768 : 1024) / RS_THREADS) rs_onesweep_kernel(const uint64_t *__restrict__ in_keys, const uint32_t *__restrict__ in_vals,
+                                                                 uint64_t *__restrict__ out_keys, uint32_t *__restrict__ out_vals, int64_t n, int byte,
+                                                                 const unsigned long long *__restrict__ gbase /* [256] of this byte */,
+                                                                 uint64_t *__restrict__ status, uint32_t *__restrict__ ticket) {
+  constexpr int RS_TILE = RS_THREADS * RS_ITEMS, RS_WARPS = RS_THREADS / 32;
+  static_assert(RS_THREADS >= 256 && RS_THREADS % 32 == 0, "one thread per digit");
   extern __shared__ __align__(16) uint8_t rs_smem[];
-  uint64_t *s_keys = (uint64_t *)rs_smem;                           // [RS_TILE]
-  int64_t *s_dst_off = (int64_t *)(s_keys + RS_TILE);               // [256]
-  uint32_t *s_vals = (uint32_t *)(s_dst_off + 256);                 // [RS_TILE]
-  uint32_t(*s_wpos)[256] = (uint32_t(*)[256])(s_vals + RS_TILE);    // [DW][256] counts -> running tile positions of (warp, digit)
-  uint32_t *s_bin_start = (uint32_t *)(s_wpos + DW);                // [256]
-  uint32_t *s_count = s_bin_start + 256;                            // [256]
   __shared__ uint32_t s_tile;
-  __shared__ uint32_t s_wsum[8];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const bool data = warp < DW;
+  const int tid = threadIdx.x;
   if (tid == 0) s_tile = atomicAdd(ticket, 1u);
-  for (int i = tid; i < DW * 256; i += RS_THREADS) (&s_wpos[0][0])[i] = 0;
+  {   // the two counter arrays ([2][RS_WARPS][256] words behind keys, offsets and values) start at zero: 16-byte stores
+    uint4 *z = (uint4 *)(rs_smem + (size_t)RS_TILE * 12 + 2 * 256 * 4);
+    for (int i = tid; i < 2 * RS_WARPS * 256 / 4; i += RS_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+  }
   __syncthreads();
   const int64_t tile = s_tile;
   const int64_t tile_base = tile * RS_TILE;
   const int tile_n = (int)(n - tile_base < RS_TILE ? n - tile_base : RS_TILE);
-  const bool full = tile_n == RS_TILE;
-  const int shift = 8 * byte;
-  const uint64_t tag_agg = (1ull << 62) | ((uint64_t)epoch << RS2_EPOCH_SHIFT), tag_incl = (2ull << 62) | ((uint64_t)epoch << RS2_EPOCH_SHIFT);
-  uint64_t key[RS_ITEMS];
-  uint32_t val[RS_ITEMS];
-  uint16_t pos[RS_ITEMS];
-  const int seg = warp * (32 * RS_ITEMS);
-  if (data) {
-#pragma unroll
-    for (int k = 0; k < RS_ITEMS; k++) {
-      const int r = seg + k * 32 + lane;
-      if (full || r < tile_n) {
-        key[k] = in_keys[tile_base + r];
-        val[k] = in_vals[tile_base + r];
-      } else {
-        key[k] = ~0ull;
-        val[k] = 0;
-      }
-    }
-  }
-  uint32_t *wp = s_wpos[data ? warp : 0];
-  const uint32_t lt = (1u << lane) - 1;
-  // peers of item k: lanes of the warp holding the same digit (eight independent ballots, see the first form)
-  auto peers_of = [&](int k, uint32_t d) -> uint32_t {
-    uint32_t m = full ? 0xffffffffu : __ballot_sync(0xffffffffu, seg + k * 32 + lane < tile_n);
-#pragma unroll
-    for (int b = 0; b < 8; b++) {
-      const uint32_t bal = __ballot_sync(0xffffffffu, (d >> b) & 1);
-      m &= ((d >> b) & 1) ? bal : ~bal;
-    }
-    return (full || seg + k * 32 + lane < tile_n) ? m : 0u;
-  };
-  if (EARLY) {
-    if (data) {
-#pragma unroll
-      for (int k = 0; k < RS_ITEMS; k++)
-        if (full || seg + k * 32 + lane < tile_n) atomicAdd(&wp[(uint32_t)((key[k] >> shift) & 0xff)], 1u);
-    }
-  } else {
-    if (data) {   // ranking first: pos = rank inside the warp's segment, the counters end up as the warp's digit counts
-#pragma unroll
-      for (int k = 0; k < RS_ITEMS; k++) {
-        const uint32_t d = (uint32_t)((key[k] >> shift) & 0xff);
-        const uint32_t p = peers_of(k, d);
-        const int leader = __ffs(p) - 1;
-        uint32_t base = 0;
-        if (lane == leader) {
-          base = wp[d];
-          wp[d] = base + __popc(p);
-        }
-        base = __shfl_sync(0xffffffffu, base, leader < 0 ? lane : leader);
-        pos[k] = (uint16_t)(base + __popc(p & lt));
-        __syncwarp();
-      }
-    }
-  }
-  __syncthreads();
-  // ---- digit owners: counts over the warps, publish the aggregate, tile-local scan ----------------------------------------------------
-  const bool digit_owner = tid < 256;
-  uint32_t count = 0, incl = 0;
-  uint32_t wc[DW];
-  if (digit_owner) {
-#pragma unroll
-    for (int w = 0; w < DW; w++) {
-      wc[w] = s_wpos[w][tid];
-      count += wc[w];
-    }
-    st_status(status + tile * 256 + tid, tag_agg | count);
-    s_count[tid] = count;
-    incl = count;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
-      if (lane >= d) incl += o;
-    }
-    if (lane == 31) s_wsum[warp] = incl;
-  }
-  __syncthreads();
-  if (digit_owner) {
-    uint32_t bin_start = incl - count;
-    for (int w = 0; w < warp; w++) bin_start += s_wsum[w];
-    s_bin_start[tid] = bin_start;
-    uint32_t run = bin_start;
-#pragma unroll
-    for (int w = 0; w < DW; w++) {   // (warp, digit) -> first tile position of that warp's keys with that digit
-      s_wpos[w][tid] = run;
-      run += wc[w];
-    }
-  }
-  __syncthreads();
-  if (!data) {
-    // ---- the look-back warp: exclusive prefix of every digit over the earlier tiles --------------------------------------------------
-    uint64_t excl[8];
-    bool done[8];
-#pragma unroll
-    for (int j = 0; j < 8; j++) { excl[j] = 0; done[j] = false; }
-    int64_t t = tile - 1;
-    while (t >= 0) {
-      uint64_t sv[LB_W][8];
-#pragma unroll
-      for (int i = 0; i < LB_W; i++)
-#pragma unroll
-        for (int j = 0; j < 8; j++) sv[i][j] = t - i >= 0 ? ld_status(status + (t - i) * 256 + j * 32 + lane) : tag_incl;
-      // how many of the LB_W tiles can every digit of every lane consume?  (stop after an inclusive prefix, or at an unpublished word)
-      int take = LB_W;
-      bool all_done_after = true;
-#pragma unroll
-      for (int j = 0; j < 8; j++) {
-        if (done[j]) continue;
-        int c = 0;
-        bool fin = false;
-#pragma unroll
-        for (int i = 0; i < LB_W; i++) {
-          if (fin || c < i) continue;
-          const uint64_t tag = sv[i][j] & ~RS2_VALUE_MASK;
-          if (tag == tag_incl) { c = i + 1; fin = true; }
-          else if (tag == tag_agg) c = i + 1;
-        }
-        if (!fin) { take = c < take ? c : take; all_done_after = false; }
-      }
-      // lanes advance together by the smallest count (the words of one tile are published together, so little is lost)
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const int ot = __shfl_xor_sync(0xffffffffu, take, o);
-        take = ot < take ? ot : take;
-      }
-      const bool warp_done = __all_sync(0xffffffffu, all_done_after);
-      const int use = warp_done ? LB_W : take;
-#pragma unroll
-      for (int j = 0; j < 8; j++) {
-        if (done[j]) continue;
-#pragma unroll
-        for (int i = 0; i < LB_W; i++) {
-          if (i < use && !done[j]) {
-            excl[j] += sv[i][j] & RS2_VALUE_MASK;
-            if ((sv[i][j] & ~RS2_VALUE_MASK) == tag_incl) done[j] = true;
-          }
-        }
-      }
-      if (warp_done) break;
-      t -= use;
-    }
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-      const int d = j * 32 + lane;
-      st_status(status + tile * 256 + d, tag_incl | (excl[j] + s_count[d]));
-      s_dst_off[d] = (int64_t)gbase[d] + (int64_t)excl[j] - (int64_t)s_bin_start[d];
-    }
-  } else {
-    // ---- data warps: rank (EARLY) and stage the tile in digit order ------------------------------------------------------------------
-    if (EARLY) {
-#pragma unroll
-      for (int k = 0; k < RS_ITEMS; k++) {
-        const uint32_t d = (uint32_t)((key[k] >> shift) & 0xff);
-        const uint32_t p = peers_of(k, d);
-        const int leader = __ffs(p) - 1;
-        uint32_t base = 0;
-        if (lane == leader) {
-          base = wp[d];
-          wp[d] = base + __popc(p);
-        }
-        base = __shfl_sync(0xffffffffu, base, leader < 0 ? lane : leader);
-        pos[k] = (uint16_t)(base + __popc(p & lt));
-        __syncwarp();
-      }
-#pragma unroll
-      for (int k = 0; k < RS_ITEMS; k++) {
-        if (full || seg + k * 32 + lane < tile_n) {
-          s_keys[pos[k]] = key[k];
-          s_vals[pos[k]] = val[k];
-        }
-      }
-    } else {
-#pragma unroll
-      for (int k = 0; k < RS_ITEMS; k++) {
-        if (full || seg + k * 32 + lane < tile_n) {
-          const uint32_t p = wp[(uint32_t)((key[k] >> shift) & 0xff)] + pos[k];
-          s_keys[p] = key[k];
-          s_vals[p] = val[k];
-        }
-      }
-    }
-  }
-  __syncthreads();
-  if (data) {
-#pragma unroll
-    for (int k = 0; k < RS_ITEMS; k++) {
-      const int p = k * DT + tid;
-      if (full || p < tile_n) {
-        const uint64_t kk = s_keys[p];
-        const int64_t dst = s_dst_off[(kk >> shift) & 0xff] + p;
-        out_keys[dst] = kk;
-        out_vals[dst] = s_vals[p];
-      }
-    }
-  }
+  if (tile_n == RS_TILE) rs_onesweep_tile<RS_THREADS, RS_ITEMS, true>(in_keys, in_vals, out_keys, out_vals, tile, tile_n, 8 * byte, gbase, status, rs_smem);
+  else rs_onesweep_tile<RS_THREADS, RS_ITEMS, false>(in_keys, in_vals, out_keys, out_vals, tile, tile_n, 8 * byte, gbase, status, rs_smem);
 }
 
 // Tiny inputs (the 4-row result of Q1, top-N candidates): one block ranks every element by counting -- rank = #keys smaller +
@@ -471,6 +270,7 @@ __global__ void __launch_bounds__(256) small_sort_kernel(uint64_t *keys, uint32_
 int radix_sort_pairs(uint64_t *keys, uint32_t *vals, int64_t n, cudaStream_t st, uint64_t *keys_alt, uint64_t **sorted_keys) {
   if (sorted_keys) *sorted_keys = keys;
   if (n <= 1) return 0;
+  SB_REQUIRE(n < (1ll << 32), "radix_sort_pairs: row ids and output positions are 32-bit");
   if (n <= SMALL_SORT_MAX) {
     small_sort_kernel<<<1, 256, 0, st>>>(keys, vals, (int)n);
     SB_LAUNCH_CHECK();
@@ -497,28 +297,17 @@ int radix_sort_pairs(uint64_t *keys, uint32_t *vals, int64_t n, cudaStream_t st,
     if (varies) bytes[passes++] = b;
   }
   if (passes == 0) return 0;
-  // tile geometry (sb_config_set("sort_variant", v) for experiments): threads x items; form 2 = dedicated look-back warp
-  struct Variant { const void *fn; int threads, items, form; };
+  // tile geometry (sb_config_set("sort_variant", v) for experiments): threads x items
+  struct Variant { const void *fn; int threads, items; };
   static const Variant variants[] = {
-      {(const void *)rs_onesweep_kernel<256, 16>, 256, 16, 1}, {(const void *)rs_onesweep_kernel<512, 8>, 512, 8, 1},
-      {(const void *)rs_onesweep_kernel<256, 8>, 256, 8, 1},   {(const void *)rs_onesweep_kernel<512, 16>, 512, 16, 1},
-      {(const void *)rs_onesweep_kernel<384, 12>, 384, 12, 1}, {(const void *)rs_onesweep_kernel<1024, 8>, 1024, 8, 1},
-      {(const void *)rs_onesweep2_kernel<384, 12, true, 2>, 384, 12, 2},    // 6
-      {(const void *)rs_onesweep2_kernel<384, 12, false, 2>, 384, 12, 2},   // 7
-      {(const void *)rs_onesweep2_kernel<416, 12, true, 2>, 416, 12, 2},    // 8
-      {(const void *)rs_onesweep2_kernel<320, 16, true, 2>, 320, 16, 2},    // 9
-      {(const void *)rs_onesweep2_kernel<544, 8, true, 2>, 544, 8, 2},      // 10
-      {(const void *)rs_onesweep2_kernel<384, 12, true, 4>, 384, 12, 2},    // 11
-      {(const void *)rs_onesweep2_kernel<288, 16, true, 2>, 288, 16, 2},    // 12
-      {(const void *)rs_onesweep2_kernel<1024, 8, true, 4>, 1024, 8, 2},    // 13: one block per SM
-  };
+      {(const void *)rs_onesweep_kernel<256, 16>, 256, 16}, {(const void *)rs_onesweep_kernel<512, 8>, 512, 8},
+      {(const void *)rs_onesweep_kernel<256, 8>, 256, 8},   {(const void *)rs_onesweep_kernel<512, 16>, 512, 16},
+      {(const void *)rs_onesweep_kernel<384, 12>, 384, 12}, {(const void *)rs_onesweep_kernel<1024, 8>, 1024, 8}};
   int vi = config().sort_variant;
   if (vi < 0 || vi >= (int)(sizeof(variants) / sizeof(variants[0]))) vi = 0;
   const Variant &V = variants[vi];
-  const int data_threads = V.form == 2 ? V.threads - 32 : V.threads;
-  const int tile_rows = data_threads * V.items;
-  const size_t smem = V.form == 2 ? (size_t)tile_rows * 12 + 256 * 8 + (size_t)(data_threads / 32) * 256 * 4 + 2 * 256 * 4
-                                  : (size_t)tile_rows * 12 + 256 * 8 + (size_t)(V.threads / 32) * 256 * 4 * 2 + 256 * 4;
+  const int tile_rows = V.threads * V.items;
+  const size_t smem = (size_t)tile_rows * 12 + 2 * 256 * 4 + (size_t)(V.threads / 32) * 256 * 4 * 2;
   SB_CUDA(cudaFuncSetAttribute(V.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t tiles = (n + tile_rows - 1) / tile_rows;
   Scratch keys2(keys_alt ? 16 : n * 8 + 16, st), vals2(n * 4 + 16, st), status(tiles * 256 * 8 + 16, st), tickets(8 * 4, st);
@@ -530,15 +319,13 @@ int radix_sort_pairs(uint64_t *keys, uint32_t *vals, int64_t n, cudaStream_t st,
     std::swap(iv, ov);
   }
   KernelTimer kt("sort_passes", st);
-  if (V.form == 2) SB_CUDA(cudaMemsetAsync(status.ptr, 0, (size_t)tiles * 256 * 8, st));   // once: the words carry the pass number
   for (int p = 0; p < passes; p++) {
-    if (V.form == 1) SB_CUDA(cudaMemsetAsync(status.ptr, 0, (size_t)tiles * 256 * 8, st));   // re-armed per pass (passes are stream-ordered)
+    SB_CUDA(cudaMemsetAsync(status.ptr, 0, (size_t)tiles * 256 * 8, st));   // one status array, re-armed per pass (passes are stream-ordered)
     const unsigned long long *gb = counts.as<unsigned long long>() + bytes[p] * 256;
     uint64_t *stp = status.as<uint64_t>();
     uint32_t *tk = tickets.as<uint32_t>() + p;
     int byte = bytes[p];
-    uint32_t epoch = (uint32_t)p + 1;
-    void *args[] = {&ik, &iv, &ok, &ov, (void *)&n, &byte, &gb, &stp, &tk, &epoch};   // form 1 ignores the last one
+    void *args[] = {&ik, &iv, &ok, &ov, (void *)&n, &byte, &gb, &stp, &tk};
     SB_CUDA(cudaLaunchKernel(V.fn, dim3((unsigned)tiles), dim3((unsigned)V.threads), args, smem, st));
     count_launch();
     std::swap(ik, ok);

@@ -185,9 +185,9 @@ def test_sorted_key_column_rebuilt_from_keys(gpu, stream, kind, asc):
     assert_tables_equal(_sort(one, [("k", asc, False)], stream), O.sort(one, [("k", asc, False)]), ordered=True)
 
 
-# every onesweep form / tile geometry (sb_config_set("sort_variant")) against the oracle: ragged sizes, full-range keys (8 passes) and
+# every onesweep tile geometry (sb_config_set("sort_variant")) against the oracle: ragged sizes, full-range keys (8 passes) and
 # heavily duplicated keys (tie order across tiles and warps)
-@pytest.mark.parametrize("variant", [0, 4, 6, 7, 8, 9, 10, 11, 12, 13])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
 def test_onesweep_variants_exact_order(gpu, stream, variant):
     from spark_b200 import _capi as capi
     prev = capi.config_get("sort_variant")

@@ -16,8 +16,7 @@ rng = np.random.default_rng(0)
 b = ColumnarBatch.from_numpy({"k": rng.integers(-2 ** 63, 2 ** 63 - 1, n)}, stream)
 stream.synchronize()
 srt = SortExec([("k", True, True)], LocalTableScanExec(b))
-names = ["256x16", "512x8", "256x8", "512x16", "384x12", "1024x8", "v2 384x12 early w2", "v2 384x12 late w2", "v2 416x12 early w2",
-         "v2 320x16 early w2", "v2 544x8 early w2", "v2 384x12 early w4", "v2 288x16 early w2", "v2 1024x8 early w4"]
+names = ["256x16", "512x8", "256x8", "512x16", "384x12", "1024x8"]
 only = [int(x) for x in sys.argv[1].split(",")] if len(sys.argv) > 1 else None
 profile_mode = len(sys.argv) > 2 and sys.argv[2] == "ncu"
 
