@@ -448,8 +448,8 @@ typedef struct sb_join_options {
   /* Runtime filters -- the reference's InjectRuntimeFilter (sql/catalyst/.../optimizer/InjectRuntimeFilter.scala:47-100) plans a
    * BloomFilterMightContain FilterExec on the application side of a join, built from the creation side's join key.  Here the creation
    * side is a single-key relation (sb_join_build*) and its prefilter (exact bitmap or Bloom) is tested on streamed column
-   * runtime_filter_cols[i] inside the join's candidate pass: streamed rows whose value cannot be a key of the relation (or is NULL)
-   * are not part of the input.  INNER / LEFT_SEMI only; like the reference's filter it may let non-members through, so it is only
+   * runtime_filter_cols[i] of the rows that survive the join's own candidate pass (short inputs: of every row): streamed rows whose
+   * value cannot be a key of the relation (or is NULL) are not part of the input.  INNER / LEFT_SEMI only; like the reference's filter it may let non-members through, so it is only
    * planned where a later inner join on that column drops them anyway. */
   int32_t n_runtime_filters;
   const int32_t *runtime_filter_cols;

@@ -162,15 +162,11 @@ __device__ __forceinline__ bool filter_test(const KeyFilter &f, uint64_t key) {
 
 // Runtime filters (the reference's InjectRuntimeFilter, sql/catalyst/.../optimizer/InjectRuntimeFilter.scala:47-100: a
 // BloomFilterMightContain FilterExec on the application side of a join, built from the creation side's join keys): here the filter
-// IS the prefilter of a single-key relation built on the creation side (exact bitmap or Bloom), tested inside the candidate pass on
-// one more streamed column -- loaded only for the rows the join's own prefilter lets through.
-constexpr int MAX_RUNTIME_FILTERS = 2;
-struct RuntimeFilters {
-  int n;
-  const void *col[MAX_RUNTIME_FILTERS];   // streamed column, NULL-free, 4 or 8 bytes wide (packed like a single join key of its type)
-  int width[MAX_RUNTIME_FILTERS];
-  KeyFilter f[MAX_RUNTIME_FILTERS];
-};
+// IS the prefilter of a single-key relation built on the creation side (exact bitmap or Bloom).  Long streamed sides: the join's own
+// candidate pass runs first and the filter is applied to the candidate LIST (runtime_filter_rows_kernel + a compaction) -- the extra
+// column is read only for the rows the join's prefilter let through.  Testing it inside the candidate pass was measured and dropped:
+// the straight-line test costs every row ~40 instructions (lineitem pass of Q5: 3.18 ms against 1.6 ms without it).  Short streamed
+// sides: a byte mask like a fused FilterExec's (runtime_filter_mask_kernel).
 
 typedef sb_hash_table::Slot JoinSlot;
 __device__ __forceinline__ void load_slot(const JoinSlot *p, uint64_t &key, uint32_t &row) {
@@ -478,10 +474,9 @@ __device__ __forceinline__ void join_key_rows(const JoinKeys &k, const int64_t (
   }
 }
 
-template <int KW, bool FULL, int CAND_STEP, bool RF = false>
+template <int KW, bool FULL, int CAND_STEP>
 __device__ __forceinline__ uint32_t candidate_step(const JoinKeys &k, int64_t n, const SimplePred &sp, const uint8_t *__restrict__ row_mask,
-                                                   const KeyFilter &kf, int mode, int64_t g0, int lane, uint32_t (&words)[CAND_STEP],
-                                                   const RuntimeFilters *rf = nullptr) {
+                                                   const KeyFilter &kf, int mode, int64_t g0, int lane, uint32_t (&words)[CAND_STEP]) {
   // rows of this lane: g0 + lane + 32 j.  FULL: the whole step lies below n, so nothing is clamped and the column pointers are
   // advanced once (the loads take constant offsets)
   const int64_t r0 = g0 + lane;
@@ -542,44 +537,6 @@ __device__ __forceinline__ uint32_t candidate_step(const JoinKeys &k, int64_t n,
 #pragma unroll
       for (int j = 0; j < CAND_STEP; j++) present[j] = present[j] && (w[j] & bb[j]) == bb[j];
     }
-    if (RF) {   // runtime filters (CAND_PRESENT only): one more column, read where the row is still alive
-#pragma unroll 1
-      for (int f = 0; f < rf->n; f++) {
-        const KeyFilter &g = rf->f[f];
-        uint64_t v[CAND_STEP];
-        if (rf->width[f] == 8) {
-          const uint64_t *p = (const uint64_t *)rf->col[f];
-#pragma unroll
-          for (int j = 0; j < CAND_STEP; j++) v[j] = present[j] ? __ldg(p + rr[j]) : 0ull;
-        } else {
-          const uint32_t *p = (const uint32_t *)rf->col[f];
-#pragma unroll
-          for (int j = 0; j < CAND_STEP; j++) v[j] = present[j] ? (uint64_t)__ldg(p + rr[j]) : 0ull;
-        }
-        if (g.exact) {
-          uint32_t w[CAND_STEP], d[CAND_STEP];
-#pragma unroll
-          for (int j = 0; j < CAND_STEP; j++) {
-            const uint64_t d64 = v[j] - g.fmin;
-            present[j] = present[j] && d64 < g.frange;
-            d[j] = (uint32_t)d64;
-            w[j] = present[j] ? __ldg(&g.words[d[j] >> 5]) : 0u;
-          }
-#pragma unroll
-          for (int j = 0; j < CAND_STEP; j++) present[j] = present[j] && ((w[j] >> (d[j] & 31)) & 1u);
-        } else {
-          uint32_t w[CAND_STEP], bb[CAND_STEP];
-#pragma unroll
-          for (int j = 0; j < CAND_STEP; j++) {
-            const uint64_t hh = join_mix(v[j]);
-            bb[j] = bloom_bits(hh);
-            w[j] = present[j] ? __ldg(&g.words[bloom_word(hh, g.mask)]) : 0u;
-          }
-#pragma unroll
-          for (int j = 0; j < CAND_STEP; j++) present[j] = present[j] && (w[j] & bb[j]) == bb[j];
-        }
-      }
-    }
     if (mode == CAND_PRESENT) {
 #pragma unroll
       for (int j = 0; j < CAND_STEP; j++) keep[j] = present[j];          // present implies keep
@@ -600,17 +557,15 @@ __device__ __forceinline__ uint32_t candidate_step(const JoinKeys &k, int64_t n,
   return count;
 }
 // the ragged last step of the input: kept out of line so that its clamping code costs the full steps no registers
-template <int KW, int CAND_STEP, bool RF>
+template <int KW, int CAND_STEP>
 __device__ __noinline__ uint32_t candidate_step_tail(const JoinKeys &k, int64_t n, const SimplePred &sp, const uint8_t *__restrict__ row_mask,
-                                                     const KeyFilter &kf, int mode, int64_t g0, int lane, uint32_t (&words)[CAND_STEP],
-                                                     const RuntimeFilters *rf) {
-  return candidate_step<KW, false, CAND_STEP, RF>(k, n, sp, row_mask, kf, mode, g0, lane, words, rf);
+                                                     const KeyFilter &kf, int mode, int64_t g0, int lane, uint32_t (&words)[CAND_STEP]) {
+  return candidate_step<KW, false, CAND_STEP>(k, n, sp, row_mask, kf, mode, g0, lane, words);
 }
-template <int KW, int CAND_STEP, int MINB, bool RF = false>
+template <int KW, int CAND_STEP, int MINB>
 __global__ void __launch_bounds__(JOIN_THREADS, MINB) join_candidate_strided_kernel(JoinKeys k, int64_t n, const __grid_constant__ SimplePred sp,
                                                                               const uint8_t *__restrict__ row_mask, KeyFilter kf, int mode,
-                                                                              uint32_t *__restrict__ bits_out, int32_t *__restrict__ block_counts,
-                                                                              const __grid_constant__ RuntimeFilters rf) {
+                                                                              uint32_t *__restrict__ bits_out, int32_t *__restrict__ block_counts) {
   __shared__ int32_t wsum[JOIN_THREADS / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int WARP_ROWS = CAND_TILE / (JOIN_THREADS / 32);
@@ -621,8 +576,8 @@ __global__ void __launch_bounds__(JOIN_THREADS, MINB) join_candidate_strided_ker
     const int64_t g0 = wbase + (int64_t)c * 32;
     if (g0 >= n) break;
     uint32_t words[CAND_STEP];
-    const uint32_t cnt = g0 + CAND_STEP * 32 <= n ? candidate_step<KW, true, CAND_STEP, RF>(k, n, sp, row_mask, kf, mode, g0, lane, words, &rf)
-                                                   : candidate_step_tail<KW, CAND_STEP, RF>(k, n, sp, row_mask, kf, mode, g0, lane, words, &rf);
+    const uint32_t cnt = g0 + CAND_STEP * 32 <= n ? candidate_step<KW, true, CAND_STEP>(k, n, sp, row_mask, kf, mode, g0, lane, words)
+                                                   : candidate_step_tail<KW, CAND_STEP>(k, n, sp, row_mask, kf, mode, g0, lane, words);
     mine += cnt;   // the same on every lane
 #pragma unroll
     for (int j = 0; j < CAND_STEP; j++)
@@ -744,6 +699,19 @@ __global__ void __launch_bounds__(JOIN_THREADS) runtime_filter_mask_kernel(JoinK
   if (have_mask && !mask[row]) return;
   uint64_t key;
   mask[row] = join_key(col, row, key) && filter_test(f, key) ? 1 : 0;   // might_contain(NULL) is NULL: the row is dropped
+}
+
+__global__ void __launch_bounds__(JOIN_THREADS) runtime_filter_rows_kernel(JoinKeys col, const int64_t *__restrict__ rows, int64_t nitems, KeyFilter f,
+                                                                           uint8_t *__restrict__ flags, int have_flags) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nitems) return;
+  if (have_flags && !flags[i]) return;
+  uint64_t key;
+  flags[i] = join_key(col, rows[i], key) && filter_test(f, key) ? 1 : 0;
+}
+__global__ void __launch_bounds__(JOIN_THREADS) take_rows_kernel(const int64_t *__restrict__ rows, const int64_t *__restrict__ idx, int64_t m, int64_t *__restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m) out[i] = rows[idx[i]];
 }
 
 static KeyFilter key_filter_of(const sb_hash_table *ht) {
@@ -1118,8 +1086,6 @@ int sb_join_probe_ex(const sb_hash_table *ht, const sb_table *probe, const int32
     if (!pred_in_pass) sp.nterms = 0;
   }
   // runtime filters (InjectRuntimeFilter): inside the candidate pass when they can be, else folded into the byte mask
-  RuntimeFilters rfs;
-  rfs.n = 0;
   std::vector<JoinKeys> rf_keys;
   std::vector<KeyFilter> rf_filters;
   if (opt && opt->n_runtime_filters > 0) {
@@ -1139,19 +1105,8 @@ int sb_join_probe_ex(const sb_hash_table *ht, const sb_table *probe, const int32
       rf_filters.push_back(key_filter_of(r));
     }
   }
-  bool rf_in_pass = !rf_keys.empty() && use_cand && config().join_cand == 2 && cand_mode == CAND_PRESENT && (int)rf_keys.size() <= MAX_RUNTIME_FILTERS;
-  for (auto &jk : rf_keys) {
-    const int32_t t = jk.type[0];
-    if (jk.valid[0] || !(t == SB_INT32 || t == SB_DATE32 || t == SB_INT64 || t == SB_TIMESTAMP || t == SB_DECIMAL64)) rf_in_pass = false;
-  }
-  if (rf_in_pass)
-    for (size_t i = 0; i < rf_keys.size(); i++) {
-      rfs.col[rfs.n] = rf_keys[i].data[0];
-      rfs.width[rfs.n] = rf_keys[i].bits[0] / 8;
-      rfs.f[rfs.n] = rf_filters[i];
-      rfs.n++;
-    }
-  const bool rf_mask = !rf_keys.empty() && !rf_in_pass;
+  const bool rf_post = !rf_keys.empty() && use_cand && cand_mode == CAND_PRESENT;   // on the candidate list, after the pass
+  const bool rf_mask = !rf_keys.empty() && !rf_post;
   const bool pred_mask = probe_filter && !pred_in_pass;
   Scratch pmask(pred_mask || rf_mask ? n + 16 : 0, st);
   if (pred_mask && n > 0) eval_predicate(probe, *probe_filter, pmask.as<uint8_t>(), st);
@@ -1177,15 +1132,12 @@ int sb_join_probe_ex(const sb_hash_table *ht, const sb_table *probe, const int32
       const int kw = !int_key ? 0 : (k.bits[0] == 64 ? 8 : k.bits[0] == 32 ? 4 : 0);
       uint32_t *bo = bits.as<uint32_t>();
       int32_t *bc = bcount.as<int32_t>();
-#define SB_CAND(KW, STEP, MINB) join_candidate_strided_kernel<KW, STEP, MINB><<<cb, JOIN_THREADS, 0, st>>>(k, n, sp, pmask_dev, kf, cand_mode, bo, bc, rfs)
-#define SB_CAND_RF(KW) join_candidate_strided_kernel<KW, 4, 3, true><<<cb, JOIN_THREADS, 0, st>>>(k, n, sp, pmask_dev, kf, cand_mode, bo, bc, rfs)
+#define SB_CAND(KW, STEP, MINB) join_candidate_strided_kernel<KW, STEP, MINB><<<cb, JOIN_THREADS, 0, st>>>(k, n, sp, pmask_dev, kf, cand_mode, bo, bc)
       const int v = config().join_cand;   // 1: 8 rows per lane and step; 2: 4 rows, 4 blocks / SM; 3: 8 rows, 3 blocks / SM
-      if (rfs.n > 0) { if (kw == 8) SB_CAND_RF(8); else if (kw == 4) SB_CAND_RF(4); else SB_CAND_RF(0); }
-      else if (v == 2) { if (kw == 8) SB_CAND(8, 4, 4); else if (kw == 4) SB_CAND(4, 4, 4); else SB_CAND(0, 4, 4); }
+      if (v == 2) { if (kw == 8) SB_CAND(8, 4, 4); else if (kw == 4) SB_CAND(4, 4, 4); else SB_CAND(0, 4, 4); }
       else if (v == 3) { if (kw == 8) SB_CAND(8, 8, 3); else if (kw == 4) SB_CAND(4, 8, 3); else SB_CAND(0, 8, 3); }
       else { if (kw == 8) SB_CAND(8, 8, 1); else if (kw == 4) SB_CAND(4, 8, 1); else SB_CAND(0, 8, 1); }
 #undef SB_CAND
-#undef SB_CAND_RF
     } else {
       join_candidate_kernel<<<cb, JOIN_THREADS, 0, st>>>(k, n, sp, pmask_dev, kf, cand_mode, fast_key, bits.as<uint16_t>(), bcount.as<int32_t>());
     }
@@ -1197,6 +1149,22 @@ int sb_join_probe_ex(const sb_hash_table *ht, const sb_table *probe, const int32
     if (nitems > 0) {
       candidate_rows_kernel<<<cb, JOIN_THREADS, 0, st>>>(bits.as<uint16_t>(), nwords, boff.as<int64_t>(), cand_rows->as<int64_t>());
       SB_LAUNCH_CHECK();
+    }
+    if (rf_post && nitems > 0) {   // runtime filters over the candidate list: flags -> compaction -> the surviving rows, still in row order
+      Scratch flags(nitems + 16, st), idx(nitems * 8 + 16, st);
+      const unsigned fb = (unsigned)((nitems + JOIN_THREADS - 1) / JOIN_THREADS);
+      for (size_t i = 0; i < rf_keys.size(); i++) {
+        runtime_filter_rows_kernel<<<fb, JOIN_THREADS, 0, st>>>(rf_keys[i], cand_rows->as<int64_t>(), nitems, rf_filters[i], flags.as<uint8_t>(), i > 0 ? 1 : 0);
+        SB_LAUNCH_CHECK();
+      }
+      const int64_t m = compact_mask(flags.as<uint8_t>(), nitems, idx.as<int64_t>(), st);
+      std::unique_ptr<Scratch> kept(new Scratch(m * 8 + 16, st));
+      if (m > 0) {
+        take_rows_kernel<<<(unsigned)((m + JOIN_THREADS - 1) / JOIN_THREADS), JOIN_THREADS, 0, st>>>(cand_rows->as<int64_t>(), idx.as<int64_t>(), m, kept->as<int64_t>());
+        SB_LAUNCH_CHECK();
+      }
+      cand_rows = std::move(kept);
+      nitems = m;
     }
     nb = (unsigned)((nitems + JOIN_THREADS - 1) / JOIN_THREADS);
   }
