@@ -85,6 +85,10 @@ class ProjectExec(SparkPlan):
         child = self.child
         if isinstance(child, FilterExec):
             cond, child = child.condition, child.child
+        if cond is None and isinstance(child, BroadcastHashJoinExec) and child.condition is None:
+            # ColumnPruning (sql/catalyst/.../optimizer/Optimizer.scala, object ColumnPruning) would have put this projection below the
+            # join as well: the join materialises only the attributes somebody above it reads
+            child.requiredOutput = {a for _, e in self.projectList for a in e.references()}
         inp = child.executeColumnar(stream)
         try:
             return _filter_project(inp, cond, self.projectList, stream)
@@ -147,6 +151,15 @@ class HashAggregateExec(SparkPlan):
         return names
 
     def executeColumnar(self, stream=None):
+        if isinstance(self.child, BroadcastHashJoinExec) and self.child.condition is None and self.mode not in ("final", "partial_merge"):
+            # ColumnPruning: the join below materialises only what the aggregate reads
+            need = set(self.groupingExpressions)
+            for fn, _ in self.aggregateExpressions:
+                if fn.child is not None:
+                    need |= fn.child.references()
+            if self.condition is not None:
+                need |= self.condition.references()
+            self.child.requiredOutput = need
         inp = self.child.executeColumnar(stream)
         try:
             return self.run(inp, stream)
@@ -606,6 +619,7 @@ class BroadcastHashJoinExec(SparkPlan):
 
     def __init__(self, leftKeys, rightKeys, joinType, buildSide, left: SparkPlan, right: SparkPlan, condition=None, runtimeFilters=None):
         self.runtimeFilters = list(runtimeFilters or [])    # on the STREAMED side (inner / left semi joins)
+        self.requiredOutput = None                          # attribute names read above the join (set by the ProjectExec over it)
         self.leftKeys, self.rightKeys = list(leftKeys), list(rightKeys)
         table = _STREAM_LEFT if buildSide == "right" else _STREAM_RIGHT
         if buildSide not in ("left", "right") or joinType not in table:
@@ -623,8 +637,12 @@ class BroadcastHashJoinExec(SparkPlan):
         fuse = self.condition is None and self.native_type not in ("existence", "left_anti_null_aware")
         b_src, b_cond, b_names = _peel(build_plan) if fuse else (build_plan, None, None)
         s_src, s_cond, s_names = _peel(stream_plan) if fuse else (stream_plan, None, None)
+        need = self.requiredOutput if fuse else None
         build = b_src.executeColumnar(stream)
         try:
+            if need is not None:
+                b_all = b_names if b_names is not None else build.names
+                b_names = [n for n in b_all if n in need] or b_all[:1]      # never a table without columns
             rel = HashedRelation(build, build_keys, stream, b_cond, b_names)
         finally:
             build.close()
@@ -638,6 +656,9 @@ class BroadcastHashJoinExec(SparkPlan):
                     cb.close()
             probe = s_src.executeColumnar(stream)
             try:
+                if need is not None:
+                    s_all = s_names if s_names is not None else probe.names
+                    s_names = [n for n in s_all if n in need] or s_all[:1]
                 out = probe_join(rel, probe, stream_keys, self.native_type, stream, self.condition, probe_filter=s_cond, probe_out=s_names,
                                  runtime_filters=rf_rels)
             finally:
