@@ -864,7 +864,12 @@ int sb_join_build_filtered(const sb_table *build, const int32_t *key_cols, int32
   ht->cap = cap;
   int64_t bwords = 1024;
   const uint64_t range = nin > 0 ? (uint64_t)stats[1] - (uint64_t)stats[0] + 1 : 0;
-  if (nin > 0 && range != 0 && range <= (1ull << 31) && (range <= (1ull << 23) || range <= 64ull * (uint64_t)nin)) {
+  // exact bitmap: dense keys, small ranges -- and SORTED sparse keys up to a 128 MB bitmap: keys that arrive in ascending order come
+  // from a key-ordered scan, whose foreign-key side is usually clustered on the same key (lineitem by l_orderkey) and then walks the
+  // bitmap sequentially, where a Bloom filter costs every streamed row a hash and a random L2 access (Q5's lineitem pass against
+  // 4.6 M order keys spread over a range of 600 M: 2.7 ms with the Bloom filter)
+  if (nin > 0 && range != 0 && range <= (1ull << 31) &&
+      (range <= (1ull << 23) || range <= 64ull * (uint64_t)nin || (ascending && range <= (1ull << 30)))) {
     ht->exact = 1;
     ht->fmin = (uint64_t)stats[0];
     ht->frange = range;

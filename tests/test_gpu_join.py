@@ -200,6 +200,23 @@ def test_long_streamed_side_goes_through_the_candidate_pass(gpu, stream, how, ke
             assert np.all(r[1:] >= r[:-1])
 
 
+@pytest.mark.parametrize("how", ["inner", "left_outer", "left_semi", "left_anti"])
+@pytest.mark.parametrize("npr", [40_000, (1 << 20) + 555])
+def test_sparse_sorted_relation_keeps_the_exact_bitmap(gpu, stream, how, npr):
+    """Ascending build keys spread thinly over a wide range (more than 64 bits of range per key, more than 2^23 in all): still an exact
+    bitmap + rank prefix (csrc/join.cu: sorted sparse keys up to a 128 MB bitmap), probed by a short side and through the candidate pass."""
+    rng = np.random.default_rng(npr)
+    nb = 20_000
+    bk = np.sort(rng.choice(np.arange(7, 1000 * nb, dtype=np.int64), nb, replace=False))
+    build = pa.table({"id": pa.array(bk, type=pa.int64()), "payload": np.arange(nb, dtype=np.int64)})
+    fk = np.where(rng.random(npr) < 0.3, bk[rng.integers(0, nb, npr)], rng.integers(-5, 1000 * nb + 5, npr))
+    probe = pa.table({"fk": pa.array(fk, type=pa.int64(), mask=rng.random(npr) < 0.02), "row": np.arange(npr, dtype=np.int64)})
+    got = _plan_join(probe, build, ["fk"], ["id"], how, stream)
+    want = O.hash_join(probe, build, ["fk"], ["id"], how)
+    assert got.num_rows == want.num_rows
+    assert_tables_equal(got, want, key_cols=list(want.column_names))
+
+
 @pytest.mark.parametrize("how", ["inner", "left_outer", "left_semi", "left_anti", "full_outer", "right_outer", "existence"])
 def test_short_streamed_side_over_a_sorted_relation(gpu, stream, how):
     """Build keys in strictly ascending order (a key-ordered scan, the output of a join over one): the relation is a bitmap + rank
