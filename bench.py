@@ -123,8 +123,8 @@ def ncu_traffic(kernel, rows):
     return {"traffic": int(rec["dram_bytes"]), "traffic_note": "from %s" % rec.get("source")}
 
 
-def host_threads():
-    """Threads the CPU arm may really use: the affinity mask capped by the cgroup's CPU quota (cpu.max)."""
+def host_threads(share=1):
+    """Threads the CPU arm may really use: the affinity mask capped by this process's share (1 / share) of the cgroup's CPU quota (cpu.max)."""
     try:
         n = len(os.sched_getaffinity(0))
     except AttributeError:
@@ -132,15 +132,15 @@ def host_threads():
     try:
         quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
         if quota != "max":
-            n = max(1, min(n, int(math.ceil(int(quota) / int(period)))))
+            n = max(1, min(n, int(math.ceil(int(quota) / int(period))) // share))
     except Exception:
         pass
     return n
 
 
-def _omp_setup():
+def _omp_setup(share=1):
     """torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every thread the cgroup grants, spread over the sockets."""
-    nt = host_threads()
+    nt = host_threads(share)
     os.environ["OMP_NUM_THREADS"] = str(nt)
     os.environ.setdefault("OMP_PROC_BIND", "spread")
     os.environ.setdefault("OMP_PLACES", "cores")
@@ -320,9 +320,23 @@ def main():
         return
     if world == 1:
         args.legs = [x for x in args.legs if x != "shuffle"]
-    nt = _omp_setup()                  # before any OpenMP runtime is loaded
+    partitioned = False
     if world > 1:
-        nt = max(1, nt // world)       # every rank checks its own shard against the oracle at the same time
+        # One rank per GPU on ONE host: give every rank its own block of the CPUs the job may use, before any OpenMP runtime loads.
+        # With OMP_PROC_BIND every rank's master thread is bound to the FIRST place of its mask -- with a shared mask that is the same
+        # core for all ranks, and the host threads (which spin in cudaStreamSynchronize between operators) then time-slice it: measured
+        # at N = 4 before this fix, Q1 took 18 ms per step with 4.3 ms of kernels (gpurun_out r26 -> profiles/r02_bench_n4_shared_mask.json).
+        try:
+            cpus = sorted(os.sched_getaffinity(0))
+            per = len(cpus) // world
+            if per >= 1:
+                os.sched_setaffinity(0, cpus[local_rank * per:(local_rank + 1) * per])
+                partitioned = True
+        except (AttributeError, OSError):
+            pass
+    nt = _omp_setup(world)             # before any OpenMP runtime is loaded; every rank checks its own shard against the oracle at the same time
+    if world > 1 and not partitioned:  # shared mask: at least do not oversubscribe it
+        nt = max(1, min(nt, len(os.sched_getaffinity(0)) // world))
         os.environ["OMP_NUM_THREADS"] = str(nt)
 
     import pyarrow as pa
