@@ -162,3 +162,30 @@ def test_runtime_filter_injection_rule():
     j2d = BroadcastHashJoinExec(["l_suppkey"], ["s_suppkey"], "inner", "right", j1d, sup_f)
     B200ColumnarRule().injectRuntimeFilters(j2d)
     assert j1d.runtimeFilters == []
+
+
+def test_column_pruning_hints_reach_the_join():
+    """ColumnPruning's effect on a join (Optimizer.scala, object ColumnPruning): the ProjectExec / HashAggregateExec directly above a
+    join tells it which attributes are read, so only those are materialised (BroadcastHashJoinExec.requiredOutput)."""
+    from spark_b200.expressions import Literal, Sum, col
+    from spark_b200.execution import BroadcastHashJoinExec, HashAggregateExec, ProjectExec, SparkPlan
+
+    seen = {}
+
+    class Leaf(SparkPlan):
+        pass
+
+    class Probe(BroadcastHashJoinExec):
+        def executeColumnar(self, stream=None):
+            seen["need"] = self.requiredOutput
+            raise StopIteration          # nothing to run on a CPU-only machine: the hint is what is under test
+
+    j = Probe(["a"], ["b"], "inner", "right", Leaf(), Leaf())
+    for plan in (ProjectExec(["x", ("y", col("p") * (Literal(1) - col("d")))], j),
+                 HashAggregateExec(["k"], [(Sum(col("p") * col("d")), "s")], j, mode="partial", condition=col("z") > Literal(3))):
+        seen.clear()
+        try:
+            plan.executeColumnar(None)
+        except StopIteration:
+            pass
+        assert seen["need"] == ({"x", "p", "d"} if isinstance(plan, ProjectExec) else {"k", "p", "d", "z"}), seen
