@@ -78,10 +78,12 @@ typedef struct sb_column {
 /* Streams and ordering.  Every operator takes the sb_stream of the calling task thread and is STREAM-ORDERED on it: its kernels,
  * copies and the allocation / release of its temporaries are enqueued there, and tables it returns may be consumed by later
  * calls on the SAME stream without any synchronisation.  Operators that size their result on the host (filter, join, aggregate,
- * partition, exchange) have synchronised the stream once before returning; the others (sort, gather-only paths, import) have
- * not.  To hand a table or a hash table to ANOTHER stream or thread, call sb_stream_synchronize on the producing stream first
- * (sb_join_build* returns synchronised: a broadcast relation is shared by the tasks of an executor).  sb_table_import_host
- * reads the host buffers asynchronously when they are pinned: keep them alive until the stream is synchronised. */
+ * partition, exchange) synchronise the stream where they read the size back, not when they return: the kernels that fill the
+ * result may still be running.  To hand a TABLE to another stream or thread, call sb_stream_synchronize on the producing stream
+ * first.  A HASH TABLE (a broadcast relation is shared by the tasks of an executor) carries an event recorded at the end of its
+ * build: sb_join_probe* on any other stream waits for it on the device, the host never does; release it only after the probes
+ * that use it have been enqueued on streams that will outlive them.  sb_table_import_host reads the host buffers asynchronously
+ * when they are pinned: keep them alive until the stream is synchronised. */
 typedef struct sb_table sb_table;             /* ColumnarBatch resident in HBM */
 typedef struct sb_stream sb_stream;           /* one per Spark task thread (CUDA stream + scratch) */
 typedef struct sb_hash_table sb_hash_table;   /* HashedRelation resident in HBM */

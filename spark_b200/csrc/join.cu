@@ -65,6 +65,7 @@ struct sb_hash_table {
   sb_table *key_table = nullptr;      // retained table the build key columns live in (the build table or its encoded view)
   int32_t key_table_col[4] = {0, 0, 0, 0};
   cudaStream_t st = nullptr;
+  cudaEvent_t ready = nullptr;        // recorded on `st` when the build's device work has been enqueued: probes on OTHER streams wait for it
 };
 
 namespace sb {
@@ -937,13 +938,17 @@ int sb_join_build_filtered(const sb_table *build, const int32_t *key_cols, int32
     }
     ht->build = const_cast<sb_table *>(build);
     ht->build->refs.fetch_add(1);
-    SB_CUDA(cudaStreamSynchronize(st));   // a relation is handed to other task threads / streams (broadcast): complete on return
+    // a relation is handed to other task threads / streams (broadcast): instead of draining the stream here, the build leaves an
+    // event behind and every consumer on another stream waits for it on the device (wait_relation)
+    SB_CUDA(cudaEventCreateWithFlags(&ht->ready, cudaEventDisableTiming));
+    SB_CUDA(cudaEventRecord(ht->ready, st));
   } catch (...) {
     if (ht->slots) cudaFreeAsync(ht->slots, st);
     if (ht->null_key_flag) cudaFreeAsync(ht->null_key_flag, st);
     if (ht->bloom) cudaFreeAsync(ht->bloom, st);
     if (ht->row_of) cudaFreeAsync(ht->row_of, st);
     if (ht->rank) cudaFreeAsync(ht->rank, st);
+    if (ht->ready) cudaEventDestroy(ht->ready);
     if (ht->key_table && ht->key_table->refs.fetch_sub(1) == 1) table_free(ht->key_table);
     for (int i = 0; i < 4; i++)
       if (ht->has_dict[i]) column_release(ht->dict[i]);
@@ -966,6 +971,7 @@ int sb_hash_table_release(sb_hash_table *ht) {
     if (ht->bloom) cudaFreeAsync(ht->bloom, ht->st);
     if (ht->row_of) cudaFreeAsync(ht->row_of, ht->st);
     if (ht->rank) cudaFreeAsync(ht->rank, ht->st);
+    if (ht->ready) cudaEventDestroy(ht->ready);
     if (ht->key_table && ht->key_table->refs.fetch_sub(1) == 1) table_free(ht->key_table);
     if (ht->build && ht->build->refs.fetch_sub(1) == 1) table_free(ht->build);
     for (int i = 0; i < 4; i++)
@@ -986,6 +992,11 @@ __global__ void unmatched_kernel(const uint8_t *__restrict__ matched, int64_t n,
 __global__ void fill_i64_kernel(int64_t *out, int64_t n, int64_t v) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = v;
+}
+
+// device-side ordering between a relation's build and a consumer on another stream (same stream: already ordered)
+static void wait_relation(const sb_hash_table *ht, cudaStream_t st) {
+  if (ht->ready && st != ht->st) SB_CUDA(cudaStreamWaitEvent(st, ht->ready, 0));
 }
 
 // a zero-copy view of `t` restricted to `cols` (NULL: all columns); the caller frees it with table_free
@@ -1033,6 +1044,7 @@ int sb_join_probe_ex(const sb_hash_table *ht, const sb_table *probe, const int32
   SB_REQUIRE(nkeys == ht->nkeys, "probe has %d key columns, the relation was built on %d", nkeys, ht->nkeys);
   SB_REQUIRE(join_type >= SB_JOIN_INNER && join_type <= SB_JOIN_LEFT_ANTI_NULL_AWARE, "unknown join type %d", join_type);
   cudaStream_t st = stream_of(s);
+  wait_relation(ht, st);
   const int64_t n = probe->nrows, nbuild = ht->build->nrows;
   EncodedView key_view;
   JoinKeys k = make_join_keys(probe_key_source(ht, probe, key_cols, nkeys, st, key_view), key_cols, nkeys, ht);
@@ -1100,6 +1112,7 @@ int sb_join_probe_ex(const sb_hash_table *ht, const sb_table *probe, const int32
     for (int i = 0; i < opt->n_runtime_filters; i++) {
       const sb_hash_table *r = opt->runtime_filter_relations[i];
       SB_REQUIRE(r, "runtime filter %d: null relation", i);
+      wait_relation(r, st);
       if (r->nkeys != 1 || r->wide || r->has_dict[0]) fail(SB_ERR_UNSUPPORTED, "runtime filter %d: the creation side must be a relation on one fixed-width key", i);
       if (!r->bloom) continue;   // a relation without a prefilter: the filter is an optimisation, leaving it out changes nothing
       const int32_t c = opt->runtime_filter_cols[i];
@@ -1236,7 +1249,6 @@ int sb_join_probe_ex(const sb_hash_table *ht, const sb_table *probe, const int32
       table_free(right);
     }
     *out = left;
-    SB_CUDA(cudaStreamSynchronize(st));
     return SB_OK;
   }
   Scratch counts(nitems * 4 + 16, st), first(nitems * 4 + 16, st), block_counts((int64_t)nb * 4 + 16, st), offsets((int64_t)nb * 8 + 16, st);
@@ -1263,7 +1275,6 @@ int sb_join_probe_ex(const sb_hash_table *ht, const sb_table *probe, const int32
       throw;
     }
     *out = t;
-    SB_CUDA(cudaStreamSynchronize(st));
     return SB_OK;
   }
   exclusive_scan_i32_to_i64(block_counts.as<int32_t>(), offsets.as<int64_t>(), nb, total.as<int64_t>(), st);
@@ -1310,7 +1321,6 @@ int sb_join_probe_ex(const sb_hash_table *ht, const sb_table *probe, const int32
     table_free(right);
     *out = left;
   }
-  SB_CUDA(cudaStreamSynchronize(st));
   SB_API_END
 }
 

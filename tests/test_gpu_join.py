@@ -310,3 +310,28 @@ def test_runtime_filter_rejected_on_outer_joins(gpu, stream):
                                  runtimeFilters=[RuntimeFilter("k", "k", LocalTableScanExec(b[2]))])
     with pytest.raises(capi.SparkB200Error):
         plan.collect(stream)
+
+
+def test_relation_built_on_one_stream_probed_on_another(gpu):
+    """sb_join_build* leaves an event behind instead of draining its stream; a probe on ANOTHER stream must wait for it on the device
+    (include/spark_b200.h, "Streams and ordering").  The build is long enough to still be running when the probe is enqueued."""
+    from spark_b200.columnar import ColumnarBatch, Stream
+    from spark_b200.execution import HashedRelation, probe_join
+    rng = np.random.default_rng(1234)
+    nb, npr = 4_000_000, 300_000
+    bk = rng.permutation(8 * nb)[:nb].astype(np.int64)
+    build = pa.table({"id": bk, "payload": np.arange(nb, dtype=np.int64)})
+    probe = pa.table({"fk": rng.integers(0, 8 * nb, npr), "row": np.arange(npr, dtype=np.int64)})
+    want = O.hash_join(probe, build, ["fk"], ["id"], "inner")
+    for _ in range(3):
+        s1, s2 = Stream(), Stream()
+        bb = ColumnarBatch.from_arrow(build, s1)
+        pb = ColumnarBatch.from_arrow(probe, s2)
+        rel = HashedRelation(bb, ["id"], s1)
+        out = probe_join(rel, pb, ["fk"], "inner", s2)
+        got = out.to_arrow(s2)
+        s1.synchronize()
+        for x in (out, rel, pb, bb):
+            x.close()
+        assert got.num_rows == want.num_rows
+        assert_tables_equal(got, want, key_cols=list(want.column_names))
