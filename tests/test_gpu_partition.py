@@ -33,7 +33,7 @@ def _mixed_table(n, seed=42, nulls=True):
 
 
 @pytest.mark.parametrize("keys", [["i32"], ["i64"], ["f64"], ["f32"], ["s"], ["b", "i8", "i16"], ["d", "i64", "s", "f64"]])
-@pytest.mark.parametrize("nparts", [1, 7, 200, 2048])
+@pytest.mark.parametrize("nparts", [1, 7, 200, 256, 2048])
 def test_partition_ids_bit_exact(gpu, stream, keys, nparts):
     from spark_b200.columnar import ColumnarBatch
     from spark_b200.execution import HashPartitioning, ShuffleExchangeExec, LocalTableScanExec
@@ -46,7 +46,7 @@ def test_partition_ids_bit_exact(gpu, stream, keys, nparts):
 
 
 @pytest.mark.parametrize("n", [0, 1, 31, 32, 33, 1000, 100003])
-@pytest.mark.parametrize("nparts", [1, 5, 200, 2048])
+@pytest.mark.parametrize("nparts", [1, 5, 200, 256, 2048])
 def test_hash_partition_stable_regrouping(gpu, stream, n, nparts):
     from spark_b200.columnar import ColumnarBatch
     from spark_b200.execution import HashPartitioning, ShuffleExchangeExec, LocalTableScanExec

@@ -299,7 +299,7 @@ def test_exchange_statistics_and_coalesced_read(one_rank_comm, stream):
     assert sorted(rows) == list(range(n))
 
 
-@pytest.mark.parametrize("nparts", [1, 7, 200, 2048])
+@pytest.mark.parametrize("nparts", [1, 7, 200, 256, 2048])
 def test_fused_exchange_on_a_one_rank_communicator(one_rank_comm, stream, nparts):
     """sb_shuffle_exchange (the multisplit's stores go straight into the receive window, then one local split) on a one-rank NCCL
     communicator: the window, the REMOTE scatter kernel, the barrier and the receiver-side split all run; the rank owns every
