@@ -18,6 +18,9 @@
 package org.apache.spark.sql.b200
 
 import org.apache.spark.sql.SparkSessionExtensions
+import org.apache.spark.sql.catalyst.expressions.Attribute
+import org.apache.spark.sql.catalyst.optimizer.BuildRight
+import org.apache.spark.sql.catalyst.plans.{Inner, LeftSemi}
 import org.apache.spark.sql.catalyst.rules.Rule
 import org.apache.spark.sql.execution._
 import org.apache.spark.sql.execution.aggregate.{HashAggregateExec, SortAggregateExec}
@@ -40,7 +43,8 @@ class B200SparkExtensions extends (SparkSessionExtensions => Unit) {
  */
 object B200ColumnarRule extends ColumnarRule {
   override def preColumnarTransitions: Rule[SparkPlan] = new Rule[SparkPlan] {
-    def apply(plan: SparkPlan): SparkPlan = plan.transformUp {
+    def apply(plan: SparkPlan): SparkPlan = injectRuntimeFilters(replaceOperators(plan))
+    private def replaceOperators(plan: SparkPlan): SparkPlan = plan.transformUp {
       case agg: HashAggregateExec if GpuSupport.supports(agg) =>
         val collapsed = GpuSupport.collapse(agg)          // (condition, aggregate inputs over source attributes, source plan)
         GpuHashAggregateExec(agg, collapsed.condition, collapsed.inputs, collapsed.source)
@@ -67,6 +71,40 @@ object B200ColumnarRule extends ColumnarRule {
       case f: FilterExec if GpuSupport.supports(f) => GpuFilterProjectExec(Some(f.condition), f.output, f.child)
       case p: ProjectExec if GpuSupport.supports(p) => GpuFilterProjectExec(None, p.projectList, p.child)
     }
+  }
+
+  /**
+   * Runtime filters on the physical plan (the rule the reference runs on the logical plan: InjectRuntimeFilter.scala:196-260, 411-460).
+   * An inner broadcast join J2 whose streamed side is (filters / projections of bare attributes over) another inner or left-semi
+   * join J1, and whose build side sits under a selective predicate: rows of J1's STREAMED input whose J2 key cannot be a key of J2's
+   * build side never reach the output, so J1 tests that key against the relation's prefilter (GpuRuntimeFilter).  At most two per join.
+   */
+  def injectRuntimeFilters(plan: SparkPlan): SparkPlan = plan.transformUp {
+    case j2: GpuHashJoinExec if j2.broadcast && j2.joinType == Inner && j2.condition.isEmpty =>
+      val (build, streamed, buildKeys, streamKeys) =
+        if (j2.buildSide == BuildRight) (j2.right, j2.left, j2.rightKeys, j2.leftKeys) else (j2.left, j2.right, j2.leftKeys, j2.rightKeys)
+      def selective(p: SparkPlan): Boolean = p.isInstanceOf[FilterExec] ||
+        (p match { case f: GpuFilterProjectExec => f.condition.isDefined; case _ => false }) || p.children.exists(selective)
+      def passThrough(p: SparkPlan): Option[GpuHashJoinExec] = p match {
+        case j1: GpuHashJoinExec => Some(j1)
+        case f: GpuFilterProjectExec if streamKeys.forall(k => f.projectList.exists(n => n.isInstanceOf[Attribute] && n.semanticEquals(k))) =>
+          passThrough(f.child)
+        case _ => None
+      }
+      passThrough(streamed) match {
+        case Some(j1) if selective(build) && j1.condition.isEmpty && (j1.joinType == Inner || j1.joinType == LeftSemi) =>
+          val j1Streamed = if (j1.buildSide == BuildRight) j1.left else j1.right
+          val filters = streamKeys.zip(buildKeys).collect {
+            case (s: Attribute, b: Attribute) if j1Streamed.outputSet.contains(s) => GpuRuntimeFilter(s, b, build)
+          }.take(2 - j1.runtimeFilters.length)
+          if (filters.isEmpty) j2
+          else {
+            val j1f = j1.copy(runtimeFilters = j1.runtimeFilters ++ filters)
+            val rewritten = streamed.transformDown { case x if x eq j1 => j1f }
+            if (j2.buildSide == BuildRight) j2.copy(left = rewritten) else j2.copy(right = rewritten)
+          }
+        case _ => j2
+      }
   }
 
   override def postColumnarTransitions: Rule[SparkPlan] = new Rule[SparkPlan] {

@@ -146,6 +146,15 @@ case class GpuTakeOrderedAndProjectExec(limit: Int, sortOrder: Seq[SortOrder], p
 }
 
 /**
+ * What InjectRuntimeFilter (sql/catalyst/.../optimizer/InjectRuntimeFilter.scala:47-100) plans as
+ * FilterExec(BloomFilterMightContain(bloomSubquery, xxhash64(applicationKey))) on the application side of a join: here the
+ * creation side (a GpuBroadcastExchangeExec shared with the join the filter was derived from) is built into a single-key
+ * relation and its prefilter is tested on `applicationKey` of the STREAMED side of the join that carries the filter
+ * (sb_join_options.runtime_filter_cols / runtime_filter_relations).  Planned by B200ColumnarRule.injectRuntimeFilters.
+ */
+case class GpuRuntimeFilter(applicationKey: Attribute, creationKey: Attribute, creation: SparkPlan)
+
+/**
  * BroadcastHashJoinExec / ShuffledHashJoinExec / SortMergeJoinExec (SQLX/joins/HashJoin.scala:184-400) as build + probe.
  * The build side is the whole partition of one child (broadcast: every partition sees the same relation through
  * GpuBroadcastExchangeExec); the streamed side is probed batch by batch.  Output is left ++ right whatever the build side
@@ -160,7 +169,8 @@ case class GpuHashJoinExec(
     left: SparkPlan,
     right: SparkPlan,
     isNullAwareAntiJoin: Boolean,
-    broadcast: Boolean) extends BinaryExecNode with GpuExec {
+    broadcast: Boolean,
+    runtimeFilters: Seq[GpuRuntimeFilter] = Nil) extends BinaryExecNode with GpuExec {
 
   override def output: Seq[Attribute] = joinType match {                                 // HashJoin.scala:55-70
     case _: InnerLike => left.output ++ right.output
@@ -200,8 +210,17 @@ case class GpuHashJoinExec(
       val b = GpuSupport.concatToDevice(buildBatches, buildTypes, stream, orEmpty = true)
       val relation = try Native.joinBuild(b.table, buildOrd, stream) finally b.close()   // the relation retains the build table
       val lowered = cond.map(_.lower())
+      // runtime filters: one single-key relation per filter, built from the creation side's broadcast (the executor's device copy)
+      val usable = if (lowered.isEmpty && (native == 0 || native == 2)   /* SB_JOIN_INNER, SB_JOIN_LEFT_SEMI */) runtimeFilters else Nil
+      val rfCols = usable.map(f => GpuSupport.ordinals(Seq(f.applicationKey), streamPlan.output)(0)).toArray
+      val rfRelations = usable.map { f =>
+        val types = f.creation.output.map(_.dataType).toArray
+        val c = GpuSupport.concatToDevice(GpuBroadcastExchangeExec.batchesOf(f.creation.executeBroadcast[Array[Long]]().value, types), types,
+          stream, orEmpty = true)
+        try Native.joinBuild(c.table, GpuSupport.ordinals(Seq(f.creationKey), f.creation.output), stream) finally c.close()
+      }.toArray
       Option(org.apache.spark.TaskContext.get()).foreach(_.addTaskCompletionListener[Unit] { _ =>
-        Native.hashTableRelease(relation); lowered.foreach(_.close()) })
+        Native.hashTableRelease(relation); rfRelations.foreach(Native.hashTableRelease); lowered.foreach(_.close()) })
       // build-side-preserving joins emit the unmatched build rows once: they need the whole streamed partition in one probe
       val whole = GpuSupport.preservesBuildSide(joinType, buildSide)
       val inputs = if (whole) Iterator.single(GpuSupport.concatToDevice(streamBatches, streamTypes, stream, orEmpty = true): ColumnarBatch)
@@ -211,6 +230,8 @@ case class GpuHashJoinExec(
         try {
           val t = lowered match {
             case Some(l) => Native.joinProbeCondition(relation, p.table, streamOrd, native, l.filterExpr, stream)
+            case None if rfRelations.nonEmpty =>
+              Native.joinProbeRuntimeFiltered(relation, p.table, streamOrd, native, 0L, null, null, rfCols, rfRelations, stream)
             case None => Native.joinProbe(relation, p.table, streamOrd, native, stream)
           }
           if (reorder == null) new DeviceBatch(t, outTypes): ColumnarBatch
