@@ -1102,7 +1102,7 @@ int sb_join_probe_ex(const sb_hash_table *ht, const sb_table *probe, const int32
     pred_in_pass = use_cand && !config().expr_interpret_only && match_simple_predicate(probe, *probe_filter, sp);
     if (!pred_in_pass) sp.nterms = 0;
   }
-  // runtime filters (InjectRuntimeFilter): inside the candidate pass when they can be, else folded into the byte mask
+  // runtime filters (InjectRuntimeFilter): on the candidate list after the pass when there is one, else folded into the byte mask
   std::vector<JoinKeys> rf_keys;
   std::vector<KeyFilter> rf_filters;
   if (opt && opt->n_runtime_filters > 0) {

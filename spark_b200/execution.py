@@ -605,7 +605,8 @@ class ReusedExchangeExec(SparkPlan):
 class RuntimeFilter:
     """What InjectRuntimeFilter (sql/catalyst/.../optimizer/InjectRuntimeFilter.scala:47-100) plans on the application side of a join:
     `applicationKey IN (creation side's creationKey)`, evaluated as a might-contain test.  Here the creation side becomes a single-key
-    HashedRelation and its prefilter (exact bitmap or Bloom) is tested on the streamed column inside the join's candidate pass."""
+    HashedRelation and its prefilter (exact bitmap or Bloom) is tested on the streamed column of the rows that survive the join's own
+    candidate pass (short inputs: of every row)."""
 
     def __init__(self, applicationKey: str, creationKey: str, creationPlan: SparkPlan):
         self.applicationKey, self.creationKey, self.creationPlan = applicationKey, creationKey, creationPlan
@@ -794,7 +795,7 @@ class B200ColumnarRule:
         """The physical-plan face of InjectRuntimeFilter (sql/catalyst/.../optimizer/InjectRuntimeFilter.scala:196-260, 411-460): for an
         inner join J2 whose streamed side is (Projects / Filters over) another inner or left-semi join J1, and whose build side has a
         selective predicate (a FilterExec somewhere below it), rows of J1's STREAMED input whose J2 key cannot be in J2's build side
-        never reach the output -- so J1 tests that key against the relation's prefilter inside its candidate pass.  J2's build subplan
+        never reach the output -- so J1 tests that key against the relation's prefilter right after its candidate pass.  J2's build subplan
         becomes a ReusedExchangeExec shared by J2 and the filter's creation side."""
         for attr in ("child", "left", "right"):
             if hasattr(plan, attr):
