@@ -189,3 +189,37 @@ def test_column_pruning_hints_reach_the_join():
         except StopIteration:
             pass
         assert seen["need"] == ({"x", "p", "d"} if isinstance(plan, ProjectExec) else {"k", "p", "d", "z"}), seen
+
+
+def test_reused_exchange_runs_its_child_once_per_round():
+    """ReusedExchangeExec: the child runs for the first consumer, the batch is shared with the others and released after the last --
+    and the next execution of the plan (the next step of the bench) starts a new round."""
+    from spark_b200.execution import ReusedExchangeExec, SparkPlan
+    log = []
+
+    class Batch:
+        names = ["a"]
+
+        def __init__(self, tag):
+            self.tag = tag
+
+        def rename(self, names):
+            log.append(("share", self.tag))
+            return Batch(self.tag)
+
+        def close(self):
+            log.append(("close", self.tag))
+
+    class Child(SparkPlan):
+        runs = 0
+
+        def executeColumnar(self, stream=None):
+            Child.runs += 1
+            return Batch(Child.runs)
+
+    ex = ReusedExchangeExec(Child(), uses=2)
+    a, b = ex.executeColumnar(), ex.executeColumnar()
+    assert Child.runs == 1 and (a.tag, b.tag) == (1, 1)
+    assert log == [("share", 1), ("share", 1), ("close", 1)]
+    c = ex.executeColumnar()
+    assert Child.runs == 2 and c.tag == 2
