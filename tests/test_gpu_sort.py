@@ -176,8 +176,8 @@ def test_range_partition_and_global_sort(gpu, stream, kind, asc, nulls_first):
 # gathered: every column of the result must still equal the oracle's.
 @pytest.mark.parametrize("kind", ["int64", "int64_small", "int32", "int8", "date32"])
 @pytest.mark.parametrize("asc", [True, False])
-def test_sorted_key_column_rebuilt_from_keys(gpu, stream, kind, asc):
-    n = 70001
+@pytest.mark.parametrize("n", [1, 2, 1000, 70001])       # one row, the single-block sort (<= 2048 rows), the onesweep passes
+def test_sorted_key_column_rebuilt_from_keys(gpu, stream, kind, asc, n):
     rng = np.random.default_rng(hash((kind, asc)) % 2 ** 32)
     t = pa.table({"p": rng.random(n), "k": _col(kind, n, rng, 0.0), "row": np.arange(n, dtype=np.int64)})
     assert_tables_equal(_sort(t, [("k", asc, True)], stream), O.sort(t, [("k", asc, True)]), ordered=True)
