@@ -789,7 +789,7 @@ class B200ColumnarRule:
         return plan
 
     # ---- runtime filters -------------------------------------------------------------------------------------------------------
-    maxRuntimeFilters = 2      # per join (csrc/join.cu MAX_RUNTIME_FILTERS); the reference caps the whole query at 10
+    maxRuntimeFilters = 2      # per join; the reference caps the whole query (spark.sql.optimizer.runtimeFilter.number.threshold = 10)
 
     def injectRuntimeFilters(self, plan: SparkPlan) -> SparkPlan:
         """The physical-plan face of InjectRuntimeFilter (sql/catalyst/.../optimizer/InjectRuntimeFilter.scala:196-260, 411-460): for an
