@@ -138,6 +138,14 @@ def host_threads(share=1):
     return n
 
 
+def rank_cpu_block(cpus, local_rank, world):
+    """The block of host CPUs rank `local_rank` of `world` ranks on one host keeps: contiguous, disjoint, equal-sized (the remainder
+    stays unused).  [] when there are fewer CPUs than ranks (the mask is then left alone)."""
+    cpus = sorted(cpus)
+    per = len(cpus) // world
+    return cpus[local_rank * per:(local_rank + 1) * per] if per >= 1 else []
+
+
 def _omp_setup(share=1):
     """torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every thread the cgroup grants, spread over the sockets."""
     nt = host_threads(share)
@@ -327,10 +335,9 @@ def main():
         # core for all ranks, and the host threads (which spin in cudaStreamSynchronize between operators) then time-slice it: measured
         # at N = 4 before this fix, Q1 took 18 ms per step with 4.3 ms of kernels (gpurun_out r26 -> profiles/r02_bench_n4_shared_mask.json).
         try:
-            cpus = sorted(os.sched_getaffinity(0))
-            per = len(cpus) // world
-            if per >= 1:
-                os.sched_setaffinity(0, cpus[local_rank * per:(local_rank + 1) * per])
+            mine = rank_cpu_block(os.sched_getaffinity(0), local_rank, world)
+            if mine:
+                os.sched_setaffinity(0, mine)
                 partitioned = True
         except (AttributeError, OSError):
             pass

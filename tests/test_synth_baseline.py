@@ -96,3 +96,18 @@ def test_q5_whole_stage_restatement_equals_operator_oracle():
     for got, i in zip(rows, range(want.num_rows)):
         assert got[0] == want.column("n_name")[i].as_py()
         assert got[1] == pytest.approx(want.column("revenue")[i].as_py(), rel=1e-9)
+
+
+def test_ranks_of_one_host_get_disjoint_cpu_blocks():
+    """bench.py --gpus N: every rank binds itself to its own block of the host CPUs before the OpenMP runtime loads (with a shared
+    mask OMP_PROC_BIND put all ranks' host threads on one core: 18 ms per Q1 step at N = 4 instead of 5)."""
+    from bench import rank_cpu_block
+    cpus = list(range(3, 131))                       # 128 CPUs, not starting at 0
+    for world in (2, 4, 8):
+        blocks = [rank_cpu_block(cpus, r, world) for r in range(world)]
+        assert all(len(b) == 128 // world for b in blocks)
+        flat = [c for b in blocks for c in b]
+        assert len(set(flat)) == len(flat) and set(flat) <= set(cpus)
+        assert all(b == sorted(b) and b[-1] - b[0] == len(b) - 1 for b in blocks)      # contiguous
+    assert rank_cpu_block([0, 1, 2], 1, 8) == []     # fewer CPUs than ranks: leave the mask alone
+    assert rank_cpu_block({5, 4, 7, 6}, 1, 2) == [6, 7]
