@@ -202,3 +202,16 @@ def test_onesweep_variants_exact_order(gpu, stream, variant):
             assert got.column("k").to_pylist() == want.column("k").to_pylist(), (variant, n, hi)
     finally:
         capi.config_set("sort_variant", prev)
+
+
+# sql-tests/results/order-by-nulls-ordering.sql.out (tests/sort_goldens.py): the reference's own answers, not the oracle's
+def test_order_by_nulls_ordering_goldens(gpu, stream):
+    import sort_goldens as G
+    t = G.t1()
+    for orders, want in G.T1_ORDER_BY:
+        got = _sort(t, orders, stream)
+        assert list(zip(*[got.column(c).to_pylist() for c in ("col1", "col2", "col3")])) == want, orders
+    t = G.t2()
+    for orders, want in G.T2_ORDER_BY:
+        got = _sort(t, orders, stream)
+        assert list(zip(*[got.column(c).to_pylist() for c in ("col1", "col3", "col5")])) == want, orders

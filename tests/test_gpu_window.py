@@ -95,3 +95,16 @@ def test_window_functions_against_the_oracle(gpu, stream, n, nparts):
         got3 = _window(t, ["p"], orders3, specs3, stream)
         want3 = O.window(t, ["p"], orders3, specs3)
         assert_tables_equal(got3, want3, key_cols=["p", orders3[0][0], "row"])
+
+
+# sql-tests/results/order-by-nulls-ordering.sql.out:22-96 (tests/sort_goldens.py): a sliding ROWS frame over every NULL placement,
+# then the outer ORDER BY sum_col2 whose ties keep the window's output order
+def test_window_under_every_null_ordering_golden(gpu, stream):
+    import sort_goldens as G
+    from spark_b200.columnar import ColumnarBatch
+    from spark_b200.execution import LocalTableScanExec, SortExec
+    t = G.t1()
+    for orders, want in G.T1_WINDOW:
+        w = _window(t, ["col1"], orders, [("sum", "col2", ("rows", -2, 2), 0, "sum_col2")], stream)
+        got = SortExec([("sum_col2", True, True)], LocalTableScanExec(ColumnarBatch.from_arrow(w, stream))).collect(stream)
+        assert list(zip(*[got.column(c).to_pylist() for c in ("col1", "col2", "col3", "sum_col2")])) == want, orders

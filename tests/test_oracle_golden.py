@@ -327,3 +327,26 @@ def test_aggregate_answers_of_the_reference_sql_goldens():
                     assert abs(x - y) <= 1e-15 * abs(y), (case[0], case[7], x, y)       # the golden prints 17 significant digits
                 else:
                     assert x == y, (case[0], case[7], g, w)
+
+
+# --- sql-tests/results/order-by-nulls-ordering.sql.out (SPARK-10747): ORDER BY with NULLS FIRST / LAST in every direction, ties in
+# --- arrival order, a string and a double key; and the same orders inside a window with a sliding ROWS frame -------------------------
+def test_order_by_nulls_ordering_goldens():
+    import sort_goldens as G
+    t = G.t1()
+    for orders, want in G.T1_ORDER_BY:
+        got = O.sort(t, orders)
+        assert list(zip(*[got.column(c).to_pylist() for c in ("col1", "col2", "col3")])) == want, orders
+    t = G.t2()
+    for orders, want in G.T2_ORDER_BY:
+        got = O.sort(t, orders)
+        assert list(zip(*[got.column(c).to_pylist() for c in ("col1", "col3", "col5")])) == want, orders
+
+
+def test_order_by_nulls_ordering_window_goldens():
+    import sort_goldens as G
+    t = G.t1()
+    for orders, want in G.T1_WINDOW:
+        w = O.window(t, ["col1"], orders, [("sum", "col2", ("rows", -2, 2), 0, "sum_col2")])
+        got = O.sort(w, [("sum_col2", True, True)])          # the outer ORDER BY sum_col2: ties keep the window's output order
+        assert list(zip(*[got.column(c).to_pylist() for c in ("col1", "col2", "col3", "sum_col2")])) == want, orders
