@@ -60,3 +60,26 @@ T2_ORDER_BY = [
     ([("col5", False, True), ("col3", False, False)],                   # order by col5 desc nulls first, col3 desc nulls last
      [("c", 2.0, N), ("a", 1.0, N), ("c", 2.0, 15.1), ("b", 1.0, 10.0), ("d", 0.0, 1.0), (N, 0.0, 1.0), ("d", N, 1.0), ("d", 2.0, 0.0)]),
 ]
+
+
+# sql-tests/results/order-by-all.sql.out: data(g, i) = (0, 1), (0, 2), (1, 3), (1, NULL); ORDER BY ALL = both columns with the same
+# direction / NULL placement (defaults: ASC NULLS FIRST, DESC NULLS LAST -- SortOrder.scala NullOrdering defaults)        -- inputs/order-by-all.sql:1-6
+T3_ROWS = [(0, 1), (0, 2), (1, 3), (1, N)]
+
+
+def t3():
+    g, i = zip(*T3_ROWS)
+    return pa.table({"g": pa.array(g, pa.int32()), "i": pa.array(i, pa.int32())})
+
+
+def _all(asc, nulls_first):
+    return [("g", asc, nulls_first), ("i", asc, nulls_first)]
+
+
+T3_ORDER_BY = [                                                                                    # order-by-all.sql.out:30-118
+    (_all(True, True), [(0, 1), (0, 2), (1, N), (1, 3)]),        # order by all / all asc / all nulls first / all asc nulls first
+    (_all(False, False), [(1, 3), (1, N), (0, 2), (0, 1)]),      # order by all desc / all desc nulls last
+    (_all(True, False), [(0, 1), (0, 2), (1, 3), (1, N)]),       # order by all nulls last / all asc nulls last
+    (_all(False, True), [(1, N), (1, 3), (0, 2), (0, 1)]),       # order by all desc nulls first
+]
+T3_LIMIT_2 = (_all(True, True), 2, [(0, 1), (0, 2)])             # order by all limit 2 (TakeOrderedAndProjectExec)      -- :163-168

@@ -215,3 +215,20 @@ def test_order_by_nulls_ordering_goldens(gpu, stream):
     for orders, want in G.T2_ORDER_BY:
         got = _sort(t, orders, stream)
         assert list(zip(*[got.column(c).to_pylist() for c in ("col1", "col3", "col5")])) == want, orders
+
+
+def test_order_by_all_goldens(gpu, stream):
+    """sql-tests/results/order-by-all.sql.out (tests/sort_goldens.py): every direction / NULL placement over two columns, and
+    ORDER BY ... LIMIT 2 through TakeOrderedAndProjectExec."""
+    import sort_goldens as G
+    from spark_b200.columnar import ColumnarBatch
+    from spark_b200.execution import LocalTableScanExec, TakeOrderedAndProjectExec
+    from spark_b200.expressions import SortOrder
+    t = G.t3()
+    for orders, want in G.T3_ORDER_BY:
+        got = _sort(t, orders, stream)
+        assert list(zip(got.column("g").to_pylist(), got.column("i").to_pylist())) == want, orders
+    orders, k, want = G.T3_LIMIT_2
+    top = TakeOrderedAndProjectExec(k, [SortOrder(c, asc, nf) for c, asc, nf in orders], ["g", "i"],
+                                    LocalTableScanExec(ColumnarBatch.from_arrow(t, stream))).collect(stream)
+    assert list(zip(top.column("g").to_pylist(), top.column("i").to_pylist())) == want

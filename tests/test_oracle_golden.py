@@ -350,3 +350,15 @@ def test_order_by_nulls_ordering_window_goldens():
         w = O.window(t, ["col1"], orders, [("sum", "col2", ("rows", -2, 2), 0, "sum_col2")])
         got = O.sort(w, [("sum_col2", True, True)])          # the outer ORDER BY sum_col2: ties keep the window's output order
         assert list(zip(*[got.column(c).to_pylist() for c in ("col1", "col2", "col3", "sum_col2")])) == want, orders
+
+
+def test_order_by_all_goldens():
+    """sql-tests/results/order-by-all.sql.out: two sort columns, every direction / NULL placement, and ORDER BY ... LIMIT 2."""
+    import sort_goldens as G
+    t = G.t3()
+    for orders, want in G.T3_ORDER_BY:
+        got = O.sort(t, orders)
+        assert list(zip(got.column("g").to_pylist(), got.column("i").to_pylist())) == want, orders
+    orders, k, want = G.T3_LIMIT_2
+    got = O.take_ordered(t, orders, k)
+    assert list(zip(got.column("g").to_pylist(), got.column("i").to_pylist())) == want
