@@ -43,3 +43,17 @@ def rows_of(table):
 
 def multiset(rows):
     return sorted(rows, key=lambda r: tuple((x is None, 0 if x is None else x) for x in r))
+
+
+# ---- NOT IN (null-aware anti join, BroadcastHashJoinExec.scala:137-162): the five uncorrelated cases of
+# ---- sql-tests/results/subquery/in-subquery/not-in-unit-tests-single-column.sql.out (views m(a, b), s(c, d): inputs/...single-column.sql:38-46)
+NOT_IN_M = [(None, 1.0), (2, 3.0), (4, 5.0)]
+NOT_IN_S = [(None, 1.0), (2, 3.0), (6, 7.0)]
+# (filter on m.b or None, filter on s.d as (op, literal), expected rows of m)
+NOT_IN_CASES = [
+    (None, (">", 10.0), [(2, 3.0), (4, 5.0), (None, 1.0)]),   # case 1: empty subquery -> every row, NULL probe key included
+    (None, ("=", 1.0), []),                                     # case 2: the subquery holds a NULL -> no row
+    (1.0, ("=", 3.0), []),                                      # case 3: the probe key is NULL -> not returned
+    (3.0, ("=", 3.0), []),                                      # case 4: the probe key is in the subquery -> not returned
+    (3.0, ("=", 7.0), [(2, 3.0)]),                              # case 5: the probe key is not in the subquery -> returned
+]

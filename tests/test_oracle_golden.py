@@ -362,3 +362,18 @@ def test_order_by_all_goldens():
     orders, k, want = G.T3_LIMIT_2
     got = O.take_ordered(t, orders, k)
     assert list(zip(got.column("g").to_pylist(), got.column("i").to_pylist())) == want
+
+
+def test_not_in_null_aware_anti_join_goldens():
+    """not-in-unit-tests-single-column.sql.out, uncorrelated cases 1-5: `a NOT IN (SELECT c FROM s WHERE ...)` is the null-aware anti
+    join of BroadcastHashJoinExec.scala:137-162 (empty relation -> every row; a NULL in the relation -> none; NULL probe keys dropped)."""
+    import join_fixtures as F
+    m = pa.table({"a": pa.array([r[0] for r in F.NOT_IN_M], pa.int32()), "b": pa.array([r[1] for r in F.NOT_IN_M], pa.float64())})
+    s = pa.table({"c": pa.array([r[0] for r in F.NOT_IN_S], pa.int32()), "d": pa.array([r[1] for r in F.NOT_IN_S], pa.float64())})
+    for mb, (op, lit), want in F.NOT_IN_CASES:
+        d = np.asarray(s.column("d"))
+        sub = s.filter(pa.array(d > lit if op == ">" else d == lit))
+        left = m if mb is None else m.filter(pa.array(np.asarray(m.column("b")) == mb))
+        got = O.hash_join(left, sub, ["a"], ["c"], "left_anti_null_aware")
+        rows = sorted(zip(got.column("a").to_pylist(), got.column("b").to_pylist()), key=lambda r: (r[0] is None, r[0] or 0))
+        assert rows == sorted(want, key=lambda r: (r[0] is None, r[0] or 0)), (mb, op, lit)
